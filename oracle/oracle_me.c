@@ -1,0 +1,453 @@
+/* oracle/oracle_me.c -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ * Restates the callers whose decisions the batched device kernels must reproduce:
+ *   BitCost tables            encoder/bitcost.cpp:33-110
+ *   MotionEstimate::motionEstimate  encoder/motion.cpp:739-1569 (DIA, HEX, STAR; luma only)
+ *   StarPatternSearch         encoder/motion.cpp:362-604
+ *   subpelCompare             encoder/motion.cpp:1571-1664 (luma part)
+ *   lowresQPelCost            common/lowres.h:94-120
+ * Pinned against the real MotionEstimate through oracle/_ref (x265ref_motion_estimate).
+ */
+#include "oracle.h"
+#include <math.h>
+#include <string.h>
+
+/* bitcost.cpp:95-109 + :49-55: s_bitsizes is float, lambda double, result capped at 2^15-1 */
+void orc_mvcost_table(double lambda, int range, uint16_t* out)
+{
+    float log2_2 = 2.0f / logf(2.0f);
+    for (int i = 0; i <= range; i++)
+    {
+        float bits = i ? logf((float)(i + 1)) * log2_2 + 1.718f : 0.718f;
+        double v = bits * lambda + 0.5f;
+        if (v > 32767.0) v = 32767.0;
+        uint16_t c = (uint16_t)v;
+        out[range + i] = out[range - i] = c;
+    }
+}
+
+typedef struct { int x, y; } mv_t;
+typedef int (*cmp_fn)(const pixel*, intptr_t, const pixel*, intptr_t, int, int);
+
+typedef struct {
+    const orc_me_job* j;
+    pixel fenc[64 * 64];        /* FENC_STRIDE cache (motion.cpp:189) */
+    const pixel* fref;          /* ref plane + blockOffset */
+    intptr_t stride;
+    mv_t mvp;                   /* qpel */
+    mv_t mvmin, mvmax;
+} me_ctx;
+
+static inline int mvcost(const me_ctx* c, int qx, int qy)
+{
+    return (uint16_t)(c->j->mvcost[qx - c->mvp.x] + c->j->mvcost[qy - c->mvp.y]);
+}
+static inline int in_range(const me_ctx* c, int x, int y)
+{ return x >= c->mvmin.x && x <= c->mvmax.x && y >= c->mvmin.y && y <= c->mvmax.y; }
+static inline int fpel_sad(const me_ctx* c, int x, int y)
+{ return orc_sad(c->fenc, 64, c->fref + x + (intptr_t)y * c->stride, c->stride, c->j->pw, c->j->ph); }
+static inline int cost_fpel(const me_ctx* c, int x, int y)
+{ return fpel_sad(c, x, y) + mvcost(c, x * 4, y * 4); }
+
+/* lowres.h:94-120 */
+static int lowres_qpel_cost(const me_ctx* c, int qx, int qy, cmp_fn cmp)
+{
+    const orc_me_job* j = c->j;
+    intptr_t st = j->refStride;
+    if ((qx | qy) & 1)
+    {
+        pixel buf[8 * 8];
+        int ha = (qy & 2) | ((qx & 2) >> 1);
+        const pixel* a = j->ref[ha] + j->offset + (qx >> 2) + (intptr_t)(qy >> 2) * st;
+        int rx = qx + (qx & 1), ry = qy + (qy & 1);
+        int hb = (ry & 2) | ((rx & 2) >> 1);
+        const pixel* b = j->ref[hb] + j->offset + (rx >> 2) + (intptr_t)(ry >> 2) * st;
+        orc_pixelavg_pp(buf, 8, a, st, b, st, 8, 8);
+        return cmp(c->fenc, 64, buf, 8, j->pw, j->ph);
+    }
+    int hp = (qy & 2) | ((qx & 2) >> 1);
+    const pixel* r = j->ref[hp] + j->offset + (qx >> 2) + (intptr_t)(qy >> 2) * st;
+    return cmp(c->fenc, 64, r, st, j->pw, j->ph);
+}
+
+/* motion.cpp:1571-1598 */
+static int subpel_compare(const me_ctx* c, int qx, int qy, cmp_fn cmp)
+{
+    const orc_me_job* j = c->j;
+    const pixel* r = c->fref + (qx >> 2) + (intptr_t)(qy >> 2) * c->stride;
+    int xf = qx & 3, yf = qy & 3;
+    if (!(xf | yf))
+        return cmp(c->fenc, 64, r, c->stride, j->pw, j->ph);
+    pixel buf[64 * 64];
+    if (!yf)      orc_interp_hpp(r, c->stride, buf, j->pw, xf, 8, j->pw, j->ph);
+    else if (!xf) orc_interp_vpp(r, c->stride, buf, j->pw, yf, 8, j->pw, j->ph);
+    else          orc_interp_hvpp(r, c->stride, buf, j->pw, xf, yf, 8, j->pw, j->ph);
+    return cmp(c->fenc, 64, buf, j->pw, j->pw, j->ph);
+}
+
+static int qpel_cost(const me_ctx* c, int qx, int qy, cmp_fn cmp)
+{ return c->j->lowres ? lowres_qpel_cost(c, qx, qy, cmp) : subpel_compare(c, qx, qy, cmp); }
+
+typedef struct { mv_t bmv; int bcost, point, dist; } star_t;
+
+static inline void star_try(const me_ctx* c, star_t* s, int x, int y, int point, int dist)
+{
+    int cost = cost_fpel(c, x, y);
+    if (cost < s->bcost) { s->bcost = cost; s->bmv.x = x; s->bmv.y = y; s->point = point; s->dist = dist; }
+}
+
+/* motion.cpp:362-604.  The reference's x4 fast path evaluates the same points in the same order
+ * as the bounds-checked path, so a single checked walk reproduces both. */
+static void star_pattern(const me_ctx* c, star_t* s, int earlyExitIters, int merange)
+{
+    const mv_t o = s->bmv;
+    int saved = s->bcost, rounds = 0;
+    {
+        const int d = 1;
+        int top = o.y - d, bot = o.y + d, lft = o.x - d, rgt = o.x + d;
+        if (top >= c->mvmin.y) star_try(c, s, o.x, top, 2, d);
+        if (lft >= c->mvmin.x) star_try(c, s, lft, o.y, 4, d);
+        if (rgt <= c->mvmax.x) star_try(c, s, rgt, o.y, 5, d);
+        if (bot <= c->mvmax.y) star_try(c, s, o.x, bot, 7, d);
+        if (s->bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+    for (int d = 2; d <= 8; d <<= 1)
+    {
+        int top = o.y - d, bot = o.y + d, lft = o.x - d, rgt = o.x + d;
+        int top2 = o.y - (d >> 1), bot2 = o.y + (d >> 1), lft2 = o.x - (d >> 1), rgt2 = o.x + (d >> 1);
+        saved = s->bcost;
+        if (top >= c->mvmin.y && lft >= c->mvmin.x && rgt <= c->mvmax.x && bot <= c->mvmax.y)
+        {
+            /* order of the two x4 bursts (motion.cpp:456-463) */
+            star_try(c, s, o.x, top, 2, d);   star_try(c, s, lft2, top2, 1, d >> 1);
+            star_try(c, s, rgt2, top2, 3, d >> 1); star_try(c, s, lft, o.y, 4, d);
+            star_try(c, s, rgt, o.y, 5, d);   star_try(c, s, lft2, bot2, 6, d >> 1);
+            star_try(c, s, rgt2, bot2, 8, d >> 1); star_try(c, s, o.x, bot, 7, d);
+        }
+        else
+        {
+            if (top >= c->mvmin.y) star_try(c, s, o.x, top, 2, d);
+            if (top2 >= c->mvmin.y)
+            {
+                if (lft2 >= c->mvmin.x) star_try(c, s, lft2, top2, 1, d >> 1);
+                if (rgt2 <= c->mvmax.x) star_try(c, s, rgt2, top2, 3, d >> 1);
+            }
+            if (lft >= c->mvmin.x) star_try(c, s, lft, o.y, 4, d);
+            if (rgt <= c->mvmax.x) star_try(c, s, rgt, o.y, 5, d);
+            if (bot2 <= c->mvmax.y)
+            {
+                if (lft2 >= c->mvmin.x) star_try(c, s, lft2, bot2, 6, d >> 1);
+                if (rgt2 <= c->mvmax.x) star_try(c, s, rgt2, bot2, 8, d >> 1);
+            }
+            if (bot <= c->mvmax.y) star_try(c, s, o.x, bot, 7, d);
+        }
+        if (s->bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+    for (int d = 16; d <= merange; d <<= 1)
+    {
+        int top = o.y - d, bot = o.y + d, lft = o.x - d, rgt = o.x + d;
+        saved = s->bcost;
+        int inside = top >= c->mvmin.y && lft >= c->mvmin.x && rgt <= c->mvmax.x && bot <= c->mvmax.y;
+        if (inside || top >= c->mvmin.y) star_try(c, s, o.x, top, 0, d);
+        if (inside || lft >= c->mvmin.x) star_try(c, s, lft, o.y, 0, d);
+        if (inside || rgt <= c->mvmax.x) star_try(c, s, rgt, o.y, 0, d);
+        if (inside || bot <= c->mvmax.y) star_try(c, s, o.x, bot, 0, d);
+        for (int k = 1; k < 4; k++)
+        {
+            int yt = top + (d >> 2) * k, yb = bot - (d >> 2) * k;
+            int xl = o.x - (d >> 2) * k, xr = o.x + (d >> 2) * k;
+            if (inside || yt >= c->mvmin.y)
+            {
+                if (inside || xl >= c->mvmin.x) star_try(c, s, xl, yt, 0, d);
+                if (inside || xr <= c->mvmax.x) star_try(c, s, xr, yt, 0, d);
+            }
+            if (inside || yb <= c->mvmax.y)
+            {
+                if (inside || xl >= c->mvmin.x) star_try(c, s, xl, yb, 0, d);
+                if (inside || xr <= c->mvmax.x) star_try(c, s, xr, yb, 0, d);
+            }
+        }
+        if (s->bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+}
+
+static const mv_t k_hex2[8] = { {-1,-2}, {-2,0}, {-1,2}, {1,2}, {2,0}, {1,-2}, {-1,-2}, {-2,0} };
+static const uint8_t k_mod6m1[8] = { 5, 0, 1, 2, 3, 4, 5, 0 };
+static const mv_t k_square1[9] = { {0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {-1,-1}, {-1,1}, {1,-1}, {1,1} };
+static const mv_t k_offsets[16] = { {-1,0},{0,-1}, {-1,-1},{1,-1}, {-1,0},{1,0}, {-1,1},{-1,-1},
+                                    {1,-1},{1,1}, {-1,0},{0,1}, {-1,1},{1,1}, {1,0},{0,1} };
+static const struct { int hpel_iters, hpel_dirs, qpel_iters, qpel_dirs, hpel_satd; } k_workload[8] = {
+    {1,4,0,4,0}, {1,4,1,4,0}, {1,4,1,4,1}, {2,4,1,4,1}, {2,4,2,4,1}, {1,8,1,8,1}, {2,8,1,8,1}, {2,8,2,8,1} };
+
+static inline int yok(const me_ctx* c, int y) { return (y >= c->mvmin.y) & (y <= c->mvmax.y); }
+
+int orc_motion_estimate(const orc_me_job* j, int* outQMv)
+{
+    me_ctx ctx; me_ctx* c = &ctx;
+    c->j = j;
+    orc_copy_pp(c->fenc, 64, j->fenc + j->offset, j->fencStride, j->pw, j->ph);
+    c->fref = j->ref[0] + j->offset;
+    c->stride = j->refStride;
+    c->mvp.x = j->qmvp[0]; c->mvp.y = j->qmvp[1];
+    c->mvmin.x = j->mvmin[0]; c->mvmin.y = j->mvmin[1];
+    c->mvmax.x = j->mvmax[0]; c->mvmax.y = j->mvmax[1];
+    const int qminx = c->mvmin.x * 4, qminy = c->mvmin.y * 4, qmaxx = c->mvmax.x * 4, qmaxy = c->mvmax.y * 4;
+    const int merange = j->merange;
+#define CLIPQ(vx, vy) do { if (vx > qmaxx) vx = qmaxx; if (vy > qmaxy) vy = qmaxy; if (vx < qminx) vx = qminx; if (vy < qminy) vy = qminy; } while (0)
+
+    /* motion.cpp:771-792: cost at the clipped qpel MVP, then at its full-pel rounding */
+    int pmvx = c->mvp.x, pmvy = c->mvp.y;
+    CLIPQ(pmvx, pmvy);
+    int bestprex = pmvx, bestprey = pmvy;
+    int bprecost = qpel_cost(c, pmvx, pmvy, orc_sad);      /* NB: no mvcost added (motion.cpp:776-779) */
+    mv_t bmv = { (pmvx + 2) >> 2, (pmvy + 2) >> 2 };
+    int bcost = bprecost;
+    if ((pmvx & 3) | (pmvy & 3))
+        bcost = cost_fpel(c, bmv.x, bmv.y);
+    /* :787-797 MV(0) */
+    if (pmvx | pmvy)
+    {
+        int cost = fpel_sad(c, 0, 0) + mvcost(c, 0, 0);
+        if (cost < bcost)
+        {
+            bcost = cost;
+            bmv.x = 0;
+            int zy = 0 < c->mvmax.y ? 0 : c->mvmax.y;
+            bmv.y = zy > c->mvmin.y ? zy : c->mvmin.y;
+        }
+    }
+    /* :801-814 qpel candidates */
+    for (int i = 0; i < j->numCand; i++)
+    {
+        int mx = j->mvc[2 * i], my = j->mvc[2 * i + 1];
+        CLIPQ(mx, my);
+        if ((mx | my) && !(mx == pmvx && my == pmvy) && !(mx == bestprex && my == bestprey))
+        {
+            int cost = subpel_compare(c, mx, my, orc_sad) + mvcost(c, mx, my);
+            if (cost < bprecost) { bprecost = cost; bestprex = mx; bestprey = my; }
+        }
+    }
+    /* pmv.roundToFPel() / omv are only used by UMH/SEA (not restated) */
+
+    switch (j->method)
+    {
+    case 0: /* X265_DIA_SEARCH motion.cpp:822-846 */
+    {
+        bcost <<= 4;
+        int i = merange;
+        do
+        {
+            int c0 = cost_fpel(c, bmv.x, bmv.y - 1), c1 = cost_fpel(c, bmv.x, bmv.y + 1);
+            int c2 = cost_fpel(c, bmv.x - 1, bmv.y), c3 = cost_fpel(c, bmv.x + 1, bmv.y);
+            if (yok(c, bmv.y - 1) && (c0 << 4) + 1 < bcost) bcost = (c0 << 4) + 1;
+            if (yok(c, bmv.y + 1) && (c1 << 4) + 3 < bcost) bcost = (c1 << 4) + 3;
+            if ((c2 << 4) + 4 < bcost) bcost = (c2 << 4) + 4;
+            if ((c3 << 4) + 12 < bcost) bcost = (c3 << 4) + 12;
+            if (!(bcost & 15)) break;
+            bmv.x -= (int)((unsigned)bcost << 28) >> 30;
+            bmv.y -= (int)((unsigned)bcost << 30) >> 30;
+            bcost &= ~15;
+        }
+        while (--i && in_range(c, bmv.x, bmv.y));
+        bcost >>= 4;
+        break;
+    }
+    case 1: /* X265_HEX_SEARCH motion.cpp:848-945 */
+    {
+        int c0 = cost_fpel(c, bmv.x - 2, bmv.y), c1 = cost_fpel(c, bmv.x - 1, bmv.y + 2), c2 = cost_fpel(c, bmv.x + 1, bmv.y + 2);
+        bcost <<= 3;
+        if (yok(c, bmv.y) && (c0 << 3) + 2 < bcost) bcost = (c0 << 3) + 2;
+        if (yok(c, bmv.y + 2))
+        {
+            if ((c1 << 3) + 3 < bcost) bcost = (c1 << 3) + 3;
+            if ((c2 << 3) + 4 < bcost) bcost = (c2 << 3) + 4;
+        }
+        c0 = cost_fpel(c, bmv.x + 2, bmv.y); c1 = cost_fpel(c, bmv.x + 1, bmv.y - 2); c2 = cost_fpel(c, bmv.x - 1, bmv.y - 2);
+        if (yok(c, bmv.y) && (c0 << 3) + 5 < bcost) bcost = (c0 << 3) + 5;
+        if (yok(c, bmv.y - 2))
+        {
+            if ((c1 << 3) + 6 < bcost) bcost = (c1 << 3) + 6;
+            if ((c2 << 3) + 7 < bcost) bcost = (c2 << 3) + 7;
+        }
+        if (bcost & 7)
+        {
+            int dir = (bcost & 7) - 2;
+            if (yok(c, bmv.y + k_hex2[dir + 1].y))
+            {
+                bmv.x += k_hex2[dir + 1].x; bmv.y += k_hex2[dir + 1].y;
+                for (int i = (merange >> 1) - 1; i > 0 && in_range(c, bmv.x, bmv.y); i--)
+                {
+                    c0 = cost_fpel(c, bmv.x + k_hex2[dir + 0].x, bmv.y + k_hex2[dir + 0].y);
+                    c1 = cost_fpel(c, bmv.x + k_hex2[dir + 1].x, bmv.y + k_hex2[dir + 1].y);
+                    c2 = cost_fpel(c, bmv.x + k_hex2[dir + 2].x, bmv.y + k_hex2[dir + 2].y);
+                    bcost &= ~7;
+                    if (yok(c, bmv.y + k_hex2[dir + 0].y) && (c0 << 3) + 1 < bcost) bcost = (c0 << 3) + 1;
+                    if (yok(c, bmv.y + k_hex2[dir + 1].y) && (c1 << 3) + 2 < bcost) bcost = (c1 << 3) + 2;
+                    if (yok(c, bmv.y + k_hex2[dir + 2].y) && (c2 << 3) + 3 < bcost) bcost = (c2 << 3) + 3;
+                    if (!(bcost & 7)) break;
+                    dir += (bcost & 7) - 2;
+                    dir = k_mod6m1[dir + 1];
+                    bmv.x += k_hex2[dir + 1].x; bmv.y += k_hex2[dir + 1].y;
+                }
+            }
+        }
+        bcost >>= 3;
+        /* square refine :921-941 */
+        int dir = 0;
+        int s0 = cost_fpel(c, bmv.x, bmv.y - 1), s1 = cost_fpel(c, bmv.x, bmv.y + 1);
+        int s2 = cost_fpel(c, bmv.x - 1, bmv.y), s3 = cost_fpel(c, bmv.x + 1, bmv.y);
+        if (yok(c, bmv.y - 1) && s0 < bcost) { bcost = s0; dir = 1; }
+        if (yok(c, bmv.y + 1) && s1 < bcost) { bcost = s1; dir = 2; }
+        if (s2 < bcost) { bcost = s2; dir = 3; }
+        if (s3 < bcost) { bcost = s3; dir = 4; }
+        s0 = cost_fpel(c, bmv.x - 1, bmv.y - 1); s1 = cost_fpel(c, bmv.x - 1, bmv.y + 1);
+        s2 = cost_fpel(c, bmv.x + 1, bmv.y - 1); s3 = cost_fpel(c, bmv.x + 1, bmv.y + 1);
+        if (yok(c, bmv.y - 1) && s0 < bcost) { bcost = s0; dir = 5; }
+        if (yok(c, bmv.y + 1) && s1 < bcost) { bcost = s1; dir = 6; }
+        if (yok(c, bmv.y - 1) && s2 < bcost) { bcost = s2; dir = 7; }
+        if (yok(c, bmv.y + 1) && s3 < bcost) { bcost = s3; dir = 8; }
+        bmv.x += k_square1[dir].x; bmv.y += k_square1[dir].y;
+        break;
+    }
+    case 3: /* X265_STAR_SEARCH motion.cpp:1132-1240 */
+    {
+        star_t s; s.bmv = bmv; s.bcost = bcost; s.point = 0; s.dist = 0;
+        star_pattern(c, &s, 3, merange);
+        int done = 0;
+        if (s.dist == 1)
+        {
+            if (s.point)
+            {
+                int saved = s.bcost;
+                mv_t m1 = { s.bmv.x + k_offsets[(s.point - 1) * 2].x, s.bmv.y + k_offsets[(s.point - 1) * 2].y };
+                mv_t m2 = { s.bmv.x + k_offsets[(s.point - 1) * 2 + 1].x, s.bmv.y + k_offsets[(s.point - 1) * 2 + 1].y };
+                if (in_range(c, m1.x, m1.y)) { int cost = cost_fpel(c, m1.x, m1.y); if (cost < s.bcost) { s.bcost = cost; s.bmv = m1; } }
+                if (in_range(c, m2.x, m2.y)) { int cost = cost_fpel(c, m2.x, m2.y); if (cost < s.bcost) { s.bcost = cost; s.bmv = m2; } }
+                if (s.bcost == saved) done = 1;
+            }
+            else
+                done = 1;
+        }
+        if (!done)
+        {
+            const int RD = 5;
+            if (s.dist > RD)
+            {
+                /* raster refinement :1171-1201; NB the 4th point's mvcost uses (tmv << 3) as written */
+                for (int ty = c->mvmin.y; ty <= c->mvmax.y; ty += RD)
+                    for (int tx = c->mvmin.x; tx <= c->mvmax.x; tx += RD)
+                    {
+                        if (tx + RD * 3 <= c->mvmax.x)
+                        {
+                            for (int k = 0; k < 4; k++)
+                            {
+                                int sad = fpel_sad(c, tx, ty);
+                                int cost = sad + (k < 3 ? mvcost(c, tx * 4, ty * 4) : mvcost(c, tx * 8, ty * 8));
+                                if (cost < s.bcost) { s.bcost = cost; s.bmv.x = tx; s.bmv.y = ty; }
+                                if (k < 3) tx += RD;
+                            }
+                        }
+                        else
+                        {
+                            int cost = cost_fpel(c, tx, ty);
+                            if (cost < s.bcost) { s.bcost = cost; s.bmv.x = tx; s.bmv.y = ty; }
+                        }
+                    }
+            }
+            while (s.dist > 0)
+            {
+                s.dist = 0; s.point = 0;
+                star_pattern(c, &s, 32, merange);
+                if (s.dist == 1)
+                {
+                    if (!s.point) break;
+                    mv_t m1 = { s.bmv.x + k_offsets[(s.point - 1) * 2].x, s.bmv.y + k_offsets[(s.point - 1) * 2].y };
+                    mv_t m2 = { s.bmv.x + k_offsets[(s.point - 1) * 2 + 1].x, s.bmv.y + k_offsets[(s.point - 1) * 2 + 1].y };
+                    if (in_range(c, m1.x, m1.y)) { int cost = cost_fpel(c, m1.x, m1.y); if (cost < s.bcost) { s.bcost = cost; s.bmv = m1; } }
+                    if (in_range(c, m2.x, m2.y)) { int cost = cost_fpel(c, m2.x, m2.y); if (cost < s.bcost) { s.bcost = cost; s.bmv = m2; } }
+                    break;
+                }
+            }
+        }
+        bmv = s.bmv; bcost = s.bcost;
+        break;
+    }
+    default:
+        return -1;
+    }
+
+    /* motion.cpp:1440-1447 */
+    int bx, by;
+    if (bprecost < bcost) { bx = bestprex; by = bestprey; bcost = bprecost; }
+    else { bx = bmv.x * 4; by = bmv.y * 4; }
+
+    const int sub = j->subme;
+    if (!bcost)
+        bcost = mvcost(c, bx, by);
+    else if (j->lowres)
+    {
+        /* :1462-1493 */
+        int bdir = 0;
+        for (int i = 1; i <= k_workload[sub].hpel_dirs; i++)
+        {
+            int qx = bx + k_square1[i].x * 2, qy = by + k_square1[i].y * 2;
+            if ((qy < qminy) | (qy > qmaxy)) continue;
+            int cost = lowres_qpel_cost(c, qx, qy, orc_sad) + mvcost(c, qx, qy);
+            if (cost < bcost) { bcost = cost; bdir = i; }
+        }
+        bx += k_square1[bdir].x * 2; by += k_square1[bdir].y * 2;
+        bcost = lowres_qpel_cost(c, bx, by, orc_satd) + mvcost(c, bx, by);
+        bdir = 0;
+        for (int i = 1; i <= k_workload[sub].qpel_dirs; i++)
+        {
+            int qx = bx + k_square1[i].x, qy = by + k_square1[i].y;
+            if ((qy < qminy) | (qy > qmaxy)) continue;
+            int cost = lowres_qpel_cost(c, qx, qy, orc_satd) + mvcost(c, qx, qy);
+            if (cost < bcost) { bcost = cost; bdir = i; }
+        }
+        bx += k_square1[bdir].x; by += k_square1[bdir].y;
+    }
+    else
+    {
+        /* :1495-1558 */
+        cmp_fn hcmp = orc_sad;
+        if (k_workload[sub].hpel_satd)
+        {
+            bcost = subpel_compare(c, bx, by, orc_satd) + mvcost(c, bx, by);
+            hcmp = orc_satd;
+        }
+        for (int it = 0; it < k_workload[sub].hpel_iters; it++)
+        {
+            int bdir = 0;
+            for (int i = 1; i <= k_workload[sub].hpel_dirs; i++)
+            {
+                int qx = bx + k_square1[i].x * 2, qy = by + k_square1[i].y * 2;
+                if ((qy < qminy) | (qy > qmaxy)) continue;
+                int cost = subpel_compare(c, qx, qy, hcmp) + mvcost(c, qx, qy);
+                if (cost < bcost) { bcost = cost; bdir = i; }
+            }
+            if (bdir) { bx += k_square1[bdir].x * 2; by += k_square1[bdir].y * 2; }
+            else break;
+        }
+        if (!k_workload[sub].hpel_satd)
+            bcost = subpel_compare(c, bx, by, orc_satd) + mvcost(c, bx, by);
+        for (int it = 0; it < k_workload[sub].qpel_iters; it++)
+        {
+            int bdir = 0;
+            for (int i = 1; i <= k_workload[sub].qpel_dirs; i++)
+            {
+                int qx = bx + k_square1[i].x, qy = by + k_square1[i].y;
+                if ((qy < qminy) | (qy > qmaxy)) continue;
+                int cost = subpel_compare(c, qx, qy, orc_satd) + mvcost(c, qx, qy);
+                if (cost < bcost) { bcost = cost; bdir = i; }
+            }
+            if (bdir) { bx += k_square1[bdir].x; by += k_square1[bdir].y; }
+            else break;
+        }
+    }
+    outQMv[0] = bx; outQMv[1] = by;
+    return bcost;
+#undef CLIPQ
+}

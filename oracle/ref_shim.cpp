@@ -1,0 +1,158 @@
+/* oracle/ref_shim.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Compiled by oracle/Makefile.ref TOGETHER WITH the unmodified reference sources under
+ * /root/reference/source into oracle/_ref/libx265ref{8,10}.so.  It exposes, through a flat
+ * extern "C" surface that Python/ctypes and the C tests can bind:
+ *   - the reference's post-alias C primitive table (primitives.cpp:63-73 setupCPrimitives +
+ *     :88-209 setupAliasPrimitives) as raw function pointers looked up by name,
+ *   - the reference's MotionEstimate::motionEstimate (encoder/motion.cpp:739) on caller planes,
+ *   - BitCost tables (encoder/bitcost.cpp:33-88), lambda tables (common/constants.cpp),
+ *   - the lookahead helpers used to pin the frame-level restatements.
+ * It contains no algorithm of its own: every call forwards to reference code.
+ */
+#include "common.h"
+#include "primitives.h"
+#include "constants.h"
+#include "lowres.h"
+#include "motion.h"
+#include "bitcost.h"
+#include "mv.h"
+#include <string.h>
+#include <stdio.h>
+
+using namespace X265_NS;
+
+namespace X265_NS {
+void setupCPrimitives(EncoderPrimitives &p);
+void setupAliasPrimitives(EncoderPrimitives &p);
+}
+
+static EncoderPrimitives g_c;
+static bool g_init = false;
+
+static void ensure_init()
+{
+    if (g_init) return;
+    memset(&g_c, 0, sizeof(g_c));
+    setupCPrimitives(g_c);
+    setupAliasPrimitives(g_c);
+    /* the global table is what lowresQPelCost / subpelCompare / MotionEstimate use */
+    memcpy(&primitives, &g_c, sizeof(g_c));
+    g_init = true;
+}
+
+#define PU_FIELD(f)   if (!strcmp(name, "pu." #f))  return (void*)g_c.pu[i].f;
+#define PU_FIELD2(f)  if (!strcmp(name, "pu." #f))  return (void*)g_c.pu[i].f[j];
+#define CU_FIELD(f)   if (!strcmp(name, "cu." #f))  return (void*)g_c.cu[i].f;
+#define CU_FIELD2(f)  if (!strcmp(name, "cu." #f))  return (void*)g_c.cu[i].f[j];
+#define TOP_FIELD(f)  if (!strcmp(name, #f))        return (void*)g_c.f;
+#define CPU_FIELD(f)  if (!strcmp(name, "chroma.pu." #f)) return (void*)g_c.chroma[k].pu[i].f;
+#define CPU_FIELD2(f) if (!strcmp(name, "chroma.pu." #f)) return (void*)g_c.chroma[k].pu[i].f[j];
+#define CCU_FIELD(f)  if (!strcmp(name, "chroma.cu." #f)) return (void*)g_c.chroma[k].cu[i].f;
+#define CCU_FIELD2(f) if (!strcmp(name, "chroma.cu." #f)) return (void*)g_c.chroma[k].cu[i].f[j];
+
+extern "C" {
+
+int x265ref_depth(void) { return X265_DEPTH; }
+
+/* name: "pu.sad", "cu.dct", "quant", "chroma.pu.filter_hpp" ...; i = LumaPU / LumaCU index,
+ * j = second index (alignment / intra mode), k = csp for chroma entries. */
+void* x265ref_get(const char* name, int i, int j, int k)
+{
+    ensure_init();
+    PU_FIELD(sad) PU_FIELD(sad_x3) PU_FIELD(sad_x4) PU_FIELD(ads) PU_FIELD(satd)
+    PU_FIELD(luma_hpp) PU_FIELD(luma_hps) PU_FIELD(luma_vpp) PU_FIELD(luma_vps)
+    PU_FIELD(luma_vsp) PU_FIELD(luma_vss) PU_FIELD(luma_hvpp)
+    PU_FIELD2(pixelavg_pp) PU_FIELD2(addAvg) PU_FIELD(copy_pp) PU_FIELD2(convert_p2s)
+
+    CU_FIELD(dct) CU_FIELD(idct) CU_FIELD2(calcresidual) CU_FIELD(sub_ps) CU_FIELD2(add_ps)
+    CU_FIELD2(blockfill_s) CU_FIELD(copy_cnt) CU_FIELD(count_nonzero)
+    CU_FIELD(cpy2Dto1D_shl) CU_FIELD(cpy2Dto1D_shr) CU_FIELD2(cpy1Dto2D_shl) CU_FIELD(cpy1Dto2D_shr)
+    CU_FIELD(copy_sp) CU_FIELD(copy_ps) CU_FIELD(copy_ss) CU_FIELD(copy_pp)
+    CU_FIELD(var) CU_FIELD(sse_pp) CU_FIELD(sse_ss) CU_FIELD(psy_cost_pp) CU_FIELD2(ssd_s)
+    CU_FIELD(sa8d) CU_FIELD(transpose) CU_FIELD(intra_pred_allangs) CU_FIELD(intra_filter)
+    CU_FIELD2(intra_pred)
+
+    TOP_FIELD(dst4x4) TOP_FIELD(idst4x4) TOP_FIELD(quant) TOP_FIELD(nquant)
+    TOP_FIELD(dequant_scaling) TOP_FIELD(dequant_normal) TOP_FIELD(denoiseDct)
+    TOP_FIELD(scale2D_64to32) TOP_FIELD(frameInitLowres) TOP_FIELD(frameInitLowerRes)
+    TOP_FIELD(extendRowBorder) TOP_FIELD(weight_pp) TOP_FIELD(weight_sp) TOP_FIELD(propagateCost)
+    if (!strcmp(name, "scale1D_128to64")) return (void*)g_c.scale1D_128to64[j];
+    if (!strcmp(name, "integral_initv")) return (void*)g_c.integral_initv[i];
+    if (!strcmp(name, "integral_inith")) return (void*)g_c.integral_inith[i];
+
+    CPU_FIELD(satd) CPU_FIELD(filter_vpp) CPU_FIELD(filter_vps) CPU_FIELD(filter_vsp)
+    CPU_FIELD(filter_vss) CPU_FIELD(filter_hpp) CPU_FIELD(filter_hps) CPU_FIELD2(addAvg)
+    CPU_FIELD(copy_pp) CPU_FIELD2(p2s)
+    CCU_FIELD(sa8d) CCU_FIELD(sse_pp) CCU_FIELD(sub_ps) CCU_FIELD2(add_ps)
+    CCU_FIELD(copy_ps) CCU_FIELD(copy_sp) CCU_FIELD(copy_ss) CCU_FIELD(copy_pp)
+    return NULL;
+}
+
+/* constants (common/constants.cpp) so the oracle's regenerated tables can be pinned */
+const int16_t* x265ref_dct_matrix(int n)
+{
+    switch (n) { case 4: return &g_t4[0][0]; case 8: return &g_t8[0][0];
+                 case 16: return &g_t16[0][0]; case 32: return &g_t32[0][0]; }
+    return NULL;
+}
+const int16_t* x265ref_luma_filter(void)   { return &g_lumaFilter[0][0]; }
+const int16_t* x265ref_chroma_filter(void) { return &g_chromaFilter[0][0]; }
+const uint8_t* x265ref_intra_filter_flags(void) { return g_intraFilterFlags; }
+double x265ref_lambda(int qp)  { return x265_lambda_tab[qp]; }
+double x265ref_lambda2(int qp) { return x265_lambda2_tab[qp]; }
+int x265ref_partition_from_sizes(int w, int h) { ensure_init(); return partitionFromSizes(w, h); }
+
+void x265ref_extend_pic_border(pixel* pic, intptr_t stride, int width, int height, int marginX, int marginY)
+{
+    ensure_init();
+    extendPicBorder(pic, stride, width, height, marginX, marginY);
+}
+
+/* BitCost (encoder/bitcost.cpp:33-88): mvcost table for one qp, centred: out[i + range] = cost[i]
+ * for i in [-range, range]. */
+struct BitCostPeek : public BitCost { uint16_t* table() { return m_cost; } };
+void x265ref_mvcost_table(int qp, int range, uint16_t* out)
+{
+    BitCostPeek bc;
+    bc.setQP(qp);
+    uint16_t* c = bc.table();
+    for (int i = -range; i <= range; i++) out[i + range] = c[i];
+}
+
+/* MotionEstimate::motionEstimate (encoder/motion.cpp:739-1569) on a caller-supplied full-res plane
+ * pair, driven through the luma-only setSourcePU (motion.cpp:167-192).  All MVs as int32 pairs.
+ * lowres != 0: `planes` are the 4 lowres hpel planes (lowres.h:67-120 path).
+ * Returns the cost, writes outQMv[2]. */
+int x265ref_motion_estimate(pixel* fencPlane, intptr_t fencStride, intptr_t offset,
+                            pixel* const* refPlanes, intptr_t refStride, int lowres,
+                            int pw, int ph, int method, int subme, int qp,
+                            const int* mvmin, const int* mvmax, const int* qmvp,
+                            int numCand, const int* mvc, int merange, int* outQMv)
+{
+    ensure_init();
+    static bool scales = false;
+    if (!scales) { MotionEstimate::initScales(); scales = true; }
+    MotionEstimate me;
+    me.init(X265_CSP_I400);
+    me.setQP(qp);
+    me.setSourcePU(fencPlane, fencStride, offset, pw, ph, method, method, method, subme);
+    ReferencePlanes ref;
+    ref.lumaStride = refStride;
+    ref.isLowres = !!lowres;
+    if (lowres)
+    {
+        for (int i = 0; i < 4; i++) ref.lowresPlane[i] = refPlanes[i];
+        ref.fpelPlane[0] = refPlanes[0];
+    }
+    else
+        ref.fpelPlane[0] = refPlanes[0];
+    MV mn(mvmin[0], mvmin[1]), mx(mvmax[0], mvmax[1]), mvp(qmvp[0], qmvp[1]), out;
+    MV cands[32];
+    for (int i = 0; i < numCand && i < 32; i++) cands[i] = MV(mvc[2 * i], mvc[2 * i + 1]);
+    int cost = me.motionEstimate(&ref, mn, mx, mvp, numCand, cands, merange, out, 1, NULL);
+    outQMv[0] = out.x; outQMv[1] = out.y;
+    return cost;
+}
+
+} // extern "C"

@@ -1,0 +1,94 @@
+"""Helpers that run one motionEstimate job through the real reference MotionEstimate
+(oracle/_ref, motion.cpp:739) and through the oracle restatement (oracle/oracle_me.c)."""
+import ctypes as C
+import numpy as np
+from common import P, I, IP, ptr, pixel_dtype, make_plane
+
+MVRANGE = 65536  # +-2*BC_MAX_MV like bitcost.h:77
+
+
+class OrcMeJob(C.Structure):
+    _fields_ = [("fenc", P), ("fencStride", IP), ("offset", IP), ("ref", P * 4), ("refStride", IP),
+                ("lowres", I), ("pw", I), ("ph", I), ("method", I), ("subme", I),
+                ("mvmin", I * 2), ("mvmax", I * 2), ("qmvp", I * 2), ("numCand", I), ("mvc", P),
+                ("merange", I), ("mvcost", P)]
+
+
+_tables = {}
+
+
+def mvcost_table(O, lam):
+    key = (id(O), lam)
+    if key not in _tables:
+        t = np.zeros(2 * MVRANGE + 1, np.uint16)
+        O.orc_mvcost_table(C.c_double(lam), MVRANGE, ptr(t))
+        _tables[key] = t
+    return _tables[key]
+
+
+def lowres_planes(O, depth, full, fw, fh, margin=32):
+    """4 hpel planes with replicated margins from a full-res image (lowres.cpp:259-302 layout)."""
+    dt = pixel_dtype(depth)
+    lw, lh = fw // 2, fh // 2
+    stride = (lw + 2 * margin + 31) // 32 * 32
+    planes = [np.zeros((lh + 2 * margin, stride), dt) for _ in range(4)]
+    org = margin * stride + margin
+    src = np.zeros((fh + 2, fw + 2), dt)
+    src[:fh, :fw] = full
+    src[fh:, :fw] = full[-1:, :]
+    src[:, fw:] = src[:, fw - 1:fw]
+    O.orc_frame_init_lowres(ptr(src), *[ptr(p, org) for p in planes], IP(fw + 2), IP(stride), lw, lh)
+    for p in planes:
+        O.orc_extend_pic_border(ptr(p, org), IP(stride), lw, lh, margin, margin)
+    return planes, stride, org, lw, lh
+
+
+def run_both(O, R, depth, rng, w, h, method, subme, lowres, smooth, merange, qp=30):
+    mx = (1 << depth) - 1
+    W, H, margin = 256, 192, 96
+    lam = R.x265ref_lambda(qp)
+    tab = mvcost_table(O, lam)
+    if lowres:
+        yy, xx = np.mgrid[0:H * 2, 0:W * 2]
+        def img(shift):
+            if smooth:
+                v = 128 + 60 * np.sin((xx + 3 * shift) / 37.0) + 40 * np.cos((yy - 2 * shift) / 29.0) + rng.integers(-6, 7, xx.shape)
+                return (np.clip(v, 0, 255).astype(np.int64) << (depth - 8)).astype(pixel_dtype(depth))
+            return rng.integers(0, mx + 1, xx.shape).astype(pixel_dtype(depth))
+        fplanes, stride, org, lw, lh = lowres_planes(O, depth, img(0), W * 2, H * 2, margin)
+        rplanes, _, _, _, _ = lowres_planes(O, depth, img(2), W * 2, H * 2, margin)
+        fenc = fplanes[0]; refs = rplanes
+    else:
+        fenc, stride, org = make_plane(rng, depth, W, H, margin, smooth=smooth)
+        refb, _, _ = make_plane(rng, depth, W, H, margin, smooth=smooth)
+        if smooth:
+            # reference = shifted source + noise so the search has something to find
+            sh = np.roll(np.roll(fenc, int(rng.integers(-9, 10)), axis=0), int(rng.integers(-9, 10)), axis=1)
+            refb = np.clip(sh.astype(np.int64) + rng.integers(-3, 4, sh.shape), 0, mx).astype(fenc.dtype)
+        refs = [refb, refb, refb, refb]
+    bx = int(rng.integers(0, (W - w) // 4 + 1)) * 4; by = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+    offset = org + by * stride + bx
+    # search window: +-merange around the predictor, clipped so all reads stay inside the margins
+    qmvp = (int(rng.integers(-40, 41)), int(rng.integers(-40, 41)))
+    lim = margin - 12
+    mvmin = (max(-bx - lim, (qmvp[0] >> 2) - merange), max(-by - lim, (qmvp[1] >> 2) - merange))
+    mvmax = (min(W - w - bx + lim, (qmvp[0] >> 2) + merange), min(H - h - by + lim, (qmvp[1] >> 2) + merange))
+    ncand = 0 if lowres else int(rng.integers(0, 4))
+    mvc = rng.integers(-60, 61, (max(ncand, 1), 2)).astype(np.int32)
+    out_r = np.zeros(2, np.int32); out_o = np.zeros(2, np.int32)
+    arr = (P * 4)(*[C.c_void_p(p.ctypes.data) for p in refs])
+    R.x265ref_motion_estimate.argtypes = [P, IP, IP, P, IP, I, I, I, I, I, I, P, P, P, I, P, I, P]
+    mn = np.array(mvmin, np.int32); mxv = np.array(mvmax, np.int32); mp = np.array(qmvp, np.int32)
+    cr = R.x265ref_motion_estimate(ptr(fenc), stride, offset, arr, stride, lowres, w, h, method, subme, qp,
+                                   ptr(mn), ptr(mxv), ptr(mp), ncand, ptr(mvc), merange, ptr(out_r))
+    job = OrcMeJob()
+    job.fenc = fenc.ctypes.data; job.fencStride = stride; job.offset = offset
+    for i in range(4):
+        job.ref[i] = refs[i].ctypes.data
+    job.refStride = stride; job.lowres = lowres; job.pw = w; job.ph = h; job.method = method; job.subme = subme
+    job.mvmin[0], job.mvmin[1] = mvmin; job.mvmax[0], job.mvmax[1] = mvmax; job.qmvp[0], job.qmvp[1] = qmvp
+    job.numCand = ncand; job.mvc = mvc.ctypes.data; job.merange = merange
+    job.mvcost = tab.ctypes.data + MVRANGE * 2
+    O.orc_motion_estimate.argtypes = [C.POINTER(OrcMeJob), P]
+    co = O.orc_motion_estimate(C.byref(job), ptr(out_o))
+    return (cr, int(out_r[0]), int(out_r[1])), (co, int(out_o[0]), int(out_o[1]))
