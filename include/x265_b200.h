@@ -1,0 +1,154 @@
+/* include/x265_b200.h -- C ABI of libx265cu.so, the B200-native (sm_100a) implementation of x265's
+ * block-primitive hot path.  Plain C: pointers and sizes only, no CUDA/torch types.
+ *
+ * Two levels, both replacing entries of the reference's EncoderPrimitives table
+ * (/root/reference/source/common/primitives.h:237-429):
+ *
+ *  (1) PER-CALL TABLE  -- x265cu_get_primitive() hands out C function pointers with EXACTLY the
+ *      reference typedefs (primitives.h:133-234): host pointers, strides in elements, caller-owned
+ *      buffers, outputs fully overwritten, nothing retained.  setupCudaPrimitives() (the drop-in
+ *      sibling of setupAssemblyPrimitives(), primitives.h:470, call site primitives.cpp:260-265)
+ *      fills an EncoderPrimitives from these; see INTEGRATION.md.  Each call stages the block to the
+ *      device, runs the same kernels as (2) with a batch of one, and copies the result back.
+ *
+ *  (2) BATCHED API     -- one launch per primitive class over a job list (all candidates x all CTUs
+ *      of a frame / row), on device-resident planes.  This is what the batching hooks at
+ *      CostEstimateGroup::finishBatch (slicetype.cpp:1942-2009) and FrameEncoder::processRowEncoder
+ *      (frameencoder.cpp:1340) call.  `_dev` arguments are device pointers obtained from
+ *      x265cu_malloc(); every function returns 0 on success, -1 on a CUDA error (message via
+ *      x265cu_last_error()); there is NO CPU fallback.
+ *
+ * depth is 8 (pixel = uint8_t) or 10 (pixel = uint16_t), cf. common/common.h:126-148.
+ */
+#ifndef X265_B200_H
+#define X265_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct x265cu_ctx x265cu_ctx;
+
+/* ---------- context / memory ---------- */
+int  x265cu_device_count(void);
+x265cu_ctx* x265cu_create(int device);                 /* NULL if no CUDA device (never falls back) */
+void x265cu_destroy(x265cu_ctx*);
+const char* x265cu_last_error(void);
+int  x265cu_sync(x265cu_ctx*);
+void* x265cu_stream(x265cu_ctx*);                       /* cudaStream_t the ctx launches on */
+void* x265cu_malloc(x265cu_ctx*, size_t bytes);
+void  x265cu_free(x265cu_ctx*, void* dev);
+void* x265cu_host_alloc(size_t bytes);                  /* pinned host memory */
+void  x265cu_host_free(void* p);
+int  x265cu_h2d(x265cu_ctx*, void* dev, const void* host, size_t bytes);   /* async on ctx stream */
+int  x265cu_d2h(x265cu_ctx*, void* host, const void* dev, size_t bytes);   /* async on ctx stream */
+int  x265cu_memset(x265cu_ctx*, void* dev, int value, size_t bytes);
+/* timing on the ctx stream (cudaEvent): returns ms between begin/end, <0 on error */
+int  x265cu_timer_begin(x265cu_ctx*);
+float x265cu_timer_end(x265cu_ctx*);
+/* number of kernels this library has launched since the ctx was created */
+uint64_t x265cu_launch_count(x265cu_ctx*);
+
+/* ---------- (1) per-call table ---------- */
+/* name / i / j / k exactly as the fields of EncoderPrimitives: "pu.sad" (i = LumaPU),
+ * "cu.dct" (i = LumaCU), "cu.intra_pred" (i = LumaCU, j = mode), "quant",
+ * "chroma.pu.filter_hpp" (k = csp, i = LumaPU) ...  Returns NULL for entries we do not provide. */
+void* x265cu_get_primitive(int depth, const char* name, int i, int j, int k);
+
+/* ---------- (2) batched API ---------- */
+
+/* pixel-compare class: sad / satd / sa8d / sse / var / psy   (pixel.cpp:40-377, 167-186, 703-757) */
+enum { X265CU_SAD = 0, X265CU_SATD = 1, X265CU_SA8D = 2, X265CU_SSE_PP = 3, X265CU_SSE_SS = 4,
+       X265CU_SSD_S = 5, X265CU_VAR = 6, X265CU_PSY = 7 };
+typedef struct {
+    int64_t a_off, b_off;      /* element offsets into plane A / plane B */
+    int32_t a_stride, b_stride;
+    int16_t w, h;
+    int32_t pad;
+} x265cu_cmp_job;
+/* out_dev[n] : uint64 (sse_t / var packing as in the reference; int costs zero-extended) */
+int x265cu_pixelcmp_batch(x265cu_ctx*, int depth, int op, const void* planeA_dev, const void* planeB_dev,
+                          const x265cu_cmp_job* jobs_dev, int n, uint64_t* out_dev);
+
+/* elementwise block-op class (pixel.cpp:379-862, ipfilter.cpp:40-57) */
+enum { X265CU_COPY_PP = 0, X265CU_COPY_SS, X265CU_COPY_SP, X265CU_COPY_PS, X265CU_SUB_PS, X265CU_ADD_PS,
+       X265CU_PIXELAVG_PP, X265CU_ADDAVG, X265CU_P2S, X265CU_TRANSPOSE, X265CU_BLOCKFILL_S,
+       X265CU_CPY2DTO1D_SHL, X265CU_CPY2DTO1D_SHR, X265CU_CPY1DTO2D_SHL, X265CU_CPY1DTO2D_SHR,
+       X265CU_WEIGHT_PP, X265CU_WEIGHT_SP, X265CU_SCALE2D_64TO32, X265CU_DEQUANT_NORMAL };
+typedef struct {
+    int64_t d_off, a_off, b_off;        /* element offsets into dst / srcA / srcB buffers */
+    int32_t d_stride, a_stride, b_stride;
+    int16_t w, h;
+    int32_t p0, p1, p2, p3;             /* op parameters (shift / value / weights) */
+} x265cu_blk_job;
+int x265cu_blockop_batch(x265cu_ctx*, int depth, int op, void* dst_dev, const void* a_dev, const void* b_dev,
+                         const x265cu_blk_job* jobs_dev, int n);
+
+/* interpolation class (ipfilter.cpp:79-369) */
+enum { X265CU_HPP = 0, X265CU_HPS, X265CU_VPP, X265CU_VPS, X265CU_VSP, X265CU_VSS, X265CU_HVPP };
+typedef struct {
+    int64_t s_off, d_off;
+    int32_t s_stride, d_stride;
+    int16_t w, h;
+    int8_t  idxX, idxY, rowExt, ntaps;   /* ntaps 8 (luma) / 4 (chroma) */
+} x265cu_interp_job;
+int x265cu_interp_batch(x265cu_ctx*, int depth, int op, const void* src_dev, void* dst_dev,
+                        const x265cu_interp_job* jobs_dev, int n);
+
+/* transform / quant class (dct.cpp:43-742).  Blocks are n contiguous TUs. */
+enum { X265CU_DCT = 0, X265CU_IDCT = 1, X265CU_DST4 = 2, X265CU_IDST4 = 3 };
+/* src: strided 2-D (stride elements between rows, tu_pitch elements between TUs) for DCT;
+ * dst contiguous N*N per TU.  For IDCT the roles swap (dst strided). */
+int x265cu_transform_batch(x265cu_ctx*, int depth, int op, int size, const int16_t* src_dev, int16_t* dst_dev,
+                           int stride, int64_t tu_pitch, int n);
+/* quant over n TUs of numCoeff each; quantCoeff shared by all TUs (numCoeff entries).
+ * numSig_dev[n] receives the per-TU return value.  deltaU_dev may be NULL (nquant semantics when
+ * `nquant` != 0: |level| stored). */
+int x265cu_quant_batch(x265cu_ctx*, const int16_t* coef_dev, const int32_t* quantCoeff_dev, int32_t* deltaU_dev,
+                       int16_t* qCoef_dev, int qBits, int add, int numCoeff, int n, int nquant, uint32_t* numSig_dev);
+int x265cu_dequant_normal_batch(x265cu_ctx*, const int16_t* q_dev, int16_t* coef_dev, int64_t num, int scale, int shift);
+int x265cu_dequant_scaling_batch(x265cu_ctx*, const int16_t* q_dev, const int32_t* dq_dev, int16_t* coef_dev,
+                                 int numCoeff, int n, int per, int shift);
+
+/* intra class (intrapred.cpp:31-234): n jobs, each with its own 4N+1 neighbour array
+ * (nb_dev + job*nb_pitch), mode, filter flag; dst block at dst_dev + job*dst_pitch, row stride dst_stride */
+typedef struct { int32_t mode, bFilter; } x265cu_intra_job;
+int x265cu_intra_pred_batch(x265cu_ctx*, int depth, int size, const void* nb_dev, int64_t nb_pitch,
+                            void* dst_dev, int64_t dst_pitch, int dst_stride,
+                            const x265cu_intra_job* jobs_dev, int n);
+int x265cu_intra_filter_batch(x265cu_ctx*, int depth, int size, const void* nb_dev, void* filt_dev, int64_t pitch, int n);
+int x265cu_intra_allangs_batch(x265cu_ctx*, int depth, int size, const void* ref_dev, const void* filt_dev, int64_t nb_pitch,
+                               void* dst_dev, int bLuma, int n);
+
+/* lowres (pixel.cpp:604-628 + :1027-1041): full frame -> 4 half-pel planes, margins extended */
+int x265cu_frame_init_lowres(x265cu_ctx*, int depth, const void* src_dev, int src_stride,
+                             void* dst0_dev, void* dsth_dev, void* dstv_dev, void* dstc_dev,
+                             int dst_stride, int width, int height, int marginX, int marginY);
+int x265cu_extend_border(x265cu_ctx*, int depth, void* plane_dev, int stride, int width, int height, int marginX, int marginY);
+
+/* mvcost table (bitcost.cpp:33-110): host helper, out[2*range+1] centred */
+void x265cu_mvcost_table(double lambda, int range, uint16_t* out_host);
+
+/* motion estimation class: one job = one MotionEstimate::motionEstimate() call
+ * (motion.cpp:739-1569; DIA / HEX / STAR integer search + sub-pel refine, luma).  All jobs of a
+ * launch share fenc plane, stride and mvcost table; results: out_dev[job] = {cost, qmv.x, qmv.y, 0}. */
+typedef struct {
+    int32_t offset;             /* block origin (element offset, same in fenc and ref planes) */
+    int16_t ref;                /* index into the ref plane table */
+    int8_t  pw, ph;             /* PU size */
+    int16_t mvmin[2], mvmax[2]; /* full-pel */
+    int16_t qmvp[2];            /* qpel predictor */
+    int16_t mvc[8];             /* up to 4 qpel candidates */
+    int8_t  numCand, method, subme, merange;
+} x265cu_me_job;
+int x265cu_me_batch(x265cu_ctx*, int depth, const void* fenc_dev, int fencStride,
+                    const void* const* refplanes_dev /* device array of plane ptrs */, int refStride, int lowres,
+                    const uint16_t* mvcost_dev /* centred table base */, int mvcost_range,
+                    const x265cu_me_job* jobs_dev, int n, int32_t* out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,161 @@
+// x265_b200/csrc/intra.cuh -- intra prediction class (DC, planar, angular 2..34, all-angs, 1:2:1 filter).
+// Semantics: /root/reference/source/common/intrapred.cpp:31-51 (filter), :53-85 (DC), :87-100 (planar),
+// :102-204 (angular), :206-234 (all-angs).  Neighbour layout: [0]=top-left, [1..2N]=top(+right),
+// [2N+1..4N]=left(+bottom).
+#pragma once
+#include "common.cuh"
+
+__constant__ int8_t  c_angle[17]   = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+__constant__ int16_t c_invAngle[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
+
+// which TU sizes use the filtered neighbours for an angular / planar mode (constants.cpp:561,
+// HEVC 8.4.4.2.3): min(|m-26|,|m-10|) > thr(N), thr = 7 (N=8), 1 (N=16), 0 (N=32); never N=4 / DC.
+__device__ __forceinline__ bool intra_use_filtered(int mode, int N)
+{
+    if (mode == 1 || N == 4) return false;
+    if (mode == 0) return N >= 8;
+    int d = min(abs(mode - 26), abs(mode - 10));
+    int thr = N == 8 ? 7 : (N == 16 ? 1 : 0);
+    return d > thr;
+}
+
+// Cooperative predictor.  nbs: neighbours in shared memory (4N+1), ref: shared scratch >= 3N+2.
+// Writes an N x N block; `vframe` = leave horizontal modes untransposed (all-angs storage).
+// Must be called by all threads of the CTA (contains __syncthreads()).
+template <typename P>
+__device__ void intra_predict_block(const int16_t* nbs, int16_t* refbuf, P* __restrict__ dst, int64_t dstStride,
+                                    int N, int mode, int bFilter, bool vframe)
+{
+    constexpr int maxv = PixTraits<P>::maxv;
+    const int lg = 31 - __clz(N), N2 = 2 * N;
+    if (mode == 0)
+    {
+        const int tr = nbs[1 + N], bl = nbs[N2 + 1 + N];
+        for (int i = threadIdx.x; i < N * N; i += blockDim.x)
+        {
+            int y = i >> lg, x = i & (N - 1);
+            dst[y * dstStride + x] = (P)(((N - 1 - x) * nbs[N2 + 1 + y] + (N - 1 - y) * nbs[1 + x] + (x + 1) * tr + (y + 1) * bl + N) >> (lg + 1));
+        }
+        return;
+    }
+    if (mode == 1)
+    {
+        int sum = N;
+        for (int i = 0; i < N; i++) sum += nbs[1 + i] + nbs[N2 + 1 + i];
+        const int dc = sum / N2;
+        for (int i = threadIdx.x; i < N * N; i += blockDim.x)
+        {
+            int y = i >> lg, x = i & (N - 1);
+            int v = dc;
+            if (bFilter)
+            {
+                if (x == 0 && y == 0) v = (nbs[1] + nbs[N2 + 1] + 2 * dc + 2) >> 2;
+                else if (y == 0)      v = (nbs[1 + x] + 3 * dc + 2) >> 2;
+                else if (x == 0)      v = (nbs[N2 + 1 + y] + 3 * dc + 2) >> 2;
+            }
+            dst[y * dstStride + x] = (P)v;
+        }
+        return;
+    }
+    const bool hor = mode < 18;
+    const int angOff = hor ? 10 - mode : mode - 26;
+    const int angle = c_angle[8 + angOff];
+    // main/side edges in the vertical-family frame
+    const int mainBase = hor ? N2 + 1 : 1;     // nbs[mainBase + i], i = 0..2N-1
+    const int sideBase = hor ? 1 : N2 + 1;
+    if (angle == 0)
+    {
+        for (int i = threadIdx.x; i < N * N; i += blockDim.x)
+        {
+            int r = i >> lg, c = i & (N - 1);
+            int v = nbs[mainBase + c];
+            if (bFilter && c == 0) v = clip3i(0, maxv, (int)(int16_t)(nbs[mainBase] + ((nbs[sideBase + r] - nbs[0]) >> 1)));
+            int y = (hor && !vframe) ? c : r, x = (hor && !vframe) ? r : c;
+            dst[y * dstStride + x] = (P)v;
+        }
+        return;
+    }
+    // reference line: refbuf[off + 1 + idx] holds ref[idx], idx in [-N-1 .. 2N]
+    const int off = N + 1;
+    __syncthreads();
+    if (angle < 0)
+    {
+        const int nproj = -((N * angle) >> 5) - 1;
+        const int inv = c_invAngle[-angOff - 1];
+        for (int i = threadIdx.x; i < nproj; i += blockDim.x)
+            refbuf[off + 1 + (-2 - i)] = nbs[sideBase - 1 + ((128 + (i + 1) * inv) >> 8)];     // side[k-1], k = acc>>8
+        for (int i = threadIdx.x; i < N + 1; i += blockDim.x)
+            refbuf[off + 1 + (-1 + i)] = (i == 0) ? nbs[0] : nbs[mainBase + i - 1];
+    }
+    else
+    {
+        for (int i = threadIdx.x; i < N2; i += blockDim.x) refbuf[off + 1 + i] = nbs[mainBase + i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * N; i += blockDim.x)
+    {
+        int r = i >> lg, c = i & (N - 1);
+        int pos = (r + 1) * angle;
+        int o = pos >> 5, f = pos & 31;
+        int a = refbuf[off + 1 + o + c];
+        int v = f ? (((32 - f) * a + f * refbuf[off + 1 + o + c + 1] + 16) >> 5) : a;
+        int y = (hor && !vframe) ? c : r, x = (hor && !vframe) ? r : c;
+        dst[y * dstStride + x] = (P)v;
+    }
+}
+
+// 1:2:1 neighbour smoothing (intrapred.cpp:31-51), element i of 4N+1
+__device__ __forceinline__ int intra_filter_elem(const int16_t* s, int i, int N)
+{
+    const int N2 = 2 * N, N4 = 4 * N;
+    if (i == 0) return (2 * s[0] + s[1] + s[N2 + 1] + 2) >> 2;
+    if (i == N2 || i == N4) return s[i];
+    if (i == N2 + 1) return (2 * s[N2 + 1] + s[0] + s[N2 + 2] + 2) >> 2;
+    return (2 * s[i] + s[i - 1] + s[i + 1] + 2) >> 2;
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256) k_intra_pred(int N, const P* __restrict__ nb, int64_t nb_pitch, P* __restrict__ dst, int64_t dst_pitch,
+                                                    int dst_stride, const x265cu_intra_job* __restrict__ jobs, int n)
+{
+    __shared__ int16_t s_nb[129];
+    __shared__ int16_t s_ref[128];
+    for (int j = blockIdx.x; j < n; j += gridDim.x)
+    {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * N + 1; i += blockDim.x) s_nb[i] = nb[j * nb_pitch + i];
+        __syncthreads();
+        intra_predict_block<P>(s_nb, s_ref, dst + j * dst_pitch, dst_stride, N, jobs[j].mode, jobs[j].bFilter, false);
+    }
+}
+
+template <typename P>
+__global__ void k_intra_filter(int N, const P* __restrict__ nb, P* __restrict__ filt, int64_t pitch, int n)
+{
+    __shared__ int16_t s_nb[129];
+    for (int j = blockIdx.x; j < n; j += gridDim.x)
+    {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * N + 1; i += blockDim.x) s_nb[i] = nb[j * pitch + i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * N + 1; i += blockDim.x) filt[j * pitch + i] = (P)intra_filter_elem(s_nb, i, N);
+    }
+}
+
+// all-angs (intrapred.cpp:206-234): grid = (33 modes, jobs); 33*N*N contiguous per job
+template <typename P>
+__global__ void __launch_bounds__(256) k_intra_allangs(int N, const P* __restrict__ refp, const P* __restrict__ filtp, int64_t nb_pitch,
+                                                       P* __restrict__ dst, int bLuma, int n)
+{
+    __shared__ int16_t s_nb[129];
+    __shared__ int16_t s_ref[128];
+    const int mode = 2 + blockIdx.x;
+    for (int j = blockIdx.y; j < n; j += gridDim.y)
+    {
+        const P* src = intra_use_filtered(mode, N) ? filtp : refp;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * N + 1; i += blockDim.x) s_nb[i] = src[j * nb_pitch + i];
+        __syncthreads();
+        intra_predict_block<P>(s_nb, s_ref, dst + ((int64_t)j * 33 + (mode - 2)) * N * N, N, N, mode, bLuma, true);
+    }
+}

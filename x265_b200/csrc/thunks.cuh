@@ -1,0 +1,485 @@
+// x265_b200/csrc/thunks.cuh -- the per-call primitive table (level 1 of include/x265_b200.h).
+// Every entry has exactly the reference typedef of the EncoderPrimitives field it replaces
+// (/root/reference/source/common/primitives.h:133-234): host pointers, element strides,
+// caller-owned buffers.  A call stages its blocks into a pinned arena, runs the SAME batched kernel
+// as the level-2 API with a batch of one, and copies back only the W x H outputs (the reference
+// harnesses memcmp whole destination buffers, source/test/ipfilterharness.cpp:62-555).
+// No CPU fallback: if no CUDA device is present the table lookup returns NULL and the getters log.
+#pragma once
+#include "common.cuh"
+#include <type_traits>
+#include <stdlib.h>
+
+namespace thunk {
+
+struct Stage
+{
+    x265cu_ctx* ctx;
+    size_t used;
+    bool ok;
+    Stage() : ctx(NULL), used(0), ok(true) {}
+    size_t reserve(size_t bytes)
+    {
+        size_t off = (used + 63) & ~(size_t)63;
+        if (off + bytes > ctx->stage_bytes) { ok = false; return 0; }
+        used = off + bytes;
+        return off;
+    }
+    // gather a strided 2-D block (rows x cols of es-byte elements) into the arena, compact
+    size_t put(const void* src, intptr_t strideElems, int cols, int rows, int es)
+    {
+        size_t off = reserve((size_t)cols * rows * es);
+        if (!ok) return 0;
+        uint8_t* d = ctx->h_stage + off;
+        const uint8_t* s = (const uint8_t*)src;
+        for (int y = 0; y < rows; y++) memcpy(d + (size_t)y * cols * es, s + (ptrdiff_t)y * strideElems * es, (size_t)cols * es);
+        return off;
+    }
+    void get(void* dst, intptr_t strideElems, int cols, int rows, int es, size_t off)
+    {
+        const uint8_t* s = ctx->h_stage + off;
+        uint8_t* d = (uint8_t*)dst;
+        for (int y = 0; y < rows; y++) memcpy(d + (ptrdiff_t)y * strideElems * es, s + (size_t)y * cols * es, (size_t)cols * es);
+    }
+    template <typename T> T* h(size_t off) { return (T*)(ctx->h_stage + off); }
+    template <typename T> T* d(size_t off) { return (T*)(ctx->d_stage + off); }
+    int upload() { return cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, used, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? 0 : -1; }
+    int download(size_t off, size_t bytes)
+    {
+        if (cudaMemcpyAsync(ctx->h_stage + off, ctx->d_stage + off, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+        return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? 0 : -1;
+    }
+};
+
+static thread_local x265cu_ctx* t_ctx = NULL;
+static x265cu_ctx* tctx()
+{
+    if (!t_ctx)
+    {
+        t_ctx = x265cu_create(0);
+        if (!t_ctx) { fprintf(stderr, "x265cu: FATAL: primitive called without a CUDA device (no CPU fallback)\n"); abort(); }
+    }
+    cudaSetDevice(t_ctx->device);
+    return t_ctx;
+}
+static void fail(const char* what) { fprintf(stderr, "x265cu: FATAL: %s: %s\n", what, x265cu_last_error()); abort(); }
+
+// ---------- pixel compare ----------
+template <typename P>
+static uint64_t pixelcmp(int op, const void* a, intptr_t sa, const void* b, intptr_t sb, int w, int h, int esA, int esB)
+{
+    Stage s; s.ctx = tctx();
+    size_t oa = s.put(a, sa, w, h, esA);
+    size_t ob = b ? s.put(b, sb, w, h, esB) : oa;
+    size_t oj = s.reserve(sizeof(x265cu_cmp_job));
+    size_t oo = s.reserve(sizeof(uint64_t));
+    if (!s.ok) fail("stage overflow");
+    x265cu_cmp_job* j = s.h<x265cu_cmp_job>(oj);
+    j->a_off = (int64_t)(oa / esA); j->b_off = (int64_t)(ob / esB); j->a_stride = w; j->b_stride = w; j->w = (int16_t)w; j->h = (int16_t)h; j->pad = 0;
+    if (s.upload() || launch_pixelcmp(s.ctx, PixTraits<P>::depth, op, s.ctx->d_stage, s.ctx->d_stage, s.d<x265cu_cmp_job>(oj), 1, s.d<uint64_t>(oo)) ||
+        s.download(oo, sizeof(uint64_t))) fail("pixelcmp");
+    return *s.h<uint64_t>(oo);
+}
+
+template <typename P>
+static void sad_xn(int nref, const P* fenc, const P* const* refs, intptr_t rs, int32_t* res, int w, int h)
+{
+    Stage s; s.ctx = tctx();
+    size_t of = s.put(fenc, X265CU_FENC_STRIDE, w, h, sizeof(P));
+    size_t orf[4];
+    for (int i = 0; i < nref; i++) orf[i] = s.put(refs[i], rs, w, h, sizeof(P));
+    size_t oj = s.reserve(sizeof(x265cu_cmp_job) * nref);
+    size_t oo = s.reserve(sizeof(uint64_t) * nref);
+    if (!s.ok) fail("stage overflow");
+    for (int i = 0; i < nref; i++)
+    {
+        x265cu_cmp_job* j = s.h<x265cu_cmp_job>(oj) + i;
+        j->a_off = of / sizeof(P); j->b_off = orf[i] / sizeof(P); j->a_stride = w; j->b_stride = w; j->w = (int16_t)w; j->h = (int16_t)h; j->pad = 0;
+    }
+    if (s.upload() || launch_pixelcmp(s.ctx, PixTraits<P>::depth, X265CU_SAD, s.ctx->d_stage, s.ctx->d_stage, s.d<x265cu_cmp_job>(oj), nref, s.d<uint64_t>(oo)) ||
+        s.download(oo, sizeof(uint64_t) * nref)) fail("sad_xn");
+    for (int i = 0; i < nref; i++) res[i] = (int32_t)s.h<uint64_t>(oo)[i];
+}
+
+// ---------- block ops ----------
+// esD/esA/esB: element sizes; dw,dh: output block; aw,ah / bw,bh: input blocks
+template <typename P>
+static void blockop(int op, void* dst, intptr_t ds, int dw, int dh, int esD, const void* a, intptr_t sa, int aw, int ah, int esA,
+                    const void* b, intptr_t sb, int bw, int bh, int esB, int w, int h, int p0 = 0, int p1 = 0, int p2 = 0, int p3 = 0)
+{
+    Stage s; s.ctx = tctx();
+    size_t oa = a ? s.put(a, sa, aw, ah, esA) : 0;
+    size_t ob = b ? s.put(b, sb, bw, bh, esB) : 0;
+    size_t od = s.reserve((size_t)dw * dh * esD);
+    size_t oj = s.reserve(sizeof(x265cu_blk_job));
+    if (!s.ok) fail("stage overflow");
+    x265cu_blk_job* j = s.h<x265cu_blk_job>(oj);
+    j->d_off = od / esD; j->a_off = a ? oa / esA : 0; j->b_off = b ? ob / esB : 0;
+    j->d_stride = dw; j->a_stride = aw; j->b_stride = bw; j->w = (int16_t)w; j->h = (int16_t)h;
+    j->p0 = p0; j->p1 = p1; j->p2 = p2; j->p3 = p3;
+    if (s.upload() || launch_blockop(s.ctx, PixTraits<P>::depth, op, s.ctx->d_stage, s.ctx->d_stage, s.ctx->d_stage, s.d<x265cu_blk_job>(oj), 1) ||
+        s.download(od, (size_t)dw * dh * esD)) fail("blockop");
+    s.get(dst, ds, dw, dh, esD, od);
+}
+
+// ---------- interpolation ----------
+template <typename P>
+static void interp(int op, const void* src, intptr_t ss, void* dst, intptr_t ds, int w, int h, int idxX, int idxY, int rowExt, int ntaps)
+{
+    const bool srcShort = (op == X265CU_VSP || op == X265CU_VSS);
+    const bool dstShort = (op == X265CU_HPS || op == X265CU_VPS || op == X265CU_VSS);
+    const bool doH = (op == X265CU_HPP || op == X265CU_HPS || op == X265CU_HVPP);
+    const bool doV = !(op == X265CU_HPP || op == X265CU_HPS);
+    const bool vHalo = doV || (op == X265CU_HPS && rowExt);
+    const int hl = doH ? ntaps / 2 - 1 : 0, hr = doH ? ntaps / 2 : 0, vt = vHalo ? ntaps / 2 - 1 : 0, vb = vHalo ? ntaps / 2 : 0;
+    const int ww = w + hl + hr, wh = h + vt + vb;
+    const int esS = srcShort ? 2 : (int)sizeof(P), esD = dstShort ? 2 : (int)sizeof(P);
+    const int outRows = (op == X265CU_HPS && rowExt) ? wh : h;
+    Stage s; s.ctx = tctx();
+    const uint8_t* sp = (const uint8_t*)src - ((ptrdiff_t)vt * ss + hl) * esS;
+    size_t os = s.put(sp, ss, ww, wh, esS);
+    size_t od = s.reserve((size_t)w * outRows * esD);
+    size_t oj = s.reserve(sizeof(x265cu_interp_job));
+    if (!s.ok) fail("stage overflow");
+    x265cu_interp_job* j = s.h<x265cu_interp_job>(oj);
+    j->s_off = os / esS + (int64_t)vt * ww + hl; j->d_off = od / esD; j->s_stride = ww; j->d_stride = w;
+    j->w = (int16_t)w; j->h = (int16_t)h; j->idxX = (int8_t)idxX; j->idxY = (int8_t)idxY; j->rowExt = (int8_t)rowExt; j->ntaps = (int8_t)ntaps;
+    if (s.upload() || launch_interp(s.ctx, PixTraits<P>::depth, op, s.ctx->d_stage, s.ctx->d_stage, s.d<x265cu_interp_job>(oj), 1) ||
+        s.download(od, (size_t)w * outRows * esD)) fail("interp");
+    s.get(dst, ds, w, outRows, esD, od);
+}
+
+// ---------- transforms ----------
+template <typename P>
+static void transform(int op, int N, const int16_t* src, int16_t* dst, intptr_t stride)
+{
+    const bool fwd = (op == X265CU_DCT || op == X265CU_DST4);
+    Stage s; s.ctx = tctx();
+    size_t os = fwd ? s.put(src, stride, N, N, 2) : s.put(src, N, N, N, 2);
+    size_t od = s.reserve((size_t)N * N * 2);
+    if (!s.ok) fail("stage overflow");
+    if (s.upload() || launch_transform(s.ctx, PixTraits<P>::depth, op, N, s.d<int16_t>(os), s.d<int16_t>(od), N, (int64_t)N * N, 1) ||
+        s.download(od, (size_t)N * N * 2)) fail("transform");
+    if (fwd) memcpy(dst, s.h<int16_t>(od), (size_t)N * N * 2);
+    else s.get(dst, stride, N, N, 2, od);
+}
+
+static uint32_t quant(const int16_t* coef, const int32_t* qc, int32_t* deltaU, int16_t* qCoef, int qBits, int add, int numCoeff, int nq)
+{
+    Stage s; s.ctx = tctx();
+    size_t oc = s.put(coef, numCoeff, numCoeff, 1, 2), oq = s.put(qc, numCoeff, numCoeff, 1, 4);
+    size_t odu = s.reserve((size_t)numCoeff * 4), oqc = s.reserve((size_t)numCoeff * 2), on = s.reserve(4);
+    if (!s.ok) fail("stage overflow");
+    if (s.upload() || x265cu_quant_batch(s.ctx, s.d<int16_t>(oc), s.d<int32_t>(oq), deltaU ? s.d<int32_t>(odu) : NULL, s.d<int16_t>(oqc), qBits, add, numCoeff, 1, nq, s.d<uint32_t>(on)) ||
+        s.download(odu, (on + 4) - odu)) fail("quant");
+    if (deltaU) memcpy(deltaU, s.h<int32_t>(odu), (size_t)numCoeff * 4);
+    memcpy(qCoef, s.h<int16_t>(oqc), (size_t)numCoeff * 2);
+    return *s.h<uint32_t>(on);
+}
+
+static void dequant_normal(const int16_t* q, int16_t* coef, int num, int scale, int shift)
+{
+    Stage s; s.ctx = tctx();
+    size_t oq = s.put(q, num, num, 1, 2), oc = s.reserve((size_t)num * 2);
+    if (!s.ok) fail("stage overflow");
+    if (s.upload() || x265cu_dequant_normal_batch(s.ctx, s.d<int16_t>(oq), s.d<int16_t>(oc), num, scale, shift) || s.download(oc, (size_t)num * 2)) fail("dequant");
+    memcpy(coef, s.h<int16_t>(oc), (size_t)num * 2);
+}
+
+static void dequant_scaling(const int16_t* q, const int32_t* dq, int16_t* coef, int num, int per, int shift)
+{
+    Stage s; s.ctx = tctx();
+    size_t oq = s.put(q, num, num, 1, 2), odq = s.put(dq, num, num, 1, 4), oc = s.reserve((size_t)num * 2);
+    if (!s.ok) fail("stage overflow");
+    if (s.upload() || x265cu_dequant_scaling_batch(s.ctx, s.d<int16_t>(oq), s.d<int32_t>(odq), s.d<int16_t>(oc), num, 1, per, shift) || s.download(oc, (size_t)num * 2)) fail("dequant_scaling");
+    memcpy(coef, s.h<int16_t>(oc), (size_t)num * 2);
+}
+
+static void denoise(int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, int numCoeff)
+{
+    Stage s; s.ctx = tctx();
+    size_t oc = s.put(dctCoef, numCoeff, numCoeff, 1, 2), orr = s.put(resSum, numCoeff, numCoeff, 1, 4), oo = s.put(offset, numCoeff, numCoeff, 1, 2);
+    if (!s.ok) fail("stage overflow");
+    if (s.upload()) fail("denoise");
+    k_denoise<<<(numCoeff + 255) / 256, 256, 0, s.ctx->stream>>>(s.d<int16_t>(oc), s.d<uint32_t>(orr), s.d<uint16_t>(oo), numCoeff);
+    s.ctx->launches++;
+    if (s.download(oc, (orr + (size_t)numCoeff * 4) - oc)) fail("denoise");
+    memcpy(dctCoef, s.h<int16_t>(oc), (size_t)numCoeff * 2);
+    memcpy(resSum, s.h<uint32_t>(orr), (size_t)numCoeff * 4);
+}
+
+// copy_cnt / count_nonzero via the compare kernel's machinery would be overkill: tiny dedicated kernel
+__global__ void k_count_nonzero(const int16_t* __restrict__ q, int n, uint32_t* __restrict__ out)
+{
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n; i += 32) cnt += (q[i] != 0);
+    cnt = warp_sum(cnt);
+    if (threadIdx.x == 0) *out = (uint32_t)cnt;
+}
+static uint32_t count_nonzero_blk(const int16_t* src, intptr_t stride, int N, int16_t* copyTo)
+{
+    Stage s; s.ctx = tctx();
+    size_t oq = s.put(src, stride, N, N, 2), on = s.reserve(4);
+    if (!s.ok || s.upload()) fail("count_nonzero");
+    k_count_nonzero<<<1, 32, 0, s.ctx->stream>>>(s.d<int16_t>(oq), N * N, s.d<uint32_t>(on));
+    s.ctx->launches++;
+    if (s.download(oq, (on + 4) - oq)) fail("count_nonzero");     // coefficients come back from the device copy
+    if (copyTo) memcpy(copyTo, s.h<int16_t>(oq), (size_t)N * N * 2);
+    return *s.h<uint32_t>(on);
+}
+
+// ---------- intra ----------
+template <typename P>
+static void intra_pred(int N, P* dst, intptr_t ds, const P* nb, int mode, int bFilter)
+{
+    Stage s; s.ctx = tctx();
+    size_t onb = s.put(nb, 4 * N + 1, 4 * N + 1, 1, sizeof(P)), od = s.reserve((size_t)N * N * sizeof(P)), oj = s.reserve(sizeof(x265cu_intra_job));
+    if (!s.ok) fail("stage overflow");
+    s.h<x265cu_intra_job>(oj)->mode = mode; s.h<x265cu_intra_job>(oj)->bFilter = bFilter;
+    if (s.upload() || x265cu_intra_pred_batch(s.ctx, PixTraits<P>::depth, N, s.d<P>(onb), 4 * N + 1, s.d<P>(od), (int64_t)N * N, N, s.d<x265cu_intra_job>(oj), 1) ||
+        s.download(od, (size_t)N * N * sizeof(P))) fail("intra_pred");
+    s.get(dst, ds, N, N, sizeof(P), od);
+}
+template <typename P>
+static void intra_filter(int N, const P* nb, P* filt)
+{
+    Stage s; s.ctx = tctx();
+    const int len = 4 * N + 1;
+    size_t onb = s.put(nb, len, len, 1, sizeof(P)), of = s.reserve((size_t)len * sizeof(P));
+    if (!s.ok) fail("stage overflow");
+    if (s.upload() || x265cu_intra_filter_batch(s.ctx, PixTraits<P>::depth, N, s.d<P>(onb), s.d<P>(of), len, 1) || s.download(of, (size_t)len * sizeof(P))) fail("intra_filter");
+    memcpy(filt, s.h<P>(of), (size_t)len * sizeof(P));
+}
+template <typename P>
+static void intra_allangs(int N, P* dst, const P* refp, const P* filtp, int bLuma)
+{
+    Stage s; s.ctx = tctx();
+    const int len = 4 * N + 1;
+    size_t orf = s.put(refp, len, len, 1, sizeof(P)), of = s.put(filtp, len, len, 1, sizeof(P)), od = s.reserve((size_t)33 * N * N * sizeof(P));
+    if (!s.ok) fail("stage overflow");
+    if (s.upload() || x265cu_intra_allangs_batch(s.ctx, PixTraits<P>::depth, N, s.d<P>(orf), s.d<P>(of), len, s.d<P>(od), bLuma, 1) ||
+        s.download(od, (size_t)33 * N * N * sizeof(P))) fail("intra_allangs");
+    memcpy(dst, s.h<P>(od), (size_t)33 * N * N * sizeof(P));
+}
+
+// ---------- lowres ----------
+template <typename P>
+static void frame_init_lowres(const P* src0, P* d0, P* dh, P* dv, P* dc, intptr_t sstride, intptr_t dstride, int width, int height)
+{
+    // dedicated buffers: frames do not fit the staging arena
+    x265cu_ctx* c = tctx();
+    const int sw = 2 * width + 1, sh = 2 * height + 1;
+    const size_t sbytes = (size_t)sw * sh * sizeof(P), dbytes = (size_t)width * height * sizeof(P);
+    P* hs = (P*)malloc(sbytes + 4 * dbytes);
+    for (int y = 0; y < sh; y++) memcpy(hs + (size_t)y * sw, src0 + (ptrdiff_t)y * sstride, (size_t)sw * sizeof(P));
+    uint8_t* dev = (uint8_t*)x265cu_malloc(c, sbytes + 4 * dbytes + 256);
+    if (!dev) fail("lowres alloc");
+    uint8_t* dd = dev + ((sbytes + 255) & ~(size_t)255);
+    if (x265cu_h2d(c, dev, hs, sbytes) ||
+        x265cu_frame_init_lowres(c, PixTraits<P>::depth, dev, sw, dd, dd + dbytes, dd + 2 * dbytes, dd + 3 * dbytes, width, width, height, 0, 0) ||
+        x265cu_d2h(c, (uint8_t*)hs + sbytes, dd, 4 * dbytes) || x265cu_sync(c)) fail("frame_init_lowres");
+    P* outs[4] = { d0, dh, dv, dc };
+    for (int p = 0; p < 4; p++)
+        for (int y = 0; y < height; y++)
+            memcpy(outs[p] + (ptrdiff_t)y * dstride, (uint8_t*)hs + sbytes + p * dbytes + (size_t)y * width * sizeof(P), (size_t)width * sizeof(P));
+    x265cu_free(c, dev);
+    free(hs);
+}
+
+// ---------- ads (pixel.cpp:121-165): ordered compaction with ballot ----------
+__global__ void k_ads(int terms, int half, const int* __restrict__ encDC, const uint32_t* __restrict__ sums, int delta,
+                      const uint16_t* __restrict__ costMvX, int16_t* __restrict__ mvs, int width, int thresh, int* __restrict__ count)
+{
+    const int lane = threadIdx.x;
+    int n = 0;
+    for (int i0 = 0; i0 < width; i0 += 32)
+    {
+        int i = i0 + lane;
+        bool hit = false;
+        if (i < width)
+        {
+            const uint32_t* s = sums + i;
+            long long v = llabs((long long)encDC[0] - (long long)s[0]);
+            if (terms == 4)
+                v += llabs((long long)encDC[1] - (long long)s[half]) + llabs((long long)encDC[2] - (long long)s[delta]) + llabs((long long)encDC[3] - (long long)s[delta + half]);
+            else if (terms == 2)
+                v += llabs((long long)encDC[1] - (long long)s[delta]);
+            int ads = (int)v + costMvX[i];
+            hit = ads < thresh;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) mvs[n + __popc(m & ((1u << lane) - 1))] = (int16_t)i;
+        n += __popc(m);
+    }
+    if (lane == 0) *count = n;
+}
+static int ads_terms(int w, int h)
+{
+    if (w == h) return (w >= 16) ? 4 : 1;
+    if (w == 2 * h || h == 2 * w) return 2;
+    if (w <= 16 && h <= 16) return 1;
+    return 4;
+}
+static int ads(int w, int h, int* encDC, uint32_t* sums, int delta, uint16_t* costMvX, int16_t* mvs, int width, int thresh)
+{
+    Stage s; s.ctx = tctx();
+    const int terms = ads_terms(w, h), half = w >> 1;
+    const int nsums = width + (terms == 4 ? delta + half : (terms == 2 ? delta : 0));
+    size_t oe = s.put(encDC, 4, terms, 1, 4), os = s.put(sums, nsums, nsums, 1, 4), oc = s.put(costMvX, width, width, 1, 2);
+    size_t om = s.reserve((size_t)width * 2), on = s.reserve(4);
+    if (!s.ok || s.upload()) fail("ads");
+    k_ads<<<1, 32, 0, s.ctx->stream>>>(terms, half, s.d<int>(oe), s.d<uint32_t>(os), delta, s.d<uint16_t>(oc), s.d<int16_t>(om), width, thresh, s.d<int>(on));
+    s.ctx->launches++;
+    if (s.download(om, (on + 4) - om)) fail("ads");
+    int n = *s.h<int>(on);
+    memcpy(mvs, s.h<int16_t>(om), (size_t)n * 2);
+    return n;
+}
+
+// =====================  typed entry points (reference typedefs)  =====================
+template <typename P> struct T
+{
+    typedef typename std::conditional<sizeof(P) == 1, uint32_t, uint64_t>::type sse_t;
+    // PU-indexed
+    template <int W, int H> static int sad(const P* a, intptr_t sa, const P* b, intptr_t sb) { return (int)pixelcmp<P>(X265CU_SAD, a, sa, b, sb, W, H, sizeof(P), sizeof(P)); }
+    template <int W, int H> static int satd(const P* a, intptr_t sa, const P* b, intptr_t sb) { return (int)pixelcmp<P>(X265CU_SATD, a, sa, b, sb, W, H, sizeof(P), sizeof(P)); }
+    template <int W, int H> static int sa8d(const P* a, intptr_t sa, const P* b, intptr_t sb) { return (int)pixelcmp<P>(X265CU_SA8D, a, sa, b, sb, W, H, sizeof(P), sizeof(P)); }
+    template <int W, int H> static void sad_x3(const P* f, const P* r0, const P* r1, const P* r2, intptr_t rs, int32_t* res) { const P* r[3] = { r0, r1, r2 }; sad_xn<P>(3, f, r, rs, res, W, H); }
+    template <int W, int H> static void sad_x4(const P* f, const P* r0, const P* r1, const P* r2, const P* r3, intptr_t rs, int32_t* res) { const P* r[4] = { r0, r1, r2, r3 }; sad_xn<P>(4, f, r, rs, res, W, H); }
+    template <int W, int H> static int adsf(int* e, uint32_t* s, int d, uint16_t* c, int16_t* m, int width, int th) { return ads(W, H, e, s, d, c, m, width, th); }
+    template <int W, int H> static void copy_pp(P* d, intptr_t ds, const P* s, intptr_t ss) { blockop<P>(X265CU_COPY_PP, d, ds, W, H, sizeof(P), s, ss, W, H, sizeof(P), NULL, 0, 0, 0, 1, W, H); }
+    template <int W, int H> static void pixelavg_pp(P* d, intptr_t ds, const P* a, intptr_t sa, const P* b, intptr_t sb, int) { blockop<P>(X265CU_PIXELAVG_PP, d, ds, W, H, sizeof(P), a, sa, W, H, sizeof(P), b, sb, W, H, sizeof(P), W, H); }
+    template <int W, int H> static void addAvg(const int16_t* a, const int16_t* b, P* d, intptr_t sa, intptr_t sb, intptr_t ds) { blockop<P>(X265CU_ADDAVG, d, ds, W, H, sizeof(P), a, sa, W, H, 2, b, sb, W, H, 2, W, H); }
+    template <int W, int H> static void p2s(const P* s, intptr_t ss, int16_t* d, intptr_t ds) { blockop<P>(X265CU_P2S, d, ds, W, H, 2, s, ss, W, H, sizeof(P), NULL, 0, 0, 0, 1, W, H); }
+    // interpolation; NT = taps
+    template <int NT, int W, int H> static void hpp(const P* s, intptr_t ss, P* d, intptr_t ds, int ci) { interp<P>(X265CU_HPP, s, ss, d, ds, W, H, ci, 0, 0, NT); }
+    template <int NT, int W, int H> static void hps(const P* s, intptr_t ss, int16_t* d, intptr_t ds, int ci, int ext) { interp<P>(X265CU_HPS, s, ss, d, ds, W, H, ci, 0, ext, NT); }
+    template <int NT, int W, int H> static void vpp(const P* s, intptr_t ss, P* d, intptr_t ds, int ci) { interp<P>(X265CU_VPP, s, ss, d, ds, W, H, ci, 0, 0, NT); }
+    template <int NT, int W, int H> static void vps(const P* s, intptr_t ss, int16_t* d, intptr_t ds, int ci) { interp<P>(X265CU_VPS, s, ss, d, ds, W, H, ci, 0, 0, NT); }
+    template <int NT, int W, int H> static void vsp(const int16_t* s, intptr_t ss, P* d, intptr_t ds, int ci) { interp<P>(X265CU_VSP, s, ss, d, ds, W, H, ci, 0, 0, NT); }
+    template <int NT, int W, int H> static void vss(const int16_t* s, intptr_t ss, int16_t* d, intptr_t ds, int ci) { interp<P>(X265CU_VSS, s, ss, d, ds, W, H, ci, 0, 0, NT); }
+    template <int NT, int W, int H> static void hvpp(const P* s, intptr_t ss, P* d, intptr_t ds, int cx, int cy) { interp<P>(X265CU_HVPP, s, ss, d, ds, W, H, cx, cy, 0, NT); }
+    // CU-indexed
+    template <int N> static sse_t sse_pp(const P* a, intptr_t sa, const P* b, intptr_t sb) { return (sse_t)pixelcmp<P>(X265CU_SSE_PP, a, sa, b, sb, N, N, sizeof(P), sizeof(P)); }
+    template <int N> static sse_t sse_ss(const int16_t* a, intptr_t sa, const int16_t* b, intptr_t sb) { return (sse_t)pixelcmp<P>(X265CU_SSE_SS, a, sa, b, sb, N, N, 2, 2); }
+    template <int N> static sse_t ssd_s(const int16_t* a, intptr_t sa) { return (sse_t)pixelcmp<P>(X265CU_SSD_S, a, sa, NULL, 0, N, N, 2, 2); }
+    template <int N> static uint64_t var(const P* a, intptr_t sa) { return pixelcmp<P>(X265CU_VAR, a, sa, NULL, 0, N, N, sizeof(P), sizeof(P)); }
+    template <int N> static int psy(const P* a, intptr_t sa, const P* b, intptr_t sb) { return (int)pixelcmp<P>(X265CU_PSY, a, sa, b, sb, N, N, sizeof(P), sizeof(P)); }
+    template <int N> static void sub_ps(int16_t* d, intptr_t ds, const P* a, const P* b, intptr_t sa, intptr_t sb) { blockop<P>(X265CU_SUB_PS, d, ds, N, N, 2, a, sa, N, N, sizeof(P), b, sb, N, N, sizeof(P), N, N); }
+    template <int N> static void add_ps(P* d, intptr_t ds, const P* a, const int16_t* r, intptr_t sa, intptr_t sr) { blockop<P>(X265CU_ADD_PS, d, ds, N, N, sizeof(P), a, sa, N, N, sizeof(P), r, sr, N, N, 2, N, N); }
+    template <int N> static void calcresidual(const P* f, const P* p, int16_t* r, intptr_t st) { blockop<P>(X265CU_SUB_PS, r, st, N, N, 2, f, st, N, N, sizeof(P), p, st, N, N, sizeof(P), N, N); }
+    template <int N> static void copy_ss(int16_t* d, intptr_t ds, const int16_t* s, intptr_t ss) { blockop<P>(X265CU_COPY_SS, d, ds, N, N, 2, s, ss, N, N, 2, NULL, 0, 0, 0, 1, N, N); }
+    template <int N> static void copy_sp(P* d, intptr_t ds, const int16_t* s, intptr_t ss) { blockop<P>(X265CU_COPY_SP, d, ds, N, N, sizeof(P), s, ss, N, N, 2, NULL, 0, 0, 0, 1, N, N); }
+    template <int N> static void copy_ps(int16_t* d, intptr_t ds, const P* s, intptr_t ss) { blockop<P>(X265CU_COPY_PS, d, ds, N, N, 2, s, ss, N, N, sizeof(P), NULL, 0, 0, 0, 1, N, N); }
+    template <int N> static void transpose(P* d, const P* s, intptr_t ss) { blockop<P>(X265CU_TRANSPOSE, d, N, N, N, sizeof(P), s, ss, N, N, sizeof(P), NULL, 0, 0, 0, 1, N, N); }
+    template <int N> static void blockfill_s(int16_t* d, intptr_t ds, int16_t v) { blockop<P>(X265CU_BLOCKFILL_S, d, ds, N, N, 2, NULL, 0, 0, 0, 1, NULL, 0, 0, 0, 1, N, N, v); }
+    template <int N> static void cpy2Dto1D_shl(int16_t* d, const int16_t* s, intptr_t ss, int sh) { blockop<P>(X265CU_CPY2DTO1D_SHL, d, N, N, N, 2, s, ss, N, N, 2, NULL, 0, 0, 0, 1, N, N, sh); }
+    template <int N> static void cpy2Dto1D_shr(int16_t* d, const int16_t* s, intptr_t ss, int sh) { blockop<P>(X265CU_CPY2DTO1D_SHR, d, N, N, N, 2, s, ss, N, N, 2, NULL, 0, 0, 0, 1, N, N, sh); }
+    template <int N> static void cpy1Dto2D_shl(int16_t* d, const int16_t* s, intptr_t ds, int sh) { blockop<P>(X265CU_CPY1DTO2D_SHL, d, ds, N, N, 2, s, N, N, N, 2, NULL, 0, 0, 0, 1, N, N, sh); }
+    template <int N> static void cpy1Dto2D_shr(int16_t* d, const int16_t* s, intptr_t ds, int sh) { blockop<P>(X265CU_CPY1DTO2D_SHR, d, ds, N, N, 2, s, N, N, N, 2, NULL, 0, 0, 0, 1, N, N, sh); }
+    template <int N> static uint32_t copy_cnt(int16_t* coeff, const int16_t* resi, intptr_t rs) { return count_nonzero_blk(resi, rs, N, coeff); }
+    template <int N> static int count_nonzero(const int16_t* q) { return (int)count_nonzero_blk(q, N, N, NULL); }
+    template <int N> static void dct(const int16_t* s, int16_t* d, intptr_t st) { transform<P>(X265CU_DCT, N, s, d, st); }
+    template <int N> static void idct(const int16_t* s, int16_t* d, intptr_t st) { transform<P>(X265CU_IDCT, N, s, d, st); }
+    static void dst4(const int16_t* s, int16_t* d, intptr_t st) { transform<P>(X265CU_DST4, 4, s, d, st); }
+    static void idst4(const int16_t* s, int16_t* d, intptr_t st) { transform<P>(X265CU_IDST4, 4, s, d, st); }
+    template <int N> static void intra_predf(P* d, intptr_t ds, const P* nb, int mode, int bf) { intra_pred<P>(N, d, ds, nb, mode, bf); }
+    template <int N> static void intra_filterf(const P* nb, P* f) { intra_filter<P>(N, nb, f); }
+    template <int N> static void intra_allangsf(P* d, P* r, P* f, int bl) { intra_allangs<P>(N, d, r, f, bl); }
+    static uint32_t quantf(const int16_t* c, const int32_t* q, int32_t* du, int16_t* qc, int qb, int add, int n) { return quant(c, q, du, qc, qb, add, n, 0); }
+    static uint32_t nquantf(const int16_t* c, const int32_t* q, int16_t* qc, int qb, int add, int n) { return quant(c, q, NULL, qc, qb, add, n, 1); }
+    static void scale2D(P* d, const P* s, intptr_t ss) { blockop<P>(X265CU_SCALE2D_64TO32, d, 32, 32, 32, sizeof(P), s, ss, 64, 64, sizeof(P), NULL, 0, 0, 0, 1, 32, 32); }
+    static void weight_pp(const P* s, P* d, intptr_t st, int w, int h, int w0, int rnd, int sh, int off) { blockop<P>(X265CU_WEIGHT_PP, d, st, w, h, sizeof(P), s, st, w, h, sizeof(P), NULL, 0, 0, 0, 1, w, h, w0, rnd, sh, off); }
+    static void weight_sp(const int16_t* s, P* d, intptr_t ss, intptr_t ds, int w, int h, int w0, int rnd, int sh, int off) { blockop<P>(X265CU_WEIGHT_SP, d, ds, w, h, sizeof(P), s, ss, w, h, 2, NULL, 0, 0, 0, 1, w, h, w0, rnd, sh, off); }
+    static void lowres(const P* s, P* d0, P* dh, P* dv, P* dc, intptr_t ss, intptr_t ds, int w, int h) { frame_init_lowres<P>(s, d0, dh, dv, dc, ss, ds, w, h); }
+};
+
+// 25 PU sizes in LumaPU order (primitives.h:41-55)
+#define PU_LIST(F) { (void*)F<4,4>, (void*)F<8,8>, (void*)F<16,16>, (void*)F<32,32>, (void*)F<64,64>, (void*)F<8,4>, (void*)F<4,8>, \
+    (void*)F<16,8>, (void*)F<8,16>, (void*)F<32,16>, (void*)F<16,32>, (void*)F<64,32>, (void*)F<32,64>, (void*)F<16,12>, (void*)F<12,16>, \
+    (void*)F<16,4>, (void*)F<4,16>, (void*)F<32,24>, (void*)F<24,32>, (void*)F<32,8>, (void*)F<8,32>, (void*)F<64,48>, (void*)F<48,64>, \
+    (void*)F<64,16>, (void*)F<16,64> }
+#define PU_LIST_NT(F, NT) { (void*)F<NT,4,4>, (void*)F<NT,8,8>, (void*)F<NT,16,16>, (void*)F<NT,32,32>, (void*)F<NT,64,64>, (void*)F<NT,8,4>, (void*)F<NT,4,8>, \
+    (void*)F<NT,16,8>, (void*)F<NT,8,16>, (void*)F<NT,32,16>, (void*)F<NT,16,32>, (void*)F<NT,64,32>, (void*)F<NT,32,64>, (void*)F<NT,16,12>, (void*)F<NT,12,16>, \
+    (void*)F<NT,16,4>, (void*)F<NT,4,16>, (void*)F<NT,32,24>, (void*)F<NT,24,32>, (void*)F<NT,32,8>, (void*)F<NT,8,32>, (void*)F<NT,64,48>, (void*)F<NT,48,64>, \
+    (void*)F<NT,64,16>, (void*)F<NT,16,64> }
+// 4:2:0 chroma block of a luma PU: (W/2, H/2); entries with a dimension < 2 do not exist
+#define PU_LIST_C420(F, NT) { (void*)F<NT,2,2>, (void*)F<NT,4,4>, (void*)F<NT,8,8>, (void*)F<NT,16,16>, (void*)F<NT,32,32>, (void*)F<NT,4,2>, (void*)F<NT,2,4>, \
+    (void*)F<NT,8,4>, (void*)F<NT,4,8>, (void*)F<NT,16,8>, (void*)F<NT,8,16>, (void*)F<NT,32,16>, (void*)F<NT,16,32>, (void*)F<NT,8,6>, (void*)F<NT,6,8>, \
+    (void*)F<NT,8,2>, (void*)F<NT,2,8>, (void*)F<NT,16,12>, (void*)F<NT,12,16>, (void*)F<NT,16,4>, (void*)F<NT,4,16>, (void*)F<NT,32,24>, (void*)F<NT,24,32>, \
+    (void*)F<NT,32,8>, (void*)F<NT,8,32> }
+#define CU_LIST(F) { (void*)F<4>, (void*)F<8>, (void*)F<16>, (void*)F<32>, (void*)F<64> }
+
+template <typename P>
+static void* lookup(const char* name, int i, int j, int k)
+{
+    typedef T<P> X;
+#define PU_ENTRY(key, F) if (!strcmp(name, key)) { static void* const t[25] = PU_LIST(X::template F); return (i >= 0 && i < 25) ? t[i] : NULL; }
+#define PU_ENTRY_NT(key, F, NT) if (!strcmp(name, key)) { static void* const t[25] = PU_LIST_NT(X::template F, NT); return (i >= 0 && i < 25) ? t[i] : NULL; }
+#define PU_ENTRY_C(key, F) if (!strcmp(name, key)) { if (k != 1) return NULL; static void* const t[25] = PU_LIST_C420(X::template F, 4); return (i >= 0 && i < 25) ? t[i] : NULL; }
+#define CU_ENTRY(key, F, lo, hi) if (!strcmp(name, key)) { static void* const t[5] = CU_LIST(X::template F); return (i >= lo && i <= hi) ? t[i] : NULL; }
+    PU_ENTRY("pu.sad", sad) PU_ENTRY("pu.satd", satd) PU_ENTRY("pu.sad_x3", sad_x3) PU_ENTRY("pu.sad_x4", sad_x4) PU_ENTRY("pu.ads", adsf)
+    PU_ENTRY("pu.copy_pp", copy_pp) PU_ENTRY("pu.pixelavg_pp", pixelavg_pp) PU_ENTRY("pu.addAvg", addAvg) PU_ENTRY("pu.convert_p2s", p2s)
+    PU_ENTRY_NT("pu.luma_hpp", hpp, 8) PU_ENTRY_NT("pu.luma_hps", hps, 8) PU_ENTRY_NT("pu.luma_vpp", vpp, 8) PU_ENTRY_NT("pu.luma_vps", vps, 8)
+    PU_ENTRY_NT("pu.luma_vsp", vsp, 8) PU_ENTRY_NT("pu.luma_vss", vss, 8) PU_ENTRY_NT("pu.luma_hvpp", hvpp, 8)
+    PU_ENTRY_C("chroma.pu.filter_hpp", hpp) PU_ENTRY_C("chroma.pu.filter_hps", hps) PU_ENTRY_C("chroma.pu.filter_vpp", vpp)
+    PU_ENTRY_C("chroma.pu.filter_vps", vps) PU_ENTRY_C("chroma.pu.filter_vsp", vsp) PU_ENTRY_C("chroma.pu.filter_vss", vss)
+    if (!strcmp(name, "chroma.pu.satd"))
+    {   // 4:2:0: luma satd of the chroma-sized block (alias pass, primitives.cpp:88-209); NULL unless multiple of 4x4
+        if (k != 1) return NULL;
+        static void* const t[25] = { NULL, (void*)X::template satd<4,4>, (void*)X::template satd<8,8>, (void*)X::template satd<16,16>, (void*)X::template satd<32,32>,
+            NULL, NULL, (void*)X::template satd<8,4>, (void*)X::template satd<4,8>, (void*)X::template satd<16,8>, (void*)X::template satd<8,16>,
+            (void*)X::template satd<32,16>, (void*)X::template satd<16,32>, NULL, NULL, NULL, NULL, (void*)X::template satd<16,12>, (void*)X::template satd<12,16>,
+            (void*)X::template satd<16,4>, (void*)X::template satd<4,16>, (void*)X::template satd<32,24>, (void*)X::template satd<24,32>,
+            (void*)X::template satd<32,8>, (void*)X::template satd<8,32> };
+        return (i >= 0 && i < 25) ? t[i] : NULL;
+    }
+    if (!strcmp(name, "chroma.cu.sa8d"))
+    {
+        if (k != 1) return NULL;
+        static void* const t[5] = { NULL, (void*)X::template satd<4,4>, (void*)X::template sa8d<8,8>, (void*)X::template sa8d<16,16>, (void*)X::template sa8d<32,32> };
+        return (i >= 0 && i < 5) ? t[i] : NULL;
+    }
+    if (!strcmp(name, "cu.sa8d"))
+    {   // post-alias table: 4x4 uses satd (primitives.cpp:88-209)
+        static void* const t[5] = { (void*)X::template satd<4,4>, (void*)X::template sa8d<8,8>, (void*)X::template sa8d<16,16>, (void*)X::template sa8d<32,32>, (void*)X::template sa8d<64,64> };
+        return (i >= 0 && i < 5) ? t[i] : NULL;
+    }
+    CU_ENTRY("cu.sse_pp", sse_pp, 0, 4) CU_ENTRY("cu.sse_ss", sse_ss, 0, 4) CU_ENTRY("cu.ssd_s", ssd_s, 0, 4) CU_ENTRY("cu.var", var, 0, 4)
+    CU_ENTRY("cu.psy_cost_pp", psy, 0, 4) CU_ENTRY("cu.sub_ps", sub_ps, 0, 4) CU_ENTRY("cu.add_ps", add_ps, 0, 4)
+    CU_ENTRY("cu.calcresidual", calcresidual, 0, 4) CU_ENTRY("cu.copy_ss", copy_ss, 0, 4) CU_ENTRY("cu.copy_sp", copy_sp, 0, 4)
+    CU_ENTRY("cu.copy_ps", copy_ps, 0, 4) CU_ENTRY("cu.transpose", transpose, 0, 4) CU_ENTRY("cu.blockfill_s", blockfill_s, 0, 4)
+    CU_ENTRY("cu.cpy2Dto1D_shl", cpy2Dto1D_shl, 0, 3) CU_ENTRY("cu.cpy2Dto1D_shr", cpy2Dto1D_shr, 0, 3)
+    CU_ENTRY("cu.cpy1Dto2D_shl", cpy1Dto2D_shl, 0, 3) CU_ENTRY("cu.cpy1Dto2D_shr", cpy1Dto2D_shr, 0, 3)
+    CU_ENTRY("cu.copy_cnt", copy_cnt, 0, 3) CU_ENTRY("cu.count_nonzero", count_nonzero, 0, 3)
+    CU_ENTRY("cu.dct", dct, 0, 3) CU_ENTRY("cu.idct", idct, 0, 3)
+    CU_ENTRY("cu.intra_filter", intra_filterf, 0, 3) CU_ENTRY("cu.intra_pred_allangs", intra_allangsf, 0, 3)
+    if (!strcmp(name, "cu.intra_pred")) { static void* const t[5] = CU_LIST(X::template intra_predf); return (i >= 0 && i <= 3 && j >= 0 && j < 35) ? t[i] : NULL; }
+    if (!strcmp(name, "cu.copy_pp")) { static void* const t[5] = { (void*)X::template copy_pp<4,4>, (void*)X::template copy_pp<8,8>, (void*)X::template copy_pp<16,16>, (void*)X::template copy_pp<32,32>, (void*)X::template copy_pp<64,64> }; return (i >= 0 && i < 5) ? t[i] : NULL; }
+    if (!strcmp(name, "dst4x4")) return (void*)X::dst4;
+    if (!strcmp(name, "idst4x4")) return (void*)X::idst4;
+    if (!strcmp(name, "quant")) return (void*)X::quantf;
+    if (!strcmp(name, "nquant")) return (void*)X::nquantf;
+    if (!strcmp(name, "dequant_normal")) return (void*)dequant_normal;
+    if (!strcmp(name, "dequant_scaling")) return (void*)dequant_scaling;
+    if (!strcmp(name, "denoiseDct")) return (void*)denoise;
+    if (!strcmp(name, "scale2D_64to32")) return (void*)X::scale2D;
+    if (!strcmp(name, "weight_pp")) return (void*)X::weight_pp;
+    if (!strcmp(name, "weight_sp")) return (void*)X::weight_sp;
+    if (!strcmp(name, "frameInitLowres") || !strcmp(name, "frameInitLowerRes")) return (void*)X::lowres;
+    return NULL;
+}
+
+} // namespace thunk
+
+extern "C" void* x265cu_get_primitive(int depth, const char* name, int i, int j, int k)
+{
+    if (x265cu_device_count() <= 0)
+    {
+        fprintf(stderr, "x265cu: no CUDA device: the primitive table is unavailable (no CPU fallback)\n");
+        return NULL;
+    }
+    if (depth == 8) return thunk::lookup<uint8_t>(name, i, j, k);
+    if (depth == 10) return thunk::lookup<uint16_t>(name, i, j, k);
+    return NULL;
+}

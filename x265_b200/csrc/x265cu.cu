@@ -1,0 +1,218 @@
+// x265_b200/csrc/x265cu.cu -- the single translation unit of libx265cu.so: context, memory,
+// batched C-ABI entry points (include/x265_b200.h) and the per-call primitive table.
+#include "common.cuh"
+#include "pixelcmp.cuh"
+#include "blockops.cuh"
+#include "interp.cuh"
+#include "transform.cuh"
+#include "intra.cuh"
+#include "me.cuh"
+#include "frame.cuh"
+#include <math.h>
+#include <mutex>
+
+static thread_local char g_err[512] = "";
+void x265cu_set_error(const char* what, cudaError_t e, const char* file, int line)
+{
+    snprintf(g_err, sizeof(g_err), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    fprintf(stderr, "x265cu: %s\n", g_err);
+}
+
+extern "C" {
+
+const char* x265cu_last_error(void) { return g_err; }
+
+int x265cu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+x265cu_ctx* x265cu_create(int device)
+{
+    if (device < 0 || device >= x265cu_device_count())
+    {
+        snprintf(g_err, sizeof(g_err), "no CUDA device %d (libx265cu has no CPU fallback)", device);
+        return NULL;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return NULL;
+    x265cu_ctx* c = new x265cu_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NULL; }
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    if (build_dct_tables() != 0) { delete c; return NULL; }
+    c->stage_bytes = 4u << 20;
+    if (cudaMallocHost((void**)&c->h_stage, c->stage_bytes) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_stage, c->stage_bytes) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_counter, 64) != cudaSuccess)
+    {
+        x265cu_set_error("ctx alloc", cudaGetLastError(), __FILE__, __LINE__);
+        delete c; return NULL;
+    }
+    return c;
+}
+
+void x265cu_destroy(x265cu_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFreeHost(c->h_stage); cudaFree(c->d_stage); cudaFree(c->d_counter);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int x265cu_sync(x265cu_ctx* c) { CU_CHECK(cudaStreamSynchronize(c->stream)); return 0; }
+void* x265cu_stream(x265cu_ctx* c) { return (void*)c->stream; }
+void* x265cu_malloc(x265cu_ctx* c, size_t bytes)
+{
+    void* p = NULL;
+    cudaSetDevice(c->device);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { x265cu_set_error("cudaMalloc", cudaGetLastError(), __FILE__, __LINE__); return NULL; }
+    return p;
+}
+void x265cu_free(x265cu_ctx* c, void* dev) { cudaSetDevice(c->device); cudaFree(dev); }
+void* x265cu_host_alloc(size_t bytes) { void* p = NULL; if (cudaMallocHost(&p, bytes) != cudaSuccess) return NULL; return p; }
+void x265cu_host_free(void* p) { cudaFreeHost(p); }
+int x265cu_h2d(x265cu_ctx* c, void* dev, const void* host, size_t bytes) { CU_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream)); return 0; }
+int x265cu_d2h(x265cu_ctx* c, void* host, const void* dev, size_t bytes) { CU_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream)); return 0; }
+int x265cu_memset(x265cu_ctx* c, void* dev, int value, size_t bytes) { CU_CHECK(cudaMemsetAsync(dev, value, bytes, c->stream)); return 0; }
+int x265cu_timer_begin(x265cu_ctx* c) { CU_CHECK(cudaEventRecord(c->ev0, c->stream)); return 0; }
+float x265cu_timer_end(x265cu_ctx* c)
+{
+    float ms = -1.f;
+    if (cudaEventRecord(c->ev1, c->stream) != cudaSuccess) return -1.f;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+uint64_t x265cu_launch_count(x265cu_ctx* c) { return c->launches; }
+
+// ---------------- batched API ----------------
+int x265cu_pixelcmp_batch(x265cu_ctx* c, int depth, int op, const void* A, const void* B, const x265cu_cmp_job* jobs, int n, uint64_t* out)
+{ return launch_pixelcmp(c, depth, op, A, B, jobs, n, out); }
+
+int x265cu_blockop_batch(x265cu_ctx* c, int depth, int op, void* D, const void* A, const void* B, const x265cu_blk_job* jobs, int n)
+{ return launch_blockop(c, depth, op, D, A, B, jobs, n); }
+
+int x265cu_interp_batch(x265cu_ctx* c, int depth, int op, const void* src, void* dst, const x265cu_interp_job* jobs, int n)
+{ return launch_interp(c, depth, op, src, dst, jobs, n); }
+
+int x265cu_transform_batch(x265cu_ctx* c, int depth, int op, int size, const int16_t* src, int16_t* dst, int stride, int64_t tu_pitch, int n)
+{ return launch_transform(c, depth, op, size, src, dst, stride, tu_pitch, n); }
+
+int x265cu_quant_batch(x265cu_ctx* c, const int16_t* coef, const int32_t* qc, int32_t* deltaU, int16_t* qCoef, int qBits, int add,
+                       int numCoeff, int n, int nquant, uint32_t* numSig)
+{
+    if (n <= 0) return 0;
+    int blocks = (n + 7) / 8; if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
+    k_quant<<<blocks, 256, 0, c->stream>>>(coef, qc, deltaU, qCoef, qBits, add, numCoeff, n, nquant, numSig);
+    CU_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int x265cu_dequant_normal_batch(x265cu_ctx* c, const int16_t* q, int16_t* coef, int64_t num, int scale, int shift)
+{
+    if (num <= 0) return 0;
+    int64_t blocks = (num + 255) / 256; if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
+    k_dequant_normal<<<(int)blocks, 256, 0, c->stream>>>(q, coef, num, scale, shift);
+    CU_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int x265cu_dequant_scaling_batch(x265cu_ctx* c, const int16_t* q, const int32_t* dq, int16_t* coef, int numCoeff, int n, int per, int shift)
+{
+    int64_t total = (int64_t)numCoeff * n;
+    if (total <= 0) return 0;
+    int64_t blocks = (total + 255) / 256; if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
+    k_dequant_scaling<<<(int)blocks, 256, 0, c->stream>>>(q, dq, coef, numCoeff, total, per, shift);
+    CU_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int x265cu_intra_pred_batch(x265cu_ctx* c, int depth, int size, const void* nb, int64_t nb_pitch, void* dst, int64_t dst_pitch, int dst_stride,
+                            const x265cu_intra_job* jobs, int n)
+{
+    if (n <= 0) return 0;
+    int blocks = n < c->sm_count * 8 ? n : c->sm_count * 8;
+    int threads = size * size < 256 ? (size * size < 32 ? 32 : size * size) : 256;
+    if (depth == 8) k_intra_pred<uint8_t><<<blocks, threads, 0, c->stream>>>(size, (const uint8_t*)nb, nb_pitch, (uint8_t*)dst, dst_pitch, dst_stride, jobs, n);
+    else            k_intra_pred<uint16_t><<<blocks, threads, 0, c->stream>>>(size, (const uint16_t*)nb, nb_pitch, (uint16_t*)dst, dst_pitch, dst_stride, jobs, n);
+    CU_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int x265cu_intra_filter_batch(x265cu_ctx* c, int depth, int size, const void* nb, void* filt, int64_t pitch, int n)
+{
+    if (n <= 0) return 0;
+    int blocks = n < c->sm_count * 8 ? n : c->sm_count * 8;
+    if (depth == 8) k_intra_filter<uint8_t><<<blocks, 160, 0, c->stream>>>(size, (const uint8_t*)nb, (uint8_t*)filt, pitch, n);
+    else            k_intra_filter<uint16_t><<<blocks, 160, 0, c->stream>>>(size, (const uint16_t*)nb, (uint16_t*)filt, pitch, n);
+    CU_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int x265cu_intra_allangs_batch(x265cu_ctx* c, int depth, int size, const void* ref, const void* filt, int64_t nb_pitch, void* dst, int bLuma, int n)
+{
+    if (n <= 0) return 0;
+    dim3 grid(33, n < 4096 ? n : 4096);
+    int threads = size * size < 256 ? (size * size < 32 ? 32 : size * size) : 256;
+    if (depth == 8) k_intra_allangs<uint8_t><<<grid, threads, 0, c->stream>>>(size, (const uint8_t*)ref, (const uint8_t*)filt, nb_pitch, (uint8_t*)dst, bLuma, n);
+    else            k_intra_allangs<uint16_t><<<grid, threads, 0, c->stream>>>(size, (const uint16_t*)ref, (const uint16_t*)filt, nb_pitch, (uint16_t*)dst, bLuma, n);
+    CU_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int x265cu_extend_border(x265cu_ctx* c, int depth, void* plane, int stride, int width, int height, int mx, int my)
+{
+    if (depth == 8) return extend_border_t<uint8_t>(c, (uint8_t*)plane, stride, width, height, mx, my);
+    return extend_border_t<uint16_t>(c, (uint16_t*)plane, stride, width, height, mx, my);
+}
+
+int x265cu_frame_init_lowres(x265cu_ctx* c, int depth, const void* src, int sstride, void* d0, void* dh, void* dv, void* dc,
+                             int dstride, int width, int height, int mx, int my)
+{
+    dim3 block(64, 4), grid((width / 4 + 63) / 64 + 1, (height + 3) / 4);
+    if (depth == 8)
+        k_lowres_init<uint8_t><<<grid, block, 0, c->stream>>>((const uint8_t*)src, sstride, (uint8_t*)d0, (uint8_t*)dh, (uint8_t*)dv, (uint8_t*)dc, dstride, width, height);
+    else
+        k_lowres_init<uint16_t><<<grid, block, 0, c->stream>>>((const uint16_t*)src, sstride, (uint16_t*)d0, (uint16_t*)dh, (uint16_t*)dv, (uint16_t*)dc, dstride, width, height);
+    CU_LAUNCH_CHECK(c);
+    if (mx > 0 || my > 0)
+    {
+        void* planes[4] = { d0, dh, dv, dc };
+        for (int i = 0; i < 4; i++)
+            if (x265cu_extend_border(c, depth, planes[i], dstride, width, height, mx, my)) return -1;
+    }
+    return 0;
+}
+
+// bitcost.cpp:95-109 + :49-55 (host helper; float log, double lambda, cap 2^15-1)
+void x265cu_mvcost_table(double lambda, int range, uint16_t* out)
+{
+    float log2_2 = 2.0f / logf(2.0f);
+    for (int i = 0; i <= range; i++)
+    {
+        float bits = i ? logf((float)(i + 1)) * log2_2 + 1.718f : 0.718f;
+        double v = bits * lambda + 0.5f;
+        if (v > 32767.0) v = 32767.0;
+        out[range + i] = out[range - i] = (uint16_t)v;
+    }
+}
+
+int x265cu_me_batch(x265cu_ctx* c, int depth, const void* fenc, int fencStride, const void* const* refs, int refStride, int lowres,
+                    const uint16_t* mvcost, int mvcost_range, const x265cu_me_job* jobs, int n, int32_t* out)
+{
+    (void)mvcost_range;
+    return launch_me(c, depth, fenc, fencStride, refs, refStride, lowres, mvcost, jobs, n, out, c->d_counter);
+}
+
+} // extern "C"
+
+#include "thunks.cuh"

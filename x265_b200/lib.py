@@ -1,0 +1,197 @@
+"""ctypes binding of libx265cu.so (include/x265_b200.h).  Host-side plumbing only: the arithmetic is
+all in the CUDA library.  Raises CudaUnavailable instead of falling back when no GPU is present."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+P = C.c_void_p
+I = C.c_int
+I64 = C.c_int64
+IP = C.c_ssize_t
+
+
+class CudaUnavailable(RuntimeError):
+    pass
+
+
+# job record layouts (must match include/x265_b200.h)
+CMP_JOB = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("a_stride", "<i4"), ("b_stride", "<i4"),
+                    ("w", "<i2"), ("h", "<i2"), ("pad", "<i4")], align=True)
+BLK_JOB = np.dtype([("d_off", "<i8"), ("a_off", "<i8"), ("b_off", "<i8"), ("d_stride", "<i4"), ("a_stride", "<i4"),
+                    ("b_stride", "<i4"), ("w", "<i2"), ("h", "<i2"), ("p0", "<i4"), ("p1", "<i4"), ("p2", "<i4"), ("p3", "<i4")], align=True)
+INTERP_JOB = np.dtype([("s_off", "<i8"), ("d_off", "<i8"), ("s_stride", "<i4"), ("d_stride", "<i4"), ("w", "<i2"), ("h", "<i2"),
+                       ("idxX", "i1"), ("idxY", "i1"), ("rowExt", "i1"), ("ntaps", "i1")], align=True)
+INTRA_JOB = np.dtype([("mode", "<i4"), ("bFilter", "<i4")], align=True)
+ME_JOB = np.dtype([("offset", "<i4"), ("ref", "<i2"), ("pw", "i1"), ("ph", "i1"), ("mvmin", "<i2", 2), ("mvmax", "<i2", 2),
+                   ("qmvp", "<i2", 2), ("mvc", "<i2", 8), ("numCand", "i1"), ("method", "i1"), ("subme", "i1"), ("merange", "i1")], align=True)
+assert CMP_JOB.itemsize == 32 and BLK_JOB.itemsize == 56 and INTERP_JOB.itemsize == 32 and ME_JOB.itemsize == 40
+
+OPS_CMP = dict(sad=0, satd=1, sa8d=2, sse_pp=3, sse_ss=4, ssd_s=5, var=6, psy=7)
+OPS_BLK = dict(copy_pp=0, copy_ss=1, copy_sp=2, copy_ps=3, sub_ps=4, add_ps=5, pixelavg_pp=6, addAvg=7, p2s=8, transpose=9,
+               blockfill_s=10, cpy2Dto1D_shl=11, cpy2Dto1D_shr=12, cpy1Dto2D_shl=13, cpy1Dto2D_shr=14, weight_pp=15,
+               weight_sp=16, scale2D_64to32=17, dequant_normal=18)
+OPS_INTERP = dict(hpp=0, hps=1, vpp=2, vps=3, vsp=4, vss=5, hvpp=6)
+OPS_TR = dict(dct=0, idct=1, dst4=2, idst4=3)
+
+_PROTOS = {
+    "x265cu_device_count": (I, []),
+    "x265cu_create": (P, [I]),
+    "x265cu_destroy": (None, [P]),
+    "x265cu_last_error": (C.c_char_p, []),
+    "x265cu_sync": (I, [P]),
+    "x265cu_stream": (P, [P]),
+    "x265cu_malloc": (P, [P, C.c_size_t]),
+    "x265cu_free": (None, [P, P]),
+    "x265cu_host_alloc": (P, [C.c_size_t]),
+    "x265cu_host_free": (None, [P]),
+    "x265cu_h2d": (I, [P, P, P, C.c_size_t]),
+    "x265cu_d2h": (I, [P, P, P, C.c_size_t]),
+    "x265cu_memset": (I, [P, P, I, C.c_size_t]),
+    "x265cu_timer_begin": (I, [P]),
+    "x265cu_timer_end": (C.c_float, [P]),
+    "x265cu_launch_count": (C.c_uint64, [P]),
+    "x265cu_get_primitive": (P, [I, C.c_char_p, I, I, I]),
+    "x265cu_pixelcmp_batch": (I, [P, I, I, P, P, P, I, P]),
+    "x265cu_blockop_batch": (I, [P, I, I, P, P, P, P, I]),
+    "x265cu_interp_batch": (I, [P, I, I, P, P, P, I]),
+    "x265cu_transform_batch": (I, [P, I, I, I, P, P, I, I64, I]),
+    "x265cu_quant_batch": (I, [P, P, P, P, P, I, I, I, I, I, P]),
+    "x265cu_dequant_normal_batch": (I, [P, P, P, I64, I, I]),
+    "x265cu_dequant_scaling_batch": (I, [P, P, P, P, I, I, I, I]),
+    "x265cu_intra_pred_batch": (I, [P, I, I, P, I64, P, I64, I, P, I]),
+    "x265cu_intra_filter_batch": (I, [P, I, I, P, P, I64, I]),
+    "x265cu_intra_allangs_batch": (I, [P, I, I, P, P, I64, P, I, I]),
+    "x265cu_frame_init_lowres": (I, [P, I, P, I, P, P, P, P, I, I, I, I, I]),
+    "x265cu_extend_border": (I, [P, I, P, I, I, I, I, I]),
+    "x265cu_mvcost_table": (None, [C.c_double, I, P]),
+    "x265cu_me_batch": (I, [P, I, P, I, P, I, I, P, I, P, I, P]),
+}
+
+
+class DeviceBuffer:
+    """A device allocation owned by the Lib context."""
+
+    def __init__(self, lib, nbytes):
+        self.lib = lib
+        self.nbytes = int(nbytes)
+        self.ptr = lib.L.x265cu_malloc(lib.ctx, max(self.nbytes, 16))
+        if not self.ptr:
+            raise MemoryError("x265cu_malloc(%d) failed: %s" % (nbytes, lib.last_error()))
+
+    def upload(self, arr, offset=0):
+        arr = np.ascontiguousarray(arr)
+        assert offset + arr.nbytes <= self.nbytes
+        self.lib.check(self.lib.L.x265cu_h2d(self.lib.ctx, self.ptr + offset, arr.ctypes.data, arr.nbytes))
+        self.lib.sync()          # pageable source: make the copy complete before numpy may free it
+        return self
+
+    def download(self, dtype, count=None, offset=0):
+        dt = np.dtype(dtype)
+        if count is None:
+            count = (self.nbytes - offset) // dt.itemsize
+        out = np.empty(count, dt)
+        self.lib.check(self.lib.L.x265cu_d2h(self.lib.ctx, out.ctypes.data, self.ptr + offset, out.nbytes))
+        self.lib.sync()
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.lib.L.x265cu_free(self.lib.ctx, self.ptr)
+            self.ptr = None
+
+
+class Lib:
+    def __init__(self, device=0, need_gpu=True):
+        path = _build.build()
+        self.path = path
+        self.L = C.CDLL(path)
+        for name, (res, args) in _PROTOS.items():
+            f = getattr(self.L, name)       # AttributeError if the ABI lost a symbol
+            f.restype = res
+            f.argtypes = args
+        self.ctx = None
+        if need_gpu:
+            if self.L.x265cu_device_count() <= 0:
+                raise CudaUnavailable("libx265cu.so loaded but no CUDA device is visible; there is no CPU fallback")
+            self.ctx = self.L.x265cu_create(device)
+            if not self.ctx:
+                raise CudaUnavailable("x265cu_create(%d) failed: %s" % (device, self.last_error()))
+
+    # ---- plumbing ----
+    def last_error(self):
+        e = self.L.x265cu_last_error()
+        return e.decode() if e else ""
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError("x265cu call failed: " + self.last_error())
+
+    def sync(self):
+        self.check(self.L.x265cu_sync(self.ctx))
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, arr.nbytes).upload(arr)
+
+    def timer_begin(self):
+        self.check(self.L.x265cu_timer_begin(self.ctx))
+
+    def timer_end(self):
+        ms = self.L.x265cu_timer_end(self.ctx)
+        if ms < 0:
+            raise RuntimeError("timer failed: " + self.last_error())
+        return ms
+
+    def launch_count(self):
+        return int(self.L.x265cu_launch_count(self.ctx))
+
+    def close(self):
+        if self.ctx:
+            self.L.x265cu_destroy(self.ctx)
+            self.ctx = None
+
+    # ---- per-call table ----
+    def primitive(self, depth, name, restype, argtypes, i=0, j=0, k=0):
+        p = self.L.x265cu_get_primitive(depth, name.encode(), i, j, k)
+        if not p:
+            return None
+        return C.CFUNCTYPE(restype, *argtypes)(p)
+
+    # ---- batched API (device buffers in, device buffers out) ----
+    def pixelcmp_batch(self, depth, op, A, B, jobs_dev, n, out_dev):
+        self.check(self.L.x265cu_pixelcmp_batch(self.ctx, depth, OPS_CMP[op], A.ptr, B.ptr, jobs_dev.ptr, n, out_dev.ptr))
+
+    def blockop_batch(self, depth, op, D, A, B, jobs_dev, n):
+        self.check(self.L.x265cu_blockop_batch(self.ctx, depth, OPS_BLK[op], D.ptr, A.ptr if A else None, B.ptr if B else None, jobs_dev.ptr, n))
+
+    def interp_batch(self, depth, op, S, D, jobs_dev, n):
+        self.check(self.L.x265cu_interp_batch(self.ctx, depth, OPS_INTERP[op], S.ptr, D.ptr, jobs_dev.ptr, n))
+
+    def transform_batch(self, depth, op, size, S, D, stride, tu_pitch, n):
+        self.check(self.L.x265cu_transform_batch(self.ctx, depth, OPS_TR[op], size, S.ptr, D.ptr, stride, tu_pitch, n))
+
+    def me_batch(self, depth, fenc, fstride, refs_ptr_table, rstride, lowres, mvcost_dev, mvcost_range, jobs_dev, n, out_dev):
+        centre = mvcost_dev.ptr + 2 * mvcost_range
+        self.check(self.L.x265cu_me_batch(self.ctx, depth, fenc.ptr, fstride, refs_ptr_table.ptr, rstride, lowres, centre,
+                                          mvcost_range, jobs_dev.ptr, n, out_dev.ptr))
+
+    def mvcost_table(self, lam, rng):
+        t = np.zeros(2 * rng + 1, np.uint16)
+        self.L.x265cu_mvcost_table(C.c_double(lam), rng, t.ctypes.data)
+        return t
+
+
+_cached = {}
+
+
+def load(device=0, need_gpu=True):
+    key = (device, need_gpu)
+    if key not in _cached:
+        _cached[key] = Lib(device, need_gpu)
+    return _cached[key]
