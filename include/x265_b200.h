@@ -148,6 +148,34 @@ int x265cu_me_batch(x265cu_ctx*, int depth, const void* fenc_dev, int fencStride
                     const uint16_t* mvcost_dev /* centred table base */, int mvcost_range,
                     const x265cu_me_job* jobs_dev, int n, int32_t* out_dev);
 
+/* ---------- frame-level CTU analysis (DESIGN.md "Frame analysis workload") ----------
+ * One analyser = one picture geometry.  Reference planes stay resident in HBM (x265cu_analyser_set_ref
+ * = what the recon-row broadcast feeds); per frame the host passes the source luma and the 16x16
+ * predictor field (AMVP / lowres MVs, search.cpp:1968-2023, 2406-2410) and gets back, for every PU x
+ * reference, the motionEstimate() result (motion.cpp:739), for every CU the residual-coding stats of
+ * its best 2Nx2N prediction (search.cpp:3178; quant.cpp:397-470, 543-605) and its 35 intra SA8D costs
+ * (search.cpp:1358-1444).  stages: bit0 ME, bit1 residual, bit2 intra. */
+typedef struct x265cu_analyser x265cu_analyser;
+typedef struct {
+    int width, height, depth, numRefs;
+    int method, subme, merange, rect;     /* X265_*_SEARCH, subpel refine level, range, rect PUs */
+    int qp; double lambda;                /* quant QP; mvcost lambda (x265_lambda_tab[qp]) */
+} x265cu_analysis_params;
+typedef struct {                          /* host destinations (any may be NULL) */
+    int32_t*  me_packed;                  /* [njobs][2]: cost, (mvx | mvy << 16) */
+    uint64_t* cu_sse; uint32_t* cu_numsig; int32_t* cu_ref;   /* [ncu] */
+    uint32_t* intra_cost;                 /* [ncu][36]: 35 costs + best mode */
+} x265cu_analysis_out;
+x265cu_analyser* x265cu_analyser_create(x265cu_ctx*, const x265cu_analysis_params*);
+void x265cu_analyser_destroy(x265cu_analyser*);
+int x265cu_analyser_counts(x265cu_analyser*, int* njobs, int* ncu, int* ntu, int64_t* ncoef, int* stride);
+int x265cu_analyser_set_ref(x265cu_analyser*, int idx, const void* host_luma, int host_stride);
+int x265cu_analyser_load_inputs(x265cu_analyser*, const void* fenc_host, int host_stride, const int16_t* field_host);
+int x265cu_analyser_run_resident(x265cu_analyser*, int stages);       /* kernels only, inputs resident */
+int x265cu_analyser_analyse(x265cu_analyser*, const void* fenc_host, int host_stride, const int16_t* field_host,
+                            int stages, x265cu_analysis_out* out);    /* H2D + kernels + D2H, synchronous */
+int x265cu_analyser_fetch(x265cu_analyser*, int what, void* host);    /* parity/debug access to resident results */
+
 #ifdef __cplusplus
 }
 #endif

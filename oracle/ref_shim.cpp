@@ -156,3 +156,68 @@ int x265ref_motion_estimate(pixel* fencPlane, intptr_t fencStride, intptr_t offs
 }
 
 } // extern "C"
+
+/* ------------------------------------------------------------------------------------------
+ * Frame-level CTU-analysis workload over the REAL reference code: MotionEstimate class for the
+ * ME stage, the post-alias C primitive table for the residual and intra stages.  Same driver
+ * source as the oracle (frame_driver.h); this is bench.py's `--impl reference` arm.
+ * ------------------------------------------------------------------------------------------ */
+#define DRV_PIXEL pixel
+#define DRV_DEPTH X265_DEPTH
+#include "frame_spec.h"
+
+static int ref_drv_me(const void* fv, const fs_me_job* j, int* qmv);
+static inline int lg2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+#define DRV_ME(f, j, qmv) ref_drv_me(f, j, qmv)
+#define DRV_MC(src, ss, dst, ds, S, xf, yf) do { int part_ = partitionFromSizes(S, S); \
+        if (!((xf) | (yf))) g_c.pu[part_].copy_pp(dst, ds, src, ss); \
+        else if (!(yf)) g_c.pu[part_].luma_hpp(src, ss, dst, ds, xf); \
+        else if (!(xf)) g_c.pu[part_].luma_vpp(src, ss, dst, ds, yf); \
+        else g_c.pu[part_].luma_hvpp(src, ss, dst, ds, xf, yf); } while (0)
+#define DRV_SUB_PS(d, ds, a, b, sa, sb, T) g_c.cu[lg2(T) - 2].sub_ps(d, ds, a, b, sa, sb)
+#define DRV_DCT(src, dst, stride, T) g_c.cu[lg2(T) - 2].dct(src, dst, stride)
+#define DRV_IDCT(src, dst, stride, T) g_c.cu[lg2(T) - 2].idct(src, dst, stride)
+#define DRV_QUANT(c, qc, du, q, qbits, add, n) g_c.quant(c, qc, du, q, qbits, add, n)
+#define DRV_DEQUANT(q, c, n, scale, shift) g_c.dequant_normal(q, c, n, scale, shift)
+#define DRV_BLOCKFILL(d, ds, v, T) g_c.cu[lg2(T) - 2].blockfill_s[0](d, ds, v)
+#define DRV_ADD_PS(d, ds, a, r, sa, sr, T) g_c.cu[lg2(T) - 2].add_ps[0](d, ds, a, r, sa, sr)
+#define DRV_COPY_PP(d, ds, s, ss, T) g_c.cu[lg2(T) - 2].copy_pp(d, ds, s, ss)
+#define DRV_SSE(a, sa, b, sb, T) g_c.cu[lg2(T) - 2].sse_pp(a, sa, b, sb)
+#define DRV_INTRA_FILTER(nb, f, S) g_c.cu[lg2(S) - 2].intra_filter(nb, f)
+#define DRV_INTRA_PRED(d, ds, nb, mode, bf, S) g_c.cu[lg2(S) - 2].intra_pred[mode](d, ds, nb, mode, bf)
+#define DRV_USE_FILTERED(mode, S) ((g_intraFilterFlags[mode] & (S)) != 0)
+#define DRV_SA8D(a, sa, b, sb, S) g_c.cu[lg2(S) - 2].sa8d(a, sa, b, sb)
+#include "frame_driver.h"
+
+static int ref_drv_me(const void* fv, const fs_me_job* j, int* qmv)
+{
+    const drv_frame* f = (const drv_frame*)fv;
+    static thread_local MotionEstimate* me = NULL;
+    static thread_local int meqp = -1;
+    if (!me) { me = new MotionEstimate(); me->init(X265_CSP_I400); }
+    if (meqp != f->p.qp) { me->setQP(f->p.qp); meqp = f->p.qp; }
+    me->setSourcePU((pixel*)f->fenc, f->p.stride, j->offset, j->pw, j->ph, j->method, j->method, j->method, j->subme);
+    ReferencePlanes ref;
+    ref.lumaStride = f->p.stride;
+    ref.isLowres = false;
+    ref.fpelPlane[0] = (pixel*)f->refs[j->ref];
+    MV mn(j->mvmin[0], j->mvmin[1]), mx(j->mvmax[0], j->mvmax[1]), mvp(j->qmvp[0], j->qmvp[1]), out;
+    MV cands[4];
+    for (int i = 0; i < j->numCand && i < 4; i++) cands[i] = MV(j->mvc[2 * i], j->mvc[2 * i + 1]);
+    int cost = me->motionEstimate(&ref, mn, mx, mvp, j->numCand, cands, j->merange, out, 1, NULL);
+    qmv[0] = out.x; qmv[1] = out.y;
+    return cost;
+}
+
+extern "C" int x265ref_analyse_frame(drv_frame* f, int stages)
+{
+    ensure_init();
+    static bool scales = false;
+    if (!scales) { MotionEstimate::initScales(); scales = true; }
+    { BitCost bc; bc.setQP(f->p.qp); }     /* build the shared cost tables before threads start */
+    drv_prepare(f);
+    if (stages & 1) drv_run_stage(f, 0);
+    if (stages & 2) drv_run_stage(f, 1);
+    if (stages & 4) drv_run_stage(f, 2);
+    return 0;
+}

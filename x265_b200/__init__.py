@@ -5,4 +5,4 @@ mirror used by tests and bench.py: it loads the library with ctypes and exposes 
 and the batched API on numpy arrays / raw device pointers.  There is no CPU fallback: importing
 works without a GPU (so the build can be checked), but every compute entry point raises without CUDA.
 """
-from .lib import Lib, load, DeviceBuffer, CudaUnavailable  # noqa: F401
+from .lib import Lib, load, DeviceBuffer, CudaUnavailable, Analyser  # noqa: F401

@@ -1,0 +1,276 @@
+// x265_b200/csrc/analyser.cuh -- host side of the frame-level CTU-analysis pipeline: geometry tables,
+// device residency of the source / reference planes, and the e2e (host buffers) / resident entry points.
+#pragma once
+#include "common.cuh"
+#include "frame.cuh"
+#include "me.cuh"
+#include <vector>
+
+struct x265cu_analyser
+{
+    x265cu_ctx* ctx;
+    x265cu_analysis_params p;
+    int stride, planeRows, fw, fh;
+    size_t planeBytes, orgBytes;        // origin pixel byte offset inside a plane allocation
+    int njobs, ncu, ntu; int64_t ncoef;
+    // device
+    uint8_t* d_fenc; uint8_t* d_refs[16]; uint8_t* d_recon[4];
+    void** d_refTable; void** d_reconTable;
+    int16_t* d_field; uint16_t* d_mvcost; int mvrange;
+    PuDesc* d_pus; CuDesc* d_cus; TuDesc* d_tus; int32_t* d_cu_jobs;
+    x265cu_me_job* d_jobs; int32_t* d_me_out; int2* d_me_packed;
+    int16_t* d_coef; unsigned long long* d_cu_sse; uint32_t* d_cu_numsig; int32_t* d_cu_ref; uint32_t* d_intra;
+    // pinned host staging for the e2e path
+    uint8_t* h_fenc; int16_t* h_field;
+    std::vector<PuDesc> pus; std::vector<CuDesc> cus; std::vector<TuDesc> tus; std::vector<int32_t> cu_jobs;
+};
+
+static const int AN_MARGIN_X = 96, AN_MARGIN_Y = 80;       // picyuv.cpp:87-88 with maxCUSize 64
+
+static void an_build_geometry(x265cu_analyser* a)
+{
+    const int W = a->p.width, H = a->p.height, nref = a->p.numRefs, stride = a->stride;
+    // CU list: CTU raster, sizes 64..8, raster inside the CTU; CUs must lie fully inside the picture
+    const int ctuW = (W + 63) / 64, ctuH = (H + 63) / 64;
+    int64_t coefOff = 0;
+    for (int cty = 0; cty < ctuH; cty++)
+        for (int ctx = 0; ctx < ctuW; ctx++)
+        {
+            const size_t cuBase = a->cus.size();
+            int local[85]; int nl = 0;
+            for (int size = 64; size >= 8; size >>= 1)
+                for (int cy = 0; cy < 64; cy += size)
+                    for (int cx = 0; cx < 64; cx += size, nl++)
+                    {
+                        const int x = ctx * 64 + cx, y = cty * 64 + cy;
+                        local[nl] = -1;
+                        if (x + size > W || y + size > H) continue;
+                        local[nl] = (int)a->cus.size();
+                        CuDesc c; c.x = (int16_t)x; c.y = (int16_t)y; c.size = (int16_t)size; c.pad = 0; c.coef_off = coefOff;
+                        coefOff += (int64_t)size * size;
+                        const int T = size > 32 ? 32 : size;
+                        for (int ty = 0; ty < size; ty += T)
+                            for (int tx = 0; tx < size; tx += T)
+                            {
+                                TuDesc t; t.cu = (int32_t)a->cus.size(); t.tx = (int16_t)tx; t.ty = (int16_t)ty;
+                                a->tus.push_back(t);
+                            }
+                        a->cus.push_back(c);
+                    }
+            (void)cuBase;
+            a->cu_jobs.resize(a->cus.size() * nref, -1);
+            // PU jobs of this CTU: per ref, per CU (same order), 2Nx2N then (rect) 2NxN x2, Nx2N x2
+            for (int r = 0; r < nref; r++)
+            {
+                int li = 0;
+                for (int size = 64; size >= 8; size >>= 1)
+                    for (int cy = 0; cy < 64; cy += size)
+                        for (int cx = 0; cx < 64; cx += size, li++)
+                        {
+                            const int half = size / 2;
+                            const int part[5][4] = { { 0, 0, size, size }, { 0, 0, size, half }, { 0, half, size, half },
+                                                     { 0, 0, half, size }, { half, 0, half, size } };
+                            const int np = a->p.rect ? 5 : 1;
+                            for (int k = 0; k < np; k++)
+                            {
+                                const int x = ctx * 64 + cx + part[k][0], y = cty * 64 + cy + part[k][1], w = part[k][2], h = part[k][3];
+                                if (x + w > W || y + h > H) continue;
+                                PuDesc d; d.offset = y * stride + x; d.cuX = (int16_t)(ctx * 64 + cx); d.cuY = (int16_t)(cty * 64 + cy);
+                                d.pw = (int8_t)w; d.ph = (int8_t)h; d.ref = (int16_t)r;
+                                if (k == 0) a->cu_jobs[(size_t)local[li] * nref + r] = (int32_t)a->pus.size();
+                                a->pus.push_back(d);
+                            }
+                        }
+            }
+        }
+    a->njobs = (int)a->pus.size(); a->ncu = (int)a->cus.size(); a->ntu = (int)a->tus.size(); a->ncoef = coefOff;
+}
+
+template <typename T> static T* an_upload(x265cu_ctx* c, const std::vector<T>& v)
+{
+    T* d = (T*)x265cu_malloc(c, v.size() * sizeof(T) + 16);
+    if (d && !v.empty()) cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+}
+
+static int an_run(x265cu_analyser* a, int stages)
+{
+    x265cu_ctx* c = a->ctx;
+    const int depth = a->p.depth;
+    const size_t es = depth == 8 ? 1 : 2;
+    (void)es;
+    if (stages & 1)
+    {
+        k_build_me_jobs<<<(a->njobs + 255) / 256, 256, 0, c->stream>>>(a->d_pus, a->njobs, a->d_field, a->fw, a->fh, a->p.width, a->p.height,
+                                                                       a->stride, a->p.method, a->p.subme, a->p.merange, a->d_jobs);
+        CU_LAUNCH_CHECK(c);
+        if (launch_me(c, depth, a->d_fenc + a->orgBytes, a->stride, (const void* const*)a->d_refTable, a->stride, 0,
+                      a->d_mvcost + a->mvrange, a->d_jobs, a->njobs, a->d_me_out, c->d_counter)) return -1;
+        k_pack_me<<<(a->njobs + 255) / 256, 256, 0, c->stream>>>(a->d_me_out, a->njobs, a->d_me_packed);
+        CU_LAUNCH_CHECK(c);
+    }
+    if (stages & 2)
+    {
+        CU_CHECK(cudaMemsetAsync(a->d_cu_sse, 0, sizeof(unsigned long long) * a->ncu, c->stream));
+        CU_CHECK(cudaMemsetAsync(a->d_cu_numsig, 0, sizeof(uint32_t) * a->ncu, c->stream));
+        int blocks = a->ntu < c->sm_count * 8 ? a->ntu : c->sm_count * 8;
+        if (depth == 8)
+            k_cu_residual<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)(a->d_fenc + a->orgBytes), (const uint8_t* const*)a->d_refTable, a->stride,
+                a->d_cus, a->d_tus, a->ntu, a->d_cu_jobs, a->p.numRefs, a->d_me_out, a->p.qp, a->d_coef, (uint8_t* const*)a->d_reconTable,
+                a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref);
+        else
+            k_cu_residual<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)(a->d_fenc + a->orgBytes), (const uint16_t* const*)a->d_refTable, a->stride,
+                a->d_cus, a->d_tus, a->ntu, a->d_cu_jobs, a->p.numRefs, a->d_me_out, a->p.qp, a->d_coef, (uint16_t* const*)a->d_reconTable,
+                a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref);
+        CU_LAUNCH_CHECK(c);
+    }
+    if (stages & 4)
+    {
+        int blocks = a->ncu < c->sm_count * 8 ? a->ncu : c->sm_count * 8;
+        if (depth == 8) k_intra_search<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)(a->d_fenc + a->orgBytes), a->stride, a->d_cus, a->ncu, a->d_intra);
+        else            k_intra_search<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)(a->d_fenc + a->orgBytes), a->stride, a->d_cus, a->ncu, a->d_intra);
+        CU_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+
+// upload a width x height host image into a margin-extended device plane
+static int an_upload_plane(x265cu_analyser* a, uint8_t* d_plane, const void* host, int hostStride)
+{
+    x265cu_ctx* c = a->ctx;
+    const size_t es = a->p.depth == 8 ? 1 : 2;
+    CU_CHECK(cudaMemcpy2DAsync(d_plane + a->orgBytes, (size_t)a->stride * es, host, (size_t)hostStride * es,
+                               (size_t)a->p.width * es, a->p.height, cudaMemcpyHostToDevice, c->stream));
+    return x265cu_extend_border(c, a->p.depth, d_plane + a->orgBytes, a->stride, a->p.width, a->p.height, AN_MARGIN_X, AN_MARGIN_Y);
+}
+
+extern "C" {
+
+x265cu_analyser* x265cu_analyser_create(x265cu_ctx* ctx, const x265cu_analysis_params* p)
+{
+    if (!ctx || p->numRefs < 1 || p->numRefs > 16 || (p->depth != 8 && p->depth != 10)) return NULL;
+    cudaSetDevice(ctx->device);
+    x265cu_analyser* a = new x265cu_analyser();
+    a->ctx = ctx; a->p = *p;
+    const size_t es = p->depth == 8 ? 1 : 2;
+    a->stride = (p->width + 2 * AN_MARGIN_X + 63) / 64 * 64;
+    a->planeRows = p->height + 2 * AN_MARGIN_Y;
+    a->planeBytes = (size_t)a->stride * a->planeRows * es + 256;
+    a->orgBytes = ((size_t)AN_MARGIN_Y * a->stride + AN_MARGIN_X) * es;
+    a->fw = (p->width + 15) / 16; a->fh = (p->height + 15) / 16;
+    an_build_geometry(a);
+    a->d_fenc = (uint8_t*)x265cu_malloc(ctx, a->planeBytes);
+    if (a->d_fenc) cudaMemset(a->d_fenc, 0, a->planeBytes);
+    void* reft[16]; void* rect[4];
+    for (int r = 0; r < p->numRefs; r++) { a->d_refs[r] = (uint8_t*)x265cu_malloc(ctx, a->planeBytes); if (a->d_refs[r]) cudaMemset(a->d_refs[r], 0, a->planeBytes); reft[r] = a->d_refs[r] + a->orgBytes; }
+    for (int d = 0; d < 4; d++) { a->d_recon[d] = (uint8_t*)x265cu_malloc(ctx, a->planeBytes); rect[d] = a->d_recon[d] + a->orgBytes; cudaMemset(a->d_recon[d], 0, a->planeBytes); }
+    a->d_refTable = (void**)x265cu_malloc(ctx, sizeof(void*) * 16);
+    a->d_reconTable = (void**)x265cu_malloc(ctx, sizeof(void*) * 4);
+    cudaMemcpy(a->d_refTable, reft, sizeof(void*) * p->numRefs, cudaMemcpyHostToDevice);
+    cudaMemcpy(a->d_reconTable, rect, sizeof(void*) * 4, cudaMemcpyHostToDevice);
+    const size_t fieldBytes = (size_t)p->numRefs * a->fw * a->fh * 2 * sizeof(int16_t);
+    a->d_field = (int16_t*)x265cu_malloc(ctx, fieldBytes);
+    a->mvrange = 65536;                                   // +-2*BC_MAX_MV like bitcost.h:77
+    std::vector<uint16_t> tab(2 * a->mvrange + 1);
+    x265cu_mvcost_table(p->lambda, a->mvrange, tab.data());
+    a->d_mvcost = an_upload(ctx, tab);
+    a->d_pus = an_upload(ctx, a->pus); a->d_cus = an_upload(ctx, a->cus); a->d_tus = an_upload(ctx, a->tus); a->d_cu_jobs = an_upload(ctx, a->cu_jobs);
+    a->d_jobs = (x265cu_me_job*)x265cu_malloc(ctx, sizeof(x265cu_me_job) * a->njobs);
+    a->d_me_out = (int32_t*)x265cu_malloc(ctx, sizeof(int32_t) * 4 * a->njobs);
+    a->d_me_packed = (int2*)x265cu_malloc(ctx, sizeof(int2) * a->njobs);
+    a->d_coef = (int16_t*)x265cu_malloc(ctx, sizeof(int16_t) * a->ncoef);
+    a->d_cu_sse = (unsigned long long*)x265cu_malloc(ctx, sizeof(unsigned long long) * a->ncu);
+    a->d_cu_numsig = (uint32_t*)x265cu_malloc(ctx, sizeof(uint32_t) * a->ncu);
+    a->d_cu_ref = (int32_t*)x265cu_malloc(ctx, sizeof(int32_t) * a->ncu);
+    a->d_intra = (uint32_t*)x265cu_malloc(ctx, sizeof(uint32_t) * 36 * a->ncu);
+    a->h_fenc = (uint8_t*)x265cu_host_alloc((size_t)p->width * p->height * es);
+    a->h_field = (int16_t*)x265cu_host_alloc(fieldBytes);
+    if (!a->d_intra || !a->d_coef || !a->d_me_out || !a->h_fenc || !a->h_field) return NULL;
+    cudaDeviceSynchronize();
+    return a;
+}
+
+void x265cu_analyser_destroy(x265cu_analyser* a)
+{
+    if (!a) return;
+    x265cu_ctx* c = a->ctx;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    void* bufs[] = { a->d_fenc, a->d_refTable, a->d_reconTable, a->d_field, a->d_mvcost, a->d_pus, a->d_cus, a->d_tus, a->d_cu_jobs, a->d_jobs,
+                     a->d_me_out, a->d_me_packed, a->d_coef, a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref, a->d_intra };
+    for (void* b : bufs) cudaFree(b);
+    for (int r = 0; r < a->p.numRefs; r++) cudaFree(a->d_refs[r]);
+    for (int d = 0; d < 4; d++) cudaFree(a->d_recon[d]);
+    x265cu_host_free(a->h_fenc); x265cu_host_free(a->h_field);
+    delete a;
+}
+
+int x265cu_analyser_counts(x265cu_analyser* a, int* njobs, int* ncu, int* ntu, int64_t* ncoef, int* stride)
+{
+    *njobs = a->njobs; *ncu = a->ncu; *ntu = a->ntu; *ncoef = a->ncoef; *stride = a->stride;
+    return 0;
+}
+
+int x265cu_analyser_set_ref(x265cu_analyser* a, int idx, const void* host_luma, int host_stride)
+{
+    if (idx < 0 || idx >= a->p.numRefs) return -1;
+    if (an_upload_plane(a, a->d_refs[idx], host_luma, host_stride)) return -1;
+    return x265cu_sync(a->ctx);
+}
+
+int x265cu_analyser_load_inputs(x265cu_analyser* a, const void* fenc_host, int host_stride, const int16_t* field_host)
+{
+    x265cu_ctx* c = a->ctx;
+    const size_t es = a->p.depth == 8 ? 1 : 2;
+    // stage through pinned memory so the copies are truly asynchronous DMA
+    for (int y = 0; y < a->p.height; y++)
+        memcpy(a->h_fenc + (size_t)y * a->p.width * es, (const uint8_t*)fenc_host + (size_t)y * host_stride * es, (size_t)a->p.width * es);
+    const size_t fieldBytes = (size_t)a->p.numRefs * a->fw * a->fh * 2 * sizeof(int16_t);
+    memcpy(a->h_field, field_host, fieldBytes);
+    if (an_upload_plane(a, a->d_fenc, a->h_fenc, a->p.width)) return -1;
+    CU_CHECK(cudaMemcpyAsync(a->d_field, a->h_field, fieldBytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int x265cu_analyser_run_resident(x265cu_analyser* a, int stages) { return an_run(a, stages); }
+
+int x265cu_analyser_analyse(x265cu_analyser* a, const void* fenc_host, int host_stride, const int16_t* field_host, int stages,
+                            x265cu_analysis_out* out)
+{
+    x265cu_ctx* c = a->ctx;
+    if (x265cu_analyser_load_inputs(a, fenc_host, host_stride, field_host)) return -1;
+    if (an_run(a, stages)) return -1;
+    if (out)
+    {
+        if (out->me_packed) CU_CHECK(cudaMemcpyAsync(out->me_packed, a->d_me_packed, sizeof(int2) * a->njobs, cudaMemcpyDeviceToHost, c->stream));
+        if (out->cu_sse) CU_CHECK(cudaMemcpyAsync(out->cu_sse, a->d_cu_sse, sizeof(uint64_t) * a->ncu, cudaMemcpyDeviceToHost, c->stream));
+        if (out->cu_numsig) CU_CHECK(cudaMemcpyAsync(out->cu_numsig, a->d_cu_numsig, sizeof(uint32_t) * a->ncu, cudaMemcpyDeviceToHost, c->stream));
+        if (out->cu_ref) CU_CHECK(cudaMemcpyAsync(out->cu_ref, a->d_cu_ref, sizeof(int32_t) * a->ncu, cudaMemcpyDeviceToHost, c->stream));
+        if (out->intra_cost) CU_CHECK(cudaMemcpyAsync(out->intra_cost, a->d_intra, sizeof(uint32_t) * 36 * a->ncu, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// debugging / parity access to device-resident results
+int x265cu_analyser_fetch(x265cu_analyser* a, int what, void* host)
+{
+    x265cu_ctx* c = a->ctx;
+    const size_t es = a->p.depth == 8 ? 1 : 2;
+    const void* src = NULL; size_t bytes = 0;
+    switch (what)
+    {
+    case 0: src = a->d_jobs; bytes = sizeof(x265cu_me_job) * a->njobs; break;
+    case 1: src = a->d_me_out; bytes = sizeof(int32_t) * 4 * a->njobs; break;
+    case 2: src = a->d_coef; bytes = sizeof(int16_t) * a->ncoef; break;
+    case 3: case 4: case 5: case 6: src = a->d_recon[what - 3]; bytes = (size_t)a->stride * a->planeRows * es; break;
+    case 7: src = a->d_cu_jobs; bytes = sizeof(int32_t) * a->ncu * a->p.numRefs; break;
+    case 8: src = a->d_fenc; bytes = (size_t)a->stride * a->planeRows * es; break;
+    default: return -1;
+    }
+    CU_CHECK(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+} // extern "C"

@@ -215,4 +215,5 @@ int x265cu_me_batch(x265cu_ctx* c, int depth, const void* fenc, int fencStride, 
 
 } // extern "C"
 
+#include "analyser.cuh"
 #include "thunks.cuh"

@@ -195,3 +195,106 @@ def load(device=0, need_gpu=True):
     if key not in _cached:
         _cached[key] = Lib(device, need_gpu)
     return _cached[key]
+
+
+# ---------------- frame-level analyser (x265cu_analyser_*) ----------------
+class AnalysisParams(C.Structure):
+    _fields_ = [("width", I), ("height", I), ("depth", I), ("numRefs", I), ("method", I), ("subme", I), ("merange", I),
+                ("rect", I), ("qp", I), ("lam", C.c_double)]
+
+
+class AnalysisOut(C.Structure):
+    _fields_ = [("me_packed", P), ("cu_sse", P), ("cu_numsig", P), ("cu_ref", P), ("intra_cost", P)]
+
+
+_AN_PROTOS = {
+    "x265cu_analyser_create": (P, [P, C.POINTER(AnalysisParams)]),
+    "x265cu_analyser_destroy": (None, [P]),
+    "x265cu_analyser_counts": (I, [P, C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I64), C.POINTER(I)]),
+    "x265cu_analyser_set_ref": (I, [P, I, P, I]),
+    "x265cu_analyser_load_inputs": (I, [P, P, I, P]),
+    "x265cu_analyser_run_resident": (I, [P, I]),
+    "x265cu_analyser_analyse": (I, [P, P, I, P, I, C.POINTER(AnalysisOut)]),
+    "x265cu_analyser_fetch": (I, [P, I, P]),
+}
+_PROTOS.update(_AN_PROTOS)
+
+
+class Analyser:
+    """Host mirror of x265cu_analyser: the public call a user makes for one frame is analyse()."""
+
+    def __init__(self, lib, width, height, depth=8, numRefs=4, method=3, subme=3, merange=57, rect=1, qp=30, lam=None):
+        self.lib = lib
+        if lam is None:
+            lam = round(2.0 ** (qp / 6.0 - 2.0) * (1 << (depth - 8)), 4)      # x265_lambda_tab (constants.cpp:33-50)
+        self.params = AnalysisParams(width, height, depth, numRefs, method, subme, merange, rect, qp, lam)
+        self.h = lib.L.x265cu_analyser_create(lib.ctx, C.byref(self.params))
+        if not self.h:
+            raise RuntimeError("x265cu_analyser_create failed: " + lib.last_error())
+        nj, nc, nt, st = I(), I(), I(), I()
+        ncoef = I64()
+        lib.L.x265cu_analyser_counts(self.h, C.byref(nj), C.byref(nc), C.byref(nt), C.byref(ncoef), C.byref(st))
+        self.njobs, self.ncu, self.ntu, self.ncoef, self.stride = nj.value, nc.value, nt.value, ncoef.value, st.value
+        self.depth, self.width, self.height, self.numRefs = depth, width, height, numRefs
+        self.dtype = np.uint8 if depth == 8 else np.uint16
+        # host result buffers (pinned so D2H is real DMA)
+        self._pinned = []
+        self.me_packed = self._pin((self.njobs, 2), np.int32)
+        self.cu_sse = self._pin((self.ncu,), np.uint64)
+        self.cu_numsig = self._pin((self.ncu,), np.uint32)
+        self.cu_ref = self._pin((self.ncu,), np.int32)
+        self.intra_cost = self._pin((self.ncu, 36), np.uint32)
+        self.out = AnalysisOut(self.me_packed.ctypes.data, self.cu_sse.ctypes.data, self.cu_numsig.ctypes.data,
+                               self.cu_ref.ctypes.data, self.intra_cost.ctypes.data)
+
+    def _pin(self, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self.lib.L.x265cu_host_alloc(max(n, 16))
+        if not p:
+            raise MemoryError("pinned alloc failed")
+        self._pinned.append(p)
+        buf = (C.c_uint8 * n).from_address(p)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def set_ref(self, idx, img):
+        img = np.ascontiguousarray(img, self.dtype)
+        assert img.shape == (self.height, self.width)
+        self.lib.check(self.lib.L.x265cu_analyser_set_ref(self.h, idx, img.ctypes.data, self.width))
+
+    def load_inputs(self, fenc, field):
+        fenc = np.ascontiguousarray(fenc, self.dtype)
+        field = np.ascontiguousarray(field, np.int16)
+        self.lib.check(self.lib.L.x265cu_analyser_load_inputs(self.h, fenc.ctypes.data, self.width, field.ctypes.data))
+
+    def run_resident(self, stages=7):
+        self.lib.check(self.lib.L.x265cu_analyser_run_resident(self.h, stages))
+
+    def analyse(self, fenc, field, stages=7):
+        """e2e: host frame + predictor field in, host results out (synchronous)."""
+        self.lib.check(self.lib.L.x265cu_analyser_analyse(self.h, fenc.ctypes.data, self.width, field.ctypes.data, stages, C.byref(self.out)))
+        return self
+
+    def h2d_bytes(self, field):
+        return self.width * self.height * np.dtype(self.dtype).itemsize + field.nbytes
+
+    def d2h_bytes(self):
+        return self.me_packed.nbytes + self.cu_sse.nbytes + self.cu_numsig.nbytes + self.cu_ref.nbytes + self.intra_cost.nbytes
+
+    def fetch(self, what):
+        es = np.dtype(self.dtype).itemsize
+        rows = self.height + 160
+        spec = {"jobs": (0, ME_JOB, self.njobs), "me_out": (1, np.int32, self.njobs * 4), "coef": (2, np.int16, self.ncoef),
+                "recon0": (3, self.dtype, self.stride * rows), "recon1": (4, self.dtype, self.stride * rows),
+                "recon2": (5, self.dtype, self.stride * rows), "recon3": (6, self.dtype, self.stride * rows),
+                "cu_jobs": (7, np.int32, self.ncu * self.numRefs), "fenc": (8, self.dtype, self.stride * rows)}[what]
+        out = np.zeros(spec[2], spec[1])
+        self.lib.check(self.lib.L.x265cu_analyser_fetch(self.h, spec[0], out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.L.x265cu_analyser_destroy(self.h)
+            self.h = None
+        for p in self._pinned:
+            self.lib.L.x265cu_host_free(p)
+        self._pinned = []
