@@ -174,6 +174,9 @@ int x265cu_analyser_load_inputs(x265cu_analyser*, const void* fenc_host, int hos
 int x265cu_analyser_run_resident(x265cu_analyser*, int stages);       /* kernels only, inputs resident */
 int x265cu_analyser_analyse(x265cu_analyser*, const void* fenc_host, int host_stride, const int16_t* field_host,
                             int stages, x265cu_analysis_out* out);    /* H2D + kernels + D2H, synchronous */
+int x265cu_analyser_stage_ms(x265cu_analyser*, float ms[4]);          /* device ms of the last run: ME stage, residual, intra, ME kernel */
+void* x265cu_analyser_ref_plane(x265cu_analyser*, int idx, int* stride); /* device address of ref idx's pixel (0,0) */
+int x265cu_analyser_ref_updated(x265cu_analyser*, int idx);            /* re-extend borders after writing the plane in place */
 int x265cu_analyser_fetch(x265cu_analyser*, int what, void* host);    /* parity/debug access to resident results */
 
 #ifdef __cplusplus

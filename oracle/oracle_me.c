@@ -25,6 +25,9 @@ void orc_mvcost_table(double lambda, int range, uint16_t* out)
     }
 }
 
+/* call counters for workload characterisation (not thread safe; tests/bench never rely on them) */
+long long g_orc_cnt[4];   /* fpel SAD evaluations, sub-pel compares, raster points, jobs */
+
 typedef struct { int x, y; } mv_t;
 typedef int (*cmp_fn)(const pixel*, intptr_t, const pixel*, intptr_t, int, int);
 
@@ -44,7 +47,7 @@ static inline int mvcost(const me_ctx* c, int qx, int qy)
 static inline int in_range(const me_ctx* c, int x, int y)
 { return x >= c->mvmin.x && x <= c->mvmax.x && y >= c->mvmin.y && y <= c->mvmax.y; }
 static inline int fpel_sad(const me_ctx* c, int x, int y)
-{ return orc_sad(c->fenc, 64, c->fref + x + (intptr_t)y * c->stride, c->stride, c->j->pw, c->j->ph); }
+{ g_orc_cnt[0]++; return orc_sad(c->fenc, 64, c->fref + x + (intptr_t)y * c->stride, c->stride, c->j->pw, c->j->ph); }
 static inline int cost_fpel(const me_ctx* c, int x, int y)
 { return fpel_sad(c, x, y) + mvcost(c, x * 4, y * 4); }
 
@@ -72,6 +75,7 @@ static int lowres_qpel_cost(const me_ctx* c, int qx, int qy, cmp_fn cmp)
 /* motion.cpp:1571-1598 */
 static int subpel_compare(const me_ctx* c, int qx, int qy, cmp_fn cmp)
 {
+    g_orc_cnt[1]++;
     const orc_me_job* j = c->j;
     const pixel* r = c->fref + (qx >> 2) + (intptr_t)(qy >> 2) * c->stride;
     int xf = qx & 3, yf = qy & 3;
@@ -187,6 +191,7 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
 {
     me_ctx ctx; me_ctx* c = &ctx;
     c->j = j;
+    g_orc_cnt[3]++;
     orc_copy_pp(c->fenc, 64, j->fenc + j->offset, j->fencStride, j->pw, j->ph);
     c->fref = j->ref[0] + j->offset;
     c->stride = j->refStride;
@@ -344,6 +349,7 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
                             for (int k = 0; k < 4; k++)
                             {
                                 int sad = fpel_sad(c, tx, ty);
+                                g_orc_cnt[2]++;
                                 int cost = sad + (k < 3 ? mvcost(c, tx * 4, ty * 4) : mvcost(c, tx * 8, ty * 8));
                                 if (cost < s.bcost) { s.bcost = cost; s.bmv.x = tx; s.bmv.y = ty; }
                                 if (k < 3) tx += RD;

@@ -22,6 +22,7 @@ struct x265cu_analyser
     int16_t* d_coef; unsigned long long* d_cu_sse; uint32_t* d_cu_numsig; int32_t* d_cu_ref; uint32_t* d_intra;
     // pinned host staging for the e2e path
     uint8_t* h_fenc; int16_t* h_field;
+    cudaEvent_t ev[5]; int ev_valid;      // stage boundaries of the last an_run (ME build+search+pack | residual | intra)
     std::vector<PuDesc> pus; std::vector<CuDesc> cus; std::vector<TuDesc> tus; std::vector<int32_t> cu_jobs;
 };
 
@@ -99,6 +100,8 @@ static int an_run(x265cu_analyser* a, int stages)
     const int depth = a->p.depth;
     const size_t es = depth == 8 ? 1 : 2;
     (void)es;
+    a->ev_valid = stages;
+    CU_CHECK(cudaEventRecord(a->ev[0], c->stream));
     if (stages & 1)
     {
         k_build_me_jobs<<<(a->njobs + 255) / 256, 256, 0, c->stream>>>(a->d_pus, a->njobs, a->d_field, a->fw, a->fh, a->p.width, a->p.height,
@@ -106,9 +109,11 @@ static int an_run(x265cu_analyser* a, int stages)
         CU_LAUNCH_CHECK(c);
         if (launch_me(c, depth, a->d_fenc + a->orgBytes, a->stride, (const void* const*)a->d_refTable, a->stride, 0,
                       a->d_mvcost + a->mvrange, a->d_jobs, a->njobs, a->d_me_out, c->d_counter)) return -1;
+        CU_CHECK(cudaEventRecord(a->ev[4], c->stream));      // ME search kernel alone ends here
         k_pack_me<<<(a->njobs + 255) / 256, 256, 0, c->stream>>>(a->d_me_out, a->njobs, a->d_me_packed);
         CU_LAUNCH_CHECK(c);
     }
+    CU_CHECK(cudaEventRecord(a->ev[1], c->stream));
     if (stages & 2)
     {
         CU_CHECK(cudaMemsetAsync(a->d_cu_sse, 0, sizeof(unsigned long long) * a->ncu, c->stream));
@@ -124,6 +129,7 @@ static int an_run(x265cu_analyser* a, int stages)
                 a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref);
         CU_LAUNCH_CHECK(c);
     }
+    CU_CHECK(cudaEventRecord(a->ev[2], c->stream));
     if (stages & 4)
     {
         int blocks = a->ncu < c->sm_count * 8 ? a->ncu : c->sm_count * 8;
@@ -131,6 +137,7 @@ static int an_run(x265cu_analyser* a, int stages)
         else            k_intra_search<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)(a->d_fenc + a->orgBytes), a->stride, a->d_cus, a->ncu, a->d_intra);
         CU_LAUNCH_CHECK(c);
     }
+    CU_CHECK(cudaEventRecord(a->ev[3], c->stream));
     return 0;
 }
 
@@ -183,6 +190,8 @@ x265cu_analyser* x265cu_analyser_create(x265cu_ctx* ctx, const x265cu_analysis_p
     a->d_cu_numsig = (uint32_t*)x265cu_malloc(ctx, sizeof(uint32_t) * a->ncu);
     a->d_cu_ref = (int32_t*)x265cu_malloc(ctx, sizeof(int32_t) * a->ncu);
     a->d_intra = (uint32_t*)x265cu_malloc(ctx, sizeof(uint32_t) * 36 * a->ncu);
+    for (int i = 0; i < 5; i++) cudaEventCreate(&a->ev[i]);
+    a->ev_valid = 0;
     a->h_fenc = (uint8_t*)x265cu_host_alloc((size_t)p->width * p->height * es);
     a->h_field = (int16_t*)x265cu_host_alloc(fieldBytes);
     if (!a->d_intra || !a->d_coef || !a->d_me_out || !a->h_fenc || !a->h_field) return NULL;
@@ -222,13 +231,12 @@ int x265cu_analyser_load_inputs(x265cu_analyser* a, const void* fenc_host, int h
 {
     x265cu_ctx* c = a->ctx;
     const size_t es = a->p.depth == 8 ? 1 : 2;
-    // stage through pinned memory so the copies are truly asynchronous DMA
-    for (int y = 0; y < a->p.height; y++)
-        memcpy(a->h_fenc + (size_t)y * a->p.width * es, (const uint8_t*)fenc_host + (size_t)y * host_stride * es, (size_t)a->p.width * es);
+    // copies are issued straight from the caller's buffers: pass pinned memory (x265cu_host_alloc)
+    // for true asynchronous DMA; pageable memory also works (the driver stages it)
+    (void)es;
     const size_t fieldBytes = (size_t)a->p.numRefs * a->fw * a->fh * 2 * sizeof(int16_t);
-    memcpy(a->h_field, field_host, fieldBytes);
-    if (an_upload_plane(a, a->d_fenc, a->h_fenc, a->p.width)) return -1;
-    CU_CHECK(cudaMemcpyAsync(a->d_field, a->h_field, fieldBytes, cudaMemcpyHostToDevice, c->stream));
+    if (an_upload_plane(a, a->d_fenc, fenc_host, host_stride)) return -1;
+    CU_CHECK(cudaMemcpyAsync(a->d_field, field_host, fieldBytes, cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 
@@ -250,6 +258,32 @@ int x265cu_analyser_analyse(x265cu_analyser* a, const void* fenc_host, int host_
     }
     CU_CHECK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+// per-stage device time of the last run (ms): [0] ME stage (job build + search + pack), [1] residual,
+// [2] intra, [3] the ME search kernel alone.  Synchronises the stream.
+int x265cu_analyser_stage_ms(x265cu_analyser* a, float* ms)
+{
+    CU_CHECK(cudaEventSynchronize(a->ev[3]));
+    for (int i = 0; i < 3; i++) CU_CHECK(cudaEventElapsedTime(&ms[i], a->ev[i], a->ev[i + 1]));
+    ms[3] = 0.f;
+    if (a->ev_valid & 1) CU_CHECK(cudaEventElapsedTime(&ms[3], a->ev[0], a->ev[4]));
+    return 0;
+}
+
+// device address of reference plane idx's origin pixel and the plane geometry, so that the owner of the
+// reconstructed pixels (e.g. an NCCL broadcast) can write them in place; call x265cu_analyser_ref_updated()
+// afterwards to re-extend the borders.
+void* x265cu_analyser_ref_plane(x265cu_analyser* a, int idx, int* stride)
+{
+    if (idx < 0 || idx >= a->p.numRefs) return NULL;
+    *stride = a->stride;
+    return a->d_refs[idx] + a->orgBytes;
+}
+int x265cu_analyser_ref_updated(x265cu_analyser* a, int idx)
+{
+    if (idx < 0 || idx >= a->p.numRefs) return -1;
+    return x265cu_extend_border(a->ctx, a->p.depth, a->d_refs[idx] + a->orgBytes, a->stride, a->p.width, a->p.height, AN_MARGIN_X, AN_MARGIN_Y);
 }
 
 // debugging / parity access to device-resident results

@@ -3,8 +3,13 @@
 // bit-exactly: MVP / zero / candidate pre-checks (:771-814), DIA (:822-846), HEX (:848-945),
 // STAR (:362-604, :1132-1240 incl. the raster refinement and its `tmv << 3` quirk), sub-pel
 // refinement by workload[subme] (:48-58, :1449-1558) through subpelCompare (:1571-1598, luma) or
-// the lowres qpel path (common/lowres.h:94-120).  Costs are warp-uniform after each reduction, so
-// all 32 lanes take identical branches.  Parallelism = (PUs x refs x CTUs) jobs per launch.
+// the lowres qpel path (common/lowres.h:94-120).
+//
+// Parallelism: (PUs x refs x CTUs) jobs per launch, one warp per job, and INSIDE a job every burst
+// of independent candidates (the 4/8/16 points of a star level, 32 raster points, the 4/8 sub-pel
+// directions of a refinement round) is evaluated by the 32 lanes at once -- (candidate, pixel-word)
+// pairs are spread over the lanes -- and then folded in the reference's sequential order, so the
+// decisions are identical.  Costs are warp-uniform after each fold: all lanes take the same branches.
 #pragma once
 #include "common.cuh"
 #include "pixelcmp.cuh"
@@ -15,8 +20,8 @@
 
 struct MeShared                            // per-warp scratch
 {
-    int16_t mid[ME_MID_ROWS * 64];         // hps(rowExt) intermediate of one band
-    uint16_t pred[ME_BAND * 64];           // predicted band (pixel values)
+    int16_t mid[ME_MID_ROWS * 64];         // hps(rowExt) intermediate of one band (or 4 small candidates)
+    uint16_t pred[ME_BAND * 64];           // predicted band (or 4 small candidates)
 };
 
 template <typename P>
@@ -27,7 +32,10 @@ struct MeCtx
     const uint16_t* mvc;                   // centred mvcost table
     int mvpx, mvpy;
     int minx, miny, maxx, maxy;            // full-pel bounds
-    int w, h, lane, lowres;
+    int w, h, lgw, lane, lowres;
+    bool pow2;                             // w and h are powers of two (all 2Nx2N / rect PUs); AMP sizes take the generic paths
+    int nw, lgnw, lgwpr;                   // words per PU, log2, log2(words per row)
+    uint32_t fw;                           // this lane's fenc word when nw <= 32
     MeShared* sm;
 };
 
@@ -37,35 +45,144 @@ __device__ __forceinline__ int me_mvcost(const MeCtx<P>& c, int qx, int qy)
     return (uint16_t)(c.mvc[qx - c.mvpx] + c.mvc[qy - c.mvpy]);
 }
 
-// SAD of the fenc block against ref at an arbitrary element pointer (rows may be unaligned).
-// Lanes walk 4-byte words; unaligned ref words are assembled from two aligned loads (funnel shift).
+template <typename P>
+__device__ __forceinline__ void me_yx(const MeCtx<P>& c, int i, int& y, int& x)
+{
+    if (c.pow2) { y = i >> c.lgw; x = i & (c.w - 1); }
+    else        { y = i / c.w; x = i - y * c.w; }
+}
+
+__device__ __forceinline__ uint32_t ld_unaligned32(uintptr_t a)
+{
+    const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t lo = ap[0];
+    return sh ? __funnelshift_r(lo, ap[1], sh) : lo;
+}
+
+template <typename P> __device__ __forceinline__ int sad_word(uint32_t a, uint32_t b, int acc)
+{
+    return sizeof(P) == 1 ? (int)(__vsadu4(a, b) + (uint32_t)acc) : (int)(__vsadu2(a, b) + (uint32_t)acc);
+}
+
+// SAD of the fenc block against ONE reference position (element pointer, rows may be unaligned).
 template <typename P>
 __device__ __forceinline__ int me_sad_direct(const MeCtx<P>& c, const P* __restrict__ r)
 {
-    const int rowBytes = c.w * (int)sizeof(P);
-    const int wpr = rowBytes >> 2;                     // words per row
-    const int rpp = 32 / wpr;                          // rows per pass (wpr <= 32)
-    const int myrow = c.lane / wpr, myword = c.lane - myrow * wpr;
-    const bool active = myrow < rpp;
     const uintptr_t rbase = (uintptr_t)r;
+    const int wpr = 1 << c.lgwpr;
     int acc = 0;
-    for (int y0 = 0; y0 < c.h; y0 += rpp)
-    {
-        int y = y0 + myrow;
-        if (active && y < c.h)
+    if (!c.pow2)
+    {   // AMP sizes (12/24/48): generic word walk
+        const int wprg = (c.w * (int)sizeof(P)) >> 2, nwg = wprg * c.h;
+        for (int wd = c.lane; wd < nwg; wd += 32)
         {
-            uint32_t f = *(const uint32_t*)((const uint8_t*)c.fenc + (size_t)y * c.fstride * sizeof(P) + myword * 4);
-            uintptr_t a = rbase + (size_t)y * c.rstride * sizeof(P) + myword * 4;
-            const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
-            uint32_t sh = (uint32_t)(a & 3) * 8;
-            uint32_t lo = ap[0];
-            uint32_t v = lo;
-            if (sh) v = __funnelshift_r(lo, ap[1], sh);
-            if (sizeof(P) == 1) acc = __vsadu4(f, v) + acc;
-            else                acc = __vsadu2(f, v) + acc;
+            int row = wd / wprg, col = wd - row * wprg;
+            uint32_t f = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * c.fstride) * sizeof(P) + col * 4);
+            acc = sad_word<P>(f, ld_unaligned32(rbase + ((size_t)row * c.rstride) * sizeof(P) + col * 4), acc);
+        }
+    }
+    else if (c.nw <= 32)
+    {
+        if (c.lane < c.nw)
+        {
+            int row = c.lane >> c.lgwpr, col = c.lane & (wpr - 1);
+            acc = sad_word<P>(c.fw, ld_unaligned32(rbase + ((size_t)row * c.rstride) * sizeof(P) + col * 4), 0);
+        }
+    }
+    else
+    {
+        const int iters = c.nw >> 5;
+#pragma unroll 4
+        for (int k = 0; k < iters; k++)
+        {
+            int wd = c.lane + (k << 5);
+            int row = wd >> c.lgwpr, col = wd & (wpr - 1);
+            uint32_t f = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * c.fstride) * sizeof(P) + col * 4);
+            acc = sad_word<P>(f, ld_unaligned32(rbase + ((size_t)row * c.rstride) * sizeof(P) + col * 4), acc);
         }
     }
     return warp_sum(acc);
+}
+
+// Full-pel SAD + mvcost of up to 32 candidate positions at once.  Lane i (< n) owns candidate i:
+// (px, py) in full-pel units relative to the block; returns that candidate's cost in lane i.
+// x8: the raster quirk (motion.cpp:1194: mvcost(tmv << 3) for every 4th column).
+template <typename P>
+__device__ __forceinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int py, bool x8)
+{
+    const int off = py * c.rstride + px;                    // element offset of my candidate
+    const uintptr_t rbase = (uintptr_t)c.ref[0];
+    const int wpr = 1 << c.lgwpr;
+    int mysad = 0;
+    if (!c.pow2)
+    {
+        for (int p = 0; p < n; p++)
+        {
+            const int offp = __shfl_sync(0xffffffffu, off, p);
+            const int v = me_sad_direct(c, c.ref[0] + offp);
+            if (c.lane == p) mysad = v;
+        }
+    }
+    else if (c.nw >= 32)
+    {
+        const int iters = c.nw >> 5;
+        for (int p = 0; p < n; p++)
+        {
+            const int offp = __shfl_sync(0xffffffffu, off, p);
+            const uintptr_t rb = rbase + (ptrdiff_t)offp * (ptrdiff_t)sizeof(P);
+            int acc = 0;
+            if (iters == 1)
+            {
+                int row = c.lane >> c.lgwpr, col = c.lane & (wpr - 1);
+                acc = sad_word<P>(c.fw, ld_unaligned32(rb + ((size_t)row * c.rstride) * sizeof(P) + col * 4), 0);
+            }
+            else
+            {
+#pragma unroll 4
+                for (int k = 0; k < iters; k++)
+                {
+                    int wd = c.lane + (k << 5);
+                    int row = wd >> c.lgwpr, col = wd & (wpr - 1);
+                    uint32_t f = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * c.fstride) * sizeof(P) + col * 4);
+                    acc = sad_word<P>(f, ld_unaligned32(rb + ((size_t)row * c.rstride) * sizeof(P) + col * 4), acc);
+                }
+            }
+            acc = warp_sum(acc);
+            if (c.lane == p) mysad = acc;
+        }
+    }
+    else
+    {
+        // several candidates per pass: lane group g = lane >> lgnw evaluates candidate base + g
+        const int ppp = 32 >> c.lgnw;
+        const int wd = c.lane & (c.nw - 1), row = wd >> c.lgwpr, col = wd & (wpr - 1);
+        for (int base = 0; base < n; base += ppp)
+        {
+            const int p = base + (c.lane >> c.lgnw);
+            const int offp = __shfl_sync(0xffffffffu, off, min(p, n - 1));
+            int acc = 0;
+            if (p < n)
+                acc = sad_word<P>(c.fw, ld_unaligned32(rbase + ((ptrdiff_t)offp + (ptrdiff_t)row * c.rstride) * (ptrdiff_t)sizeof(P) + col * 4), 0);
+            for (int s = c.nw >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+            const int v = __shfl_sync(0xffffffffu, acc, ((c.lane - base) << c.lgnw) & 31);
+            if (c.lane >= base && c.lane < base + ppp) mysad = v;
+        }
+    }
+    int cost = 0x7fffffff;
+    if (c.lane < n) cost = mysad + (x8 ? me_mvcost(c, px * 8, py * 8) : me_mvcost(c, px * 4, py * 4));
+    return cost;
+}
+
+// keep only the valid candidates, preserving order: returns n and moves candidate k to lane k
+__device__ __forceinline__ int me_compact(bool valid, int& a, int& b, int& c2, int& d)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31;
+    const int src = __fns(m, 0, lane + 1) & 31;          // position of the (lane+1)-th set bit (garbage if none)
+    a = __shfl_sync(0xffffffffu, a, src); b = __shfl_sync(0xffffffffu, b, src);
+    c2 = __shfl_sync(0xffffffffu, c2, src); d = __shfl_sync(0xffffffffu, d, src);
+    return __popc(m);
 }
 
 // cost of a band of prediction held in c.sm->pred (stride 64) against fenc rows [y0, y0+rows)
@@ -77,36 +194,44 @@ __device__ __forceinline__ int me_band_cost(const MeCtx<P>& c, int y0, int rows,
     int acc = 0;
     if (!satd)
     {
-        const int n = c.w * rows;
+        const int n = rows * c.w;
         for (int i = c.lane; i < n; i += 32)
         {
-            int y = i / c.w, x = i - y * c.w;
+            int y, x; me_yx(c, i, y, x);
             acc += abs((int)f[y * c.fstride + x] - (int)pr[y * 64 + x]);
         }
     }
-    else if ((c.w & 7) == 0)
-    {
-        const int tw = c.w >> 3, nt = tw * (rows >> 2);
+    else if (!c.pow2)
+    {   // AMP sizes: 8x4 tiles when w % 8 == 0, else 4x4 tiles (pixel.cpp:1134-1158)
+        const int tw = (c.w & 7) == 0 ? 8 : 4, tpr = c.w / tw, nt = tpr * (rows >> 2);
         for (int t = c.lane; t < nt; t += 32)
         {
-            int ty = t / tw, tx = t - ty * tw;
+            int ty = t / tpr, tx = t - ty * tpr;
+            const P* pf = f + (ty * 4) * c.fstride + tx * tw; const uint16_t* pp = pr + (ty * 4) * 64 + tx * tw;
+            if (tw == 8) acc += (had4x4_abs(pf, c.fstride, pp, 64) + had4x4_abs(pf + 4, c.fstride, pp + 4, 64)) >> 1;
+            else         acc += had4x4_abs(pf, c.fstride, pp, 64) >> 1;
+        }
+    }
+    else if (c.w >= 8)
+    {
+        const int lgtw = c.lgw - 3, nt = (rows >> 2) << lgtw;
+        for (int t = c.lane; t < nt; t += 32)
+        {
+            int ty = t >> lgtw, tx = t & ((1 << lgtw) - 1);
             const P* pf = f + (ty * 4) * c.fstride + tx * 8; const uint16_t* pp = pr + (ty * 4) * 64 + tx * 8;
             acc += (had4x4_abs(pf, c.fstride, pp, 64) + had4x4_abs(pf + 4, c.fstride, pp + 4, 64)) >> 1;
         }
     }
     else
     {
-        const int tw = c.w >> 2, nt = tw * (rows >> 2);
+        const int nt = rows >> 2;                    // w == 4: one 4x4 tile per 4 rows
         for (int t = c.lane; t < nt; t += 32)
-        {
-            int ty = t / tw, tx = t - ty * tw;
-            acc += had4x4_abs(f + (ty * 4) * c.fstride + tx * 4, c.fstride, pr + (ty * 4) * 64 + tx * 4, 64) >> 1;
-        }
+            acc += had4x4_abs(f + (t * 4) * c.fstride, c.fstride, pr + (t * 4) * 64, 64) >> 1;
     }
     return acc;           // un-reduced partial (caller reduces once)
 }
 
-// subpelCompare (motion.cpp:1571-1598): luma_hpp / luma_vpp / luma_hvpp into a scratch, then cmp.
+// subpelCompare (motion.cpp:1571-1598) for ONE candidate: luma_hpp / luma_vpp / luma_hvpp, then cmp.
 template <typename P>
 __device__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
 {
@@ -126,10 +251,10 @@ __device__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
         const int rows = min(ME_BAND, c.h - y0);
         __syncwarp();
         if (!yf)
-        {   // horizontal only: pp rounding
-            for (int i = c.lane; i < c.w * rows; i += 32)
+        {
+            for (int i = c.lane; i < rows * c.w; i += 32)
             {
-                int y = i / c.w, x = i - y * c.w;
+                int y, x; me_yx(c, i, y, x);
                 const P* s = r + (ptrdiff_t)(y0 + y) * c.rstride + x - 3;
                 int sum = 0;
 #pragma unroll
@@ -138,10 +263,10 @@ __device__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
             }
         }
         else if (!xf)
-        {   // vertical only
-            for (int i = c.lane; i < c.w * rows; i += 32)
+        {
+            for (int i = c.lane; i < rows * c.w; i += 32)
             {
-                int y = i / c.w, x = i - y * c.w;
+                int y, x; me_yx(c, i, y, x);
                 const P* s = r + (ptrdiff_t)(y0 + y - 3) * c.rstride + x;
                 int sum = 0;
 #pragma unroll
@@ -150,11 +275,11 @@ __device__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
             }
         }
         else
-        {   // hps with row extension into mid, then vsp
+        {
             const int mrows = rows + 7;
-            for (int i = c.lane; i < c.w * mrows; i += 32)
+            for (int i = c.lane; i < mrows * c.w; i += 32)
             {
-                int y = i / c.w, x = i - y * c.w;
+                int y, x; me_yx(c, i, y, x);
                 const P* s = r + (ptrdiff_t)(y0 + y - 3) * c.rstride + x - 3;
                 int sum = 0;
 #pragma unroll
@@ -162,9 +287,9 @@ __device__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
                 c.sm->mid[y * 64 + x] = (int16_t)interp_finish<DEPTH>(sum, 1);
             }
             __syncwarp();
-            for (int i = c.lane; i < c.w * rows; i += 32)
+            for (int i = c.lane; i < rows * c.w; i += 32)
             {
-                int y = i / c.w, x = i - y * c.w;
+                int y, x; me_yx(c, i, y, x);
                 int sum = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) sum += (int)c.sm->mid[(y + k) * 64 + x] * cy[k];
@@ -175,6 +300,153 @@ __device__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
         acc += me_band_cost(c, y0, rows, satd);
     }
     return warp_sum(acc);
+}
+
+// Up to 4 sub-pel candidates of a SMALL PU (w, h <= 16) evaluated concurrently: lanes are spread over
+// (candidate, pixel).  Lane i (< n <= 4) owns candidate i (qx, qy); returns its distortion in lane i.
+// Per candidate the arithmetic is exactly me_subpel_compare's.
+template <typename P>
+__device__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+{
+    constexpr int DEPTH = PixTraits<P>::depth;
+    const int lgh = 31 - __clz(c.h);
+    const int lgpx = c.lgw + lgh;                         // log2 pixels per candidate
+    const int mrows = c.h + 7;
+    __syncwarp();
+    // phase 1: horizontal pass into mid (candidates with xf && yf), [cand][row][x] with row stride w
+    const int midPer = mrows << c.lgw;                    // <= 368
+    int cqx[4], cqy[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { cqx[k] = __shfl_sync(0xffffffffu, qx, k); cqy[k] = __shfl_sync(0xffffffffu, qy, k); }
+#pragma unroll
+    for (int cand = 0; cand < 4; cand++)
+    {
+        const int mqx = cqx[cand], mqy = cqy[cand];
+        const int xf = mqx & 3, yf = mqy & 3;
+        if (cand < n && xf && yf)
+        {
+            const int16_t* cx = c_lumaFilter[xf];
+            const P* r0 = c.ref[0] + (mqx >> 2) + (ptrdiff_t)((mqy >> 2) - 3) * c.rstride - 3;
+            for (int rem = c.lane; rem < midPer; rem += 32)
+            {
+                const int y = rem >> c.lgw, x = rem & (c.w - 1);
+                const P* s = r0 + (ptrdiff_t)y * c.rstride + x;
+                int sum = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) sum += (int)s[k] * cx[k];
+                c.sm->mid[cand * 368 + rem] = (int16_t)interp_finish<DEPTH>(sum, 1);
+            }
+        }
+    }
+    __syncwarp();
+    // phase 2: prediction into pred, [cand][y][x] with row stride w
+    const int npx = 1 << lgpx;
+    for (int i = c.lane; i < (n << lgpx); i += 32)
+    {
+        const int cand = i >> lgpx, rem = i & (npx - 1);
+        const int mqx = cand == 0 ? cqx[0] : cand == 1 ? cqx[1] : cand == 2 ? cqx[2] : cqx[3];
+        const int mqy = cand == 0 ? cqy[0] : cand == 1 ? cqy[1] : cand == 2 ? cqy[2] : cqy[3];
+        const int xf = mqx & 3, yf = mqy & 3;
+        const int y = rem >> c.lgw, x = rem & (c.w - 1);
+        const P* r = c.ref[0] + (mqx >> 2) + (ptrdiff_t)(mqy >> 2) * c.rstride;
+        int v;
+        if (!(xf | yf)) v = r[(ptrdiff_t)y * c.rstride + x];
+        else if (!yf)
+        {
+            const P* s = r + (ptrdiff_t)y * c.rstride + x - 3;
+            const int16_t* cx = c_lumaFilter[xf];
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += (int)s[k] * cx[k];
+            v = interp_finish<DEPTH>(sum, 0);
+        }
+        else if (!xf)
+        {
+            const P* s = r + (ptrdiff_t)(y - 3) * c.rstride + x;
+            const int16_t* cy = c_lumaFilter[yf];
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += (int)s[(ptrdiff_t)k * c.rstride] * cy[k];
+            v = interp_finish<DEPTH>(sum, 0);
+        }
+        else
+        {
+            const int16_t* cy = c_lumaFilter[yf];
+            const int16_t* m = c.sm->mid + cand * 368 + (y << c.lgw) + x;
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += (int)m[k << c.lgw] * cy[k];
+            v = interp_finish<DEPTH>(sum, 2);
+        }
+        c.sm->pred[(cand << 8) + rem] = (uint16_t)v;
+    }
+    __syncwarp();
+    // phase 3: distortion; per-lane partials for (candidate, element) then a per-candidate fold
+    int part[4] = { 0, 0, 0, 0 };
+    if (!satd)
+    {
+        for (int i = c.lane; i < (n << lgpx); i += 32)
+        {
+            const int cand = i >> lgpx, rem = i & (npx - 1);
+            const int y = rem >> c.lgw, x = rem & (c.w - 1);
+            int d = abs((int)c.fenc[y * c.fstride + x] - (int)c.sm->pred[(cand << 8) + rem]);
+            part[0] += cand == 0 ? d : 0; part[1] += cand == 1 ? d : 0; part[2] += cand == 2 ? d : 0; part[3] += cand == 3 ? d : 0;
+        }
+    }
+    else
+    {
+        // tiles: 8x4 when w >= 8 (halved per tile), 4x4 when w == 4 (pixel.cpp:1134-1158)
+        const int tw = c.w >= 8 ? 8 : 4;
+        const int lgtpr = c.lgw - (c.w >= 8 ? 3 : 2);               // log2 tiles per row
+        const int lgtiles = lgtpr + lgh - 2;                         // log2 tiles per candidate
+        for (int i = c.lane; i < (n << lgtiles); i += 32)
+        {
+            const int cand = i >> lgtiles, t = i & ((1 << lgtiles) - 1);
+            const int ty = t >> lgtpr, tx = t & ((1 << lgtpr) - 1);
+            const P* pf = c.fenc + (ty * 4) * c.fstride + tx * tw;
+            const uint16_t* pp = c.sm->pred + (cand << 8) + ((ty * 4) << c.lgw) + tx * tw;
+            int d;
+            if (tw == 8) d = (had4x4_abs(pf, c.fstride, pp, c.w) + had4x4_abs(pf + 4, c.fstride, pp + 4, c.w)) >> 1;
+            else         d = had4x4_abs(pf, c.fstride, pp, c.w) >> 1;
+            part[0] += cand == 0 ? d : 0; part[1] += cand == 1 ? d : 0; part[2] += cand == 2 ? d : 0; part[3] += cand == 3 ? d : 0;
+        }
+    }
+    int out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        int t = warp_sum(part[k]);
+        if (c.lane == k) out = t;
+    }
+    return out;
+}
+
+// distortion of up to 8 sub-pel candidates, lane i (< n) owns candidate i; result in lane i
+template <typename P>
+__device__ int me_subpel_batch(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+{
+    int out = 0;
+    if (c.pow2 && c.w <= 16 && c.h <= 16)
+    {
+        for (int base = 0; base < n; base += 4)
+        {
+            const int src = min(base + (c.lane & 3), n - 1);
+            const int bqx = __shfl_sync(0xffffffffu, qx, src), bqy = __shfl_sync(0xffffffffu, qy, src);
+            int v = me_subpel_multi_small(c, min(4, n - base), bqx, bqy, satd);
+            v = __shfl_sync(0xffffffffu, v, (c.lane - base) & 3);
+            if (c.lane >= base && c.lane < base + 4) out = v;
+        }
+    }
+    else
+    {
+        for (int k = 0; k < n; k++)
+        {
+            const int kqx = __shfl_sync(0xffffffffu, qx, k), kqy = __shfl_sync(0xffffffffu, qy, k);
+            int v = me_subpel_compare(c, kqx, kqy, satd);
+            if (c.lane == k) out = v;
+        }
+    }
+    return out;
 }
 
 // lowresQPelCost (lowres.h:94-120): qpel = rounded average of the two nearest hpel planes; 8x8 blocks
@@ -195,7 +467,6 @@ __device__ int me_lowres_cost(const MeCtx<P>& c, int qx, int qy, bool satd)
             c.sm->pred[y * 64 + x] = (uint16_t)(((int)a[(ptrdiff_t)y * c.rstride + x] + (int)b[(ptrdiff_t)y * c.rstride + x] + 1) >> 1);
         }
         __syncwarp();
-        // lowres PUs are 8x8 (common.h:217-218); the compare uses the job's w,h like the reference's comp()
         return warp_sum(me_band_cost(c, 0, c.h, satd));
     }
     int hp = (qy & 2) | ((qx & 2) >> 1);
@@ -218,72 +489,75 @@ __device__ __forceinline__ int me_cost_fpel(const MeCtx<P>& c, int x, int y)
 
 struct MeStar { int bx, by, bcost, point, dist; };
 
-template <typename P>
-__device__ __forceinline__ void me_star_try(const MeCtx<P>& c, MeStar& s, int x, int y, int point, int dist)
+// fold a burst in the reference's order: strict '<' keeps the earliest minimum
+__device__ __forceinline__ void me_fold(MeStar& s, int n, int cost, int px, int py, int point, int dist)
 {
-    int cost = me_cost_fpel(c, x, y);
-    if (cost < s.bcost) { s.bcost = cost; s.bx = x; s.by = y; s.point = point; s.dist = dist; }
+    for (int i = 0; i < n; i++)
+    {
+        const int ci = __shfl_sync(0xffffffffu, cost, i);
+        if (ci < s.bcost)
+        {
+            s.bcost = ci;
+            s.bx = __shfl_sync(0xffffffffu, px, i); s.by = __shfl_sync(0xffffffffu, py, i);
+            s.point = __shfl_sync(0xffffffffu, point, i); s.dist = __shfl_sync(0xffffffffu, dist, i);
+        }
+    }
 }
 
-// StarPatternSearch (motion.cpp:362-604).  The reference's x4 fast path visits the same points in
-// the same order as its bounds-checked path, so one checked walk reproduces both.
+// StarPatternSearch (motion.cpp:362-604).  Each distance level is one burst; candidate order inside
+// a level is the reference's (its x4 fast path and its bounds-checked path visit the same points in
+// the same order), out-of-range candidates are dropped before evaluation.
 template <typename P>
 __device__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters, int merange)
 {
-    const int ox = s.bx, oy = s.by;
+    const int ox = s.bx, oy = s.by, lane = c.lane;
     int saved = s.bcost, rounds = 0;
     {
-        if (oy - 1 >= c.miny) me_star_try(c, s, ox, oy - 1, 2, 1);
-        if (ox - 1 >= c.minx) me_star_try(c, s, ox - 1, oy, 4, 1);
-        if (ox + 1 <= c.maxx) me_star_try(c, s, ox + 1, oy, 5, 1);
-        if (oy + 1 <= c.maxy) me_star_try(c, s, ox, oy + 1, 7, 1);
+        // dist 1: top(2) left(4) right(5) bottom(7)
+        int px = ox + (lane == 1 ? -1 : lane == 2 ? 1 : 0), py = oy + (lane == 0 ? -1 : lane == 3 ? 1 : 0);
+        int point = lane == 0 ? 2 : lane == 1 ? 4 : lane == 2 ? 5 : 7, dist = 1;
+        bool valid = lane < 4 && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
+        int n = me_compact(valid, px, py, point, dist);
+        int cost = me_eval_points(c, n, px, py, false);
+        me_fold(s, n, cost, px, py, point, dist);
         if (s.bcost < saved) rounds = 0;
         else if (++rounds >= earlyExitIters) return;
     }
     for (int d = 2; d <= 8; d <<= 1)
     {
-        const int top = oy - d, bot = oy + d, lft = ox - d, rgt = ox + d, h2 = d >> 1;
-        const int top2 = oy - h2, bot2 = oy + h2, lft2 = ox - h2, rgt2 = ox + h2;
+        // order: 2(top) 1 3 4(left) 5(right) 6 8 7(bottom); half-distance points need both their checks
+        const int h2 = d >> 1;
+        const int8_t dxs[8] = { 0, -1, 1, -2, 2, -1, 1, 0 }, dys[8] = { -2, -1, -1, 0, 0, 1, 1, 2 };
+        const int8_t pts[8] = { 2, 1, 3, 4, 5, 6, 8, 7 };
+        const int k = lane & 7;
+        int px = ox + dxs[k] * h2, py = oy + dys[k] * h2;
+        int point = pts[k], dist = (k == 1 || k == 2 || k == 5 || k == 6) ? h2 : d;
+        bool valid = lane < 8 && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
         saved = s.bcost;
-        if (top >= c.miny) me_star_try(c, s, ox, top, 2, d);
-        if (top2 >= c.miny)
-        {
-            if (lft2 >= c.minx) me_star_try(c, s, lft2, top2, 1, h2);
-            if (rgt2 <= c.maxx) me_star_try(c, s, rgt2, top2, 3, h2);
-        }
-        if (lft >= c.minx) me_star_try(c, s, lft, oy, 4, d);
-        if (rgt <= c.maxx) me_star_try(c, s, rgt, oy, 5, d);
-        if (bot2 <= c.maxy)
-        {
-            if (lft2 >= c.minx) me_star_try(c, s, lft2, bot2, 6, h2);
-            if (rgt2 <= c.maxx) me_star_try(c, s, rgt2, bot2, 8, h2);
-        }
-        if (bot <= c.maxy) me_star_try(c, s, ox, bot, 7, d);
+        int n = me_compact(valid, px, py, point, dist);
+        int cost = me_eval_points(c, n, px, py, false);
+        me_fold(s, n, cost, px, py, point, dist);
         if (s.bcost < saved) rounds = 0;
         else if (++rounds >= earlyExitIters) return;
     }
     for (int d = 16; d <= merange; d <<= 1)
     {
-        const int top = oy - d, bot = oy + d, lft = ox - d, rgt = ox + d, q = d >> 2;
-        saved = s.bcost;
-        if (top >= c.miny) me_star_try(c, s, ox, top, 0, d);
-        if (lft >= c.minx) me_star_try(c, s, lft, oy, 0, d);
-        if (rgt <= c.maxx) me_star_try(c, s, rgt, oy, 0, d);
-        if (bot <= c.maxy) me_star_try(c, s, ox, bot, 0, d);
-        for (int k = 1; k < 4; k++)
+        // order: top, left, right, bottom, then k = 1..3: (xl,yt) (xr,yt) (xl,yb) (xr,yb)
+        const int q = d >> 2;
+        int px, py;
+        if (lane < 4) { px = ox + (lane == 1 ? -d : lane == 2 ? d : 0); py = oy + (lane == 0 ? -d : lane == 3 ? d : 0); }
+        else
         {
-            const int yt = top + q * k, yb = bot - q * k, xl = ox - q * k, xr = ox + q * k;
-            if (yt >= c.miny)
-            {
-                if (xl >= c.minx) me_star_try(c, s, xl, yt, 0, d);
-                if (xr <= c.maxx) me_star_try(c, s, xr, yt, 0, d);
-            }
-            if (yb <= c.maxy)
-            {
-                if (xl >= c.minx) me_star_try(c, s, xl, yb, 0, d);
-                if (xr <= c.maxx) me_star_try(c, s, xr, yb, 0, d);
-            }
+            const int k = ((lane - 4) >> 2) + 1, m = (lane - 4) & 3;
+            px = ox + ((m & 1) ? q * k : -q * k);
+            py = (m & 2) ? (oy + d - q * k) : (oy - d + q * k);
         }
+        int point = 0, dist = d;
+        bool valid = lane < 16 && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
+        saved = s.bcost;
+        int n = me_compact(valid, px, py, point, dist);
+        int cost = me_eval_points(c, n, px, py, false);
+        me_fold(s, n, cost, px, py, point, dist);
         if (s.bcost < saved) rounds = 0;
         else if (++rounds >= earlyExitIters) return;
     }
@@ -297,6 +571,27 @@ __constant__ int8_t c_star_off[16][2] = { {-1,0},{0,-1}, {-1,-1},{1,-1}, {-1,0},
 // motion.cpp:48-58 {hpel_iters, hpel_dirs, qpel_iters, qpel_dirs, hpel_satd}
 __constant__ int8_t c_workload[8][5] = { {1,4,0,4,0}, {1,4,1,4,0}, {1,4,1,4,1}, {2,4,1,4,1}, {2,4,2,4,1}, {1,8,1,8,1}, {2,8,1,8,1}, {2,8,2,8,1} };
 
+// one sub-pel refinement round (motion.cpp:1506-1523 / :1537-1553): candidates bmv + square1[1..dirs]*step,
+// folded in order with strict '<'; returns the winning direction (0 = none)
+template <typename P>
+__device__ __forceinline__ int me_subpel_round(const MeCtx<P>& c, int bx, int by, int dirs, int step, bool satd, int qminy, int qmaxy, int& bcost)
+{
+    const int lane = c.lane;
+    const int i1 = min(lane + 1, 8);
+    int qx = bx + c_square1[i1][0] * step, qy = by + c_square1[i1][1] * step, dir = lane + 1, dummy = 0;
+    bool valid = lane < dirs && !((qy < qminy) | (qy > qmaxy));
+    int n = me_compact(valid, qx, qy, dir, dummy);
+    int cost = me_subpel_batch(c, n, qx, qy, satd);
+    if (lane < n) cost += me_mvcost(c, qx, qy);
+    int bdir = 0;
+    for (int i = 0; i < n; i++)
+    {
+        const int ci = __shfl_sync(0xffffffffu, cost, i);
+        if (ci < bcost) { bcost = ci; bdir = __shfl_sync(0xffffffffu, dir, i); }
+    }
+    return bdir;
+}
+
 template <typename P>
 __device__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restrict__ out)
 {
@@ -304,9 +599,8 @@ __device__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restr
     const int merange = j.merange;
 #define ME_YOK(y) (((y) >= c.miny) & ((y) <= c.maxy))
 #define ME_INRANGE(x, y) ((x) >= c.minx && (x) <= c.maxx && (y) >= c.miny && (y) <= c.maxy)
-    int pmvx = min(max(c.mvpx, qminx), qmaxx) , pmvy = min(max(c.mvpy, qminy), qmaxy);
-    // NB: clipped() = min with max first, then max with min (mv.h:100-105); identical when min <= max
-    pmvx = max(min(c.mvpx, qmaxx), qminx); pmvy = max(min(c.mvpy, qmaxy), qminy);
+    // clipped() = min with max first, then max with min (mv.h:100-105)
+    const int pmvx = max(min(c.mvpx, qmaxx), qminx), pmvy = max(min(c.mvpy, qmaxy), qminy);
     int bestprex = pmvx, bestprey = pmvy;
     int bprecost = me_qpel_cost(c, pmvx, pmvy, false);
     int bmx = (pmvx + 2) >> 2, bmy = (pmvy + 2) >> 2;
@@ -425,25 +719,24 @@ __device__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restr
             const int RD = 5;
             if (s.dist > RD)
             {
-                for (int ty = c.miny; ty <= c.maxy; ty += RD)
-                    for (int tx = c.minx; tx <= c.maxx; tx += RD)
+                // raster refinement (motion.cpp:1171-1201): grid of step 5 over the whole window, 32 points per burst.
+                // Every 4th column of a row (when it closes a full x4 group) adds mvcost(tmv << 3) as in the reference.
+                const int ncols = (c.maxx - c.minx) / RD + 1, nrows = (c.maxy - c.miny) / RD + 1;
+                const int total = ncols * nrows;
+                for (int base = 0; base < total; base += 32)
+                {
+                    const int idx = min(base + c.lane, total - 1);
+                    const int rj = idx / ncols, ri = idx - rj * ncols;
+                    int px = c.minx + ri * RD, py = c.miny + rj * RD;
+                    const int n = min(32, total - base);
+                    const bool x8 = (ri & 3) == 3;
+                    int cost = me_eval_points(c, n, px, py, x8);
+                    for (int i = 0; i < n; i++)
                     {
-                        if (tx + RD * 3 <= c.maxx)
-                        {
-                            for (int k = 0; k < 4; k++)
-                            {
-                                int sad = me_sad_direct(c, c.ref[0] + tx + (ptrdiff_t)ty * c.rstride);
-                                int cost = sad + (k < 3 ? me_mvcost(c, tx * 4, ty * 4) : me_mvcost(c, tx * 8, ty * 8));
-                                if (cost < s.bcost) { s.bcost = cost; s.bx = tx; s.by = ty; }
-                                if (k < 3) tx += RD;
-                            }
-                        }
-                        else
-                        {
-                            int cost = me_cost_fpel(c, tx, ty);
-                            if (cost < s.bcost) { s.bcost = cost; s.bx = tx; s.by = ty; }
-                        }
+                        const int ci = __shfl_sync(0xffffffffu, cost, i);
+                        if (ci < s.bcost) { s.bcost = ci; s.bx = __shfl_sync(0xffffffffu, px, i); s.by = __shfl_sync(0xffffffffu, py, i); }
                     }
+                }
             }
             while (s.dist > 0)
             {
@@ -497,28 +790,14 @@ __device__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restr
         if (wl[4]) { bcost = me_subpel_compare(c, bx, by, true) + me_mvcost(c, bx, by); hsatd = true; }
         for (int it = 0; it < wl[0]; it++)
         {
-            int bdir = 0;
-            for (int i = 1; i <= wl[1]; i++)
-            {
-                int qx = bx + c_square1[i][0] * 2, qy = by + c_square1[i][1] * 2;
-                if ((qy < qminy) | (qy > qmaxy)) continue;
-                int cost = me_subpel_compare(c, qx, qy, hsatd) + me_mvcost(c, qx, qy);
-                if (cost < bcost) { bcost = cost; bdir = i; }
-            }
+            int bdir = me_subpel_round(c, bx, by, wl[1], 2, hsatd, qminy, qmaxy, bcost);
             if (bdir) { bx += c_square1[bdir][0] * 2; by += c_square1[bdir][1] * 2; }
             else break;
         }
         if (!wl[4]) bcost = me_subpel_compare(c, bx, by, true) + me_mvcost(c, bx, by);
         for (int it = 0; it < wl[2]; it++)
         {
-            int bdir = 0;
-            for (int i = 1; i <= wl[3]; i++)
-            {
-                int qx = bx + c_square1[i][0], qy = by + c_square1[i][1];
-                if ((qy < qminy) | (qy > qmaxy)) continue;
-                int cost = me_subpel_compare(c, qx, qy, true) + me_mvcost(c, qx, qy);
-                if (cost < bcost) { bcost = cost; bdir = i; }
-            }
+            int bdir = me_subpel_round(c, bx, by, wl[3], 1, true, qminy, qmaxy, bcost);
             if (bdir) { bx += c_square1[bdir][0]; by += c_square1[bdir][1]; }
             else break;
         }
@@ -530,9 +809,9 @@ __device__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restr
 
 // persistent warps, dynamic job fetch (jobs differ by up to 64x in work)
 template <typename P>
-__global__ void __launch_bounds__(256) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
-                                            const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
-                                            int32_t* __restrict__ out, int* __restrict__ counter)
+__global__ void __launch_bounds__(256, 3) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
+                                               const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
+                                               int32_t* __restrict__ out, int* __restrict__ counter)
 {
     extern __shared__ unsigned char me_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -551,7 +830,18 @@ __global__ void __launch_bounds__(256) k_me(const P* __restrict__ fenc, int fstr
         c.rstride = rstride; c.mvc = mvcost;
         c.mvpx = j.qmvp[0]; c.mvpy = j.qmvp[1];
         c.minx = j.mvmin[0]; c.miny = j.mvmin[1]; c.maxx = j.mvmax[0]; c.maxy = j.mvmax[1];
-        c.w = j.pw; c.h = j.ph; c.lane = lane; c.lowres = lowres; c.sm = sm;
+        c.w = j.pw; c.h = j.ph; c.lgw = 31 - __clz(c.w); c.lane = lane; c.lowres = lowres; c.sm = sm;
+        c.pow2 = ((c.w & (c.w - 1)) | (c.h & (c.h - 1))) == 0;
+        const int wpr = (c.w * (int)sizeof(P)) >> 2;            // words per row (>= 1: w >= 4)
+        c.lgwpr = 31 - __clz(wpr);
+        c.nw = wpr * c.h; c.lgnw = 31 - __clz(c.nw);
+        c.fw = 0;
+        if (c.pow2 && c.nw <= 32)
+        {   // every lane caches the fenc word of its slot (lane mod nw): groups of nw lanes evaluate different candidates
+            const int wd = lane & (c.nw - 1);
+            int row = wd >> c.lgwpr, col = wd & (wpr - 1);
+            c.fw = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * fstride) * sizeof(P) + col * 4);
+        }
         me_run_job<P>(c, j, out + (size_t)jid * 4);
         __syncwarp();
     }
@@ -564,7 +854,7 @@ static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, 
     CU_CHECK(cudaMemsetAsync(counter_dev, 0, sizeof(int), ctx->stream));
     const int threads = 256, warps = threads / 32;
     const size_t smem = sizeof(MeShared) * warps;
-    int blocks = ctx->sm_count * 4;
+    int blocks = ctx->sm_count * 3;
     int need = (n + warps - 1) / warps;
     if (blocks > need) blocks = need;
     if (depth == 8)

@@ -216,6 +216,9 @@ _AN_PROTOS = {
     "x265cu_analyser_run_resident": (I, [P, I]),
     "x265cu_analyser_analyse": (I, [P, P, I, P, I, C.POINTER(AnalysisOut)]),
     "x265cu_analyser_fetch": (I, [P, I, P]),
+    "x265cu_analyser_stage_ms": (I, [P, C.POINTER(C.c_float)]),
+    "x265cu_analyser_ref_plane": (P, [P, I, C.POINTER(I)]),
+    "x265cu_analyser_ref_updated": (I, [P, I]),
 }
 _PROTOS.update(_AN_PROTOS)
 
@@ -279,6 +282,18 @@ class Analyser:
 
     def d2h_bytes(self):
         return self.me_packed.nbytes + self.cu_sse.nbytes + self.cu_numsig.nbytes + self.cu_ref.nbytes + self.intra_cost.nbytes
+
+    def stage_ms(self):
+        ms = (C.c_float * 4)()
+        self.lib.check(self.lib.L.x265cu_analyser_stage_ms(self.h, ms))
+        return [float(x) for x in ms]
+
+    def ref_plane_ptr(self, idx):
+        st = I()
+        return self.lib.L.x265cu_analyser_ref_plane(self.h, idx, C.byref(st)), st.value
+
+    def ref_updated(self, idx):
+        self.lib.check(self.lib.L.x265cu_analyser_ref_updated(self.h, idx))
 
     def fetch(self, what):
         es = np.dtype(self.dtype).itemsize
