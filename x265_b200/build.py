@@ -20,6 +20,8 @@ def _newest_source():
 
 
 def build(force=False, verbose=False):
+    if os.environ.get("X265CU_LIB"):          # experiment hook: use a specific prebuilt variant
+        return os.environ["X265CU_LIB"]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

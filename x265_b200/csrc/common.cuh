@@ -36,9 +36,7 @@ __device__ __forceinline__ int clip16(int v) { return min(max(v, -32768), 32767)
 
 __device__ __forceinline__ int warp_sum(int v)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    return __reduce_add_sync(0xffffffffu, v);          // REDUX.SUM: one instruction on sm_80+
 }
 __device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v)
 {

@@ -174,12 +174,17 @@ __device__ __forceinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, 
     return cost;
 }
 
-// keep only the valid candidates, preserving order: returns n and moves candidate k to lane k
-__device__ __forceinline__ int me_compact(bool valid, int& a, int& b, int& c2, int& d)
+// keep only the valid candidates, preserving order: returns n and moves candidate k to lane k.
+// `cnt` = number of generated candidates (lanes >= cnt are invalid by construction).
+__device__ __forceinline__ int me_compact(bool valid, int cnt, int& a, int& b, int& c2, int& d)
 {
     const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (m == ((cnt >= 32) ? 0xffffffffu : ((1u << cnt) - 1u))) return cnt;      // common case: nothing to drop
     const int lane = threadIdx.x & 31;
-    const int src = __fns(m, 0, lane + 1) & 31;          // position of the (lane+1)-th set bit (garbage if none)
+    // lane k takes the candidate of the k-th set bit: strip the k lowest set bits, then find-first-set
+    unsigned t = m;
+    for (int k = 0; k < lane && t; k++) t &= t - 1;
+    const int src = t ? (__ffs(t) - 1) : 0;
     a = __shfl_sync(0xffffffffu, a, src); b = __shfl_sync(0xffffffffu, b, src);
     c2 = __shfl_sync(0xffffffffu, c2, src); d = __shfl_sync(0xffffffffu, d, src);
     return __popc(m);
@@ -489,18 +494,25 @@ __device__ __forceinline__ int me_cost_fpel(const MeCtx<P>& c, int x, int y)
 
 struct MeStar { int bx, by, bcost, point, dist; };
 
-// fold a burst in the reference's order: strict '<' keeps the earliest minimum
+// Fold a burst in the reference's order.  The sequential `if (cost < bcost)` chain keeps the EARLIEST
+// candidate among those reaching the minimum, so it equals one arg-min with ties to the lowest index:
+// pack (cost << 5 | index) and take a single warp min (REDUX.MIN).  Costs stay below 2^26.
+__device__ __forceinline__ int me_argmin(int n, int cost, int lane)
+{
+    unsigned key = (lane < n) ? (((unsigned)cost << 5) | (unsigned)lane) : 0xffffffffu;
+    return (int)__reduce_min_sync(0xffffffffu, key);
+}
 __device__ __forceinline__ void me_fold(MeStar& s, int n, int cost, int px, int py, int point, int dist)
 {
-    for (int i = 0; i < n; i++)
+    if (n <= 0) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned key = (unsigned)me_argmin(n, cost, lane);
+    const int best = (int)(key >> 5), i = (int)(key & 31);
+    if (best < s.bcost)
     {
-        const int ci = __shfl_sync(0xffffffffu, cost, i);
-        if (ci < s.bcost)
-        {
-            s.bcost = ci;
-            s.bx = __shfl_sync(0xffffffffu, px, i); s.by = __shfl_sync(0xffffffffu, py, i);
-            s.point = __shfl_sync(0xffffffffu, point, i); s.dist = __shfl_sync(0xffffffffu, dist, i);
-        }
+        s.bcost = best;
+        s.bx = __shfl_sync(0xffffffffu, px, i); s.by = __shfl_sync(0xffffffffu, py, i);
+        s.point = __shfl_sync(0xffffffffu, point, i); s.dist = __shfl_sync(0xffffffffu, dist, i);
     }
 }
 
@@ -517,7 +529,7 @@ __device__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters
         int px = ox + (lane == 1 ? -1 : lane == 2 ? 1 : 0), py = oy + (lane == 0 ? -1 : lane == 3 ? 1 : 0);
         int point = lane == 0 ? 2 : lane == 1 ? 4 : lane == 2 ? 5 : 7, dist = 1;
         bool valid = lane < 4 && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
-        int n = me_compact(valid, px, py, point, dist);
+        int n = me_compact(valid, 4, px, py, point, dist);
         int cost = me_eval_points(c, n, px, py, false);
         me_fold(s, n, cost, px, py, point, dist);
         if (s.bcost < saved) rounds = 0;
@@ -534,7 +546,7 @@ __device__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters
         int point = pts[k], dist = (k == 1 || k == 2 || k == 5 || k == 6) ? h2 : d;
         bool valid = lane < 8 && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
         saved = s.bcost;
-        int n = me_compact(valid, px, py, point, dist);
+        int n = me_compact(valid, 8, px, py, point, dist);
         int cost = me_eval_points(c, n, px, py, false);
         me_fold(s, n, cost, px, py, point, dist);
         if (s.bcost < saved) rounds = 0;
@@ -555,7 +567,7 @@ __device__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters
         int point = 0, dist = d;
         bool valid = lane < 16 && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
         saved = s.bcost;
-        int n = me_compact(valid, px, py, point, dist);
+        int n = me_compact(valid, 16, px, py, point, dist);
         int cost = me_eval_points(c, n, px, py, false);
         me_fold(s, n, cost, px, py, point, dist);
         if (s.bcost < saved) rounds = 0;
@@ -580,14 +592,14 @@ __device__ __forceinline__ int me_subpel_round(const MeCtx<P>& c, int bx, int by
     const int i1 = min(lane + 1, 8);
     int qx = bx + c_square1[i1][0] * step, qy = by + c_square1[i1][1] * step, dir = lane + 1, dummy = 0;
     bool valid = lane < dirs && !((qy < qminy) | (qy > qmaxy));
-    int n = me_compact(valid, qx, qy, dir, dummy);
+    int n = me_compact(valid, dirs, qx, qy, dir, dummy);
     int cost = me_subpel_batch(c, n, qx, qy, satd);
     if (lane < n) cost += me_mvcost(c, qx, qy);
     int bdir = 0;
-    for (int i = 0; i < n; i++)
+    if (n > 0)
     {
-        const int ci = __shfl_sync(0xffffffffu, cost, i);
-        if (ci < bcost) { bcost = ci; bdir = __shfl_sync(0xffffffffu, dir, i); }
+        const unsigned key = (unsigned)me_argmin(n, cost, lane);
+        if ((int)(key >> 5) < bcost) { bcost = (int)(key >> 5); bdir = __shfl_sync(0xffffffffu, dir, (int)(key & 31)); }
     }
     return bdir;
 }
@@ -731,10 +743,11 @@ __device__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restr
                     const int n = min(32, total - base);
                     const bool x8 = (ri & 3) == 3;
                     int cost = me_eval_points(c, n, px, py, x8);
-                    for (int i = 0; i < n; i++)
+                    const unsigned key = (unsigned)me_argmin(n, cost, c.lane);
+                    if ((int)(key >> 5) < s.bcost)
                     {
-                        const int ci = __shfl_sync(0xffffffffu, cost, i);
-                        if (ci < s.bcost) { s.bcost = ci; s.bx = __shfl_sync(0xffffffffu, px, i); s.by = __shfl_sync(0xffffffffu, py, i); }
+                        s.bcost = (int)(key >> 5);
+                        s.bx = __shfl_sync(0xffffffffu, px, (int)(key & 31)); s.by = __shfl_sync(0xffffffffu, py, (int)(key & 31));
                     }
                 }
             }
@@ -808,8 +821,11 @@ __device__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restr
 }
 
 // persistent warps, dynamic job fetch (jobs differ by up to 64x in work)
+#ifndef ME_MIN_BLOCKS
+#define ME_MIN_BLOCKS 2
+#endif
 template <typename P>
-__global__ void __launch_bounds__(256, 3) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
+__global__ void __launch_bounds__(256, ME_MIN_BLOCKS) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
                                                const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
                                                int32_t* __restrict__ out, int* __restrict__ counter)
 {
@@ -854,7 +870,7 @@ static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, 
     CU_CHECK(cudaMemsetAsync(counter_dev, 0, sizeof(int), ctx->stream));
     const int threads = 256, warps = threads / 32;
     const size_t smem = sizeof(MeShared) * warps;
-    int blocks = ctx->sm_count * 3;
+    int blocks = ctx->sm_count * ME_MIN_BLOCKS;
     int need = (n + warps - 1) / warps;
     if (blocks > need) blocks = need;
     if (depth == 8)
