@@ -383,7 +383,10 @@ template <typename P> struct T
     template <int N> static void idct(const int16_t* s, int16_t* d, intptr_t st) { transform<P>(X265CU_IDCT, N, s, d, st); }
     static void dst4(const int16_t* s, int16_t* d, intptr_t st) { transform<P>(X265CU_DST4, 4, s, d, st); }
     static void idst4(const int16_t* s, int16_t* d, intptr_t st) { transform<P>(X265CU_IDST4, 4, s, d, st); }
+    // table slots: [PLANAR_IDX] and [DC_IDX] ignore dirMode like the C entries (intrapred.cpp:69-100), the angular slots use it
     template <int N> static void intra_predf(P* d, intptr_t ds, const P* nb, int mode, int bf) { intra_pred<P>(N, d, ds, nb, mode, bf); }
+    template <int N> static void intra_planarf(P* d, intptr_t ds, const P* nb, int, int bf) { intra_pred<P>(N, d, ds, nb, 0, bf); }
+    template <int N> static void intra_dcf(P* d, intptr_t ds, const P* nb, int, int bf) { intra_pred<P>(N, d, ds, nb, 1, bf); }
     template <int N> static void intra_filterf(const P* nb, P* f) { intra_filter<P>(N, nb, f); }
     template <int N> static void intra_allangsf(P* d, P* r, P* f, int bl) { intra_allangs<P>(N, d, r, f, bl); }
     static uint32_t quantf(const int16_t* c, const int32_t* q, int32_t* du, int16_t* qc, int qb, int add, int n) { return quant(c, q, du, qc, qb, add, n, 0); }
@@ -454,7 +457,14 @@ static void* lookup(const char* name, int i, int j, int k)
     CU_ENTRY("cu.copy_cnt", copy_cnt, 0, 3) CU_ENTRY("cu.count_nonzero", count_nonzero, 0, 3)
     CU_ENTRY("cu.dct", dct, 0, 3) CU_ENTRY("cu.idct", idct, 0, 3)
     CU_ENTRY("cu.intra_filter", intra_filterf, 0, 3) CU_ENTRY("cu.intra_pred_allangs", intra_allangsf, 0, 3)
-    if (!strcmp(name, "cu.intra_pred")) { static void* const t[5] = CU_LIST(X::template intra_predf); return (i >= 0 && i <= 3 && j >= 0 && j < 35) ? t[i] : NULL; }
+    if (!strcmp(name, "cu.intra_pred"))
+    {
+        static void* const ta[5] = CU_LIST(X::template intra_predf);
+        static void* const tp[5] = CU_LIST(X::template intra_planarf);
+        static void* const td[5] = CU_LIST(X::template intra_dcf);
+        if (!(i >= 0 && i <= 3 && j >= 0 && j < 35)) return NULL;
+        return j == 0 ? tp[i] : (j == 1 ? td[i] : ta[i]);
+    }
     if (!strcmp(name, "cu.copy_pp")) { static void* const t[5] = { (void*)X::template copy_pp<4,4>, (void*)X::template copy_pp<8,8>, (void*)X::template copy_pp<16,16>, (void*)X::template copy_pp<32,32>, (void*)X::template copy_pp<64,64> }; return (i >= 0 && i < 5) ? t[i] : NULL; }
     if (!strcmp(name, "dst4x4")) return (void*)X::dst4;
     if (!strcmp(name, "idst4x4")) return (void*)X::idst4;
