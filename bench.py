@@ -163,6 +163,7 @@ def plane_as_tensor(torch, ptr, nbytes, device):
 def run_ours(args, rank, world, local_rank):
     import torch
     import x265_b200
+    from x265_b200 import shard
     from frame_helpers import gen_luma, make_field, MARGIN_X, MARGIN_Y
     dist = None
     if world > 1:
@@ -176,7 +177,7 @@ def run_ours(args, rank, world, local_rank):
     # synthetic clip (BASELINE.md generator): refs = frames 3..0, this rank's current frame = 4 + rank
     for r in range(NREFS):
         an.set_ref(r, gen_luma(W, H, NREFS - 1 - r))
-    cur = gen_luma(W, H, NREFS + rank)
+    cur = gen_luma(W, H, NREFS + shard.frame_of(0, rank, world))
     field = make_field(W, H, NREFS)
     # pinned host buffers: these are what the user hands to the public call
     pin = lib.L.x265cu_host_alloc(W * H)
@@ -194,7 +195,7 @@ def run_ours(args, rank, world, local_rank):
 
     def exchange(step):
         if world > 1:
-            dist.broadcast(ref0, src=step % world)          # newest reconstructed reference plane from its owner
+            shard.exchange_ref(dist, ref0, step, world)     # newest reconstructed reference plane from its owner
             torch.cuda.current_stream().synchronize()
 
     def barrier():
