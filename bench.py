@@ -142,7 +142,7 @@ def run_reference_arm(args, rank, world):
             "config": workload_config(), "cpu_baseline": {"value": r["ctus_per_s"], "unit": "CTUs/s", "cores": threads, "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["ctus_per_s"], "unit": "CTUs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def workload_config():
@@ -291,13 +291,17 @@ def run_ours(args, rank, world, local_rank):
         line["checks"] = {"me_cost_sum": int(an.me_packed[:, 0].astype(np.int64).sum()), "numsig_sum": int(an.cu_numsig.astype(np.int64).sum()),
                           "sse_sum": int(an.cu_sse.astype(np.uint64).sum()), "intra_best_hist_nonzero": int((an.intra_cost[:, 35] > 0).sum()),
                           "mv_nonzero": int((mv != 0).sum())}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     an.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # keep stdout clean for the ONE JSON line: library chatter (e.g. "NCCL version ...") goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -1,0 +1,139 @@
+"""Per-primitive-class throughput of the batched kernels at frame scale (the second half of BASELINE.json's
+metric: "per-primitive HBM GB/s vs peak").  Each class runs ONE launch over a 3840x2160 frame's worth of
+jobs on device-resident planes; time = CUDA events, median of `reps` after warm-up, L2 flushed between
+repetitions; GB/s = ALGORITHMIC bytes per launch (SURVEY 8(d) per-call formulas x jobs) / time.
+
+    python profiles/primitive_bench.py [--reps 7] [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import x265_b200  # noqa: E402
+from x265_b200.lib import CMP_JOB, BLK_JOB, INTERP_JOB, INTRA_JOB  # noqa: E402
+from frame_helpers import gen_luma, pad_plane, MARGIN_X, MARGIN_Y  # noqa: E402
+
+W, H = 3840, 2160
+FRAMES = 24          # one launch covers a lookahead-window-sized batch: 24 stacked 2160p frames (~200 MB per plane)
+
+
+def timed(lib, flush, fn, reps):
+    for _ in range(2):
+        fn()
+    lib.sync()
+    ts = []
+    for r in range(reps):
+        lib.check(lib.L.x265cu_memset(lib.ctx, flush.ptr, r & 255, flush.nbytes))
+        lib.sync()
+        lib.timer_begin()
+        fn()
+        ts.append(lib.timer_end())
+    return float(np.median(ts))
+
+
+def grid_jobs(dtype, bw, bh, stride, org, fields):
+    xs, ys = np.meshgrid(np.arange(0, W - bw + 1, bw), np.arange(0, H - bh + 1, bh))
+    n = xs.size
+    j = np.zeros(n, dtype)
+    off = (org + ys.ravel() * stride + xs.ravel()).astype(np.int64)
+    return j, off, n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    lib = x265_b200.load()
+    peak = 6567.1
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    flush = lib.alloc(256 << 20)
+    print("batch = %d stacked 2160p frames per launch" % FRAMES)
+    global H
+    fa, fb = gen_luma(W, H, 4), gen_luma(W, H, 3)
+    a, stride, org = pad_plane(np.tile(fa, (FRAMES, 1)), 8)       # FRAMES frames stacked vertically
+    b, _, _ = pad_plane(np.tile(fb, (FRAMES, 1)), 8)
+    H = H * FRAMES
+    dA, dB = lib.to_device(a), lib.to_device(b)
+    rows = []
+
+    def add(name, ms, nbytes, note=""):
+        gbs = nbytes / (ms / 1000.0) / 1e9
+        rows.append({"kernel": name, "ms": ms, "algorithmic_MB": nbytes / 1e6, "GBps": gbs, "frac_of_measured_peak": gbs / peak, "note": note})
+        print("%-34s %8.3f ms %9.1f MB %8.1f GB/s  %5.1f%% of %.0f  %s" % (name, ms, nbytes / 1e6, gbs, 100 * gbs / peak, peak, note), flush=True)
+
+    # ---- pixel compare: whole-frame grids of 8x8 / 16x16 / 64x64 blocks, frame n vs frame n-1 ----
+    for op, (bw, bh) in (("sad", (8, 8)), ("sad", (16, 16)), ("sad", (64, 64)), ("satd", (8, 8)), ("satd", (16, 16)), ("satd", (64, 64)),
+                         ("sa8d", (16, 16)), ("sa8d", (64, 64)), ("sse_pp", (16, 16)), ("sse_pp", (64, 64))):
+        j, off, n = grid_jobs(CMP_JOB, bw, bh, stride, org, None)
+        j["a_off"] = off; j["b_off"] = off + 3 * stride + 5; j["a_stride"] = stride; j["b_stride"] = stride; j["w"] = bw; j["h"] = bh
+        dJ = lib.to_device(j); dO = lib.alloc(8 * n)
+        ms = timed(lib, flush, lambda: lib.pixelcmp_batch(8, op, dA, dB, dJ, n, dO), args.reps)
+        add("k_pixelcmp %s %dx%d grid" % (op, bw, bh), ms, n * (2 * bw * bh + 8), "%d jobs" % n)
+        dJ.free(); dO.free()
+    # ---- interpolation: whole frame as 64x64 / 16x16 hvpp jobs ----
+    dD = lib.alloc(a.nbytes)
+    for op, (bw, bh) in (("hvpp", (64, 64)), ("hvpp", (16, 16)), ("hpp", (64, 64)), ("vpp", (64, 64))):
+        j, off, n = grid_jobs(INTERP_JOB, bw, bh, stride, org, None)
+        j["s_off"] = off; j["d_off"] = off; j["s_stride"] = stride; j["d_stride"] = stride; j["w"] = bw; j["h"] = bh
+        j["idxX"] = 2; j["idxY"] = 3; j["ntaps"] = 8
+        dJ = lib.to_device(j)
+        ms = timed(lib, flush, lambda: lib.interp_batch(8, op, dA, dD, dJ, n), args.reps)
+        halo_w = bw + (7 if op in ("hvpp", "hpp") else 0); halo_h = bh + (7 if op in ("hvpp", "vpp") else 0)
+        add("k_interp luma_%s %dx%d grid" % (op, bw, bh), ms, n * (halo_w * halo_h + bw * bh), "%d jobs" % n)
+        dJ.free()
+    # ---- block ops: sub_ps over the frame as 64x64 blocks (pixel,pixel -> int16) ----
+    dS = lib.alloc(a.size * 2)
+    j, off, n = grid_jobs(BLK_JOB, 64, 64, stride, org, None)
+    j["d_off"] = off; j["a_off"] = off; j["b_off"] = off; j["d_stride"] = stride; j["a_stride"] = stride; j["b_stride"] = stride; j["w"] = 64; j["h"] = 64
+    dJ = lib.to_device(j)
+    ms = timed(lib, flush, lambda: lib.blockop_batch(8, "sub_ps", dS, dA, dB, dJ, n), args.reps)
+    add("k_blockop sub_ps 64x64 grid", ms, n * 64 * 64 * 4, "%d jobs" % n)
+    dJ.free()
+    # ---- transforms / quant on a frame of residual (contiguous TUs) ----
+    r1 = (np.random.default_rng(1).integers(0, 256, W * 2160) - np.random.default_rng(2).integers(0, 256, W * 2160)).astype(np.int16)
+    resid = np.tile(r1, FRAMES // 2)
+    dR = lib.to_device(resid); dC = lib.alloc(resid.nbytes); dQ = lib.alloc(resid.nbytes); dDU = lib.alloc(resid.size * 4)
+    for N in (4, 8, 16, 32):
+        n = resid.size // (N * N)
+        ms = timed(lib, flush, lambda: lib.transform_batch(8, "dct", N, dR, dC, N, N * N, n), args.reps)
+        add("k_transform dct%d" % N, ms, n * 4 * N * N, "%d TUs" % n)
+        ms = timed(lib, flush, lambda: lib.transform_batch(8, "idct", N, dC, dQ, N, N * N, n), args.reps)
+        add("k_transform idct%d" % N, ms, n * 4 * N * N, "%d TUs" % n)
+    qc = lib.to_device(np.full(1024, 18396, np.int32)); ns = lib.alloc(4 * (resid.size // 1024))
+    n = resid.size // 1024
+    ms = timed(lib, flush, lambda: lib.check(lib.L.x265cu_quant_batch(lib.ctx, dC.ptr, qc.ptr, dDU.ptr, dQ.ptr, 19, 85 << 10, 1024, n, 0, ns.ptr)), args.reps)
+    add("k_quant 32x32", ms, n * 1024 * 12 + n * 4, "%d TUs" % n)
+    ms = timed(lib, flush, lambda: lib.check(lib.L.x265cu_dequant_normal_batch(lib.ctx, dQ.ptr, dC.ptr, resid.size, 57 << 5, 6)), args.reps)
+    add("k_dequant_normal", ms, resid.size * 4, "")
+    # ---- intra: all-angs for every 16x16 block of the frame ----
+    N = 16
+    nblk = (W // N) * (2160 // N) * 2
+    nb = np.random.default_rng(3).integers(0, 256, (nblk, 4 * N + 1)).astype(np.uint8)
+    dNB = lib.to_device(nb); dF = lib.alloc(nb.nbytes); dP = lib.alloc(nblk * 33 * N * N)
+    ms = timed(lib, flush, lambda: lib.check(lib.L.x265cu_intra_filter_batch(lib.ctx, 8, N, dNB.ptr, dF.ptr, 4 * N + 1, nblk)), args.reps)
+    add("k_intra_filter 16", ms, nblk * 2 * (4 * N + 1), "%d blocks" % nblk)
+    ms = timed(lib, flush, lambda: lib.check(lib.L.x265cu_intra_allangs_batch(lib.ctx, 8, N, dNB.ptr, dF.ptr, 4 * N + 1, dP.ptr, 1, nblk)), args.reps)
+    add("k_intra_allangs 16", ms, nblk * (2 * (4 * N + 1) + 33 * N * N), "%d blocks" % nblk)
+    # ---- lowres init (+ border extension) ----
+    lw, lh = W // 2, H // 2
+    lstride = (lw + 2 * 32 + 31) // 32 * 32
+    planes = [lib.alloc(lstride * (lh + 64)) for _ in range(4)]
+    lorg = 32 * lstride + 32
+    ms = timed(lib, flush, lambda: lib.check(lib.L.x265cu_frame_init_lowres(lib.ctx, 8, dA.ptr + org, stride, planes[0].ptr + lorg, planes[1].ptr + lorg,
+                                                                             planes[2].ptr + lorg, planes[3].ptr + lorg, lstride, lw, lh, 32, 32)), args.reps)
+    add("k_lowres_init + extend (5 launches)", ms, 2 * W * H, "")
+    if args.json:
+        json.dump({"peak_gbs": peak, "rows": rows}, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

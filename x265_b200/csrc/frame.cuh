@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256) k_cu_residual(const P* __restrict__ fenc,
     __shared__ int16_t s_win[39 * 40];     // (T+7)^2 source window
     __shared__ int16_t s_mid[39 * 32];     // hps(rowExt) intermediate
     __shared__ int16_t s_pred[32 * 32];
-    __shared__ int16_t s_a[32 * 32];
-    __shared__ int16_t s_b[32 * 32];
+    __shared__ int16_t s_a[32 * 34];       // rows padded to 34 in the forward passes (bank-conflict-free column reads)
+    __shared__ int16_t s_b[32 * 34];
     __shared__ int8_t  s_m[32 * 32];
     __shared__ int s_red[8];
     __shared__ int s_lvl0;                 // quantised DC level of the TU
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) k_cu_residual(const P* __restrict__ fenc,
         __syncthreads();
         // ---- residual ----
         const P* fe = fenc + (size_t)py * stride + px;
-        for (int i = tid; i < NN; i += blockDim.x) { int y = i >> lg, x = i & (T - 1); s_a[i] = (int16_t)((int)fe[(size_t)y * stride + x] - (int)s_pred[i]); }
+        for (int i = tid; i < NN; i += blockDim.x) { int y = i >> lg, x = i & (T - 1); s_a[y * 34 + x] = (int16_t)((int)fe[(size_t)y * stride + x] - (int)s_pred[i]); }
         __syncthreads();
         // ---- forward DCT: two passes (dct.cpp:83-240, 442-525) ----
         {
@@ -161,15 +161,15 @@ __global__ void __launch_bounds__(256) k_cu_residual(const P* __restrict__ fenc,
             for (int i = tid; i < NN; i += blockDim.x)
             {
                 int k = i >> lg, jj = i & (T - 1), acc = 0;
-                for (int q = 0; q < T; q++) acc += (int)s_m[k * T + q] * s_a[jj * T + q];
-                s_b[i] = (int16_t)((acc + (1 << (sh1 - 1))) >> sh1);
+                for (int q = 0; q < T; q++) acc += (int)s_m[k * T + q] * s_a[jj * 34 + q];
+                s_b[k * 34 + jj] = (int16_t)((acc + (1 << (sh1 - 1))) >> sh1);
             }
             __syncthreads();
             for (int i = tid; i < NN; i += blockDim.x)
             {
                 int k = i >> lg, jj = i & (T - 1), acc = 0;
-                for (int q = 0; q < T; q++) acc += (int)s_m[k * T + q] * s_b[jj * T + q];
-                s_a[i] = (int16_t)((acc + (1 << (sh2 - 1))) >> sh2);
+                for (int q = 0; q < T; q++) acc += (int)s_m[k * T + q] * s_b[jj * 34 + q];
+                s_a[i] = (int16_t)((acc + (1 << (sh2 - 1))) >> sh2);           // coefficients back in linear k*T + j order
             }
             __syncthreads();
         }

@@ -32,88 +32,129 @@ static int build_dct_tables()
     return 0;
 }
 
-// One CTA handles `tpb` TUs.  smem: in tile, mid tile (int16), matrix copy (int8).
+// One CTA (256 threads) handles TPB = max(1, 1024 / N^2) TUs per iteration.  Both passes are shared-memory
+// matrix products; rows are padded to N+2 int16 so that the 32 lanes of a warp (one output column each)
+// hit 32 different banks, and every thread produces 4 outputs per input element it reads.
 // op: X265CU_DCT / IDCT / DST4 / IDST4
-template <int DEPTH>
-__global__ void __launch_bounds__(256) k_transform(int op, int N, const int16_t* __restrict__ src, int16_t* __restrict__ dst,
-                                                   int stride, int64_t tu_pitch, int n, int tpb)
+template <int DEPTH, int N>
+__global__ void __launch_bounds__(256) k_transform(int op, const int16_t* __restrict__ src, int16_t* __restrict__ dst,
+                                                   int stride, int64_t tu_pitch, int n)
 {
-    extern __shared__ int16_t sm[];
-    const int NN = N * N;
-    int16_t* s_in = sm;                      // tpb * NN
-    int16_t* s_mid = sm + tpb * NN;          // tpb * NN
-    __shared__ int8_t s_m[32 * 32];
-    const int lg = 31 - __clz(N);
+    constexpr int NN = N * N, LG = (N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5);
+    constexpr int TPB = (1024 / NN) < 1 ? 1 : (1024 / NN > 16 ? 16 : 1024 / NN);       // 32:1  16:4  8:16  4:16
+    constexpr int PS = N + 2;                                                           // padded row stride
+    constexpr int OPT = 4;                                                              // outputs per thread
+    constexpr int TPT = NN / OPT;                                                       // threads per TU (N=4: 4)
+    __shared__ int16_t s_in[TPB * N * PS];
+    __shared__ int16_t s_mid[TPB * N * PS];
+    __shared__ int8_t s_m[NN];
     const bool fwd = (op == X265CU_DCT || op == X265CU_DST4);
     const bool dstm = (op == X265CU_DST4 || op == X265CU_IDST4);
-    for (int i = threadIdx.x; i < NN; i += blockDim.x) s_m[i] = dstm ? c_dst4[i] : c_dct[lg - 2][i];
-    const int shift1 = fwd ? lg - 1 + (DEPTH - 8) : 7;
-    const int shift2 = fwd ? lg + 6 : 12 - (DEPTH - 8);
+    for (int i = threadIdx.x; i < NN; i += blockDim.x) s_m[i] = dstm ? c_dst4[i] : c_dct[LG - 2][i];
+    const int shift1 = fwd ? LG - 1 + (DEPTH - 8) : 7;
+    const int shift2 = fwd ? LG + 6 : 12 - (DEPTH - 8);
+    const int tl = threadIdx.x / TPT, tt = threadIdx.x % TPT;      // TU slot in the CTA, thread inside the TU
+    const int col = tt & (N - 1), rb = tt >> LG;                   // output column, first output row (rows rb + (N/4)*m)
+    constexpr int RSTEP = N / OPT;
 
-    for (int base = blockIdx.x * tpb; base < n; base += gridDim.x * tpb)
+    for (int base = blockIdx.x * TPB; base < n; base += gridDim.x * TPB)
     {
-        const int cnt = min(tpb, n - base);
+        const int cnt = min(TPB, n - base);
         __syncthreads();
-        // load: forward reads the strided residual, inverse reads contiguous coefficients
         for (int i = threadIdx.x; i < cnt * NN; i += blockDim.x)
         {
-            int t = i / NN, e = i - t * NN;
-            if (fwd) { int y = e >> lg, x = e & (N - 1); s_in[i] = src[(int64_t)(base + t) * tu_pitch + (int64_t)y * stride + x]; }
-            else     s_in[i] = src[(int64_t)(base + t) * NN + e];
+            int t = i >> (2 * LG), e = i & (NN - 1), y = e >> LG, x = e & (N - 1);
+            s_in[(t * N + y) * PS + x] = fwd ? src[(int64_t)(base + t) * tu_pitch + (int64_t)y * stride + x] : src[(int64_t)(base + t) * NN + e];
         }
         __syncthreads();
-        // pass 1
-        for (int i = threadIdx.x; i < cnt * NN; i += blockDim.x)
+        const bool act = tl < cnt && threadIdx.x < TPB * TPT;
+        const int16_t* in = s_in + tl * N * PS;
+        int16_t* mid = s_mid + tl * N * PS;
+        if (act)
         {
-            int t = i / NN, e = i - t * NN;
-            const int16_t* in = s_in + t * NN;
-            int acc = 0;
+            int acc[OPT] = { 0, 0, 0, 0 };
             if (fwd)
-            {   // out[k*N + j] = sum_i M[k][i] * in[j*N + i]
-                int k = e >> lg, jj = e & (N - 1);
-                for (int q = 0; q < N; q++) acc += (int)s_m[k * N + q] * in[jj * N + q];
-                s_mid[i] = (int16_t)((acc + (1 << (shift1 - 1))) >> shift1);
+            {   // mid[k][j] = sum_q M[k][q] * in[j][q];  j = col, k = rb + RSTEP*m
+#pragma unroll 8
+                for (int q = 0; q < N; q++)
+                {
+                    const int x = in[col * PS + q];
+#pragma unroll
+                    for (int m = 0; m < OPT; m++) acc[m] += (int)s_m[(rb + RSTEP * m) * N + q] * x;
+                }
+#pragma unroll
+                for (int m = 0; m < OPT; m++) mid[(rb + RSTEP * m) * PS + col] = (int16_t)((acc[m] + (1 << (shift1 - 1))) >> shift1);
             }
             else
-            {   // out[j*N + i2] = clip16(sum_k M[k][i2] * in[k*N + j])
-                int jj = e >> lg, i2 = e & (N - 1);
-                for (int q = 0; q < N; q++) acc += (int)s_m[q * N + i2] * in[q * N + jj];
-                s_mid[i] = (int16_t)clip16((acc + (1 << (shift1 - 1))) >> shift1);
+            {   // mid[j][i] = clip16(sum_q M[q][i] * in[q][j]);  j = col, i = rb + RSTEP*m
+#pragma unroll 8
+                for (int q = 0; q < N; q++)
+                {
+                    const int x = in[q * PS + col];
+#pragma unroll
+                    for (int m = 0; m < OPT; m++) acc[m] += (int)s_m[q * N + rb + RSTEP * m] * x;
+                }
+#pragma unroll
+                for (int m = 0; m < OPT; m++) mid[col * PS + rb + RSTEP * m] = (int16_t)clip16((acc[m] + (1 << (shift1 - 1))) >> shift1);
             }
         }
         __syncthreads();
-        // pass 2
-        for (int i = threadIdx.x; i < cnt * NN; i += blockDim.x)
+        if (act)
         {
-            int t = i / NN, e = i - t * NN;
-            const int16_t* in = s_mid + t * NN;
-            int acc = 0;
+            int acc[OPT] = { 0, 0, 0, 0 };
             if (fwd)
             {
-                int k = e >> lg, jj = e & (N - 1);
-                for (int q = 0; q < N; q++) acc += (int)s_m[k * N + q] * in[jj * N + q];
-                dst[(int64_t)(base + t) * NN + e] = (int16_t)((acc + (1 << (shift2 - 1))) >> shift2);
+#pragma unroll 8
+                for (int q = 0; q < N; q++)
+                {
+                    const int x = mid[col * PS + q];
+#pragma unroll
+                    for (int m = 0; m < OPT; m++) acc[m] += (int)s_m[(rb + RSTEP * m) * N + q] * x;
+                }
+#pragma unroll
+                for (int m = 0; m < OPT; m++)
+                    dst[(int64_t)(base + tl) * NN + (rb + RSTEP * m) * N + col] = (int16_t)((acc[m] + (1 << (shift2 - 1))) >> shift2);
             }
             else
             {
-                int jj = e >> lg, i2 = e & (N - 1);
-                for (int q = 0; q < N; q++) acc += (int)s_m[q * N + i2] * in[q * N + jj];
-                dst[(int64_t)(base + t) * tu_pitch + (int64_t)jj * stride + i2] = (int16_t)clip16((acc + (1 << (shift2 - 1))) >> shift2);
+#pragma unroll 8
+                for (int q = 0; q < N; q++)
+                {
+                    const int x = mid[q * PS + col];
+#pragma unroll
+                    for (int m = 0; m < OPT; m++) acc[m] += (int)s_m[q * N + rb + RSTEP * m] * x;
+                }
+#pragma unroll
+                for (int m = 0; m < OPT; m++)
+                    dst[(int64_t)(base + tl) * tu_pitch + (int64_t)col * stride + rb + RSTEP * m] = (int16_t)clip16((acc[m] + (1 << (shift2 - 1))) >> shift2);
             }
         }
     }
+}
+
+template <int DEPTH>
+static int launch_transform_d(x265cu_ctx* ctx, int op, int N, const int16_t* src, int16_t* dst, int stride, int64_t tu_pitch, int n)
+{
+    int tpb = 1024 / (N * N); if (tpb < 1) tpb = 1; if (tpb > 16) tpb = 16;
+    int blocks = (n + tpb - 1) / tpb;
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    switch (N)
+    {
+    case 4:  k_transform<DEPTH, 4><<<blocks, 256, 0, ctx->stream>>>(op, src, dst, stride, tu_pitch, n); break;
+    case 8:  k_transform<DEPTH, 8><<<blocks, 256, 0, ctx->stream>>>(op, src, dst, stride, tu_pitch, n); break;
+    case 16: k_transform<DEPTH, 16><<<blocks, 256, 0, ctx->stream>>>(op, src, dst, stride, tu_pitch, n); break;
+    default: k_transform<DEPTH, 32><<<blocks, 256, 0, ctx->stream>>>(op, src, dst, stride, tu_pitch, n); break;
+    }
+    return 0;
 }
 
 static int launch_transform(x265cu_ctx* ctx, int depth, int op, int N, const int16_t* src, int16_t* dst, int stride, int64_t tu_pitch, int n)
 {
     if (n <= 0) return 0;
     if (op == X265CU_DST4 || op == X265CU_IDST4) N = 4;
-    int tpb = 1024 / (N * N); if (tpb < 1) tpb = 1; if (tpb > 16) tpb = 16;
-    int blocks = (n + tpb - 1) / tpb;
-    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-    size_t smem = (size_t)2 * tpb * N * N * sizeof(int16_t);
-    if (depth == 8) k_transform<8><<<blocks, 256, smem, ctx->stream>>>(op, N, src, dst, stride, tu_pitch, n, tpb);
-    else            k_transform<10><<<blocks, 256, smem, ctx->stream>>>(op, N, src, dst, stride, tu_pitch, n, tpb);
+    if (N != 4 && N != 8 && N != 16 && N != 32) { x265cu_set_error("transform size", cudaErrorInvalidValue, __FILE__, __LINE__); return -1; }
+    if (depth == 8) launch_transform_d<8>(ctx, op, N, src, dst, stride, tu_pitch, n);
+    else            launch_transform_d<10>(ctx, op, N, src, dst, stride, tu_pitch, n);
     CU_LAUNCH_CHECK(ctx);
     return 0;
 }
