@@ -179,6 +179,24 @@ void* x265cu_analyser_ref_plane(x265cu_analyser*, int idx, int* stride); /* devi
 int x265cu_analyser_ref_updated(x265cu_analyser*, int idx);            /* re-extend borders after writing the plane in place */
 int x265cu_analyser_fetch(x265cu_analyser*, int what, void* host);    /* parity/debug access to resident results */
 
+/* ---------- lookahead frame costs (BASELINE configs[1]; slicetype.cpp:696-805, 3115-3388) ----------
+ * All pointers are device pointers.  Planes are the 4 lowres hpel planes of a frame (origin pixel,
+ * margins extended: x265cu_frame_init_lowres).  One launch handles n frames / n (p0,p1,b) triples. */
+typedef struct {
+    const void* plane0; const int32_t* invQscale;            /* invQscale NULL when AQ is off */
+    int32_t* intraCost; uint8_t* intraMode; uint16_t* lowresCosts; int32_t* rowSatds; int64_t* out; /* out[2]: costEst, costEstAq */
+} x265cu_la_intra_job;
+int x265cu_lowres_intra_batch(x265cu_ctx*, int depth, const x265cu_la_intra_job* jobs_dev, int n, int stride, int w8, int h8, int lambda);
+typedef struct {
+    const void* fenc[4]; const void* ref0[4]; const void* ref1[4];
+    int32_t* mvs[2]; int32_t* mvcosts[2];                    /* [cu][2] qpel MVs and [cu] costs per list, in/out */
+    const int32_t* intraCost; const int32_t* invQscale;
+    uint16_t* lowresCosts; int32_t* rowSatds; int64_t* out;  /* out[3]: costEst, costEstAq, intraMbs */
+    int32_t bidir, doSearch0, doSearch1, pad;
+} x265cu_la_job;
+int x265cu_lookahead_cost_batch(x265cu_ctx*, int depth, const x265cu_la_job* jobs_dev, int n, int stride, int w8, int h8,
+                                const uint16_t* mvcost_dev /* centred table base, lambda of X265_LOOKAHEAD_QP */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,3 +221,104 @@ extern "C" int x265ref_analyse_frame(drv_frame* f, int stages)
     if (stages & 4) drv_run_stage(f, 2);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Lookahead (BASELINE configs[1]): the REAL Lowres::init, LookaheadTLD::lowresIntraEstimate
+ * (slicetype.cpp:696-805) and CostEstimateGroup::singleCost -> estimateFrameCost -> estimateCUCost
+ * (slicetype.cpp:3021-3388) on caller frames, serial (non-coop) path, no weightp / AQ / HME.
+ * ------------------------------------------------------------------------------------------ */
+#include "slicetype.h"
+#include "picyuv.h"
+#include "x265.h"
+
+struct RefLookahead
+{
+    x265_param* param;
+    Lookahead* la;
+    int n;
+    PicYuv** pics;
+    Lowres** frames;
+};
+
+extern "C" {
+
+void* x265ref_la_create(int width, int height, int nframes, const pixel* const* luma, intptr_t stride, int bframes)
+{
+    ensure_init();
+    static bool scales = false;
+    if (!scales) { MotionEstimate::initScales(); scales = true; }
+    RefLookahead* h = new RefLookahead();
+    x265_param* p = x265_param_alloc();
+    x265_param_default(p);
+    p->sourceWidth = width; p->sourceHeight = height; p->internalCsp = X265_CSP_I420;
+    p->bframes = bframes; p->bEnableWeightedPred = 0; p->bEnableWeightedBiPred = 0;
+    p->rc.aqMode = 0; p->rc.cuTree = 0; p->rc.hevcAq = 0; p->bAQMotion = 0; p->lookaheadSlices = 0; p->bEnableHME = 0;
+    p->rc.qgSize = 32; p->maxCUSize = 64; p->rc.vbvBufferSize = 0; p->bFrameAdaptive = 0;
+    h->param = p; h->n = nframes;
+    h->pics = new PicYuv*[nframes]; h->frames = new Lowres*[nframes + 2];
+    for (int i = 0; i < nframes; i++)
+    {
+        PicYuv* pic = new PicYuv();
+        pic->create(p, true, NULL);
+        for (int y = 0; y < height; y++)
+            memcpy(pic->m_picOrg[0] + (intptr_t)y * pic->m_stride, luma[i] + (intptr_t)y * stride, (size_t)width * sizeof(pixel));
+        extendPicBorder(pic->m_picOrg[0], pic->m_stride, width, height, pic->m_lumaMarginX, pic->m_lumaMarginY);
+        Lowres* lr = new Lowres();
+        memset((void*)lr, 0, sizeof(Lowres));
+        lr->create(p, pic, p->rc.qgSize);
+        lr->init(pic, i);
+        h->pics[i] = pic; h->frames[i] = lr;
+    }
+    h->la = new Lookahead(p, NULL);
+    h->la->m_tld = new LookaheadTLD[1];
+    h->la->m_tld[0].init(h->la->m_8x8Width, h->la->m_8x8Height, h->la->m_cuCount);
+    for (int i = 0; i < nframes; i++)
+        h->la->m_tld[0].lowresIntraEstimate(*h->frames[i], p->rc.qgSize);
+    return h;
+}
+
+int64_t x265ref_la_cost(void* hv, int p0, int p1, int b)
+{
+    RefLookahead* h = (RefLookahead*)hv;
+    CostEstimateGroup est(*h->la, h->frames);
+    return est.singleCost(p0, p1, b, false);
+}
+
+/* geometry: out = {width8, height8, lumaStride, lowres width, lowres lines, marginX, marginY} */
+void x265ref_la_geometry(void* hv, int* out)
+{
+    RefLookahead* h = (RefLookahead*)hv;
+    Lowres* f = h->frames[0];
+    out[0] = h->la->m_8x8Width; out[1] = h->la->m_8x8Height; out[2] = (int)f->lumaStride; out[3] = f->width; out[4] = f->lines;
+    out[5] = h->pics[0]->m_lumaMarginX; out[6] = h->pics[0]->m_lumaMarginY;
+}
+
+/* what: 0 intraCost[int32], 1 intraMode[u8], 2 lowresCosts[d0][d1][u16], 3 rowSatds[d0][d1][int32 per row],
+ * 4 lowresMvs[list][dist] as int32 pairs, 5 lowresMvCosts[list][dist][int32], 6 {costEst, costEstAq, intraMbs[d0]} as int64 x3,
+ * 7 lowres plane `d0` (0..3) rows [-marginY, lines+marginY) x lumaStride */
+int x265ref_la_get(void* hv, int frame, int what, int d0, int d1, void* out)
+{
+    RefLookahead* h = (RefLookahead*)hv;
+    Lowres* f = h->frames[frame];
+    const int ncu = h->la->m_cuCount, rows = h->la->m_8x8Height;
+    switch (what)
+    {
+    case 0: memcpy(out, f->intraCost, sizeof(int32_t) * ncu); break;
+    case 1: memcpy(out, f->intraMode, ncu); break;
+    case 2: memcpy(out, f->lowresCosts[d0][d1], sizeof(uint16_t) * ncu); break;
+    case 3: memcpy(out, f->rowSatds[d0][d1], sizeof(int32_t) * rows); break;
+    case 4: for (int i = 0; i < ncu; i++) { ((int32_t*)out)[2 * i] = f->lowresMvs[d0][d1][i].x; ((int32_t*)out)[2 * i + 1] = f->lowresMvs[d0][d1][i].y; } break;
+    case 5: memcpy(out, f->lowresMvCosts[d0][d1], sizeof(int32_t) * ncu); break;
+    case 6: ((int64_t*)out)[0] = f->costEst[d0][d1]; ((int64_t*)out)[1] = f->costEstAq[d0][d1]; ((int64_t*)out)[2] = f->intraMbs[d0]; break;
+    case 7:
+    {
+        const int my = h->pics[0]->m_lumaMarginY, mx = h->pics[0]->m_lumaMarginX;
+        memcpy(out, f->lowresPlane[d0] - (intptr_t)my * f->lumaStride - mx, sizeof(pixel) * f->lumaStride * (f->lines + 2 * my));
+        break;
+    }
+    default: return -1;
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -8,6 +8,7 @@
 #include "intra.cuh"
 #include "me.cuh"
 #include "frame.cuh"
+#include "lookahead.cuh"
 #include <math.h>
 #include <mutex>
 
@@ -211,6 +212,44 @@ int x265cu_me_batch(x265cu_ctx* c, int depth, const void* fenc, int fencStride, 
 {
     (void)mvcost_range;
     return launch_me(c, depth, fenc, fencStride, refs, refStride, lowres, mvcost, jobs, n, out, c->d_counter);
+}
+
+__global__ void k_la_intra_zero(const x265cu_la_intra_job* jobs, int h8)
+{
+    const x265cu_la_intra_job jb = jobs[blockIdx.x];
+    for (int i = threadIdx.x; i < h8; i += blockDim.x) jb.rowSatds[i] = 0;
+    if (threadIdx.x < 2) jb.out[threadIdx.x] = 0;
+}
+
+int x265cu_lowres_intra_batch(x265cu_ctx* c, int depth, const x265cu_la_intra_job* jobs, int n, int stride, int w8, int h8, int lambda)
+{
+    if (n <= 0) return 0;
+    k_la_intra_zero<<<n, 128, 0, c->stream>>>(jobs, h8);
+    CU_LAUNCH_CHECK(c);
+    int bx = (w8 * h8 + 31) / 32; if (bx > c->sm_count * 4) bx = c->sm_count * 4;
+    dim3 grid(bx, n);
+    if (depth == 8) k_lowres_intra<uint8_t><<<grid, 256, 0, c->stream>>>(jobs, stride, w8, h8, lambda);
+    else            k_lowres_intra<uint16_t><<<grid, 256, 0, c->stream>>>(jobs, stride, w8, h8, lambda);
+    CU_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int x265cu_lookahead_cost_batch(x265cu_ctx* c, int depth, const x265cu_la_job* jobs, int n, int stride, int w8, int h8, const uint16_t* mvcost)
+{
+    if (n <= 0) return 0;
+    const size_t smem = sizeof(MeShared) * LA_WARPS;
+    if (depth == 8)
+    {
+        CU_CHECK(cudaFuncSetAttribute(k_lookahead_cost<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_lookahead_cost<uint8_t><<<n, LA_WARPS * 32, smem, c->stream>>>(jobs, stride, w8, h8, mvcost);
+    }
+    else
+    {
+        CU_CHECK(cudaFuncSetAttribute(k_lookahead_cost<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_lookahead_cost<uint16_t><<<n, LA_WARPS * 32, smem, c->stream>>>(jobs, stride, w8, h8, mvcost);
+    }
+    CU_LAUNCH_CHECK(c);
+    return 0;
 }
 
 } // extern "C"

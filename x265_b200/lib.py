@@ -197,6 +197,14 @@ def load(device=0, need_gpu=True):
     return _cached[key]
 
 
+LA_INTRA_JOB = np.dtype([("plane0", "<u8"), ("invQscale", "<u8"), ("intraCost", "<u8"), ("intraMode", "<u8"), ("lowresCosts", "<u8"),
+                         ("rowSatds", "<u8"), ("out", "<u8")], align=True)
+LA_JOB = np.dtype([("fenc", "<u8", 4), ("ref0", "<u8", 4), ("ref1", "<u8", 4), ("mvs", "<u8", 2), ("mvcosts", "<u8", 2), ("intraCost", "<u8"),
+                   ("invQscale", "<u8"), ("lowresCosts", "<u8"), ("rowSatds", "<u8"), ("out", "<u8"), ("bidir", "<i4"), ("doSearch0", "<i4"),
+                   ("doSearch1", "<i4"), ("pad", "<i4")], align=True)
+assert LA_INTRA_JOB.itemsize == 56 and LA_JOB.itemsize == 184
+
+
 # ---------------- frame-level analyser (x265cu_analyser_*) ----------------
 class AnalysisParams(C.Structure):
     _fields_ = [("width", I), ("height", I), ("depth", I), ("numRefs", I), ("method", I), ("subme", I), ("merange", I),
@@ -220,6 +228,8 @@ _AN_PROTOS = {
     "x265cu_analyser_ref_plane": (P, [P, I, C.POINTER(I)]),
     "x265cu_analyser_ref_updated": (I, [P, I]),
 }
+_AN_PROTOS["x265cu_lowres_intra_batch"] = (I, [P, I, P, I, I, I, I, I])
+_AN_PROTOS["x265cu_lookahead_cost_batch"] = (I, [P, I, P, I, I, I, I, P])
 _PROTOS.update(_AN_PROTOS)
 
 
