@@ -54,36 +54,46 @@ class GpuLookahead:
         self.tab = cu.to_device(cu.mvcost_table(LOOKAHEAD_LAMBDA[depth], MVRANGE))
 
     def cost(self, p0, p1, b):
+        return self.cost_batch([(p0, p1, b)])[0]
+
+    def cost_batch(self, triples):
+        """One launch for all triples (they must not share a motion field that still has to be searched)."""
         from x265_b200.lib import LA_JOB
         cu = self.cu
-        f = self.fr[b]
-        d0, d1 = b - p0, p1 - b
-        if (d0, d1) in f["res"]:
-            return f["res"][(d0, d1)]["score"]
-        j = np.zeros(1, LA_JOB)
-        for k in range(4):
-            j["fenc"][0][k] = f["planes"][k].ptr + self.lorg
-            j["ref0"][0][k] = self.fr[p0]["planes"][k].ptr + self.lorg
-            j["ref1"][0][k] = self.fr[p1]["planes"][k].ptr + self.lorg
-        j["bidir"] = int(b < p1)
-        for lst, dist in ((0, d0), (1, d1)):
-            new = (lst, dist) not in f["mvs"]
-            if new:
-                f["mvs"][(lst, dist)] = cu.alloc(8 * self.ncu); f["mvcosts"][(lst, dist)] = cu.alloc(4 * self.ncu)
-                cu.check(cu.L.x265cu_memset(cu.ctx, f["mvs"][(lst, dist)].ptr, 0, 8 * self.ncu))
-                cu.check(cu.L.x265cu_memset(cu.ctx, f["mvcosts"][(lst, dist)].ptr, 0, 4 * self.ncu))
-            j["doSearch%d" % lst] = int(new and (lst == 0 or p1 > b))
-            j["mvs"][0][lst] = f["mvs"][(lst, dist)].ptr; j["mvcosts"][0][lst] = f["mvcosts"][(lst, dist)].ptr
-        lc, rs, out = cu.alloc(2 * self.ncu), cu.alloc(4 * self.h8), cu.alloc(24)
-        j["intraCost"] = f["intraCost"].ptr; j["invQscale"] = 0; j["lowresCosts"] = lc.ptr; j["rowSatds"] = rs.ptr; j["out"] = out.ptr
-        d_j = cu.to_device(j)
-        cu.check(cu.L.x265cu_lookahead_cost_batch(cu.ctx, self.depth, d_j.ptr, 1, self.ls, self.w8, self.h8, self.tab.ptr + 2 * MVRANGE))
-        o = out.download(np.int64)
-        score = int(o[0])
-        if b != p1:
-            score = score * 100 // 130
-        f["res"][(d0, d1)] = dict(score=score, costEstAq=int(o[1]), intraMbs=int(o[2]), lowresCosts=lc.download(np.uint16), rowSatds=rs.download(np.int32))
-        return score
+        todo = [t for t in triples if (t[2] - t[0], t[1] - t[2]) not in self.fr[t[2]]["res"]]
+        jobs = np.zeros(max(len(todo), 1), LA_JOB)
+        bufs = []
+        for n, (p0, p1, b) in enumerate(todo):
+            f = self.fr[b]
+            d0, d1 = b - p0, p1 - b
+            j = jobs[n]
+            for k in range(4):
+                j["fenc"][k] = f["planes"][k].ptr + self.lorg
+                j["ref0"][k] = self.fr[p0]["planes"][k].ptr + self.lorg
+                j["ref1"][k] = self.fr[p1]["planes"][k].ptr + self.lorg
+            j["bidir"] = int(b < p1)
+            for lst, dist in ((0, d0), (1, d1)):
+                new = (lst, dist) not in f["mvs"]
+                if new:
+                    f["mvs"][(lst, dist)] = cu.alloc(8 * self.ncu); f["mvcosts"][(lst, dist)] = cu.alloc(4 * self.ncu)
+                    cu.check(cu.L.x265cu_memset(cu.ctx, f["mvs"][(lst, dist)].ptr, 0, 8 * self.ncu))
+                    cu.check(cu.L.x265cu_memset(cu.ctx, f["mvcosts"][(lst, dist)].ptr, 0, 4 * self.ncu))
+                j["doSearch%d" % lst] = int(new and (lst == 0 or p1 > b))
+                j["mvs"][lst] = f["mvs"][(lst, dist)].ptr; j["mvcosts"][lst] = f["mvcosts"][(lst, dist)].ptr
+            lc, rs, out = cu.alloc(2 * self.ncu), cu.alloc(4 * self.h8), cu.alloc(24)
+            bufs.append((lc, rs, out))
+            j["intraCost"] = f["intraCost"].ptr; j["invQscale"] = 0; j["lowresCosts"] = lc.ptr; j["rowSatds"] = rs.ptr; j["out"] = out.ptr
+        if todo:
+            d_j = cu.to_device(jobs)
+            cu.check(cu.L.x265cu_lookahead_cost_batch(cu.ctx, self.depth, d_j.ptr, len(todo), self.ls, self.w8, self.h8, self.tab.ptr + 2 * MVRANGE))
+            for (p0, p1, b), (lc, rs, out) in zip(todo, bufs):
+                o = out.download(np.int64)
+                score = int(o[0])
+                if b != p1:
+                    score = score * 100 // 130
+                self.fr[b]["res"][(b - p0, p1 - b)] = dict(score=score, costEstAq=int(o[1]), intraMbs=int(o[2]), lowresCosts=lc.download(np.uint16),
+                                                           rowSatds=rs.download(np.int32))
+        return [self.fr[b]["res"][(b - p0, p1 - b)]["score"] for (p0, p1, b) in triples]
 
 
 @pytest.mark.parametrize("depth", [8, 10])
