@@ -67,7 +67,7 @@ template <typename P> __device__ __forceinline__ int sad_word(uint32_t a, uint32
 
 // SAD of the fenc block against ONE reference position (element pointer, rows may be unaligned).
 template <typename P>
-__device__ __forceinline__ int me_sad_direct(const MeCtx<P>& c, const P* __restrict__ r)
+__device__ __noinline__ int me_sad_direct(const MeCtx<P>& c, const P* __restrict__ r)
 {
     const uintptr_t rbase = (uintptr_t)r;
     const int wpr = 1 << c.lgwpr;
@@ -108,62 +108,98 @@ __device__ __forceinline__ int me_sad_direct(const MeCtx<P>& c, const P* __restr
 // Full-pel SAD + mvcost of up to 32 candidate positions at once.  Lane i (< n) owns candidate i:
 // (px, py) in full-pel units relative to the block; returns that candidate's cost in lane i.
 // x8: the raster quirk (motion.cpp:1194: mvcost(tmv << 3) for every 4th column).
+// Plane strides are multiples of 4 bytes and every lane's word offset is a multiple of 4, so the byte
+// misalignment of a candidate ((offset * sizeof(P)) & 3) is the same for all of its words: the funnel
+// shift amount is computed once per candidate, and the per-lane part of the address once per job.
 template <typename P>
-__device__ __forceinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int py, bool x8)
+__device__ __noinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int py, bool x8)
 {
-    const int off = py * c.rstride + px;                    // element offset of my candidate
-    const uintptr_t rbase = (uintptr_t)c.ref[0];
+    const int offB = (py * c.rstride + px) * (int)sizeof(P);          // byte offset of my candidate
+    const uint8_t* rbase = (const uint8_t*)c.ref[0];
     const int wpr = 1 << c.lgwpr;
     int mysad = 0;
     if (!c.pow2)
     {
         for (int p = 0; p < n; p++)
         {
-            const int offp = __shfl_sync(0xffffffffu, off, p);
-            const int v = me_sad_direct(c, c.ref[0] + offp);
+            const int offp = __shfl_sync(0xffffffffu, offB, p);
+            const int v = me_sad_direct(c, (const P*)(rbase + offp));
             if (c.lane == p) mysad = v;
         }
     }
     else if (c.nw >= 32)
     {
+        // sad_x4 style: every fenc word is loaded once per 4 candidates; lane walks words lane, lane+32, ...
         const int iters = c.nw >> 5;
-        for (int p = 0; p < n; p++)
+        const int rowsPerIter = 32 >> c.lgwpr;                          // rows advanced by one iteration (wpr <= 32)
+        const int row0 = c.lane >> c.lgwpr, col4 = (c.lane & (wpr - 1)) * 4;
+        const int laneRef = row0 * c.rstride * (int)sizeof(P) + col4;   // byte offset of my first word inside the block (ref)
+        const int laneFenc = row0 * c.fstride * (int)sizeof(P) + col4;
+        const int stepRef = rowsPerIter * c.rstride * (int)sizeof(P), stepFenc = rowsPerIter * c.fstride * (int)sizeof(P);
+        for (int p0 = 0; p0 < n; p0 += 4)
         {
-            const int offp = __shfl_sync(0xffffffffu, off, p);
-            const uintptr_t rb = rbase + (ptrdiff_t)offp * (ptrdiff_t)sizeof(P);
-            int acc = 0;
+            int o[4], sh[4], acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int ob = __shfl_sync(0xffffffffu, offB, min(p0 + q, n - 1));
+                sh[q] = (ob & 3) * 8;
+                o[q] = (ob & ~3) + laneRef;
+            }
+            const uint8_t* fp = (const uint8_t*)c.fenc + laneFenc;
             if (iters == 1)
             {
-                int row = c.lane >> c.lgwpr, col = c.lane & (wpr - 1);
-                acc = sad_word<P>(c.fw, ld_unaligned32(rb + ((size_t)row * c.rstride) * sizeof(P) + col * 4), 0);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const uint32_t* ap = (const uint32_t*)(rbase + o[q]);
+                    uint32_t lo = ap[0];
+                    uint32_t v = sh[q] ? __funnelshift_r(lo, ap[1], sh[q]) : lo;
+                    acc[q] = sad_word<P>(c.fw, v, 0);
+                }
             }
             else
             {
-#pragma unroll 4
+#pragma unroll 2
                 for (int k = 0; k < iters; k++)
                 {
-                    int wd = c.lane + (k << 5);
-                    int row = wd >> c.lgwpr, col = wd & (wpr - 1);
-                    uint32_t f = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * c.fstride) * sizeof(P) + col * 4);
-                    acc = sad_word<P>(f, ld_unaligned32(rb + ((size_t)row * c.rstride) * sizeof(P) + col * 4), acc);
+                    const uint32_t f = *(const uint32_t*)(fp + k * stepFenc);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                    {
+                        const uint32_t* ap = (const uint32_t*)(rbase + o[q] + k * stepRef);
+                        uint32_t lo = ap[0];
+                        uint32_t v = sh[q] ? __funnelshift_r(lo, ap[1], sh[q]) : lo;
+                        acc[q] = sad_word<P>(f, v, acc[q]);
+                    }
                 }
             }
-            acc = warp_sum(acc);
-            if (c.lane == p) mysad = acc;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int t = warp_sum(acc[q]);
+                if (c.lane == p0 + q) mysad = t;          // (candidates past n are duplicates of the last one and ignored)
+            }
         }
     }
     else
     {
         // several candidates per pass: lane group g = lane >> lgnw evaluates candidate base + g
         const int ppp = 32 >> c.lgnw;
-        const int wd = c.lane & (c.nw - 1), row = wd >> c.lgwpr, col = wd & (wpr - 1);
+        const int wd = c.lane & (c.nw - 1);
+        const int laneRef = (wd >> c.lgwpr) * c.rstride * (int)sizeof(P) + (wd & (wpr - 1)) * 4;
         for (int base = 0; base < n; base += ppp)
         {
             const int p = base + (c.lane >> c.lgnw);
-            const int offp = __shfl_sync(0xffffffffu, off, min(p, n - 1));
+            const int ob = __shfl_sync(0xffffffffu, offB, min(p, n - 1));
             int acc = 0;
             if (p < n)
-                acc = sad_word<P>(c.fw, ld_unaligned32(rbase + ((ptrdiff_t)offp + (ptrdiff_t)row * c.rstride) * (ptrdiff_t)sizeof(P) + col * 4), 0);
+            {
+                const uint32_t* ap = (const uint32_t*)(rbase + (ob & ~3) + laneRef);
+                const int sh = (ob & 3) * 8;
+                uint32_t lo = ap[0];
+                acc = sad_word<P>(c.fw, sh ? __funnelshift_r(lo, ap[1], sh) : lo, 0);
+            }
             for (int s = c.nw >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
             const int v = __shfl_sync(0xffffffffu, acc, ((c.lane - base) << c.lgnw) & 31);
             if (c.lane >= base && c.lane < base + ppp) mysad = v;
@@ -172,6 +208,20 @@ __device__ __forceinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, 
     int cost = 0x7fffffff;
     if (c.lane < n) cost = mysad + (x8 ? me_mvcost(c, px * 8, py * 8) : me_mvcost(c, px * 4, py * 4));
     return cost;
+}
+
+
+// tile distortions kept out of line: the job loop is instruction-cache bound, one copy of the unrolled
+// Hadamard instead of six is worth more than the call overhead (measured: profiles/me_r1 notes)
+template <typename PA, typename PB>
+__device__ __noinline__ int me_tile8x4(const PA* pf, int sf, const PB* pp, int sp)
+{
+    return (had4x4_abs(pf, sf, pp, sp) + had4x4_abs(pf + 4, sf, pp + 4, sp)) >> 1;
+}
+template <typename PA, typename PB>
+__device__ __noinline__ int me_tile4x4(const PA* pf, int sf, const PB* pp, int sp)
+{
+    return had4x4_abs(pf, sf, pp, sp) >> 1;
 }
 
 // keep only the valid candidates, preserving order: returns n and moves candidate k to lane k.
@@ -192,7 +242,7 @@ __device__ __forceinline__ int me_compact(bool valid, int cnt, int& a, int& b, i
 
 // cost of a band of prediction held in c.sm->pred (stride 64) against fenc rows [y0, y0+rows)
 template <typename P>
-__device__ __forceinline__ int me_band_cost(const MeCtx<P>& c, int y0, int rows, bool satd)
+__device__ __noinline__ int me_band_cost(const MeCtx<P>& c, int y0, int rows, bool satd)
 {
     const uint16_t* pr = c.sm->pred;
     const P* f = c.fenc + (size_t)y0 * c.fstride;
@@ -213,7 +263,7 @@ __device__ __forceinline__ int me_band_cost(const MeCtx<P>& c, int y0, int rows,
         {
             int ty = t / tpr, tx = t - ty * tpr;
             const P* pf = f + (ty * 4) * c.fstride + tx * tw; const uint16_t* pp = pr + (ty * 4) * 64 + tx * tw;
-            if (tw == 8) acc += (had4x4_abs(pf, c.fstride, pp, 64) + had4x4_abs(pf + 4, c.fstride, pp + 4, 64)) >> 1;
+            if (tw == 8) acc += me_tile8x4(pf, c.fstride, pp, 64);
             else         acc += had4x4_abs(pf, c.fstride, pp, 64) >> 1;
         }
     }
@@ -224,21 +274,21 @@ __device__ __forceinline__ int me_band_cost(const MeCtx<P>& c, int y0, int rows,
         {
             int ty = t >> lgtw, tx = t & ((1 << lgtw) - 1);
             const P* pf = f + (ty * 4) * c.fstride + tx * 8; const uint16_t* pp = pr + (ty * 4) * 64 + tx * 8;
-            acc += (had4x4_abs(pf, c.fstride, pp, 64) + had4x4_abs(pf + 4, c.fstride, pp + 4, 64)) >> 1;
+            acc += me_tile8x4(pf, c.fstride, pp, 64);
         }
     }
     else
     {
         const int nt = rows >> 2;                    // w == 4: one 4x4 tile per 4 rows
         for (int t = c.lane; t < nt; t += 32)
-            acc += had4x4_abs(f + (t * 4) * c.fstride, c.fstride, pr + (t * 4) * 64, 64) >> 1;
+            acc += me_tile4x4(f + (t * 4) * c.fstride, c.fstride, pr + (t * 4) * 64, 64);
     }
     return acc;           // un-reduced partial (caller reduces once)
 }
 
 // subpelCompare (motion.cpp:1571-1598) for ONE candidate: luma_hpp / luma_vpp / luma_hvpp, then cmp.
 template <typename P>
-__device__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
+__device__ __noinline__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
 {
     constexpr int DEPTH = PixTraits<P>::depth;
     const P* r = c.ref[0] + (qx >> 2) + (ptrdiff_t)(qy >> 2) * c.rstride;
@@ -311,7 +361,7 @@ __device__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
 // (candidate, pixel).  Lane i (< n <= 4) owns candidate i (qx, qy); returns its distortion in lane i.
 // Per candidate the arithmetic is exactly me_subpel_compare's.
 template <typename P>
-__device__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+__device__ __noinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
 {
     constexpr int DEPTH = PixTraits<P>::depth;
     const int lgh = 31 - __clz(c.h);
@@ -411,8 +461,8 @@ __device__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, b
             const P* pf = c.fenc + (ty * 4) * c.fstride + tx * tw;
             const uint16_t* pp = c.sm->pred + (cand << 8) + ((ty * 4) << c.lgw) + tx * tw;
             int d;
-            if (tw == 8) d = (had4x4_abs(pf, c.fstride, pp, c.w) + had4x4_abs(pf + 4, c.fstride, pp + 4, c.w)) >> 1;
-            else         d = had4x4_abs(pf, c.fstride, pp, c.w) >> 1;
+            if (tw == 8) d = me_tile8x4(pf, c.fstride, pp, c.w);
+            else         d = me_tile4x4(pf, c.fstride, pp, c.w);
             part[0] += cand == 0 ? d : 0; part[1] += cand == 1 ? d : 0; part[2] += cand == 2 ? d : 0; part[3] += cand == 3 ? d : 0;
         }
     }
@@ -428,7 +478,7 @@ __device__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, b
 
 // distortion of up to 8 sub-pel candidates, lane i (< n) owns candidate i; result in lane i
 template <typename P>
-__device__ int me_subpel_batch(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+__device__ __noinline__ int me_subpel_batch(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
 {
     int out = 0;
     if (c.pow2 && c.w <= 16 && c.h <= 16)
@@ -520,7 +570,7 @@ __device__ __forceinline__ void me_fold(MeStar& s, int n, int cost, int px, int 
 // a level is the reference's (its x4 fast path and its bounds-checked path visit the same points in
 // the same order), out-of-range candidates are dropped before evaluation.
 template <typename P>
-__device__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters, int merange)
+__device__ __noinline__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters, int merange)
 {
     const int ox = s.bx, oy = s.by, lane = c.lane;
     int saved = s.bcost, rounds = 0;
@@ -605,7 +655,7 @@ __device__ __forceinline__ int me_subpel_round(const MeCtx<P>& c, int bx, int by
 }
 
 template <typename P>
-__device__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restrict__ out)
+__device__ __forceinline__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restrict__ out)
 {
     const int qminx = c.minx * 4, qminy = c.miny * 4, qmaxx = c.maxx * 4, qmaxy = c.maxy * 4;
     const int merange = j.merange;
