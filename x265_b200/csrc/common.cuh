@@ -17,7 +17,8 @@ struct x265cu_ctx
     uint64_t launches;
     // per-call thunk staging (pinned host + device arenas)
     uint8_t* h_stage; uint8_t* d_stage; size_t stage_bytes;
-    int* d_counter;                     // work-queue counter for persistent kernels
+    int* d_counter;                     // work-queue counters for persistent kernels
+    void* d_me_state; size_t me_state_bytes;   // per-job state between the ME phases
 };
 
 void x265cu_set_error(const char* what, cudaError_t e, const char* file, int line);

@@ -654,13 +654,18 @@ __device__ __forceinline__ int me_subpel_round(const MeCtx<P>& c, int bx, int by
     return bdir;
 }
 
-template <typename P>
-__device__ __forceinline__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restrict__ out)
-{
-    const int qminx = c.minx * 4, qminy = c.miny * 4, qmaxx = c.maxx * 4, qmaxy = c.maxy * 4;
-    const int merange = j.merange;
+struct MeState { int bmx, bmy, bcost, bprecost, bestprex, bestprey; };
+
 #define ME_YOK(y) (((y) >= c.miny) & ((y) <= c.maxy))
 #define ME_INRANGE(x, y) ((x) >= c.minx && (x) <= c.maxx && (y) >= c.miny && (y) <= c.maxy)
+
+// phase 1 (motion.cpp:771-814): cost at the clipped MVP, at its full-pel rounding, at MV 0 and at the qpel candidates
+template <typename P>
+__device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, MeState& st)
+{
+
+    const int qminx = c.minx * 4, qminy = c.miny * 4, qmaxx = c.maxx * 4, qmaxy = c.maxy * 4;
+    const int merange = j.merange;
     // clipped() = min with max first, then max with min (mv.h:100-105)
     const int pmvx = max(min(c.mvpx, qmaxx), qminx), pmvy = max(min(c.mvpy, qmaxy), qminy);
     int bestprex = pmvx, bestprey = pmvy;
@@ -683,6 +688,15 @@ __device__ __forceinline__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, 
         }
     }
 
+    st.bmx = bmx; st.bmy = bmy; st.bcost = bcost; st.bprecost = bprecost; st.bestprex = bestprex; st.bestprey = bestprey;
+}
+
+// phase 2 (motion.cpp:816-1438): the integer search proper
+template <typename P>
+__device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, MeState& st)
+{
+    const int merange = j.merange;
+    int bmx = st.bmx, bmy = st.bmy, bcost = st.bcost;
     if (j.method == 0)
     {   // DIA (motion.cpp:822-846)
         bcost <<= 4;
@@ -819,6 +833,16 @@ __device__ __forceinline__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, 
         bmx = s.bx; bmy = s.by; bcost = s.bcost;
     }
 
+    st.bmx = bmx; st.bmy = bmy; st.bcost = bcost;
+}
+
+// phase 3 (motion.cpp:1440-1569): pick pre-check vs search winner, sub-pel refinement
+template <typename P>
+__device__ __forceinline__ void me_phase3(MeCtx<P>& c, const x265cu_me_job& j, const MeState& st, int32_t* __restrict__ out)
+{
+    const int qminy = c.miny * 4, qmaxy = c.maxy * 4;
+    int bcost = st.bcost;
+    const int bmx = st.bmx, bmy = st.bmy, bprecost = st.bprecost, bestprex = st.bestprex, bestprey = st.bestprey;
     int bx, by;
     if (bprecost < bcost) { bx = bestprex; by = bestprey; bcost = bprecost; }
     else { bx = bmx * 4; by = bmy * 4; }
@@ -866,18 +890,54 @@ __device__ __forceinline__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, 
         }
     }
     if (c.lane == 0) { out[0] = bcost; out[1] = bx; out[2] = by; out[3] = 0; }
-#undef ME_YOK
-#undef ME_INRANGE
 }
 
-// persistent warps, dynamic job fetch (jobs differ by up to 64x in work)
+
+template <typename P>
+__device__ __forceinline__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restrict__ out)
+{
+    MeState st;
+    me_phase1<P>(c, j, st);
+    me_phase2<P>(c, j, st);
+    me_phase3<P>(c, j, st, out);
+}
+
+// Job setup shared by all ME kernels
+template <typename P>
+__device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j, const P* fenc, int fstride, const P* const* refs, int rstride,
+                                            int lowres, const uint16_t* mvcost, int lane, MeShared* sm)
+{
+    c.fenc = fenc + j.offset; c.fstride = fstride;
+    if (lowres) { for (int i = 0; i < 4; i++) c.ref[i] = refs[j.ref * 4 + i] + j.offset; }
+    else        { c.ref[0] = refs[j.ref] + j.offset; c.ref[1] = c.ref[2] = c.ref[3] = c.ref[0]; }
+    c.rstride = rstride; c.mvc = mvcost;
+    c.mvpx = j.qmvp[0]; c.mvpy = j.qmvp[1];
+    c.minx = j.mvmin[0]; c.miny = j.mvmin[1]; c.maxx = j.mvmax[0]; c.maxy = j.mvmax[1];
+    c.w = j.pw; c.h = j.ph; c.lgw = 31 - __clz(c.w); c.lane = lane; c.lowres = lowres; c.sm = sm;
+    c.pow2 = ((c.w & (c.w - 1)) | (c.h & (c.h - 1))) == 0;
+    const int wpr = (c.w * (int)sizeof(P)) >> 2;            // words per row (>= 1: w >= 4)
+    c.lgwpr = 31 - __clz(wpr);
+    c.nw = wpr * c.h; c.lgnw = 31 - __clz(c.nw);
+    c.fw = 0;
+    if (c.pow2 && c.nw <= 32)
+    {   // every lane caches the fenc word of its slot (lane mod nw): groups of nw lanes evaluate different candidates
+        const int wd = lane & (c.nw - 1);
+        int row = wd >> c.lgwpr, col = wd & (wpr - 1);
+        c.fw = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * fstride) * sizeof(P) + col * 4);
+    }
+}
+
+// Persistent warps with a dynamic job queue (jobs differ by up to 64x in work).  The search is split into
+// three launches -- pre-checks, integer search, sub-pel refinement -- because the fused body (12.4 K SASS
+// instructions, ~200 KB) thrashes the instruction cache: ncu showed 80 % of the stall samples in
+// `no_instructions` at a 46 % i-cache hit rate.  PHASE 0 = all three fused (used by small batches / tests).
 #ifndef ME_MIN_BLOCKS
 #define ME_MIN_BLOCKS 2
 #endif
-template <typename P>
+template <typename P, int PHASE>
 __global__ void __launch_bounds__(256, ME_MIN_BLOCKS) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
-                                               const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
-                                               int32_t* __restrict__ out, int* __restrict__ counter)
+                                                           const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
+                                                           int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter)
 {
     extern __shared__ unsigned char me_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -890,43 +950,60 @@ __global__ void __launch_bounds__(256, ME_MIN_BLOCKS) k_me(const P* __restrict__
         if (jid >= n) break;
         const x265cu_me_job j = jobs[jid];
         MeCtx<P> c;
-        c.fenc = fenc + j.offset; c.fstride = fstride;
-        if (lowres) { for (int i = 0; i < 4; i++) c.ref[i] = refs[j.ref * 4 + i] + j.offset; }
-        else        { c.ref[0] = refs[j.ref] + j.offset; c.ref[1] = c.ref[2] = c.ref[3] = c.ref[0]; }
-        c.rstride = rstride; c.mvc = mvcost;
-        c.mvpx = j.qmvp[0]; c.mvpy = j.qmvp[1];
-        c.minx = j.mvmin[0]; c.miny = j.mvmin[1]; c.maxx = j.mvmax[0]; c.maxy = j.mvmax[1];
-        c.w = j.pw; c.h = j.ph; c.lgw = 31 - __clz(c.w); c.lane = lane; c.lowres = lowres; c.sm = sm;
-        c.pow2 = ((c.w & (c.w - 1)) | (c.h & (c.h - 1))) == 0;
-        const int wpr = (c.w * (int)sizeof(P)) >> 2;            // words per row (>= 1: w >= 4)
-        c.lgwpr = 31 - __clz(wpr);
-        c.nw = wpr * c.h; c.lgnw = 31 - __clz(c.nw);
-        c.fw = 0;
-        if (c.pow2 && c.nw <= 32)
-        {   // every lane caches the fenc word of its slot (lane mod nw): groups of nw lanes evaluate different candidates
-            const int wd = lane & (c.nw - 1);
-            int row = wd >> c.lgwpr, col = wd & (wpr - 1);
-            c.fw = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * fstride) * sizeof(P) + col * 4);
+        me_make_ctx<P>(c, j, fenc, fstride, refs, rstride, lowres, mvcost, lane, sm);
+        if (PHASE == 0) me_run_job<P>(c, j, out + (size_t)jid * 4);
+        else
+        {
+            MeState st;
+            if (PHASE != 1) st = state[jid];
+            if (PHASE == 1) { me_phase1<P>(c, j, st); if (lane == 0) state[jid] = st; }
+            if (PHASE == 2) { me_phase2<P>(c, j, st); if (lane == 0) state[jid] = st; }
+            if (PHASE == 3) me_phase3<P>(c, j, st, out + (size_t)jid * 4);
         }
-        me_run_job<P>(c, j, out + (size_t)jid * 4);
         __syncwarp();
     }
+}
+
+template <typename P, int PHASE>
+static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
+                           const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter)
+{
+    const int threads = 256, warps = threads / 32;
+    const size_t smem = sizeof(MeShared) * warps;
+    int blocks = ctx->sm_count * ME_MIN_BLOCKS;
+    int need = (n + warps - 1) / warps;
+    if (blocks > need) blocks = need;
+    k_me<P, PHASE><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, lowres, mvcost, jobs, n, out, state, counter);
+    CU_LAUNCH_CHECK(ctx);
+    return 0;
 }
 
 static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
                      const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, int* counter_dev)
 {
     if (n <= 0) return 0;
-    CU_CHECK(cudaMemsetAsync(counter_dev, 0, sizeof(int), ctx->stream));
-    const int threads = 256, warps = threads / 32;
-    const size_t smem = sizeof(MeShared) * warps;
-    int blocks = ctx->sm_count * ME_MIN_BLOCKS;
-    int need = (n + warps - 1) / warps;
-    if (blocks > need) blocks = need;
+    CU_CHECK(cudaMemsetAsync(counter_dev, 0, 4 * sizeof(int), ctx->stream));
+    // per-job state between the phases (24 B per job), grown on demand and kept by the context
+    const size_t need = (size_t)n * sizeof(MeState);
+    if (ctx->me_state_bytes < need)
+    {
+        if (ctx->d_me_state) { CU_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_me_state); }
+        CU_CHECK(cudaMalloc(&ctx->d_me_state, need));
+        ctx->me_state_bytes = need;
+    }
+    MeState* st = (MeState*)ctx->d_me_state;
+    int rc = 0;
     if (depth == 8)
-        k_me<uint8_t><<<blocks, threads, smem, ctx->stream>>>((const uint8_t*)fenc, fstride, (const uint8_t* const*)refs, rstride, lowres, mvcost, jobs, n, out, counter_dev);
+    {
+        rc |= launch_me_phase<uint8_t, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
+        rc |= launch_me_phase<uint8_t, 2>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
+        rc |= launch_me_phase<uint8_t, 3>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
+    }
     else
-        k_me<uint16_t><<<blocks, threads, smem, ctx->stream>>>((const uint16_t*)fenc, fstride, (const uint16_t* const*)refs, rstride, lowres, mvcost, jobs, n, out, counter_dev);
-    CU_LAUNCH_CHECK(ctx);
-    return 0;
+    {
+        rc |= launch_me_phase<uint16_t, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
+        rc |= launch_me_phase<uint16_t, 2>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
+        rc |= launch_me_phase<uint16_t, 3>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
+    }
+    return rc;
 }

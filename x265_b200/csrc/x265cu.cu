@@ -63,7 +63,7 @@ void x265cu_destroy(x265cu_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFreeHost(c->h_stage); cudaFree(c->d_stage); cudaFree(c->d_counter);
+    cudaFreeHost(c->h_stage); cudaFree(c->d_stage); cudaFree(c->d_counter); cudaFree(c->d_me_state);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
