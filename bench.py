@@ -91,6 +91,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_cores():
+    """Usable host cores: os.cpu_count() capped by the cgroup CPU quota (the GPU box exposes 128 logical CPUs
+    but grants a quota of 16)."""
+    n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    return n
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -128,7 +145,7 @@ def cpu_reference(sample_rows, threads, kind_pref="reference", steps=1, warmup=0
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_cores()
     rows = 1
     # size the per-step sample so that the whole run stays within a few minutes
     probe = cpu_reference(rows, threads, steps=1)
@@ -281,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
         }
         # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ----
         if world == 1 and not args.no_cpu:
-            threads = os.cpu_count() or 1
+            threads = host_cores()
             probe = cpu_reference(1, threads)
             rows = int(max(1, min(34, 15.0 / max(probe["seconds"], 1e-3))))
             r = cpu_reference(rows, threads) if rows > 1 else probe

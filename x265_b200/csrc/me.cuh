@@ -506,7 +506,7 @@ __device__ __noinline__ int me_subpel_batch(const MeCtx<P>& c, int n, int qx, in
 
 // lowresQPelCost (lowres.h:94-120): qpel = rounded average of the two nearest hpel planes; 8x8 blocks
 template <typename P>
-__device__ int me_lowres_cost(const MeCtx<P>& c, int qx, int qy, bool satd)
+__device__ __noinline__ int me_lowres_cost(const MeCtx<P>& c, int qx, int qy, bool satd)
 {
     if ((qx | qy) & 1)
     {
@@ -636,7 +636,7 @@ __constant__ int8_t c_workload[8][5] = { {1,4,0,4,0}, {1,4,1,4,0}, {1,4,1,4,1}, 
 // one sub-pel refinement round (motion.cpp:1506-1523 / :1537-1553): candidates bmv + square1[1..dirs]*step,
 // folded in order with strict '<'; returns the winning direction (0 = none)
 template <typename P>
-__device__ __forceinline__ int me_subpel_round(const MeCtx<P>& c, int bx, int by, int dirs, int step, bool satd, int qminy, int qmaxy, int& bcost)
+__device__ __noinline__ int me_subpel_round(const MeCtx<P>& c, int bx, int by, int dirs, int step, bool satd, int qminy, int qmaxy, int& bcost)
 {
     const int lane = c.lane;
     const int i1 = min(lane + 1, 8);
