@@ -127,7 +127,7 @@ __device__ __noinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int
             if (c.lane == p) mysad = v;
         }
     }
-    else if (c.nw >= 32)
+    else if (c.nw >= 32 && !(c.nw == 32 && n > 16))
     {
         // sad_x4 style: every fenc word is loaded once per 4 candidates; lane walks words lane, lane+32, ...
         const int iters = c.nw >> 5;
@@ -181,6 +181,32 @@ __device__ __noinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int
                 if (c.lane == p0 + q) mysad = t;          // (candidates past n are duplicates of the last one and ignored)
             }
         }
+    }
+    else if ((c.nw <= 16 && n > 8) || (c.nw == 32 && n > 16))
+    {
+        // small block, many candidates (raster chunks, outer star levels): one candidate per LANE, the lane walks
+        // all words of its candidate; the fenc word of step k is broadcast from lane k's cache.  No reduction,
+        // ~7 instructions per word for up to 32 candidates at once.
+        const int sh = (offB & 3) * 8;
+        const uint8_t* base = rbase + (offB & ~3);
+        const int rstrideB = c.rstride * (int)sizeof(P);
+        const int rows = c.nw >> c.lgwpr;
+        int acc = 0, wd = 0;
+        for (int row = 0; row < rows; row++)
+        {
+            const uint8_t* rp = base + row * rstrideB;
+            for (int col = 0; col < wpr; col++, wd++)
+            {
+                const uint32_t f = __shfl_sync(0xffffffffu, c.fw, wd);
+                if (c.lane < n)
+                {
+                    const uint32_t* ap = (const uint32_t*)(rp + col * 4);
+                    uint32_t lo = ap[0];
+                    acc = sad_word<P>(f, sh ? __funnelshift_r(lo, ap[1], sh) : lo, acc);
+                }
+            }
+        }
+        mysad = acc;
     }
     else
     {
@@ -932,7 +958,7 @@ __device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j,
 // instructions, ~200 KB) thrashes the instruction cache: ncu showed 80 % of the stall samples in
 // `no_instructions` at a 46 % i-cache hit rate.  PHASE 0 = all three fused (used by small batches / tests).
 #ifndef ME_MIN_BLOCKS
-#define ME_MIN_BLOCKS 2
+#define ME_MIN_BLOCKS 3
 #endif
 template <typename P, int PHASE>
 __global__ void __launch_bounds__(256, ME_MIN_BLOCKS) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
