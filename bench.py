@@ -232,7 +232,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- resident: kernels only, per-step CUDA events, L2 flushed between steps ----
     barrier()
     sampler.start()
-    res_ms, stage = [], np.zeros(4)
+    res_ms, stage, phases = [], np.zeros(4), np.zeros(3)
     for s in range(args.steps):
         lib.check(lib.L.x265cu_memset(lib.ctx, flush.ptr, s & 255, flush.nbytes))
         lib.sync()
@@ -243,6 +243,7 @@ def run_ours(args, rank, world, local_rank):
         an.run_resident(7)
         res_ms.append(lib.timer_end() + t_ex)
         stage += np.array(an.stage_ms())
+        phases += np.array(lib.me_phase_ms())
     barrier()
     launches = lib.launch_count() - launches0
     t_res = float(np.sum(res_ms))
@@ -265,16 +266,18 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         stage /= args.steps
+        phases /= args.steps
         units = CTUS_PER_FRAME * world * args.steps
         value = units / (t_res / 1000.0)
         e2e = units / (t_e2e / 1000.0)
         peak, peak_src = peaks()
         es = 1
         plane = W * H * es
-        # algorithmic (compulsory) bytes of the dominant kernel k_me per launch:
-        # source plane + each reference plane read once + job records read + results written
-        me_bytes = plane * (1 + NREFS) + an.njobs * (40 + 16)
-        me_ms = stage[3] if stage[3] > 0 else stage[0]
+        # dominant kernel: k_me<P,2>, the integer-search launch of the three motion-estimation launches.
+        # Algorithmic (compulsory) bytes per launch: source plane + each reference plane
+        # read once + per job the 40 B job record and the 24 B phase state read and written.
+        me_bytes = plane * (1 + NREFS) + an.njobs * (40 + 24 + 24)
+        me_ms = phases[1]
         achieved = me_bytes / (me_ms / 1000.0) / 1e9
         cfg = workload_config()
         cfg["pu_jobs_per_frame"] = an.njobs
@@ -287,11 +290,11 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "CTUs/s", "ms_per_step": t_e2e / args.steps,
                     "h2d_bytes_per_step": int(an.h2d_bytes(field)), "d2h_bytes_per_step": int(an.d2h_bytes())},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_me (batched motionEstimate, one warp per PU x ref)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "k_me<P,2> (integer search phase of the batched motionEstimate, one warp per PU x ref)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(me_bytes), "kernel_ms": float(me_ms),
-                         "note": "ME is integer-ALU/LSU bound by construction (about 150 SAD points + 13 sub-pel SATDs per job); see DESIGN.md"},
-            "stages_ms": {"me_stage": float(stage[0]), "me_kernel": float(stage[3]), "residual": float(stage[1]), "intra": float(stage[2])},
+                         "note": "integer-issue bound by construction (about 380 SAD candidates per job against 88 B of compulsory traffic, planes L2-resident); see DESIGN.md section 5 and profiles/me_r1_ncu.md"},
+            "stages_ms": {"me_stage": float(stage[0]), "me_prechecks": float(phases[0]), "me_integer_search": float(phases[1]), "me_subpel": float(phases[2]), "residual": float(stage[1]), "intra": float(stage[2])},
             "stage_rooflines": {
                 "k_cu_residual": {"achieved": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9, "unit": "GB/s", "frac": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9 / peak},
                 "k_intra_search": {"achieved": sizes["intra_bytes"] / (stage[2] / 1000.0) / 1e9, "unit": "GB/s", "frac": sizes["intra_bytes"] / (stage[2] / 1000.0) / 1e9 / peak}},

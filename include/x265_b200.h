@@ -50,6 +50,8 @@ int  x265cu_timer_begin(x265cu_ctx*);
 float x265cu_timer_end(x265cu_ctx*);
 /* number of kernels this library has launched since the ctx was created */
 uint64_t x265cu_launch_count(x265cu_ctx*);
+/* device ms of the three launches of the last motion-estimation batch: pre-checks, integer search, sub-pel */
+int x265cu_me_phase_ms(x265cu_ctx*, float ms[3]);
 
 /* ---------- (1) per-call table ---------- */
 /* name / i / j / k exactly as the fields of EncoderPrimitives: "pu.sad" (i = LumaPU),

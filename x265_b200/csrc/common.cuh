@@ -19,6 +19,7 @@ struct x265cu_ctx
     uint8_t* h_stage; uint8_t* d_stage; size_t stage_bytes;
     int* d_counter;                     // work-queue counters for persistent kernels
     void* d_me_state; size_t me_state_bytes;   // per-job state between the ME phases
+    cudaEvent_t me_ev[4];               // boundaries of the three ME launches of the last x265cu_me_batch / analyser run
 };
 
 void x265cu_set_error(const char* what, cudaError_t e, const char* file, int line);

@@ -1019,17 +1019,23 @@ static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, 
     }
     MeState* st = (MeState*)ctx->d_me_state;
     int rc = 0;
+    CU_CHECK(cudaEventRecord(ctx->me_ev[0], ctx->stream));
     if (depth == 8)
     {
         rc |= launch_me_phase<uint8_t, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
+        CU_CHECK(cudaEventRecord(ctx->me_ev[1], ctx->stream));
         rc |= launch_me_phase<uint8_t, 2>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
+        CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
         rc |= launch_me_phase<uint8_t, 3>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
     }
     else
     {
         rc |= launch_me_phase<uint16_t, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
+        CU_CHECK(cudaEventRecord(ctx->me_ev[1], ctx->stream));
         rc |= launch_me_phase<uint16_t, 2>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
+        CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
         rc |= launch_me_phase<uint16_t, 3>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
     }
+    CU_CHECK(cudaEventRecord(ctx->me_ev[3], ctx->stream));
     return rc;
 }

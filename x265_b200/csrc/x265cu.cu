@@ -46,6 +46,7 @@ x265cu_ctx* x265cu_create(int device)
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NULL; }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    for (int i = 0; i < 4; i++) cudaEventCreate(&c->me_ev[i]);
     if (build_dct_tables() != 0) { delete c; return NULL; }
     c->stage_bytes = 4u << 20;
     if (cudaMallocHost((void**)&c->h_stage, c->stage_bytes) != cudaSuccess ||
@@ -94,6 +95,12 @@ float x265cu_timer_end(x265cu_ctx* c)
     return ms;
 }
 uint64_t x265cu_launch_count(x265cu_ctx* c) { return c->launches; }
+int x265cu_me_phase_ms(x265cu_ctx* c, float* ms)
+{
+    CU_CHECK(cudaEventSynchronize(c->me_ev[3]));
+    for (int i = 0; i < 3; i++) CU_CHECK(cudaEventElapsedTime(&ms[i], c->me_ev[i], c->me_ev[i + 1]));
+    return 0;
+}
 
 // ---------------- batched API ----------------
 int x265cu_pixelcmp_batch(x265cu_ctx* c, int depth, int op, const void* A, const void* B, const x265cu_cmp_job* jobs, int n, uint64_t* out)

@@ -53,6 +53,7 @@ _PROTOS = {
     "x265cu_timer_begin": (I, [P]),
     "x265cu_timer_end": (C.c_float, [P]),
     "x265cu_launch_count": (C.c_uint64, [P]),
+    "x265cu_me_phase_ms": (I, [P, C.POINTER(C.c_float)]),
     "x265cu_get_primitive": (P, [I, C.c_char_p, I, I, I]),
     "x265cu_pixelcmp_batch": (I, [P, I, I, P, P, P, I, P]),
     "x265cu_blockop_batch": (I, [P, I, I, P, P, P, P, I]),
@@ -147,6 +148,11 @@ class Lib:
         if ms < 0:
             raise RuntimeError("timer failed: " + self.last_error())
         return ms
+
+    def me_phase_ms(self):
+        ms = (C.c_float * 3)()
+        self.check(self.L.x265cu_me_phase_ms(self.ctx, ms))
+        return [float(x) for x in ms]
 
     def launch_count(self):
         return int(self.L.x265cu_launch_count(self.ctx))
