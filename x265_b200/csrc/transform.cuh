@@ -5,6 +5,7 @@
 // matrix product below is bit-identical (|acc| <= 32*90*32768 < 2^31).
 #pragma once
 #include "common.cuh"
+#include "transform_mma.cuh"
 
 // host: regenerate the HEVC matrices from the 32-point basis and upload them
 static const int16_t h_basis[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67,
@@ -153,8 +154,14 @@ static int launch_transform(x265cu_ctx* ctx, int depth, int op, int N, const int
     if (n <= 0) return 0;
     if (op == X265CU_DST4 || op == X265CU_IDST4) N = 4;
     if (N != 4 && N != 8 && N != 16 && N != 32) { x265cu_set_error("transform size", cudaErrorInvalidValue, __FILE__, __LINE__); return -1; }
-    if (depth == 8) launch_transform_d<8>(ctx, op, N, src, dst, stride, tu_pitch, n);
-    else            launch_transform_d<10>(ctx, op, N, src, dst, stride, tu_pitch, n);
+    // 16x16 / 32x32 go to the tensor-core (IMMA) kernel when the operands are vector-load aligned
+    int took = (depth == 8) ? launch_transform_mma<8>(ctx, op, N, src, dst, stride, tu_pitch, n)
+                            : launch_transform_mma<10>(ctx, op, N, src, dst, stride, tu_pitch, n);
+    if (!took)
+    {
+        if (depth == 8) launch_transform_d<8>(ctx, op, N, src, dst, stride, tu_pitch, n);
+        else            launch_transform_d<10>(ctx, op, N, src, dst, stride, tu_pitch, n);
+    }
     CU_LAUNCH_CHECK(ctx);
     return 0;
 }
