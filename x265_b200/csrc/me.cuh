@@ -127,7 +127,7 @@ __device__ __noinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int
             if (c.lane == p) mysad = v;
         }
     }
-    else if (c.nw >= 32 && !(c.nw == 32 && n > 16))
+    else if (c.nw >= 32 && !(wpr <= 4 && c.nw == 32 && n > 16))
     {
         // sad_x4 style: every fenc word is loaded once per 4 candidates; lane walks words lane, lane+32, ...
         const int iters = c.nw >> 5;
@@ -153,9 +153,7 @@ __device__ __noinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int
                 for (int q = 0; q < 4; q++)
                 {
                     const uint32_t* ap = (const uint32_t*)(rbase + o[q]);
-                    uint32_t lo = ap[0];
-                    uint32_t v = sh[q] ? __funnelshift_r(lo, ap[1], sh[q]) : lo;
-                    acc[q] = sad_word<P>(c.fw, v, 0);
+                    acc[q] = sad_word<P>(c.fw, __funnelshift_r(ap[0], ap[1], sh[q]), 0);
                 }
             }
             else
@@ -168,9 +166,7 @@ __device__ __noinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int
                     for (int q = 0; q < 4; q++)
                     {
                         const uint32_t* ap = (const uint32_t*)(rbase + o[q] + k * stepRef);
-                        uint32_t lo = ap[0];
-                        uint32_t v = sh[q] ? __funnelshift_r(lo, ap[1], sh[q]) : lo;
-                        acc[q] = sad_word<P>(f, v, acc[q]);
+                        acc[q] = sad_word<P>(f, __funnelshift_r(ap[0], ap[1], sh[q]), acc[q]);
                     }
                 }
             }
@@ -182,30 +178,25 @@ __device__ __noinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int
             }
         }
     }
-    else if ((c.nw <= 16 && n > 8) || (c.nw == 32 && n > 16))
+    else if (wpr <= 4 && ((c.nw <= 16 && n > 8) || (c.nw == 32 && n > 16)))
     {
         // small block, many candidates (raster chunks, outer star levels): one candidate per LANE, the lane walks
         // all words of its candidate; the fenc word of step k is broadcast from lane k's cache.  No reduction,
         // ~7 instructions per word for up to 32 candidates at once.
-        const int sh = (offB & 3) * 8;
-        const uint8_t* base = rbase + (offB & ~3);
+        // idle lanes (>= n) walk candidate 0's addresses so that every load is in bounds and unpredicated
+        const int myOff = __shfl_sync(0xffffffffu, offB, c.lane < n ? c.lane : 0);
+        const int sh = (myOff & 3) * 8;
+        const uint8_t* rp = rbase + (myOff & ~3);
         const int rstrideB = c.rstride * (int)sizeof(P);
         const int rows = c.nw >> c.lgwpr;
         int acc = 0, wd = 0;
-        for (int row = 0; row < rows; row++)
-        {
-            const uint8_t* rp = base + row * rstrideB;
-            for (int col = 0; col < wpr; col++, wd++)
-            {
-                const uint32_t f = __shfl_sync(0xffffffffu, c.fw, wd);
-                if (c.lane < n)
-                {
-                    const uint32_t* ap = (const uint32_t*)(rp + col * 4);
-                    uint32_t lo = ap[0];
-                    acc = sad_word<P>(f, sh ? __funnelshift_r(lo, ap[1], sh) : lo, acc);
-                }
-            }
-        }
+#define ME_LPC_WORD(COL) { const uint32_t f = __shfl_sync(0xffffffffu, c.fw, wd + (COL)); \
+                           const uint32_t* ap = (const uint32_t*)(rp + (COL) * 4); \
+                           acc = sad_word<P>(f, __funnelshift_r(ap[0], ap[1], sh), acc); }
+        if (wpr == 1)      for (int row = 0; row < rows; row++, rp += rstrideB, wd += 1) { ME_LPC_WORD(0) }
+        else if (wpr == 2) for (int row = 0; row < rows; row++, rp += rstrideB, wd += 2) { ME_LPC_WORD(0) ME_LPC_WORD(1) }
+        else               for (int row = 0; row < rows; row++, rp += rstrideB, wd += 4) { ME_LPC_WORD(0) ME_LPC_WORD(1) ME_LPC_WORD(2) ME_LPC_WORD(3) }
+#undef ME_LPC_WORD
         mysad = acc;
     }
     else
@@ -223,8 +214,7 @@ __device__ __noinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int
             {
                 const uint32_t* ap = (const uint32_t*)(rbase + (ob & ~3) + laneRef);
                 const int sh = (ob & 3) * 8;
-                uint32_t lo = ap[0];
-                acc = sad_word<P>(c.fw, sh ? __funnelshift_r(lo, ap[1], sh) : lo, 0);
+                acc = sad_word<P>(c.fw, __funnelshift_r(ap[0], ap[1], sh), 0);
             }
             for (int s = c.nw >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
             const int v = __shfl_sync(0xffffffffu, acc, ((c.lane - base) << c.lgnw) & 31);
@@ -960,8 +950,11 @@ __device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j,
 #ifndef ME_MIN_BLOCKS
 #define ME_MIN_BLOCKS 3
 #endif
+#ifndef ME_P2_BLOCKS
+#define ME_P2_BLOCKS 4
+#endif
 template <typename P, int PHASE>
-__global__ void __launch_bounds__(256, ME_MIN_BLOCKS) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
+__global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : ME_MIN_BLOCKS) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
                                                            const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
                                                            int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter)
 {
@@ -995,8 +988,8 @@ static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const
                            const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter)
 {
     const int threads = 256, warps = threads / 32;
-    const size_t smem = sizeof(MeShared) * warps;
-    int blocks = ctx->sm_count * ME_MIN_BLOCKS;
+    const size_t smem = PHASE == 2 ? 0 : sizeof(MeShared) * warps;      // the integer search never touches the interpolation scratch
+    int blocks = ctx->sm_count * (PHASE == 2 ? ME_P2_BLOCKS : ME_MIN_BLOCKS);
     int need = (n + warps - 1) / warps;
     if (blocks > need) blocks = need;
     k_me<P, PHASE><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, lowres, mvcost, jobs, n, out, state, counter);
