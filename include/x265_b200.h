@@ -73,6 +73,13 @@ typedef struct {
 /* out_dev[n] : uint64 (sse_t / var packing as in the reference; int costs zero-extended) */
 int x265cu_pixelcmp_batch(x265cu_ctx*, int depth, int op, const void* planeA_dev, const void* planeB_dev,
                           const x265cu_cmp_job* jobs_dev, int n, uint64_t* out_dev);
+/* Same costs over a regular grid: block (bx,by) compares A + by*bh*a_stride + bx*bw with the same
+ * offset from B (the displacement of a whole-frame compare is baked into B); strides in pixels;
+ * op = SAD / SATD / SA8D / SSE_PP; out_dev[by*nbx + bx].  This is the shape of the frame-level cost
+ * passes (lowres SATD maps, slicetype.cpp:640-700; weightp cost, slicetype.cpp:462-520): no job list,
+ * one lane per 16-byte column so plane reads are fully coalesced. */
+int x265cu_pixelcmp_grid(x265cu_ctx*, int depth, int op, const void* A_dev, int64_t a_stride, const void* B_dev, int64_t b_stride,
+                         int bw, int bh, int nbx, int nby, uint64_t* out_dev);
 
 /* elementwise block-op class (pixel.cpp:379-862, ipfilter.cpp:40-57) */
 enum { X265CU_COPY_PP = 0, X265CU_COPY_SS, X265CU_COPY_SP, X265CU_COPY_PS, X265CU_SUB_PS, X265CU_ADD_PS,

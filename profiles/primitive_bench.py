@@ -79,6 +79,16 @@ def main():
         ms = timed(lib, flush, lambda: lib.pixelcmp_batch(8, op, dA, dB, dJ, n, dO), args.reps)
         add("k_pixelcmp %s %dx%d grid" % (op, bw, bh), ms, n * (2 * bw * bh + 8), "%d jobs" % n)
         dJ.free(); dO.free()
+    # ---- same compares through the grid entry point (no job list; lane per 16-byte column) ----
+    for op, (bw, bh) in (("sad", (8, 8)), ("sad", (16, 16)), ("sad", (64, 64)), ("satd", (8, 8)), ("satd", (16, 16)), ("satd", (64, 64)),
+                         ("sa8d", (8, 8)), ("sa8d", (16, 16)), ("sa8d", (64, 64)), ("sse_pp", (16, 16)), ("sse_pp", (64, 64))):
+        nbx, nby = W // bw, H // bh
+        n = nbx * nby
+        dO = lib.alloc(8 * n)
+        for tag, boff in (("B displaced (+5,+3)", org + 3 * stride + 5), ("B aligned", org + 16 * stride)):
+            ms = timed(lib, flush, lambda: lib.pixelcmp_grid(8, op, dA.ptr + org, stride, dB.ptr + boff, stride, bw, bh, nbx, nby, dO), args.reps)
+            add("k_pixelcmp_grid %s %dx%d" % (op, bw, bh), ms, n * (2 * bw * bh + 8), "%d blocks, %s" % (n, tag))
+        dO.free()
     # ---- interpolation: whole frame as 64x64 / 16x16 hvpp jobs ----
     dD = lib.alloc(a.nbytes)
     for op, (bw, bh) in (("hvpp", (64, 64)), ("hvpp", (16, 16)), ("hpp", (64, 64)), ("vpp", (64, 64))):

@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(LA_WARPS * 32, 1) k_lookahead_cost(const x265c
             const int wpr = (8 * (int)sizeof(P)) >> 2;
             c.lgwpr = 31 - __clz(wpr); c.nw = wpr * 8; c.lgnw = 31 - __clz(c.nw);
             {
-                const int wd = lane & (c.nw - 1);
-                c.fw = (c.nw <= 32) ? *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)(wd >> c.lgwpr) * stride) * sizeof(P) + (wd & (wpr - 1)) * 4) : 0;
+                const unsigned fal = (unsigned)(uintptr_t)c.fenc | (unsigned)(stride * (int)sizeof(P));
+                c.lgsegw = min(c.lgwpr, (fal & 15u) == 0 ? 2 : (fal & 7u) == 0 ? 1 : 0);
             }
             int bcost = LA_COST_MAX, listused = 0;
             int lmx[2] = { 0, 0 }, lmy[2] = { 0, 0 };            // final MV of each list for the bidir candidates

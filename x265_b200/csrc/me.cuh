@@ -35,14 +35,14 @@ struct MeCtx
     int w, h, lgw, lane, lowres;
     bool pow2;                             // w and h are powers of two (all 2Nx2N / rect PUs); AMP sizes take the generic paths
     int nw, lgnw, lgwpr;                   // words per PU, log2, log2(words per row)
-    uint32_t fw;                           // this lane's fenc word when nw <= 32
+    int lgsegw;                            // log2 words per lane segment (16 B when the fenc rows allow vector loads)
     MeShared* sm;
 };
 
 template <typename P>
 __device__ __forceinline__ int me_mvcost(const MeCtx<P>& c, int qx, int qy)
 {
-    return (uint16_t)(c.mvc[qx - c.mvpx] + c.mvc[qy - c.mvpy]);
+    return (uint16_t)(__ldg(c.mvc + (qx - c.mvpx)) + __ldg(c.mvc + (qy - c.mvpy)));
 }
 
 template <typename P>
@@ -56,8 +56,8 @@ __device__ __forceinline__ uint32_t ld_unaligned32(uintptr_t a)
 {
     const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(a & 3) * 8;
-    uint32_t lo = ap[0];
-    return sh ? __funnelshift_r(lo, ap[1], sh) : lo;
+    uint32_t lo = __ldg(ap);
+    return sh ? __funnelshift_r(lo, __ldg(ap + 1), sh) : lo;
 }
 
 template <typename P> __device__ __forceinline__ int sad_word(uint32_t a, uint32_t b, int acc)
@@ -65,42 +65,89 @@ template <typename P> __device__ __forceinline__ int sad_word(uint32_t a, uint32
     return sizeof(P) == 1 ? (int)(__vsadu4(a, b) + (uint32_t)acc) : (int)(__vsadu2(a, b) + (uint32_t)acc);
 }
 
-// SAD of the fenc block against ONE reference position (element pointer, rows may be unaligned).
+// ---- full-pel SAD of up to 32 candidate positions at once (pow2 PUs) -----------------------------
+// The PU is cut into row segments of SEGW words (16 bytes when the rows are wide and aligned enough).
+// With n candidates in the burst, lpc = 32 / pow2ceil(n) lanes share one candidate (capped by the number
+// of segments); the lpc lanes split the PU's columns first and its rows second, so a lane walks a fixed
+// set of columns down the rows with incremental addresses.  Per segment: one vector load of fenc (the
+// same address in every candidate group: one L1 broadcast), SEGW+1 aligned words of the reference
+// funnel-shifted to the candidate's byte phase, SEGW VABSDIFF4.ACC.  All candidates of a burst are in
+// flight together; one xor-shuffle tree per burst folds the lanes of each candidate.
+// `offB` = byte offset of lane i's candidate from `base` (lanes >= n ignored).  Result in lane i < n.
+template <typename P, int LGSEGW>
+__device__ __forceinline__ int me_sad_multi_t(const MeCtx<P>& c, const uint8_t* __restrict__ base, int n, int offB)
+{
+    constexpr int SEGW = 1 << LGSEGW;
+    const int lane = c.lane;
+    const int lgn = n <= 1 ? 0 : 32 - __clz(n - 1);
+    const int lgnseg = c.lgnw - LGSEGW, lgspr = c.lgwpr - LGSEGW;          // log2 segments per PU / per row
+    const int lglpc = min(5 - lgn, lgnseg);
+    const int lgcols = min(lglpc, lgspr), lgrows = lglpc - lgcols;         // lanes of a candidate: 2^lgcols across, 2^lgrows down
+    const int sub = lane & ((1 << lglpc) - 1);
+    const int ob = __shfl_sync(0xffffffffu, offB, min(lane >> lglpc, n - 1));
+    const uintptr_t cptr = (uintptr_t)base + (intptr_t)ob;                 // my candidate's block origin; any byte phase
+    const unsigned sh = ((unsigned)cptr & 3u) * 8u;
+    const int rsB = c.rstride * (int)sizeof(P), fsB = c.fstride * (int)sizeof(P);
+    const int subcol = sub & ((1 << lgcols) - 1), subrow = sub >> lgcols;
+    const uint8_t* rrow = (const uint8_t*)(cptr & ~(uintptr_t)3) + subrow * rsB + subcol * (SEGW * 4);
+    const uint8_t* frow = (const uint8_t*)c.fenc + subrow * fsB + subcol * (SEGW * 4);
+    const int rowStepR = rsB << lgrows, rowStepF = fsB << lgrows, colStep = (SEGW * 4) << lgcols;
+    const int nrows = c.h >> lgrows, ncols = 1 << (lgspr - lgcols);
+    int acc = 0;
+    // columns outside (1..8 iterations), rows inside: the long dimension is the unrolled one
+    for (int jc = 0; jc < ncols; jc++, rrow += colStep, frow += colStep)
+    {
+        const uint8_t* rp = rrow; const uint8_t* fp = frow;
+#pragma unroll 2
+        for (int i = 0; i < nrows; i++, rp += rowStepR, fp += rowStepF)
+        {
+            const uint32_t* ap = (const uint32_t*)rp;
+            if (SEGW == 4)
+            {
+                const uint4 f = __ldg((const uint4*)fp);
+                const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2), w3 = __ldg(ap + 3), w4 = __ldg(ap + 4);
+                acc = sad_word<P>(f.x, __funnelshift_r(w0, w1, sh), acc); acc = sad_word<P>(f.y, __funnelshift_r(w1, w2, sh), acc);
+                acc = sad_word<P>(f.z, __funnelshift_r(w2, w3, sh), acc); acc = sad_word<P>(f.w, __funnelshift_r(w3, w4, sh), acc);
+            }
+            else if (SEGW == 2)
+            {
+                const uint2 f = __ldg((const uint2*)fp);
+                const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
+                acc = sad_word<P>(f.x, __funnelshift_r(w0, w1, sh), acc); acc = sad_word<P>(f.y, __funnelshift_r(w1, w2, sh), acc);
+            }
+            else
+            {
+                const uint32_t f = __ldg((const uint32_t*)fp);
+                acc = sad_word<P>(f, __funnelshift_r(__ldg(ap), __ldg(ap + 1), sh), acc);
+            }
+        }
+    }
+    for (int o = 1; o < (1 << lglpc); o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return __shfl_sync(0xffffffffu, acc, (lane << lglpc) & 31);
+}
+
+template <typename P>
+__device__ __forceinline__ int me_sad_multi(const MeCtx<P>& c, const uint8_t* __restrict__ base, int n, int offB)
+{
+    if (c.lgsegw == 2) return me_sad_multi_t<P, 2>(c, base, n, offB);
+    if (c.lgsegw == 1) return me_sad_multi_t<P, 1>(c, base, n, offB);
+    return me_sad_multi_t<P, 0>(c, base, n, offB);
+}
+
+// SAD of the fenc block against ONE reference position (element pointer, rows may be unaligned); all lanes get it.
 template <typename P>
 __device__ __noinline__ int me_sad_direct(const MeCtx<P>& c, const P* __restrict__ r)
 {
+    if (c.pow2) return __shfl_sync(0xffffffffu, me_sad_multi(c, (const uint8_t*)r, 1, 0), 0);
+    // AMP sizes (12/24/48): generic word walk
     const uintptr_t rbase = (uintptr_t)r;
-    const int wpr = 1 << c.lgwpr;
     int acc = 0;
-    if (!c.pow2)
-    {   // AMP sizes (12/24/48): generic word walk
-        const int wprg = (c.w * (int)sizeof(P)) >> 2, nwg = wprg * c.h;
-        for (int wd = c.lane; wd < nwg; wd += 32)
-        {
-            int row = wd / wprg, col = wd - row * wprg;
-            uint32_t f = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * c.fstride) * sizeof(P) + col * 4);
-            acc = sad_word<P>(f, ld_unaligned32(rbase + ((size_t)row * c.rstride) * sizeof(P) + col * 4), acc);
-        }
-    }
-    else if (c.nw <= 32)
+    const int wprg = (c.w * (int)sizeof(P)) >> 2, nwg = wprg * c.h;
+    for (int wd = c.lane; wd < nwg; wd += 32)
     {
-        if (c.lane < c.nw)
-        {
-            int row = c.lane >> c.lgwpr, col = c.lane & (wpr - 1);
-            acc = sad_word<P>(c.fw, ld_unaligned32(rbase + ((size_t)row * c.rstride) * sizeof(P) + col * 4), 0);
-        }
-    }
-    else
-    {
-        const int iters = c.nw >> 5;
-#pragma unroll 4
-        for (int k = 0; k < iters; k++)
-        {
-            int wd = c.lane + (k << 5);
-            int row = wd >> c.lgwpr, col = wd & (wpr - 1);
-            uint32_t f = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * c.fstride) * sizeof(P) + col * 4);
-            acc = sad_word<P>(f, ld_unaligned32(rbase + ((size_t)row * c.rstride) * sizeof(P) + col * 4), acc);
-        }
+        int row = wd / wprg, col = wd - row * wprg;
+        uint32_t f = __ldg((const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * c.fstride) * sizeof(P) + col * 4));
+        acc = sad_word<P>(f, ld_unaligned32(rbase + ((size_t)row * c.rstride) * sizeof(P) + col * 4), acc);
     }
     return warp_sum(acc);
 }
@@ -108,117 +155,20 @@ __device__ __noinline__ int me_sad_direct(const MeCtx<P>& c, const P* __restrict
 // Full-pel SAD + mvcost of up to 32 candidate positions at once.  Lane i (< n) owns candidate i:
 // (px, py) in full-pel units relative to the block; returns that candidate's cost in lane i.
 // x8: the raster quirk (motion.cpp:1194: mvcost(tmv << 3) for every 4th column).
-// Plane strides are multiples of 4 bytes and every lane's word offset is a multiple of 4, so the byte
-// misalignment of a candidate ((offset * sizeof(P)) & 3) is the same for all of its words: the funnel
-// shift amount is computed once per candidate, and the per-lane part of the address once per job.
 template <typename P>
-__device__ __noinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int py, bool x8)
+__device__ __forceinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, int py, bool x8)
 {
     const int offB = (py * c.rstride + px) * (int)sizeof(P);          // byte offset of my candidate
     const uint8_t* rbase = (const uint8_t*)c.ref[0];
-    const int wpr = 1 << c.lgwpr;
     int mysad = 0;
-    if (!c.pow2)
+    if (c.pow2) mysad = me_sad_multi(c, rbase, n, offB);
+    else
     {
         for (int p = 0; p < n; p++)
         {
             const int offp = __shfl_sync(0xffffffffu, offB, p);
             const int v = me_sad_direct(c, (const P*)(rbase + offp));
             if (c.lane == p) mysad = v;
-        }
-    }
-    else if (c.nw >= 32 && !(wpr <= 4 && c.nw == 32 && n > 16))
-    {
-        // sad_x4 style: every fenc word is loaded once per 4 candidates; lane walks words lane, lane+32, ...
-        const int iters = c.nw >> 5;
-        const int rowsPerIter = 32 >> c.lgwpr;                          // rows advanced by one iteration (wpr <= 32)
-        const int row0 = c.lane >> c.lgwpr, col4 = (c.lane & (wpr - 1)) * 4;
-        const int laneRef = row0 * c.rstride * (int)sizeof(P) + col4;   // byte offset of my first word inside the block (ref)
-        const int laneFenc = row0 * c.fstride * (int)sizeof(P) + col4;
-        const int stepRef = rowsPerIter * c.rstride * (int)sizeof(P), stepFenc = rowsPerIter * c.fstride * (int)sizeof(P);
-        for (int p0 = 0; p0 < n; p0 += 4)
-        {
-            int o[4], sh[4], acc[4] = { 0, 0, 0, 0 };
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-            {
-                const int ob = __shfl_sync(0xffffffffu, offB, min(p0 + q, n - 1));
-                sh[q] = (ob & 3) * 8;
-                o[q] = (ob & ~3) + laneRef;
-            }
-            const uint8_t* fp = (const uint8_t*)c.fenc + laneFenc;
-            if (iters == 1)
-            {
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                {
-                    const uint32_t* ap = (const uint32_t*)(rbase + o[q]);
-                    acc[q] = sad_word<P>(c.fw, __funnelshift_r(ap[0], ap[1], sh[q]), 0);
-                }
-            }
-            else
-            {
-#pragma unroll 2
-                for (int k = 0; k < iters; k++)
-                {
-                    const uint32_t f = *(const uint32_t*)(fp + k * stepFenc);
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                    {
-                        const uint32_t* ap = (const uint32_t*)(rbase + o[q] + k * stepRef);
-                        acc[q] = sad_word<P>(f, __funnelshift_r(ap[0], ap[1], sh[q]), acc[q]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-            {
-                const int t = warp_sum(acc[q]);
-                if (c.lane == p0 + q) mysad = t;          // (candidates past n are duplicates of the last one and ignored)
-            }
-        }
-    }
-    else if (wpr <= 4 && ((c.nw <= 16 && n > 8) || (c.nw == 32 && n > 16)))
-    {
-        // small block, many candidates (raster chunks, outer star levels): one candidate per LANE, the lane walks
-        // all words of its candidate; the fenc word of step k is broadcast from lane k's cache.  No reduction,
-        // ~7 instructions per word for up to 32 candidates at once.
-        // idle lanes (>= n) walk candidate 0's addresses so that every load is in bounds and unpredicated
-        const int myOff = __shfl_sync(0xffffffffu, offB, c.lane < n ? c.lane : 0);
-        const int sh = (myOff & 3) * 8;
-        const uint8_t* rp = rbase + (myOff & ~3);
-        const int rstrideB = c.rstride * (int)sizeof(P);
-        const int rows = c.nw >> c.lgwpr;
-        int acc = 0, wd = 0;
-#define ME_LPC_WORD(COL) { const uint32_t f = __shfl_sync(0xffffffffu, c.fw, wd + (COL)); \
-                           const uint32_t* ap = (const uint32_t*)(rp + (COL) * 4); \
-                           acc = sad_word<P>(f, __funnelshift_r(ap[0], ap[1], sh), acc); }
-        if (wpr == 1)      for (int row = 0; row < rows; row++, rp += rstrideB, wd += 1) { ME_LPC_WORD(0) }
-        else if (wpr == 2) for (int row = 0; row < rows; row++, rp += rstrideB, wd += 2) { ME_LPC_WORD(0) ME_LPC_WORD(1) }
-        else               for (int row = 0; row < rows; row++, rp += rstrideB, wd += 4) { ME_LPC_WORD(0) ME_LPC_WORD(1) ME_LPC_WORD(2) ME_LPC_WORD(3) }
-#undef ME_LPC_WORD
-        mysad = acc;
-    }
-    else
-    {
-        // several candidates per pass: lane group g = lane >> lgnw evaluates candidate base + g
-        const int ppp = 32 >> c.lgnw;
-        const int wd = c.lane & (c.nw - 1);
-        const int laneRef = (wd >> c.lgwpr) * c.rstride * (int)sizeof(P) + (wd & (wpr - 1)) * 4;
-        for (int base = 0; base < n; base += ppp)
-        {
-            const int p = base + (c.lane >> c.lgnw);
-            const int ob = __shfl_sync(0xffffffffu, offB, min(p, n - 1));
-            int acc = 0;
-            if (p < n)
-            {
-                const uint32_t* ap = (const uint32_t*)(rbase + (ob & ~3) + laneRef);
-                const int sh = (ob & 3) * 8;
-                acc = sad_word<P>(c.fw, __funnelshift_r(ap[0], ap[1], sh), 0);
-            }
-            for (int s = c.nw >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-            const int v = __shfl_sync(0xffffffffu, acc, ((c.lane - base) << c.lgnw) & 31);
-            if (c.lane >= base && c.lane < base + ppp) mysad = v;
         }
     }
     int cost = 0x7fffffff;
@@ -254,6 +204,35 @@ __device__ __forceinline__ int me_compact(bool valid, int cnt, int& a, int& b, i
     a = __shfl_sync(0xffffffffu, a, src); b = __shfl_sync(0xffffffffu, b, src);
     c2 = __shfl_sync(0xffffffffu, c2, src); d = __shfl_sync(0xffffffffu, d, src);
     return __popc(m);
+}
+
+// 8-tap horizontal luma sum of the 8 pixels starting at s (ipfilter.cpp:79-118 inner loop).  8-bit planes:
+// three aligned words, two funnel shifts and two DP4A (u8 pixels x s8 taps, exact in int32) instead of
+// eight byte loads and eight IMADs; the third word is within the plane margin even when unused.
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int acc)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+}
+// c_lumaFilter[xf] packed as 2 x 4 signed bytes (taps 0-3, taps 4-7), little-endian
+__constant__ uint32_t c_luma4[4][2] = { { 0x40000000u, 0u }, { 0x3af604ffu, 0x0001fb11u }, { 0x28f504ffu, 0xff04f528u }, { 0x11fb0100u, 0xff04f63au } };
+template <typename P>
+__device__ __forceinline__ int me_hsum8(const P* __restrict__ s, const int16_t* __restrict__ cx, int xf)
+{
+    if (sizeof(P) == 1)
+    {
+        const uintptr_t a = (uintptr_t)s;
+        const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+        const unsigned sh = ((unsigned)a & 3u) * 8u;
+        const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        return dp4a_us(hi, c_luma4[xf][1], dp4a_us(lo, c_luma4[xf][0], 0));
+    }
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += (int)s[k] * cx[k];
+    return sum;
 }
 
 // cost of a band of prediction held in c.sm->pred (stride 64) against fenc rows [y0, y0+rows)
@@ -327,10 +306,7 @@ __device__ __noinline__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy,
             {
                 int y, x; me_yx(c, i, y, x);
                 const P* s = r + (ptrdiff_t)(y0 + y) * c.rstride + x - 3;
-                int sum = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) sum += (int)s[k] * cx[k];
-                c.sm->pred[y * 64 + x] = (uint16_t)interp_finish<DEPTH>(sum, 0);
+                c.sm->pred[y * 64 + x] = (uint16_t)interp_finish<DEPTH>(me_hsum8(s, cx, xf), 0);
             }
         }
         else if (!xf)
@@ -352,10 +328,7 @@ __device__ __noinline__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy,
             {
                 int y, x; me_yx(c, i, y, x);
                 const P* s = r + (ptrdiff_t)(y0 + y - 3) * c.rstride + x - 3;
-                int sum = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) sum += (int)s[k] * cx[k];
-                c.sm->mid[y * 64 + x] = (int16_t)interp_finish<DEPTH>(sum, 1);
+                c.sm->mid[y * 64 + x] = (int16_t)interp_finish<DEPTH>(me_hsum8(s, cx, xf), 1);
             }
             __syncwarp();
             for (int i = c.lane; i < rows * c.w; i += 32)
@@ -402,10 +375,7 @@ __device__ __noinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int 
             {
                 const int y = rem >> c.lgw, x = rem & (c.w - 1);
                 const P* s = r0 + (ptrdiff_t)y * c.rstride + x;
-                int sum = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) sum += (int)s[k] * cx[k];
-                c.sm->mid[cand * 368 + rem] = (int16_t)interp_finish<DEPTH>(sum, 1);
+                c.sm->mid[cand * 368 + rem] = (int16_t)interp_finish<DEPTH>(me_hsum8(s, cx, xf), 1);
             }
         }
     }
@@ -426,10 +396,7 @@ __device__ __noinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int 
         {
             const P* s = r + (ptrdiff_t)y * c.rstride + x - 3;
             const int16_t* cx = c_lumaFilter[xf];
-            int sum = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) sum += (int)s[k] * cx[k];
-            v = interp_finish<DEPTH>(sum, 0);
+            v = interp_finish<DEPTH>(me_hsum8(s, cx, xf), 0);
         }
         else if (!xf)
         {
@@ -586,55 +553,51 @@ __device__ __forceinline__ void me_fold(MeStar& s, int n, int cost, int px, int 
 // a level is the reference's (its x4 fast path and its bounds-checked path visit the same points in
 // the same order), out-of-range candidates are dropped before evaluation.
 template <typename P>
-__device__ __noinline__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters, int merange)
+__device__ __forceinline__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters, int merange)
 {
+    // One loop over the distance levels with a SINGLE evaluation site (the SAD core is inlined, so every extra
+    // site is another copy in the instruction cache): level 0 = distance 1 (4 points), levels 1..3 = distances
+    // 2, 4, 8 (8 points), levels 4.. = distances 16, 32, ... <= merange (16 points).
     const int ox = s.bx, oy = s.by, lane = c.lane;
-    int saved = s.bcost, rounds = 0;
+    int rounds = 0;
+    for (int lvl = 0; ; lvl++)
     {
-        // dist 1: top(2) left(4) right(5) bottom(7)
-        int px = ox + (lane == 1 ? -1 : lane == 2 ? 1 : 0), py = oy + (lane == 0 ? -1 : lane == 3 ? 1 : 0);
-        int point = lane == 0 ? 2 : lane == 1 ? 4 : lane == 2 ? 5 : 7, dist = 1;
-        bool valid = lane < 4 && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
-        int n = me_compact(valid, 4, px, py, point, dist);
-        int cost = me_eval_points(c, n, px, py, false);
-        me_fold(s, n, cost, px, py, point, dist);
-        if (s.bcost < saved) rounds = 0;
-        else if (++rounds >= earlyExitIters) return;
-    }
-    for (int d = 2; d <= 8; d <<= 1)
-    {
-        // order: 2(top) 1 3 4(left) 5(right) 6 8 7(bottom); half-distance points need both their checks
-        const int h2 = d >> 1;
-        const int8_t dxs[8] = { 0, -1, 1, -2, 2, -1, 1, 0 }, dys[8] = { -2, -1, -1, 0, 0, 1, 1, 2 };
-        const int8_t pts[8] = { 2, 1, 3, 4, 5, 6, 8, 7 };
-        const int k = lane & 7;
-        int px = ox + dxs[k] * h2, py = oy + dys[k] * h2;
-        int point = pts[k], dist = (k == 1 || k == 2 || k == 5 || k == 6) ? h2 : d;
-        bool valid = lane < 8 && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
-        saved = s.bcost;
-        int n = me_compact(valid, 8, px, py, point, dist);
-        int cost = me_eval_points(c, n, px, py, false);
-        me_fold(s, n, cost, px, py, point, dist);
-        if (s.bcost < saved) rounds = 0;
-        else if (++rounds >= earlyExitIters) return;
-    }
-    for (int d = 16; d <= merange; d <<= 1)
-    {
-        // order: top, left, right, bottom, then k = 1..3: (xl,yt) (xr,yt) (xl,yb) (xr,yb)
-        const int q = d >> 2;
-        int px, py;
-        if (lane < 4) { px = ox + (lane == 1 ? -d : lane == 2 ? d : 0); py = oy + (lane == 0 ? -d : lane == 3 ? d : 0); }
+        const int d = lvl < 4 ? (1 << lvl) : (16 << (lvl - 4));
+        if (lvl >= 4 && d > merange) break;
+        int px, py, point, dist, cnt;
+        if (lvl == 0)
+        {
+            // dist 1: top(2) left(4) right(5) bottom(7)
+            px = ox + (lane == 1 ? -1 : lane == 2 ? 1 : 0); py = oy + (lane == 0 ? -1 : lane == 3 ? 1 : 0);
+            point = lane == 0 ? 2 : lane == 1 ? 4 : lane == 2 ? 5 : 7; dist = 1; cnt = 4;
+        }
+        else if (lvl < 4)
+        {
+            // order: 2(top) 1 3 4(left) 5(right) 6 8 7(bottom); half-distance points need both their checks
+            const int h2 = d >> 1, k = lane & 7;
+            const int dx = k == 0 ? 0 : k == 1 ? -1 : k == 2 ? 1 : k == 3 ? -2 : k == 4 ? 2 : k == 5 ? -1 : k == 6 ? 1 : 0;
+            const int dy = k == 0 ? -2 : k < 3 ? -1 : k < 5 ? 0 : k < 7 ? 1 : 2;
+            px = ox + dx * h2; py = oy + dy * h2;
+            point = k == 0 ? 2 : k == 1 ? 1 : k == 2 ? 3 : k == 3 ? 4 : k == 4 ? 5 : k == 5 ? 6 : k == 6 ? 8 : 7;
+            dist = (k == 1 || k == 2 || k == 5 || k == 6) ? h2 : d; cnt = 8;
+        }
         else
         {
-            const int k = ((lane - 4) >> 2) + 1, m = (lane - 4) & 3;
-            px = ox + ((m & 1) ? q * k : -q * k);
-            py = (m & 2) ? (oy + d - q * k) : (oy - d + q * k);
+            // order: top, left, right, bottom, then k = 1..3: (xl,yt) (xr,yt) (xl,yb) (xr,yb)
+            const int q = d >> 2;
+            if (lane < 4) { px = ox + (lane == 1 ? -d : lane == 2 ? d : 0); py = oy + (lane == 0 ? -d : lane == 3 ? d : 0); }
+            else
+            {
+                const int k = ((lane - 4) >> 2) + 1, m = (lane - 4) & 3;
+                px = ox + ((m & 1) ? q * k : -q * k);
+                py = (m & 2) ? (oy + d - q * k) : (oy - d + q * k);
+            }
+            point = 0; dist = d; cnt = 16;
         }
-        int point = 0, dist = d;
-        bool valid = lane < 16 && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
-        saved = s.bcost;
-        int n = me_compact(valid, 16, px, py, point, dist);
-        int cost = me_eval_points(c, n, px, py, false);
+        const bool valid = lane < cnt && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
+        const int saved = s.bcost;
+        const int n = me_compact(valid, cnt, px, py, point, dist);
+        const int cost = me_eval_points(c, n, px, py, false);
         me_fold(s, n, cost, px, py, point, dist);
         if (s.bcost < saved) rounds = 0;
         else if (++rounds >= earlyExitIters) return;
@@ -789,62 +752,58 @@ __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, M
         bmx += c_square1[dir][0]; bmy += c_square1[dir][1];
     }
     else
-    {   // STAR (motion.cpp:1132-1240)
+    {   // STAR (motion.cpp:1132-1240), written as one loop so that the star pattern, the two-point refinement and
+        // the raster scan each have exactly one (inlined) evaluation site
         MeStar s; s.bx = bmx; s.by = bmy; s.bcost = bcost; s.point = 0; s.dist = 0;
-        me_star_pattern(c, s, 3, merange);
-        bool done = false;
-        if (s.dist == 1)
+        bool first = true;
+        for (;;)
         {
-            if (s.point)
+            me_star_pattern(c, s, first ? 3 : 32, merange);
+            const bool d1 = s.dist == 1;
+            bool improved = false;
+            if (d1 && s.point)
             {
+                // the two neighbours of the winning distance-1 point (motion.cpp:1139-1166 / :1215-1236), in order, strict '<'
                 const int saved = s.bcost;
-                const int x1 = s.bx + c_star_off[(s.point - 1) * 2][0], y1 = s.by + c_star_off[(s.point - 1) * 2][1];
-                const int x2 = s.bx + c_star_off[(s.point - 1) * 2 + 1][0], y2 = s.by + c_star_off[(s.point - 1) * 2 + 1][1];
-                if (ME_INRANGE(x1, y1)) { int cost = me_cost_fpel(c, x1, y1); if (cost < s.bcost) { s.bcost = cost; s.bx = x1; s.by = y1; } }
-                if (ME_INRANGE(x2, y2)) { int cost = me_cost_fpel(c, x2, y2); if (cost < s.bcost) { s.bcost = cost; s.bx = x2; s.by = y2; } }
-                if (s.bcost == saved) done = true;
+                const int o = (s.point - 1) * 2 + (c.lane & 1);
+                int px = s.bx + c_star_off[o][0], py = s.by + c_star_off[o][1], pt = s.point, ds = s.dist;
+                const bool valid = c.lane < 2 && ME_INRANGE(px, py);
+                const int n = me_compact(valid, 2, px, py, pt, ds);
+                const int cost = me_eval_points(c, n, px, py, false);
+                me_fold(s, n, cost, px, py, pt, ds);
+                improved = s.bcost != saved;
             }
-            else done = true;
-        }
-        if (!done)
-        {
-            const int RD = 5;
-            if (s.dist > RD)
+            if (first)
             {
-                // raster refinement (motion.cpp:1171-1201): grid of step 5 over the whole window, 32 points per burst.
-                // Every 4th column of a row (when it closes a full x4 group) adds mvcost(tmv << 3) as in the reference.
-                const int ncols = (c.maxx - c.minx) / RD + 1, nrows = (c.maxy - c.miny) / RD + 1;
-                const int total = ncols * nrows;
-                for (int base = 0; base < total; base += 32)
+                if (d1 && !improved) break;
+                const int RD = 5;
+                if (s.dist > RD)
                 {
-                    const int idx = min(base + c.lane, total - 1);
-                    const int rj = idx / ncols, ri = idx - rj * ncols;
-                    int px = c.minx + ri * RD, py = c.miny + rj * RD;
-                    const int n = min(32, total - base);
-                    const bool x8 = (ri & 3) == 3;
-                    int cost = me_eval_points(c, n, px, py, x8);
-                    const unsigned key = (unsigned)me_argmin(n, cost, c.lane);
-                    if ((int)(key >> 5) < s.bcost)
+                    // raster refinement (motion.cpp:1171-1201): grid of step 5 over the whole window, 32 points per burst.
+                    // Every 4th column of a row (when it closes a full x4 group) adds mvcost(tmv << 3) as in the reference.
+                    const int ncols = (c.maxx - c.minx) / RD + 1, nrows = (c.maxy - c.miny) / RD + 1;
+                    const int total = ncols * nrows;
+                    for (int base = 0; base < total; base += 32)
                     {
-                        s.bcost = (int)(key >> 5);
-                        s.bx = __shfl_sync(0xffffffffu, px, (int)(key & 31)); s.by = __shfl_sync(0xffffffffu, py, (int)(key & 31));
+                        const int idx = min(base + c.lane, total - 1);
+                        const int rj = idx / ncols, ri = idx - rj * ncols;
+                        int px = c.minx + ri * RD, py = c.miny + rj * RD;
+                        const int n = min(32, total - base);
+                        const bool x8 = (ri & 3) == 3;
+                        int cost = me_eval_points(c, n, px, py, x8);
+                        const unsigned key = (unsigned)me_argmin(n, cost, c.lane);
+                        if ((int)(key >> 5) < s.bcost)
+                        {
+                            s.bcost = (int)(key >> 5);
+                            s.bx = __shfl_sync(0xffffffffu, px, (int)(key & 31)); s.by = __shfl_sync(0xffffffffu, py, (int)(key & 31));
+                        }
                     }
                 }
+                first = false;
             }
-            while (s.dist > 0)
-            {
-                s.dist = 0; s.point = 0;
-                me_star_pattern(c, s, 32, merange);
-                if (s.dist == 1)
-                {
-                    if (!s.point) break;
-                    const int x1 = s.bx + c_star_off[(s.point - 1) * 2][0], y1 = s.by + c_star_off[(s.point - 1) * 2][1];
-                    const int x2 = s.bx + c_star_off[(s.point - 1) * 2 + 1][0], y2 = s.by + c_star_off[(s.point - 1) * 2 + 1][1];
-                    if (ME_INRANGE(x1, y1)) { int cost = me_cost_fpel(c, x1, y1); if (cost < s.bcost) { s.bcost = cost; s.bx = x1; s.by = y1; } }
-                    if (ME_INRANGE(x2, y2)) { int cost = me_cost_fpel(c, x2, y2); if (cost < s.bcost) { s.bcost = cost; s.bx = x2; s.by = y2; } }
-                    break;
-                }
-            }
+            else if (d1) break;
+            if (s.dist <= 0) break;
+            s.dist = 0; s.point = 0;
         }
         bmx = s.bx; bmy = s.by; bcost = s.bcost;
     }
@@ -934,13 +893,9 @@ __device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j,
     const int wpr = (c.w * (int)sizeof(P)) >> 2;            // words per row (>= 1: w >= 4)
     c.lgwpr = 31 - __clz(wpr);
     c.nw = wpr * c.h; c.lgnw = 31 - __clz(c.nw);
-    c.fw = 0;
-    if (c.pow2 && c.nw <= 32)
-    {   // every lane caches the fenc word of its slot (lane mod nw): groups of nw lanes evaluate different candidates
-        const int wd = lane & (c.nw - 1);
-        int row = wd >> c.lgwpr, col = wd & (wpr - 1);
-        c.fw = *(const uint32_t*)((const uint8_t*)c.fenc + ((size_t)row * fstride) * sizeof(P) + col * 4);
-    }
+    // widest lane segment (16 / 8 / 4 bytes) that both a PU row and the fenc row alignment allow
+    const unsigned fal = (unsigned)(uintptr_t)c.fenc | (unsigned)(fstride * (int)sizeof(P));
+    c.lgsegw = min(c.lgwpr, (fal & 15u) == 0 ? 2 : (fal & 7u) == 0 ? 1 : 0);
 }
 
 // Persistent warps with a dynamic job queue (jobs differ by up to 64x in work).  The search is split into

@@ -2,6 +2,7 @@
 // batched C-ABI entry points (include/x265_b200.h) and the per-call primitive table.
 #include "common.cuh"
 #include "pixelcmp.cuh"
+#include "pixelcmp_grid.cuh"
 #include "blockops.cuh"
 #include "interp.cuh"
 #include "transform.cuh"
@@ -105,6 +106,9 @@ int x265cu_me_phase_ms(x265cu_ctx* c, float* ms)
 // ---------------- batched API ----------------
 int x265cu_pixelcmp_batch(x265cu_ctx* c, int depth, int op, const void* A, const void* B, const x265cu_cmp_job* jobs, int n, uint64_t* out)
 { return launch_pixelcmp(c, depth, op, A, B, jobs, n, out); }
+int x265cu_pixelcmp_grid(x265cu_ctx* c, int depth, int op, const void* A, int64_t a_stride, const void* B, int64_t b_stride,
+                         int bw, int bh, int nbx, int nby, uint64_t* out)
+{ return launch_pixelcmp_grid(c, depth, op, A, a_stride, B, b_stride, bw, bh, nbx, nby, out); }
 
 int x265cu_blockop_batch(x265cu_ctx* c, int depth, int op, void* D, const void* A, const void* B, const x265cu_blk_job* jobs, int n)
 { return launch_blockop(c, depth, op, D, A, B, jobs, n); }

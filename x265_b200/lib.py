@@ -56,6 +56,7 @@ _PROTOS = {
     "x265cu_me_phase_ms": (I, [P, C.POINTER(C.c_float)]),
     "x265cu_get_primitive": (P, [I, C.c_char_p, I, I, I]),
     "x265cu_pixelcmp_batch": (I, [P, I, I, P, P, P, I, P]),
+    "x265cu_pixelcmp_grid": (I, [P, I, I, P, I64, P, I64, I, I, I, I, P]),
     "x265cu_blockop_batch": (I, [P, I, I, P, P, P, P, I]),
     "x265cu_interp_batch": (I, [P, I, I, P, P, P, I]),
     "x265cu_transform_batch": (I, [P, I, I, I, P, P, I, I64, I]),
@@ -172,6 +173,10 @@ class Lib:
     # ---- batched API (device buffers in, device buffers out) ----
     def pixelcmp_batch(self, depth, op, A, B, jobs_dev, n, out_dev):
         self.check(self.L.x265cu_pixelcmp_batch(self.ctx, depth, OPS_CMP[op], A.ptr, B.ptr, jobs_dev.ptr, n, out_dev.ptr))
+
+    def pixelcmp_grid(self, depth, op, a_ptr, a_stride, b_ptr, b_stride, bw, bh, nbx, nby, out_dev):
+        """a_ptr / b_ptr: device addresses of block (0,0) in each plane (ints); strides in pixels."""
+        self.check(self.L.x265cu_pixelcmp_grid(self.ctx, depth, OPS_CMP[op], a_ptr, a_stride, b_ptr, b_stride, bw, bh, nbx, nby, out_dev.ptr))
 
     def blockop_batch(self, depth, op, D, A, B, jobs_dev, n):
         self.check(self.L.x265cu_blockop_batch(self.ctx, depth, OPS_BLK[op], D.ptr, A.ptr if A else None, B.ptr if B else None, jobs_dev.ptr, n))
