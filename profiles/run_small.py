@@ -18,4 +18,4 @@ an.load_inputs(gen_luma(W, H, 4), make_field(W, H, 4))
 for _ in range(reps):
     an.run_resident(stages)
     lib.sync()
-    print("stage ms (me_stage, resid, intra, me_kernel):", an.stage_ms(), "jobs", an.njobs)
+    print("stage ms (me_stage, resid, intra, me_kernel):", an.stage_ms(), "jobs", an.njobs, "ME phases ms (pre, int, subpel):", ["%.2f" % v for v in lib.me_phase_ms()])

@@ -180,12 +180,12 @@ __device__ __forceinline__ int me_eval_points(const MeCtx<P>& c, int n, int px, 
 // tile distortions kept out of line: the job loop is instruction-cache bound, one copy of the unrolled
 // Hadamard instead of six is worth more than the call overhead (measured: profiles/me_r1 notes)
 template <typename PA, typename PB>
-__device__ __noinline__ int me_tile8x4(const PA* pf, int sf, const PB* pp, int sp)
+__device__ __forceinline__ int me_tile8x4(const PA* pf, int sf, const PB* pp, int sp)
 {
     return (had4x4_abs(pf, sf, pp, sp) + had4x4_abs(pf + 4, sf, pp + 4, sp)) >> 1;
 }
 template <typename PA, typename PB>
-__device__ __noinline__ int me_tile4x4(const PA* pf, int sf, const PB* pp, int sp)
+__device__ __forceinline__ int me_tile4x4(const PA* pf, int sf, const PB* pp, int sp)
 {
     return had4x4_abs(pf, sf, pp, sp) >> 1;
 }
@@ -237,7 +237,7 @@ __device__ __forceinline__ int me_hsum8(const P* __restrict__ s, const int16_t* 
 
 // cost of a band of prediction held in c.sm->pred (stride 64) against fenc rows [y0, y0+rows)
 template <typename P>
-__device__ __noinline__ int me_band_cost(const MeCtx<P>& c, int y0, int rows, bool satd)
+__device__ __forceinline__ int me_band_cost(const MeCtx<P>& c, int y0, int rows, bool satd)
 {
     const uint16_t* pr = c.sm->pred;
     const P* f = c.fenc + (size_t)y0 * c.fstride;
@@ -283,7 +283,7 @@ __device__ __noinline__ int me_band_cost(const MeCtx<P>& c, int y0, int rows, bo
 
 // subpelCompare (motion.cpp:1571-1598) for ONE candidate: luma_hpp / luma_vpp / luma_hvpp, then cmp.
 template <typename P>
-__device__ __noinline__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd)
+__device__ __forceinline__ int me_subpel_compare_t(const MeCtx<P>& c, int qx, int qy, bool satd)
 {
     constexpr int DEPTH = PixTraits<P>::depth;
     const P* r = c.ref[0] + (qx >> 2) + (ptrdiff_t)(qy >> 2) * c.rstride;
@@ -350,7 +350,7 @@ __device__ __noinline__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy,
 // (candidate, pixel).  Lane i (< n <= 4) owns candidate i (qx, qy); returns its distortion in lane i.
 // Per candidate the arithmetic is exactly me_subpel_compare's.
 template <typename P>
-__device__ __noinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+__device__ __forceinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
 {
     constexpr int DEPTH = PixTraits<P>::depth;
     const int lgh = 31 - __clz(c.h);
@@ -362,10 +362,11 @@ __device__ __noinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int 
     int cqx[4], cqy[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) { cqx[k] = __shfl_sync(0xffffffffu, qx, k); cqy[k] = __shfl_sync(0xffffffffu, qy, k); }
-#pragma unroll
+#pragma unroll 1
     for (int cand = 0; cand < 4; cand++)
     {
-        const int mqx = cqx[cand], mqy = cqy[cand];
+        const int mqx = cand == 0 ? cqx[0] : cand == 1 ? cqx[1] : cand == 2 ? cqx[2] : cqx[3];
+        const int mqy = cand == 0 ? cqy[0] : cand == 1 ? cqy[1] : cand == 2 ? cqy[2] : cqy[3];
         const int xf = mqx & 3, yf = mqy & 3;
         if (cand < n && xf && yf)
         {
@@ -460,11 +461,23 @@ __device__ __noinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int 
 }
 
 // distortion of up to 8 sub-pel candidates, lane i (< n) owns candidate i; result in lane i
+// out-of-line copy for the cold multi-site users (pre-checks, lowres band cost)
 template <typename P>
-__device__ __noinline__ int me_subpel_batch(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+__device__ __noinline__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd) { return me_subpel_compare_t(c, qx, qy, satd); }
+template <typename P>
+__device__ __noinline__ int me_band_cost_ni(const MeCtx<P>& c, int y0, int rows, bool satd) { return me_band_cost(c, y0, rows, satd); }
+
+// PU classes of the sub-pel stage: 0 = small (pow2, w and h <= 16: four candidates at a time through
+// me_subpel_multi_small), 1 = everything else (one candidate at a time, banded).  CLS = -1 compiles both.
+template <typename P>
+__device__ __forceinline__ int me_subpel_class(const MeCtx<P>& c) { return (c.pow2 && c.w <= 16 && c.h <= 16) ? 0 : 1; }
+
+// distortion of up to 8 sub-pel candidates, lane i (< n) owns candidate i; result in lane i
+template <typename P, int CLS>
+__device__ __forceinline__ int me_subpel_batch(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
 {
     int out = 0;
-    if (c.pow2 && c.w <= 16 && c.h <= 16)
+    if (CLS == 0 || (CLS < 0 && me_subpel_class(c) == 0))
     {
         for (int base = 0; base < n; base += 4)
         {
@@ -480,7 +493,7 @@ __device__ __noinline__ int me_subpel_batch(const MeCtx<P>& c, int n, int qx, in
         for (int k = 0; k < n; k++)
         {
             const int kqx = __shfl_sync(0xffffffffu, qx, k), kqy = __shfl_sync(0xffffffffu, qy, k);
-            int v = me_subpel_compare(c, kqx, kqy, satd);
+            int v = me_subpel_compare_t(c, kqx, kqy, satd);
             if (c.lane == k) out = v;
         }
     }
@@ -505,7 +518,7 @@ __device__ __noinline__ int me_lowres_cost(const MeCtx<P>& c, int qx, int qy, bo
             c.sm->pred[y * 64 + x] = (uint16_t)(((int)a[(ptrdiff_t)y * c.rstride + x] + (int)b[(ptrdiff_t)y * c.rstride + x] + 1) >> 1);
         }
         __syncwarp();
-        return warp_sum(me_band_cost(c, 0, c.h, satd));
+        return warp_sum(me_band_cost_ni(c, 0, c.h, satd));
     }
     int hp = (qy & 2) | ((qx & 2) >> 1);
     const P* r = c.ref[hp] + (qx >> 2) + (ptrdiff_t)(qy >> 2) * c.rstride;
@@ -611,27 +624,6 @@ __constant__ int8_t c_star_off[16][2] = { {-1,0},{0,-1}, {-1,-1},{1,-1}, {-1,0},
                                           {1,-1},{1,1}, {-1,0},{0,1}, {-1,1},{1,1}, {1,0},{0,1} };
 // motion.cpp:48-58 {hpel_iters, hpel_dirs, qpel_iters, qpel_dirs, hpel_satd}
 __constant__ int8_t c_workload[8][5] = { {1,4,0,4,0}, {1,4,1,4,0}, {1,4,1,4,1}, {2,4,1,4,1}, {2,4,2,4,1}, {1,8,1,8,1}, {2,8,1,8,1}, {2,8,2,8,1} };
-
-// one sub-pel refinement round (motion.cpp:1506-1523 / :1537-1553): candidates bmv + square1[1..dirs]*step,
-// folded in order with strict '<'; returns the winning direction (0 = none)
-template <typename P>
-__device__ __noinline__ int me_subpel_round(const MeCtx<P>& c, int bx, int by, int dirs, int step, bool satd, int qminy, int qmaxy, int& bcost)
-{
-    const int lane = c.lane;
-    const int i1 = min(lane + 1, 8);
-    int qx = bx + c_square1[i1][0] * step, qy = by + c_square1[i1][1] * step, dir = lane + 1, dummy = 0;
-    bool valid = lane < dirs && !((qy < qminy) | (qy > qmaxy));
-    int n = me_compact(valid, dirs, qx, qy, dir, dummy);
-    int cost = me_subpel_batch(c, n, qx, qy, satd);
-    if (lane < n) cost += me_mvcost(c, qx, qy);
-    int bdir = 0;
-    if (n > 0)
-    {
-        const unsigned key = (unsigned)me_argmin(n, cost, lane);
-        if ((int)(key >> 5) < bcost) { bcost = (int)(key >> 5); bdir = __shfl_sync(0xffffffffu, dir, (int)(key & 31)); }
-    }
-    return bdir;
-}
 
 struct MeState { int bmx, bmy, bcost, bprecost, bestprex, bestprey; };
 
@@ -812,7 +804,7 @@ __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, M
 }
 
 // phase 3 (motion.cpp:1440-1569): pick pre-check vs search winner, sub-pel refinement
-template <typename P>
+template <typename P, int CLS>
 __device__ __forceinline__ void me_phase3(MeCtx<P>& c, const x265cu_me_job& j, const MeState& st, int32_t* __restrict__ out)
 {
     const int qminy = c.miny * 4, qmaxy = c.maxy * 4;
@@ -848,19 +840,33 @@ __device__ __forceinline__ void me_phase3(MeCtx<P>& c, const x265cu_me_job& j, c
     }
     else
     {
-        bool hsatd = false;
-        if (wl[4]) { bcost = me_subpel_compare(c, bx, by, true) + me_mvcost(c, bx, by); hsatd = true; }
-        for (int it = 0; it < wl[0]; it++)
+        // motion.cpp:1496-1558 as one loop with a single (inlined) evaluation site: stage 0 = SATD at the start point
+        // (when the half-pel rounds use SATD), stage 1 = half-pel rounds, stage 2 = SATD at the half-pel winner
+        // (otherwise), stage 3 = quarter-pel rounds.  A "centre" step is a burst of one candidate.
+        const bool hsatd = wl[4] != 0;
+        int stage = hsatd ? 0 : 1, it = 0;
+        for (;;)
         {
-            int bdir = me_subpel_round(c, bx, by, wl[1], 2, hsatd, qminy, qmaxy, bcost);
-            if (bdir) { bx += c_square1[bdir][0] * 2; by += c_square1[bdir][1] * 2; }
-            else break;
-        }
-        if (!wl[4]) bcost = me_subpel_compare(c, bx, by, true) + me_mvcost(c, bx, by);
-        for (int it = 0; it < wl[2]; it++)
-        {
-            int bdir = me_subpel_round(c, bx, by, wl[3], 1, true, qminy, qmaxy, bcost);
-            if (bdir) { bx += c_square1[bdir][0]; by += c_square1[bdir][1]; }
+            if (stage == 1 && it >= wl[0]) { stage = hsatd ? 3 : 2; it = 0; }
+            if (stage == 3 && it >= wl[2]) break;
+            const bool centre = (stage & 1) == 0;
+            const int dirs = centre ? 1 : (stage == 1 ? wl[1] : wl[3]), step = stage == 1 ? 2 : 1;
+            const bool satd = stage == 1 ? hsatd : true;
+            const int i1 = centre ? 0 : min(c.lane + 1, 8);
+            int qx = bx + c_square1[i1][0] * step, qy = by + c_square1[i1][1] * step, dir = i1, dummy = 0;
+            const bool valid = c.lane < dirs && (centre || !((qy < qminy) | (qy > qmaxy)));
+            const int n = me_compact(valid, dirs, qx, qy, dir, dummy);
+            int cost = me_subpel_batch<P, CLS>(c, n, qx, qy, satd);
+            if (c.lane < n) cost += me_mvcost(c, qx, qy);
+            if (centre) { bcost = __shfl_sync(0xffffffffu, cost, 0); stage++; continue; }
+            int bdir = 0;
+            if (n > 0)
+            {
+                const unsigned key = (unsigned)me_argmin(n, cost, c.lane);
+                if ((int)(key >> 5) < bcost) { bcost = (int)(key >> 5); bdir = __shfl_sync(0xffffffffu, dir, (int)(key & 31)); }
+            }
+            if (bdir) { bx += c_square1[bdir][0] * step; by += c_square1[bdir][1] * step; it++; }
+            else if (stage == 1) { stage = hsatd ? 3 : 2; it = 0; }
             else break;
         }
     }
@@ -874,7 +880,7 @@ __device__ __forceinline__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, 
     MeState st;
     me_phase1<P>(c, j, st);
     me_phase2<P>(c, j, st);
-    me_phase3<P>(c, j, st, out);
+    me_phase3<P, -1>(c, j, st, out);
 }
 
 // Job setup shared by all ME kernels
@@ -899,9 +905,11 @@ __device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j,
 }
 
 // Persistent warps with a dynamic job queue (jobs differ by up to 64x in work).  The search is split into
-// three launches -- pre-checks, integer search, sub-pel refinement -- because the fused body (12.4 K SASS
-// instructions, ~200 KB) thrashes the instruction cache: ncu showed 80 % of the stall samples in
-// `no_instructions` at a 46 % i-cache hit rate.  PHASE 0 = all three fused (used by small batches / tests).
+// launches -- 1 pre-checks, 2 integer search, 3 sub-pel refinement of the small PUs, 4 sub-pel refinement of the
+// others -- because the fused body (12.4 K SASS instructions, ~200 KB) thrashes the instruction cache: ncu
+// showed 80 % of the stall samples in `no_instructions` at a 46 % i-cache hit rate, and the un-split sub-pel
+// kernel (8.8 K instructions, both PU classes resident on every SM) still sat at 64 %.  PHASE 0 = all fused
+// (the lookahead kernel's per-CU call).
 #ifndef ME_MIN_BLOCKS
 #define ME_MIN_BLOCKS 3
 #endif
@@ -925,6 +933,7 @@ __global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : ME_MIN_BLOCKS
         const x265cu_me_job j = jobs[jid];
         MeCtx<P> c;
         me_make_ctx<P>(c, j, fenc, fstride, refs, rstride, lowres, mvcost, lane, sm);
+        if (PHASE >= 3 && me_subpel_class(c) != PHASE - 3) continue;          // the other sub-pel launch owns this job
         if (PHASE == 0) me_run_job<P>(c, j, out + (size_t)jid * 4);
         else
         {
@@ -932,7 +941,7 @@ __global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : ME_MIN_BLOCKS
             if (PHASE != 1) st = state[jid];
             if (PHASE == 1) { me_phase1<P>(c, j, st); if (lane == 0) state[jid] = st; }
             if (PHASE == 2) { me_phase2<P>(c, j, st); if (lane == 0) state[jid] = st; }
-            if (PHASE == 3) me_phase3<P>(c, j, st, out + (size_t)jid * 4);
+            if (PHASE >= 3) me_phase3<P, PHASE - 3>(c, j, st, out + (size_t)jid * 4);
         }
         __syncwarp();
     }
@@ -956,7 +965,7 @@ static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, 
                      const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, int* counter_dev)
 {
     if (n <= 0) return 0;
-    CU_CHECK(cudaMemsetAsync(counter_dev, 0, 4 * sizeof(int), ctx->stream));
+    CU_CHECK(cudaMemsetAsync(counter_dev, 0, 8 * sizeof(int), ctx->stream));
     // per-job state between the phases (24 B per job), grown on demand and kept by the context
     const size_t need = (size_t)n * sizeof(MeState);
     if (ctx->me_state_bytes < need)
@@ -975,6 +984,7 @@ static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, 
         rc |= launch_me_phase<uint8_t, 2>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
         CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
         rc |= launch_me_phase<uint8_t, 3>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
+        rc |= launch_me_phase<uint8_t, 4>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 3);
     }
     else
     {
@@ -983,6 +993,7 @@ static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, 
         rc |= launch_me_phase<uint16_t, 2>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
         CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
         rc |= launch_me_phase<uint16_t, 3>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
+        rc |= launch_me_phase<uint16_t, 4>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 3);
     }
     CU_CHECK(cudaEventRecord(ctx->me_ev[3], ctx->stream));
     return rc;
