@@ -568,52 +568,77 @@ __device__ __forceinline__ void me_fold(MeStar& s, int n, int cost, int px, int 
 template <typename P>
 __device__ __forceinline__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters, int merange)
 {
-    // One loop over the distance levels with a SINGLE evaluation site (the SAD core is inlined, so every extra
-    // site is another copy in the instruction cache): level 0 = distance 1 (4 points), levels 1..3 = distances
-    // 2, 4, 8 (8 points), levels 4.. = distances 16, 32, ... <= merange (16 points).
+    // Levels: 0 = distance 1 (4 points), 1..3 = distances 2, 4, 8 (8 points), 4.. = distances 16, 32, ... <= merange
+    // (16 points).  Every level's points depend only on the start position, so levels can be evaluated ahead of the
+    // early-exit decision without changing it: for small PUs (<= 64 words, where the per-burst bookkeeping costs more
+    // than the SADs) levels 0-3 form ONE burst of 28 candidates and the far levels go two per burst; the decisions
+    // are then replayed level by level with a masked arg-min.  Large PUs keep one level per burst (no wasted SADs).
+    // One loop, one evaluation site (the SAD core is inlined).
     const int ox = s.bx, oy = s.by, lane = c.lane;
-    int rounds = 0;
-    for (int lvl = 0; ; lvl++)
+    const bool spec = c.pow2 && c.nw <= 64;
+    int rounds = 0, lvl0 = 0;
+    for (;;)
     {
-        const int d = lvl < 4 ? (1 << lvl) : (16 << (lvl - 4));
-        if (lvl >= 4 && d > merange) break;
-        int px, py, point, dist, cnt;
-        if (lvl == 0)
+        const int lvl1 = !spec ? lvl0 + 1 : (lvl0 == 0 ? 4 : lvl0 + 2);
+        int mylvl, k;
+        if (!spec)          { mylvl = lvl0; k = lane; }
+        else if (lvl0 == 0) { mylvl = lane < 4 ? 0 : 1 + ((lane - 4) >> 3); k = lane < 4 ? lane : (lane - 4) & 7; }
+        else                { mylvl = lvl0 + (lane >> 4); k = lane & 15; }
+        const int d = mylvl < 4 ? (1 << mylvl) : (16 << (mylvl - 4));
+        const int cnt = mylvl == 0 ? 4 : mylvl < 4 ? 8 : 16;
+        int px, py, point, dist;
+        if (mylvl == 0)
         {
             // dist 1: top(2) left(4) right(5) bottom(7)
-            px = ox + (lane == 1 ? -1 : lane == 2 ? 1 : 0); py = oy + (lane == 0 ? -1 : lane == 3 ? 1 : 0);
-            point = lane == 0 ? 2 : lane == 1 ? 4 : lane == 2 ? 5 : 7; dist = 1; cnt = 4;
+            px = ox + (k == 1 ? -1 : k == 2 ? 1 : 0); py = oy + (k == 0 ? -1 : k == 3 ? 1 : 0);
+            point = k == 0 ? 2 : k == 1 ? 4 : k == 2 ? 5 : 7; dist = 1;
         }
-        else if (lvl < 4)
+        else if (mylvl < 4)
         {
             // order: 2(top) 1 3 4(left) 5(right) 6 8 7(bottom); half-distance points need both their checks
-            const int h2 = d >> 1, k = lane & 7;
-            const int dx = k == 0 ? 0 : k == 1 ? -1 : k == 2 ? 1 : k == 3 ? -2 : k == 4 ? 2 : k == 5 ? -1 : k == 6 ? 1 : 0;
-            const int dy = k == 0 ? -2 : k < 3 ? -1 : k < 5 ? 0 : k < 7 ? 1 : 2;
+            const int h2 = d >> 1, kk = k & 7;
+            const int dx = kk == 0 ? 0 : kk == 1 ? -1 : kk == 2 ? 1 : kk == 3 ? -2 : kk == 4 ? 2 : kk == 5 ? -1 : kk == 6 ? 1 : 0;
+            const int dy = kk == 0 ? -2 : kk < 3 ? -1 : kk < 5 ? 0 : kk < 7 ? 1 : 2;
             px = ox + dx * h2; py = oy + dy * h2;
-            point = k == 0 ? 2 : k == 1 ? 1 : k == 2 ? 3 : k == 3 ? 4 : k == 4 ? 5 : k == 5 ? 6 : k == 6 ? 8 : 7;
-            dist = (k == 1 || k == 2 || k == 5 || k == 6) ? h2 : d; cnt = 8;
+            point = kk == 0 ? 2 : kk == 1 ? 1 : kk == 2 ? 3 : kk == 3 ? 4 : kk == 4 ? 5 : kk == 5 ? 6 : kk == 6 ? 8 : 7;
+            dist = (kk == 1 || kk == 2 || kk == 5 || kk == 6) ? h2 : d;
         }
         else
         {
-            // order: top, left, right, bottom, then k = 1..3: (xl,yt) (xr,yt) (xl,yb) (xr,yb)
-            const int q = d >> 2;
-            if (lane < 4) { px = ox + (lane == 1 ? -d : lane == 2 ? d : 0); py = oy + (lane == 0 ? -d : lane == 3 ? d : 0); }
+            // order: top, left, right, bottom, then j = 1..3: (xl,yt) (xr,yt) (xl,yb) (xr,yb)
+            const int q = d >> 2, kk = k & 15;
+            if (kk < 4) { px = ox + (kk == 1 ? -d : kk == 2 ? d : 0); py = oy + (kk == 0 ? -d : kk == 3 ? d : 0); }
             else
             {
-                const int k = ((lane - 4) >> 2) + 1, m = (lane - 4) & 3;
-                px = ox + ((m & 1) ? q * k : -q * k);
-                py = (m & 2) ? (oy + d - q * k) : (oy - d + q * k);
+                const int jj = ((kk - 4) >> 2) + 1, m = (kk - 4) & 3;
+                px = ox + ((m & 1) ? q * jj : -q * jj);
+                py = (m & 2) ? (oy + d - q * jj) : (oy - d + q * jj);
             }
-            point = 0; dist = d; cnt = 16;
+            point = 0; dist = d;
         }
-        const bool valid = lane < cnt && px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
-        const int saved = s.bcost;
-        const int n = me_compact(valid, cnt, px, py, point, dist);
+        const bool valid = mylvl < lvl1 && k < cnt && !(mylvl >= 4 && d > merange) &&
+                           px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
+        if (!valid) { px = ox; py = oy; }                        // idle lanes evaluate the (in-range) centre and are masked out
+        const int n = spec ? (lvl0 == 0 ? 28 : 32) : (lvl0 == 0 ? 4 : lvl0 < 4 ? 8 : 16);
         const int cost = me_eval_points(c, n, px, py, false);
-        me_fold(s, n, cost, px, py, point, dist);
-        if (s.bcost < saved) rounds = 0;
-        else if (++rounds >= earlyExitIters) return;
+        for (int l = lvl0; l < lvl1; l++)
+        {
+            if (l >= 4 && (16 << (l - 4)) > merange) return;
+            const int saved = s.bcost;
+            const unsigned key = (valid && mylvl == l) ? (((unsigned)cost << 5) | (unsigned)lane) : 0xffffffffu;
+            const unsigned m = __reduce_min_sync(0xffffffffu, key);
+            if (m != 0xffffffffu && (int)(m >> 5) < s.bcost)
+            {
+                const int src = (int)(m & 31);
+                s.bcost = (int)(m >> 5);
+                s.bx = __shfl_sync(0xffffffffu, px, src); s.by = __shfl_sync(0xffffffffu, py, src);
+                s.point = __shfl_sync(0xffffffffu, point, src); s.dist = __shfl_sync(0xffffffffu, dist, src);
+            }
+            if (s.bcost < saved) rounds = 0;
+            else if (++rounds >= earlyExitIters) return;
+        }
+        lvl0 = lvl1;
+        if (lvl0 >= 4 && (16 << (lvl0 - 4)) > merange) return;
     }
 }
 
@@ -631,7 +656,7 @@ struct MeState { int bmx, bmy, bcost, bprecost, bestprex, bestprey; };
 #define ME_INRANGE(x, y) ((x) >= c.minx && (x) <= c.maxx && (y) >= c.miny && (y) <= c.maxy)
 
 // phase 1 (motion.cpp:771-814): cost at the clipped MVP, at its full-pel rounding, at MV 0 and at the qpel candidates
-template <typename P>
+template <typename P, int CLS>
 __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, MeState& st)
 {
 
@@ -640,22 +665,69 @@ __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, M
     // clipped() = min with max first, then max with min (mv.h:100-105)
     const int pmvx = max(min(c.mvpx, qmaxx), qminx), pmvy = max(min(c.mvpy, qmaxy), qminy);
     int bestprex = pmvx, bestprey = pmvy;
-    int bprecost = me_qpel_cost(c, pmvx, pmvy, false);
-    int bmx = (pmvx + 2) >> 2, bmy = (pmvy + 2) >> 2;
-    int bcost = bprecost;
-    if ((pmvx & 3) | (pmvy & 3)) bcost = me_cost_fpel(c, bmx, bmy);
-    if (pmvx | pmvy)
+    int bprecost, bmx = (pmvx + 2) >> 2, bmy = (pmvy + 2) >> 2, bcost;
+    if (c.lowres)
     {
-        int cost = me_sad_direct(c, c.ref[0]) + me_mvcost(c, 0, 0);
-        if (cost < bcost) { bcost = cost; bmx = 0; bmy = max(min(0, c.maxy), c.miny); }
-    }
-    for (int i = 0; i < j.numCand; i++)
-    {
-        int mx = max(min((int)j.mvc[2 * i], qmaxx), qminx), my = max(min((int)j.mvc[2 * i + 1], qmaxy), qminy);
-        if ((mx | my) && !(mx == pmvx && my == pmvy) && !(mx == bestprex && my == bestprey))
+        bprecost = me_lowres_cost(c, pmvx, pmvy, false);
+        bcost = bprecost;
+        if ((pmvx & 3) | (pmvy & 3)) bcost = me_cost_fpel(c, bmx, bmy);
+        if (pmvx | pmvy)
         {
-            int cost = me_subpel_compare(c, mx, my, false) + me_mvcost(c, mx, my);
-            if (cost < bprecost) { bprecost = cost; bestprex = mx; bestprey = my; }
+            int cost = me_sad_direct(c, c.ref[0]) + me_mvcost(c, 0, 0);
+            if (cost < bcost) { bcost = cost; bmx = 0; bmy = max(min(0, c.maxy), c.miny); }
+        }
+        for (int i = 0; i < j.numCand; i++)
+        {
+            int mx = max(min((int)j.mvc[2 * i], qmaxx), qminx), my = max(min((int)j.mvc[2 * i + 1], qmaxy), qminy);
+            if ((mx | my) && !(mx == pmvx && my == pmvy) && !(mx == bestprex && my == bestprey))
+            {
+                int cost = me_subpel_compare(c, mx, my, false) + me_mvcost(c, mx, my);
+                if (cost < bprecost) { bprecost = cost; bestprex = mx; bestprey = my; }
+            }
+        }
+    }
+    else
+    {
+        // All the pre-checks are SADs at independent positions: ONE burst.  Lane 0 = clipped MVP (qpel), lane 1 = its
+        // full-pel rounding (only when the MVP is fractional), lane 2 = MV 0 (only when the MVP is not 0), lanes 3.. =
+        // the qpel candidates.  The reference skips a candidate equal to the best so far; evaluating it is harmless (its
+        // cost equals that best and '<' is strict), so the candidate fold is one arg-min with ties to the earliest.
+        const int lane = c.lane, ci = min(max(lane - 3, 0), 3);
+        int qx, qy, tag = lane, dummy = 0;
+        bool valid;
+        if (lane == 0)      { qx = pmvx; qy = pmvy; valid = true; }
+        else if (lane == 1) { qx = bmx * 4; qy = bmy * 4; valid = ((pmvx & 3) | (pmvy & 3)) != 0; }
+        else if (lane == 2) { qx = 0; qy = 0; valid = (pmvx | pmvy) != 0; }
+        else
+        {
+            qx = max(min((int)j.mvc[2 * ci], qmaxx), qminx); qy = max(min((int)j.mvc[2 * ci + 1], qmaxy), qminy);
+            valid = lane - 3 < j.numCand && (qx | qy) && !(qx == pmvx && qy == pmvy);
+        }
+        const int cnt = 3 + j.numCand;
+        valid = valid && lane < cnt;
+        const int n = me_compact(valid, cnt, qx, qy, tag, dummy);
+        int cost = me_subpel_batch<P, CLS>(c, n, qx, qy, false);
+        const bool mine = lane < n;
+        const unsigned m0 = __ballot_sync(0xffffffffu, mine && tag == 0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, mine && tag == 1);
+        const unsigned m2 = __ballot_sync(0xffffffffu, mine && tag == 2);
+        bprecost = __shfl_sync(0xffffffffu, cost, __ffs(m0) - 1);
+        bcost = bprecost;
+        const int mvc1 = me_mvcost(c, bmx * 4, bmy * 4), mvc0 = me_mvcost(c, 0, 0);
+        if (m1) bcost = __shfl_sync(0xffffffffu, cost, __ffs(m1) - 1) + mvc1;
+        if (m2)
+        {
+            const int cz = __shfl_sync(0xffffffffu, cost, __ffs(m2) - 1) + mvc0;
+            if (cz < bcost) { bcost = cz; bmx = 0; bmy = max(min(0, c.maxy), c.miny); }
+        }
+        const bool isCand = mine && tag >= 3;
+        if (isCand) cost += me_mvcost(c, qx, qy);
+        const unsigned key = isCand ? (((unsigned)cost << 5) | (unsigned)lane) : 0xffffffffu;
+        const unsigned mk = __reduce_min_sync(0xffffffffu, key);
+        if (mk != 0xffffffffu && (int)(mk >> 5) < bprecost)
+        {
+            bprecost = (int)(mk >> 5);
+            bestprex = __shfl_sync(0xffffffffu, qx, (int)(mk & 31)); bestprey = __shfl_sync(0xffffffffu, qy, (int)(mk & 31));
         }
     }
 
@@ -878,7 +950,7 @@ template <typename P>
 __device__ __forceinline__ void me_run_job(MeCtx<P>& c, const x265cu_me_job& j, int32_t* __restrict__ out)
 {
     MeState st;
-    me_phase1<P>(c, j, st);
+    me_phase1<P, -1>(c, j, st);
     me_phase2<P>(c, j, st);
     me_phase3<P, -1>(c, j, st, out);
 }
@@ -905,8 +977,8 @@ __device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j,
 }
 
 // Persistent warps with a dynamic job queue (jobs differ by up to 64x in work).  The search is split into
-// launches -- 1 pre-checks, 2 integer search, 3 sub-pel refinement of the small PUs, 4 sub-pel refinement of the
-// others -- because the fused body (12.4 K SASS instructions, ~200 KB) thrashes the instruction cache: ncu
+// launches -- pre-checks (small PUs, other PUs), integer search, sub-pel refinement (small PUs, other PUs) --
+// because the fused body (12.4 K SASS instructions, ~200 KB) thrashes the instruction cache: ncu
 // showed 80 % of the stall samples in `no_instructions` at a 46 % i-cache hit rate, and the un-split sub-pel
 // kernel (8.8 K instructions, both PU classes resident on every SM) still sat at 64 %.  PHASE 0 = all fused
 // (the lookahead kernel's per-CU call).
@@ -916,7 +988,7 @@ __device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j,
 #ifndef ME_P2_BLOCKS
 #define ME_P2_BLOCKS 4
 #endif
-template <typename P, int PHASE>
+template <typename P, int PHASE, int CLS>
 __global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : ME_MIN_BLOCKS) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
                                                            const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
                                                            int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter)
@@ -933,21 +1005,21 @@ __global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : ME_MIN_BLOCKS
         const x265cu_me_job j = jobs[jid];
         MeCtx<P> c;
         me_make_ctx<P>(c, j, fenc, fstride, refs, rstride, lowres, mvcost, lane, sm);
-        if (PHASE >= 3 && me_subpel_class(c) != PHASE - 3) continue;          // the other sub-pel launch owns this job
+        if (CLS >= 0 && me_subpel_class(c) != CLS) continue;                   // the sibling launch owns this job
         if (PHASE == 0) me_run_job<P>(c, j, out + (size_t)jid * 4);
         else
         {
             MeState st;
             if (PHASE != 1) st = state[jid];
-            if (PHASE == 1) { me_phase1<P>(c, j, st); if (lane == 0) state[jid] = st; }
+            if (PHASE == 1) { me_phase1<P, CLS>(c, j, st); if (lane == 0) state[jid] = st; }
             if (PHASE == 2) { me_phase2<P>(c, j, st); if (lane == 0) state[jid] = st; }
-            if (PHASE >= 3) me_phase3<P, PHASE - 3>(c, j, st, out + (size_t)jid * 4);
+            if (PHASE == 3) me_phase3<P, CLS>(c, j, st, out + (size_t)jid * 4);
         }
         __syncwarp();
     }
 }
 
-template <typename P, int PHASE>
+template <typename P, int PHASE, int CLS>
 static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
                            const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter)
 {
@@ -956,9 +1028,24 @@ static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const
     int blocks = ctx->sm_count * (PHASE == 2 ? ME_P2_BLOCKS : ME_MIN_BLOCKS);
     int need = (n + warps - 1) / warps;
     if (blocks > need) blocks = need;
-    k_me<P, PHASE><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, lowres, mvcost, jobs, n, out, state, counter);
+    k_me<P, PHASE, CLS><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, lowres, mvcost, jobs, n, out, state, counter);
     CU_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+template <typename P>
+static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
+                       const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* st, int* counter_dev)
+{
+    int rc = 0;
+    rc |= launch_me_phase<P, 1, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
+    rc |= launch_me_phase<P, 1, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
+    CU_CHECK(cudaEventRecord(ctx->me_ev[1], ctx->stream));
+    rc |= launch_me_phase<P, 2, -1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
+    CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
+    rc |= launch_me_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 3);
+    rc |= launch_me_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 4);
+    return rc;
 }
 
 static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
@@ -975,26 +1062,9 @@ static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, 
         ctx->me_state_bytes = need;
     }
     MeState* st = (MeState*)ctx->d_me_state;
-    int rc = 0;
     CU_CHECK(cudaEventRecord(ctx->me_ev[0], ctx->stream));
-    if (depth == 8)
-    {
-        rc |= launch_me_phase<uint8_t, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
-        CU_CHECK(cudaEventRecord(ctx->me_ev[1], ctx->stream));
-        rc |= launch_me_phase<uint8_t, 2>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
-        CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
-        rc |= launch_me_phase<uint8_t, 3>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
-        rc |= launch_me_phase<uint8_t, 4>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 3);
-    }
-    else
-    {
-        rc |= launch_me_phase<uint16_t, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
-        CU_CHECK(cudaEventRecord(ctx->me_ev[1], ctx->stream));
-        rc |= launch_me_phase<uint16_t, 2>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
-        CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
-        rc |= launch_me_phase<uint16_t, 3>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
-        rc |= launch_me_phase<uint16_t, 4>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 3);
-    }
+    const int rc = depth == 8 ? launch_me_t<uint8_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev)
+                              : launch_me_t<uint16_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev);
     CU_CHECK(cudaEventRecord(ctx->me_ev[3], ctx->stream));
     return rc;
 }
