@@ -273,12 +273,20 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = peaks()
         es = 1
         plane = W * H * es
-        # dominant kernel: k_me<P,2>, the integer-search launch of the three motion-estimation launches.
+        # dominant kernel: k_me<P,2,-1>, the integer-search launch of the five motion-estimation launches.
         # Algorithmic (compulsory) bytes per launch: source plane + each reference plane
         # read once + per job the 40 B job record and the 24 B phase state read and written.
         me_bytes = plane * (1 + NREFS) + an.njobs * (40 + 24 + 24)
         me_ms = phases[1]
         achieved = me_bytes / (me_ms / 1000.0) / 1e9
+        # DRAM bytes of that kernel from the committed ncu capture of this same command (profiles/launches_r1.md)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "me_r1_traffic.json")))
+            if "3840x2160" in tr.get("config", ""):
+                traffic = float(tr["traffic_bytes_per_launch"])
+        except Exception:
+            pass
         cfg = workload_config()
         cfg["pu_jobs_per_frame"] = an.njobs
         sizes = {"resid_bytes": plane * 2 + an.ncoef * 2 + 4 * plane, "intra_bytes": plane + an.ncu * 36 * 4}
@@ -290,10 +298,10 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "CTUs/s", "ms_per_step": t_e2e / args.steps,
                     "h2d_bytes_per_step": int(an.h2d_bytes(field)), "d2h_bytes_per_step": int(an.d2h_bytes())},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_me<P,2> (integer search phase of the batched motionEstimate, one warp per PU x ref)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"kernel": "k_me<P,2,-1> (integer search phase of the batched motionEstimate, one warp per PU x ref)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(me_bytes), "kernel_ms": float(me_ms),
-                         "note": "integer-issue bound by construction (about 380 SAD candidates per job against 88 B of compulsory traffic, planes L2-resident); see DESIGN.md section 5 and profiles/me_r1_ncu.md"},
+                         "note": "instruction-issue bound, not memory bound: ~380 SAD candidates per job against 88 B of compulsory traffic, planes L2-resident; ncu: 59 % of issue slots busy, DRAM traffic = 1.03 x algorithmic bytes (traffic = bytes per launch from profiles/me_r1_traffic.json); see DESIGN.md section 5, profiles/launches_r1.md, profiles/me_r1_ncu.md"},
             "stages_ms": {"me_stage": float(stage[0]), "me_prechecks": float(phases[0]), "me_integer_search": float(phases[1]), "me_subpel": float(phases[2]), "residual": float(stage[1]), "intra": float(stage[2])},
             "stage_rooflines": {
                 "k_cu_residual": {"achieved": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9, "unit": "GB/s", "frac": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9 / peak},
