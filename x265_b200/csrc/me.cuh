@@ -346,121 +346,277 @@ __device__ __forceinline__ int me_subpel_compare_t(const MeCtx<P>& c, int qx, in
     return warp_sum(acc);
 }
 
-// Up to 4 sub-pel candidates of a SMALL PU (w, h <= 16) evaluated concurrently: lanes are spread over
-// (candidate, pixel).  Lane i (< n <= 4) owns candidate i (qx, qy); returns its distortion in lane i.
-// Per candidate the arithmetic is exactly me_subpel_compare's.
-template <typename P>
-__device__ __forceinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+// ---- sub-pel evaluation of SMALL PUs (pow2, w and h <= 16): one lane = one 8-pixel (4 for w = 4) row segment ----
+__device__ __forceinline__ int dp2a_lo_ss(uint32_t a, uint32_t b, int acc)
 {
-    constexpr int DEPTH = PixTraits<P>::depth;
-    const int lgh = 31 - __clz(c.h);
-    const int lgpx = c.lgw + lgh;                         // log2 pixels per candidate
-    const int mrows = c.h + 7;
-    __syncwarp();
-    // phase 1: horizontal pass into mid (candidates with xf && yf), [cand][row][x] with row stride w
-    const int midPer = mrows << c.lgw;                    // <= 368
-    int cqx[4], cqy[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) { cqx[k] = __shfl_sync(0xffffffffu, qx, k); cqy[k] = __shfl_sync(0xffffffffu, qy, k); }
-#pragma unroll 1
-    for (int cand = 0; cand < 4; cand++)
+    int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc)); return d;
+}
+__device__ __forceinline__ int dp2a_hi_ss(uint32_t a, uint32_t b, int acc)
+{
+    int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc)); return d;
+}
+
+// NPX horizontal 8-tap sums of the outputs starting at pixel s (reads s[-3 .. NPX+3]).  8-bit planes: NPX/4+3
+// aligned words, one funnel shift per word to the row's byte phase, then every output is two DP4A on a
+// byte-shifted window (shared between neighbouring outputs): 4.25 instructions per output.
+template <typename P, int NPX>
+__device__ __forceinline__ void me_hrow(const P* __restrict__ s, int xf, int (&sum)[NPX])
+{
+    if (sizeof(P) == 1)
     {
-        const int mqx = cand == 0 ? cqx[0] : cand == 1 ? cqx[1] : cand == 2 ? cqx[2] : cqx[3];
-        const int mqy = cand == 0 ? cqy[0] : cand == 1 ? cqy[1] : cand == 2 ? cqy[2] : cqy[3];
-        const int xf = mqx & 3, yf = mqy & 3;
-        if (cand < n && xf && yf)
-        {
-            const int16_t* cx = c_lumaFilter[xf];
-            const P* r0 = c.ref[0] + (mqx >> 2) + (ptrdiff_t)((mqy >> 2) - 3) * c.rstride - 3;
-            for (int rem = c.lane; rem < midPer; rem += 32)
-            {
-                const int y = rem >> c.lgw, x = rem & (c.w - 1);
-                const P* s = r0 + (ptrdiff_t)y * c.rstride + x;
-                c.sm->mid[cand * 368 + rem] = (int16_t)interp_finish<DEPTH>(me_hsum8(s, cx, xf), 1);
-            }
-        }
-    }
-    __syncwarp();
-    // phase 2: prediction into pred, [cand][y][x] with row stride w
-    const int npx = 1 << lgpx;
-    for (int i = c.lane; i < (n << lgpx); i += 32)
-    {
-        const int cand = i >> lgpx, rem = i & (npx - 1);
-        const int mqx = cand == 0 ? cqx[0] : cand == 1 ? cqx[1] : cand == 2 ? cqx[2] : cqx[3];
-        const int mqy = cand == 0 ? cqy[0] : cand == 1 ? cqy[1] : cand == 2 ? cqy[2] : cqy[3];
-        const int xf = mqx & 3, yf = mqy & 3;
-        const int y = rem >> c.lgw, x = rem & (c.w - 1);
-        const P* r = c.ref[0] + (mqx >> 2) + (ptrdiff_t)(mqy >> 2) * c.rstride;
-        int v;
-        if (!(xf | yf)) v = r[(ptrdiff_t)y * c.rstride + x];
-        else if (!yf)
-        {
-            const P* s = r + (ptrdiff_t)y * c.rstride + x - 3;
-            const int16_t* cx = c_lumaFilter[xf];
-            v = interp_finish<DEPTH>(me_hsum8(s, cx, xf), 0);
-        }
-        else if (!xf)
-        {
-            const P* s = r + (ptrdiff_t)(y - 3) * c.rstride + x;
-            const int16_t* cy = c_lumaFilter[yf];
-            int sum = 0;
+        constexpr int NA = NPX / 4 + 2;                          // window words
+        const uintptr_t a = (uintptr_t)(s - 3);
+        const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+        const unsigned sh = ((unsigned)a & 3u) * 8u;
+        uint32_t W[NA + 1], A[NA];
 #pragma unroll
-            for (int k = 0; k < 8; k++) sum += (int)s[(ptrdiff_t)k * c.rstride] * cy[k];
-            v = interp_finish<DEPTH>(sum, 0);
-        }
-        else
-        {
-            const int16_t* cy = c_lumaFilter[yf];
-            const int16_t* m = c.sm->mid + cand * 368 + (y << c.lgw) + x;
-            int sum = 0;
+        for (int i = 0; i <= NA; i++) W[i] = __ldg(ap + i);
 #pragma unroll
-            for (int k = 0; k < 8; k++) sum += (int)m[k << c.lgw] * cy[k];
-            v = interp_finish<DEPTH>(sum, 2);
-        }
-        c.sm->pred[(cand << 8) + rem] = (uint16_t)v;
-    }
-    __syncwarp();
-    // phase 3: distortion; per-lane partials for (candidate, element) then a per-candidate fold
-    int part[4] = { 0, 0, 0, 0 };
-    if (!satd)
-    {
-        for (int i = c.lane; i < (n << lgpx); i += 32)
+        for (int i = 0; i < NA; i++) A[i] = __funnelshift_r(W[i], W[i + 1], sh);   // A[i] = window bytes 4i..4i+3, byte 0 = s[-3]
+        const uint32_t t0 = c_luma4[xf][0], t1 = c_luma4[xf][1];
+#pragma unroll
+        for (int x = 0; x < NPX; x++)
         {
-            const int cand = i >> lgpx, rem = i & (npx - 1);
-            const int y = rem >> c.lgw, x = rem & (c.w - 1);
-            int d = abs((int)c.fenc[y * c.fstride + x] - (int)c.sm->pred[(cand << 8) + rem]);
-            part[0] += cand == 0 ? d : 0; part[1] += cand == 1 ? d : 0; part[2] += cand == 2 ? d : 0; part[3] += cand == 3 ? d : 0;
+            const int jw = x >> 2, k = (x & 3) * 8;
+            const uint32_t lo = k ? __funnelshift_r(A[jw], A[jw + 1], k) : A[jw];
+            const uint32_t hi = k ? __funnelshift_r(A[jw + 1], A[jw + 2], k) : A[jw + 1];
+            sum[x] = dp4a_us(hi, t1, dp4a_us(lo, t0, 0));
         }
     }
     else
     {
-        // tiles: 8x4 when w >= 8 (halved per tile), 4x4 when w == 4 (pixel.cpp:1134-1158)
-        const int tw = c.w >= 8 ? 8 : 4;
-        const int lgtpr = c.lgw - (c.w >= 8 ? 3 : 2);               // log2 tiles per row
-        const int lgtiles = lgtpr + lgh - 2;                         // log2 tiles per candidate
-        for (int i = c.lane; i < (n << lgtiles); i += 32)
+        const int16_t* cx = c_lumaFilter[xf];
+#pragma unroll
+        for (int x = 0; x < NPX; x++)
         {
-            const int cand = i >> lgtiles, t = i & ((1 << lgtiles) - 1);
-            const int ty = t >> lgtpr, tx = t & ((1 << lgtpr) - 1);
-            const P* pf = c.fenc + (ty * 4) * c.fstride + tx * tw;
-            const uint16_t* pp = c.sm->pred + (cand << 8) + ((ty * 4) << c.lgw) + tx * tw;
-            int d;
-            if (tw == 8) d = me_tile8x4(pf, c.fstride, pp, c.w);
-            else         d = me_tile4x4(pf, c.fstride, pp, c.w);
-            part[0] += cand == 0 ? d : 0; part[1] += cand == 1 ? d : 0; part[2] += cand == 2 ? d : 0; part[3] += cand == 3 ? d : 0;
+            int v = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v += (int)s[x + k - 3] * cx[k];
+            sum[x] = v;
         }
     }
-    int out = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
+}
+
+// NPX vertical 8-tap sums straight from pixel rows; s = (row y-3, first pixel of the segment).  8-bit: each
+// 4x4 block of bytes is transposed in registers (8 PRMT) so that a pixel's four vertical taps are one DP4A.
+template <typename P, int NPX>
+__device__ __forceinline__ void me_vcol(const P* __restrict__ s, int rstride, int yf, int (&sum)[NPX])
+{
+    if (sizeof(P) == 1)
     {
-        int t = warp_sum(part[k]);
-        if (c.lane == k) out = t;
+        constexpr int NW = NPX / 4;
+        uint32_t R[8][NW];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            const uintptr_t a = (uintptr_t)(s + (ptrdiff_t)k * rstride);
+            const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+            const unsigned sh = ((unsigned)a & 3u) * 8u;
+            uint32_t w[NW + 1];
+#pragma unroll
+            for (int i = 0; i <= NW; i++) w[i] = __ldg(ap + i);
+#pragma unroll
+            for (int i = 0; i < NW; i++) R[k][i] = __funnelshift_r(w[i], w[i + 1], sh);
+        }
+        const uint32_t t0 = c_luma4[yf][0], t1 = c_luma4[yf][1];
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+        {
+            uint32_t col[2][4];
+#pragma unroll
+            for (int g = 0; g < 2; g++)
+            {
+                const uint32_t r0 = R[4 * g][i], r1 = R[4 * g + 1][i], r2 = R[4 * g + 2][i], r3 = R[4 * g + 3][i];
+                const uint32_t p0 = __byte_perm(r0, r1, 0x5140), p1 = __byte_perm(r2, r3, 0x5140);     // (r0b0 r1b0 r0b1 r1b1), (r2b0 r3b0 r2b1 r3b1)
+                const uint32_t p2 = __byte_perm(r0, r1, 0x7362), p3 = __byte_perm(r2, r3, 0x7362);     // same for bytes 2, 3
+                col[g][0] = __byte_perm(p0, p1, 0x5410); col[g][1] = __byte_perm(p0, p1, 0x7632);
+                col[g][2] = __byte_perm(p2, p3, 0x5410); col[g][3] = __byte_perm(p2, p3, 0x7632);
+            }
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++) sum[4 * i + bb] = dp4a_us(col[1][bb], t1, dp4a_us(col[0][bb], t0, 0));
+        }
+    }
+    else
+    {
+        const int16_t* cy = c_lumaFilter[yf];
+#pragma unroll
+        for (int x = 0; x < NPX; x++)
+        {
+            int v = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v += (int)s[(ptrdiff_t)k * rstride + x] * cy[k];
+            sum[x] = v;
+        }
+    }
+}
+
+// NPX vertical 8-tap sums over int16 intermediate rows in shared memory (second stage of hv); m = (row y, first
+// element of the segment), row pitch `pitch` elements.  Two vertically adjacent int16 of one column are packed
+// with one PRMT and consumed by DP2A (2 x s16 . 2 x s8 taps): 4 DP2A per pixel.
+template <int NPX>
+__device__ __forceinline__ void me_vmid(const int16_t* __restrict__ m, int pitch, int yf, int (&sum)[NPX])
+{
+    constexpr int NW = NPX / 2;
+    uint32_t M[8][NW];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+    {
+        if (NPX == 8) { const uint4 v = *(const uint4*)(m + k * pitch); M[k][0] = v.x; M[k][1] = v.y; M[k][NW - 2] = v.z; M[k][NW - 1] = v.w; }
+        else          { const uint2 v = *(const uint2*)(m + k * pitch); M[k][0] = v.x; M[k][NW - 1] = v.y; }
+    }
+    const uint32_t t0 = c_luma4[yf][0], t1 = c_luma4[yf][1];
+#pragma unroll
+    for (int i = 0; i < NW; i++)
+    {
+        int s0 = 0, s1 = 0;
+#pragma unroll
+        for (int pr = 0; pr < 4; pr++)
+        {
+            const uint32_t lo = __byte_perm(M[2 * pr][i], M[2 * pr + 1][i], 0x5410);      // (m[2p][2i], m[2p+1][2i])
+            const uint32_t hi = __byte_perm(M[2 * pr][i], M[2 * pr + 1][i], 0x7632);      // (m[2p][2i+1], m[2p+1][2i+1])
+            const uint32_t t = pr < 2 ? t0 : t1;
+            if (pr & 1) { s0 = dp2a_hi_ss(lo, t, s0); s1 = dp2a_hi_ss(hi, t, s1); }
+            else        { s0 = dp2a_lo_ss(lo, t, s0); s1 = dp2a_lo_ss(hi, t, s1); }
+        }
+        sum[2 * i] = s0; sum[2 * i + 1] = s1;
+    }
+}
+
+// Up to 4 sub-pel candidates of a SMALL PU, lane i (< n <= 4) owns candidate i (qx, qy) and gets its distortion.
+// Per candidate the arithmetic is exactly subpelCompare's (motion.cpp:1571-1598: luma_hpp / luma_vpp / luma_hvpp
+// = hps(rowExt) + vsp, ipfilter.cpp:79-369) followed by sad or satd (8x4 tiles, 4x4 for w = 4; pixel.cpp:263-297).
+// Mapping: lane = (candidate slot, segment, row): a PU of h rows and w/8 segments takes h * w/8 lanes, so 4
+// candidates of an 8x8 run at once (2 of a 16x8, 1 of a 16x16).  hv candidates first write their h+7 horizontally
+// filtered rows to shared memory (one row segment per lane-task), then every lane produces ITS row of the
+// prediction in registers, differences it against the source row, does the horizontal half of the 4x4 Hadamards
+// in registers and the vertical half with two xor-shuffle butterflies over the 4 lanes of a tile.
+template <typename P, int NPX>
+__device__ __forceinline__ int me_subpel_small_t(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+{
+    constexpr int DEPTH = PixTraits<P>::depth;
+    const int lane = c.lane;
+    const int lgsegs = NPX == 8 ? c.lgw - 3 : 0;                 // log2 segments per row
+    const int lgh = 31 - __clz(c.h);
+    const int lglpc = lgh + lgsegs, lpc = 1 << lglpc;            // lanes per candidate: 4 .. 32
+    const int cpp = min(4, 32 >> lglpc);                         // candidate slots per pass
+    const int midPer = (c.h + 7) * c.w;                          // int16 elements of one candidate's intermediate
+    const int tasksPer = (c.h + 7) << lgsegs;
+    int16_t* mid = c.sm->mid;
+    int out = 0;
+    for (int base = 0; base < n; base += cpp)
+    {
+        const int live_n = min(cpp, n - base);
+        __syncwarp();
+        // ---- stage 1: horizontally filtered rows of the hv candidates ----
+        for (int t0 = 0; t0 < live_n * tasksPer; t0 += 32)
+        {
+            const int t = t0 + lane;
+            const int tci = min((int)(t >= tasksPer) + (int)(t >= 2 * tasksPer) + (int)(t >= 3 * tasksPer), live_n - 1);
+            const int tt = t - tci * tasksPer;
+            const int tqx = __shfl_sync(0xffffffffu, qx, base + tci), tqy = __shfl_sync(0xffffffffu, qy, base + tci);
+            const int txf = tqx & 3, tyf = tqy & 3;
+            if (t < live_n * tasksPer && txf && tyf)
+            {
+                const int mrow = tt >> lgsegs, seg = tt & ((1 << lgsegs) - 1);
+                const P* s = c.ref[0] + (tqx >> 2) + (ptrdiff_t)((tqy >> 2) - 3 + mrow) * c.rstride + seg * 8;
+                int sum[NPX];
+                me_hrow<P, NPX>(s, txf, sum);
+                uint32_t pk[NPX / 2];
+#pragma unroll
+                for (int i = 0; i < NPX / 2; i++)
+                    pk[i] = ((uint32_t)interp_finish<DEPTH>(sum[2 * i], 1) & 0xffffu) | ((uint32_t)interp_finish<DEPTH>(sum[2 * i + 1], 1) << 16);
+                int16_t* d = mid + tci * midPer + mrow * c.w + seg * 8;
+                if (NPX == 8) *(uint4*)d = make_uint4(pk[0], pk[1], pk[NPX / 2 - 2], pk[NPX / 2 - 1]);
+                else          *(uint2*)d = make_uint2(pk[0], pk[NPX / 2 - 1]);
+            }
+        }
+        __syncwarp();
+        // ---- stage 2: my row segment of my candidate's prediction ----
+        const int ci = lane >> lglpc, sub = lane & (lpc - 1);
+        const bool live = ci < live_n;
+        const int cand = base + min(ci, live_n - 1);
+        const int mqx = __shfl_sync(0xffffffffu, qx, cand), mqy = __shfl_sync(0xffffffffu, qy, cand);
+        const int xf = mqx & 3, yf = mqy & 3;
+        const int row = sub & (c.h - 1), seg = sub >> lgh;
+        int d[NPX];
+        if (live)
+        {
+            const P* r = c.ref[0] + (mqx >> 2) + (ptrdiff_t)((mqy >> 2) + row) * c.rstride + seg * 8;
+            int pr[NPX];
+            if (!(xf | yf))
+            {
+#pragma unroll
+                for (int x = 0; x < NPX; x++) pr[x] = (int)__ldg(r + x);
+            }
+            else if (!yf)
+            {
+                me_hrow<P, NPX>(r, xf, pr);
+#pragma unroll
+                for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 0);
+            }
+            else if (!xf)
+            {
+                me_vcol<P, NPX>(r - 3 * (ptrdiff_t)c.rstride, c.rstride, yf, pr);
+#pragma unroll
+                for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 0);
+            }
+            else
+            {
+                me_vmid<NPX>(mid + min(ci, live_n - 1) * midPer + row * c.w + seg * 8, c.w, yf, pr);
+#pragma unroll
+                for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 2);
+            }
+            const P* f = c.fenc + (ptrdiff_t)row * c.fstride + seg * 8;
+#pragma unroll
+            for (int x = 0; x < NPX; x++) d[x] = (int)__ldg(f + x) - pr[x];
+        }
+        else
+        {
+#pragma unroll
+            for (int x = 0; x < NPX; x++) d[x] = 0;
+        }
+        // ---- stage 3: distortion ----
+        int part = 0;
+        if (!satd)
+        {
+#pragma unroll
+            for (int x = 0; x < NPX; x++) part += abs(d[x]);
+            for (int o = 1; o < lpc; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        }
+        else
+        {
+#pragma unroll
+            for (int x = 0; x < NPX; x += 4) had4(d[x], d[x + 1], d[x + 2], d[x + 3]);
+#pragma unroll
+            for (int st = 1; st <= 2; st <<= 1)
+            {
+                const bool up = (lane & st) != 0;
+#pragma unroll
+                for (int x = 0; x < NPX; x++)
+                {
+                    const int o = __shfl_xor_sync(0xffffffffu, d[x], st);
+                    d[x] = up ? o - d[x] : o + d[x];
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < NPX; x++) part += abs(d[x]);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part = (lane & 3) ? 0 : (part >> 1);                    // one 8x4 (4x4) tile per 4 lanes, halved per tile
+            for (int o = 4; o < lpc; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        }
+        const int v = __shfl_sync(0xffffffffu, part, ((lane - base) << lglpc) & 31);
+        if (lane >= base && lane < base + live_n) out = v;
     }
     return out;
 }
 
-// distortion of up to 8 sub-pel candidates, lane i (< n) owns candidate i; result in lane i
+template <typename P>
+__device__ __forceinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+{
+    return c.w >= 8 ? me_subpel_small_t<P, 8>(c, n, qx, qy, satd) : me_subpel_small_t<P, 4>(c, n, qx, qy, satd);
+}
+
 // out-of-line copy for the cold multi-site users (pre-checks, lowres band cost)
 template <typename P>
 __device__ __noinline__ int me_subpel_compare(const MeCtx<P>& c, int qx, int qy, bool satd) { return me_subpel_compare_t(c, qx, qy, satd); }
