@@ -611,6 +611,115 @@ __device__ __forceinline__ int me_subpel_small_t(const MeCtx<P>& c, int n, int q
     return out;
 }
 
+// One sub-pel candidate of a LARGE pow2 PU (w >= 8, more than 32 row segments), same lane = row-segment scheme in
+// bands of 16 rows: the band's 23 horizontally filtered rows go through shared memory (hv only), every lane then
+// produces row segments of the prediction in registers, 32 at a time.  All lanes get the distortion.
+template <typename P>
+__device__ __forceinline__ int me_subpel_big(const MeCtx<P>& c, int qx, int qy, bool satd)
+{
+    constexpr int DEPTH = PixTraits<P>::depth;
+    constexpr int NPX = 8;
+    const int lane = c.lane;
+    const int lgsegs = c.lgw - 3;
+    const int xf = qx & 3, yf = qy & 3;
+    const P* r0 = c.ref[0] + (qx >> 2) + (ptrdiff_t)(qy >> 2) * c.rstride;
+    int16_t* mid = c.sm->mid;
+    int acc = 0;
+    for (int y0 = 0; y0 < c.h; y0 += ME_BAND)
+    {
+        const int rows = min(ME_BAND, c.h - y0), lgrows = 31 - __clz(rows);
+        if (xf && yf)
+        {
+            __syncwarp();
+            const int tasks = (rows + 7) << lgsegs;
+            for (int t = lane; t < tasks; t += 32)
+            {
+                const int mrow = t >> lgsegs, seg = t & ((1 << lgsegs) - 1);
+                int sum[NPX];
+                me_hrow<P, NPX>(r0 + (ptrdiff_t)(y0 - 3 + mrow) * c.rstride + seg * 8, xf, sum);
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    pk[i] = ((uint32_t)interp_finish<DEPTH>(sum[2 * i], 1) & 0xffffu) | ((uint32_t)interp_finish<DEPTH>(sum[2 * i + 1], 1) << 16);
+                *(uint4*)(mid + mrow * c.w + seg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            __syncwarp();
+        }
+        const int units = rows << lgsegs;
+        for (int u0 = 0; u0 < units; u0 += 32)
+        {
+            const int u = u0 + lane;
+            const bool live = u < units;
+            const int row = u & (rows - 1), seg = (u >> lgrows) & ((1 << lgsegs) - 1);
+            int d[NPX];
+            if (live)
+            {
+                const P* r = r0 + (ptrdiff_t)(y0 + row) * c.rstride + seg * 8;
+                int pr[NPX];
+                if (!(xf | yf))
+                {
+#pragma unroll
+                    for (int x = 0; x < NPX; x++) pr[x] = (int)__ldg(r + x);
+                }
+                else if (!yf)
+                {
+                    me_hrow<P, NPX>(r, xf, pr);
+#pragma unroll
+                    for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 0);
+                }
+                else if (!xf)
+                {
+                    me_vcol<P, NPX>(r - 3 * (ptrdiff_t)c.rstride, c.rstride, yf, pr);
+#pragma unroll
+                    for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 0);
+                }
+                else
+                {
+                    me_vmid<NPX>(mid + row * c.w + seg * 8, c.w, yf, pr);
+#pragma unroll
+                    for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 2);
+                }
+                const P* f = c.fenc + (ptrdiff_t)(y0 + row) * c.fstride + seg * 8;
+#pragma unroll
+                for (int x = 0; x < NPX; x++) d[x] = (int)__ldg(f + x) - pr[x];
+            }
+            else
+            {
+#pragma unroll
+                for (int x = 0; x < NPX; x++) d[x] = 0;
+            }
+            int part = 0;
+            if (!satd)
+            {
+#pragma unroll
+                for (int x = 0; x < NPX; x++) part += abs(d[x]);
+            }
+            else
+            {
+                had4(d[0], d[1], d[2], d[3]); had4(d[4], d[5], d[6], d[7]);
+#pragma unroll
+                for (int st = 1; st <= 2; st <<= 1)
+                {
+                    const bool up = (lane & st) != 0;
+#pragma unroll
+                    for (int x = 0; x < NPX; x++)
+                    {
+                        const int o = __shfl_xor_sync(0xffffffffu, d[x], st);
+                        d[x] = up ? o - d[x] : o + d[x];
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < NPX; x++) part += abs(d[x]);
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                part = (lane & 3) ? 0 : (part >> 1);
+            }
+            acc += part;
+        }
+    }
+    return warp_sum(acc);
+}
+
 template <typename P>
 __device__ __forceinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
 {
@@ -649,7 +758,7 @@ __device__ __forceinline__ int me_subpel_batch(const MeCtx<P>& c, int n, int qx,
         for (int k = 0; k < n; k++)
         {
             const int kqx = __shfl_sync(0xffffffffu, qx, k), kqy = __shfl_sync(0xffffffffu, qy, k);
-            int v = me_subpel_compare_t(c, kqx, kqy, satd);
+            int v = c.pow2 ? me_subpel_big(c, kqx, kqy, satd) : me_subpel_compare(c, kqx, kqy, satd);      // AMP sizes: generic, out of line
             if (c.lane == k) out = v;
         }
     }
@@ -1144,8 +1253,11 @@ __device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j,
 #ifndef ME_P2_BLOCKS
 #define ME_P2_BLOCKS 4
 #endif
+#ifndef ME_BIG_BLOCKS
+#define ME_BIG_BLOCKS 2          // large-PU pre-check / sub-pel kernels: 128 registers beat a third resident CTA (no spills in the tap loops)
+#endif
 template <typename P, int PHASE, int CLS>
-__global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : ME_MIN_BLOCKS) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
+__global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : (CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS)) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
                                                            const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
                                                            int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter)
 {
@@ -1181,7 +1293,7 @@ static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const
 {
     const int threads = 256, warps = threads / 32;
     const size_t smem = PHASE == 2 ? 0 : sizeof(MeShared) * warps;      // the integer search never touches the interpolation scratch
-    int blocks = ctx->sm_count * (PHASE == 2 ? ME_P2_BLOCKS : ME_MIN_BLOCKS);
+    int blocks = ctx->sm_count * (PHASE == 2 ? ME_P2_BLOCKS : (CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS));
     int need = (n + warps - 1) / warps;
     if (blocks > need) blocks = need;
     k_me<P, PHASE, CLS><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, lowres, mvcost, jobs, n, out, state, counter);
