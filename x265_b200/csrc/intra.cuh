@@ -142,6 +142,82 @@ __global__ void k_intra_filter(int N, const P* __restrict__ nb, P* __restrict__ 
     }
 }
 
+// all-angs, one CTA per block: the neighbours (unfiltered and filtered) are staged once, each of the 8 warps takes
+// every 8th mode, a lane produces 4 consecutive pixels of a row and stores them with one 4 / 8-byte store
+// (33*N*N contiguous per job, 128 contiguous bytes per warp store).  Same per-pixel arithmetic as
+// intra_predict_block (intrapred.cpp:102-234).
+template <typename P>
+__global__ void __launch_bounds__(256) k_intra_allangs_cta(int N, const P* __restrict__ refp, const P* __restrict__ filtp, int64_t nb_pitch,
+                                                           P* __restrict__ dst, int bLuma, int n)
+{
+    constexpr int maxv = PixTraits<P>::maxv;
+    __shared__ int16_t s_nb[2][132];
+    __shared__ int16_t s_ref[8][132];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lg = 31 - __clz(N), N2 = 2 * N, upr = N >> 2, nunits = (N * N) >> 2;      // units of 4 pixels
+    for (int j = blockIdx.x; j < n; j += gridDim.x)
+    {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * (4 * N + 1); i += blockDim.x)
+        {
+            const int which = i >= 4 * N + 1, e = which ? i - (4 * N + 1) : i;
+            s_nb[which][e] = (int16_t)(which ? filtp : refp)[j * nb_pitch + e];
+        }
+        __syncthreads();
+        int16_t* refbuf = s_ref[warp];
+        for (int mode = 2 + warp; mode < 35; mode += 8)
+        {
+            const int16_t* nbs = s_nb[intra_use_filtered(mode, N) ? 1 : 0];
+            P* out = dst + ((int64_t)j * 33 + (mode - 2)) * N * N;
+            const bool hor = mode < 18;
+            const int angOff = hor ? 10 - mode : mode - 26;
+            const int angle = c_angle[8 + angOff];
+            const int mainBase = hor ? N2 + 1 : 1, sideBase = hor ? 1 : N2 + 1;
+            const int off = N + 1;
+            __syncwarp();
+            if (angle < 0)
+            {
+                const int nproj = -((N * angle) >> 5) - 1;
+                const int inv = c_invAngle[-angOff - 1];
+                for (int i = lane; i < nproj; i += 32) refbuf[off + 1 + (-2 - i)] = nbs[sideBase - 1 + ((128 + (i + 1) * inv) >> 8)];
+                for (int i = lane; i < N + 1; i += 32) refbuf[off + 1 + (-1 + i)] = (i == 0) ? nbs[0] : nbs[mainBase + i - 1];
+            }
+            else if (angle > 0)
+            {
+                for (int i = lane; i < N2; i += 32) refbuf[off + 1 + i] = nbs[mainBase + i];
+            }
+            __syncwarp();
+            for (int u = lane; u < nunits; u += 32)
+            {
+                const int r = u / upr, c0 = (u - r * upr) * 4;
+                int v[4];
+                if (angle == 0)
+                {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) v[k] = nbs[mainBase + c0 + k];
+                    if (bLuma && c0 == 0) v[0] = clip3i(0, maxv, (int)(int16_t)(nbs[mainBase] + ((nbs[sideBase + r] - nbs[0]) >> 1)));
+                }
+                else
+                {
+                    const int pos = (r + 1) * angle, o = pos >> 5, f = pos & 31;
+                    const int16_t* rp = refbuf + off + 1 + o + c0;
+                    int a = rp[0];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        const int b = rp[k + 1];
+                        v[k] = f ? (((32 - f) * a + f * b + 16) >> 5) : a;
+                        a = b;
+                    }
+                }
+                P* d = out + (r << lg) + c0;
+                if (sizeof(P) == 1) *(uint32_t*)d = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+                else                *(uint2*)d = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+            }
+        }
+    }
+}
+
 // all-angs (intrapred.cpp:206-234): grid = (33 modes, jobs); 33*N*N contiguous per job
 template <typename P>
 __global__ void __launch_bounds__(256) k_intra_allangs(int N, const P* __restrict__ refp, const P* __restrict__ filtp, int64_t nb_pitch,

@@ -206,35 +206,6 @@ __device__ __forceinline__ int me_compact(bool valid, int cnt, int& a, int& b, i
     return __popc(m);
 }
 
-// 8-tap horizontal luma sum of the 8 pixels starting at s (ipfilter.cpp:79-118 inner loop).  8-bit planes:
-// three aligned words, two funnel shifts and two DP4A (u8 pixels x s8 taps, exact in int32) instead of
-// eight byte loads and eight IMADs; the third word is within the plane margin even when unused.
-__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int acc)
-{
-    int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
-    return d;
-}
-// c_lumaFilter[xf] packed as 2 x 4 signed bytes (taps 0-3, taps 4-7), little-endian
-__constant__ uint32_t c_luma4[4][2] = { { 0x40000000u, 0u }, { 0x3af604ffu, 0x0001fb11u }, { 0x28f504ffu, 0xff04f528u }, { 0x11fb0100u, 0xff04f63au } };
-template <typename P>
-__device__ __forceinline__ int me_hsum8(const P* __restrict__ s, const int16_t* __restrict__ cx, int xf)
-{
-    if (sizeof(P) == 1)
-    {
-        const uintptr_t a = (uintptr_t)s;
-        const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
-        const unsigned sh = ((unsigned)a & 3u) * 8u;
-        const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
-        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-        return dp4a_us(hi, c_luma4[xf][1], dp4a_us(lo, c_luma4[xf][0], 0));
-    }
-    int sum = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) sum += (int)s[k] * cx[k];
-    return sum;
-}
-
 // cost of a band of prediction held in c.sm->pred (stride 64) against fenc rows [y0, y0+rows)
 template <typename P>
 __device__ __forceinline__ int me_band_cost(const MeCtx<P>& c, int y0, int rows, bool satd)
@@ -347,141 +318,7 @@ __device__ __forceinline__ int me_subpel_compare_t(const MeCtx<P>& c, int qx, in
 }
 
 // ---- sub-pel evaluation of SMALL PUs (pow2, w and h <= 16): one lane = one 8-pixel (4 for w = 4) row segment ----
-__device__ __forceinline__ int dp2a_lo_ss(uint32_t a, uint32_t b, int acc)
-{
-    int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc)); return d;
-}
-__device__ __forceinline__ int dp2a_hi_ss(uint32_t a, uint32_t b, int acc)
-{
-    int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc)); return d;
-}
-
-// NPX horizontal 8-tap sums of the outputs starting at pixel s (reads s[-3 .. NPX+3]).  8-bit planes: NPX/4+3
-// aligned words, one funnel shift per word to the row's byte phase, then every output is two DP4A on a
-// byte-shifted window (shared between neighbouring outputs): 4.25 instructions per output.
-template <typename P, int NPX>
-__device__ __forceinline__ void me_hrow(const P* __restrict__ s, int xf, int (&sum)[NPX])
-{
-    if (sizeof(P) == 1)
-    {
-        constexpr int NA = NPX / 4 + 2;                          // window words
-        const uintptr_t a = (uintptr_t)(s - 3);
-        const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
-        const unsigned sh = ((unsigned)a & 3u) * 8u;
-        uint32_t W[NA + 1], A[NA];
-#pragma unroll
-        for (int i = 0; i <= NA; i++) W[i] = __ldg(ap + i);
-#pragma unroll
-        for (int i = 0; i < NA; i++) A[i] = __funnelshift_r(W[i], W[i + 1], sh);   // A[i] = window bytes 4i..4i+3, byte 0 = s[-3]
-        const uint32_t t0 = c_luma4[xf][0], t1 = c_luma4[xf][1];
-#pragma unroll
-        for (int x = 0; x < NPX; x++)
-        {
-            const int jw = x >> 2, k = (x & 3) * 8;
-            const uint32_t lo = k ? __funnelshift_r(A[jw], A[jw + 1], k) : A[jw];
-            const uint32_t hi = k ? __funnelshift_r(A[jw + 1], A[jw + 2], k) : A[jw + 1];
-            sum[x] = dp4a_us(hi, t1, dp4a_us(lo, t0, 0));
-        }
-    }
-    else
-    {
-        const int16_t* cx = c_lumaFilter[xf];
-#pragma unroll
-        for (int x = 0; x < NPX; x++)
-        {
-            int v = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) v += (int)s[x + k - 3] * cx[k];
-            sum[x] = v;
-        }
-    }
-}
-
-// NPX vertical 8-tap sums straight from pixel rows; s = (row y-3, first pixel of the segment).  8-bit: each
-// 4x4 block of bytes is transposed in registers (8 PRMT) so that a pixel's four vertical taps are one DP4A.
-template <typename P, int NPX>
-__device__ __forceinline__ void me_vcol(const P* __restrict__ s, int rstride, int yf, int (&sum)[NPX])
-{
-    if (sizeof(P) == 1)
-    {
-        constexpr int NW = NPX / 4;
-        uint32_t R[8][NW];
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-        {
-            const uintptr_t a = (uintptr_t)(s + (ptrdiff_t)k * rstride);
-            const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
-            const unsigned sh = ((unsigned)a & 3u) * 8u;
-            uint32_t w[NW + 1];
-#pragma unroll
-            for (int i = 0; i <= NW; i++) w[i] = __ldg(ap + i);
-#pragma unroll
-            for (int i = 0; i < NW; i++) R[k][i] = __funnelshift_r(w[i], w[i + 1], sh);
-        }
-        const uint32_t t0 = c_luma4[yf][0], t1 = c_luma4[yf][1];
-#pragma unroll
-        for (int i = 0; i < NW; i++)
-        {
-            uint32_t col[2][4];
-#pragma unroll
-            for (int g = 0; g < 2; g++)
-            {
-                const uint32_t r0 = R[4 * g][i], r1 = R[4 * g + 1][i], r2 = R[4 * g + 2][i], r3 = R[4 * g + 3][i];
-                const uint32_t p0 = __byte_perm(r0, r1, 0x5140), p1 = __byte_perm(r2, r3, 0x5140);     // (r0b0 r1b0 r0b1 r1b1), (r2b0 r3b0 r2b1 r3b1)
-                const uint32_t p2 = __byte_perm(r0, r1, 0x7362), p3 = __byte_perm(r2, r3, 0x7362);     // same for bytes 2, 3
-                col[g][0] = __byte_perm(p0, p1, 0x5410); col[g][1] = __byte_perm(p0, p1, 0x7632);
-                col[g][2] = __byte_perm(p2, p3, 0x5410); col[g][3] = __byte_perm(p2, p3, 0x7632);
-            }
-#pragma unroll
-            for (int bb = 0; bb < 4; bb++) sum[4 * i + bb] = dp4a_us(col[1][bb], t1, dp4a_us(col[0][bb], t0, 0));
-        }
-    }
-    else
-    {
-        const int16_t* cy = c_lumaFilter[yf];
-#pragma unroll
-        for (int x = 0; x < NPX; x++)
-        {
-            int v = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) v += (int)s[(ptrdiff_t)k * rstride + x] * cy[k];
-            sum[x] = v;
-        }
-    }
-}
-
-// NPX vertical 8-tap sums over int16 intermediate rows in shared memory (second stage of hv); m = (row y, first
-// element of the segment), row pitch `pitch` elements.  Two vertically adjacent int16 of one column are packed
-// with one PRMT and consumed by DP2A (2 x s16 . 2 x s8 taps): 4 DP2A per pixel.
-template <int NPX>
-__device__ __forceinline__ void me_vmid(const int16_t* __restrict__ m, int pitch, int yf, int (&sum)[NPX])
-{
-    constexpr int NW = NPX / 2;
-    uint32_t M[8][NW];
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-    {
-        if (NPX == 8) { const uint4 v = *(const uint4*)(m + k * pitch); M[k][0] = v.x; M[k][1] = v.y; M[k][NW - 2] = v.z; M[k][NW - 1] = v.w; }
-        else          { const uint2 v = *(const uint2*)(m + k * pitch); M[k][0] = v.x; M[k][NW - 1] = v.y; }
-    }
-    const uint32_t t0 = c_luma4[yf][0], t1 = c_luma4[yf][1];
-#pragma unroll
-    for (int i = 0; i < NW; i++)
-    {
-        int s0 = 0, s1 = 0;
-#pragma unroll
-        for (int pr = 0; pr < 4; pr++)
-        {
-            const uint32_t lo = __byte_perm(M[2 * pr][i], M[2 * pr + 1][i], 0x5410);      // (m[2p][2i], m[2p+1][2i])
-            const uint32_t hi = __byte_perm(M[2 * pr][i], M[2 * pr + 1][i], 0x7632);      // (m[2p][2i+1], m[2p+1][2i+1])
-            const uint32_t t = pr < 2 ? t0 : t1;
-            if (pr & 1) { s0 = dp2a_hi_ss(lo, t, s0); s1 = dp2a_hi_ss(hi, t, s1); }
-            else        { s0 = dp2a_lo_ss(lo, t, s0); s1 = dp2a_lo_ss(hi, t, s1); }
-        }
-        sum[2 * i] = s0; sum[2 * i + 1] = s1;
-    }
-}
-
+// (row helpers me_hrow / me_vcol / me_vmid: interp.cuh)
 // Up to 4 sub-pel candidates of a SMALL PU, lane i (< n <= 4) owns candidate i (qx, qy) and gets its distortion.
 // Per candidate the arithmetic is exactly subpelCompare's (motion.cpp:1571-1598: luma_hpp / luma_vpp / luma_hvpp
 // = hps(rowExt) + vsp, ipfilter.cpp:79-369) followed by sad or satd (8x4 tiles, 4x4 for w = 4; pixel.cpp:263-297).

@@ -133,6 +133,146 @@ __global__ void __launch_bounds__(256) k_transform(int op, const int16_t* __rest
     }
 }
 
+// ---- 4x4 / 8x8, contiguous TUs: one THREAD per TU, everything in registers -------------------------------
+// The even/odd symmetry of the DCT rows (M[k][N-1-q] = (-1)^k M[k][q]) halves the multiplies; the sums are the
+// same integers as the matrix product (dct.cpp:83-440 are the same factorisation), the rounding shifts and
+// the int16 truncation / clipping are the reference's (dct.cpp:442-610).  Matrix entries are compile-time
+// indexed constant-bank operands.  A thread reads and writes its TU with 16-byte accesses.
+template <int N>
+__device__ __forceinline__ void dct_fwd1d(const int (&x)[N], int (&y)[N])
+{
+    constexpr int LG = N == 4 ? 2 : 3, H = N / 2;
+    int sm[H], df[H];
+#pragma unroll
+    for (int q = 0; q < H; q++) { sm[q] = x[q] + x[N - 1 - q]; df[q] = x[q] - x[N - 1 - q]; }
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        int acc = 0;
+#pragma unroll
+        for (int q = 0; q < H; q++) acc += (int)c_dct[LG - 2][k * N + q] * ((k & 1) ? df[q] : sm[q]);
+        y[k] = acc;
+    }
+}
+template <int N>
+__device__ __forceinline__ void dct_inv1d(const int (&x)[N], int (&y)[N])
+{
+    constexpr int LG = N == 4 ? 2 : 3, H = N / 2;
+#pragma unroll
+    for (int i = 0; i < H; i++)
+    {
+        int e = 0, o = 0;
+#pragma unroll
+        for (int q = 0; q < N; q += 2) { e += (int)c_dct[LG - 2][q * N + i] * x[q]; o += (int)c_dct[LG - 2][(q + 1) * N + i] * x[q + 1]; }
+        y[i] = e + o; y[N - 1 - i] = e - o;
+    }
+}
+
+template <int DEPTH, int N, bool FWD>
+__global__ void __launch_bounds__(128) k_transform_reg(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int n)
+{
+    constexpr int NN = N * N, LG = N == 4 ? 2 : 3;
+    constexpr int shift1 = FWD ? LG - 1 + (DEPTH - 8) : 7;
+    constexpr int shift2 = FWD ? LG + 6 : 12 - (DEPTH - 8);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int a[N][N];
+    {
+        const uint4* sp = (const uint4*)(src + (size_t)t * NN);
+#pragma unroll
+        for (int i = 0; i < NN / 8; i++)
+        {
+            const uint4 v = __ldg(sp + i);
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const int e = i * 8 + k * 2;
+                a[e / N][e % N] = (int)(int16_t)(w[k] & 0xffffu);
+                a[(e + 1) / N][(e + 1) % N] = (int)(int16_t)(w[k] >> 16);
+            }
+        }
+    }
+    int m[N][N], o[N][N];
+    if (FWD)
+    {
+        // mid[k][j] = (sum_q M[k][q] in[j][q] + r) >> shift1, truncated to int16; dst[k][c] = (sum_q M[k][q] mid[c][q] + r) >> shift2
+#pragma unroll
+        for (int j = 0; j < N; j++)
+        {
+            int y[N];
+            dct_fwd1d<N>(a[j], y);
+#pragma unroll
+            for (int k = 0; k < N; k++) m[k][j] = (int)(int16_t)((y[k] + (1 << (shift1 - 1))) >> shift1);
+        }
+#pragma unroll
+        for (int c = 0; c < N; c++)
+        {
+            int y[N];
+            dct_fwd1d<N>(m[c], y);
+#pragma unroll
+            for (int k = 0; k < N; k++) o[k][c] = (int)(int16_t)((y[k] + (1 << (shift2 - 1))) >> shift2);
+        }
+    }
+    else
+    {
+        // mid[j][i] = clip16((sum_q M[q][i] in[q][j] + 64) >> 7); out[c][i] = clip16((sum_q M[q][i] mid[q][c] + r) >> shift2)
+#pragma unroll
+        for (int j = 0; j < N; j++)
+        {
+            int x[N], y[N];
+#pragma unroll
+            for (int q = 0; q < N; q++) x[q] = a[q][j];
+            dct_inv1d<N>(x, y);
+#pragma unroll
+            for (int i = 0; i < N; i++) m[j][i] = clip16((y[i] + (1 << (shift1 - 1))) >> shift1);
+        }
+#pragma unroll
+        for (int c = 0; c < N; c++)
+        {
+            int x[N], y[N];
+#pragma unroll
+            for (int q = 0; q < N; q++) x[q] = m[q][c];
+            dct_inv1d<N>(x, y);
+#pragma unroll
+            for (int i = 0; i < N; i++) o[c][i] = clip16((y[i] + (1 << (shift2 - 1))) >> shift2);
+        }
+    }
+    uint4* dp = (uint4*)(dst + (size_t)t * NN);
+#pragma unroll
+    for (int i = 0; i < NN / 8; i++)
+    {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const int e = i * 8 + k * 2;
+            w[k] = ((uint32_t)o[e / N][e % N] & 0xffffu) | ((uint32_t)o[(e + 1) / N][(e + 1) % N] << 16);
+        }
+        dp[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+template <int DEPTH>
+static int launch_transform_reg(x265cu_ctx* ctx, int op, int N, const int16_t* src, int16_t* dst, int stride, int64_t tu_pitch, int n)
+{
+    if ((op != X265CU_DCT && op != X265CU_IDCT) || (N != 4 && N != 8) || stride != N || tu_pitch != (int64_t)N * N ||
+        (((uintptr_t)src | (uintptr_t)dst) & 15))
+        return 0;
+    const int blocks = (n + 127) / 128;
+    if (N == 4)
+    {
+        if (op == X265CU_DCT) k_transform_reg<DEPTH, 4, true><<<blocks, 128, 0, ctx->stream>>>(src, dst, n);
+        else                  k_transform_reg<DEPTH, 4, false><<<blocks, 128, 0, ctx->stream>>>(src, dst, n);
+    }
+    else
+    {
+        if (op == X265CU_DCT) k_transform_reg<DEPTH, 8, true><<<blocks, 128, 0, ctx->stream>>>(src, dst, n);
+        else                  k_transform_reg<DEPTH, 8, false><<<blocks, 128, 0, ctx->stream>>>(src, dst, n);
+    }
+    return 1;
+}
+
 template <int DEPTH>
 static int launch_transform_d(x265cu_ctx* ctx, int op, int N, const int16_t* src, int16_t* dst, int stride, int64_t tu_pitch, int n)
 {
@@ -157,6 +297,8 @@ static int launch_transform(x265cu_ctx* ctx, int depth, int op, int N, const int
     // 16x16 / 32x32 go to the tensor-core (IMMA) kernel when the operands are vector-load aligned
     int took = (depth == 8) ? launch_transform_mma<8>(ctx, op, N, src, dst, stride, tu_pitch, n)
                             : launch_transform_mma<10>(ctx, op, N, src, dst, stride, tu_pitch, n);
+    if (!took) took = (depth == 8) ? launch_transform_reg<8>(ctx, op, N, src, dst, stride, tu_pitch, n)
+                                   : launch_transform_reg<10>(ctx, op, N, src, dst, stride, tu_pitch, n);
     if (!took)
     {
         if (depth == 8) launch_transform_d<8>(ctx, op, N, src, dst, stride, tu_pitch, n);

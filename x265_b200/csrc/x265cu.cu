@@ -173,6 +173,14 @@ int x265cu_intra_filter_batch(x265cu_ctx* c, int depth, int size, const void* nb
 int x265cu_intra_allangs_batch(x265cu_ctx* c, int depth, int size, const void* ref, const void* filt, int64_t nb_pitch, void* dst, int bLuma, int n)
 {
     if (n <= 0) return 0;
+    if ((((uintptr_t)dst) & 7) == 0 && size >= 4 && size <= 32)
+    {   // vector-store kernel: one CTA per block, all 33 modes
+        int blocks = n < c->sm_count * 16 ? n : c->sm_count * 16;
+        if (depth == 8) k_intra_allangs_cta<uint8_t><<<blocks, 256, 0, c->stream>>>(size, (const uint8_t*)ref, (const uint8_t*)filt, nb_pitch, (uint8_t*)dst, bLuma, n);
+        else            k_intra_allangs_cta<uint16_t><<<blocks, 256, 0, c->stream>>>(size, (const uint16_t*)ref, (const uint16_t*)filt, nb_pitch, (uint16_t*)dst, bLuma, n);
+        CU_LAUNCH_CHECK(c);
+        return 0;
+    }
     dim3 grid(33, n < 4096 ? n : 4096);
     int threads = size * size < 256 ? (size * size < 32 ? 32 : size * size) : 256;
     if (depth == 8) k_intra_allangs<uint8_t><<<grid, threads, 0, c->stream>>>(size, (const uint8_t*)ref, (const uint8_t*)filt, nb_pitch, (uint8_t*)dst, bLuma, n);
