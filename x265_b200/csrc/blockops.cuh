@@ -56,6 +56,90 @@ __device__ __forceinline__ void blockop_elem(int op, const x265cu_blk_job& jb, v
     }
 }
 
+// ---- vector path for the element-wise ops: a thread handles 8 consecutive elements of a row ---------------
+// operand element kinds per op: 0 = none, 1 = pixel, 2 = int16
+__device__ __forceinline__ void blockop_kinds(int op, int& kd, int& ka, int& kb)
+{
+    kd = ka = kb = 0;
+    switch (op)
+    {
+    case X265CU_COPY_PP: kd = 1; ka = 1; break;
+    case X265CU_COPY_SS: kd = 2; ka = 2; break;
+    case X265CU_COPY_SP: kd = 1; ka = 2; break;
+    case X265CU_COPY_PS: kd = 2; ka = 1; break;
+    case X265CU_SUB_PS:  kd = 2; ka = 1; kb = 1; break;
+    case X265CU_ADD_PS:  kd = 1; ka = 1; kb = 2; break;
+    case X265CU_PIXELAVG_PP: kd = 1; ka = 1; kb = 1; break;
+    case X265CU_ADDAVG:  kd = 1; ka = 2; kb = 2; break;
+    case X265CU_P2S:     kd = 2; ka = 1; break;
+    case X265CU_BLOCKFILL_S: kd = 2; break;
+    case X265CU_CPY2DTO1D_SHL: case X265CU_CPY1DTO2D_SHL: case X265CU_CPY2DTO1D_SHR: case X265CU_CPY1DTO2D_SHR:
+    case X265CU_DEQUANT_NORMAL: kd = 2; ka = 2; break;
+    case X265CU_WEIGHT_PP: kd = 1; ka = 1; break;
+    case X265CU_WEIGHT_SP: kd = 1; ka = 2; break;
+    default: break;                                   // transpose / scale2D: not element-wise, scalar path only
+    }
+}
+
+// the value an element-wise op writes for inputs a, b (same arithmetic as blockop_elem)
+template <typename P>
+__device__ __forceinline__ int blockop_value(int op, const x265cu_blk_job& jb, int a, int b)
+{
+    constexpr int depth = PixTraits<P>::depth;
+    constexpr int maxv = PixTraits<P>::maxv;
+    switch (op)
+    {
+    case X265CU_SUB_PS:  return (int)(int16_t)(a - b);
+    case X265CU_ADD_PS:  return clip3i(0, maxv, a + b);
+    case X265CU_PIXELAVG_PP: return (a + b + 1) >> 1;
+    case X265CU_ADDAVG:
+    {
+        constexpr int shift = 14 + 1 - depth;
+        constexpr int offset = (1 << (shift - 1)) + 2 * 8192;
+        return clip3i(0, maxv, (a + b + offset) >> shift);
+    }
+    case X265CU_P2S: return (int)(int16_t)((int)(int16_t)(a << (14 - depth)) - 8192);
+    case X265CU_BLOCKFILL_S: return (int)(int16_t)jb.p0;
+    case X265CU_CPY2DTO1D_SHL: case X265CU_CPY1DTO2D_SHL: return (int)(int16_t)(a << jb.p0);
+    case X265CU_CPY2DTO1D_SHR: case X265CU_CPY1DTO2D_SHR: return (int)(int16_t)((a + (int16_t)(1 << (jb.p0 - 1))) >> jb.p0);
+    case X265CU_WEIGHT_PP: { int16_t v = (int16_t)(a << (14 - depth)); return clip3i(0, maxv, ((jb.p0 * v + jb.p1) >> jb.p2) + jb.p3); }
+    case X265CU_WEIGHT_SP: return clip3i(0, maxv, ((jb.p0 * (a + 8192) + jb.p1) >> jb.p2) + jb.p3);
+    case X265CU_DEQUANT_NORMAL: return (int)(int16_t)clip16((a * jb.p0 + (1 << (jb.p1 - 1))) >> jb.p1);
+    default: return a;                                // the copies
+    }
+}
+
+// 8 consecutive elements of `bytes`-wide type (1: u8, 2: u16 / int16 with `sgn`) at p, 8 x bytes aligned
+__device__ __forceinline__ void blk_load8(const void* __restrict__ p, int bytes, bool sgn, int (&v)[8])
+{
+    if (bytes == 1)
+    {
+        const uint2 w = __ldg((const uint2*)p);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = (int)((w.x >> (8 * k)) & 255u); v[4 + k] = (int)((w.y >> (8 * k)) & 255u); }
+    }
+    else
+    {
+        const uint4 w = __ldg((const uint4*)p);
+        const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            v[2 * k]     = sgn ? (int)(int16_t)(ww[k] & 0xffffu) : (int)(ww[k] & 0xffffu);
+            v[2 * k + 1] = sgn ? (int)(int16_t)(ww[k] >> 16) : (int)(ww[k] >> 16);
+        }
+    }
+}
+__device__ __forceinline__ void blk_store8(void* __restrict__ p, int bytes, const int (&v)[8])
+{
+    if (bytes == 1)
+        *(uint2*)p = make_uint2((uint32_t)(v[0] & 255) | ((uint32_t)(v[1] & 255) << 8) | ((uint32_t)(v[2] & 255) << 16) | ((uint32_t)v[3] << 24),
+                                (uint32_t)(v[4] & 255) | ((uint32_t)(v[5] & 255) << 8) | ((uint32_t)(v[6] & 255) << 16) | ((uint32_t)v[7] << 24));
+    else
+        *(uint4*)p = make_uint4(((uint32_t)v[0] & 0xffffu) | ((uint32_t)v[1] << 16), ((uint32_t)v[2] & 0xffffu) | ((uint32_t)v[3] << 16),
+                                ((uint32_t)v[4] & 0xffffu) | ((uint32_t)v[5] << 16), ((uint32_t)v[6] & 0xffffu) | ((uint32_t)v[7] << 16));
+}
+
 // one block per job (grid-stride over jobs), threads stride over the w*h elements
 template <typename P>
 __global__ void __launch_bounds__(256) k_blockop(int op, void* __restrict__ D, const void* __restrict__ A, const void* __restrict__ B,
@@ -65,6 +149,32 @@ __global__ void __launch_bounds__(256) k_blockop(int op, void* __restrict__ D, c
     {
         const x265cu_blk_job jb = jobs[j];
         const int w = jb.w, cnt = jb.w * jb.h;
+        int kd, ka, kb;
+        blockop_kinds(op, kd, ka, kb);
+        if (kd && (w & 7) == 0)
+        {
+            // element sizes and the 8-element alignment of every operand row
+            const int sd = kd == 1 ? (int)sizeof(P) : 2, sa = ka == 1 ? (int)sizeof(P) : 2, sb = kb == 1 ? (int)sizeof(P) : 2;
+            const uintptr_t pd = (uintptr_t)D + (size_t)jb.d_off * sd, pa = (uintptr_t)A + (size_t)jb.a_off * sa, pb = (uintptr_t)B + (size_t)jb.b_off * sb;
+            bool ok = ((pd | (uintptr_t)((size_t)jb.d_stride * sd)) & (8 * sd - 1)) == 0;
+            if (ka) ok = ok && ((pa | (uintptr_t)((size_t)jb.a_stride * sa)) & (8 * sa - 1)) == 0;
+            if (kb) ok = ok && ((pb | (uintptr_t)((size_t)jb.b_stride * sb)) & (8 * sb - 1)) == 0;
+            if (ok)
+            {
+                const int upr = w >> 3;
+                for (int u = threadIdx.x; u < upr * jb.h; u += blockDim.x)
+                {
+                    const int y = u / upr, x = (u - y * upr) * 8;
+                    int a[8], b[8], v[8];
+                    if (ka) blk_load8((const void*)(pa + ((size_t)y * jb.a_stride + x) * sa), sa, ka == 2, a);
+                    if (kb) blk_load8((const void*)(pb + ((size_t)y * jb.b_stride + x) * sb), sb, kb == 2, b);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = blockop_value<P>(op, jb, ka ? a[k] : 0, kb ? b[k] : 0);
+                    blk_store8((void*)(pd + ((size_t)y * jb.d_stride + x) * sd), sd, v);
+                }
+                continue;
+            }
+        }
         for (int i = threadIdx.x; i < cnt; i += blockDim.x)
         {
             int y = i / w, x = i - y * w;
@@ -120,6 +230,42 @@ __global__ void __launch_bounds__(256) k_lowres_init(const P* __restrict__ src, 
             dc[o + k] = (P)((v12[2 * k + 1] + v12[2 * k + 2] + 1) >> 1);
         }
     }
+}
+
+// 8-bit fast path: a thread produces 8 adjacent lowres pixels of all 4 planes with packed-byte arithmetic: three
+// 16-byte row loads (+ the 17th pixel), VAVGU4 (the reference's (a + b + 1) >> 1 on four bytes at once) for the
+// vertical pairs, PRMT to split even / odd columns, VAVGU4 again, four 8-byte stores.
+__global__ void __launch_bounds__(256) k_lowres_init_u8x8(const uint8_t* __restrict__ src, int sstride, uint8_t* __restrict__ d0, uint8_t* __restrict__ dh,
+                                                          uint8_t* __restrict__ dv, uint8_t* __restrict__ dc, int dstride, int width8, int height)
+{
+    const int xu = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xu >= width8 || y >= height) return;
+    const uint8_t* r0 = src + (int64_t)(2 * y) * sstride + 16 * xu;
+    const uint8_t* r1 = r0 + sstride;
+    const uint8_t* r2 = r1 + sstride;
+    const uint4 a = __ldg((const uint4*)r0), b = __ldg((const uint4*)r1), c = __ldg((const uint4*)r2);
+    const uint32_t a16 = __ldg(r0 + 16), b16 = __ldg(r1 + 16), c16 = __ldg(r2 + 16);
+    const uint32_t A[4] = { a.x, a.y, a.z, a.w }, B[4] = { b.x, b.y, b.z, b.w }, C4[4] = { c.x, c.y, c.z, c.w };
+    uint32_t out[4][2];
+#pragma unroll
+    for (int half = 0; half < 2; half++)
+    {
+        uint32_t V[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) V[i] = half ? __vavgu4(B[i], C4[i]) : __vavgu4(A[i], B[i]);
+        const uint32_t t = half ? (b16 + c16 + 1) >> 1 : (a16 + b16 + 1) >> 1;
+        const uint32_t E0 = __byte_perm(V[0], V[1], 0x6420), O0 = __byte_perm(V[0], V[1], 0x7531);
+        const uint32_t E1 = __byte_perm(V[2], V[3], 0x6420), O1 = __byte_perm(V[2], V[3], 0x7531);
+        const uint32_t ES0 = __byte_perm(E0, E1, 0x4321), ES1 = __byte_perm(E1, t, 0x4321);
+        out[2 * half][0] = __vavgu4(E0, O0);      out[2 * half][1] = __vavgu4(E1, O1);         // even/odd pair: columns 2k, 2k+1
+        out[2 * half + 1][0] = __vavgu4(O0, ES0); out[2 * half + 1][1] = __vavgu4(O1, ES1);    // columns 2k+1, 2k+2
+    }
+    const int64_t o = (int64_t)y * dstride + 8 * xu;
+    *(uint2*)(d0 + o) = make_uint2(out[0][0], out[0][1]);
+    *(uint2*)(dh + o) = make_uint2(out[1][0], out[1][1]);
+    *(uint2*)(dv + o) = make_uint2(out[2][0], out[2][1]);
+    *(uint2*)(dc + o) = make_uint2(out[3][0], out[3][1]);
 }
 
 // replicate left/right edges (rows 0..height-1), then copy first/last rows into the top/bottom margins

@@ -123,18 +123,30 @@ __global__ void __launch_bounds__(LA_WARPS * 32, 1) k_lookahead_cost(const x265c
 {
     extern __shared__ unsigned char la_smem[];
     __shared__ int32_t s_out[LA_WARPS][4];
-    const x265cu_la_job jb = jobs[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    MeShared* sm = (MeShared*)la_smem + warp;
-    for (int i = threadIdx.x; i < h8; i += blockDim.x) jb.rowSatds[i] = 0;
-    if (threadIdx.x < 3) jb.out[threadIdx.x] = 0;
+    // One thread-block CLUSTER per triple: the CTAs of the cluster (1..4, chosen at launch from the diagonal length)
+    // split the CUs of every anti-diagonal, so a diagonal of up to 64 CUs is one round of warps instead of four; the
+    // per-diagonal barrier is the cluster barrier, whose release / acquire pair also publishes the MVs and costs the
+    // other CTAs wrote to global memory.
+    unsigned crank, csize;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    const x265cu_la_job jb = jobs[blockIdx.x / csize];
+    const int lane = threadIdx.x & 31, warp = (int)crank * LA_WARPS + (threadIdx.x >> 5);      // warp index inside the cluster
+    const int nwarps = (int)csize * LA_WARPS;
+    MeShared* sm = (MeShared*)la_smem + (threadIdx.x >> 5);
+    if (crank == 0)
+    {
+        for (int i = threadIdx.x; i < h8; i += blockDim.x) jb.rowSatds[i] = 0;
+        if (threadIdx.x < 3) jb.out[threadIdx.x] = 0;
+    }
     const int ndiag = (w8 - 1) + 2 * (h8 - 1) + 1;
     for (int t = 0; t < ndiag; t++)
     {
-        __syncthreads();                                   // MVs of the previous diagonals are visible
+        // MVs / costs of the previous diagonals are visible to every CTA of the cluster
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
         // CUs on this diagonal: k = 0.. with cuY = h8-1-k, cuX = w8-1-(t-2k)
         const int kmin = max(0, (t - (w8 - 1) + 1) >> 1), kmax = min(h8 - 1, t >> 1);
-        for (int k = kmin + warp; k <= kmax; k += LA_WARPS)
+        for (int k = kmin + warp; k <= kmax; k += nwarps)
         {
             const int cuY = h8 - 1 - k, cuX = w8 - 1 - (t - 2 * k);
             if (cuX < 0 || cuX >= w8) continue;
@@ -195,9 +207,9 @@ __global__ void __launch_bounds__(LA_WARPS * 32, 1) k_lookahead_cost(const x265c
                 c.mvpx = mvpx; c.mvpy = mvpy;
                 mj.qmvp[0] = (int16_t)mvpx; mj.qmvp[1] = (int16_t)mvpy;
                 __syncwarp();
-                me_run_job<P>(c, mj, s_out[warp]);
+                me_run_job<P>(c, mj, s_out[threadIdx.x >> 5]);
                 __syncwarp();
-                int fc = s_out[warp][0], mx = s_out[warp][1], my = s_out[warp][2];
+                int fc = s_out[threadIdx.x >> 5][0], mx = s_out[threadIdx.x >> 5][1], my = s_out[threadIdx.x >> 5][2];
                 __syncwarp();
                 if (skipCost < 64 && skipCost < fc && jb.bidir) { fc = skipCost; mx = 0; my = 0; }
                 if (lane == 0) { *fencCost = fc; fmv[0] = mx; fmv[1] = my; }

@@ -843,17 +843,20 @@ __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, M
     const int merange = j.merange;
     int bmx = st.bmx, bmy = st.bmy, bcost = st.bcost;
     if (j.method == 0)
-    {   // DIA (motion.cpp:822-846)
+    {   // DIA (motion.cpp:822-846): the four neighbours of every step are one burst; the reference's packed compare
+        // ((cost << 4) + tag, smallest wins) is the burst's key
         bcost <<= 4;
         int i = merange;
         do
         {
-            int c0 = me_cost_fpel(c, bmx, bmy - 1), c1 = me_cost_fpel(c, bmx, bmy + 1);
-            int c2 = me_cost_fpel(c, bmx - 1, bmy), c3 = me_cost_fpel(c, bmx + 1, bmy);
-            if (ME_YOK(bmy - 1) && (c0 << 4) + 1 < bcost) bcost = (c0 << 4) + 1;
-            if (ME_YOK(bmy + 1) && (c1 << 4) + 3 < bcost) bcost = (c1 << 4) + 3;
-            if ((c2 << 4) + 4 < bcost) bcost = (c2 << 4) + 4;
-            if ((c3 << 4) + 12 < bcost) bcost = (c3 << 4) + 12;
+            const int k = c.lane & 3;
+            const int px = bmx + (k == 2 ? -1 : k == 3 ? 1 : 0), py = bmy + (k == 0 ? -1 : k == 1 ? 1 : 0);
+            const int tag = k == 0 ? 1 : k == 1 ? 3 : k == 2 ? 4 : 12;
+            const int cost = me_eval_points(c, 4, px, py, false);
+            const bool ok = c.lane < 4 && (k >= 2 || ME_YOK(py));
+            const unsigned key = ok ? (unsigned)((cost << 4) + tag) : 0xffffffffu;
+            const unsigned m = __reduce_min_sync(0xffffffffu, key);
+            if (m < (unsigned)bcost) bcost = (int)m;
             if (!(bcost & 15)) break;
             bmx -= (int)((unsigned)bcost << 28) >> 30;
             bmy -= (int)((unsigned)bcost << 30) >> 30;
@@ -863,21 +866,18 @@ __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, M
         bcost >>= 4;
     }
     else if (j.method == 1)
-    {   // HEX (motion.cpp:848-945)
-        int c0 = me_cost_fpel(c, bmx - 2, bmy), c1 = me_cost_fpel(c, bmx - 1, bmy + 2), c2 = me_cost_fpel(c, bmx + 1, bmy + 2);
-        bcost <<= 3;
-        if (ME_YOK(bmy) && (c0 << 3) + 2 < bcost) bcost = (c0 << 3) + 2;
-        if (ME_YOK(bmy + 2))
+    {   // HEX (motion.cpp:848-945), burst per step: the 6 hexagon points, then 3 new points per move, then the
+        // 8-point square; keys are the reference's (cost << 3) + tag, ties to the smaller tag as in its compare chain
+        const int lane = c.lane;
         {
-            if ((c1 << 3) + 3 < bcost) bcost = (c1 << 3) + 3;
-            if ((c2 << 3) + 4 < bcost) bcost = (c2 << 3) + 4;
-        }
-        c0 = me_cost_fpel(c, bmx + 2, bmy); c1 = me_cost_fpel(c, bmx + 1, bmy - 2); c2 = me_cost_fpel(c, bmx - 1, bmy - 2);
-        if (ME_YOK(bmy) && (c0 << 3) + 5 < bcost) bcost = (c0 << 3) + 5;
-        if (ME_YOK(bmy - 2))
-        {
-            if ((c1 << 3) + 6 < bcost) bcost = (c1 << 3) + 6;
-            if ((c2 << 3) + 7 < bcost) bcost = (c2 << 3) + 7;
+            // tags 2..7 = hex2[1..6]: (-2,0) (-1,2) (1,2) (2,0) (1,-2) (-1,-2)
+            const int k = min(lane, 5);
+            const int px = bmx + c_hex2[k + 1][0], py = bmy + c_hex2[k + 1][1];
+            const int cost = me_eval_points(c, 6, px, py, false);
+            bcost <<= 3;
+            const unsigned key = (lane < 6 && ME_YOK(py)) ? (unsigned)((cost << 3) + k + 2) : 0xffffffffu;
+            const unsigned m = __reduce_min_sync(0xffffffffu, key);
+            if (m < (unsigned)bcost) bcost = (int)m;
         }
         if (bcost & 7)
         {
@@ -887,13 +887,13 @@ __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, M
                 bmx += c_hex2[dir + 1][0]; bmy += c_hex2[dir + 1][1];
                 for (int i = (merange >> 1) - 1; i > 0 && ME_INRANGE(bmx, bmy); i--)
                 {
-                    c0 = me_cost_fpel(c, bmx + c_hex2[dir + 0][0], bmy + c_hex2[dir + 0][1]);
-                    c1 = me_cost_fpel(c, bmx + c_hex2[dir + 1][0], bmy + c_hex2[dir + 1][1]);
-                    c2 = me_cost_fpel(c, bmx + c_hex2[dir + 2][0], bmy + c_hex2[dir + 2][1]);
+                    const int k = min(lane, 2);
+                    const int px = bmx + c_hex2[dir + k][0], py = bmy + c_hex2[dir + k][1];
+                    const int cost = me_eval_points(c, 3, px, py, false);
                     bcost &= ~7;
-                    if (ME_YOK(bmy + c_hex2[dir + 0][1]) && (c0 << 3) + 1 < bcost) bcost = (c0 << 3) + 1;
-                    if (ME_YOK(bmy + c_hex2[dir + 1][1]) && (c1 << 3) + 2 < bcost) bcost = (c1 << 3) + 2;
-                    if (ME_YOK(bmy + c_hex2[dir + 2][1]) && (c2 << 3) + 3 < bcost) bcost = (c2 << 3) + 3;
+                    const unsigned key = (lane < 3 && ME_YOK(py)) ? (unsigned)((cost << 3) + k + 1) : 0xffffffffu;
+                    const unsigned m = __reduce_min_sync(0xffffffffu, key);
+                    if (m < (unsigned)bcost) bcost = (int)m;
                     if (!(bcost & 7)) break;
                     dir += (bcost & 7) - 2;
                     dir = c_mod6m1[dir + 1];
@@ -902,20 +902,18 @@ __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, M
             }
         }
         bcost >>= 3;
-        int dir = 0;
-        int s0 = me_cost_fpel(c, bmx, bmy - 1), s1 = me_cost_fpel(c, bmx, bmy + 1);
-        int s2 = me_cost_fpel(c, bmx - 1, bmy), s3 = me_cost_fpel(c, bmx + 1, bmy);
-        if (ME_YOK(bmy - 1) && s0 < bcost) { bcost = s0; dir = 1; }
-        if (ME_YOK(bmy + 1) && s1 < bcost) { bcost = s1; dir = 2; }
-        if (s2 < bcost) { bcost = s2; dir = 3; }
-        if (s3 < bcost) { bcost = s3; dir = 4; }
-        s0 = me_cost_fpel(c, bmx - 1, bmy - 1); s1 = me_cost_fpel(c, bmx - 1, bmy + 1);
-        s2 = me_cost_fpel(c, bmx + 1, bmy - 1); s3 = me_cost_fpel(c, bmx + 1, bmy + 1);
-        if (ME_YOK(bmy - 1) && s0 < bcost) { bcost = s0; dir = 5; }
-        if (ME_YOK(bmy + 1) && s1 < bcost) { bcost = s1; dir = 6; }
-        if (ME_YOK(bmy - 1) && s2 < bcost) { bcost = s2; dir = 7; }
-        if (ME_YOK(bmy + 1) && s3 < bcost) { bcost = s3; dir = 8; }
-        bmx += c_square1[dir][0]; bmy += c_square1[dir][1];
+        {
+            // square refine: square1[1..8] in order, strict '<' (x is not range-checked by the reference, y is)
+            const int k = min(lane, 7) + 1;
+            const int px = bmx + c_square1[k][0], py = bmy + c_square1[k][1];
+            const int cost = me_eval_points(c, 8, px, py, false);
+            const bool ok = lane < 8 && (c_square1[k][1] == 0 || ME_YOK(py));
+            const unsigned key = ok ? (((unsigned)cost << 5) | (unsigned)lane) : 0xffffffffu;
+            const unsigned m = __reduce_min_sync(0xffffffffu, key);
+            int dir = 0;
+            if (m != 0xffffffffu && (int)(m >> 5) < bcost) { bcost = (int)(m >> 5); dir = (int)(m & 31) + 1; }
+            bmx += c_square1[dir][0]; bmy += c_square1[dir][1];
+        }
     }
     else
     {   // STAR (motion.cpp:1132-1240), written as one loop so that the star pattern, the two-point refinement and

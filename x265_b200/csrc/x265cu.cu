@@ -199,7 +199,13 @@ int x265cu_frame_init_lowres(x265cu_ctx* c, int depth, const void* src, int sstr
                              int dstride, int width, int height, int mx, int my)
 {
     dim3 block(64, 4), grid((width / 4 + 63) / 64 + 1, (height + 3) / 4);
-    if (depth == 8)
+    const uintptr_t dal = (uintptr_t)d0 | (uintptr_t)dh | (uintptr_t)dv | (uintptr_t)dc | (uintptr_t)dstride;
+    if (depth == 8 && (width & 7) == 0 && (((uintptr_t)src | (uintptr_t)sstride) & 15) == 0 && (dal & 7) == 0)
+    {
+        dim3 g8((width / 8 + 63) / 64, (height + 3) / 4);
+        k_lowres_init_u8x8<<<g8, block, 0, c->stream>>>((const uint8_t*)src, sstride, (uint8_t*)d0, (uint8_t*)dh, (uint8_t*)dv, (uint8_t*)dc, dstride, width / 8, height);
+    }
+    else if (depth == 8)
         k_lowres_init<uint8_t><<<grid, block, 0, c->stream>>>((const uint8_t*)src, sstride, (uint8_t*)d0, (uint8_t*)dh, (uint8_t*)dv, (uint8_t*)dc, dstride, width, height);
     else
         k_lowres_init<uint16_t><<<grid, block, 0, c->stream>>>((const uint16_t*)src, sstride, (uint16_t*)d0, (uint16_t*)dh, (uint16_t*)dv, (uint16_t*)dc, dstride, width, height);
@@ -257,15 +263,25 @@ int x265cu_lookahead_cost_batch(x265cu_ctx* c, int depth, const x265cu_la_job* j
 {
     if (n <= 0) return 0;
     const size_t smem = sizeof(MeShared) * LA_WARPS;
+    // cluster size: enough CTAs (of LA_WARPS warps) for the longest anti-diagonal in one round, at most 4
+    const int maxdiag = h8 < (w8 + 1) / 2 ? h8 : (w8 + 1) / 2;
+    int csize = (maxdiag + LA_WARPS - 1) / LA_WARPS;
+    csize = csize >= 4 ? 4 : (csize >= 2 ? 2 : 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n * csize); cfg.blockDim = dim3(LA_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     if (depth == 8)
     {
         CU_CHECK(cudaFuncSetAttribute(k_lookahead_cost<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_lookahead_cost<uint8_t><<<n, LA_WARPS * 32, smem, c->stream>>>(jobs, stride, w8, h8, mvcost);
+        CU_CHECK(cudaLaunchKernelEx(&cfg, k_lookahead_cost<uint8_t>, jobs, stride, w8, h8, mvcost));
     }
     else
     {
         CU_CHECK(cudaFuncSetAttribute(k_lookahead_cost<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_lookahead_cost<uint16_t><<<n, LA_WARPS * 32, smem, c->stream>>>(jobs, stride, w8, h8, mvcost);
+        CU_CHECK(cudaLaunchKernelEx(&cfg, k_lookahead_cost<uint16_t>, jobs, stride, w8, h8, mvcost));
     }
     CU_LAUNCH_CHECK(c);
     return 0;
