@@ -319,6 +319,28 @@ __device__ __forceinline__ int me_subpel_compare_t(const MeCtx<P>& c, int qx, in
 
 // ---- sub-pel evaluation of SMALL PUs (pow2, w and h <= 16): one lane = one 8-pixel (4 for w = 4) row segment ----
 // (row helpers me_hrow / me_vcol / me_vmid: interp.cuh)
+// NPX pixels of a source row segment as ints: one aligned vector load when the rows allow it
+template <typename P, int NPX>
+__device__ __forceinline__ void me_load_fenc(const MeCtx<P>& c, const P* __restrict__ f, int (&v)[NPX])
+{
+    constexpr int NWD = NPX * (int)sizeof(P) / 4;
+    if ((4 << c.lgsegw) >= NPX * (int)sizeof(P))
+    {
+        uint32_t w[NWD];
+        if (NWD == 1) w[0] = __ldg((const uint32_t*)f);
+        else if (NWD == 2) { const uint2 t = __ldg((const uint2*)f); w[0] = t.x; w[NWD - 1] = t.y; }
+        else { const uint4 t = __ldg((const uint4*)f); w[0] = t.x; w[1 % NWD] = t.y; w[2 % NWD] = t.z; w[3 % NWD] = t.w; }
+#pragma unroll
+        for (int x = 0; x < NPX; x++)
+            v[x] = sizeof(P) == 1 ? (int)((w[x >> 2] >> (8 * (x & 3))) & 255u) : (int)((w[x >> 1] >> (16 * (x & 1))) & 65535u);
+    }
+    else
+    {
+#pragma unroll
+        for (int x = 0; x < NPX; x++) v[x] = (int)__ldg(f + x);
+    }
+}
+
 // Up to 4 sub-pel candidates of a SMALL PU, lane i (< n <= 4) owns candidate i (qx, qy) and gets its distortion.
 // Per candidate the arithmetic is exactly subpelCompare's (motion.cpp:1571-1598: luma_hpp / luma_vpp / luma_hvpp
 // = hps(rowExt) + vsp, ipfilter.cpp:79-369) followed by sad or satd (8x4 tiles, 4x4 for w = 4; pixel.cpp:263-297).
@@ -403,9 +425,10 @@ __device__ __forceinline__ int me_subpel_small_t(const MeCtx<P>& c, int n, int q
 #pragma unroll
                 for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 2);
             }
-            const P* f = c.fenc + (ptrdiff_t)row * c.fstride + seg * 8;
+            int fv[NPX];
+            me_load_fenc<P, NPX>(c, c.fenc + (ptrdiff_t)row * c.fstride + seg * 8, fv);
 #pragma unroll
-            for (int x = 0; x < NPX; x++) d[x] = (int)__ldg(f + x) - pr[x];
+            for (int x = 0; x < NPX; x++) d[x] = fv[x] - pr[x];
         }
         else
         {
@@ -516,9 +539,10 @@ __device__ __forceinline__ int me_subpel_big(const MeCtx<P>& c, int qx, int qy, 
 #pragma unroll
                     for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 2);
                 }
-                const P* f = c.fenc + (ptrdiff_t)(y0 + row) * c.fstride + seg * 8;
+                int fv[NPX];
+                me_load_fenc<P, NPX>(c, c.fenc + (ptrdiff_t)(y0 + row) * c.fstride + seg * 8, fv);
 #pragma unroll
-                for (int x = 0; x < NPX; x++) d[x] = (int)__ldg(f + x) - pr[x];
+                for (int x = 0; x < NPX; x++) d[x] = fv[x] - pr[x];
             }
             else
             {
@@ -778,8 +802,10 @@ __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, M
             int cost = me_sad_direct(c, c.ref[0]) + me_mvcost(c, 0, 0);
             if (cost < bcost) { bcost = cost; bmx = 0; bmy = max(min(0, c.maxy), c.miny); }
         }
-        for (int i = 0; i < j.numCand; i++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)                         // static indices keep the job record in registers
         {
+            if (i >= j.numCand) break;
             int mx = max(min((int)j.mvc[2 * i], qmaxx), qminx), my = max(min((int)j.mvc[2 * i + 1], qmaxy), qminy);
             if ((mx | my) && !(mx == pmvx && my == pmvy) && !(mx == bestprex && my == bestprey))
             {
@@ -795,6 +821,10 @@ __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, M
         // the qpel candidates.  The reference skips a candidate equal to the best so far; evaluating it is harmless (its
         // cost equals that best and '<' is strict), so the candidate fold is one arg-min with ties to the earliest.
         const int lane = c.lane, ci = min(max(lane - 3, 0), 3);
+        int mvl = 0;                                        // lane k holds mvc[k]: no dynamic indexing of the job record
+#pragma unroll
+        for (int k = 0; k < 8; k++) mvl = (lane == k) ? (int)j.mvc[k] : mvl;
+        const int candx = __shfl_sync(0xffffffffu, mvl, 2 * ci), candy = __shfl_sync(0xffffffffu, mvl, 2 * ci + 1);
         int qx, qy, tag = lane, dummy = 0;
         bool valid;
         if (lane == 0)      { qx = pmvx; qy = pmvy; valid = true; }
@@ -802,7 +832,7 @@ __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, M
         else if (lane == 2) { qx = 0; qy = 0; valid = (pmvx | pmvy) != 0; }
         else
         {
-            qx = max(min((int)j.mvc[2 * ci], qmaxx), qminx); qy = max(min((int)j.mvc[2 * ci + 1], qmaxy), qminy);
+            qx = max(min(candx, qmaxx), qminx); qy = max(min(candy, qmaxy), qminy);
             valid = lane - 3 < j.numCand && (qx | qy) && !(qx == pmvx && qy == pmvy);
         }
         const int cnt = 3 + j.numCand;
