@@ -197,9 +197,16 @@ __global__ void __launch_bounds__(LA_WARPS * 32, 1) k_lookahead_cost(const x265c
                 if (numc)
                 {
                     int mvpcost = LA_COST_MAX;
-                    for (int idx = 0; idx < numc; idx++)
+                    // bufSATD(lowresMC(mvc)) of all candidates in one burst, then the reference's sequential fold
+                    const int lq = min(lane, numc - 1);
+                    const int cqx = lq == 0 ? mvcx[0] : lq == 1 ? mvcx[1] : lq == 2 ? mvcx[2] : mvcx[3];
+                    const int cqy = lq == 0 ? mvcy[0] : lq == 1 ? mvcy[1] : lq == 2 ? mvcy[2] : mvcy[3];
+                    const int ccost = me_lowres_multi(c, numc, cqx, cqy, true);
+#pragma unroll
+                    for (int idx = 0; idx < 4; idx++)
                     {
-                        const int cost = me_lowres_cost(c, mvcx[idx], mvcy[idx], true);      // bufSATD(lowresMC(mvc))
+                        if (idx >= numc) break;
+                        const int cost = __shfl_sync(0xffffffffu, ccost, idx);
                         if (cost < mvpcost) { mvpcost = cost; mvpx = mvcx[idx]; mvpy = mvcy[idx]; }
                         if (!(mvpx | mvpy) && jb.bidir) skipCost = cost;
                     }

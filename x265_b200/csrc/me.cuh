@@ -652,6 +652,113 @@ __device__ __noinline__ int me_lowres_cost(const MeCtx<P>& c, int qx, int qy, bo
     return warp_satd(c.fenc, c.fstride, r, c.rstride, c.w, c.h, c.lane);
 }
 
+// SATD partial of one row segment: horizontal 4-point Hadamards in registers, vertical ones over the 4 lanes of a
+// tile; returns the halved tile sum in the tile's first lane (0 elsewhere)
+template <int NPX>
+__device__ __forceinline__ int me_seg_satd(int (&d)[NPX], int lane)
+{
+#pragma unroll
+    for (int x = 0; x < NPX; x += 4) had4(d[x], d[x + 1], d[x + 2], d[x + 3]);
+#pragma unroll
+    for (int st = 1; st <= 2; st <<= 1)
+    {
+        const bool up = (lane & st) != 0;
+#pragma unroll
+        for (int x = 0; x < NPX; x++)
+        {
+            const int o = __shfl_xor_sync(0xffffffffu, d[x], st);
+            d[x] = up ? o - d[x] : o + d[x];
+        }
+    }
+    int part = 0;
+#pragma unroll
+    for (int x = 0; x < NPX; x++) part += abs(d[x]);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    return (lane & 3) ? 0 : (part >> 1);                 // one 8x4 (4x4) tile per 4 lanes, halved per tile
+}
+
+// 8 pixels of a reference row at any byte phase
+template <typename P>
+__device__ __forceinline__ void me_load_row8(const P* __restrict__ p, int (&v)[8])
+{
+    if (sizeof(P) == 1)
+    {
+        const uintptr_t a = (uintptr_t)p;
+        const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+        const unsigned sh = ((unsigned)a & 3u) * 8u;
+        const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = sh ? __ldg(ap + 2) : 0u;
+        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = (int)((x0 >> (8 * k)) & 255u); v[4 + k] = (int)((x1 >> (8 * k)) & 255u); }
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (int)__ldg(p + k);
+    }
+}
+
+// lowresQPelCost (lowres.h:94-120) of up to 4 candidates of an 8x8 lowres CU at once: 8 lanes per candidate, one
+// row each; the row of the prediction (one half-pel plane, or the rounded average of the two nearest for odd
+// quarter-pel positions) stays in registers, SATD = two 8x4 tiles through the shuffle butterflies.  Lane i (< n)
+// gets candidate i's distortion.  Same arithmetic as me_lowres_cost.
+template <typename P>
+__device__ __forceinline__ int me_lowres_multi(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+{
+    const int lane = c.lane, slot = lane >> 3, row = lane & 7;
+    const int cand = min(slot, n - 1);
+    const int mqx = __shfl_sync(0xffffffffu, qx, cand), mqy = __shfl_sync(0xffffffffu, qy, cand);
+    int d[8];
+    {
+        const int ha = (mqy & 2) | ((mqx & 2) >> 1);
+        const P* pa = ha == 0 ? c.ref[0] : ha == 1 ? c.ref[1] : ha == 2 ? c.ref[2] : c.ref[3];
+        int a[8];
+        me_load_row8<P>(pa + (mqx >> 2) + (ptrdiff_t)((mqy >> 2) + row) * c.rstride, a);
+        if ((mqx | mqy) & 1)
+        {
+            const int rx = mqx + (mqx & 1), ry = mqy + (mqy & 1);
+            const int hb = (ry & 2) | ((rx & 2) >> 1);
+            const P* pb = hb == 0 ? c.ref[0] : hb == 1 ? c.ref[1] : hb == 2 ? c.ref[2] : c.ref[3];
+            int b[8];
+            me_load_row8<P>(pb + (rx >> 2) + (ptrdiff_t)((ry >> 2) + row) * c.rstride, b);
+#pragma unroll
+            for (int x = 0; x < 8; x++) a[x] = (a[x] + b[x] + 1) >> 1;
+        }
+        int fv[8];
+        me_load_fenc<P, 8>(c, c.fenc + (ptrdiff_t)row * c.fstride, fv);
+#pragma unroll
+        for (int x = 0; x < 8; x++) d[x] = slot < n ? fv[x] - a[x] : 0;
+    }
+    int part = 0;
+    if (!satd)
+    {
+#pragma unroll
+        for (int x = 0; x < 8; x++) part += abs(d[x]);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+    }
+    else part = me_seg_satd<8>(d, lane);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    return __shfl_sync(0xffffffffu, part, (lane << 3) & 31);
+}
+
+// distortion of up to 8 lowres candidates, lane i (< n) owns candidate i
+template <typename P>
+__device__ __forceinline__ int me_lowres_batch(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
+{
+    int out = 0;
+    for (int base = 0; base < n; base += 4)
+    {
+        const int src = min(base + (c.lane & 3), n - 1);
+        const int bqx = __shfl_sync(0xffffffffu, qx, src), bqy = __shfl_sync(0xffffffffu, qy, src);
+        int v = me_lowres_multi(c, min(4, n - base), bqx, bqy, satd);
+        v = __shfl_sync(0xffffffffu, v, (c.lane - base) & 3);
+        if (c.lane >= base && c.lane < base + 4) out = v;
+    }
+    return out;
+}
+
 template <typename P>
 __device__ __forceinline__ int me_qpel_cost(const MeCtx<P>& c, int qx, int qy, bool satd)
 {
@@ -794,13 +901,19 @@ __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, M
     int bprecost, bmx = (pmvx + 2) >> 2, bmy = (pmvy + 2) >> 2, bcost;
     if (c.lowres)
     {
-        bprecost = me_lowres_cost(c, pmvx, pmvy, false);
-        bcost = bprecost;
-        if ((pmvx & 3) | (pmvy & 3)) bcost = me_cost_fpel(c, bmx, bmy);
-        if (pmvx | pmvy)
         {
-            int cost = me_sad_direct(c, c.ref[0]) + me_mvcost(c, 0, 0);
-            if (cost < bcost) { bcost = cost; bmx = 0; bmy = max(min(0, c.maxy), c.miny); }
+            // lane 0 = clipped MVP (qpel), lane 1 = its full-pel rounding, lane 2 = MV 0: one burst of SADs
+            const int l = c.lane;
+            const int bqx = l == 0 ? pmvx : l == 1 ? bmx * 4 : 0, bqy = l == 0 ? pmvy : l == 1 ? bmy * 4 : 0;
+            const int cost = me_lowres_multi(c, 3, bqx, bqy, false);
+            bprecost = __shfl_sync(0xffffffffu, cost, 0);
+            bcost = bprecost;
+            if ((pmvx & 3) | (pmvy & 3)) bcost = __shfl_sync(0xffffffffu, cost, 1) + me_mvcost(c, bmx * 4, bmy * 4);
+            if (pmvx | pmvy)
+            {
+                const int cz = __shfl_sync(0xffffffffu, cost, 2) + me_mvcost(c, 0, 0);
+                if (cz < bcost) { bcost = cz; bmx = 0; bmy = max(min(0, c.maxy), c.miny); }
+            }
         }
 #pragma unroll
         for (int i = 0; i < 4; i++)                         // static indices keep the job record in registers
@@ -1020,25 +1133,29 @@ __device__ __forceinline__ void me_phase3(MeCtx<P>& c, const x265cu_me_job& j, c
         bcost = me_mvcost(c, bx, by);
     else if (c.lowres)
     {
-        int bdir = 0;
-        for (int i = 1; i <= wl[1]; i++)
+        // half-pel round (SAD), SATD at the winner, quarter-pel round (SATD): each round is one burst over the lowres planes
+        for (int rnd = 0; rnd < 2; rnd++)
         {
-            int qx = bx + c_square1[i][0] * 2, qy = by + c_square1[i][1] * 2;
-            if ((qy < qminy) | (qy > qmaxy)) continue;
-            int cost = me_lowres_cost(c, qx, qy, false) + me_mvcost(c, qx, qy);
-            if (cost < bcost) { bcost = cost; bdir = i; }
+            const int dirs = rnd ? wl[3] : wl[1], step = rnd ? 1 : 2;
+            if (rnd)
+            {
+                const int cc = me_lowres_multi(c, 1, bx, by, true);
+                bcost = __shfl_sync(0xffffffffu, cc, 0) + me_mvcost(c, bx, by);
+            }
+            const int i1 = min(c.lane + 1, 8);
+            int qx = bx + c_square1[i1][0] * step, qy = by + c_square1[i1][1] * step, dir = i1, dummy = 0;
+            const bool valid = c.lane < dirs && !((qy < qminy) | (qy > qmaxy));
+            const int n = me_compact(valid, dirs, qx, qy, dir, dummy);
+            int cost = me_lowres_batch(c, n, qx, qy, rnd != 0);
+            if (c.lane < n) cost += me_mvcost(c, qx, qy);
+            int bdir = 0;
+            if (n > 0)
+            {
+                const unsigned key = (unsigned)me_argmin(n, cost, c.lane);
+                if ((int)(key >> 5) < bcost) { bcost = (int)(key >> 5); bdir = __shfl_sync(0xffffffffu, dir, (int)(key & 31)); }
+            }
+            bx += c_square1[bdir][0] * step; by += c_square1[bdir][1] * step;
         }
-        bx += c_square1[bdir][0] * 2; by += c_square1[bdir][1] * 2;
-        bcost = me_lowres_cost(c, bx, by, true) + me_mvcost(c, bx, by);
-        bdir = 0;
-        for (int i = 1; i <= wl[3]; i++)
-        {
-            int qx = bx + c_square1[i][0], qy = by + c_square1[i][1];
-            if ((qy < qminy) | (qy > qmaxy)) continue;
-            int cost = me_lowres_cost(c, qx, qy, true) + me_mvcost(c, qx, qy);
-            if (cost < bcost) { bcost = cost; bdir = i; }
-        }
-        bx += c_square1[bdir][0]; by += c_square1[bdir][1];
     }
     else
     {
