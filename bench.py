@@ -301,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"kernel": "k_me<P,2,-1> (integer search phase of the batched motionEstimate, one warp per PU x ref)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(me_bytes), "kernel_ms": float(me_ms),
-                         "note": "instruction-issue bound, not memory bound: ~380 SAD candidates per job against 88 B of compulsory traffic, planes L2-resident; ncu: 59 % of issue slots busy, DRAM traffic = 1.09 x algorithmic bytes (traffic = bytes per launch from profiles/me_r1_traffic.json); see DESIGN.md section 5, profiles/launches_r1.md, profiles/me_r1_ncu.md"},
+                         "note": "not HBM bound: ~380 SAD candidates per job against 88 B of compulsory traffic, planes L2-resident; ncu: 94 % of l1tex throughput (unaligned candidate-row gathers), 56-59 % of issue slots busy, DRAM traffic = 1.09 x algorithmic bytes (traffic = bytes per launch from profiles/me_r1_traffic.json); see DESIGN.md section 5, profiles/launches_r1.md, profiles/me_r1_ncu.md"},
             "stages_ms": {"me_stage": float(stage[0]), "me_prechecks": float(phases[0]), "me_integer_search": float(phases[1]), "me_subpel": float(phases[2]), "residual": float(stage[1]), "intra": float(stage[2])},
             "stage_rooflines": {
                 "k_cu_residual": {"achieved": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9, "unit": "GB/s", "frac": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9 / peak},
