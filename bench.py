@@ -15,6 +15,10 @@ intra SA8D search (DESIGN.md "Frame analysis workload").  2040 CTUs per frame.
 Multi-GPU (torchrun, one process per GPU): the frames of a mini-GOP share one reference set, so each rank
 analyses its own frame (weak scaling) and the only exchange is an NCCL broadcast of the newest
 reconstructed reference plane from its owner rank, once per step.
+
+  --shard rows : the other partition of SURVEY 8(e) (BASELINE configs[4]): ONE frame per step, its CTU rows dealt
+          to the ranks (x265cu_analyser_run_rows), every owner broadcasting its reconstructed rows afterwards
+          (strong scaling; value = CTUs of the frame / max-over-ranks time).  Not the default line.
 """
 import argparse
 import ctypes as C
@@ -162,7 +166,12 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config():
+def workload_config(rows=False):
+    if rows:
+        c = workload_config()
+        c["frames_per_step"] = "1 per step, CTU rows sharded over the GPUs (contiguous row blocks)"
+        c["exchange"] = "NCCL broadcast of every owner's reconstructed CTU rows (one luma plane in total) per step (N>1 only)"
+        return c
     return {"workload": "3840x2160 8-bit preset slow: full ME + sub-pel interp + DCT/quant + intra primitives on device (BASELINE configs[2])",
             "ctus_per_frame": CTUS_PER_FRAME, "refs": NREFS, "search": "star", "merange": MERANGE, "subme": SUBME, "rect": RECT, "qp": QP,
             "pu_jobs_per_frame": None, "frames_per_step": "1 per GPU", "l2": "256 MiB memset between timed steps (untimed) + >300 MB per-step working set",
@@ -194,7 +203,9 @@ def run_ours(args, rank, world, local_rank):
     # synthetic clip (BASELINE.md generator): refs = frames 3..0, this rank's current frame = 4 + rank
     for r in range(NREFS):
         an.set_ref(r, gen_luma(W, H, NREFS - 1 - r))
-    cur = gen_luma(W, H, NREFS + shard.frame_of(0, rank, world))
+    rows_mode = args.shard == "rows"
+    cur = gen_luma(W, H, NREFS + (0 if rows_mode else shard.frame_of(0, rank, world)))
+    my_rows = shard.row_blocks(an.ctu_rows, rank, world, "block") if rows_mode else [(0, an.ctu_rows)]
     field = make_field(W, H, NREFS)
     # pinned host buffers: these are what the user hands to the public call
     pin = lib.L.x265cu_host_alloc(W * H)
@@ -206,14 +217,29 @@ def run_ours(args, rank, world, local_rank):
     flush = lib.alloc(256 << 20)
     ref0 = None
     if world > 1:
-        ptr, stride = an.ref_plane_ptr(0)
+        ptr, stride = an.recon_plane_ptr(1) if rows_mode else an.ref_plane_ptr(0)
         base = ptr - (MARGIN_Y * stride + MARGIN_X)
         ref0 = plane_as_tensor(torch, base, stride * (H + 2 * MARGIN_Y), dev)
 
     def exchange(step):
-        if world > 1:
+        if world > 1 and not rows_mode:
             shard.exchange_ref(dist, ref0, step, world)     # newest reconstructed reference plane from its owner
             torch.cuda.current_stream().synchronize()
+
+    def exchange_rows():
+        # rows mode: every owner publishes the CTU rows it reconstructed (CU-size-32 recon plane)
+        if world > 1 and rows_mode:
+            lib.sync()
+            shard.exchange_rows(dist, ref0, an.ctu_rows, world, H, an.stride, MARGIN_Y)
+            torch.cuda.current_stream().synchronize()
+
+    def analyse_e2e():
+        for r0, r1 in my_rows:
+            an.analyse_rows(h_fenc, h_field, r0, r1)
+
+    def run_resident():
+        for r0, r1 in my_rows:
+            an.run_rows(r0, r1, 7)
 
     def barrier():
         if world > 1:
@@ -223,7 +249,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- warm-up (both paths) ----
     for s in range(args.warmup):
         exchange(s)
-        an.analyse(h_fenc, h_field)
+        analyse_e2e()
+        exchange_rows()
     an.load_inputs(h_fenc, h_field)
     lib.sync()
     sampler = ClockSampler(local_rank)
@@ -240,8 +267,13 @@ def run_ours(args, rank, world, local_rank):
         exchange(s)
         t_ex = (time.perf_counter() - t_ex0) * 1000.0 if world > 1 else 0.0
         lib.timer_begin()
-        an.run_resident(7)
-        res_ms.append(lib.timer_end() + t_ex)
+        run_resident()
+        t_k = lib.timer_end()
+        t_ex0 = time.perf_counter()
+        exchange_rows()
+        if world > 1 and rows_mode:
+            t_ex += (time.perf_counter() - t_ex0) * 1000.0
+        res_ms.append(t_k + t_ex)
         stage += np.array(an.stage_ms())
         phases += np.array(lib.me_phase_ms())
     barrier()
@@ -253,7 +285,8 @@ def run_ours(args, rank, world, local_rank):
     t0 = time.perf_counter()
     for s in range(args.steps):
         exchange(s)
-        an.analyse(h_fenc, h_field)
+        analyse_e2e()
+        exchange_rows()
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) * 1000.0
     barrier()
@@ -267,7 +300,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         stage /= args.steps
         phases /= args.steps
-        units = CTUS_PER_FRAME * world * args.steps
+        units = CTUS_PER_FRAME * (1 if rows_mode else world) * args.steps
         value = units / (t_res / 1000.0)
         e2e = units / (t_e2e / 1000.0)
         peak, peak_src = peaks()
@@ -276,7 +309,9 @@ def run_ours(args, rank, world, local_rank):
         # dominant kernel: k_me<P,2,-1>, the integer-search launch of the five motion-estimation launches.
         # Algorithmic (compulsory) bytes per launch: source plane + each reference plane
         # read once + per job the 40 B job record and the 24 B phase state read and written.
-        me_bytes = plane * (1 + NREFS) + an.njobs * (40 + 24 + 24)
+        my_jobs = sum(an.row_range(r0, r1)[1] for r0, r1 in my_rows)
+        my_share = sum(r1 - r0 for r0, r1 in my_rows) / float(an.ctu_rows)
+        me_bytes = int(plane * (1 + NREFS) * my_share) + my_jobs * (40 + 24 + 24)
         me_ms = phases[1]
         achieved = me_bytes / (me_ms / 1000.0) / 1e9
         # DRAM bytes of that kernel from the committed ncu capture of this same command (profiles/launches_r1.md)
@@ -287,16 +322,16 @@ def run_ours(args, rank, world, local_rank):
                 traffic = float(tr["traffic_bytes_per_launch"])
         except Exception:
             pass
-        cfg = workload_config()
+        cfg = workload_config(rows_mode)
         cfg["pu_jobs_per_frame"] = an.njobs
         sizes = {"resid_bytes": plane * 2 + an.ncoef * 2 + 4 * plane, "intra_bytes": plane + an.ncu * 36 * 4}
         line = {
             "metric": "2160p preset-slow CTU-analysis throughput", "value": value, "unit": "CTUs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_res / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+            "scaling": "strong" if rows_mode else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "CTUs/s", "ms_per_step": t_e2e / args.steps,
-                    "h2d_bytes_per_step": int(an.h2d_bytes(field)), "d2h_bytes_per_step": int(an.d2h_bytes())},
+                    "h2d_bytes_per_step": int(an.h2d_bytes(field)), "d2h_bytes_per_step": int(sum(an.d2h_bytes_rows(r0, r1) for r0, r1 in my_rows))},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_me<P,2,-1> (integer search phase of the batched motionEstimate, one warp per PU x ref)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -336,6 +371,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard", default="frames", choices=["frames", "rows"],
+                    help="N>1 partition: a frame per GPU (default, weak scaling) or the CTU rows of one frame per GPU (strong scaling)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

@@ -187,6 +187,18 @@ int x265cu_analyser_stage_ms(x265cu_analyser*, float ms[4]);          /* device 
 void* x265cu_analyser_ref_plane(x265cu_analyser*, int idx, int* stride); /* device address of ref idx's pixel (0,0) */
 int x265cu_analyser_ref_updated(x265cu_analyser*, int idx);            /* re-extend borders after writing the plane in place */
 int x265cu_analyser_fetch(x265cu_analyser*, int what, void* host);    /* parity/debug access to resident results */
+/* CTU-row shards (BASELINE configs[4]: WPP CTU rows sharded per GPU; the reference enables row r once the reference
+ * rows it needs are reconstructed, frameencoder.cpp:850-868, producer side framefilter.cpp:664).  All job / CU / TU
+ * lists are in CTU raster order, so rows [ctuRow0, ctuRow1) are one contiguous slice of every result array
+ * (x265cu_analyser_row_range); run_rows / analyse_rows compute exactly that slice, bit-identical to the same
+ * entries of a full-frame run.  `out` arrays stay full-frame sized. */
+int x265cu_analyser_ctu_rows(x265cu_analyser*);
+int x265cu_analyser_row_range(x265cu_analyser*, int ctuRow0, int ctuRow1, int* job0, int* njobs, int* cu0, int* ncu);
+int x265cu_analyser_run_rows(x265cu_analyser*, int stages, int ctuRow0, int ctuRow1);
+int x265cu_analyser_analyse_rows(x265cu_analyser*, const void* fenc_host, int host_stride, const int16_t* field_host,
+                                 int stages, int ctuRow0, int ctuRow1, x265cu_analysis_out* out);
+void* x265cu_analyser_recon_plane(x265cu_analyser*, int depthIdx /* 0..3 = CU 64,32,16,8 */, int* stride);
+int x265cu_analyser_recon_to_ref(x265cu_analyser*, int depthIdx, int refIdx, int ctuRow0, int ctuRow1);
 
 /* ---------- lookahead frame costs (BASELINE configs[1]; slicetype.cpp:696-805, 3115-3388) ----------
  * All pointers are device pointers.  Planes are the 4 lowres hpel planes of a frame (origin pixel,

@@ -66,3 +66,68 @@ def test_frame_analysis(cu, depth, noise, size):
         assert np.array_equal(got, exp), "recon depth %d" % d
     assert np.array_equal(an.intra_cost, want["intra_cost"])
     an.close()
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("mode,world", [("block", 2), ("cyclic", 2), ("block", 3)])
+def test_row_shards_equal_full_frame(cu, depth, mode, world):
+    """CTU-row shards (x265cu_analyser_*_rows): the shards' slices, computed by separate launches in any order,
+    are bit-identical to the same entries of a full-frame run, and the recon rows promoted to a reference
+    reproduce the full-frame reconstruction (sharding changes placement, never arithmetic)."""
+    from x265_b200 import shard
+    qp = 30
+    W, H = 200, 200                                   # 4 CTU rows, the last one 8 pixels high
+    wl = Workload(W, H, depth=depth, numRefs=2, method=3, subme=3, merange=57, rect=1, qp=qp, noise=True)
+    full = run_gpu(cu, wl, qp)
+    want = {k: np.array(getattr(full, k)) for k in ("me_packed", "cu_sse", "cu_numsig", "cu_ref", "intra_cost")}
+    want_coef = full.fetch("coef")
+    want_recon = [full.fetch("recon%d" % d) for d in range(4)]
+    nrows = full.ctu_rows
+    assert nrows == 4
+    full.close()
+
+    import x265_b200
+    p = wl.params
+    an = x265_b200.Analyser(cu, W, H, depth=depth, numRefs=p["numRefs"], method=p["method"], subme=p["subme"],
+                            merange=p["merange"], rect=p["rect"], qp=qp, lam=lambda_for(qp, depth))
+    for r, ref in enumerate(wl.refs):
+        an.set_ref(r, ref[MARGIN_Y:MARGIN_Y + H, MARGIN_X:MARGIN_X + W])
+    fenc = np.ascontiguousarray(wl.fenc[MARGIN_Y:MARGIN_Y + H, MARGIN_X:MARGIN_X + W])
+    for k in want:
+        getattr(an, k)[...] = 0
+    # the shards of all "ranks", highest rank first (order must not matter)
+    seen_jobs = 0
+    for g in reversed(range(world)):
+        for r0, r1 in shard.row_blocks(nrows, g, world, mode):
+            an.analyse_rows(fenc, wl.field, r0, r1)
+            j0, nj, c0, nc = an.row_range(r0, r1)
+            seen_jobs += nj
+            assert np.array_equal(an.me_packed[j0:j0 + nj], want["me_packed"][j0:j0 + nj]), (g, r0, r1)
+            assert an.d2h_bytes_rows(r0, r1) == nj * 8 + nc * 160
+    assert seen_jobs == an.njobs
+    for k in want:
+        assert np.array_equal(getattr(an, k), want[k]), k
+    assert np.array_equal(an.fetch("coef"), want_coef)
+    for d in range(4):
+        got = an.fetch("recon%d" % d).reshape(wl.fenc.shape)[MARGIN_Y:MARGIN_Y + H, MARGIN_X:MARGIN_X + W]
+        exp = want_recon[d].reshape(wl.fenc.shape)[MARGIN_Y:MARGIN_Y + H, MARGIN_X:MARGIN_X + W]
+        assert np.array_equal(got, exp), "recon depth %d" % d
+    # promote the reconstructed rows (CU size 16 plane) to reference 1, row block by row block, then re-extend
+    for g in range(world):
+        for r0, r1 in shard.row_blocks(nrows, g, world, mode):
+            an.recon_to_ref(2, 1, r0, r1)
+    an.ref_updated(1)
+    ptr, stride = an.ref_plane_ptr(1)
+    assert stride == wl.stride
+    es = 1 if depth == 8 else 2
+    buf = np.zeros(stride * (H + 2 * MARGIN_Y), an.dtype)
+    base = ptr - (MARGIN_Y * stride + MARGIN_X) * es
+    cu.check(cu.L.x265cu_d2h(cu.ctx, buf.ctypes.data, base, buf.nbytes)); cu.sync()
+    newref = buf.reshape(wl.fenc.shape)
+    rec = want_recon[2].reshape(wl.fenc.shape)[MARGIN_Y:MARGIN_Y + H, MARGIN_X:MARGIN_X + W]
+    assert np.array_equal(newref[MARGIN_Y:MARGIN_Y + H, MARGIN_X:MARGIN_X + W], rec)
+    # borders replicated like extendPicBorder (pixel.cpp:1027-1041)
+    vw = W + 2 * MARGIN_X
+    padded = np.pad(rec, ((MARGIN_Y, MARGIN_Y), (MARGIN_X, MARGIN_X)), mode="edge")
+    assert np.array_equal(newref[:, :vw], padded)
+    an.close()

@@ -54,3 +54,39 @@ def test_frame_dealing_is_a_partition():
         frames = sorted(shard.frame_of(s, r, world) for s in range(5) for r in range(world))
         assert frames == list(range(5 * world))
         assert [shard.ref_owner(s, world) for s in range(world)] == list(range(world))
+
+
+def _row_worker(rank, world, port, ret, mode):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    H, stride, my, nrows = 136, 448, 80, 3          # a 200x136 picture: 3 CTU rows, the last one 8 pixels high
+    truth = torch.from_numpy(np.random.default_rng(7).integers(0, 256, stride * (H + 2 * my)).astype(np.uint8))
+    plane = torch.zeros_like(truth)
+    for r0, r1 in shard.row_blocks(nrows, rank, world, mode):      # a rank holds only the rows it reconstructed
+        b0, b1 = shard.band_slice(r0, r1, H, stride, my)
+        plane[b0:b1] = truth[b0:b1]
+    shard.exchange_rows(dist, plane, nrows, world, H, stride, my, mode=mode)
+    lo, hi = my * stride, (my + H) * stride
+    ok = bool(torch.equal(plane[lo:hi], truth[lo:hi])) and int(plane[:lo].sum()) == 0 and int(plane[hi:].sum()) == 0
+    t = torch.tensor([1 if ok else 0]); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    ret[rank] = int(t.item())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["block", "cyclic"])
+def test_row_shard_exchange_gloo(mode):
+    world = 2
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_row_worker, args=(world, _free_port(), ret, mode), nprocs=world, join=True)
+    assert all(ret[r] == 1 for r in range(world))
+
+
+@pytest.mark.parametrize("mode", ["block", "cyclic"])
+def test_row_blocks_are_a_partition(mode):
+    for nrows in (1, 3, 34, 68):
+        for world in (1, 2, 4, 8):
+            rows = sorted(r for g in range(world) for r0, r1 in shard.row_blocks(nrows, g, world, mode) for r in range(r0, r1))
+            assert rows == list(range(nrows))
+            assert all(shard.row_owner(r, nrows, world, mode) in range(world) for r in range(nrows))
+            sizes = [sum(r1 - r0 for r0, r1 in shard.row_blocks(nrows, g, world, mode)) for g in range(world)]
+            assert max(sizes) - min(sizes) <= 1

@@ -24,6 +24,9 @@ struct x265cu_analyser
     uint8_t* h_fenc; int16_t* h_field;
     cudaEvent_t ev[5]; int ev_valid;      // stage boundaries of the last an_run (ME build+search+pack | residual | intra)
     std::vector<PuDesc> pus; std::vector<CuDesc> cus; std::vector<TuDesc> tus; std::vector<int32_t> cu_jobs;
+    // first PU job / CU / TU of every CTU row (+ one past the end): the lists are in CTU raster order, so a CTU-row
+    // range [r0, r1) is one contiguous slice of each list (what a WPP row shard owns, frameencoder.cpp:850-868)
+    int ctuRows; std::vector<int> rowJob, rowCu, rowTu;
 };
 
 static const int AN_MARGIN_X = 96, AN_MARGIN_Y = 80;       // picyuv.cpp:87-88 with maxCUSize 64
@@ -34,7 +37,10 @@ static void an_build_geometry(x265cu_analyser* a)
     // CU list: CTU raster, sizes 64..8, raster inside the CTU; CUs must lie fully inside the picture
     const int ctuW = (W + 63) / 64, ctuH = (H + 63) / 64;
     int64_t coefOff = 0;
+    a->ctuRows = ctuH;
     for (int cty = 0; cty < ctuH; cty++)
+    {
+        a->rowJob.push_back((int)a->pus.size()); a->rowCu.push_back((int)a->cus.size()); a->rowTu.push_back((int)a->tus.size());
         for (int ctx = 0; ctx < ctuW; ctx++)
         {
             const size_t cuBase = a->cus.size();
@@ -84,6 +90,8 @@ static void an_build_geometry(x265cu_analyser* a)
                         }
             }
         }
+    }
+    a->rowJob.push_back((int)a->pus.size()); a->rowCu.push_back((int)a->cus.size()); a->rowTu.push_back((int)a->tus.size());
     a->njobs = (int)a->pus.size(); a->ncu = (int)a->cus.size(); a->ntu = (int)a->tus.size(); a->ncoef = coefOff;
 }
 
@@ -94,47 +102,52 @@ template <typename T> static T* an_upload(x265cu_ctx* c, const std::vector<T>& v
     return d;
 }
 
-static int an_run(x265cu_analyser* a, int stages)
+// Runs the stages over the CTU rows [r0, r1).  Every list is sliced by pointer offset only: PU jobs, ME results and
+// the intra table are indexed by the slice-local index inside the kernels, CU / TU records carry absolute indices.
+static int an_run(x265cu_analyser* a, int stages, int r0, int r1)
 {
     x265cu_ctx* c = a->ctx;
     const int depth = a->p.depth;
-    const size_t es = depth == 8 ? 1 : 2;
-    (void)es;
+    if (r0 < 0 || r1 > a->ctuRows || r0 >= r1) { x265cu_set_error("analyser: bad CTU row range", cudaErrorInvalidValue, __FILE__, __LINE__); return -1; }
+    const int job0 = a->rowJob[r0], nj = a->rowJob[r1] - job0;
+    const int cu0 = a->rowCu[r0], ncu = a->rowCu[r1] - cu0;
+    const int tu0 = a->rowTu[r0], ntu = a->rowTu[r1] - tu0;
     a->ev_valid = stages;
     CU_CHECK(cudaEventRecord(a->ev[0], c->stream));
-    if (stages & 1)
+    if ((stages & 1) && nj > 0)
     {
-        k_build_me_jobs<<<(a->njobs + 255) / 256, 256, 0, c->stream>>>(a->d_pus, a->njobs, a->d_field, a->fw, a->fh, a->p.width, a->p.height,
-                                                                       a->stride, a->p.method, a->p.subme, a->p.merange, a->d_jobs);
+        k_build_me_jobs<<<(nj + 255) / 256, 256, 0, c->stream>>>(a->d_pus + job0, nj, a->d_field, a->fw, a->fh, a->p.width, a->p.height,
+                                                                 a->stride, a->p.method, a->p.subme, a->p.merange, a->d_jobs + job0);
         CU_LAUNCH_CHECK(c);
         if (launch_me(c, depth, a->d_fenc + a->orgBytes, a->stride, (const void* const*)a->d_refTable, a->stride, 0,
-                      a->d_mvcost + a->mvrange, a->d_jobs, a->njobs, a->d_me_out, c->d_counter)) return -1;
+                      a->d_mvcost + a->mvrange, a->d_jobs + job0, nj, a->d_me_out + (size_t)job0 * 4, c->d_counter)) return -1;
         CU_CHECK(cudaEventRecord(a->ev[4], c->stream));      // ME search kernel alone ends here
-        k_pack_me<<<(a->njobs + 255) / 256, 256, 0, c->stream>>>(a->d_me_out, a->njobs, a->d_me_packed);
+        k_pack_me<<<(nj + 255) / 256, 256, 0, c->stream>>>(a->d_me_out + (size_t)job0 * 4, nj, a->d_me_packed + job0);
         CU_LAUNCH_CHECK(c);
     }
+    else if (stages & 1) CU_CHECK(cudaEventRecord(a->ev[4], c->stream));
     CU_CHECK(cudaEventRecord(a->ev[1], c->stream));
-    if (stages & 2)
+    if ((stages & 2) && ntu > 0)
     {
-        CU_CHECK(cudaMemsetAsync(a->d_cu_sse, 0, sizeof(unsigned long long) * a->ncu, c->stream));
-        CU_CHECK(cudaMemsetAsync(a->d_cu_numsig, 0, sizeof(uint32_t) * a->ncu, c->stream));
-        int blocks = a->ntu < c->sm_count * 8 ? a->ntu : c->sm_count * 8;
+        CU_CHECK(cudaMemsetAsync(a->d_cu_sse + cu0, 0, sizeof(unsigned long long) * ncu, c->stream));
+        CU_CHECK(cudaMemsetAsync(a->d_cu_numsig + cu0, 0, sizeof(uint32_t) * ncu, c->stream));
+        int blocks = ntu < c->sm_count * 8 ? ntu : c->sm_count * 8;
         if (depth == 8)
             k_cu_residual<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)(a->d_fenc + a->orgBytes), (const uint8_t* const*)a->d_refTable, a->stride,
-                a->d_cus, a->d_tus, a->ntu, a->d_cu_jobs, a->p.numRefs, a->d_me_out, a->p.qp, a->d_coef, (uint8_t* const*)a->d_reconTable,
+                a->d_cus, a->d_tus + tu0, ntu, a->d_cu_jobs, a->p.numRefs, a->d_me_out, a->p.qp, a->d_coef, (uint8_t* const*)a->d_reconTable,
                 a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref);
         else
             k_cu_residual<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)(a->d_fenc + a->orgBytes), (const uint16_t* const*)a->d_refTable, a->stride,
-                a->d_cus, a->d_tus, a->ntu, a->d_cu_jobs, a->p.numRefs, a->d_me_out, a->p.qp, a->d_coef, (uint16_t* const*)a->d_reconTable,
+                a->d_cus, a->d_tus + tu0, ntu, a->d_cu_jobs, a->p.numRefs, a->d_me_out, a->p.qp, a->d_coef, (uint16_t* const*)a->d_reconTable,
                 a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref);
         CU_LAUNCH_CHECK(c);
     }
     CU_CHECK(cudaEventRecord(a->ev[2], c->stream));
-    if (stages & 4)
+    if ((stages & 4) && ncu > 0)
     {
-        int blocks = a->ncu < c->sm_count * 8 ? a->ncu : c->sm_count * 8;
-        if (depth == 8) k_intra_search<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)(a->d_fenc + a->orgBytes), a->stride, a->d_cus, a->ncu, a->d_intra);
-        else            k_intra_search<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)(a->d_fenc + a->orgBytes), a->stride, a->d_cus, a->ncu, a->d_intra);
+        int blocks = ncu < c->sm_count * 8 ? ncu : c->sm_count * 8;
+        if (depth == 8) k_intra_search<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)(a->d_fenc + a->orgBytes), a->stride, a->d_cus + cu0, ncu, a->d_intra + (size_t)cu0 * 36);
+        else            k_intra_search<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)(a->d_fenc + a->orgBytes), a->stride, a->d_cus + cu0, ncu, a->d_intra + (size_t)cu0 * 36);
         CU_LAUNCH_CHECK(c);
     }
     CU_CHECK(cudaEventRecord(a->ev[3], c->stream));
@@ -240,24 +253,46 @@ int x265cu_analyser_load_inputs(x265cu_analyser* a, const void* fenc_host, int h
     return 0;
 }
 
-int x265cu_analyser_run_resident(x265cu_analyser* a, int stages) { return an_run(a, stages); }
+int x265cu_analyser_run_resident(x265cu_analyser* a, int stages) { return an_run(a, stages, 0, a->ctuRows); }
+
+// ---- CTU-row shards (the WPP row partition of SURVEY 8(e): frameencoder.cpp:850-868 enables row r once the
+// reference rows it needs are reconstructed; a rank owns a set of CTU rows and analyses exactly those) ----
+int x265cu_analyser_ctu_rows(x265cu_analyser* a) { return a->ctuRows; }
+
+int x265cu_analyser_row_range(x265cu_analyser* a, int ctuRow0, int ctuRow1, int* job0, int* njobs, int* cu0, int* ncu)
+{
+    if (ctuRow0 < 0 || ctuRow1 > a->ctuRows || ctuRow0 > ctuRow1) return -1;
+    *job0 = a->rowJob[ctuRow0]; *njobs = a->rowJob[ctuRow1] - a->rowJob[ctuRow0];
+    *cu0 = a->rowCu[ctuRow0];   *ncu = a->rowCu[ctuRow1] - a->rowCu[ctuRow0];
+    return 0;
+}
+
+int x265cu_analyser_run_rows(x265cu_analyser* a, int stages, int ctuRow0, int ctuRow1) { return an_run(a, stages, ctuRow0, ctuRow1); }
+
+// `out` arrays are always full-frame sized; a row shard fills only the entries of its own rows.
+int x265cu_analyser_analyse_rows(x265cu_analyser* a, const void* fenc_host, int host_stride, const int16_t* field_host, int stages,
+                                 int ctuRow0, int ctuRow1, x265cu_analysis_out* out)
+{
+    x265cu_ctx* c = a->ctx;
+    if (x265cu_analyser_load_inputs(a, fenc_host, host_stride, field_host)) return -1;
+    if (an_run(a, stages, ctuRow0, ctuRow1)) return -1;
+    if (out)
+    {
+        const size_t j0 = a->rowJob[ctuRow0], nj = a->rowJob[ctuRow1] - j0, c0 = a->rowCu[ctuRow0], nc = a->rowCu[ctuRow1] - c0;
+        if (out->me_packed && nj) CU_CHECK(cudaMemcpyAsync(out->me_packed + 2 * j0, a->d_me_packed + j0, sizeof(int2) * nj, cudaMemcpyDeviceToHost, c->stream));
+        if (out->cu_sse && nc) CU_CHECK(cudaMemcpyAsync(out->cu_sse + c0, a->d_cu_sse + c0, sizeof(uint64_t) * nc, cudaMemcpyDeviceToHost, c->stream));
+        if (out->cu_numsig && nc) CU_CHECK(cudaMemcpyAsync(out->cu_numsig + c0, a->d_cu_numsig + c0, sizeof(uint32_t) * nc, cudaMemcpyDeviceToHost, c->stream));
+        if (out->cu_ref && nc) CU_CHECK(cudaMemcpyAsync(out->cu_ref + c0, a->d_cu_ref + c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, c->stream));
+        if (out->intra_cost && nc) CU_CHECK(cudaMemcpyAsync(out->intra_cost + 36 * c0, a->d_intra + 36 * c0, sizeof(uint32_t) * 36 * nc, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
 
 int x265cu_analyser_analyse(x265cu_analyser* a, const void* fenc_host, int host_stride, const int16_t* field_host, int stages,
                             x265cu_analysis_out* out)
 {
-    x265cu_ctx* c = a->ctx;
-    if (x265cu_analyser_load_inputs(a, fenc_host, host_stride, field_host)) return -1;
-    if (an_run(a, stages)) return -1;
-    if (out)
-    {
-        if (out->me_packed) CU_CHECK(cudaMemcpyAsync(out->me_packed, a->d_me_packed, sizeof(int2) * a->njobs, cudaMemcpyDeviceToHost, c->stream));
-        if (out->cu_sse) CU_CHECK(cudaMemcpyAsync(out->cu_sse, a->d_cu_sse, sizeof(uint64_t) * a->ncu, cudaMemcpyDeviceToHost, c->stream));
-        if (out->cu_numsig) CU_CHECK(cudaMemcpyAsync(out->cu_numsig, a->d_cu_numsig, sizeof(uint32_t) * a->ncu, cudaMemcpyDeviceToHost, c->stream));
-        if (out->cu_ref) CU_CHECK(cudaMemcpyAsync(out->cu_ref, a->d_cu_ref, sizeof(int32_t) * a->ncu, cudaMemcpyDeviceToHost, c->stream));
-        if (out->intra_cost) CU_CHECK(cudaMemcpyAsync(out->intra_cost, a->d_intra, sizeof(uint32_t) * 36 * a->ncu, cudaMemcpyDeviceToHost, c->stream));
-    }
-    CU_CHECK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return x265cu_analyser_analyse_rows(a, fenc_host, host_stride, field_host, stages, 0, a->ctuRows, out);
 }
 
 // per-stage device time of the last run (ms): [0] ME stage (job build + search + pack), [1] residual,
@@ -284,6 +319,27 @@ int x265cu_analyser_ref_updated(x265cu_analyser* a, int idx)
 {
     if (idx < 0 || idx >= a->p.numRefs) return -1;
     return x265cu_extend_border(a->ctx, a->p.depth, a->d_refs[idx] + a->orgBytes, a->stride, a->p.width, a->p.height, AN_MARGIN_X, AN_MARGIN_Y);
+}
+
+// device address of the origin pixel of reconstruction plane `depthIdx` (0..3 = CU size 64, 32, 16, 8): what a row
+// shard's owner broadcasts (the producer side of m_reconRowFlag, framefilter.cpp:664)
+void* x265cu_analyser_recon_plane(x265cu_analyser* a, int depthIdx, int* stride)
+{
+    if (depthIdx < 0 || depthIdx >= 4) return NULL;
+    *stride = a->stride;
+    return a->d_recon[depthIdx] + a->orgBytes;
+}
+// promote the reconstructed CTU rows [ctuRow0, ctuRow1) of recon plane depthIdx to reference idx (device copy);
+// call x265cu_analyser_ref_updated() once all rows of the new reference are in place
+int x265cu_analyser_recon_to_ref(x265cu_analyser* a, int depthIdx, int idx, int ctuRow0, int ctuRow1)
+{
+    if (depthIdx < 0 || depthIdx >= 4 || idx < 0 || idx >= a->p.numRefs || ctuRow0 < 0 || ctuRow1 > a->ctuRows || ctuRow0 >= ctuRow1) return -1;
+    const size_t es = a->p.depth == 8 ? 1 : 2;
+    const int y0 = ctuRow0 * 64, y1 = ctuRow1 * 64 < a->p.height ? ctuRow1 * 64 : a->p.height;
+    const size_t off = a->orgBytes + (size_t)y0 * a->stride * es, pitch = (size_t)a->stride * es;
+    CU_CHECK(cudaMemcpy2DAsync(a->d_refs[idx] + off, pitch, a->d_recon[depthIdx] + off, pitch, (size_t)a->p.width * es, y1 - y0,
+                               cudaMemcpyDeviceToDevice, a->ctx->stream));
+    return 0;
 }
 
 // debugging / parity access to device-resident results

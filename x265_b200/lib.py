@@ -238,6 +238,12 @@ _AN_PROTOS = {
     "x265cu_analyser_stage_ms": (I, [P, C.POINTER(C.c_float)]),
     "x265cu_analyser_ref_plane": (P, [P, I, C.POINTER(I)]),
     "x265cu_analyser_ref_updated": (I, [P, I]),
+    "x265cu_analyser_ctu_rows": (I, [P]),
+    "x265cu_analyser_row_range": (I, [P, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I)]),
+    "x265cu_analyser_run_rows": (I, [P, I, I, I]),
+    "x265cu_analyser_analyse_rows": (I, [P, P, I, P, I, I, I, C.POINTER(AnalysisOut)]),
+    "x265cu_analyser_recon_plane": (P, [P, I, C.POINTER(I)]),
+    "x265cu_analyser_recon_to_ref": (I, [P, I, I, I, I]),
 }
 _AN_PROTOS["x265cu_lowres_intra_batch"] = (I, [P, I, P, I, I, I, I, I])
 _AN_PROTOS["x265cu_lookahead_cost_batch"] = (I, [P, I, P, I, I, I, I, P])
@@ -297,6 +303,36 @@ class Analyser:
         """e2e: host frame + predictor field in, host results out (synchronous)."""
         self.lib.check(self.lib.L.x265cu_analyser_analyse(self.h, fenc.ctypes.data, self.width, field.ctypes.data, stages, C.byref(self.out)))
         return self
+
+    # ---- CTU-row shards (x265cu_analyser_*_rows): rows [r0, r1) are one contiguous slice of every result array ----
+    @property
+    def ctu_rows(self):
+        return int(self.lib.L.x265cu_analyser_ctu_rows(self.h))
+
+    def row_range(self, r0, r1):
+        """(job0, njobs, cu0, ncu) of the CTU rows [r0, r1)."""
+        v = [I(), I(), I(), I()]
+        self.lib.check(self.lib.L.x265cu_analyser_row_range(self.h, r0, r1, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def run_rows(self, r0, r1, stages=7):
+        self.lib.check(self.lib.L.x265cu_analyser_run_rows(self.h, stages, r0, r1))
+
+    def analyse_rows(self, fenc, field, r0, r1, stages=7):
+        """e2e for a row shard: host frame + field in, the shard's slice of the host result arrays out."""
+        self.lib.check(self.lib.L.x265cu_analyser_analyse_rows(self.h, fenc.ctypes.data, self.width, field.ctypes.data, stages, r0, r1, C.byref(self.out)))
+        return self
+
+    def d2h_bytes_rows(self, r0, r1):
+        _, nj, _, nc = self.row_range(r0, r1)
+        return nj * 8 + nc * (8 + 4 + 4 + 36 * 4)
+
+    def recon_plane_ptr(self, depth_idx):
+        st = I()
+        return self.lib.L.x265cu_analyser_recon_plane(self.h, depth_idx, C.byref(st)), st.value
+
+    def recon_to_ref(self, depth_idx, ref_idx, r0, r1):
+        self.lib.check(self.lib.L.x265cu_analyser_recon_to_ref(self.h, depth_idx, ref_idx, r0, r1))
 
     def h2d_bytes(self, field):
         return self.width * self.height * np.dtype(self.dtype).itemsize + field.nbytes
