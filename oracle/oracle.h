@@ -119,6 +119,14 @@ typedef struct {
     int numCand; const int* mvc; /* qpel candidates (x,y pairs) */
     int merange;
     const uint16_t* mvcost; /* centred table (index 0 = mvd 0), qpel units */
+    /* chroma-SATD term of subpelCompare (motion.cpp:1601-1661), 4:2:0: when `chroma` != 0, subme > 2 and the chroma
+     * block has a SATD (motion.cpp:204-212: pw and ph multiples of 8), every subpelCompare adds the Cb and Cr SATD.
+     * Planes are half resolution, `cstride` pixels per row; the PU's chroma origin is
+     * ((offset / fencStride) >> 1) * cstride + ((offset % fencStride) >> 1) from the pointers given. */
+    int chroma;
+    const pixel* fencC[2];  /* source Cb, Cr (origin pixel) */
+    const pixel* refC[2];   /* reference Cb, Cr (origin pixel) */
+    intptr_t cstride;
 } orc_me_job;
 int orc_motion_estimate(const orc_me_job* job, int* outQMv);
 

@@ -43,6 +43,7 @@ static int orc_drv_me(const void* fv, const fs_me_job* j, int* qmv)
     const drv_frame* f = (const drv_frame*)fv;
     orc_me_job job;
     int mvc[8];
+    job.chroma = 0;
     job.fenc = f->fenc; job.fencStride = f->p.stride; job.offset = j->offset;
     job.ref[0] = job.ref[1] = job.ref[2] = job.ref[3] = f->refs[j->ref];
     job.refStride = f->p.stride; job.lowres = 0; job.pw = j->pw; job.ph = j->ph;

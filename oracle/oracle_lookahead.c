@@ -160,6 +160,7 @@ void orc_lookahead_frame_cost(orc_la_job* j)
                     }
                 }
                 orc_me_job job;
+                job.chroma = 0;
                 job.fenc = j->fenc[0]; job.fencStride = stride; job.offset = off;
                 for (int k = 0; k < 4; k++) job.ref[k] = fref[k];
                 job.refStride = stride; job.lowres = 1; job.pw = 8; job.ph = 8; job.method = 1; job.subme = 1;

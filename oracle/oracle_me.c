@@ -38,6 +38,10 @@ typedef struct {
     intptr_t stride;
     mv_t mvp;                   /* qpel */
     mv_t mvmin, mvmax;
+    int chroma;                 /* bChromaSATD (motion.cpp:212) */
+    pixel fencCb[32 * 32], fencCr[32 * 32];   /* fencPUYuv chroma, stride m_csize = 32 (yuv.cpp:126-140) */
+    const pixel* refCb; const pixel* refCr;    /* ref chroma planes + the PU's chroma offset */
+    intptr_t cstride;
 } me_ctx;
 
 static inline int mvcost(const me_ctx* c, int qx, int qy)
@@ -72,20 +76,55 @@ static int lowres_qpel_cost(const me_ctx* c, int qx, int qy, cmp_fn cmp)
     return cmp(c->fenc, 64, r, st, j->pw, j->ph);
 }
 
-/* motion.cpp:1571-1598 */
+/* motion.cpp:1601-1661, 4:2:0 (hshift = vshift = 1: mvx = qmv.x, eighth-pel): Cb + Cr SATD of the chroma block.
+ * chromaSatd = the luma SATD of the chroma-sized block (primitives.cpp:139-158), i.e. orc_satd's tiling of (w/2, h/2);
+ * hv = hps(rowExt) into a (h/2 + 3)-row intermediate, then vsp from its second row (ipfilter.cpp:362-369 pattern
+ * with the 4-tap filter: motion.cpp:1648-1658). */
+static int chroma_cost(const me_ctx* c, int qx, int qy)
+{
+    const int cw = c->j->pw >> 1, ch = c->j->ph >> 1;
+    const int xf = qx & 7, yf = qy & 7;
+    const intptr_t off = (qx >> 3) + (intptr_t)(qy >> 3) * c->cstride;
+    const pixel* ref[2] = { c->refCb + off, c->refCr + off };
+    const pixel* fenc[2] = { c->fencCb, c->fencCr };
+    int cost = 0;
+    for (int p = 0; p < 2; p++)
+    {
+        if (!(xf | yf)) { cost += orc_satd(fenc[p], 32, ref[p], c->cstride, cw, ch); continue; }
+        pixel buf[32 * 32];
+        if (!yf)      orc_interp_hpp(ref[p], c->cstride, buf, cw, xf, 4, cw, ch);
+        else if (!xf) orc_interp_vpp(ref[p], c->cstride, buf, cw, yf, 4, cw, ch);
+        else
+        {
+            int16_t immed[32 * (32 + 3)];
+            orc_interp_hps(ref[p], c->cstride, immed, cw, xf, 1, 4, cw, ch);
+            orc_interp_vsp(immed + cw, cw, buf, cw, yf, 4, cw, ch);
+        }
+        cost += orc_satd(fenc[p], 32, buf, cw, cw, ch);
+    }
+    return cost;
+}
+
+/* motion.cpp:1571-1664 */
 static int subpel_compare(const me_ctx* c, int qx, int qy, cmp_fn cmp)
 {
     g_orc_cnt[1]++;
     const orc_me_job* j = c->j;
     const pixel* r = c->fref + (qx >> 2) + (intptr_t)(qy >> 2) * c->stride;
     int xf = qx & 3, yf = qy & 3;
+    int cost;
     if (!(xf | yf))
-        return cmp(c->fenc, 64, r, c->stride, j->pw, j->ph);
-    pixel buf[64 * 64];
-    if (!yf)      orc_interp_hpp(r, c->stride, buf, j->pw, xf, 8, j->pw, j->ph);
-    else if (!xf) orc_interp_vpp(r, c->stride, buf, j->pw, yf, 8, j->pw, j->ph);
-    else          orc_interp_hvpp(r, c->stride, buf, j->pw, xf, yf, 8, j->pw, j->ph);
-    return cmp(c->fenc, 64, buf, j->pw, j->pw, j->ph);
+        cost = cmp(c->fenc, 64, r, c->stride, j->pw, j->ph);
+    else
+    {
+        pixel buf[64 * 64];
+        if (!yf)      orc_interp_hpp(r, c->stride, buf, j->pw, xf, 8, j->pw, j->ph);
+        else if (!xf) orc_interp_vpp(r, c->stride, buf, j->pw, yf, 8, j->pw, j->ph);
+        else          orc_interp_hvpp(r, c->stride, buf, j->pw, xf, yf, 8, j->pw, j->ph);
+        cost = cmp(c->fenc, 64, buf, j->pw, j->pw, j->ph);
+    }
+    if (c->chroma) cost += chroma_cost(c, qx, qy);
+    return cost;
 }
 
 static int qpel_cost(const me_ctx* c, int qx, int qy, cmp_fn cmp)
@@ -195,6 +234,16 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
     orc_copy_pp(c->fenc, 64, j->fenc + j->offset, j->fencStride, j->pw, j->ph);
     c->fref = j->ref[0] + j->offset;
     c->stride = j->refStride;
+    /* motion.cpp:204-212: chroma residual cost if subme > 2 and the chroma block has a SATD primitive */
+    c->chroma = j->chroma && !j->lowres && j->subme > 2 && !(j->pw & 7) && !(j->ph & 7);
+    if (c->chroma)
+    {
+        const intptr_t py = j->offset / j->fencStride, px = j->offset % j->fencStride;
+        const intptr_t coff = (py >> 1) * j->cstride + (px >> 1);
+        orc_copy_pp(c->fencCb, 32, j->fencC[0] + coff, j->cstride, j->pw >> 1, j->ph >> 1);
+        orc_copy_pp(c->fencCr, 32, j->fencC[1] + coff, j->cstride, j->pw >> 1, j->ph >> 1);
+        c->refCb = j->refC[0] + coff; c->refCr = j->refC[1] + coff; c->cstride = j->cstride;
+    }
     c->mvp.x = j->qmvp[0]; c->mvp.y = j->qmvp[1];
     c->mvmin.x = j->mvmin[0]; c->mvmin.y = j->mvmin[1];
     c->mvmax.x = j->mvmax[0]; c->mvmax.y = j->mvmax[1];

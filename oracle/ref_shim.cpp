@@ -17,6 +17,8 @@
 #include "motion.h"
 #include "bitcost.h"
 #include "mv.h"
+#include "yuv.h"
+#include "picyuv.h"
 #include <string.h>
 #include <stdio.h>
 
@@ -152,6 +154,57 @@ int x265ref_motion_estimate(pixel* fencPlane, intptr_t fencStride, intptr_t offs
     for (int i = 0; i < numCand && i < 32; i++) cands[i] = MV(mvc[2 * i], mvc[2 * i + 1]);
     int cost = me.motionEstimate(&ref, mn, mx, mvp, numCand, cands, merange, out, 1, NULL);
     outQMv[0] = out.x; outQMv[1] = out.y;
+    return cost;
+}
+
+/* The same call with the chroma-SATD term of subpelCompare active (motion.cpp:204-212, 1601-1661): driven
+ * through the Yuv variant of setSourcePU (motion.cpp:194-222) with bChroma = true, 4:2:0.  The PU is handed
+ * over as a Yuv whose top-left block is the PU (puPartIdx 0) and the reference as planes already offset to the
+ * PU, with a PicYuv whose CTU / partition offset tables are a single zero (so blockOffset = 0, motion.cpp:753,
+ * and getCbAddr(0, 0) = fpelPlane[1], lowres.h:62-63).  Chroma origin of the PU: (x >> 1, y >> 1). */
+int x265ref_motion_estimate_chroma(pixel* fencPlane, intptr_t fencStride, intptr_t offset,
+                                   pixel* fencCb, pixel* fencCr, intptr_t cstride,
+                                   pixel* refPlane, intptr_t refStride, pixel* refCb, pixel* refCr,
+                                   int pw, int ph, int method, int subme, int qp,
+                                   const int* mvmin, const int* mvmax, const int* qmvp,
+                                   int numCand, const int* mvc, int merange, int* outQMv)
+{
+    ensure_init();
+    static bool scales = false;
+    if (!scales) { MotionEstimate::initScales(); scales = true; }
+    const intptr_t py = offset / fencStride, px = offset % fencStride;
+    const intptr_t coff = (py >> 1) * cstride + (px >> 1);
+    Yuv src;
+    if (!src.create(64, X265_CSP_I420)) return -1;
+    for (int y = 0; y < ph; y++)
+        memcpy(src.m_buf[0] + y * src.m_size, fencPlane + offset + y * fencStride, pw * sizeof(pixel));
+    for (int y = 0; y < ph / 2; y++)
+    {
+        memcpy(src.m_buf[1] + y * src.m_csize, fencCb + coff + y * cstride, (pw / 2) * sizeof(pixel));
+        memcpy(src.m_buf[2] + y * src.m_csize, fencCr + coff + y * cstride, (pw / 2) * sizeof(pixel));
+    }
+    MotionEstimate me;
+    me.init(X265_CSP_I420);
+    me.setQP(qp);
+    me.setSourcePU(src, 0, 0, 0, pw, ph, method, subme, true);
+    PicYuv pic;
+    intptr_t zero = 0;
+    pic.m_cuOffsetY = &zero; pic.m_cuOffsetC = &zero; pic.m_buOffsetY = &zero; pic.m_buOffsetC = &zero;
+    pic.m_picOrg[0] = refPlane + offset; pic.m_picOrg[1] = refCb + coff; pic.m_picOrg[2] = refCr + coff;
+    pic.m_stride = refStride; pic.m_strideC = cstride;
+    ReferencePlanes ref;
+    ref.reconPic = &pic;
+    ref.lumaStride = refStride;
+    ref.isLowres = false;
+    ref.fpelPlane[0] = refPlane + offset; ref.fpelPlane[1] = refCb + coff; ref.fpelPlane[2] = refCr + coff;
+    MV mn(mvmin[0], mvmin[1]), mx(mvmax[0], mvmax[1]), mvp(qmvp[0], qmvp[1]), out;
+    MV cands[32];
+    for (int i = 0; i < numCand && i < 32; i++) cands[i] = MV(mvc[2 * i], mvc[2 * i + 1]);
+    int cost = me.motionEstimate(&ref, mn, mx, mvp, numCand, cands, merange, out, 1, NULL);
+    outQMv[0] = out.x; outQMv[1] = out.y;
+    src.destroy();
+    pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = NULL;
+    pic.m_picOrg[0] = pic.m_picOrg[1] = pic.m_picOrg[2] = NULL;
     return cost;
 }
 

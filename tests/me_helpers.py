@@ -11,7 +11,8 @@ class OrcMeJob(C.Structure):
     _fields_ = [("fenc", P), ("fencStride", IP), ("offset", IP), ("ref", P * 4), ("refStride", IP),
                 ("lowres", I), ("pw", I), ("ph", I), ("method", I), ("subme", I),
                 ("mvmin", I * 2), ("mvmax", I * 2), ("qmvp", I * 2), ("numCand", I), ("mvc", P),
-                ("merange", I), ("mvcost", P)]
+                ("merange", I), ("mvcost", P),
+                ("chroma", I), ("fencC", P * 2), ("refC", P * 2), ("cstride", IP)]
 
 
 _tables = {}
@@ -89,6 +90,68 @@ def run_both(O, R, depth, rng, w, h, method, subme, lowres, smooth, merange, qp=
     job.mvmin[0], job.mvmin[1] = mvmin; job.mvmax[0], job.mvmax[1] = mvmax; job.qmvp[0], job.qmvp[1] = qmvp
     job.numCand = ncand; job.mvc = mvc.ctypes.data; job.merange = merange
     job.mvcost = tab.ctypes.data + MVRANGE * 2
+    O.orc_motion_estimate.argtypes = [C.POINTER(OrcMeJob), P]
+    co = O.orc_motion_estimate(C.byref(job), ptr(out_o))
+    return (cr, int(out_r[0]), int(out_r[1])), (co, int(out_o[0]), int(out_o[1]))
+
+
+def chroma_case(depth, rng, w, h, smooth, merange, W=256, H=192, margin=96):
+    """Planes and window of one 4:2:0 motionEstimate job: luma + Cb/Cr of source and reference (chroma planes at
+    half resolution with half the margin, so a luma offset maps to chroma by halving its row and column)."""
+    mx = (1 << depth) - 1
+    fenc, stride, org = make_plane(rng, depth, W, H, margin, smooth=smooth)
+    sy, sx = int(rng.integers(-9, 10)), int(rng.integers(-9, 10))
+
+    def ref_of(src, dy, dx):
+        if not smooth:
+            return rng.integers(0, mx + 1, src.shape).astype(src.dtype)
+        sh = np.roll(np.roll(src, dy, axis=0), dx, axis=1)
+        return np.clip(sh.astype(np.int64) + rng.integers(-3, 4, sh.shape), 0, mx).astype(src.dtype)
+    ref = ref_of(fenc, sy, sx)
+    fc, rc = [], []
+    for _ in range(2):
+        c, cstride, corg = make_plane(rng, depth, W // 2, H // 2, margin // 2, smooth=smooth)
+        fc.append(c); rc.append(ref_of(c, sy // 2, sx // 2))
+    assert corg == (margin // 2) * cstride + margin // 2
+    bx = int(rng.integers(0, (W - w) // 8 + 1)) * 8; by = int(rng.integers(0, (H - h) // 8 + 1)) * 8
+    offset = org + by * stride + bx
+    qmvp = (int(rng.integers(-40, 41)), int(rng.integers(-40, 41)))
+    lim = margin - 12
+    mvmin = (max(-bx - lim, (qmvp[0] >> 2) - merange), max(-by - lim, (qmvp[1] >> 2) - merange))
+    mvmax = (min(W - w - bx + lim, (qmvp[0] >> 2) + merange), min(H - h - by + lim, (qmvp[1] >> 2) + merange))
+    ncand = int(rng.integers(0, 4))
+    mvc = rng.integers(-60, 61, (max(ncand, 1), 2)).astype(np.int32)
+    return dict(fenc=fenc, ref=ref, stride=stride, fc=fc, rc=rc, cstride=cstride, offset=offset, qmvp=qmvp, mvmin=mvmin,
+                mvmax=mvmax, ncand=ncand, mvc=mvc, w=w, h=h)
+
+
+def orc_chroma_job(O, cs, method, subme, merange, tab):
+    job = OrcMeJob()
+    job.fenc = cs["fenc"].ctypes.data; job.fencStride = cs["stride"]; job.offset = cs["offset"]
+    for i in range(4):
+        job.ref[i] = cs["ref"].ctypes.data
+    job.refStride = cs["stride"]; job.lowres = 0; job.pw = cs["w"]; job.ph = cs["h"]; job.method = method; job.subme = subme
+    job.mvmin[0], job.mvmin[1] = cs["mvmin"]; job.mvmax[0], job.mvmax[1] = cs["mvmax"]; job.qmvp[0], job.qmvp[1] = cs["qmvp"]
+    job.numCand = cs["ncand"]; job.mvc = cs["mvc"].ctypes.data; job.merange = merange
+    job.mvcost = tab.ctypes.data + MVRANGE * 2
+    job.chroma = 1; job.cstride = cs["cstride"]
+    for i in range(2):
+        job.fencC[i] = cs["fc"][i].ctypes.data; job.refC[i] = cs["rc"][i].ctypes.data
+    return job
+
+
+def run_both_chroma(O, R, depth, rng, w, h, method, subme, smooth, merange, qp=30):
+    """One 4:2:0 job with the chroma-SATD term (motion.cpp:1601-1661) through the real MotionEstimate (Yuv variant of
+    setSourcePU, bChroma = true) and through the oracle."""
+    cs = chroma_case(depth, rng, w, h, smooth, merange)
+    tab = mvcost_table(O, R.x265ref_lambda(qp))
+    out_r = np.zeros(2, np.int32); out_o = np.zeros(2, np.int32)
+    mn = np.array(cs["mvmin"], np.int32); mxv = np.array(cs["mvmax"], np.int32); mp = np.array(cs["qmvp"], np.int32)
+    R.x265ref_motion_estimate_chroma.argtypes = [P, IP, IP, P, P, IP, P, IP, P, P, I, I, I, I, I, P, P, P, I, P, I, P]
+    cr = R.x265ref_motion_estimate_chroma(ptr(cs["fenc"]), cs["stride"], cs["offset"], ptr(cs["fc"][0]), ptr(cs["fc"][1]), cs["cstride"],
+                                          ptr(cs["ref"]), cs["stride"], ptr(cs["rc"][0]), ptr(cs["rc"][1]),
+                                          w, h, method, subme, qp, ptr(mn), ptr(mxv), ptr(mp), cs["ncand"], ptr(cs["mvc"]), merange, ptr(out_r))
+    job = orc_chroma_job(O, cs, method, subme, merange, tab)
     O.orc_motion_estimate.argtypes = [C.POINTER(OrcMeJob), P]
     co = O.orc_motion_estimate(C.byref(job), ptr(out_o))
     return (cr, int(out_r[0]), int(out_r[1])), (co, int(out_o[0]), int(out_o[1]))

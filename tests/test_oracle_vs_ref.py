@@ -86,3 +86,25 @@ def test_motion_estimate_lowres(depth):
                 for it in range(4):
                     r, o = _me_job(O, R, depth, rng, 8, 8, method, subme, 1, smooth, 16)
                     assert r == o, (method, subme, smooth, r, o)
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+@pytest.mark.parametrize("method", [1, 3])
+def test_motion_estimate_chroma_satd(depth, method):
+    """subpelCompare's chroma term (motion.cpp:1601-1661; active for subme > 2 when the chroma block has a SATD,
+    motion.cpp:204-212): every PU size whose chroma block is a multiple of 4x4, plus sizes / sub-pel levels where
+    the term must stay off."""
+    from me_helpers import run_both_chroma
+    R, O = libs(depth)
+    rng = np.random.default_rng(31 + method)
+    sizes = [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (32, 16), (16, 32), (64, 32), (32, 64),
+             (32, 24), (24, 32), (32, 8), (8, 32), (64, 48), (48, 64), (64, 16), (16, 64),
+             (8, 4), (4, 8), (16, 12), (12, 16), (16, 4), (4, 16)]
+    n = diff = 0
+    for (w, h) in sizes:
+        for subme in (2, 3, 4, 5, 7):
+            for smooth in (True, False):
+                r, o = run_both_chroma(O, R, depth, rng, w, h, method, subme, smooth, 57 if method == 3 else 16)
+                assert r == o, (w, h, method, subme, smooth, r, o)
+                n += 1
+    assert n == len(sizes) * 10
