@@ -157,6 +157,23 @@ int x265cu_me_batch(x265cu_ctx*, int depth, const void* fenc_dev, int fencStride
                     const uint16_t* mvcost_dev /* centred table base */, int mvcost_range,
                     const x265cu_me_job* jobs_dev, int n, int32_t* out_dev);
 
+/* The same call with the chroma-SATD term of subpelCompare (motion.cpp:1601-1661) for 4:2:0 sources: with
+ * MotionEstimate::bChromaSATD (motion.cpp:204-212: subme > 2 and PU width and height multiples of 8, so that the
+ * chroma block has a SATD primitive, primitives.cpp:139-158) every sub-pel compare -- the clipped MVP, the MV
+ * candidates and all refinement points -- adds SATD(Cb) + SATD(Cr) of the chroma block predicted at the eighth-pel
+ * vector with the 4-tap filters.  Other jobs of the launch behave exactly as in x265cu_me_batch.
+ * Chroma planes are half resolution, `cstride` pixels per row for source and references alike; the chroma pixel of the
+ * luma position (x, y) = (offset % fencStride, offset / fencStride) is at (y >> 1) * cstride + (x >> 1) from the
+ * pointers given.  `chroma` is a host struct of device pointers. */
+typedef struct {
+    const void* fencCb_dev; const void* fencCr_dev;
+    const void* const* refCb_dev; const void* const* refCr_dev;   /* device arrays of plane pointers, indexed by job.ref */
+    int cstride;
+} x265cu_me_chroma;
+int x265cu_me_batch_chroma(x265cu_ctx*, int depth, const void* fenc_dev, int fencStride,
+                           const void* const* refplanes_dev, int refStride, const x265cu_me_chroma* chroma,
+                           const uint16_t* mvcost_dev, int mvcost_range, const x265cu_me_job* jobs_dev, int n, int32_t* out_dev);
+
 /* ---------- frame-level CTU analysis (DESIGN.md "Frame analysis workload") ----------
  * One analyser = one picture geometry.  Reference planes stay resident in HBM (x265cu_analyser_set_ref
  * = what the recon-row broadcast feeds); per frame the host passes the source luma and the 16x16

@@ -883,14 +883,160 @@ __constant__ int8_t c_star_off[16][2] = { {-1,0},{0,-1}, {-1,-1},{1,-1}, {-1,0},
 // motion.cpp:48-58 {hpel_iters, hpel_dirs, qpel_iters, qpel_dirs, hpel_satd}
 __constant__ int8_t c_workload[8][5] = { {1,4,0,4,0}, {1,4,1,4,0}, {1,4,1,4,1}, {2,4,1,4,1}, {2,4,2,4,1}, {1,8,1,8,1}, {2,8,1,8,1}, {2,8,2,8,1} };
 
+// ---- chroma-SATD term of subpelCompare (motion.cpp:1601-1661), 4:2:0 -----------------------------------------
+// With bChromaSATD (subme > 2 and a chroma block that is a multiple of 4x4: motion.cpp:204-212) EVERY subpelCompare
+// adds chromaSatd(Cb) + chromaSatd(Cr) of the chroma block predicted at the eighth-pel vector (mvx = qmv.x for
+// 4:2:0): filter_hpp / filter_vpp / filter_hps(rowExt) + filter_vsp with the 4-tap filter.
+struct MeChromaArgs                        // device pointers; the chroma pixel of luma (x, y) is at (y >> 1) * cstride + (x >> 1)
+{
+    const void* fencCb; const void* fencCr;
+    const void* const* refCb; const void* const* refCr;      // device arrays of plane pointers, indexed by job.ref
+    int cstride;
+};
+
+// per-job chroma context (kept out of MeCtx so that the luma-only kernels are not touched by it)
+template <typename P>
+struct MeChromaCtx
+{
+    bool on;                               // MotionEstimate::bChromaSATD of this job (motion.cpp:204-212)
+    const P* fcb; const P* fcr;            // source Cb / Cr at the PU's chroma origin
+    const P* rcb; const P* rcr;            // reference Cb / Cr at the PU's chroma origin
+    int cstride;
+};
+
+template <typename P>
+__device__ __forceinline__ void me_set_chroma(MeChromaCtx<P>& cc, const MeCtx<P>& c, const x265cu_me_job& j, const MeChromaArgs& a, int fstride)
+{
+    cc.on = !c.lowres && j.subme > 2 && !(c.w & 7) && !(c.h & 7);
+    const int py = j.offset / fstride, px = j.offset - py * fstride;
+    const ptrdiff_t coff = (ptrdiff_t)(py >> 1) * a.cstride + (px >> 1);
+    cc.cstride = a.cstride;
+    cc.fcb = (const P*)a.fencCb + coff; cc.fcr = (const P*)a.fencCr + coff;
+    cc.rcb = ((const P* const*)a.refCb)[j.ref] + coff; cc.rcr = ((const P* const*)a.refCr)[j.ref] + coff;
+}
+
+// un-normalised 4x4 Hadamard abs-sum of (source chroma block - predicted chroma block).  One lane, registers only;
+// out of line (one copy per kernel: the ME kernels are instruction-cache sensitive).
+template <typename P>
+__device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* __restrict__ r, int stride, int xf, int yf)
+{
+    constexpr int DEPTH = PixTraits<P>::depth;
+    int m[4][4];
+    if (!(xf | yf))
+    {
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) m[y][x] = (int)r[y * stride + x];
+    }
+    else if (!yf)
+    {
+        const int c0 = c_chromaFilter[xf][0], c1 = c_chromaFilter[xf][1], c2 = c_chromaFilter[xf][2], c3 = c_chromaFilter[xf][3];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+        {
+            int p[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) p[k] = (int)r[y * stride + k - 1];
+#pragma unroll
+            for (int x = 0; x < 4; x++) m[y][x] = interp_finish<DEPTH>(c0 * p[x] + c1 * p[x + 1] + c2 * p[x + 2] + c3 * p[x + 3], 0);
+        }
+    }
+    else if (!xf)
+    {
+        const int c0 = c_chromaFilter[yf][0], c1 = c_chromaFilter[yf][1], c2 = c_chromaFilter[yf][2], c3 = c_chromaFilter[yf][3];
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+        {
+            int p[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) p[k] = (int)r[(k - 1) * stride + x];
+#pragma unroll
+            for (int y = 0; y < 4; y++) m[y][x] = interp_finish<DEPTH>(c0 * p[y] + c1 * p[y + 1] + c2 * p[y + 2] + c3 * p[y + 3], 0);
+        }
+    }
+    else
+    {
+        const int h0 = c_chromaFilter[xf][0], h1 = c_chromaFilter[xf][1], h2 = c_chromaFilter[xf][2], h3 = c_chromaFilter[xf][3];
+        const int v0 = c_chromaFilter[yf][0], v1 = c_chromaFilter[yf][1], v2 = c_chromaFilter[yf][2], v3 = c_chromaFilter[yf][3];
+        int mid[7][4];                     // filter_hps with isRowExt: rows -1 .. +5 of the block (ipfilter.cpp:120-162)
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+        {
+            int p[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) p[i] = (int)r[(k - 1) * stride + i - 1];
+#pragma unroll
+            for (int x = 0; x < 4; x++) mid[k][x] = interp_finish<DEPTH>(h0 * p[x] + h1 * p[x + 1] + h2 * p[x + 2] + h3 * p[x + 3], 1);
+        }
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                m[y][x] = interp_finish<DEPTH>(v0 * mid[y][x] + v1 * mid[y + 1][x] + v2 * mid[y + 2][x] + v3 * mid[y + 3][x], 2);
+    }
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+    {
+#pragma unroll
+        for (int x = 0; x < 4; x++) m[y][x] = (int)f[y * stride + x] - m[y][x];
+        had4(m[y][0], m[y][1], m[y][2], m[y][3]);
+    }
+    int acc = 0;
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+    {
+        had4(m[0][x], m[1][x], m[2][x], m[3][x]);
+        acc += abs(m[0][x]) + abs(m[1][x]) + abs(m[2][x]) + abs(m[3][x]);
+    }
+    return acc;
+}
+
+// Cb + Cr chroma SATD of the candidates of a burst: lane k (k < n, bit k of `need` set) receives candidate k's cost.
+// chromaSatd is the luma SATD primitive of the chroma-sized block (primitives.cpp:139-158): 8x4 tiles when the chroma
+// width is a multiple of 8, else 4x4 tiles, each tile halved on its own (pixel.cpp:210-297, 1131-1155).  One candidate
+// at a time, the (plane, tile) pairs over the lanes, one REDUX per candidate.
+template <typename P>
+__device__ __forceinline__ int me_chroma_batch(const MeCtx<P>& c, const MeChromaCtx<P>& cc, int n, int qx, int qy, unsigned need)
+{
+    const int cw = c.w >> 1, chh = c.h >> 1;
+    const int tw = (cw & 7) ? 4 : 8;
+    const int tpr = cw / tw, nt = tpr * (chh >> 2);                 // tiles per row / per plane
+    int out = 0;
+    for (int k = 0; k < n; k++)
+    {
+        if (!((need >> k) & 1u)) continue;                         // warp-uniform
+        const int kqx = __shfl_sync(0xffffffffu, qx, k), kqy = __shfl_sync(0xffffffffu, qy, k);
+        const int xf = kqx & 7, yf = kqy & 7;
+        const ptrdiff_t roff = (kqx >> 3) + (ptrdiff_t)(kqy >> 3) * cc.cstride;
+        int part = 0;
+        for (int t = c.lane; t < 2 * nt; t += 32)
+        {
+            const bool cr = t >= nt;
+            const int tt = cr ? t - nt : t;
+            const int ty = tt / tpr, tx = tt - ty * tpr;
+            const ptrdiff_t o = (ptrdiff_t)(ty * 4) * cc.cstride + tx * tw;
+            const P* f = (cr ? cc.fcr : cc.fcb) + o;
+            const P* r = (cr ? cc.rcr : cc.rcb) + o + roff;
+            int v = me_chroma_had4x4<P>(f, r, cc.cstride, xf, yf);
+            if (tw == 8) v += me_chroma_had4x4<P>(f + 4, r + 4, cc.cstride, xf, yf);
+            part += v >> 1;
+        }
+        __syncwarp();
+        const int tot = __reduce_add_sync(0xffffffffu, part);
+        if (c.lane == k) out = tot;
+    }
+    return out;
+}
+
 struct MeState { int bmx, bmy, bcost, bprecost, bestprex, bestprey; };
 
 #define ME_YOK(y) (((y) >= c.miny) & ((y) <= c.maxy))
 #define ME_INRANGE(x, y) ((x) >= c.minx && (x) <= c.maxx && (y) >= c.miny && (y) <= c.maxy)
 
 // phase 1 (motion.cpp:771-814): cost at the clipped MVP, at its full-pel rounding, at MV 0 and at the qpel candidates
-template <typename P, int CLS>
-__device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, MeState& st)
+template <typename P, int CLS, bool CHROMA = false>
+__device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, MeState& st, const MeChromaCtx<P>* cc = nullptr)
 {
 
     const int qminx = c.minx * 4, qminy = c.miny * 4, qmaxx = c.maxx * 4, qmaxy = c.maxy * 4;
@@ -952,6 +1098,14 @@ __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, M
         valid = valid && lane < cnt;
         const int n = me_compact(valid, cnt, qx, qy, tag, dummy);
         int cost = me_subpel_batch<P, CLS>(c, n, qx, qy, false);
+        if (CHROMA && cc->on)
+        {
+            // the clipped MVP and the candidates go through subpelCompare (chroma term included); the MVP's full-pel
+            // rounding and MV 0 are plain COST_MV SADs (motion.cpp:771-814)
+            const bool wantC = lane < n && (tag == 0 || tag >= 3);
+            const int ccost = me_chroma_batch<P>(c, *cc, n, qx, qy, __ballot_sync(0xffffffffu, wantC));
+            if (wantC) cost += ccost;
+        }
         const bool mine = lane < n;
         const unsigned m0 = __ballot_sync(0xffffffffu, mine && tag == 0);
         const unsigned m1 = __ballot_sync(0xffffffffu, mine && tag == 1);
@@ -1119,8 +1273,8 @@ __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, M
 }
 
 // phase 3 (motion.cpp:1440-1569): pick pre-check vs search winner, sub-pel refinement
-template <typename P, int CLS>
-__device__ __forceinline__ void me_phase3(MeCtx<P>& c, const x265cu_me_job& j, const MeState& st, int32_t* __restrict__ out)
+template <typename P, int CLS, bool CHROMA = false>
+__device__ __forceinline__ void me_phase3(MeCtx<P>& c, const x265cu_me_job& j, const MeState& st, int32_t* __restrict__ out, const MeChromaCtx<P>* cc = nullptr)
 {
     const int qminy = c.miny * 4, qmaxy = c.maxy * 4;
     int bcost = st.bcost;
@@ -1176,6 +1330,11 @@ __device__ __forceinline__ void me_phase3(MeCtx<P>& c, const x265cu_me_job& j, c
             const bool valid = c.lane < dirs && (centre || !((qy < qminy) | (qy > qmaxy)));
             const int n = me_compact(valid, dirs, qx, qy, dir, dummy);
             int cost = me_subpel_batch<P, CLS>(c, n, qx, qy, satd);
+            if (CHROMA && cc->on)
+            {
+                const int ccost = me_chroma_batch<P>(c, *cc, n, qx, qy, n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+                if (c.lane < n) cost += ccost;
+            }
             if (c.lane < n) cost += me_mvcost(c, qx, qy);
             if (centre) { bcost = __shfl_sync(0xffffffffu, cost, 0); stage++; continue; }
             int bdir = 0;
@@ -1269,6 +1428,49 @@ __global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : (CLS == 1 ? M
     }
 }
 
+// The pre-check and sub-pel launches with the chroma-SATD term (x265cu_me_batch_chroma): separate instantiations, so
+// the luma-only kernels above are unchanged by it.  The integer search (phase 2) is luma only in the reference too.
+template <typename P, int PHASE, int CLS>
+__global__ void __launch_bounds__(256, CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS) k_me_chroma(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride,
+                                                           MeChromaArgs ch, const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
+                                                           int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter)
+{
+    extern __shared__ unsigned char me_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    MeShared* sm = (MeShared*)me_smem + warp;
+    for (;;)
+    {
+        int jid = 0;
+        if (lane == 0) jid = atomicAdd(counter, 1);
+        jid = __shfl_sync(0xffffffffu, jid, 0);
+        if (jid >= n) break;
+        const x265cu_me_job j = jobs[jid];
+        MeCtx<P> c;
+        me_make_ctx<P>(c, j, fenc, fstride, refs, rstride, 0, mvcost, lane, sm);
+        if (me_subpel_class(c) != CLS) continue;                   // the sibling launch owns this job
+        MeChromaCtx<P> cc;
+        me_set_chroma<P>(cc, c, j, ch, fstride);
+        MeState st;
+        if (PHASE == 1) { me_phase1<P, CLS, true>(c, j, st, &cc); if (lane == 0) state[jid] = st; }
+        else            { st = state[jid]; me_phase3<P, CLS, true>(c, j, st, out + (size_t)jid * 4, &cc); }
+        __syncwarp();
+    }
+}
+
+template <typename P, int PHASE, int CLS>
+static int launch_me_chroma_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, const MeChromaArgs& ch,
+                                  const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter)
+{
+    const int threads = 256, warps = threads / 32;
+    const size_t smem = sizeof(MeShared) * warps;
+    int blocks = ctx->sm_count * (CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS);
+    int need = (n + warps - 1) / warps;
+    if (blocks > need) blocks = need;
+    k_me_chroma<P, PHASE, CLS><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, ch, mvcost, jobs, n, out, state, counter);
+    CU_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 template <typename P, int PHASE, int CLS>
 static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
                            const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter)
@@ -1285,21 +1487,38 @@ static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const
 
 template <typename P>
 static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
-                       const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* st, int* counter_dev)
+                       const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* st, int* counter_dev,
+                       const MeChromaArgs* ch)
 {
     int rc = 0;
-    rc |= launch_me_phase<P, 1, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
-    rc |= launch_me_phase<P, 1, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
+    if (ch)
+    {
+        rc |= launch_me_chroma_phase<P, 1, 0>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 0);
+        rc |= launch_me_chroma_phase<P, 1, 1>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 1);
+    }
+    else
+    {
+        rc |= launch_me_phase<P, 1, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
+        rc |= launch_me_phase<P, 1, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
+    }
     CU_CHECK(cudaEventRecord(ctx->me_ev[1], ctx->stream));
     rc |= launch_me_phase<P, 2, -1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
     CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
-    rc |= launch_me_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 3);
-    rc |= launch_me_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 4);
+    if (ch)
+    {
+        rc |= launch_me_chroma_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 3);
+        rc |= launch_me_chroma_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 4);
+    }
+    else
+    {
+        rc |= launch_me_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 3);
+        rc |= launch_me_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 4);
+    }
     return rc;
 }
 
 static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
-                     const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, int* counter_dev)
+                     const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, int* counter_dev, const MeChromaArgs* chroma = NULL)
 {
     if (n <= 0) return 0;
     CU_CHECK(cudaMemsetAsync(counter_dev, 0, 8 * sizeof(int), ctx->stream));
@@ -1313,8 +1532,9 @@ static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, 
     }
     MeState* st = (MeState*)ctx->d_me_state;
     CU_CHECK(cudaEventRecord(ctx->me_ev[0], ctx->stream));
-    const int rc = depth == 8 ? launch_me_t<uint8_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev)
-                              : launch_me_t<uint16_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev);
+    if (chroma && lowres) chroma = NULL;                    // the lowres planes have no chroma (lowres.h)
+    const int rc = depth == 8 ? launch_me_t<uint8_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev, chroma)
+                              : launch_me_t<uint16_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev, chroma);
     CU_CHECK(cudaEventRecord(ctx->me_ev[3], ctx->stream));
     return rc;
 }

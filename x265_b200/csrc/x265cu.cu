@@ -239,6 +239,20 @@ int x265cu_me_batch(x265cu_ctx* c, int depth, const void* fenc, int fencStride, 
     return launch_me(c, depth, fenc, fencStride, refs, refStride, lowres, mvcost, jobs, n, out, c->d_counter);
 }
 
+int x265cu_me_batch_chroma(x265cu_ctx* c, int depth, const void* fenc, int fencStride, const void* const* refs, int refStride,
+                           const x265cu_me_chroma* chroma, const uint16_t* mvcost, int mvcost_range, const x265cu_me_job* jobs, int n, int32_t* out)
+{
+    (void)mvcost_range;
+    if (!chroma || !chroma->fencCb_dev || !chroma->fencCr_dev || !chroma->refCb_dev || !chroma->refCr_dev || chroma->cstride <= 0)
+    {
+        x265cu_set_error("x265cu_me_batch_chroma: chroma planes missing", cudaErrorInvalidValue, __FILE__, __LINE__);
+        return -1;
+    }
+    MeChromaArgs a;
+    a.fencCb = chroma->fencCb_dev; a.fencCr = chroma->fencCr_dev; a.refCb = chroma->refCb_dev; a.refCr = chroma->refCr_dev; a.cstride = chroma->cstride;
+    return launch_me(c, depth, fenc, fencStride, refs, refStride, 0, mvcost, jobs, n, out, c->d_counter, &a);
+}
+
 __global__ void k_la_intra_zero(const x265cu_la_intra_job* jobs, int h8)
 {
     const x265cu_la_intra_job jb = jobs[blockIdx.x];

@@ -17,6 +17,12 @@ class CudaUnavailable(RuntimeError):
     pass
 
 
+class MeChroma(C.Structure):
+    """x265cu_me_chroma (include/x265_b200.h)"""
+    _fields_ = [("fencCb_dev", C.c_void_p), ("fencCr_dev", C.c_void_p), ("refCb_dev", C.c_void_p), ("refCr_dev", C.c_void_p),
+                ("cstride", C.c_int)]
+
+
 # job record layouts (must match include/x265_b200.h)
 CMP_JOB = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("a_stride", "<i4"), ("b_stride", "<i4"),
                     ("w", "<i2"), ("h", "<i2"), ("pad", "<i4")], align=True)
@@ -70,6 +76,7 @@ _PROTOS = {
     "x265cu_extend_border": (I, [P, I, P, I, I, I, I, I]),
     "x265cu_mvcost_table": (None, [C.c_double, I, P]),
     "x265cu_me_batch": (I, [P, I, P, I, P, I, I, P, I, P, I, P]),
+    "x265cu_me_batch_chroma": (I, [P, I, P, I, P, I, P, P, I, P, I, P]),
 }
 
 
@@ -191,6 +198,13 @@ class Lib:
         centre = mvcost_dev.ptr + 2 * mvcost_range
         self.check(self.L.x265cu_me_batch(self.ctx, depth, fenc.ptr, fstride, refs_ptr_table.ptr, rstride, lowres, centre,
                                           mvcost_range, jobs_dev.ptr, n, out_dev.ptr))
+
+    def me_batch_chroma(self, depth, fenc, fstride, refs_ptr_table, rstride, fenc_cb, fenc_cr, ref_cb_table, ref_cr_table, cstride,
+                        mvcost_dev, mvcost_range, jobs_dev, n, out_dev):
+        """x265cu_me_batch with the chroma-SATD term of subpelCompare (4:2:0 planes at half resolution)."""
+        ch = MeChroma(fenc_cb.ptr, fenc_cr.ptr, ref_cb_table.ptr, ref_cr_table.ptr, cstride)
+        self.check(self.L.x265cu_me_batch_chroma(self.ctx, depth, fenc.ptr, fstride, refs_ptr_table.ptr, rstride, C.byref(ch),
+                                                 mvcost_dev.ptr + 2 * mvcost_range, mvcost_range, jobs_dev.ptr, n, out_dev.ptr))
 
     def mvcost_table(self, lam, rng):
         t = np.zeros(2 * rng + 1, np.uint16)
