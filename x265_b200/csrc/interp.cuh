@@ -193,6 +193,119 @@ __device__ __forceinline__ void me_vmid(const int16_t* __restrict__ m, int pitch
 }
 
 
+// ---- 4-row units: a lane owns 4 consecutive rows of an 8-pixel column strip ---------------------------------------
+// Vertical filters re-use their source rows: 11 rows feed 4 output rows (2.75 row loads per output row instead of 8).
+
+// 8 pixels of a row at any byte phase as two packed words (8-bit planes); the third aligned word is inside the plane
+// margin even when it is not needed
+__device__ __forceinline__ void ip_row8_packed(const uint8_t* __restrict__ p, uint32_t& x0, uint32_t& x1)
+{
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+    const unsigned sh = ((unsigned)a & 3u) * 8u;
+    const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
+    x0 = __funnelshift_r(w0, w1, sh); x1 = __funnelshift_r(w1, w2, sh);
+}
+
+// 4 x 8 vertical 8-tap sums straight from pixel rows; s = (row y-3 of the first output row, first pixel of the strip).
+// 8-bit: the 11 source rows are transposed once in 4-row groups G0 = rows 0-3, G1 = 4-7, G2 = 8-10 (one byte per row in
+// a word per column), then output row y is DP4A(G0, A[y]) + DP4A(G1, B[y]) + DP4A(G2, C[y]) with the 8 taps shifted by
+// y bytes and zero padded (A[0], B[0] = the plain tap words, C[0] = 0): exact integer sums, same as ipfilter.cpp:164-203.
+template <typename P>
+__device__ __forceinline__ void me_vcol4(const P* __restrict__ s, int rstride, int yf, int (&sum)[4][8])
+{
+    if (sizeof(P) == 1)
+    {
+        const uint32_t TL = c_luma4[yf][0], TH = c_luma4[yf][1];
+        uint32_t A[4], B[4], C[4];
+        A[0] = TL; B[0] = TH; C[0] = 0u;
+        A[1] = TL << 8;  B[1] = __funnelshift_r(TL, TH, 24); C[1] = TH >> 24;
+        A[2] = TL << 16; B[2] = __funnelshift_r(TL, TH, 16); C[2] = TH >> 16;
+        A[3] = TL << 24; B[3] = __funnelshift_r(TL, TH, 8);  C[3] = TH >> 8;
+        uint32_t R[12][2];
+#pragma unroll
+        for (int k = 0; k < 11; k++) ip_row8_packed((const uint8_t*)(s + (ptrdiff_t)k * rstride), R[k][0], R[k][1]);
+        R[11][0] = 0u; R[11][1] = 0u;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+        {
+            uint32_t col[3][4];
+#pragma unroll
+            for (int g = 0; g < 3; g++)
+            {
+                const uint32_t r0 = R[4 * g][i], r1 = R[4 * g + 1][i], r2 = R[4 * g + 2][i], r3 = R[4 * g + 3][i];
+                const uint32_t p0 = __byte_perm(r0, r1, 0x5140), p1 = __byte_perm(r2, r3, 0x5140);
+                const uint32_t p2 = __byte_perm(r0, r1, 0x7362), p3 = __byte_perm(r2, r3, 0x7362);
+                col[g][0] = __byte_perm(p0, p1, 0x5410); col[g][1] = __byte_perm(p0, p1, 0x7632);
+                col[g][2] = __byte_perm(p2, p3, 0x5410); col[g][3] = __byte_perm(p2, p3, 0x7632);
+            }
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++)
+            {
+                sum[0][4 * i + bb] = dp4a_us(col[1][bb], B[0], dp4a_us(col[0][bb], A[0], 0));
+#pragma unroll
+                for (int y = 1; y < 4; y++)
+                    sum[y][4 * i + bb] = dp4a_us(col[2][bb], C[y], dp4a_us(col[1][bb], B[y], dp4a_us(col[0][bb], A[y], 0)));
+            }
+        }
+    }
+    else
+    {
+        const int16_t* cy = c_lumaFilter[yf];
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+        {
+            int p[11];
+#pragma unroll
+            for (int k = 0; k < 11; k++) p[k] = (int)__ldg(s + (ptrdiff_t)k * rstride + x);
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+            {
+                int v = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) v += p[y + k] * cy[k];
+                sum[y][x] = v;
+            }
+        }
+    }
+}
+
+// 4 x 8 vertical 8-tap sums over int16 intermediate rows in shared memory (second stage of hv); m = (row y of the first
+// output row, first element of the strip), 16-byte aligned, row pitch `pitch` elements.  The 10 vertically adjacent row
+// pairs (q, q+1) of a column are packed once (PRMT); output row y consumes pairs y, y+2, y+4, y+6 with DP2A.
+__device__ __forceinline__ void me_vmid4(const int16_t* __restrict__ m, int pitch, int yf, int (&sum)[4][8])
+{
+    const uint32_t t0 = c_luma4[yf][0], t1 = c_luma4[yf][1];
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++)
+    {
+        uint32_t M[11][2];
+#pragma unroll
+        for (int k = 0; k < 11; k++) { const uint2 v = *(const uint2*)(m + k * pitch + 4 * hf); M[k][0] = v.x; M[k][1] = v.y; }
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+        {
+            uint32_t lo[10], hi[10];
+#pragma unroll
+            for (int q = 0; q < 10; q++)
+            {
+                lo[q] = __byte_perm(M[q][i], M[q + 1][i], 0x5410);       // (m[q][c], m[q+1][c]), c = 4 hf + 2 i
+                hi[q] = __byte_perm(M[q][i], M[q + 1][i], 0x7632);       // column c + 1
+            }
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+            {
+                int s0 = 0, s1 = 0;
+                s0 = dp2a_lo_ss(lo[y], t0, s0);     s1 = dp2a_lo_ss(hi[y], t0, s1);
+                s0 = dp2a_hi_ss(lo[y + 2], t0, s0); s1 = dp2a_hi_ss(hi[y + 2], t0, s1);
+                s0 = dp2a_lo_ss(lo[y + 4], t1, s0); s1 = dp2a_lo_ss(hi[y + 4], t1, s1);
+                s0 = dp2a_hi_ss(lo[y + 6], t1, s0); s1 = dp2a_hi_ss(hi[y + 6], t1, s1);
+                sum[y][4 * hf + 2 * i] = s0; sum[y][4 * hf + 2 * i + 1] = s1;
+            }
+        }
+    }
+}
+
 // jobs the row-segment kernel (k_interp_rows, below) takes; the generic kernel skips them
 __device__ __forceinline__ bool interp_fast_eligible(int op, const x265cu_interp_job& jb)
 {

@@ -474,6 +474,118 @@ __device__ __forceinline__ int me_subpel_small_t(const MeCtx<P>& c, int n, int q
 // One sub-pel candidate of a LARGE pow2 PU (w >= 8, more than 32 row segments), same lane = row-segment scheme in
 // bands of 16 rows: the band's 23 horizontally filtered rows go through shared memory (hv only), every lane then
 // produces row segments of the prediction in registers, 32 at a time.  All lanes get the distortion.
+// 8 reference pixels of a row at any byte phase as ints (forward declaration: defined with the lowres helpers below)
+template <typename P>
+__device__ __forceinline__ void me_load_row8(const P* __restrict__ p, int (&v)[8]);
+
+#ifndef ME_BIG_V1
+// LARGE pow2 PUs (w > 16 or h > 16; w >= 8): a lane owns an 8x4 UNIT = 4 consecutive rows of an 8-pixel strip, i.e.
+// exactly one 8x4 SATD tile: the Hadamard is entirely in the lane's registers (no shuffles) and the vertical filters
+// re-use their source rows (11 rows feed 4 output rows: me_vcol4 / me_vmid4).  The PU is processed in bands of
+// BR = min(h, 1024 / w) rows (a full warp of units for w = 64 / 32 / 16 with h >= 16 / 32 / 64); hv candidates first
+// write the band's BR + 7 horizontally filtered rows to shared memory (one row segment per lane-task).
+template <typename P>
+__device__ __forceinline__ int me_subpel_big(const MeCtx<P>& c, int qx, int qy, bool satd)
+{
+    constexpr int DEPTH = PixTraits<P>::depth;
+    const int lane = c.lane;
+    const int lgsegs = c.lgw - 3, segs = 1 << lgsegs;
+    const int xf = qx & 3, yf = qy & 3;
+    const P* r0 = c.ref[0] + (qx >> 2) + (ptrdiff_t)(qy >> 2) * c.rstride;
+    if (!(xf | yf) && !satd) return me_sad_direct(c, r0);             // full-pel SAD: the word-wise SAD core
+    int16_t* mid = c.sm->mid;
+    const int BR = min(c.h, 1024 >> c.lgw);
+    const int units = (BR >> 2) << lgsegs;
+    int acc = 0;
+    for (int y0 = 0; y0 < c.h; y0 += BR)
+    {
+        if (xf && yf)
+        {
+            __syncwarp();
+            const int tasks = (BR + 7) << lgsegs;
+            for (int t = lane; t < tasks; t += 32)
+            {
+                const int mrow = t >> lgsegs, seg = t & (segs - 1);
+                int sum[8];
+                me_hrow<P, 8>(r0 + (ptrdiff_t)(y0 - 3 + mrow) * c.rstride + seg * 8, xf, sum);
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    pk[i] = ((uint32_t)interp_finish<DEPTH>(sum[2 * i], 1) & 0xffffu) | ((uint32_t)interp_finish<DEPTH>(sum[2 * i + 1], 1) << 16);
+                *(uint4*)(mid + mrow * c.w + seg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            __syncwarp();
+        }
+        for (int u = lane; u < units; u += 32)
+        {
+            const int seg = u & (segs - 1), row = (u >> lgsegs) << 2;          // first row of the unit inside the band
+            const P* r = r0 + (ptrdiff_t)(y0 + row) * c.rstride + seg * 8;
+            int d[4][8];
+            if (!(xf | yf))
+            {
+#pragma unroll
+                for (int y = 0; y < 4; y++) me_load_row8<P>(r + (ptrdiff_t)y * c.rstride, d[y]);
+            }
+            else if (!yf)
+            {
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+                {
+                    me_hrow<P, 8>(r + (ptrdiff_t)y * c.rstride, xf, d[y]);
+#pragma unroll
+                    for (int x = 0; x < 8; x++) d[y][x] = interp_finish<DEPTH>(d[y][x], 0);
+                }
+            }
+            else if (!xf)
+            {
+                me_vcol4<P>(r - 3 * (ptrdiff_t)c.rstride, c.rstride, yf, d);
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+#pragma unroll
+                    for (int x = 0; x < 8; x++) d[y][x] = interp_finish<DEPTH>(d[y][x], 0);
+            }
+            else
+            {
+                me_vmid4(mid + row * c.w + seg * 8, c.w, yf, d);
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+#pragma unroll
+                    for (int x = 0; x < 8; x++) d[y][x] = interp_finish<DEPTH>(d[y][x], 2);
+            }
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+            {
+                int fv[8];
+                me_load_fenc<P, 8>(c, c.fenc + (ptrdiff_t)(y0 + row + y) * c.fstride + seg * 8, fv);
+#pragma unroll
+                for (int x = 0; x < 8; x++) d[y][x] = fv[x] - d[y][x];
+            }
+            int part = 0;
+            if (!satd)
+            {
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+#pragma unroll
+                    for (int x = 0; x < 8; x++) part += abs(d[y][x]);
+            }
+            else
+            {   // one 8x4 tile (pixel.cpp:239-261): two 4x4 Hadamards, halved together
+#pragma unroll
+                for (int y = 0; y < 4; y++) { had4(d[y][0], d[y][1], d[y][2], d[y][3]); had4(d[y][4], d[y][5], d[y][6], d[y][7]); }
+#pragma unroll
+                for (int x = 0; x < 8; x++)
+                {
+                    had4(d[0][x], d[1][x], d[2][x], d[3][x]);
+                    part += abs(d[0][x]) + abs(d[1][x]) + abs(d[2][x]) + abs(d[3][x]);
+                }
+                part >>= 1;
+            }
+            acc += part;
+        }
+    }
+    return warp_sum(acc);
+}
+#else
 template <typename P>
 __device__ __forceinline__ int me_subpel_big(const MeCtx<P>& c, int qx, int qy, bool satd)
 {
@@ -580,6 +692,8 @@ __device__ __forceinline__ int me_subpel_big(const MeCtx<P>& c, int qx, int qy, 
     }
     return warp_sum(acc);
 }
+
+#endif
 
 template <typename P>
 __device__ __forceinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
