@@ -309,8 +309,9 @@ __device__ __forceinline__ void me_vmid4(const int16_t* __restrict__ m, int pitc
 // jobs the row-segment kernel (k_interp_rows, below) takes; the generic kernel skips them
 __device__ __forceinline__ bool interp_fast_eligible(int op, const x265cu_interp_job& jb)
 {
-    return jb.ntaps == 8 && (jb.w & 7) == 0 && jb.w <= 64 && jb.h > 0 &&
-           (op == X265CU_HPP || op == X265CU_HPS || op == X265CU_VPP || op == X265CU_VPS || op == X265CU_HVPP);
+    const bool vert = op == X265CU_VPP || op == X265CU_VPS || op == X265CU_HVPP;        // 4-row units: h must be a multiple of 4
+    return jb.ntaps == 8 && (jb.w & 7) == 0 && jb.w <= 64 && jb.h > 0 && (!vert || (jb.h & 3) == 0) &&
+           (op == X265CU_HPP || op == X265CU_HPS || vert);
 }
 
 // One CTA per job.  The source window (block + filter halo) is staged once in shared memory as int16,
@@ -457,14 +458,18 @@ __global__ void __launch_bounds__(256) k_interp_rows(int op, const P* __restrict
                     *(uint4*)(mid + mrow * w + seg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
                 __syncwarp();
-                for (int u = lane; u < rows * segs; u += 32)
-                {
-                    const int row = u / segs, seg = u - row * segs;
-                    int v[8];
-                    me_vmid<8>(mid + row * w + seg * 8, w, jb.idxY, v);
+                for (int u = lane; u < (rows >> 2) * segs; u += 32)
+                {   // 8x4 unit per lane-task: 11 intermediate rows feed 4 output rows
+                    const int grp = u / segs, seg = u - grp * segs, row = grp * 4;
+                    int v[4][8];
+                    me_vmid4(mid + row * w + seg * 8, w, jb.idxY, v);
 #pragma unroll
-                    for (int x = 0; x < 8; x++) v[x] = interp_finish<DEPTH>(v[x], 2);
-                    interp_store8<P, P>(d0 + (ptrdiff_t)(y0 + row) * jb.d_stride + seg * 8, v, vec);
+                    for (int y = 0; y < 4; y++)
+                    {
+#pragma unroll
+                        for (int x = 0; x < 8; x++) v[y][x] = interp_finish<DEPTH>(v[y][x], 2);
+                        interp_store8<P, P>(d0 + (ptrdiff_t)(y0 + row + y) * jb.d_stride + seg * 8, v[y], vec);
+                    }
                 }
             }
         }
@@ -477,13 +482,30 @@ __global__ void __launch_bounds__(256) k_interp_rows(int op, const P* __restrict
             const size_t dsz = toShort ? 2 : sizeof(P);
             const uintptr_t dbase = (uintptr_t)dstv + (size_t)jb.d_off * dsz;
             const bool vec = ((dbase | (uintptr_t)((size_t)jb.d_stride * dsz)) & (dsz == 1 ? 7 : 15)) == 0;
+            if (!horiz)
+            {   // vertical: 8x4 unit per lane-task, 11 source rows feed 4 output rows (me_vcol4)
+                for (int u = lane; u < (jb.h >> 2) * segs; u += 32)
+                {
+                    const int grp = u / segs, seg = u - grp * segs, row = grp * 4;
+                    int v[4][8];
+                    me_vcol4<P>(s0 + (ptrdiff_t)(row - 3) * jb.s_stride + seg * 8, jb.s_stride, jb.idxX, v);
+#pragma unroll
+                    for (int y = 0; y < 4; y++)
+                    {
+#pragma unroll
+                        for (int x = 0; x < 8; x++) v[y][x] = interp_finish<DEPTH>(v[y][x], toShort ? 1 : 0);
+                        if (toShort) interp_store8<P, int16_t>((int16_t*)dbase + (ptrdiff_t)(row + y) * jb.d_stride + seg * 8, v[y], vec);
+                        else         interp_store8<P, P>((P*)dbase + (ptrdiff_t)(row + y) * jb.d_stride + seg * 8, v[y], vec);
+                    }
+                }
+                continue;
+            }
             for (int u = lane; u < rows * segs; u += 32)
             {
                 const int row = u / segs, seg = u - row * segs;
                 const P* s = s0 + (ptrdiff_t)(row - ext) * jb.s_stride + seg * 8;
                 int v[8];
-                if (horiz) me_hrow<P, 8>(s, jb.idxX, v);
-                else       me_vcol<P, 8>(s - 3 * (ptrdiff_t)jb.s_stride, jb.s_stride, jb.idxX, v);
+                me_hrow<P, 8>(s, jb.idxX, v);
 #pragma unroll
                 for (int x = 0; x < 8; x++) v[x] = interp_finish<DEPTH>(v[x], toShort ? 1 : 0);
                 if (toShort) interp_store8<P, int16_t>((int16_t*)dbase + (ptrdiff_t)row * jb.d_stride + seg * 8, v, vec);

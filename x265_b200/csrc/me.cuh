@@ -89,7 +89,15 @@ __device__ __forceinline__ int me_sad_multi_t(const MeCtx<P>& c, const uint8_t* 
     const unsigned sh = ((unsigned)cptr & 3u) * 8u;
     const int rsB = c.rstride * (int)sizeof(P), fsB = c.fstride * (int)sizeof(P);
     const int subcol = sub & ((1 << lgcols) - 1), subrow = sub >> lgcols;
+#ifndef ME_SAD_V1
+    // 16- and 8-byte segments read the reference as 8-byte aligned LDG.64 (three / two instead of five / three LDG.32: the
+    // kernel sits at the LSU issue floor) and pick the word phase with one select per word; row pitch and column step are
+    // multiples of 8 bytes, so the phase is the same for every segment of the walk
+    const bool hi8 = SEGW >= 2 && ((unsigned)cptr & 4u) != 0;
+    const uint8_t* rrow = (const uint8_t*)(cptr & ~(uintptr_t)(SEGW >= 2 ? 7 : 3)) + subrow * rsB + subcol * (SEGW * 4);
+#else
     const uint8_t* rrow = (const uint8_t*)(cptr & ~(uintptr_t)3) + subrow * rsB + subcol * (SEGW * 4);
+#endif
     const uint8_t* frow = (const uint8_t*)c.fenc + subrow * fsB + subcol * (SEGW * 4);
     const int rowStepR = rsB << lgrows, rowStepF = fsB << lgrows, colStep = (SEGW * 4) << lgcols;
     const int nrows = c.h >> lgrows, ncols = 1 << (lgspr - lgcols);
@@ -105,14 +113,24 @@ __device__ __forceinline__ int me_sad_multi_t(const MeCtx<P>& c, const uint8_t* 
             if (SEGW == 4)
             {
                 const uint4 f = __ldg((const uint4*)fp);
+#ifndef ME_SAD_V1
+                const uint2 a0 = __ldg((const uint2*)rp), a1 = __ldg((const uint2*)rp + 1), a2 = __ldg((const uint2*)rp + 2);
+                const uint32_t w0 = hi8 ? a0.y : a0.x, w1 = hi8 ? a1.x : a0.y, w2 = hi8 ? a1.y : a1.x, w3 = hi8 ? a2.x : a1.y, w4 = hi8 ? a2.y : a2.x;
+#else
                 const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2), w3 = __ldg(ap + 3), w4 = __ldg(ap + 4);
+#endif
                 acc = sad_word<P>(f.x, __funnelshift_r(w0, w1, sh), acc); acc = sad_word<P>(f.y, __funnelshift_r(w1, w2, sh), acc);
                 acc = sad_word<P>(f.z, __funnelshift_r(w2, w3, sh), acc); acc = sad_word<P>(f.w, __funnelshift_r(w3, w4, sh), acc);
             }
             else if (SEGW == 2)
             {
                 const uint2 f = __ldg((const uint2*)fp);
+#ifndef ME_SAD_V1
+                const uint2 a0 = __ldg((const uint2*)rp), a1 = __ldg((const uint2*)rp + 1);
+                const uint32_t w0 = hi8 ? a0.y : a0.x, w1 = hi8 ? a1.x : a0.y, w2 = hi8 ? a1.y : a1.x;
+#else
                 const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
+#endif
                 acc = sad_word<P>(f.x, __funnelshift_r(w0, w1, sh), acc); acc = sad_word<P>(f.y, __funnelshift_r(w1, w2, sh), acc);
             }
             else
@@ -1494,6 +1512,7 @@ __device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j,
     // widest lane segment (16 / 8 / 4 bytes) that both a PU row and the fenc row alignment allow
     const unsigned fal = (unsigned)(uintptr_t)c.fenc | (unsigned)(fstride * (int)sizeof(P));
     c.lgsegw = min(c.lgwpr, (fal & 15u) == 0 ? 2 : (fal & 7u) == 0 ? 1 : 0);
+    if ((unsigned)(rstride * (int)sizeof(P)) & 7u) c.lgsegw = 0;        // the 8-byte aligned reference loads need an 8-byte row pitch
 }
 
 // Persistent warps with a dynamic job queue (jobs differ by up to 64x in work).  The search is split into
