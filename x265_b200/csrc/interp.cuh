@@ -309,9 +309,8 @@ __device__ __forceinline__ void me_vmid4(const int16_t* __restrict__ m, int pitc
 // jobs the row-segment kernel (k_interp_rows, below) takes; the generic kernel skips them
 __device__ __forceinline__ bool interp_fast_eligible(int op, const x265cu_interp_job& jb)
 {
-    const bool vert = op == X265CU_VPP || op == X265CU_VPS || op == X265CU_HVPP;        // 4-row units: h must be a multiple of 4
-    return jb.ntaps == 8 && (jb.w & 7) == 0 && jb.w <= 64 && jb.h > 0 && (!vert || (jb.h & 3) == 0) &&
-           (op == X265CU_HPP || op == X265CU_HPS || vert);
+    return jb.ntaps == 8 && (jb.w & 7) == 0 && jb.w <= 64 && jb.h > 0 &&
+           (op == X265CU_HPP || op == X265CU_HPS || op == X265CU_VPP || op == X265CU_VPS || op == X265CU_HVPP);
 }
 
 // One CTA per job.  The source window (block + filter halo) is staged once in shared memory as int16,
@@ -423,21 +422,23 @@ __device__ __forceinline__ void interp_store8(D* __restrict__ d, const int (&v)[
     }
 }
 
-template <typename P>
+// GROUP: 0 = horizontal (hpp, hps), 1 = vertical (vpp, vps), 2 = hvpp -- separate instantiations so that each pass
+// keeps its own register budget (the 8x4-unit vertical path needs 80 registers, the horizontal one 48).
+template <typename P, int GROUP>
 __global__ void __launch_bounds__(256) k_interp_rows(int op, const P* __restrict__ src, void* __restrict__ dstv,
                                                      const x265cu_interp_job* __restrict__ jobs, int n)
 {
     constexpr int DEPTH = PixTraits<P>::depth;
-    __shared__ __align__(16) int16_t s_mid[8][(IP_BAND + 7) * 64];
+    __shared__ __align__(16) int16_t s_mid[GROUP == 2 ? 8 : 1][GROUP == 2 ? (IP_BAND + 7) * 64 : 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int16_t* mid = s_mid[warp];
+    int16_t* mid = s_mid[GROUP == 2 ? warp : 0];
     for (int j = blockIdx.x * 8 + warp; j < n; j += gridDim.x * 8)
     {
         const x265cu_interp_job jb = jobs[j];
         if (!interp_fast_eligible(op, jb)) continue;
         const int w = jb.w, segs = w >> 3;
         const P* s0 = src + jb.s_off;
-        if (op == X265CU_HVPP)
+        if (GROUP == 2)
         {
             P* d0 = (P*)dstv + jb.d_off;
             const bool vec = (((uintptr_t)d0 | (uintptr_t)((size_t)jb.d_stride * sizeof(P))) & 7) == 0 && sizeof(P) == 1 ||
@@ -458,32 +459,27 @@ __global__ void __launch_bounds__(256) k_interp_rows(int op, const P* __restrict
                     *(uint4*)(mid + mrow * w + seg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
                 __syncwarp();
-                for (int u = lane; u < (rows >> 2) * segs; u += 32)
-                {   // 8x4 unit per lane-task: 11 intermediate rows feed 4 output rows
-                    const int grp = u / segs, seg = u - grp * segs, row = grp * 4;
-                    int v[4][8];
-                    me_vmid4(mid + row * w + seg * 8, w, jb.idxY, v);
+                for (int u = lane; u < rows * segs; u += 32)
+                {
+                    const int row = u / segs, seg = u - row * segs;
+                    int v[8];
+                    me_vmid<8>(mid + row * w + seg * 8, w, jb.idxY, v);
 #pragma unroll
-                    for (int y = 0; y < 4; y++)
-                    {
-#pragma unroll
-                        for (int x = 0; x < 8; x++) v[y][x] = interp_finish<DEPTH>(v[y][x], 2);
-                        interp_store8<P, P>(d0 + (ptrdiff_t)(y0 + row + y) * jb.d_stride + seg * 8, v[y], vec);
-                    }
+                    for (int x = 0; x < 8; x++) v[x] = interp_finish<DEPTH>(v[x], 2);
+                    interp_store8<P, P>(d0 + (ptrdiff_t)(y0 + row) * jb.d_stride + seg * 8, v, vec);
                 }
             }
         }
         else
         {
-            const bool horiz = op == X265CU_HPP || op == X265CU_HPS;
             const bool toShort = op == X265CU_HPS || op == X265CU_VPS;
             const int ext = (op == X265CU_HPS && jb.rowExt) ? 3 : 0;          // rowExt: 3 rows above .. 4 rows below, dst row 0 = first of them
             const int rows = jb.h + (ext ? 7 : 0);
             const size_t dsz = toShort ? 2 : sizeof(P);
             const uintptr_t dbase = (uintptr_t)dstv + (size_t)jb.d_off * dsz;
             const bool vec = ((dbase | (uintptr_t)((size_t)jb.d_stride * dsz)) & (dsz == 1 ? 7 : 15)) == 0;
-            if (!horiz)
-            {   // vertical: 8x4 unit per lane-task, 11 source rows feed 4 output rows (me_vcol4)
+            if (GROUP == 1 && (jb.h & 3) == 0 && (jb.h >> 2) * segs >= 32)
+            {   // vertical, a warp's worth of 8x4 units: 11 source rows feed 4 output rows (me_vcol4)
                 for (int u = lane; u < (jb.h >> 2) * segs; u += 32)
                 {
                     const int grp = u / segs, seg = u - grp * segs, row = grp * 4;
@@ -505,7 +501,8 @@ __global__ void __launch_bounds__(256) k_interp_rows(int op, const P* __restrict
                 const int row = u / segs, seg = u - row * segs;
                 const P* s = s0 + (ptrdiff_t)(row - ext) * jb.s_stride + seg * 8;
                 int v[8];
-                me_hrow<P, 8>(s, jb.idxX, v);
+                if (GROUP == 0) me_hrow<P, 8>(s, jb.idxX, v);
+                else            me_vcol<P, 8>(s - 3 * (ptrdiff_t)jb.s_stride, jb.s_stride, jb.idxX, v);
 #pragma unroll
                 for (int x = 0; x < 8; x++) v[x] = interp_finish<DEPTH>(v[x], toShort ? 1 : 0);
                 if (toShort) interp_store8<P, int16_t>((int16_t*)dbase + (ptrdiff_t)row * jb.d_stride + seg * 8, v, vec);
@@ -513,6 +510,14 @@ __global__ void __launch_bounds__(256) k_interp_rows(int op, const P* __restrict
             }
         }
     }
+}
+
+template <typename P>
+static void launch_interp_rows(x265cu_ctx* ctx, int fb, int op, const void* src, void* dst, const x265cu_interp_job* jobs, int n)
+{
+    if (op == X265CU_HVPP)                          k_interp_rows<P, 2><<<fb, 256, 0, ctx->stream>>>(op, (const P*)src, dst, jobs, n);
+    else if (op == X265CU_VPP || op == X265CU_VPS)  k_interp_rows<P, 1><<<fb, 256, 0, ctx->stream>>>(op, (const P*)src, dst, jobs, n);
+    else                                            k_interp_rows<P, 0><<<fb, 256, 0, ctx->stream>>>(op, (const P*)src, dst, jobs, n);
 }
 
 static int launch_interp(x265cu_ctx* ctx, int depth, int op, const void* src, void* dst, const x265cu_interp_job* jobs, int n)
@@ -524,8 +529,8 @@ static int launch_interp(x265cu_ctx* ctx, int depth, int op, const void* src, vo
     {   // the row-segment kernel takes the eligible jobs (one warp each), the generic kernel the rest
         int fb = (n + 7) / 8;
         if (fb > ctx->sm_count * 8) fb = ctx->sm_count * 8;
-        if (depth == 8) k_interp_rows<uint8_t><<<fb, 256, 0, ctx->stream>>>(op, (const uint8_t*)src, dst, jobs, n);
-        else            k_interp_rows<uint16_t><<<fb, 256, 0, ctx->stream>>>(op, (const uint16_t*)src, dst, jobs, n);
+        if (depth == 8) launch_interp_rows<uint8_t>(ctx, fb, op, src, dst, jobs, n);
+        else            launch_interp_rows<uint16_t>(ctx, fb, op, src, dst, jobs, n);
         CU_LAUNCH_CHECK(ctx);
     }
     if (depth == 8) k_interp<uint8_t><<<blocks, 256, 0, ctx->stream>>>(op, src, dst, jobs, n);
