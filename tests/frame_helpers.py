@@ -52,14 +52,16 @@ def pad_plane(img, depth):
     return buf, stride, MARGIN_Y * stride + MARGIN_X
 
 
-def make_field(W, H, numRefs, seed=7):
-    """16x16-granular qpel predictor field: global motion (-3*(r+1), 2*(r+1)) px plus jitter."""
+def make_field(W, H, numRefs, seed=7, dist=0):
+    """16x16-granular qpel predictor field: global motion (-3*d, 2*d) px plus jitter, d = r + 1 + dist = the temporal
+    distance from the analysed frame to reference r (`dist` = how many frames the analysed frame lies beyond the one
+    right after the newest reference: what AMVP / the lowres MVs of that frame would report)."""
     rng = np.random.default_rng(seed)
     fw, fh = (W + 15) // 16, (H + 15) // 16
     f = np.zeros((numRefs, fh, fw, 2), np.int16)
     for r in range(numRefs):
-        f[r, :, :, 0] = -12 * (r + 1) + rng.integers(-6, 7, (fh, fw))
-        f[r, :, :, 1] = 8 * (r + 1) + rng.integers(-6, 7, (fh, fw))
+        f[r, :, :, 0] = -12 * (r + 1 + dist) + rng.integers(-6, 7, (fh, fw))
+        f[r, :, :, 1] = 8 * (r + 1 + dist) + rng.integers(-6, 7, (fh, fw))
     return f
 
 
