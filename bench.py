@@ -206,9 +206,11 @@ def run_ours(args, rank, world, local_rank):
     rows_mode = args.shard == "rows"
     cur = gen_luma(W, H, NREFS + (0 if rows_mode else shard.frame_of(0, rank, world)))
     my_rows = shard.row_blocks(an.ctu_rows, rank, world, "block") if rows_mode else [(0, an.ctu_rows)]
-    # predictor field of THIS rank's frame: its temporal distance to reference r is r + 1 + (frame - NREFS), so every rank
-    # searches around the true motion of its own frame (as AMVP / the lowres MVs would give it) and the ranks' work is alike
-    field = make_field(W, H, NREFS, dist=0 if rows_mode else shard.frame_of(0, rank, world))
+    # predictor field of THIS rank's frame.  The clip's global motion to reference r is (+3, -2) * (r + 1 + k) px for the frame
+    # k positions after the first one; the N=1 field (k = 0) sits at (-3, +2) * (r + 1), i.e. off by (6, -4) * (r + 1) px.
+    # Rank k gets the field with the SAME offset from its own true motion (dist = -k), so every rank faces the same search
+    # problem (measured with the CPU oracle: equal cost sums) instead of a predictor that is further off the later the frame.
+    field = make_field(W, H, NREFS, dist=0 if rows_mode else -shard.frame_of(0, rank, world))
     # pinned host buffers: these are what the user hands to the public call
     pin = lib.L.x265cu_host_alloc(W * H)
     h_fenc = np.frombuffer((C.c_uint8 * (W * H)).from_address(pin), np.uint8).reshape(H, W)

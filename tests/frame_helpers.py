@@ -53,9 +53,9 @@ def pad_plane(img, depth):
 
 
 def make_field(W, H, numRefs, seed=7, dist=0):
-    """16x16-granular qpel predictor field: global motion (-3*d, 2*d) px plus jitter, d = r + 1 + dist = the temporal
-    distance from the analysed frame to reference r (`dist` = how many frames the analysed frame lies beyond the one
-    right after the newest reference: what AMVP / the lowres MVs of that frame would report)."""
+    """16x16-granular qpel predictor field: (-3*d, 2*d) px plus jitter with d = r + 1 + dist.  dist = 0 is the field of
+    the frame right after the newest reference; bench.py passes dist = -k for the frame k positions later so that the
+    field keeps the same offset from that frame's true global motion ((+3, -2) px per frame of distance)."""
     rng = np.random.default_rng(seed)
     fw, fh = (W + 15) // 16, (H + 15) // 16
     f = np.zeros((numRefs, fh, fw, 2), np.int16)
