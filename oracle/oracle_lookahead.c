@@ -4,10 +4,12 @@
  *   CostEstimateGroup::estimateFrameCost     encoder/slicetype.cpp:3115-3214 (serial path)
  *   CostEstimateGroup::estimateCUCost        encoder/slicetype.cpp:3216-3388 (no HME / weightp / AQ)
  *   ReferencePlanes::lowresMC                common/lowres.h:67-92
+ *   LookaheadTLD::weightsAnalyse / weightCostLuma  encoder/slicetype.cpp:807-840, 860-961 (end of this file)
  * Pinned against the real classes through oracle/_ref (x265ref_la_*), tests/test_lookahead_oracle_vs_ref.py.
  */
 #include "oracle.h"
 #include <string.h>
+#include <math.h>
 
 #define COST_MAX (1 << 28)               /* motion.h:65 */
 #define LOWRES_COST_MASK ((1 << 14) - 1) /* slicetype.h:41-42 */
@@ -203,4 +205,110 @@ void orc_lookahead_frame_cost(orc_la_job* j)
         }
     }
     j->out[0] = costEst; j->out[1] = costEstAq; j->out[2] = intraMbs;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Lookahead weighted-prediction analysis: LookaheadTLD::weightCostLuma + weightsAnalyse
+ * (encoder/slicetype.cpp:807-840, 860-961; WeightParam::setFromWeightAndOffset common/slice.h:304-316).
+ * Planes are the whole padded lowres buffers (Lowres::buffer[i], common/lowres.cpp:132-139): `planesize` pixels each,
+ * picture origin at `padoffset`.  The picture statistics wp_sum / wp_ssd of luma (accumulated by the reference in
+ * calcAdaptiveQuantFrame, slicetype.cpp:49-57, 462-480, 665-676) are inputs.
+ * Returns Lowres::weightedRef[].isWeighted; when 1, wbuf holds the 4 re-weighted planes and wp = {scale, denom, offset}.
+ * wbuf (4 * planesize pixels) is also the scratch of the trial weightings, exactly like LookaheadTLD::wbuffer.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct { int wtPresent, inputWeight, log2WeightDenom, inputOffset; } orc_wp;
+
+static uint32_t la_weight_cost_luma(const pixel* fencBuf, const pixel* const* refBuf, pixel* wbuf, intptr_t stride, int width, int lines,
+                                    int paddedLines, intptr_t padoffset, const int32_t* intraCost, const orc_wp* wp)
+{
+    const pixel* src = refBuf[0] + padoffset;
+    if (wp->wtPresent)
+    {
+        const int offset = wp->inputOffset << (ORC_DEPTH - 8);
+        const int scale = wp->inputWeight, denom = wp->log2WeightDenom;
+        const int round = denom ? 1 << (denom - 1) : 0;
+        const int correction = 14 - ORC_DEPTH;
+        orc_weight_pp(refBuf[0], wbuf, stride, (int)stride, paddedLines, scale, round << correction, denom + correction, offset);
+        src = wbuf + padoffset;
+    }
+    const pixel* fenc = fencBuf + padoffset;
+    uint32_t cost = 0;
+    int mb = 0;
+    for (int y = 0; y < lines; y += 8)
+        for (int x = 0; x < width; x += 8, mb++)
+        {
+            const intptr_t pixoff = (intptr_t)y * stride + x;
+            const int satd = orc_satd(src + pixoff, stride, fenc + pixoff, stride, 8, 8);
+            cost += satd < intraCost[mb] ? (uint32_t)satd : (uint32_t)intraCost[mb];
+        }
+    return cost;
+}
+
+int orc_la_weights_analyse(const pixel* fencBuf, const pixel* const* refBuf, pixel* wbuf, intptr_t planesize, intptr_t stride,
+                           int width, int lines, intptr_t padoffset, const int32_t* intraCost,
+                           uint64_t fencSum, uint64_t fencSsd, uint64_t refSum, uint64_t refSsd, int* wpOut)
+{
+    static const float epsilon = 1.f / 128.f;
+    const int paddedLines = (int)(planesize / stride);
+    orc_wp wp = { 0, 0, 0, 0 };
+    float guessScale, fencMean, refMean;
+    if (fencSsd && refSsd) guessScale = sqrtf((float)fencSsd / refSsd);
+    else                   guessScale = 1.0f;
+    fencMean = (float)fencSum / (lines * width) / (1 << (ORC_DEPTH - 8));
+    refMean  = (float)refSum / (lines * width) / (1 << (ORC_DEPTH - 8));
+    if (fabsf(refMean - fencMean) < 0.5f && fabsf(1.f - guessScale) < epsilon)
+        return 0;
+
+    int minoff = 0, minscale, mindenom;
+    unsigned int minscore = 0, origscore = 1;
+    int found = 0;
+    /* wp.setFromWeightAndOffset((int)(guessScale * 128 + 0.5f), 0, 7, true): note wtPresent stays 0 for the first cost */
+    wp.inputOffset = 0; wp.log2WeightDenom = 7; wp.inputWeight = (int)(guessScale * 128 + 0.5f);
+    while (wp.log2WeightDenom > 0 && wp.inputWeight > 127) { wp.log2WeightDenom--; wp.inputWeight >>= 1; }
+    if (wp.inputWeight > 127) wp.inputWeight = 127;
+    mindenom = wp.log2WeightDenom;
+    minscale = wp.inputWeight;
+
+    origscore = minscore = la_weight_cost_luma(fencBuf, refBuf, wbuf, stride, width, lines, paddedLines, padoffset, intraCost, &wp);
+    if (!minscore)
+        return 0;
+
+    unsigned int s = 0;
+    int curScale = minscale;
+    int curOffset = (int)(fencMean - refMean * curScale / (1 << mindenom) + 0.5f);
+    if (curOffset < -128 || curOffset > 127)
+    {
+        curOffset = curOffset < -128 ? -128 : (curOffset > 127 ? 127 : curOffset);
+        curScale = (int)((1 << mindenom) * (fencMean - curOffset) / refMean + 0.5f);
+        curScale = curScale < 0 ? 0 : (curScale > 127 ? 127 : curScale);
+    }
+    wp.inputWeight = curScale; wp.log2WeightDenom = mindenom; wp.inputOffset = curOffset; wp.wtPresent = 1;
+    s = la_weight_cost_luma(fencBuf, refBuf, wbuf, stride, width, lines, paddedLines, padoffset, intraCost, &wp);
+    if (s < minscore) { minscore = s; minscale = curScale; minoff = curOffset; found = 1; }
+
+    /* use a smaller denominator if possible */
+    if (mindenom > 0 && !(minscale & 1))
+    {
+        int idx = 0;
+        while (!((minscale >> idx) & 1) && idx < 31) idx++;         /* CTZ; minscale = 0 cannot get here with found = 1 mattering */
+        if (minscale == 0) idx = 0;
+        int shift = idx < mindenom ? idx : mindenom;
+        mindenom -= shift;
+        minscale >>= shift;
+    }
+
+    if (!found || (minscale == 1 << mindenom && minoff == 0) || (float)minscore / origscore > 0.998f)
+        return 0;
+
+    wp.inputWeight = minscale; wp.log2WeightDenom = mindenom; wp.inputOffset = minoff; wp.wtPresent = 1;
+    {
+        const int offset = wp.inputOffset << (ORC_DEPTH - 8);
+        const int scale = wp.inputWeight, denom = wp.log2WeightDenom;
+        const int round = denom ? 1 << (denom - 1) : 0;
+        const int correction = 14 - ORC_DEPTH;
+        for (int i = 0; i < 4; i++)
+            orc_weight_pp(refBuf[i], wbuf + i * planesize, stride, (int)stride, paddedLines, scale, round << correction, denom + correction, offset);
+    }
+    wpOut[0] = minscale; wpOut[1] = mindenom; wpOut[2] = minoff;
+    return 1;
 }

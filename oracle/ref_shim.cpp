@@ -337,6 +337,27 @@ int64_t x265ref_la_cost(void* hv, int p0, int p1, int b)
     return est.singleCost(p0, p1, b, false);
 }
 
+/* LookaheadTLD::weightsAnalyse (slicetype.cpp:860-961, with weightCostLuma :807-840) on frames b (fenc) and p0 (ref), with the
+ * picture statistics Lowres::wp_sum[0] / wp_ssd[0] supplied by the caller (the reference accumulates them in
+ * calcAdaptiveQuantFrame, slicetype.cpp:49-57, 462-480, 665-676: inputs of the analysis, not part of it).
+ * stats = {fenc sum, fenc ssd, ref sum, ref ssd}.  Returns weightedRef[b - p0].isWeighted; out = {planesize (pixels),
+ * paddedLines}; when weighted and wplanes != NULL, the 4 re-weighted planes (4 * planesize pixels) are copied out. */
+int x265ref_la_weights(void* hv, int b, int p0, const uint64_t* stats, int64_t* out, pixel* wplanes)
+{
+    RefLookahead* h = (RefLookahead*)hv;
+    Lowres& fenc = *h->frames[b];
+    Lowres& ref = *h->frames[p0];
+    fenc.wp_sum[0] = stats[0]; fenc.wp_ssd[0] = stats[1]; ref.wp_sum[0] = stats[2]; ref.wp_ssd[0] = stats[3];
+    LookaheadTLD& tld = h->la->m_tld[0];
+    fenc.weightedRef[b - p0].isWeighted = false;
+    tld.weightsAnalyse(fenc, ref);
+    const intptr_t planesize = fenc.buffer[1] - fenc.buffer[0];
+    out[0] = (int64_t)planesize; out[1] = tld.paddedLines;
+    const int w = fenc.weightedRef[b - p0].isWeighted ? 1 : 0;
+    if (w && wplanes) memcpy(wplanes, tld.wbuffer[0], sizeof(pixel) * 4 * planesize);
+    return w;
+}
+
 /* geometry: out = {width8, height8, lumaStride, lowres width, lowres lines, marginX, marginY} */
 void x265ref_la_geometry(void* hv, int* out)
 {

@@ -72,3 +72,56 @@ def test_lookahead(depth, size, noise):
         st = ref.get(b, 6, d0, d1, np.int64, 3)
         assert (int(st[0]), int(st[1])) == orc.fr[b]["costEst"][(d0, d1)]
         assert int(st[2]) == orc.fr[b]["intraMbs"].get(d0, 0)
+
+
+def _wp_stats(img):
+    """Lowres::wp_sum[0] / wp_ssd[0] as calcAdaptiveQuantFrame leaves them (slicetype.cpp:49-57, 462-480, 665-676):
+    sum of the luma samples and sum of squares minus the rounded mean-square term."""
+    a = img.astype(np.int64)
+    s, q, n = int(a.sum()), int((a * a).sum()), a.size
+    return s, q - (s * s + n // 2) // n
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("case", ["same", "fade", "fade2", "bright", "offset", "noise_fade"])
+def test_lookahead_weights_analyse(depth, case):
+    """LookaheadTLD::weightsAnalyse + weightCostLuma (slicetype.cpp:807-961): the decision and the 4 re-weighted lowres
+    planes of the oracle against the real class, on fades that take every exit of the analysis."""
+    R = load_ref(depth)
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    O = load_oracle(depth)
+    W, H = 416, 240
+    mx = (1 << depth) - 1
+    base = gen_luma(W, H, 0, s1=17.0, s2=11.0, bits=depth, noise=case.startswith("noise")).astype(np.float64)
+    nxt = gen_luma(W, H, 1, s1=17.0, s2=11.0, bits=depth, noise=case.startswith("noise")).astype(np.float64)
+    sc = 1 << (depth - 8)
+    # NB the analysis estimates the offset from full-resolution sums over the LOWRES area (slicetype.cpp:892-893), i.e. 4x the
+    # true mean difference, so only (nearly) pure scalings end up weighted; "offset" exercises the rejected path
+    cur = {"same": nxt, "fade": nxt * 0.78, "fade2": nxt * 0.55 + 1 * sc, "bright": nxt * 1.07, "offset": nxt + 21 * sc,
+           "noise_fade": nxt * 0.6}[case]
+    frames = [base.astype(pixel_dtype(depth)), np.clip(np.rint(cur), 0, mx).astype(pixel_dtype(depth))]
+    ref = RefLookahead(R, frames)
+    rows = ref.lh + 2 * MARGIN_Y
+    planesize = rows * ref.stride
+    bufs = [[ref.get(f, 7, k, 0, pixel_dtype(depth), planesize) for k in range(4)] for f in range(2)]
+    intra = ref.get(1, 0)
+    stats = np.array(list(_wp_stats(frames[1])) + list(_wp_stats(frames[0])), np.uint64)
+    out = np.zeros(2, np.int64)
+    wref = np.zeros(4 * planesize, pixel_dtype(depth))
+    R.x265ref_la_weights.argtypes = [P, I, I, P, P, P]
+    got_r = R.x265ref_la_weights(ref.h, 1, 0, ptr(stats), ptr(out), ptr(wref))
+    assert int(out[0]) == planesize and int(out[1]) == rows
+
+    refarr = (P * 4)(*[C.c_void_p(b.ctypes.data) for b in bufs[0]])
+    worc = np.zeros(4 * planesize, pixel_dtype(depth))
+    wp = np.zeros(3, np.int32)
+    O.orc_la_weights_analyse.argtypes = [P, P, P, IP, IP, I, I, IP, P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, P]
+    got_o = O.orc_la_weights_analyse(ptr(bufs[1][0]), refarr, ptr(worc), planesize, ref.stride, ref.lw, ref.lh,
+                                     MARGIN_Y * ref.stride + MARGIN_X, ptr(intra),
+                                     int(stats[0]), int(stats[1]), int(stats[2]), int(stats[3]), ptr(wp))
+    assert got_o == got_r, (case, got_o, got_r)
+    assert (got_r == 0) == (case in ("same", "offset", "noise_fade")), (case, got_r)   # noise: inter never beats intra, no gain
+    if got_r:
+        assert np.array_equal(worc, wref), (case, wp.tolist())
+        assert 0 <= wp[0] <= 127 and 0 <= wp[1] <= 7 and -128 <= wp[2] <= 127
