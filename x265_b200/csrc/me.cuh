@@ -89,15 +89,11 @@ __device__ __forceinline__ int me_sad_multi_t(const MeCtx<P>& c, const uint8_t* 
     const unsigned sh = ((unsigned)cptr & 3u) * 8u;
     const int rsB = c.rstride * (int)sizeof(P), fsB = c.fstride * (int)sizeof(P);
     const int subcol = sub & ((1 << lgcols) - 1), subrow = sub >> lgcols;
-#ifndef ME_SAD_V1
     // 16- and 8-byte segments read the reference as 8-byte aligned LDG.64 (three / two instead of five / three LDG.32: the
     // kernel sits at the LSU issue floor) and pick the word phase with one select per word; row pitch and column step are
     // multiples of 8 bytes, so the phase is the same for every segment of the walk
     const bool hi8 = SEGW >= 2 && ((unsigned)cptr & 4u) != 0;
     const uint8_t* rrow = (const uint8_t*)(cptr & ~(uintptr_t)(SEGW >= 2 ? 7 : 3)) + subrow * rsB + subcol * (SEGW * 4);
-#else
-    const uint8_t* rrow = (const uint8_t*)(cptr & ~(uintptr_t)3) + subrow * rsB + subcol * (SEGW * 4);
-#endif
     const uint8_t* frow = (const uint8_t*)c.fenc + subrow * fsB + subcol * (SEGW * 4);
     const int rowStepR = rsB << lgrows, rowStepF = fsB << lgrows, colStep = (SEGW * 4) << lgcols;
     const int nrows = c.h >> lgrows, ncols = 1 << (lgspr - lgcols);
@@ -113,24 +109,16 @@ __device__ __forceinline__ int me_sad_multi_t(const MeCtx<P>& c, const uint8_t* 
             if (SEGW == 4)
             {
                 const uint4 f = __ldg((const uint4*)fp);
-#ifndef ME_SAD_V1
                 const uint2 a0 = __ldg((const uint2*)rp), a1 = __ldg((const uint2*)rp + 1), a2 = __ldg((const uint2*)rp + 2);
                 const uint32_t w0 = hi8 ? a0.y : a0.x, w1 = hi8 ? a1.x : a0.y, w2 = hi8 ? a1.y : a1.x, w3 = hi8 ? a2.x : a1.y, w4 = hi8 ? a2.y : a2.x;
-#else
-                const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2), w3 = __ldg(ap + 3), w4 = __ldg(ap + 4);
-#endif
                 acc = sad_word<P>(f.x, __funnelshift_r(w0, w1, sh), acc); acc = sad_word<P>(f.y, __funnelshift_r(w1, w2, sh), acc);
                 acc = sad_word<P>(f.z, __funnelshift_r(w2, w3, sh), acc); acc = sad_word<P>(f.w, __funnelshift_r(w3, w4, sh), acc);
             }
             else if (SEGW == 2)
             {
                 const uint2 f = __ldg((const uint2*)fp);
-#ifndef ME_SAD_V1
                 const uint2 a0 = __ldg((const uint2*)rp), a1 = __ldg((const uint2*)rp + 1);
                 const uint32_t w0 = hi8 ? a0.y : a0.x, w1 = hi8 ? a1.x : a0.y, w2 = hi8 ? a1.y : a1.x;
-#else
-                const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
-#endif
                 acc = sad_word<P>(f.x, __funnelshift_r(w0, w1, sh), acc); acc = sad_word<P>(f.y, __funnelshift_r(w1, w2, sh), acc);
             }
             else
@@ -496,7 +484,6 @@ __device__ __forceinline__ int me_subpel_small_t(const MeCtx<P>& c, int n, int q
 template <typename P>
 __device__ __forceinline__ void me_load_row8(const P* __restrict__ p, int (&v)[8]);
 
-#ifndef ME_BIG_V1
 // LARGE pow2 PUs (w > 16 or h > 16; w >= 8): a lane owns an 8x4 UNIT = 4 consecutive rows of an 8-pixel strip, i.e.
 // exactly one 8x4 SATD tile: the Hadamard is entirely in the lane's registers (no shuffles) and the vertical filters
 // re-use their source rows (11 rows feed 4 output rows: me_vcol4 / me_vmid4).  The PU is processed in bands of
@@ -603,115 +590,6 @@ __device__ __forceinline__ int me_subpel_big(const MeCtx<P>& c, int qx, int qy, 
     }
     return warp_sum(acc);
 }
-#else
-template <typename P>
-__device__ __forceinline__ int me_subpel_big(const MeCtx<P>& c, int qx, int qy, bool satd)
-{
-    constexpr int DEPTH = PixTraits<P>::depth;
-    constexpr int NPX = 8;
-    const int lane = c.lane;
-    const int lgsegs = c.lgw - 3;
-    const int xf = qx & 3, yf = qy & 3;
-    const P* r0 = c.ref[0] + (qx >> 2) + (ptrdiff_t)(qy >> 2) * c.rstride;
-    int16_t* mid = c.sm->mid;
-    int acc = 0;
-    for (int y0 = 0; y0 < c.h; y0 += ME_BAND)
-    {
-        const int rows = min(ME_BAND, c.h - y0), lgrows = 31 - __clz(rows);
-        if (xf && yf)
-        {
-            __syncwarp();
-            const int tasks = (rows + 7) << lgsegs;
-            for (int t = lane; t < tasks; t += 32)
-            {
-                const int mrow = t >> lgsegs, seg = t & ((1 << lgsegs) - 1);
-                int sum[NPX];
-                me_hrow<P, NPX>(r0 + (ptrdiff_t)(y0 - 3 + mrow) * c.rstride + seg * 8, xf, sum);
-                uint32_t pk[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    pk[i] = ((uint32_t)interp_finish<DEPTH>(sum[2 * i], 1) & 0xffffu) | ((uint32_t)interp_finish<DEPTH>(sum[2 * i + 1], 1) << 16);
-                *(uint4*)(mid + mrow * c.w + seg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-            __syncwarp();
-        }
-        const int units = rows << lgsegs;
-        for (int u0 = 0; u0 < units; u0 += 32)
-        {
-            const int u = u0 + lane;
-            const bool live = u < units;
-            const int row = u & (rows - 1), seg = (u >> lgrows) & ((1 << lgsegs) - 1);
-            int d[NPX];
-            if (live)
-            {
-                const P* r = r0 + (ptrdiff_t)(y0 + row) * c.rstride + seg * 8;
-                int pr[NPX];
-                if (!(xf | yf))
-                {
-#pragma unroll
-                    for (int x = 0; x < NPX; x++) pr[x] = (int)__ldg(r + x);
-                }
-                else if (!yf)
-                {
-                    me_hrow<P, NPX>(r, xf, pr);
-#pragma unroll
-                    for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 0);
-                }
-                else if (!xf)
-                {
-                    me_vcol<P, NPX>(r - 3 * (ptrdiff_t)c.rstride, c.rstride, yf, pr);
-#pragma unroll
-                    for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 0);
-                }
-                else
-                {
-                    me_vmid<NPX>(mid + row * c.w + seg * 8, c.w, yf, pr);
-#pragma unroll
-                    for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], 2);
-                }
-                int fv[NPX];
-                me_load_fenc<P, NPX>(c, c.fenc + (ptrdiff_t)(y0 + row) * c.fstride + seg * 8, fv);
-#pragma unroll
-                for (int x = 0; x < NPX; x++) d[x] = fv[x] - pr[x];
-            }
-            else
-            {
-#pragma unroll
-                for (int x = 0; x < NPX; x++) d[x] = 0;
-            }
-            int part = 0;
-            if (!satd)
-            {
-#pragma unroll
-                for (int x = 0; x < NPX; x++) part += abs(d[x]);
-            }
-            else
-            {
-                had4(d[0], d[1], d[2], d[3]); had4(d[4], d[5], d[6], d[7]);
-#pragma unroll
-                for (int st = 1; st <= 2; st <<= 1)
-                {
-                    const bool up = (lane & st) != 0;
-#pragma unroll
-                    for (int x = 0; x < NPX; x++)
-                    {
-                        const int o = __shfl_xor_sync(0xffffffffu, d[x], st);
-                        d[x] = up ? o - d[x] : o + d[x];
-                    }
-                }
-#pragma unroll
-                for (int x = 0; x < NPX; x++) part += abs(d[x]);
-                part += __shfl_xor_sync(0xffffffffu, part, 1);
-                part += __shfl_xor_sync(0xffffffffu, part, 2);
-                part = (lane & 3) ? 0 : (part >> 1);
-            }
-            acc += part;
-        }
-    }
-    return warp_sum(acc);
-}
-
-#endif
 
 template <typename P>
 __device__ __forceinline__ int me_subpel_multi_small(const MeCtx<P>& c, int n, int qx, int qy, bool satd)
