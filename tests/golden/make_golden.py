@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from common import LUMA_PU, LUMA_CU, P, I, IP, load_ref, load_oracle, ref_fn, ptr, pixel_dtype  # noqa: E402
-from me_helpers import run_both  # noqa: E402
+from me_helpers import run_both, run_both_chroma, CHROMA_CASES  # noqa: E402
 
 
 def gen(depth):
@@ -83,6 +83,23 @@ def gen(depth):
     print("wrote primitives_%d.npz with %d arrays" % (depth, len(g)))
 
 
+def gen_chroma(depth):
+    """4:2:0 motionEstimate with the chroma-SATD term (motion.cpp:1601-1661): results of the real MotionEstimate driven
+    through the Yuv variant of setSourcePU (x265ref_motion_estimate_chroma); inputs are regenerated from the seed."""
+    R = load_ref(depth)
+    O = load_oracle(depth)
+    rng = np.random.default_rng(177 + depth)
+    rows = []
+    for (method, w, h, subme) in CHROMA_CASES:
+        r, o = run_both_chroma(O, R, depth, rng, w, h, method, subme, True, 57 if method == 3 else 16)
+        assert r == o
+        rows.append([method, w, h, subme] + list(r))
+    np.savez_compressed(os.path.join(HERE, "me_chroma_%d.npz" % depth), me_results=np.array(rows, np.int64))
+    print("wrote me_chroma_%d.npz with %d jobs" % (depth, len(rows)))
+
+
 if __name__ == "__main__":
     for d in (8, 10):
-        gen(d)
+        if "--chroma-only" not in sys.argv:
+            gen(d)
+        gen_chroma(d)

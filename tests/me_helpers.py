@@ -95,6 +95,11 @@ def run_both(O, R, depth, rng, w, h, method, subme, lowres, smooth, merange, qp=
     return (cr, int(out_r[0]), int(out_r[1])), (co, int(out_o[0]), int(out_o[1]))
 
 
+# jobs of tests/golden/me_chroma_*.npz (make_golden.py::gen_chroma): (method, w, h, subme)
+CHROMA_CASES = [(m, w, h, sub) for m in (1, 3) for (w, h) in ((8, 8), (16, 16), (32, 16), (16, 32), (64, 64), (32, 24), (8, 32), (16, 12), (8, 4))
+                for sub in (2, 3, 5)]
+
+
 def chroma_case(depth, rng, w, h, smooth, merange, W=256, H=192, margin=96):
     """Planes and window of one 4:2:0 motionEstimate job: luma + Cb/Cr of source and reference (chroma planes at
     half resolution with half the margin, so a luma offset maps to chroma by halving its row and column)."""

@@ -82,6 +82,7 @@ class _NoRef:
         def __call__(self, *a):
             return 0
     x265ref_motion_estimate = _Fn()
+    x265ref_motion_estimate_chroma = _Fn()
 
 
 @pytest.mark.parametrize("depth", [8, 10])
@@ -102,3 +103,20 @@ def test_oracle_me_matches_golden(depth):
                 assert list(row[:4]) == [method, w, h, subme]
                 assert list(o) == [int(x) for x in row[4:7]], (method, w, h, subme, o, row)
                 k += 1
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_oracle_me_chroma_matches_golden(depth):
+    """The chroma-SATD term of subpelCompare (motion.cpp:1601-1661): the oracle against the stored results of the real
+    MotionEstimate (tests/golden/me_chroma_*.npz, make_golden.py::gen_chroma), inputs regenerated from the seed."""
+    from frame_helpers import lambda_for
+    from me_helpers import run_both_chroma, CHROMA_CASES
+    g = np.load(os.path.join(HERE, "golden", "me_chroma_%d.npz" % depth))["me_results"]
+    O = load_oracle(depth)
+    R = _NoRef(lambda_for(30, depth))
+    rng = np.random.default_rng(177 + depth)
+    assert len(g) == len(CHROMA_CASES)
+    for k, (method, w, h, subme) in enumerate(CHROMA_CASES):
+        _, o = run_both_chroma(O, R, depth, rng, w, h, method, subme, True, 57 if method == 3 else 16)
+        assert list(g[k][:4]) == [method, w, h, subme]
+        assert list(o) == [int(x) for x in g[k][4:7]], (method, w, h, subme, o, g[k])
