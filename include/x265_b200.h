@@ -235,6 +235,19 @@ typedef struct {
 int x265cu_lookahead_cost_batch(x265cu_ctx*, int depth, const x265cu_la_job* jobs_dev, int n, int stride, int w8, int h8,
                                 const uint16_t* mvcost_dev /* centred table base, lambda of X265_LOOKAHEAD_QP */);
 
+/* Lookahead weighted-prediction analysis: LookaheadTLD::weightsAnalyse + weightCostLuma (slicetype.cpp:807-840, 860-961), the
+ * call estimateFrameCost makes before the L0 search when --weightp is on (slicetype.cpp:3137).  Planes are whole padded
+ * lowres buffers (Lowres::buffer[i], lowres.cpp:132-139: `planesize` pixels each, picture origin at `padoffset`), device
+ * resident; refBuf_dev4 is a HOST array of the 4 device plane pointers; wbuf_dev (4 * planesize pixels) is
+ * LookaheadTLD::wbuffer.  Host inputs: intraCost_host[CUs] (Lowres::intraCost) and stats = {fenc wp_sum, fenc wp_ssd,
+ * ref wp_sum, ref wp_ssd} (Lowres::wp_sum[0] / wp_ssd[0], slicetype.cpp:49-57, 665-676).  wp_out = {isWeighted, scale,
+ * log2 denominator, offset}; when isWeighted, wbuf_dev holds the 4 re-weighted planes for x265cu_lookahead_cost_batch's
+ * ref0 (slicetype.cpp:3222).  The decision logic runs on the host as in the reference; the plane passes (weight_pp over
+ * the padded plane, 8x8 SATD map) are launches of the block-op and grid pixel-compare kernels. */
+int x265cu_lookahead_weights_analyse(x265cu_ctx*, int depth, const void* fencBuf_dev, const void* const* refBuf_dev4,
+                                     void* wbuf_dev, int64_t planesize, int stride, int width, int lines, int64_t padoffset,
+                                     const int32_t* intraCost_host, const uint64_t* stats, int* wp_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,3 +305,4 @@ int x265cu_lookahead_cost_batch(x265cu_ctx* c, int depth, const x265cu_la_job* j
 
 #include "analyser.cuh"
 #include "thunks.cuh"
+#include "la_weights.cuh"

@@ -206,6 +206,16 @@ class Lib:
         self.check(self.L.x265cu_me_batch_chroma(self.ctx, depth, fenc.ptr, fstride, refs_ptr_table.ptr, rstride, C.byref(ch),
                                                  mvcost_dev.ptr + 2 * mvcost_range, mvcost_range, jobs_dev.ptr, n, out_dev.ptr))
 
+    def lookahead_weights_analyse(self, depth, fenc_buf, ref_bufs, wbuf, planesize, stride, width, lines, padoffset, intra_cost, stats):
+        """x265cu_lookahead_weights_analyse: returns (isWeighted, scale, log2denom, offset); wbuf then holds the 4 weighted planes."""
+        refs = (C.c_void_p * 4)(*[b.ptr for b in ref_bufs])
+        intra = np.ascontiguousarray(intra_cost, np.int32)
+        st = np.ascontiguousarray(stats, np.uint64)
+        wp = np.zeros(4, np.int32)
+        self.check(self.L.x265cu_lookahead_weights_analyse(self.ctx, depth, fenc_buf.ptr, refs, wbuf.ptr, planesize, stride, width, lines,
+                                                           padoffset, intra.ctypes.data, st.ctypes.data, wp.ctypes.data))
+        return tuple(int(x) for x in wp)
+
     def mvcost_table(self, lam, rng):
         t = np.zeros(2 * rng + 1, np.uint16)
         self.L.x265cu_mvcost_table(C.c_double(lam), rng, t.ctypes.data)
@@ -261,6 +271,7 @@ _AN_PROTOS = {
 }
 _AN_PROTOS["x265cu_lowres_intra_batch"] = (I, [P, I, P, I, I, I, I, I])
 _AN_PROTOS["x265cu_lookahead_cost_batch"] = (I, [P, I, P, I, I, I, I, P])
+_AN_PROTOS["x265cu_lookahead_weights_analyse"] = (I, [P, I, P, P, P, I64, I, I, I, I64, P, P, P])
 _PROTOS.update(_AN_PROTOS)
 
 
