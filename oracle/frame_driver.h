@@ -36,6 +36,12 @@ typedef struct {
     int threads;
     volatile int next;
     int stage;
+    /* 4:2:0 chroma for the chroma-SATD term of subpelCompare (motion.cpp:204-212, 1601-1661; MotionEstimate::bChromaSATD).
+     * chroma != 0: every ME job runs as the encoder runs it for a 4:2:0 source (setSourcePU with bChroma = true).
+     * Planes are half resolution, origin pixels, `cstride` elements per row, margins = half the luma margins. */
+    int chroma, cstride;
+    const DRV_PIXEL* fencC[2];        /* source Cb, Cr */
+    const DRV_PIXEL* refC[16][2];     /* reference Cb, Cr */
 } drv_frame;
 
 static inline int drv_depth_idx(int size) { return size == 64 ? 0 : (size == 32 ? 1 : (size == 16 ? 2 : 3)); }

@@ -43,7 +43,13 @@ static int orc_drv_me(const void* fv, const fs_me_job* j, int* qmv)
     const drv_frame* f = (const drv_frame*)fv;
     orc_me_job job;
     int mvc[8];
-    job.chroma = 0;
+    job.chroma = f->chroma;
+    if (f->chroma)
+    {
+        job.fencC[0] = f->fencC[0]; job.fencC[1] = f->fencC[1];
+        job.refC[0] = f->refC[j->ref][0]; job.refC[1] = f->refC[j->ref][1];
+        job.cstride = f->cstride;
+    }
     job.fenc = f->fenc; job.fencStride = f->p.stride; job.offset = j->offset;
     job.ref[0] = job.ref[1] = job.ref[2] = job.ref[3] = f->refs[j->ref];
     job.refStride = f->p.stride; job.lowres = 0; job.pw = j->pw; job.ph = j->ph;

@@ -245,6 +245,46 @@ static inline int lg2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
 static int ref_drv_me(const void* fv, const fs_me_job* j, int* qmv)
 {
     const drv_frame* f = (const drv_frame*)fv;
+    if (f->chroma)
+    {
+        /* the encoder's 4:2:0 call: Yuv variant of setSourcePU with bChroma = true (motion.cpp:194-222), which switches the
+         * chroma-SATD term of subpelCompare on for the PUs that have a chroma SATD (see x265ref_motion_estimate_chroma) */
+        static thread_local MotionEstimate* mec = NULL;
+        static thread_local Yuv* src = NULL;
+        static thread_local int mecqp = -1;
+        if (!mec) { mec = new MotionEstimate(); mec->init(X265_CSP_I420); src = new Yuv(); src->create(64, X265_CSP_I420); }
+        if (mecqp != f->p.qp) { mec->setQP(f->p.qp); mecqp = f->p.qp; }
+        const intptr_t stride = f->p.stride, cstride = f->cstride;
+        const intptr_t py = j->offset / stride, px = j->offset % stride;
+        const intptr_t coff = (py >> 1) * cstride + (px >> 1);
+        const pixel* fy = (const pixel*)f->fenc + j->offset;
+        for (int y = 0; y < j->ph; y++) memcpy(src->m_buf[0] + y * src->m_size, fy + y * stride, j->pw * sizeof(pixel));
+        for (int y = 0; y < j->ph / 2; y++)
+        {
+            memcpy(src->m_buf[1] + y * src->m_csize, (const pixel*)f->fencC[0] + coff + y * cstride, (j->pw / 2) * sizeof(pixel));
+            memcpy(src->m_buf[2] + y * src->m_csize, (const pixel*)f->fencC[1] + coff + y * cstride, (j->pw / 2) * sizeof(pixel));
+        }
+        mec->setSourcePU(*src, 0, 0, 0, j->pw, j->ph, j->method, j->subme, true);
+        PicYuv pic;
+        intptr_t zero = 0;
+        pic.m_cuOffsetY = &zero; pic.m_cuOffsetC = &zero; pic.m_buOffsetY = &zero; pic.m_buOffsetC = &zero;
+        pic.m_stride = stride; pic.m_strideC = cstride;
+        ReferencePlanes ref;
+        ref.reconPic = &pic;
+        ref.lumaStride = stride;
+        ref.isLowres = false;
+        ref.fpelPlane[0] = (pixel*)f->refs[j->ref] + j->offset;
+        ref.fpelPlane[1] = (pixel*)f->refC[j->ref][0] + coff; ref.fpelPlane[2] = (pixel*)f->refC[j->ref][1] + coff;
+        pic.m_picOrg[0] = ref.fpelPlane[0]; pic.m_picOrg[1] = ref.fpelPlane[1]; pic.m_picOrg[2] = ref.fpelPlane[2];
+        MV mn(j->mvmin[0], j->mvmin[1]), mx(j->mvmax[0], j->mvmax[1]), mvp(j->qmvp[0], j->qmvp[1]), out;
+        MV cands[4];
+        for (int i = 0; i < j->numCand && i < 4; i++) cands[i] = MV(j->mvc[2 * i], j->mvc[2 * i + 1]);
+        int cost = mec->motionEstimate(&ref, mn, mx, mvp, j->numCand, cands, j->merange, out, 1, NULL);
+        qmv[0] = out.x; qmv[1] = out.y;
+        pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = NULL;
+        pic.m_picOrg[0] = pic.m_picOrg[1] = pic.m_picOrg[2] = NULL;
+        return cost;
+    }
     static thread_local MotionEstimate* me = NULL;
     static thread_local int meqp = -1;
     if (!me) { me = new MotionEstimate(); me->init(X265_CSP_I400); }

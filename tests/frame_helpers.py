@@ -20,7 +20,8 @@ class DrvFrame(C.Structure):
                 ("njobs", I), ("jobs", P), ("me_out", P),
                 ("ncu", I), ("cus", P), ("cu_jobs", P), ("cu_coef_off", P), ("coef", P), ("recon", P * 4),
                 ("cu_sse", P), ("cu_numsig", P), ("cu_ref", P), ("intra_cost", P),
-                ("threads", I), ("next", I), ("stage", I)]
+                ("threads", I), ("next", I), ("stage", I),
+                ("chroma", I), ("cstride", I), ("fencC", P * 2), ("refC", (P * 2) * 16)]
 
 
 def stride_for(width):
@@ -37,6 +38,34 @@ def gen_luma(W, H, n, s1=37.0, s2=29.0, bits=8, seed=265, noise=False):
         y = 128 + 60 * np.sin((xx + 3 * n) / s1) + 40 * np.cos((yy - 2 * n) / s2) + rng.integers(-6, 7, (H, W))
     y = np.clip(y, 0, 255).astype(np.int64) << (bits - 8)
     return y.astype(pixel_dtype(bits))
+
+
+def gen_chroma(W, H, n, plane, bits=8, seed=265, noise=False):
+    """Cb (plane 1) / Cr (plane 2) of frame n, 4:2:0: smooth sinusoids moving with the clip's global motion (half the luma
+    displacement), BASELINE.md generator."""
+    cw, ch = W // 2, H // 2
+    rng = np.random.default_rng(seed + 1000 * plane + n)
+    if noise:
+        c = rng.integers(0, 256, (ch, cw))
+    else:
+        yy, xx = np.mgrid[0:ch, 0:cw]
+        ph = 0.7 * plane
+        c = 128 + 30 * np.sin((xx + 1.5 * n) / 23.0 + ph) + 25 * np.cos((yy - 1.0 * n) / 19.0 - ph) + rng.integers(-4, 5, (ch, cw))
+    c = np.clip(c, 0, 255).astype(np.int64) << (bits - 8)
+    return c.astype(pixel_dtype(bits))
+
+
+def pad_plane_c(img, depth, luma_stride):
+    """Margin-extended chroma plane: stride = luma stride / 2, margins = half the luma margins (picyuv.cpp:87-94)."""
+    H, W = img.shape
+    mx, my, stride = MARGIN_X // 2, MARGIN_Y // 2, luma_stride // 2
+    buf = np.zeros((H + 2 * my, stride), pixel_dtype(depth))
+    buf[my:my + H, mx:mx + W] = img
+    buf[my:my + H, :mx] = img[:, :1]
+    buf[my:my + H, mx + W:mx + W + mx] = img[:, -1:]
+    buf[:my, :] = buf[my:my + 1, :]
+    buf[my + H:, :] = buf[my + H - 1:my + H, :]
+    return buf, stride, my * stride + mx
 
 
 def pad_plane(img, depth):
@@ -68,8 +97,9 @@ def make_field(W, H, numRefs, seed=7, dist=0):
 class Workload:
     """Inputs of one analysed frame (host side)."""
 
-    def __init__(self, W, H, depth=8, numRefs=4, method=3, subme=3, merange=57, rect=1, qp=30, noise=False, seed=265):
+    def __init__(self, W, H, depth=8, numRefs=4, method=3, subme=3, merange=57, rect=1, qp=30, noise=False, seed=265, chroma=False):
         self.W, self.H, self.depth = W, H, depth
+        self.chroma = chroma
         self.stride = stride_for(W)
         self.params = dict(width=W, height=H, stride=self.stride, numRefs=numRefs, method=method, subme=subme,
                            merange=merange, rect=rect, qp=qp)
@@ -80,6 +110,15 @@ class Workload:
             img = gen_luma(W, H, numRefs - 1 - r, bits=depth, seed=seed, noise=noise)
             self.refs.append(pad_plane(img, depth)[0])
         self.field = make_field(W, H, numRefs)
+        if chroma:
+            # 4:2:0 planes for the chroma-SATD term of subpelCompare: [Cb, Cr] of the source and of every reference
+            self.fencC, self.refC = [], []
+            for pl in (1, 2):
+                buf, self.cstride, self.corg = pad_plane_c(gen_chroma(W, H, numRefs, pl, bits=depth, seed=seed, noise=noise), depth, self.stride)
+                self.fencC.append(buf)
+            for r in range(numRefs):
+                self.refC.append([pad_plane_c(gen_chroma(W, H, numRefs - 1 - r, pl, bits=depth, seed=seed, noise=noise), depth, self.stride)[0]
+                                  for pl in (1, 2)])
 
 
 def lambda_for(qp, depth):
@@ -99,6 +138,12 @@ def cpu_analyse(lib, fn_name, wl, mvcost_tab, threads=1, stages=7):
         f.refs[r] = ref.ctypes.data + wl.org * es
     f.field = wl.field.ctypes.data
     f.mvcost = mvcost_tab.ctypes.data + MVRANGE * 2
+    if getattr(wl, "chroma", False):
+        f.chroma, f.cstride = 1, wl.cstride
+        for k in range(2):
+            f.fencC[k] = wl.fencC[k].ctypes.data + wl.corg * es
+            for r in range(len(wl.refs)):
+                f.refC[r][k] = wl.refC[r][k].ctypes.data + wl.corg * es
     W, H, nref = wl.W, wl.H, wl.params["numRefs"]
     ctus = ((W + 63) // 64) * ((H + 63) // 64)
     maxjobs = ctus * nref * 425

@@ -36,3 +36,25 @@ def test_frame_driver(depth, noise):
     b = cpu_analyse(R, "x265ref_analyse_frame", wl, tab, threads=4)
     assert a["njobs"] > 2000 and a["cu_numsig"].sum() > 0
     compare(a, b)
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("noise", [False, True])
+def test_frame_driver_chroma(depth, noise):
+    """The same frame with 4:2:0 chroma planes: every ME job runs as the encoder's setSourcePU(Yuv, ..., bChroma = true) call,
+    i.e. with the chroma-SATD term of subpelCompare for the PUs that have one (motion.cpp:204-212, 1601-1661)."""
+    R = load_ref(depth)
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    O = load_oracle(depth)
+    qp = 30
+    wl = Workload(200, 136, depth=depth, numRefs=2, method=3, subme=3, merange=57, rect=1, qp=qp, noise=noise, chroma=True)
+    tab = mvcost_table(O, R.x265ref_lambda(qp))
+    a = cpu_analyse(O, "orc_analyse_frame", wl, tab, threads=4)
+    b = cpu_analyse(R, "x265ref_analyse_frame", wl, tab, threads=4)
+    compare(a, b)
+    # the term is really on: results differ from the luma-only run of the same frame
+    wl.chroma = False
+    c = cpu_analyse(O, "orc_analyse_frame", wl, tab, threads=4)
+    assert np.array_equal(a["jobs"], c["jobs"])
+    assert (a["me_out"][:, 0] != c["me_out"][:, 0]).mean() > 0.3
