@@ -123,6 +123,9 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------
+CHROMA = False      # --chroma: 4:2:0 planes resident, chroma-SATD term of subpelCompare on (both arms)
+
+
 def cpu_reference(sample_rows, threads, kind_pref="reference", steps=1, warmup=0):
     """The same workload on host cores: reference-from-source driver (oracle/_ref) or the oracle port."""
     from common import load_ref, load_oracle
@@ -132,7 +135,7 @@ def cpu_reference(sample_rows, threads, kind_pref="reference", steps=1, warmup=0
     R = load_ref(DEPTH) if kind_pref == "reference" else None
     lib, fn, kind = (R, "x265ref_analyse_frame", "reference") if R is not None else (O, "orc_analyse_frame", "port")
     hs = min(H, 64 * sample_rows)
-    wl = Workload(W, hs, depth=DEPTH, numRefs=NREFS, method=METHOD, subme=SUBME, merange=MERANGE, rect=RECT, qp=QP)
+    wl = Workload(W, hs, depth=DEPTH, numRefs=NREFS, method=METHOD, subme=SUBME, merange=MERANGE, rect=RECT, qp=QP, chroma=CHROMA)
     tab = mvcost_table(O, lambda_for(QP, DEPTH))
     ctus = ((W + 63) // 64) * ((hs + 63) // 64)
     for _ in range(warmup):
@@ -190,7 +193,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import x265_b200
     from x265_b200 import shard
-    from frame_helpers import gen_luma, make_field, MARGIN_X, MARGIN_Y
+    from frame_helpers import gen_luma, gen_chroma, make_field, MARGIN_X, MARGIN_Y
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -218,6 +221,17 @@ def run_ours(args, rank, world, local_rank):
     pinf = lib.L.x265cu_host_alloc(field.nbytes)
     h_field = np.frombuffer((C.c_uint8 * field.nbytes).from_address(pinf), np.int16).reshape(field.shape)
     h_field[:] = field
+    h_cb = h_cr = None
+    if CHROMA:
+        # the reference runs preset slow (subme 3) on a 4:2:0 source with MotionEstimate::bChromaSATD on (motion.cpp:204-212)
+        an.enable_chroma()
+        for r in range(NREFS):
+            an.set_ref_chroma(r, gen_chroma(W, H, NREFS - 1 - r, 1), gen_chroma(W, H, NREFS - 1 - r, 2))
+        cf = NREFS + (0 if rows_mode else shard.frame_of(0, rank, world))
+        pc = [lib.L.x265cu_host_alloc(W * H // 4) for _ in range(2)]
+        h_cb, h_cr = [np.frombuffer((C.c_uint8 * (W * H // 4)).from_address(p), np.uint8).reshape(H // 2, W // 2) for p in pc]
+        h_cb[:] = gen_chroma(W, H, cf, 1); h_cr[:] = gen_chroma(W, H, cf, 2)
+        an.load_chroma(h_cb, h_cr)
     flush = lib.alloc(256 << 20)
     ref0 = None
     if world > 1:
@@ -238,6 +252,8 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.current_stream().synchronize()
 
     def analyse_e2e():
+        if CHROMA:
+            an.load_chroma(h_cb, h_cr)                     # the frame's chroma travels with it (H2D inside the timed region)
         for r0, r1 in my_rows:
             an.analyse_rows(h_fenc, h_field, r0, r1)
 
@@ -328,6 +344,7 @@ def run_ours(args, rank, world, local_rank):
             pass
         cfg = workload_config(rows_mode)
         cfg["pu_jobs_per_frame"] = an.njobs
+        cfg["chroma_satd"] = bool(CHROMA)
         sizes = {"resid_bytes": plane * 2 + an.ncoef * 2 + 4 * plane, "intra_bytes": plane + an.ncu * 36 * 4}
         line = {
             "metric": "2160p preset-slow CTU-analysis throughput", "value": value, "unit": "CTUs/s", "n_gpus": world,
@@ -335,7 +352,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "strong" if rows_mode else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "CTUs/s", "ms_per_step": t_e2e / args.steps,
-                    "h2d_bytes_per_step": int(an.h2d_bytes(field)), "d2h_bytes_per_step": int(sum(an.d2h_bytes_rows(r0, r1) for r0, r1 in my_rows))},
+                    "h2d_bytes_per_step": int(an.h2d_bytes(field)) + (W * H // 2 if CHROMA else 0), "d2h_bytes_per_step": int(sum(an.d2h_bytes_rows(r0, r1) for r0, r1 in my_rows))},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_me<P,2,-1> (integer search phase of the batched motionEstimate, one warp per PU x ref)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -377,7 +394,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--shard", default="frames", choices=["frames", "rows"],
                     help="N>1 partition: a frame per GPU (default, weak scaling) or the CTU rows of one frame per GPU (strong scaling)")
+    ap.add_argument("--chroma", action="store_true",
+                    help="4:2:0 chroma planes resident and the chroma-SATD term of subpelCompare on (MotionEstimate::bChromaSATD), both arms")
     args = ap.parse_args()
+    global CHROMA
+    CHROMA = args.chroma
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         run_reference_arm(args, rank, world)

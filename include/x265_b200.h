@@ -214,6 +214,14 @@ int x265cu_analyser_row_range(x265cu_analyser*, int ctuRow0, int ctuRow1, int* j
 int x265cu_analyser_run_rows(x265cu_analyser*, int stages, int ctuRow0, int ctuRow1);
 int x265cu_analyser_analyse_rows(x265cu_analyser*, const void* fenc_host, int host_stride, const int16_t* field_host,
                                  int stages, int ctuRow0, int ctuRow1, x265cu_analysis_out* out);
+/* 4:2:0 chroma for the chroma-SATD term of subpelCompare (MotionEstimate::bChromaSATD, motion.cpp:204-212, 1601-1661): after
+ * enable_chroma() the ME stage of every run adds SATD(Cb) + SATD(Cr) to every sub-pel compare of the PUs that have a chroma
+ * SATD, as the encoder does for a 4:2:0 source at subme > 2 (x265cu_me_batch_chroma's kernels on resident planes).  Upload
+ * the source's chroma with load_chroma() before analyse() / run_*(), each reference's with set_ref_chroma(); host planes are
+ * (width / 2) x (height / 2), host_stride in pixels. */
+int x265cu_analyser_enable_chroma(x265cu_analyser*);
+int x265cu_analyser_set_ref_chroma(x265cu_analyser*, int idx, const void* cb_host, const void* cr_host, int host_stride);
+int x265cu_analyser_load_chroma(x265cu_analyser*, const void* cb_host, const void* cr_host, int host_stride);
 void* x265cu_analyser_recon_plane(x265cu_analyser*, int depthIdx /* 0..3 = CU 64,32,16,8 */, int* stride);
 int x265cu_analyser_recon_to_ref(x265cu_analyser*, int depthIdx, int refIdx, int ctuRow0, int ctuRow1);
 

@@ -27,6 +27,11 @@ struct x265cu_analyser
     // first PU job / CU / TU of every CTU row (+ one past the end): the lists are in CTU raster order, so a CTU-row
     // range [r0, r1) is one contiguous slice of each list (what a WPP row shard owns, frameencoder.cpp:850-868)
     int ctuRows; std::vector<int> rowJob, rowCu, rowTu;
+    // 4:2:0 chroma planes for the chroma-SATD term of subpelCompare (x265cu_analyser_enable_chroma): half resolution,
+    // stride / 2 elements per row, margins = half the luma margins (picyuv.cpp:87-94)
+    int chromaOn, cstride, cRows; size_t cPlaneBytes, cOrgBytes;
+    uint8_t* d_fencC[2]; uint8_t* d_refC[16][2];
+    void** d_refCbTable; void** d_refCrTable;
 };
 
 static const int AN_MARGIN_X = 96, AN_MARGIN_Y = 80;       // picyuv.cpp:87-88 with maxCUSize 64
@@ -119,8 +124,15 @@ static int an_run(x265cu_analyser* a, int stages, int r0, int r1)
         k_build_me_jobs<<<(nj + 255) / 256, 256, 0, c->stream>>>(a->d_pus + job0, nj, a->d_field, a->fw, a->fh, a->p.width, a->p.height,
                                                                  a->stride, a->p.method, a->p.subme, a->p.merange, a->d_jobs + job0);
         CU_LAUNCH_CHECK(c);
+        MeChromaArgs ch;
+        if (a->chromaOn)
+        {
+            ch.fencCb = a->d_fencC[0] + a->cOrgBytes; ch.fencCr = a->d_fencC[1] + a->cOrgBytes;
+            ch.refCb = (const void* const*)a->d_refCbTable; ch.refCr = (const void* const*)a->d_refCrTable; ch.cstride = a->cstride;
+        }
         if (launch_me(c, depth, a->d_fenc + a->orgBytes, a->stride, (const void* const*)a->d_refTable, a->stride, 0,
-                      a->d_mvcost + a->mvrange, a->d_jobs + job0, nj, a->d_me_out + (size_t)job0 * 4, c->d_counter)) return -1;
+                      a->d_mvcost + a->mvrange, a->d_jobs + job0, nj, a->d_me_out + (size_t)job0 * 4, c->d_counter,
+                      a->chromaOn ? &ch : NULL)) return -1;
         CU_CHECK(cudaEventRecord(a->ev[4], c->stream));      // ME search kernel alone ends here
         k_pack_me<<<(nj + 255) / 256, 256, 0, c->stream>>>(a->d_me_out + (size_t)job0 * 4, nj, a->d_me_packed + job0);
         CU_LAUNCH_CHECK(c);
@@ -205,6 +217,9 @@ x265cu_analyser* x265cu_analyser_create(x265cu_ctx* ctx, const x265cu_analysis_p
     a->d_intra = (uint32_t*)x265cu_malloc(ctx, sizeof(uint32_t) * 36 * a->ncu);
     for (int i = 0; i < 5; i++) cudaEventCreate(&a->ev[i]);
     a->ev_valid = 0;
+    a->chromaOn = 0; a->d_refCbTable = a->d_refCrTable = NULL;
+    a->d_fencC[0] = a->d_fencC[1] = NULL;
+    for (int r = 0; r < 16; r++) a->d_refC[r][0] = a->d_refC[r][1] = NULL;
     a->h_fenc = (uint8_t*)x265cu_host_alloc((size_t)p->width * p->height * es);
     a->h_field = (int16_t*)x265cu_host_alloc(fieldBytes);
     if (!a->d_intra || !a->d_coef || !a->d_me_out || !a->h_fenc || !a->h_field) return NULL;
@@ -223,6 +238,8 @@ void x265cu_analyser_destroy(x265cu_analyser* a)
     for (void* b : bufs) cudaFree(b);
     for (int r = 0; r < a->p.numRefs; r++) cudaFree(a->d_refs[r]);
     for (int d = 0; d < 4; d++) cudaFree(a->d_recon[d]);
+    for (int k = 0; k < 2; k++) { cudaFree(a->d_fencC[k]); for (int r = 0; r < a->p.numRefs; r++) cudaFree(a->d_refC[r][k]); }
+    cudaFree(a->d_refCbTable); cudaFree(a->d_refCrTable);
     x265cu_host_free(a->h_fenc); x265cu_host_free(a->h_field);
     delete a;
 }
@@ -250,6 +267,66 @@ int x265cu_analyser_load_inputs(x265cu_analyser* a, const void* fenc_host, int h
     const size_t fieldBytes = (size_t)a->p.numRefs * a->fw * a->fh * 2 * sizeof(int16_t);
     if (an_upload_plane(a, a->d_fenc, fenc_host, host_stride)) return -1;
     CU_CHECK(cudaMemcpyAsync(a->d_field, field_host, fieldBytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+// ---- 4:2:0 chroma for the chroma-SATD term of subpelCompare (MotionEstimate::bChromaSATD, motion.cpp:204-212, 1601-1661) ----
+// After enable_chroma() the ME stage runs the k_me_chroma launches (x265cu_me_batch_chroma's kernels) on the resident chroma
+// planes; the caller uploads the source's Cb / Cr with load_chroma() and every reference's with set_ref_chroma().
+static int an_upload_cplane(x265cu_analyser* a, uint8_t* d_plane, const void* host, int hostStride)
+{
+    x265cu_ctx* c = a->ctx;
+    const size_t es = a->p.depth == 8 ? 1 : 2;
+    const int cw = a->p.width >> 1, ch = a->p.height >> 1;
+    CU_CHECK(cudaMemcpy2DAsync(d_plane + a->cOrgBytes, (size_t)a->cstride * es, host, (size_t)hostStride * es,
+                               (size_t)cw * es, ch, cudaMemcpyHostToDevice, c->stream));
+    return x265cu_extend_border(c, a->p.depth, d_plane + a->cOrgBytes, a->cstride, cw, ch, AN_MARGIN_X / 2, AN_MARGIN_Y / 2);
+}
+
+int x265cu_analyser_enable_chroma(x265cu_analyser* a)
+{
+    if (a->chromaOn) return 0;
+    x265cu_ctx* c = a->ctx;
+    cudaSetDevice(c->device);
+    const size_t es = a->p.depth == 8 ? 1 : 2;
+    a->cstride = a->stride / 2;
+    a->cRows = (a->p.height >> 1) + AN_MARGIN_Y;                 // 2 * (AN_MARGIN_Y / 2)
+    a->cPlaneBytes = (size_t)a->cstride * a->cRows * es + 256;
+    a->cOrgBytes = ((size_t)(AN_MARGIN_Y / 2) * a->cstride + AN_MARGIN_X / 2) * es;
+    void* cbt[16]; void* crt[16];
+    for (int k = 0; k < 2; k++)
+    {
+        a->d_fencC[k] = (uint8_t*)x265cu_malloc(c, a->cPlaneBytes);
+        if (!a->d_fencC[k]) return -1;
+        CU_CHECK(cudaMemset(a->d_fencC[k], 0, a->cPlaneBytes));
+        for (int r = 0; r < a->p.numRefs; r++)
+        {
+            a->d_refC[r][k] = (uint8_t*)x265cu_malloc(c, a->cPlaneBytes);
+            if (!a->d_refC[r][k]) return -1;
+            CU_CHECK(cudaMemset(a->d_refC[r][k], 0, a->cPlaneBytes));
+            (k ? crt : cbt)[r] = a->d_refC[r][k] + a->cOrgBytes;
+        }
+    }
+    a->d_refCbTable = (void**)x265cu_malloc(c, sizeof(void*) * 16);
+    a->d_refCrTable = (void**)x265cu_malloc(c, sizeof(void*) * 16);
+    if (!a->d_refCbTable || !a->d_refCrTable) return -1;
+    CU_CHECK(cudaMemcpy(a->d_refCbTable, cbt, sizeof(void*) * a->p.numRefs, cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMemcpy(a->d_refCrTable, crt, sizeof(void*) * a->p.numRefs, cudaMemcpyHostToDevice));
+    a->chromaOn = 1;
+    return 0;
+}
+
+int x265cu_analyser_set_ref_chroma(x265cu_analyser* a, int idx, const void* cb_host, const void* cr_host, int host_stride)
+{
+    if (!a->chromaOn || idx < 0 || idx >= a->p.numRefs) return -1;
+    if (an_upload_cplane(a, a->d_refC[idx][0], cb_host, host_stride) || an_upload_cplane(a, a->d_refC[idx][1], cr_host, host_stride)) return -1;
+    return x265cu_sync(a->ctx);
+}
+
+int x265cu_analyser_load_chroma(x265cu_analyser* a, const void* cb_host, const void* cr_host, int host_stride)
+{
+    if (!a->chromaOn) return -1;
+    if (an_upload_cplane(a, a->d_fencC[0], cb_host, host_stride) || an_upload_cplane(a, a->d_fencC[1], cr_host, host_stride)) return -1;
     return 0;
 }
 

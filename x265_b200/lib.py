@@ -268,6 +268,9 @@ _AN_PROTOS = {
     "x265cu_analyser_analyse_rows": (I, [P, P, I, P, I, I, I, C.POINTER(AnalysisOut)]),
     "x265cu_analyser_recon_plane": (P, [P, I, C.POINTER(I)]),
     "x265cu_analyser_recon_to_ref": (I, [P, I, I, I, I]),
+    "x265cu_analyser_enable_chroma": (I, [P]),
+    "x265cu_analyser_set_ref_chroma": (I, [P, I, P, P, I]),
+    "x265cu_analyser_load_chroma": (I, [P, P, P, I]),
 }
 _AN_PROTOS["x265cu_lowres_intra_batch"] = (I, [P, I, P, I, I, I, I, I])
 _AN_PROTOS["x265cu_lookahead_cost_batch"] = (I, [P, I, P, I, I, I, I, P])
@@ -358,6 +361,20 @@ class Analyser:
 
     def recon_to_ref(self, depth_idx, ref_idx, r0, r1):
         self.lib.check(self.lib.L.x265cu_analyser_recon_to_ref(self.h, depth_idx, ref_idx, r0, r1))
+
+    # ---- 4:2:0 chroma for the chroma-SATD term of subpelCompare ----
+    def enable_chroma(self):
+        self.lib.check(self.lib.L.x265cu_analyser_enable_chroma(self.h))
+
+    def set_ref_chroma(self, idx, cb, cr):
+        cb = np.ascontiguousarray(cb, self.dtype); cr = np.ascontiguousarray(cr, self.dtype)
+        assert cb.shape == cr.shape == (self.height // 2, self.width // 2)
+        self.lib.check(self.lib.L.x265cu_analyser_set_ref_chroma(self.h, idx, cb.ctypes.data, cr.ctypes.data, self.width // 2))
+
+    def load_chroma(self, cb, cr):
+        """Source chroma of the next analyse() / run_*() (pass pinned arrays for true async DMA)."""
+        assert cb.shape == cr.shape == (self.height // 2, self.width // 2) and cb.dtype == self.dtype and cb.flags.c_contiguous and cr.flags.c_contiguous
+        self.lib.check(self.lib.L.x265cu_analyser_load_chroma(self.h, cb.ctypes.data, cr.ctypes.data, self.width // 2))
 
     def h2d_bytes(self, field):
         return self.width * self.height * np.dtype(self.dtype).itemsize + field.nbytes
