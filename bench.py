@@ -178,7 +178,8 @@ def workload_config(rows=False):
     return {"workload": "3840x2160 8-bit preset slow: full ME + sub-pel interp + DCT/quant + intra primitives on device (BASELINE configs[2])",
             "ctus_per_frame": CTUS_PER_FRAME, "refs": NREFS, "search": "star", "merange": MERANGE, "subme": SUBME, "rect": RECT, "qp": QP,
             "pu_jobs_per_frame": None, "frames_per_step": "1 per GPU", "l2": "256 MiB memset between timed steps (untimed) + >300 MB per-step working set",
-            "exchange": "NCCL broadcast of one reference luma plane per step (N>1 only)"}
+            "exchange": "NCCL broadcast of one reference luma plane per step (N>1 only)",
+            "frames": "rank k: frame 4+k against frames 3+k..k (frame-parallel: own nearest references per frame)"}
 
 
 def plane_as_tensor(torch, ptr, nbytes, device):
@@ -203,17 +204,16 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     lib = x265_b200.load(local_rank)
     an = x265_b200.Analyser(lib, W, H, depth=DEPTH, numRefs=NREFS, method=METHOD, subme=SUBME, merange=MERANGE, rect=RECT, qp=QP)
-    # synthetic clip (BASELINE.md generator): refs = frames 3..0, this rank's current frame = 4 + rank
-    for r in range(NREFS):
-        an.set_ref(r, gen_luma(W, H, NREFS - 1 - r))
+    # synthetic clip (BASELINE.md generator).  Frame shards: rank k analyses frame 4 + k against ITS four nearest previous frames
+    # (3 + k .. k), as frame-parallel encoding does, so every rank has the same temporal distances and the same search problem.
+    # Row shards: one frame (4) and one reference set (3..0) for all ranks.
     rows_mode = args.shard == "rows"
-    cur = gen_luma(W, H, NREFS + (0 if rows_mode else shard.frame_of(0, rank, world)))
+    k_frame = 0 if rows_mode else shard.frame_of(0, rank, world)
+    for r in range(NREFS):
+        an.set_ref(r, gen_luma(W, H, NREFS - 1 - r + k_frame))
+    cur = gen_luma(W, H, NREFS + k_frame)
     my_rows = shard.row_blocks(an.ctu_rows, rank, world, "block") if rows_mode else [(0, an.ctu_rows)]
-    # predictor field of THIS rank's frame.  The clip's global motion to reference r is (+3, -2) * (r + 1 + k) px for the frame
-    # k positions after the first one; the N=1 field (k = 0) sits at (-3, +2) * (r + 1), i.e. off by (6, -4) * (r + 1) px.
-    # Rank k gets the field with the SAME offset from its own true motion (dist = -k), so every rank faces the same search
-    # problem (measured with the CPU oracle: equal cost sums) instead of a predictor that is further off the later the frame.
-    field = make_field(W, H, NREFS, dist=0 if rows_mode else -shard.frame_of(0, rank, world))
+    field = make_field(W, H, NREFS)
     # pinned host buffers: these are what the user hands to the public call
     pin = lib.L.x265cu_host_alloc(W * H)
     h_fenc = np.frombuffer((C.c_uint8 * (W * H)).from_address(pin), np.uint8).reshape(H, W)
@@ -226,22 +226,27 @@ def run_ours(args, rank, world, local_rank):
         # the reference runs preset slow (subme 3) on a 4:2:0 source with MotionEstimate::bChromaSATD on (motion.cpp:204-212)
         an.enable_chroma()
         for r in range(NREFS):
-            an.set_ref_chroma(r, gen_chroma(W, H, NREFS - 1 - r, 1), gen_chroma(W, H, NREFS - 1 - r, 2))
-        cf = NREFS + (0 if rows_mode else shard.frame_of(0, rank, world))
+            an.set_ref_chroma(r, gen_chroma(W, H, NREFS - 1 - r + k_frame, 1), gen_chroma(W, H, NREFS - 1 - r + k_frame, 2))
+        cf = NREFS + k_frame
         pc = [lib.L.x265cu_host_alloc(W * H // 4) for _ in range(2)]
         h_cb, h_cr = [np.frombuffer((C.c_uint8 * (W * H // 4)).from_address(p), np.uint8).reshape(H // 2, W // 2) for p in pc]
         h_cb[:] = gen_chroma(W, H, cf, 1); h_cr[:] = gen_chroma(W, H, cf, 2)
         an.load_chroma(h_cb, h_cr)
     flush = lib.alloc(256 << 20)
-    ref0 = None
+    ref0 = incoming = None
     if world > 1:
         ptr, stride = an.recon_plane_ptr(1) if rows_mode else an.ref_plane_ptr(0)
         base = ptr - (MARGIN_Y * stride + MARGIN_X)
         ref0 = plane_as_tensor(torch, base, stride * (H + 2 * MARGIN_Y), dev)
+        if not rows_mode:
+            # incoming-reference plane: the owner's newest reference lands here on the other ranks (making it a reference is a
+            # pointer swap the bench does not do, so that every step analyses the same frames)
+            inc = lib.alloc(stride * (H + 2 * MARGIN_Y))
+            incoming = plane_as_tensor(torch, inc.ptr, stride * (H + 2 * MARGIN_Y), dev)
 
     def exchange(step):
         if world > 1 and not rows_mode:
-            shard.exchange_ref(dist, ref0, step, world)     # newest reconstructed reference plane from its owner
+            shard.exchange_ref(dist, ref0, step, world, recv=incoming)     # newest reconstructed reference plane from its owner
             torch.cuda.current_stream().synchronize()
 
     def exchange_rows():

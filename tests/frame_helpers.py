@@ -81,16 +81,14 @@ def pad_plane(img, depth):
     return buf, stride, MARGIN_Y * stride + MARGIN_X
 
 
-def make_field(W, H, numRefs, seed=7, dist=0):
-    """16x16-granular qpel predictor field: (-3*d, 2*d) px plus jitter with d = r + 1 + dist.  dist = 0 is the field of
-    the frame right after the newest reference; bench.py passes dist = -k for the frame k positions later so that the
-    field keeps the same offset from that frame's true global motion ((+3, -2) px per frame of distance)."""
+def make_field(W, H, numRefs, seed=7):
+    """16x16-granular qpel predictor field: global motion (-3*(r+1), 2*(r+1)) px plus jitter."""
     rng = np.random.default_rng(seed)
     fw, fh = (W + 15) // 16, (H + 15) // 16
     f = np.zeros((numRefs, fh, fw, 2), np.int16)
     for r in range(numRefs):
-        f[r, :, :, 0] = -12 * (r + 1 + dist) + rng.integers(-6, 7, (fh, fw))
-        f[r, :, :, 1] = 8 * (r + 1 + dist) + rng.integers(-6, 7, (fh, fw))
+        f[r, :, :, 0] = -12 * (r + 1) + rng.integers(-6, 7, (fh, fw))
+        f[r, :, :, 1] = 8 * (r + 1) + rng.integers(-6, 7, (fh, fw))
     return f
 
 

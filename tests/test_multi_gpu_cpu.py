@@ -31,6 +31,14 @@ def _worker(rank, world, port, ret):
             plane.copy_(truth)                      # only the owner has the reconstructed pixels
         shard.exchange_ref(dist, plane, step, world)
         ok = ok and bool(torch.equal(plane, truth))
+        # incoming-reference variant: non-owners receive into `recv`, their own plane stays as it was
+        mine = torch.full((64 * 80,), rank + 1, dtype=torch.uint8)
+        recv = torch.zeros(64 * 80, dtype=torch.uint8)
+        got = shard.exchange_ref(dist, truth.clone() if rank == owner else mine, step, world, recv=recv)
+        if rank == owner:
+            ok = ok and bool(torch.equal(got, truth)) and int(recv.sum()) == 0
+        else:
+            ok = ok and bool(torch.equal(recv, truth)) and bool(torch.equal(mine, torch.full_like(mine, rank + 1))) and got is recv
         seen.append(shard.frame_of(step, rank, world))
     gathered = [None] * world
     dist.all_gather_object(gathered, seen)

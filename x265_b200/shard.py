@@ -1,8 +1,8 @@
 """Multi-GPU partitioning of the frame-analysis path (host logic only; one process per GPU).
 
-The frames of a mini-GOP share one reference set, so each rank analyses its own frame: no data-path
-collective inside a frame.  The single exchange step is the broadcast of the newest reconstructed
-reference plane from the rank that owns (reconstructed) it -- the producer side of m_reconRowFlag
+Frame shards (the reference's frame-parallel mode, -F): each rank analyses its own frame against its own nearest
+reference frames: no data-path collective inside a frame.  The single exchange step is the broadcast of the newest
+reconstructed reference plane from the rank that owns (reconstructed) it -- the producer side of m_reconRowFlag
 (/root/reference/source/encoder/framefilter.cpp:664) -- once per step."""
 
 
@@ -16,12 +16,16 @@ def ref_owner(step, world):
     return step % world
 
 
-def exchange_ref(dist, plane_tensor, step, world):
+def exchange_ref(dist, plane_tensor, step, world, recv=None):
     """Broadcast the newest reference plane (whole padded allocation, margins included) from its owner.
-    `dist` is torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
-    if world > 1:
-        dist.broadcast(plane_tensor, src=ref_owner(step, world))
-    return plane_tensor
+    `dist` is torch.distributed (NCCL on GPUs, gloo in the CPU tests).  With `recv`, the non-owners receive into that
+    tensor (an incoming-reference plane the caller swaps in when it wants to) instead of overwriting `plane_tensor`."""
+    if world <= 1:
+        return plane_tensor
+    owner = ref_owner(step, world)
+    t = plane_tensor if (recv is None or dist.get_rank() == owner) else recv
+    dist.broadcast(t, src=owner)
+    return t
 
 
 # ---- CTU-row shards inside one frame (BASELINE configs[4]: WPP CTU rows sharded per GPU) -----------------------
