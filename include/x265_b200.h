@@ -186,6 +186,7 @@ typedef struct {
     int width, height, depth, numRefs;
     int method, subme, merange, rect;     /* X265_*_SEARCH, subpel refine level, range, rect PUs */
     int qp; double lambda;                /* quant QP; mvcost lambda (x265_lambda_tab[qp]) */
+    int amp;                              /* AMP PUs (2NxnU/nD, nLx2N/nRx2N at CU >= 16; presets slower+, param.cpp:494-520) */
 } x265cu_analysis_params;
 typedef struct {                          /* host destinations (any may be NULL) */
     int32_t*  me_packed;                  /* [njobs][2]: cost, (mvx | mvy << 16) */

@@ -27,6 +27,7 @@ typedef struct {
     int method, subme, merange;
     int rect;               /* evaluate 2NxN / Nx2N */
     int qp;                 /* luma QP for quant/dequant (per = qp/6, rem = qp%6) */
+    int amp;                /* evaluate the AMP partitions 2NxnU / 2NxnD / nLx2N / nRx2N of CUs >= 16 (param.cpp:494-520: slower+) */
 } fs_params;
 
 typedef struct {
@@ -43,8 +44,9 @@ static inline int fs_stride(int width) { return (width + 2 * FS_MARGIN_X + 63) /
 static inline int fs_field_w(int width) { return (width + 15) / 16; }
 static inline int fs_field_h(int height) { return (height + 15) / 16; }
 
-/* PU table of one CTU: (x, y, w, h, cuX, cuY, cuSize); returns count (<= 425) */
-static inline int fs_ctu_pus(int rect, int16_t out[][7])
+/* PU table of one CTU: (x, y, w, h, cuX, cuY, cuSize); returns count (<= 85 * 5 + 21 * 8 = 593) */
+#define FS_MAX_CTU_PUS 593
+static inline int fs_ctu_pus(int rect, int amp, int16_t out[][7])
 {
     int n = 0;
     for (int size = 64; size >= 8; size >>= 1)
@@ -63,6 +65,18 @@ static inline int fs_ctu_pus(int rect, int16_t out[][7])
                     out[n][4] = (int16_t)cx; out[n][5] = (int16_t)cy; out[n][6] = (int16_t)size;
                     n++;
                 }
+                if (amp && size >= 16)
+                {   /* AMP (not at the minimum CU size): 2NxnU, 2NxnD, nLx2N, nRx2N -- the quarter / three-quarter splits */
+                    const int16_t q = (int16_t)(size / 4), t = (int16_t)(size - size / 4), S = (int16_t)size;
+                    const int16_t a[8][4] = { { 0, 0, S, q }, { 0, q, S, t }, { 0, 0, S, t }, { 0, t, S, q },
+                                              { 0, 0, q, S }, { q, 0, t, S }, { 0, 0, t, S }, { t, 0, q, S } };
+                    for (int k = 0; k < 8; k++)
+                    {
+                        out[n][0] = (int16_t)(cx + a[k][0]); out[n][1] = (int16_t)(cy + a[k][1]); out[n][2] = a[k][2]; out[n][3] = a[k][3];
+                        out[n][4] = (int16_t)cx; out[n][5] = (int16_t)cy; out[n][6] = (int16_t)size;
+                        n++;
+                    }
+                }
             }
     return n;
 }
@@ -73,8 +87,8 @@ static inline int fs_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > h
  * field: int16 [numRefs][fh][fw][2] qpel predictors.  jobs may be NULL to count only. */
 static inline int fs_build_me_jobs(const fs_params* p, const int16_t* field, fs_me_job* jobs)
 {
-    int16_t pus[425][7];
-    const int npu = fs_ctu_pus(p->rect, pus);
+    int16_t pus[FS_MAX_CTU_PUS][7];
+    const int npu = fs_ctu_pus(p->rect, p->amp, pus);
     const int fw = fs_field_w(p->width), fh = fs_field_h(p->height);
     const int ctuW = (p->width + 63) / 64, ctuH = (p->height + 63) / 64;
     int n = 0;

@@ -12,7 +12,7 @@ MVRANGE = 65536
 
 class FsParams(C.Structure):
     _fields_ = [("width", I), ("height", I), ("stride", I), ("numRefs", I), ("method", I), ("subme", I),
-                ("merange", I), ("rect", I), ("qp", I)]
+                ("merange", I), ("rect", I), ("qp", I), ("amp", I)]
 
 
 class DrvFrame(C.Structure):
@@ -95,12 +95,12 @@ def make_field(W, H, numRefs, seed=7):
 class Workload:
     """Inputs of one analysed frame (host side)."""
 
-    def __init__(self, W, H, depth=8, numRefs=4, method=3, subme=3, merange=57, rect=1, qp=30, noise=False, seed=265, chroma=False):
+    def __init__(self, W, H, depth=8, numRefs=4, method=3, subme=3, merange=57, rect=1, qp=30, noise=False, seed=265, chroma=False, amp=0):
         self.W, self.H, self.depth = W, H, depth
         self.chroma = chroma
         self.stride = stride_for(W)
         self.params = dict(width=W, height=H, stride=self.stride, numRefs=numRefs, method=method, subme=subme,
-                           merange=merange, rect=rect, qp=qp)
+                           merange=merange, rect=rect, qp=qp, amp=amp)
         cur = gen_luma(W, H, numRefs, bits=depth, seed=seed, noise=noise)
         self.fenc, _, self.org = pad_plane(cur, depth)
         self.refs = []
@@ -144,7 +144,7 @@ def cpu_analyse(lib, fn_name, wl, mvcost_tab, threads=1, stages=7):
                 f.refC[r][k] = wl.refC[r][k].ctypes.data + wl.corg * es
     W, H, nref = wl.W, wl.H, wl.params["numRefs"]
     ctus = ((W + 63) // 64) * ((H + 63) // 64)
-    maxjobs = ctus * nref * 425
+    maxjobs = ctus * nref * 593
     maxcu = ctus * 85
     from x265_b200.lib import ME_JOB
     out = dict(

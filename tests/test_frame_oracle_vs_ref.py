@@ -58,3 +58,20 @@ def test_frame_driver_chroma(depth, noise):
     c = cpu_analyse(O, "orc_analyse_frame", wl, tab, threads=4)
     assert np.array_equal(a["jobs"], c["jobs"])
     assert (a["me_out"][:, 0] != c["me_out"][:, 0]).mean() > 0.3
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_frame_driver_amp(depth):
+    """rect + AMP partitions (presets slower / veryslow, BASELINE configs[3..4]): 2NxnU / 2NxnD / nLx2N / nRx2N of CUs >= 16."""
+    R = load_ref(depth)
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    O = load_oracle(depth)
+    qp = 30
+    wl = Workload(200, 136, depth=depth, numRefs=2, method=3, subme=4, merange=57, rect=1, qp=qp, amp=1)
+    tab = mvcost_table(O, R.x265ref_lambda(qp))
+    a = cpu_analyse(O, "orc_analyse_frame", wl, tab, threads=4)
+    b = cpu_analyse(R, "x265ref_analyse_frame", wl, tab, threads=4)
+    sizes = {(int(j["pw"]), int(j["ph"])) for j in a["jobs"]}
+    assert {(64, 16), (64, 48), (16, 64), (48, 64), (32, 8), (32, 24), (8, 32), (24, 32), (16, 4), (16, 12), (4, 16), (12, 16)} <= sizes
+    compare(a, b)

@@ -38,66 +38,11 @@ static const int AN_MARGIN_X = 96, AN_MARGIN_Y = 80;       // picyuv.cpp:87-88 w
 
 static void an_build_geometry(x265cu_analyser* a)
 {
-    const int W = a->p.width, H = a->p.height, nref = a->p.numRefs, stride = a->stride;
-    // CU list: CTU raster, sizes 64..8, raster inside the CTU; CUs must lie fully inside the picture
-    const int ctuW = (W + 63) / 64, ctuH = (H + 63) / 64;
-    int64_t coefOff = 0;
-    a->ctuRows = ctuH;
-    for (int cty = 0; cty < ctuH; cty++)
-    {
-        a->rowJob.push_back((int)a->pus.size()); a->rowCu.push_back((int)a->cus.size()); a->rowTu.push_back((int)a->tus.size());
-        for (int ctx = 0; ctx < ctuW; ctx++)
-        {
-            const size_t cuBase = a->cus.size();
-            int local[85]; int nl = 0;
-            for (int size = 64; size >= 8; size >>= 1)
-                for (int cy = 0; cy < 64; cy += size)
-                    for (int cx = 0; cx < 64; cx += size, nl++)
-                    {
-                        const int x = ctx * 64 + cx, y = cty * 64 + cy;
-                        local[nl] = -1;
-                        if (x + size > W || y + size > H) continue;
-                        local[nl] = (int)a->cus.size();
-                        CuDesc c; c.x = (int16_t)x; c.y = (int16_t)y; c.size = (int16_t)size; c.pad = 0; c.coef_off = coefOff;
-                        coefOff += (int64_t)size * size;
-                        const int T = size > 32 ? 32 : size;
-                        for (int ty = 0; ty < size; ty += T)
-                            for (int tx = 0; tx < size; tx += T)
-                            {
-                                TuDesc t; t.cu = (int32_t)a->cus.size(); t.tx = (int16_t)tx; t.ty = (int16_t)ty;
-                                a->tus.push_back(t);
-                            }
-                        a->cus.push_back(c);
-                    }
-            (void)cuBase;
-            a->cu_jobs.resize(a->cus.size() * nref, -1);
-            // PU jobs of this CTU: per ref, per CU (same order), 2Nx2N then (rect) 2NxN x2, Nx2N x2
-            for (int r = 0; r < nref; r++)
-            {
-                int li = 0;
-                for (int size = 64; size >= 8; size >>= 1)
-                    for (int cy = 0; cy < 64; cy += size)
-                        for (int cx = 0; cx < 64; cx += size, li++)
-                        {
-                            const int half = size / 2;
-                            const int part[5][4] = { { 0, 0, size, size }, { 0, 0, size, half }, { 0, half, size, half },
-                                                     { 0, 0, half, size }, { half, 0, half, size } };
-                            const int np = a->p.rect ? 5 : 1;
-                            for (int k = 0; k < np; k++)
-                            {
-                                const int x = ctx * 64 + cx + part[k][0], y = cty * 64 + cy + part[k][1], w = part[k][2], h = part[k][3];
-                                if (x + w > W || y + h > H) continue;
-                                PuDesc d; d.offset = y * stride + x; d.cuX = (int16_t)(ctx * 64 + cx); d.cuY = (int16_t)(cty * 64 + cy);
-                                d.pw = (int8_t)w; d.ph = (int8_t)h; d.ref = (int16_t)r;
-                                if (k == 0) a->cu_jobs[(size_t)local[li] * nref + r] = (int32_t)a->pus.size();
-                                a->pus.push_back(d);
-                            }
-                        }
-            }
-        }
-    }
-    a->rowJob.push_back((int)a->pus.size()); a->rowCu.push_back((int)a->cus.size()); a->rowTu.push_back((int)a->tus.size());
-    a->njobs = (int)a->pus.size(); a->ncu = (int)a->cus.size(); a->ntu = (int)a->tus.size(); a->ncoef = coefOff;
+    FrameGeometry g;
+    geometry_build(a->p.width, a->p.height, a->stride, a->p.numRefs, a->p.rect, a->p.amp, g);
+    a->pus.swap(g.pus); a->cus.swap(g.cus); a->tus.swap(g.tus); a->cu_jobs.swap(g.cu_jobs);
+    a->ctuRows = g.ctuRows; a->rowJob.swap(g.rowJob); a->rowCu.swap(g.rowCu); a->rowTu.swap(g.rowTu);
+    a->njobs = (int)a->pus.size(); a->ncu = (int)a->cus.size(); a->ntu = (int)a->tus.size(); a->ncoef = g.ncoef;
 }
 
 template <typename T> static T* an_upload(x265cu_ctx* c, const std::vector<T>& v)

@@ -11,9 +11,7 @@
 #include "interp.cuh"
 #include "intra.cuh"
 
-struct PuDesc { int32_t offset; int16_t cuX, cuY; int8_t pw, ph; int16_t ref; };   // static per geometry
-struct CuDesc { int16_t x, y, size, pad; int64_t coef_off; };
-struct TuDesc { int32_t cu; int16_t tx, ty; };                                        // TU origin inside the CU
+#include "geometry.h"        // PuDesc / CuDesc / TuDesc and the host-side table builder
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 

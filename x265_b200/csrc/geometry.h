@@ -1,0 +1,105 @@
+// x265_b200/csrc/geometry.h -- host-only (no CUDA): the static geometry tables of the frame analyser.
+// PU / CU / TU lists of a picture in canonical order (CTU raster; per CTU and reference the CUs 64..8 in raster order, each
+// with its 2Nx2N PU, then -- rect -- 2NxN x2, Nx2N x2, then -- amp, CU >= 16 -- 2NxnU, 2NxnD, nLx2N, nRx2N; preset slow has rect
+// on and AMP off, slower / veryslow have both: common/param.cpp:478-520).  PUs and CUs must lie fully inside the picture
+// (analysis.cpp only visits CUs inside it).  Kept free of CUDA so that tests/test_geometry.py can check it on the CPU
+// against the oracle's independent enumeration (oracle/frame_spec.h) at every BASELINE picture size.
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+struct PuDesc { int32_t offset; int16_t cuX, cuY; int8_t pw, ph; int16_t ref; };   // static per geometry
+struct CuDesc { int16_t x, y, size, pad; int64_t coef_off; };
+struct TuDesc { int32_t cu; int16_t tx, ty; };                                        // TU origin inside the CU
+
+struct FrameGeometry
+{
+    std::vector<PuDesc> pus; std::vector<CuDesc> cus; std::vector<TuDesc> tus;
+    std::vector<int32_t> cu_jobs;                 // [cu][ref] -> index of the CU's 2Nx2N PU job
+    // first PU job / CU / TU of every CTU row (+ one past the end): the lists are in CTU raster order, so a CTU-row
+    // range [r0, r1) is one contiguous slice of each list (what a WPP row shard owns, frameencoder.cpp:850-868)
+    int ctuRows; std::vector<int> rowJob, rowCu, rowTu;
+    int64_t ncoef;
+};
+
+// partitions of a CU of `size`: returns the count and fills part[k] = {x, y, w, h} relative to the CU origin
+static inline int geometry_cu_parts(int size, int rect, int amp, int part[13][4])
+{
+    const int h2 = size / 2, q = size / 4;
+    int n = 0;
+#define GEO_PART(x, y, w, h) do { part[n][0] = (x); part[n][1] = (y); part[n][2] = (w); part[n][3] = (h); n++; } while (0)
+    GEO_PART(0, 0, size, size);
+    if (rect)
+    {
+        GEO_PART(0, 0, size, h2); GEO_PART(0, h2, size, h2);
+        GEO_PART(0, 0, h2, size); GEO_PART(h2, 0, h2, size);
+    }
+    if (amp && size >= 16)
+    {   // 2NxnU, 2NxnD, nLx2N, nRx2N (AMP is not allowed at the minimum CU size)
+        GEO_PART(0, 0, size, q);          GEO_PART(0, q, size, size - q);
+        GEO_PART(0, 0, size, size - q);   GEO_PART(0, size - q, size, q);
+        GEO_PART(0, 0, q, size);          GEO_PART(q, 0, size - q, size);
+        GEO_PART(0, 0, size - q, size);   GEO_PART(size - q, 0, q, size);
+    }
+#undef GEO_PART
+    return n;
+}
+
+static inline void geometry_build(int W, int H, int stride, int nref, int rect, int amp, FrameGeometry& g)
+{
+    // CU list: CTU raster, sizes 64..8, raster inside the CTU; CUs must lie fully inside the picture
+    const int ctuW = (W + 63) / 64, ctuH = (H + 63) / 64;
+    int64_t coefOff = 0;
+    g.ctuRows = ctuH;
+    for (int cty = 0; cty < ctuH; cty++)
+    {
+        g.rowJob.push_back((int)g.pus.size()); g.rowCu.push_back((int)g.cus.size()); g.rowTu.push_back((int)g.tus.size());
+        for (int ctx = 0; ctx < ctuW; ctx++)
+        {
+            int local[85]; int nl = 0;
+            for (int size = 64; size >= 8; size >>= 1)
+                for (int cy = 0; cy < 64; cy += size)
+                    for (int cx = 0; cx < 64; cx += size, nl++)
+                    {
+                        const int x = ctx * 64 + cx, y = cty * 64 + cy;
+                        local[nl] = -1;
+                        if (x + size > W || y + size > H) continue;
+                        local[nl] = (int)g.cus.size();
+                        CuDesc c; c.x = (int16_t)x; c.y = (int16_t)y; c.size = (int16_t)size; c.pad = 0; c.coef_off = coefOff;
+                        coefOff += (int64_t)size * size;
+                        const int T = size > 32 ? 32 : size;
+                        for (int ty = 0; ty < size; ty += T)
+                            for (int tx = 0; tx < size; tx += T)
+                            {
+                                TuDesc t; t.cu = (int32_t)g.cus.size(); t.tx = (int16_t)tx; t.ty = (int16_t)ty;
+                                g.tus.push_back(t);
+                            }
+                        g.cus.push_back(c);
+                    }
+            g.cu_jobs.resize(g.cus.size() * nref, -1);
+            // PU jobs of this CTU: per ref, per CU (same order), the CU's partitions in geometry_cu_parts order
+            for (int r = 0; r < nref; r++)
+            {
+                int li = 0;
+                for (int size = 64; size >= 8; size >>= 1)
+                    for (int cy = 0; cy < 64; cy += size)
+                        for (int cx = 0; cx < 64; cx += size, li++)
+                        {
+                            int part[13][4];
+                            const int np = geometry_cu_parts(size, rect, amp, part);
+                            for (int k = 0; k < np; k++)
+                            {
+                                const int x = ctx * 64 + cx + part[k][0], y = cty * 64 + cy + part[k][1], w = part[k][2], h = part[k][3];
+                                if (x + w > W || y + h > H) continue;
+                                PuDesc d; d.offset = y * stride + x; d.cuX = (int16_t)(ctx * 64 + cx); d.cuY = (int16_t)(cty * 64 + cy);
+                                d.pw = (int8_t)w; d.ph = (int8_t)h; d.ref = (int16_t)r;
+                                if (k == 0) g.cu_jobs[(size_t)local[li] * nref + r] = (int32_t)g.pus.size();
+                                g.pus.push_back(d);
+                            }
+                        }
+            }
+        }
+    }
+    g.rowJob.push_back((int)g.pus.size()); g.rowCu.push_back((int)g.cus.size()); g.rowTu.push_back((int)g.tus.size());
+    g.ncoef = coefOff;
+}

@@ -243,7 +243,7 @@ assert LA_INTRA_JOB.itemsize == 56 and LA_JOB.itemsize == 184
 # ---------------- frame-level analyser (x265cu_analyser_*) ----------------
 class AnalysisParams(C.Structure):
     _fields_ = [("width", I), ("height", I), ("depth", I), ("numRefs", I), ("method", I), ("subme", I), ("merange", I),
-                ("rect", I), ("qp", I), ("lam", C.c_double)]
+                ("rect", I), ("qp", I), ("lam", C.c_double), ("amp", I)]
 
 
 class AnalysisOut(C.Structure):
@@ -281,11 +281,11 @@ _PROTOS.update(_AN_PROTOS)
 class Analyser:
     """Host mirror of x265cu_analyser: the public call a user makes for one frame is analyse()."""
 
-    def __init__(self, lib, width, height, depth=8, numRefs=4, method=3, subme=3, merange=57, rect=1, qp=30, lam=None):
+    def __init__(self, lib, width, height, depth=8, numRefs=4, method=3, subme=3, merange=57, rect=1, qp=30, lam=None, amp=0):
         self.lib = lib
         if lam is None:
             lam = round(2.0 ** (qp / 6.0 - 2.0) * (1 << (depth - 8)), 4)      # x265_lambda_tab (constants.cpp:33-50)
-        self.params = AnalysisParams(width, height, depth, numRefs, method, subme, merange, rect, qp, lam)
+        self.params = AnalysisParams(width, height, depth, numRefs, method, subme, merange, rect, qp, lam, amp)
         self.h = lib.L.x265cu_analyser_create(lib.ctx, C.byref(self.params))
         if not self.h:
             raise RuntimeError("x265cu_analyser_create failed: " + lib.last_error())
