@@ -11,7 +11,7 @@ timeout 120 python bench.py --chroma --steps 5 --warmup 3 --no-cpu > gpurun_out/
 timeout 120 python bench.py --shard rows --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_rows.json 2> gpurun_out/bench_rows.err
 M=l1tex__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__lsuin_requests.avg.pct_of_peak_sustained_elapsed,l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sector_hit_rate.pct,l1tex__m_xbar2l1tex_read_sectors.sum,l1tex__f_wavefronts.avg.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum
 timeout 200 ncu --metrics $M --clock-control none -k regex:k_me -c 12 --csv --log-file gpurun_out/me_l1tex.csv python profiles/run_small.py 1024 576 1 2 > gpurun_out/me_l1tex.log 2>&1
-nvcc -arch=sm_100a -O3 -o /tmp/l1_probe profiles/l1_probe.cu && timeout 60 /tmp/l1_probe > gpurun_out/l1_probe.txt 2>&1
+/usr/local/cuda/bin/nvcc -arch=sm_100a -O3 -o /tmp/l1_probe profiles/l1_probe.cu && timeout 60 /tmp/l1_probe > gpurun_out/l1_probe.txt 2>&1
 tail -n 8 gpurun_out/pending_tests.log
 for f in default chroma rows; do python - "$f" <<'P'
 import json, sys
