@@ -12,8 +12,13 @@ timeout 120 python bench.py --shard rows --steps 5 --warmup 3 --no-cpu > gpurun_
 M=l1tex__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__lsuin_requests.avg.pct_of_peak_sustained_elapsed,l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sector_hit_rate.pct,l1tex__m_xbar2l1tex_read_sectors.sum,l1tex__f_wavefronts.avg.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum
 timeout 200 ncu --metrics $M --clock-control none -k regex:k_me -c 12 --csv --log-file gpurun_out/me_l1tex.csv python profiles/run_small.py 1024 576 1 2 > gpurun_out/me_l1tex.log 2>&1
 /usr/local/cuda/bin/nvcc -arch=sm_100a -O3 -o /tmp/l1_probe profiles/l1_probe.cu && timeout 60 /tmp/l1_probe > gpurun_out/l1_probe.txt 2>&1
+# A/B of the per-burst segment width: variant library built on the box (~80 s), parity first, then the bench
+/usr/local/cuda/bin/nvcc -DME_SEG_PER_BURST -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -o /tmp/libx265cu_seg.so x265_b200/csrc/x265cu.cu > gpurun_out/seg_build.log 2>&1 \
+  && X265CU_LIB=/tmp/libx265cu_seg.so timeout 120 python -m pytest tests/test_gpu_me.py tests/test_gpu_frame.py tests/test_gpu_lookahead.py -x -q > gpurun_out/seg_tests.log 2>&1 \
+  && X265CU_LIB=/tmp/libx265cu_seg.so timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_seg.json 2> gpurun_out/bench_seg.err
+tail -n 3 gpurun_out/seg_tests.log
 tail -n 8 gpurun_out/pending_tests.log
-for f in default chroma rows; do python - "$f" <<'P'
+for f in default seg chroma rows; do python - "$f" <<'P'
 import json, sys
 try:
     d = json.load(open("gpurun_out/bench_%s.json" % sys.argv[1])); print(sys.argv[1], round(d["value"]), d["stages_ms"])

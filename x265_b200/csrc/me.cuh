@@ -135,9 +135,19 @@ __device__ __forceinline__ int me_sad_multi_t(const MeCtx<P>& c, const uint8_t* 
 template <typename P>
 __device__ __forceinline__ int me_sad_multi(const MeCtx<P>& c, const uint8_t* __restrict__ base, int n, int offB)
 {
+#ifdef ME_SEG_PER_BURST
+    // experiment (build with -DME_SEG_PER_BURST): narrow the lane segment so that the lanes sharing a
+    // candidate fill one row before they spread over rows (fewer distinct lines per request for small-PU star bursts)
+    const int lgn = n <= 1 ? 0 : 32 - __clz(n - 1);
+    const int lgseg = min(c.lgsegw, max(0, c.lgwpr - (5 - lgn)));
+    if (lgseg == 2) return me_sad_multi_t<P, 2>(c, base, n, offB);
+    if (lgseg == 1) return me_sad_multi_t<P, 1>(c, base, n, offB);
+    return me_sad_multi_t<P, 0>(c, base, n, offB);
+#else
     if (c.lgsegw == 2) return me_sad_multi_t<P, 2>(c, base, n, offB);
     if (c.lgsegw == 1) return me_sad_multi_t<P, 1>(c, base, n, offB);
     return me_sad_multi_t<P, 0>(c, base, n, offB);
+#endif
 }
 
 // SAD of the fenc block against ONE reference position (element pointer, rows may be unaligned); all lanes get it.
