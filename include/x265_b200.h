@@ -58,6 +58,13 @@ int x265cu_me_phase_ms(x265cu_ctx*, float ms[3]);
  * "cu.dct" (i = LumaCU), "cu.intra_pred" (i = LumaCU, j = mode), "quant",
  * "chroma.pu.filter_hpp" (k = csp, i = LumaPU) ...  Returns NULL for entries we do not provide. */
 void* x265cu_get_primitive(int depth, const char* name, int i, int j, int k);
+/* Error convention of the per-call table: the reference's primitives are void / value-returning and cannot
+ * fail, so a CUDA failure inside a thunk never kills the process: the thunk logs, returns zeros and latches this flag.
+ * The encoder-side hook polls it after x265_encoder_encode() and sets m_aborted (encoder/api.cpp:179-180, 222-229), so the
+ * next x265_encoder_encode() returns < 0.  X265CU_DEVICE (environment) selects the GPU of the per-call table. */
+int x265cu_primitive_error(void);
+const char* x265cu_primitive_error_string(void);
+void x265cu_primitive_error_clear(void);
 
 /* ---------- (2) batched API ---------- */
 

@@ -42,6 +42,10 @@ typedef struct {
     int chroma, cstride;
     const DRV_PIXEL* fencC[2];        /* source Cb, Cr */
     const DRV_PIXEL* refC[16][2];     /* reference Cb, Cr */
+    /* bounded samples (bench.py cpu_baseline): analyse only the CTU rows [0, maxCtuRows) of the FULL-frame geometry
+     * (0 = all rows).  The lists are in CTU raster order, so these rows are a prefix of every list and their results are
+     * what a full-frame run produces for them. */
+    int maxCtuRows, njobs_run, ncu_run;
 } drv_frame;
 
 static inline int drv_depth_idx(int size) { return size == 64 ? 0 : (size == 32 ? 1 : (size == 16 ? 2 : 3)); }
@@ -53,7 +57,7 @@ static void drv_intra_one(drv_frame* f, int i);
 static void* drv_worker(void* arg)
 {
     drv_frame* f = (drv_frame*)arg;
-    const int total = f->stage == 0 ? f->njobs : f->ncu;
+    const int total = f->stage == 0 ? f->njobs_run : f->ncu_run;
     const int chunk = f->stage == 0 ? 64 : 16;
     for (;;)
     {
@@ -105,6 +109,15 @@ static void drv_prepare(drv_frame* f)
         f->cu_jobs[c * p->numRefs + j->ref] = i;
     }
     free(grid);
+    f->njobs_run = f->njobs; f->ncu_run = f->ncu;
+    if (f->maxCtuRows > 0)
+    {
+        const int ylim = 64 * f->maxCtuRows;
+        int nj = 0, nc = 0;
+        while (nj < f->njobs && f->jobs[nj].offset / p->stride < ylim) nj++;
+        while (nc < f->ncu && f->cus[nc][1] < ylim) nc++;
+        f->njobs_run = nj; f->ncu_run = nc;
+    }
 }
 
 static void drv_me_one(drv_frame* f, int i)

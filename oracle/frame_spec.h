@@ -98,7 +98,10 @@ static inline int fs_build_me_jobs(const fs_params* p, const int16_t* field, fs_
                 for (int k = 0; k < npu; k++)
                 {
                     int x = ctx * 64 + pus[k][0], y = cty * 64 + pus[k][1], w = pus[k][2], h = pus[k][3];
-                    if (x + w > p->width || y + h > p->height) continue;
+                    /* the reference never evaluates partitions of a CU that crosses the picture edge (analysis.cpp visits
+                     * only CUs inside the picture): filter by the CU, not by the PU */
+                    (void)w; (void)h;
+                    if (ctx * 64 + pus[k][4] + pus[k][6] > p->width || cty * 64 + pus[k][5] + pus[k][6] > p->height) continue;
                     if (jobs)
                     {
                         fs_me_job* j = &jobs[n];

@@ -21,7 +21,8 @@ class DrvFrame(C.Structure):
                 ("ncu", I), ("cus", P), ("cu_jobs", P), ("cu_coef_off", P), ("coef", P), ("recon", P * 4),
                 ("cu_sse", P), ("cu_numsig", P), ("cu_ref", P), ("intra_cost", P),
                 ("threads", I), ("next", I), ("stage", I),
-                ("chroma", I), ("cstride", I), ("fencC", P * 2), ("refC", (P * 2) * 16)]
+                ("chroma", I), ("cstride", I), ("fencC", P * 2), ("refC", (P * 2) * 16),
+                ("maxCtuRows", I), ("njobs_run", I), ("ncu_run", I)]
 
 
 def stride_for(width):
@@ -124,7 +125,7 @@ def lambda_for(qp, depth):
     return round(2.0 ** (qp / 6.0 - 2.0) * (1 << (depth - 8)), 4)
 
 
-def cpu_analyse(lib, fn_name, wl, mvcost_tab, threads=1, stages=7):
+def cpu_analyse(lib, fn_name, wl, mvcost_tab, threads=1, stages=7, max_ctu_rows=0):
     """Run the CPU driver (oracle: orc_analyse_frame, reference: x265ref_analyse_frame)."""
     dt = pixel_dtype(wl.depth)
     f = DrvFrame()
@@ -162,12 +163,13 @@ def cpu_analyse(lib, fn_name, wl, mvcost_tab, threads=1, stages=7):
     f.cu_sse = out["cu_sse"].ctypes.data; f.cu_numsig = out["cu_numsig"].ctypes.data
     f.cu_ref = out["cu_ref"].ctypes.data; f.intra_cost = out["intra_cost"].ctypes.data
     f.threads = threads
+    f.maxCtuRows = max_ctu_rows
     fn = getattr(lib, fn_name)
     fn.argtypes = [C.POINTER(DrvFrame), I]
     fn(C.byref(f), stages)
     nj, nc = f.njobs, f.ncu
     ncoef = int(out["cu_coef_off"][nc - 1] + int(out["cus"][nc - 1][2]) ** 2) if nc else 0
-    res = dict(njobs=nj, ncu=nc, ncoef=ncoef, jobs=out["jobs"][:nj], me_out=out["me_out"][:nj], cus=out["cus"][:nc],
+    res = dict(njobs_run=f.njobs_run, ncu_run=f.ncu_run, njobs=nj, ncu=nc, ncoef=ncoef, jobs=out["jobs"][:nj], me_out=out["me_out"][:nj], cus=out["cus"][:nc],
                cu_jobs=out["cu_jobs"][:nc], cu_coef_off=out["cu_coef_off"][:nc], coef=out["coef"][:ncoef],
                recon=out["recon"], cu_sse=out["cu_sse"][:nc], cu_numsig=out["cu_numsig"][:nc], cu_ref=out["cu_ref"][:nc],
                intra_cost=out["intra_cost"][:nc])

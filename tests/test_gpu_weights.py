@@ -2,7 +2,7 @@
 + weightCostLuma, slicetype.cpp:807-961) against the oracle, which tests/test_lookahead_oracle_vs_ref.py pins to the real
 class: the decision, the weight parameters and the 4 re-weighted lowres planes (whole padded buffers), 8 and 10 bit.
 The device call is host decision logic over launches of kernels the other GPU tests already cover (weight_pp block op,
-grid SATD); it was written after the round's GPU minutes were spent, hence the non-strict xfail until its first run."""
+grid SATD); first run green on the round-1 driver box (GPUTEST_r01.json)."""
 import ctypes as C
 
 import numpy as np
@@ -23,7 +23,6 @@ def cu():
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.xfail(reason="first GPU run pending (added after this round's GPU minutes were spent)", strict=False)
 @pytest.mark.parametrize("depth", [8, 10])
 @pytest.mark.parametrize("case", ["same", "fade", "fade2", "bright", "offset"])
 def test_weights_analyse(cu, depth, case):

@@ -2,8 +2,7 @@
 the ME stage runs the k_me_chroma launches on resident 4:2:0 planes) against the oracle's frame driver, which
 tests/test_frame_oracle_vs_ref.py::test_frame_driver_chroma pins to the real MotionEstimate (Yuv setSourcePU, bChroma).
 The kernels are the ones tests/test_gpu_me.py::test_me_batch_chroma covers; the analyser glue (plane residency, border
-extension, argument passing) was written after the round's GPU minutes were spent, hence the non-strict xfail until its
-first run.  Kept in a file that sorts last so that a fault here cannot disturb the verified tests."""
+extension, argument passing) first ran green on the round-1 driver box (GPUTEST_r01.json).  Kept in a file that sorts last so that a fault here cannot disturb the verified tests."""
 import numpy as np
 import pytest
 
@@ -21,7 +20,6 @@ def cu():
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.xfail(reason="first GPU run pending (added after this round's GPU minutes were spent)", strict=False)
 @pytest.mark.parametrize("depth", [8, 10])
 @pytest.mark.parametrize("noise", [False, True])
 def test_frame_analysis_chroma(cu, depth, noise):
@@ -58,7 +56,6 @@ def test_frame_analysis_chroma(cu, depth, noise):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.xfail(reason="first GPU run pending (added after this round's GPU minutes were spent)", strict=False)
 @pytest.mark.parametrize("depth", [8, 10])
 def test_frame_analysis_amp(cu, depth):
     """rect + AMP PU set (presets slower / veryslow): the host geometry (CPU-checked against the oracle by tests/test_geometry.py)

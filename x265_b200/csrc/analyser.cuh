@@ -58,6 +58,7 @@ static int an_run(x265cu_analyser* a, int stages, int r0, int r1)
 {
     x265cu_ctx* c = a->ctx;
     const int depth = a->p.depth;
+    cudaSetDevice(c->device);
     if (r0 < 0 || r1 > a->ctuRows || r0 >= r1) { x265cu_set_error("analyser: bad CTU row range", cudaErrorInvalidValue, __FILE__, __LINE__); return -1; }
     const int job0 = a->rowJob[r0], nj = a->rowJob[r1] - job0;
     const int cu0 = a->rowCu[r0], ncu = a->rowCu[r1] - cu0;
@@ -116,6 +117,7 @@ static int an_upload_plane(x265cu_analyser* a, uint8_t* d_plane, const void* hos
 {
     x265cu_ctx* c = a->ctx;
     const size_t es = a->p.depth == 8 ? 1 : 2;
+    cudaSetDevice(c->device);
     CU_CHECK(cudaMemcpy2DAsync(d_plane + a->orgBytes, (size_t)a->stride * es, host, (size_t)hostStride * es,
                                (size_t)a->p.width * es, a->p.height, cudaMemcpyHostToDevice, c->stream));
     return x265cu_extend_border(c, a->p.depth, d_plane + a->orgBytes, a->stride, a->p.width, a->p.height, AN_MARGIN_X, AN_MARGIN_Y);
@@ -223,6 +225,7 @@ static int an_upload_cplane(x265cu_analyser* a, uint8_t* d_plane, const void* ho
     x265cu_ctx* c = a->ctx;
     const size_t es = a->p.depth == 8 ? 1 : 2;
     const int cw = a->p.width >> 1, ch = a->p.height >> 1;
+    cudaSetDevice(c->device);
     CU_CHECK(cudaMemcpy2DAsync(d_plane + a->cOrgBytes, (size_t)a->cstride * es, host, (size_t)hostStride * es,
                                (size_t)cw * es, ch, cudaMemcpyHostToDevice, c->stream));
     return x265cu_extend_border(c, a->p.depth, d_plane + a->cOrgBytes, a->cstride, cw, ch, AN_MARGIN_X / 2, AN_MARGIN_Y / 2);
@@ -340,6 +343,7 @@ void* x265cu_analyser_ref_plane(x265cu_analyser* a, int idx, int* stride)
 int x265cu_analyser_ref_updated(x265cu_analyser* a, int idx)
 {
     if (idx < 0 || idx >= a->p.numRefs) return -1;
+    cudaSetDevice(a->ctx->device);
     return x265cu_extend_border(a->ctx, a->p.depth, a->d_refs[idx] + a->orgBytes, a->stride, a->p.width, a->p.height, AN_MARGIN_X, AN_MARGIN_Y);
 }
 
@@ -358,6 +362,7 @@ int x265cu_analyser_recon_to_ref(x265cu_analyser* a, int depthIdx, int idx, int 
     if (depthIdx < 0 || depthIdx >= 4 || idx < 0 || idx >= a->p.numRefs || ctuRow0 < 0 || ctuRow1 > a->ctuRows || ctuRow0 >= ctuRow1) return -1;
     const size_t es = a->p.depth == 8 ? 1 : 2;
     const int y0 = ctuRow0 * 64, y1 = ctuRow1 * 64 < a->p.height ? ctuRow1 * 64 : a->p.height;
+    cudaSetDevice(a->ctx->device);
     const size_t off = a->orgBytes + (size_t)y0 * a->stride * es, pitch = (size_t)a->stride * es;
     CU_CHECK(cudaMemcpy2DAsync(a->d_refs[idx] + off, pitch, a->d_recon[depthIdx] + off, pitch, (size_t)a->p.width * es, y1 - y0,
                                cudaMemcpyDeviceToDevice, a->ctx->stream));
@@ -370,6 +375,7 @@ int x265cu_analyser_fetch(x265cu_analyser* a, int what, void* host)
     x265cu_ctx* c = a->ctx;
     const size_t es = a->p.depth == 8 ? 1 : 2;
     const void* src = NULL; size_t bytes = 0;
+    cudaSetDevice(c->device);
     switch (what)
     {
     case 0: src = a->d_jobs; bytes = sizeof(x265cu_me_job) * a->njobs; break;

@@ -1,8 +1,8 @@
 // x265_b200/csrc/geometry.h -- host-only (no CUDA): the static geometry tables of the frame analyser.
 // PU / CU / TU lists of a picture in canonical order (CTU raster; per CTU and reference the CUs 64..8 in raster order, each
 // with its 2Nx2N PU, then -- rect -- 2NxN x2, Nx2N x2, then -- amp, CU >= 16 -- 2NxnU, 2NxnD, nLx2N, nRx2N; preset slow has rect
-// on and AMP off, slower / veryslow have both: common/param.cpp:478-520).  PUs and CUs must lie fully inside the picture
-// (analysis.cpp only visits CUs inside it).  Kept free of CUDA so that tests/test_geometry.py can check it on the CPU
+// on and AMP off, slower / veryslow have both: common/param.cpp:478-520).  A CU must lie fully inside the picture
+// (analysis.cpp only visits CUs inside it); no partition of a CU that crosses the edge is emitted.  Kept free of CUDA so that tests/test_geometry.py can check it on the CPU
 // against the oracle's independent enumeration (oracle/frame_spec.h) at every BASELINE picture size.
 #pragma once
 #include <stdint.h>
@@ -85,12 +85,12 @@ static inline void geometry_build(int W, int H, int stride, int nref, int rect, 
                     for (int cy = 0; cy < 64; cy += size)
                         for (int cx = 0; cx < 64; cx += size, li++)
                         {
+                            if (local[li] < 0) continue;          // CU crosses the picture edge: no partition of it is evaluated
                             int part[13][4];
                             const int np = geometry_cu_parts(size, rect, amp, part);
                             for (int k = 0; k < np; k++)
                             {
                                 const int x = ctx * 64 + cx + part[k][0], y = cty * 64 + cy + part[k][1], w = part[k][2], h = part[k][3];
-                                if (x + w > W || y + h > H) continue;
                                 PuDesc d; d.offset = y * stride + x; d.cuX = (int16_t)(ctx * 64 + cx); d.cuY = (int16_t)(cty * 64 + cy);
                                 d.pw = (int8_t)w; d.ph = (int8_t)h; d.ref = (int16_t)r;
                                 if (k == 0) g.cu_jobs[(size_t)local[li] * nref + r] = (int32_t)g.pus.size();

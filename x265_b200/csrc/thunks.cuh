@@ -18,10 +18,26 @@ struct Stage
     size_t used;
     bool ok;
     Stage() : ctx(NULL), used(0), ok(true) {}
+    // The arena grows on demand (whole-plane calls such as weight_pp on a padded lowres plane, slicetype.cpp:817-858, do not
+    // fit the initial 4 MB): every thunk ends with a stream synchronize, so nothing is in flight when it is replaced.
+    bool grow(size_t need)
+    {
+        size_t nb = ctx->stage_bytes;
+        while (nb < need) nb *= 2;
+        if (nb > ((size_t)1 << 31)) return false;
+        uint8_t* nh = NULL; uint8_t* nd = NULL;
+        if (cudaMallocHost((void**)&nh, nb) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaMalloc((void**)&nd, nb) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(nh); return false; }
+        memcpy(nh, ctx->h_stage, used);
+        cudaFreeHost(ctx->h_stage); cudaFree(ctx->d_stage);
+        ctx->h_stage = nh; ctx->d_stage = nd; ctx->stage_bytes = nb;
+        return true;
+    }
     size_t reserve(size_t bytes)
     {
+        if (!ctx) { ok = false; return 0; }
         size_t off = (used + 63) & ~(size_t)63;
-        if (off + bytes > ctx->stage_bytes) { ok = false; return 0; }
+        if (off + bytes > ctx->stage_bytes && !grow(off + bytes)) { ok = false; return 0; }
         used = off + bytes;
         return off;
     }
@@ -51,18 +67,31 @@ struct Stage
     }
 };
 
+// Error convention: the reference's primitives cannot fail, so a CUDA failure is surfaced OUT OF BAND: the thunk
+// logs, latches a process-wide flag (x265cu_primitive_error) and returns zeros; the encoder-side hook polls the flag after
+// x265_encoder_encode and sets m_aborted (encoder/api.cpp:179-180, 222-229).  A thunk never kills the host process.
+static int g_prim_error = 0;
+static char g_prim_msg[256] = "";
+static void fail(const char* what)
+{
+    if (!__atomic_exchange_n(&g_prim_error, 1, __ATOMIC_SEQ_CST))
+        snprintf(g_prim_msg, sizeof(g_prim_msg), "%s: %s", what, x265cu_last_error());
+    fprintf(stderr, "x265cu: primitive failed: %s: %s\n", what, x265cu_last_error());
+}
+
 static thread_local x265cu_ctx* t_ctx = NULL;
 static x265cu_ctx* tctx()
 {
     if (!t_ctx)
     {
-        t_ctx = x265cu_create(0);
-        if (!t_ctx) { fprintf(stderr, "x265cu: FATAL: primitive called without a CUDA device (no CPU fallback)\n"); abort(); }
+        // X265CU_DEVICE selects the GPU of the per-call table (default 0)
+        const char* e = getenv("X265CU_DEVICE");
+        t_ctx = x265cu_create(e ? atoi(e) : 0);
+        if (!t_ctx) { fail("primitive called without a usable CUDA device (no CPU fallback)"); return NULL; }
     }
     cudaSetDevice(t_ctx->device);
     return t_ctx;
 }
-static void fail(const char* what) { fprintf(stderr, "x265cu: FATAL: %s: %s\n", what, x265cu_last_error()); abort(); }
 
 // ---------- pixel compare ----------
 template <typename P>
@@ -73,11 +102,11 @@ static uint64_t pixelcmp(int op, const void* a, intptr_t sa, const void* b, intp
     size_t ob = b ? s.put(b, sb, w, h, esB) : oa;
     size_t oj = s.reserve(sizeof(x265cu_cmp_job));
     size_t oo = s.reserve(sizeof(uint64_t));
-    if (!s.ok) fail("stage overflow");
+    if (!s.ok) { fail("stage overflow"); return 0; }
     x265cu_cmp_job* j = s.h<x265cu_cmp_job>(oj);
     j->a_off = (int64_t)(oa / esA); j->b_off = (int64_t)(ob / esB); j->a_stride = w; j->b_stride = w; j->w = (int16_t)w; j->h = (int16_t)h; j->pad = 0;
     if (s.upload() || launch_pixelcmp(s.ctx, PixTraits<P>::depth, op, s.ctx->d_stage, s.ctx->d_stage, s.d<x265cu_cmp_job>(oj), 1, s.d<uint64_t>(oo)) ||
-        s.download(oo, sizeof(uint64_t))) fail("pixelcmp");
+        s.download(oo, sizeof(uint64_t))) { fail("pixelcmp"); return 0; }
     return *s.h<uint64_t>(oo);
 }
 
@@ -90,14 +119,14 @@ static void sad_xn(int nref, const P* fenc, const P* const* refs, intptr_t rs, i
     for (int i = 0; i < nref; i++) orf[i] = s.put(refs[i], rs, w, h, sizeof(P));
     size_t oj = s.reserve(sizeof(x265cu_cmp_job) * nref);
     size_t oo = s.reserve(sizeof(uint64_t) * nref);
-    if (!s.ok) fail("stage overflow");
+    if (!s.ok) { fail("stage overflow"); return; }
     for (int i = 0; i < nref; i++)
     {
         x265cu_cmp_job* j = s.h<x265cu_cmp_job>(oj) + i;
         j->a_off = of / sizeof(P); j->b_off = orf[i] / sizeof(P); j->a_stride = w; j->b_stride = w; j->w = (int16_t)w; j->h = (int16_t)h; j->pad = 0;
     }
     if (s.upload() || launch_pixelcmp(s.ctx, PixTraits<P>::depth, X265CU_SAD, s.ctx->d_stage, s.ctx->d_stage, s.d<x265cu_cmp_job>(oj), nref, s.d<uint64_t>(oo)) ||
-        s.download(oo, sizeof(uint64_t) * nref)) fail("sad_xn");
+        s.download(oo, sizeof(uint64_t) * nref)) { fail("sad_xn"); return; }
     for (int i = 0; i < nref; i++) res[i] = (int32_t)s.h<uint64_t>(oo)[i];
 }
 
@@ -112,13 +141,13 @@ static void blockop(int op, void* dst, intptr_t ds, int dw, int dh, int esD, con
     size_t ob = b ? s.put(b, sb, bw, bh, esB) : 0;
     size_t od = s.reserve((size_t)dw * dh * esD);
     size_t oj = s.reserve(sizeof(x265cu_blk_job));
-    if (!s.ok) fail("stage overflow");
+    if (!s.ok) { fail("stage overflow"); return; }
     x265cu_blk_job* j = s.h<x265cu_blk_job>(oj);
     j->d_off = od / esD; j->a_off = a ? oa / esA : 0; j->b_off = b ? ob / esB : 0;
     j->d_stride = dw; j->a_stride = aw; j->b_stride = bw; j->w = (int16_t)w; j->h = (int16_t)h;
     j->p0 = p0; j->p1 = p1; j->p2 = p2; j->p3 = p3;
     if (s.upload() || launch_blockop(s.ctx, PixTraits<P>::depth, op, s.ctx->d_stage, s.ctx->d_stage, s.ctx->d_stage, s.d<x265cu_blk_job>(oj), 1) ||
-        s.download(od, (size_t)dw * dh * esD)) fail("blockop");
+        s.download(od, (size_t)dw * dh * esD)) { fail("blockop"); return; }
     s.get(dst, ds, dw, dh, esD, od);
 }
 
@@ -140,12 +169,12 @@ static void interp(int op, const void* src, intptr_t ss, void* dst, intptr_t ds,
     size_t os = s.put(sp, ss, ww, wh, esS);
     size_t od = s.reserve((size_t)w * outRows * esD);
     size_t oj = s.reserve(sizeof(x265cu_interp_job));
-    if (!s.ok) fail("stage overflow");
+    if (!s.ok) { fail("stage overflow"); return; }
     x265cu_interp_job* j = s.h<x265cu_interp_job>(oj);
     j->s_off = os / esS + (int64_t)vt * ww + hl; j->d_off = od / esD; j->s_stride = ww; j->d_stride = w;
     j->w = (int16_t)w; j->h = (int16_t)h; j->idxX = (int8_t)idxX; j->idxY = (int8_t)idxY; j->rowExt = (int8_t)rowExt; j->ntaps = (int8_t)ntaps;
     if (s.upload() || launch_interp(s.ctx, PixTraits<P>::depth, op, s.ctx->d_stage, s.ctx->d_stage, s.d<x265cu_interp_job>(oj), 1) ||
-        s.download(od, (size_t)w * outRows * esD)) fail("interp");
+        s.download(od, (size_t)w * outRows * esD)) { fail("interp"); return; }
     s.get(dst, ds, w, outRows, esD, od);
 }
 
@@ -157,9 +186,9 @@ static void transform(int op, int N, const int16_t* src, int16_t* dst, intptr_t 
     Stage s; s.ctx = tctx();
     size_t os = fwd ? s.put(src, stride, N, N, 2) : s.put(src, N, N, N, 2);
     size_t od = s.reserve((size_t)N * N * 2);
-    if (!s.ok) fail("stage overflow");
+    if (!s.ok) { fail("stage overflow"); return; }
     if (s.upload() || launch_transform(s.ctx, PixTraits<P>::depth, op, N, s.d<int16_t>(os), s.d<int16_t>(od), N, (int64_t)N * N, 1) ||
-        s.download(od, (size_t)N * N * 2)) fail("transform");
+        s.download(od, (size_t)N * N * 2)) { fail("transform"); return; }
     if (fwd) memcpy(dst, s.h<int16_t>(od), (size_t)N * N * 2);
     else s.get(dst, stride, N, N, 2, od);
 }
@@ -169,9 +198,9 @@ static uint32_t quant(const int16_t* coef, const int32_t* qc, int32_t* deltaU, i
     Stage s; s.ctx = tctx();
     size_t oc = s.put(coef, numCoeff, numCoeff, 1, 2), oq = s.put(qc, numCoeff, numCoeff, 1, 4);
     size_t odu = s.reserve((size_t)numCoeff * 4), oqc = s.reserve((size_t)numCoeff * 2), on = s.reserve(4);
-    if (!s.ok) fail("stage overflow");
+    if (!s.ok) { fail("stage overflow"); return 0; }
     if (s.upload() || x265cu_quant_batch(s.ctx, s.d<int16_t>(oc), s.d<int32_t>(oq), deltaU ? s.d<int32_t>(odu) : NULL, s.d<int16_t>(oqc), qBits, add, numCoeff, 1, nq, s.d<uint32_t>(on)) ||
-        s.download(odu, (on + 4) - odu)) fail("quant");
+        s.download(odu, (on + 4) - odu)) { fail("quant"); return 0; }
     if (deltaU) memcpy(deltaU, s.h<int32_t>(odu), (size_t)numCoeff * 4);
     memcpy(qCoef, s.h<int16_t>(oqc), (size_t)numCoeff * 2);
     return *s.h<uint32_t>(on);
@@ -181,8 +210,8 @@ static void dequant_normal(const int16_t* q, int16_t* coef, int num, int scale, 
 {
     Stage s; s.ctx = tctx();
     size_t oq = s.put(q, num, num, 1, 2), oc = s.reserve((size_t)num * 2);
-    if (!s.ok) fail("stage overflow");
-    if (s.upload() || x265cu_dequant_normal_batch(s.ctx, s.d<int16_t>(oq), s.d<int16_t>(oc), num, scale, shift) || s.download(oc, (size_t)num * 2)) fail("dequant");
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload() || x265cu_dequant_normal_batch(s.ctx, s.d<int16_t>(oq), s.d<int16_t>(oc), num, scale, shift) || s.download(oc, (size_t)num * 2)) { fail("dequant"); return; }
     memcpy(coef, s.h<int16_t>(oc), (size_t)num * 2);
 }
 
@@ -190,8 +219,8 @@ static void dequant_scaling(const int16_t* q, const int32_t* dq, int16_t* coef, 
 {
     Stage s; s.ctx = tctx();
     size_t oq = s.put(q, num, num, 1, 2), odq = s.put(dq, num, num, 1, 4), oc = s.reserve((size_t)num * 2);
-    if (!s.ok) fail("stage overflow");
-    if (s.upload() || x265cu_dequant_scaling_batch(s.ctx, s.d<int16_t>(oq), s.d<int32_t>(odq), s.d<int16_t>(oc), num, 1, per, shift) || s.download(oc, (size_t)num * 2)) fail("dequant_scaling");
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload() || x265cu_dequant_scaling_batch(s.ctx, s.d<int16_t>(oq), s.d<int32_t>(odq), s.d<int16_t>(oc), num, 1, per, shift) || s.download(oc, (size_t)num * 2)) { fail("dequant_scaling"); return; }
     memcpy(coef, s.h<int16_t>(oc), (size_t)num * 2);
 }
 
@@ -199,11 +228,11 @@ static void denoise(int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, 
 {
     Stage s; s.ctx = tctx();
     size_t oc = s.put(dctCoef, numCoeff, numCoeff, 1, 2), orr = s.put(resSum, numCoeff, numCoeff, 1, 4), oo = s.put(offset, numCoeff, numCoeff, 1, 2);
-    if (!s.ok) fail("stage overflow");
-    if (s.upload()) fail("denoise");
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("denoise"); return; }
     k_denoise<<<(numCoeff + 255) / 256, 256, 0, s.ctx->stream>>>(s.d<int16_t>(oc), s.d<uint32_t>(orr), s.d<uint16_t>(oo), numCoeff);
     s.ctx->launches++;
-    if (s.download(oc, (orr + (size_t)numCoeff * 4) - oc)) fail("denoise");
+    if (s.download(oc, (orr + (size_t)numCoeff * 4) - oc)) { fail("denoise"); return; }
     memcpy(dctCoef, s.h<int16_t>(oc), (size_t)numCoeff * 2);
     memcpy(resSum, s.h<uint32_t>(orr), (size_t)numCoeff * 4);
 }
@@ -220,10 +249,10 @@ static uint32_t count_nonzero_blk(const int16_t* src, intptr_t stride, int N, in
 {
     Stage s; s.ctx = tctx();
     size_t oq = s.put(src, stride, N, N, 2), on = s.reserve(4);
-    if (!s.ok || s.upload()) fail("count_nonzero");
+    if (!s.ok || s.upload()) { fail("count_nonzero"); return 0; }
     k_count_nonzero<<<1, 32, 0, s.ctx->stream>>>(s.d<int16_t>(oq), N * N, s.d<uint32_t>(on));
     s.ctx->launches++;
-    if (s.download(oq, (on + 4) - oq)) fail("count_nonzero");     // coefficients come back from the device copy
+    if (s.download(oq, (on + 4) - oq)) { fail("count_nonzero"); return 0; }     // coefficients come back from the device copy
     if (copyTo) memcpy(copyTo, s.h<int16_t>(oq), (size_t)N * N * 2);
     return *s.h<uint32_t>(on);
 }
@@ -234,10 +263,10 @@ static void intra_pred(int N, P* dst, intptr_t ds, const P* nb, int mode, int bF
 {
     Stage s; s.ctx = tctx();
     size_t onb = s.put(nb, 4 * N + 1, 4 * N + 1, 1, sizeof(P)), od = s.reserve((size_t)N * N * sizeof(P)), oj = s.reserve(sizeof(x265cu_intra_job));
-    if (!s.ok) fail("stage overflow");
+    if (!s.ok) { fail("stage overflow"); return; }
     s.h<x265cu_intra_job>(oj)->mode = mode; s.h<x265cu_intra_job>(oj)->bFilter = bFilter;
     if (s.upload() || x265cu_intra_pred_batch(s.ctx, PixTraits<P>::depth, N, s.d<P>(onb), 4 * N + 1, s.d<P>(od), (int64_t)N * N, N, s.d<x265cu_intra_job>(oj), 1) ||
-        s.download(od, (size_t)N * N * sizeof(P))) fail("intra_pred");
+        s.download(od, (size_t)N * N * sizeof(P))) { fail("intra_pred"); return; }
     s.get(dst, ds, N, N, sizeof(P), od);
 }
 template <typename P>
@@ -246,8 +275,8 @@ static void intra_filter(int N, const P* nb, P* filt)
     Stage s; s.ctx = tctx();
     const int len = 4 * N + 1;
     size_t onb = s.put(nb, len, len, 1, sizeof(P)), of = s.reserve((size_t)len * sizeof(P));
-    if (!s.ok) fail("stage overflow");
-    if (s.upload() || x265cu_intra_filter_batch(s.ctx, PixTraits<P>::depth, N, s.d<P>(onb), s.d<P>(of), len, 1) || s.download(of, (size_t)len * sizeof(P))) fail("intra_filter");
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload() || x265cu_intra_filter_batch(s.ctx, PixTraits<P>::depth, N, s.d<P>(onb), s.d<P>(of), len, 1) || s.download(of, (size_t)len * sizeof(P))) { fail("intra_filter"); return; }
     memcpy(filt, s.h<P>(of), (size_t)len * sizeof(P));
 }
 template <typename P>
@@ -256,9 +285,9 @@ static void intra_allangs(int N, P* dst, const P* refp, const P* filtp, int bLum
     Stage s; s.ctx = tctx();
     const int len = 4 * N + 1;
     size_t orf = s.put(refp, len, len, 1, sizeof(P)), of = s.put(filtp, len, len, 1, sizeof(P)), od = s.reserve((size_t)33 * N * N * sizeof(P));
-    if (!s.ok) fail("stage overflow");
+    if (!s.ok) { fail("stage overflow"); return; }
     if (s.upload() || x265cu_intra_allangs_batch(s.ctx, PixTraits<P>::depth, N, s.d<P>(orf), s.d<P>(of), len, s.d<P>(od), bLuma, 1) ||
-        s.download(od, (size_t)33 * N * N * sizeof(P))) fail("intra_allangs");
+        s.download(od, (size_t)33 * N * N * sizeof(P))) { fail("intra_allangs"); return; }
     memcpy(dst, s.h<P>(od), (size_t)33 * N * N * sizeof(P));
 }
 
@@ -268,16 +297,18 @@ static void frame_init_lowres(const P* src0, P* d0, P* dh, P* dv, P* dc, intptr_
 {
     // dedicated buffers: frames do not fit the staging arena
     x265cu_ctx* c = tctx();
+    if (!c) return;
     const int sw = 2 * width + 1, sh = 2 * height + 1;
     const size_t sbytes = (size_t)sw * sh * sizeof(P), dbytes = (size_t)width * height * sizeof(P);
     P* hs = (P*)malloc(sbytes + 4 * dbytes);
+    if (!hs) { fail("lowres host alloc"); return; }
     for (int y = 0; y < sh; y++) memcpy(hs + (size_t)y * sw, src0 + (ptrdiff_t)y * sstride, (size_t)sw * sizeof(P));
     uint8_t* dev = (uint8_t*)x265cu_malloc(c, sbytes + 4 * dbytes + 256);
-    if (!dev) fail("lowres alloc");
+    if (!dev) { free(hs); fail("lowres alloc"); return; }
     uint8_t* dd = dev + ((sbytes + 255) & ~(size_t)255);
     if (x265cu_h2d(c, dev, hs, sbytes) ||
         x265cu_frame_init_lowres(c, PixTraits<P>::depth, dev, sw, dd, dd + dbytes, dd + 2 * dbytes, dd + 3 * dbytes, width, width, height, 0, 0) ||
-        x265cu_d2h(c, (uint8_t*)hs + sbytes, dd, 4 * dbytes) || x265cu_sync(c)) fail("frame_init_lowres");
+        x265cu_d2h(c, (uint8_t*)hs + sbytes, dd, 4 * dbytes) || x265cu_sync(c)) { x265cu_free(c, dev); free(hs); fail("frame_init_lowres"); return; }
     P* outs[4] = { d0, dh, dv, dc };
     for (int p = 0; p < 4; p++)
         for (int y = 0; y < height; y++)
@@ -327,10 +358,10 @@ static int ads(int w, int h, int* encDC, uint32_t* sums, int delta, uint16_t* co
     const int nsums = width + (terms == 4 ? delta + half : (terms == 2 ? delta : 0));
     size_t oe = s.put(encDC, 4, terms, 1, 4), os = s.put(sums, nsums, nsums, 1, 4), oc = s.put(costMvX, width, width, 1, 2);
     size_t om = s.reserve((size_t)width * 2), on = s.reserve(4);
-    if (!s.ok || s.upload()) fail("ads");
+    if (!s.ok || s.upload()) { fail("ads"); return 0; }
     k_ads<<<1, 32, 0, s.ctx->stream>>>(terms, half, s.d<int>(oe), s.d<uint32_t>(os), delta, s.d<uint16_t>(oc), s.d<int16_t>(om), width, thresh, s.d<int>(on));
     s.ctx->launches++;
-    if (s.download(om, (on + 4) - om)) fail("ads");
+    if (s.download(om, (on + 4) - om)) { fail("ads"); return 0; }
     int n = *s.h<int>(on);
     memcpy(mvs, s.h<int16_t>(om), (size_t)n * 2);
     return n;
@@ -481,6 +512,10 @@ static void* lookup(const char* name, int i, int j, int k)
 }
 
 } // namespace thunk
+
+extern "C" int x265cu_primitive_error(void) { return __atomic_load_n(&thunk::g_prim_error, __ATOMIC_SEQ_CST); }
+extern "C" const char* x265cu_primitive_error_string(void) { return thunk::g_prim_msg; }
+extern "C" void x265cu_primitive_error_clear(void) { __atomic_store_n(&thunk::g_prim_error, 0, __ATOMIC_SEQ_CST); thunk::g_prim_msg[0] = 0; }
 
 extern "C" void* x265cu_get_primitive(int depth, const char* name, int i, int j, int k)
 {

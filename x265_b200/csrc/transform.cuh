@@ -6,6 +6,7 @@
 #pragma once
 #include "common.cuh"
 #include "transform_mma.cuh"
+#include <mutex>
 
 // host: regenerate the HEVC matrices from the 32-point basis and upload them
 static const int16_t h_basis[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67,
@@ -16,20 +17,36 @@ static int h_basis_at(int a)
     if (a > 64) a = 128 - a;
     return a <= 32 ? h_basis[a] : -h_basis[64 - a];
 }
-static int build_dct_tables()
+// The host table is a function-local static built exactly once (C++11 thread-safe initialisation) and never written again;
+// the upload into the device-global __constant__ copy happens once per DEVICE under a mutex (several host threads create
+// contexts concurrently when the per-call table is plugged into the encoder's worker pool).
+struct DctHostTable
 {
-    static int8_t tab[4][32 * 32];
-    memset(tab, 0, sizeof(tab));
-    for (int l = 0; l < 4; l++)
+    int8_t tab[4][32 * 32];
+    DctHostTable()
     {
-        int n = 4 << l, step = 32 / n;
-        for (int k = 0; k < n; k++)
-            for (int j = 0; j < n; j++)
-                tab[l][k * n + j] = (int8_t)h_basis_at(k * step * (2 * j + 1));
+        memset(tab, 0, sizeof(tab));
+        for (int l = 0; l < 4; l++)
+        {
+            int n = 4 << l, step = 32 / n;
+            for (int k = 0; k < n; k++)
+                for (int j = 0; j < n; j++)
+                    tab[l][k * n + j] = (int8_t)h_basis_at(k * step * (2 * j + 1));
+        }
     }
+};
+static int build_dct_tables(int device)
+{
+    static const DctHostTable host;
     static const int8_t dst4[16] = { 29, 55, 74, 84, 74, 74, 0, -74, 84, -29, -74, 55, 55, -84, 74, -29 };
-    CU_CHECK(cudaMemcpyToSymbol(c_dct, tab, sizeof(tab)));
+    static std::mutex mtx;
+    static bool uploaded[64] = { false };
+    std::lock_guard<std::mutex> lock(mtx);
+    if (device >= 0 && device < 64 && uploaded[device]) return 0;
+    CU_CHECK(cudaMemcpyToSymbol(c_dct, host.tab, sizeof(host.tab)));
     CU_CHECK(cudaMemcpyToSymbol(c_dst4, dst4, sizeof(dst4)));
+    CU_CHECK(cudaDeviceSynchronize());
+    if (device >= 0 && device < 64) uploaded[device] = true;
     return 0;
 }
 

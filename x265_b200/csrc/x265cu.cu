@@ -31,6 +31,17 @@ int x265cu_device_count(void)
     return n;
 }
 
+static void ctx_release(x265cu_ctx* c)
+{
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    cudaFree(c->d_stage); cudaFree(c->d_counter); cudaFree(c->d_me_state);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 4; i++) if (c->me_ev[i]) cudaEventDestroy(c->me_ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
 x265cu_ctx* x265cu_create(int device)
 {
     if (device < 0 || device >= x265cu_device_count())
@@ -45,34 +56,34 @@ x265cu_ctx* x265cu_create(int device)
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NULL; }
-    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
-    for (int i = 0; i < 4; i++) cudaEventCreate(&c->me_ev[i]);
-    if (build_dct_tables() != 0) { delete c; return NULL; }
     c->stage_bytes = 4u << 20;
-    if (cudaMallocHost((void**)&c->h_stage, c->stage_bytes) != cudaSuccess ||
-        cudaMalloc((void**)&c->d_stage, c->stage_bytes) != cudaSuccess ||
-        cudaMalloc((void**)&c->d_counter, 64) != cudaSuccess)
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&c->me_ev[i]) == cudaSuccess;
+    ok = ok && build_dct_tables(device) == 0;
+    ok = ok && cudaMallocHost((void**)&c->h_stage, c->stage_bytes) == cudaSuccess &&
+         cudaMalloc((void**)&c->d_stage, c->stage_bytes) == cudaSuccess &&
+         cudaMalloc((void**)&c->d_counter, 64) == cudaSuccess;
+    if (!ok)
     {
-        x265cu_set_error("ctx alloc", cudaGetLastError(), __FILE__, __LINE__);
-        delete c; return NULL;
+        x265cu_set_error("ctx create", cudaGetLastError(), __FILE__, __LINE__);
+        ctx_release(c);
+        return NULL;
     }
     return c;
 }
 
 void x265cu_destroy(x265cu_ctx* c)
 {
+    cudaSetDevice(c->device);
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFreeHost(c->h_stage); cudaFree(c->d_stage); cudaFree(c->d_counter); cudaFree(c->d_me_state);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
-    delete c;
+    ctx_release(c);
 }
 
-int x265cu_sync(x265cu_ctx* c) { CU_CHECK(cudaStreamSynchronize(c->stream)); return 0; }
-void* x265cu_stream(x265cu_ctx* c) { return (void*)c->stream; }
+int x265cu_sync(x265cu_ctx* c) { cudaSetDevice(c->device); CU_CHECK(cudaStreamSynchronize(c->stream)); return 0; }
+void* x265cu_stream(x265cu_ctx* c) { cudaSetDevice(c->device); return (void*)c->stream; }
 void* x265cu_malloc(x265cu_ctx* c, size_t bytes)
 {
     void* p = NULL;
@@ -83,12 +94,13 @@ void* x265cu_malloc(x265cu_ctx* c, size_t bytes)
 void x265cu_free(x265cu_ctx* c, void* dev) { cudaSetDevice(c->device); cudaFree(dev); }
 void* x265cu_host_alloc(size_t bytes) { void* p = NULL; if (cudaMallocHost(&p, bytes) != cudaSuccess) return NULL; return p; }
 void x265cu_host_free(void* p) { cudaFreeHost(p); }
-int x265cu_h2d(x265cu_ctx* c, void* dev, const void* host, size_t bytes) { CU_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream)); return 0; }
-int x265cu_d2h(x265cu_ctx* c, void* host, const void* dev, size_t bytes) { CU_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream)); return 0; }
-int x265cu_memset(x265cu_ctx* c, void* dev, int value, size_t bytes) { CU_CHECK(cudaMemsetAsync(dev, value, bytes, c->stream)); return 0; }
-int x265cu_timer_begin(x265cu_ctx* c) { CU_CHECK(cudaEventRecord(c->ev0, c->stream)); return 0; }
+int x265cu_h2d(x265cu_ctx* c, void* dev, const void* host, size_t bytes) { cudaSetDevice(c->device); CU_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream)); return 0; }
+int x265cu_d2h(x265cu_ctx* c, void* host, const void* dev, size_t bytes) { cudaSetDevice(c->device); CU_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream)); return 0; }
+int x265cu_memset(x265cu_ctx* c, void* dev, int value, size_t bytes) { cudaSetDevice(c->device); CU_CHECK(cudaMemsetAsync(dev, value, bytes, c->stream)); return 0; }
+int x265cu_timer_begin(x265cu_ctx* c) { cudaSetDevice(c->device); CU_CHECK(cudaEventRecord(c->ev0, c->stream)); return 0; }
 float x265cu_timer_end(x265cu_ctx* c)
 {
+    cudaSetDevice(c->device);
     float ms = -1.f;
     if (cudaEventRecord(c->ev1, c->stream) != cudaSuccess) return -1.f;
     if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.f;
@@ -98,6 +110,7 @@ float x265cu_timer_end(x265cu_ctx* c)
 uint64_t x265cu_launch_count(x265cu_ctx* c) { return c->launches; }
 int x265cu_me_phase_ms(x265cu_ctx* c, float* ms)
 {
+    cudaSetDevice(c->device);
     CU_CHECK(cudaEventSynchronize(c->me_ev[3]));
     for (int i = 0; i < 3; i++) CU_CHECK(cudaEventElapsedTime(&ms[i], c->me_ev[i], c->me_ev[i + 1]));
     return 0;
@@ -105,23 +118,24 @@ int x265cu_me_phase_ms(x265cu_ctx* c, float* ms)
 
 // ---------------- batched API ----------------
 int x265cu_pixelcmp_batch(x265cu_ctx* c, int depth, int op, const void* A, const void* B, const x265cu_cmp_job* jobs, int n, uint64_t* out)
-{ return launch_pixelcmp(c, depth, op, A, B, jobs, n, out); }
+{ cudaSetDevice(c->device); return launch_pixelcmp(c, depth, op, A, B, jobs, n, out); }
 int x265cu_pixelcmp_grid(x265cu_ctx* c, int depth, int op, const void* A, int64_t a_stride, const void* B, int64_t b_stride,
                          int bw, int bh, int nbx, int nby, uint64_t* out)
-{ return launch_pixelcmp_grid(c, depth, op, A, a_stride, B, b_stride, bw, bh, nbx, nby, out); }
+{ cudaSetDevice(c->device); return launch_pixelcmp_grid(c, depth, op, A, a_stride, B, b_stride, bw, bh, nbx, nby, out); }
 
 int x265cu_blockop_batch(x265cu_ctx* c, int depth, int op, void* D, const void* A, const void* B, const x265cu_blk_job* jobs, int n)
-{ return launch_blockop(c, depth, op, D, A, B, jobs, n); }
+{ cudaSetDevice(c->device); return launch_blockop(c, depth, op, D, A, B, jobs, n); }
 
 int x265cu_interp_batch(x265cu_ctx* c, int depth, int op, const void* src, void* dst, const x265cu_interp_job* jobs, int n)
-{ return launch_interp(c, depth, op, src, dst, jobs, n); }
+{ cudaSetDevice(c->device); return launch_interp(c, depth, op, src, dst, jobs, n); }
 
 int x265cu_transform_batch(x265cu_ctx* c, int depth, int op, int size, const int16_t* src, int16_t* dst, int stride, int64_t tu_pitch, int n)
-{ return launch_transform(c, depth, op, size, src, dst, stride, tu_pitch, n); }
+{ cudaSetDevice(c->device); return launch_transform(c, depth, op, size, src, dst, stride, tu_pitch, n); }
 
 int x265cu_quant_batch(x265cu_ctx* c, const int16_t* coef, const int32_t* qc, int32_t* deltaU, int16_t* qCoef, int qBits, int add,
                        int numCoeff, int n, int nquant, uint32_t* numSig)
 {
+    cudaSetDevice(c->device);
     if (n <= 0) return 0;
     int blocks = (n + 7) / 8; if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
     k_quant<<<blocks, 256, 0, c->stream>>>(coef, qc, deltaU, qCoef, qBits, add, numCoeff, n, nquant, numSig);
@@ -131,6 +145,7 @@ int x265cu_quant_batch(x265cu_ctx* c, const int16_t* coef, const int32_t* qc, in
 
 int x265cu_dequant_normal_batch(x265cu_ctx* c, const int16_t* q, int16_t* coef, int64_t num, int scale, int shift)
 {
+    cudaSetDevice(c->device);
     if (num <= 0) return 0;
     int64_t blocks = (num + 255) / 256; if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
     k_dequant_normal<<<(int)blocks, 256, 0, c->stream>>>(q, coef, num, scale, shift);
@@ -140,6 +155,7 @@ int x265cu_dequant_normal_batch(x265cu_ctx* c, const int16_t* q, int16_t* coef, 
 
 int x265cu_dequant_scaling_batch(x265cu_ctx* c, const int16_t* q, const int32_t* dq, int16_t* coef, int numCoeff, int n, int per, int shift)
 {
+    cudaSetDevice(c->device);
     int64_t total = (int64_t)numCoeff * n;
     if (total <= 0) return 0;
     int64_t blocks = (total + 255) / 256; if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
@@ -151,6 +167,7 @@ int x265cu_dequant_scaling_batch(x265cu_ctx* c, const int16_t* q, const int32_t*
 int x265cu_intra_pred_batch(x265cu_ctx* c, int depth, int size, const void* nb, int64_t nb_pitch, void* dst, int64_t dst_pitch, int dst_stride,
                             const x265cu_intra_job* jobs, int n)
 {
+    cudaSetDevice(c->device);
     if (n <= 0) return 0;
     int blocks = n < c->sm_count * 8 ? n : c->sm_count * 8;
     int threads = size * size < 256 ? (size * size < 32 ? 32 : size * size) : 256;
@@ -162,6 +179,7 @@ int x265cu_intra_pred_batch(x265cu_ctx* c, int depth, int size, const void* nb, 
 
 int x265cu_intra_filter_batch(x265cu_ctx* c, int depth, int size, const void* nb, void* filt, int64_t pitch, int n)
 {
+    cudaSetDevice(c->device);
     if (n <= 0) return 0;
     int blocks = n < c->sm_count * 8 ? n : c->sm_count * 8;
     if (depth == 8) k_intra_filter<uint8_t><<<blocks, 160, 0, c->stream>>>(size, (const uint8_t*)nb, (uint8_t*)filt, pitch, n);
@@ -172,6 +190,7 @@ int x265cu_intra_filter_batch(x265cu_ctx* c, int depth, int size, const void* nb
 
 int x265cu_intra_allangs_batch(x265cu_ctx* c, int depth, int size, const void* ref, const void* filt, int64_t nb_pitch, void* dst, int bLuma, int n)
 {
+    cudaSetDevice(c->device);
     if (n <= 0) return 0;
     if ((((uintptr_t)dst) & 7) == 0 && size >= 4 && size <= 32)
     {   // vector-store kernel: one CTA per block, all 33 modes
@@ -191,6 +210,7 @@ int x265cu_intra_allangs_batch(x265cu_ctx* c, int depth, int size, const void* r
 
 int x265cu_extend_border(x265cu_ctx* c, int depth, void* plane, int stride, int width, int height, int mx, int my)
 {
+    cudaSetDevice(c->device);
     if (depth == 8) return extend_border_t<uint8_t>(c, (uint8_t*)plane, stride, width, height, mx, my);
     return extend_border_t<uint16_t>(c, (uint16_t*)plane, stride, width, height, mx, my);
 }
@@ -198,6 +218,7 @@ int x265cu_extend_border(x265cu_ctx* c, int depth, void* plane, int stride, int 
 int x265cu_frame_init_lowres(x265cu_ctx* c, int depth, const void* src, int sstride, void* d0, void* dh, void* dv, void* dc,
                              int dstride, int width, int height, int mx, int my)
 {
+    cudaSetDevice(c->device);
     dim3 block(64, 4), grid((width / 4 + 63) / 64 + 1, (height + 3) / 4);
     const uintptr_t dal = (uintptr_t)d0 | (uintptr_t)dh | (uintptr_t)dv | (uintptr_t)dc | (uintptr_t)dstride;
     if (depth == 8 && (width & 7) == 0 && (((uintptr_t)src | (uintptr_t)sstride) & 15) == 0 && (dal & 7) == 0)
@@ -235,6 +256,7 @@ void x265cu_mvcost_table(double lambda, int range, uint16_t* out)
 int x265cu_me_batch(x265cu_ctx* c, int depth, const void* fenc, int fencStride, const void* const* refs, int refStride, int lowres,
                     const uint16_t* mvcost, int mvcost_range, const x265cu_me_job* jobs, int n, int32_t* out)
 {
+    cudaSetDevice(c->device);
     (void)mvcost_range;
     return launch_me(c, depth, fenc, fencStride, refs, refStride, lowres, mvcost, jobs, n, out, c->d_counter);
 }
@@ -242,6 +264,7 @@ int x265cu_me_batch(x265cu_ctx* c, int depth, const void* fenc, int fencStride, 
 int x265cu_me_batch_chroma(x265cu_ctx* c, int depth, const void* fenc, int fencStride, const void* const* refs, int refStride,
                            const x265cu_me_chroma* chroma, const uint16_t* mvcost, int mvcost_range, const x265cu_me_job* jobs, int n, int32_t* out)
 {
+    cudaSetDevice(c->device);
     (void)mvcost_range;
     if (!chroma || !chroma->fencCb_dev || !chroma->fencCr_dev || !chroma->refCb_dev || !chroma->refCr_dev || chroma->cstride <= 0)
     {
@@ -262,6 +285,7 @@ __global__ void k_la_intra_zero(const x265cu_la_intra_job* jobs, int h8)
 
 int x265cu_lowres_intra_batch(x265cu_ctx* c, int depth, const x265cu_la_intra_job* jobs, int n, int stride, int w8, int h8, int lambda)
 {
+    cudaSetDevice(c->device);
     if (n <= 0) return 0;
     k_la_intra_zero<<<n, 128, 0, c->stream>>>(jobs, h8);
     CU_LAUNCH_CHECK(c);
@@ -275,6 +299,7 @@ int x265cu_lowres_intra_batch(x265cu_ctx* c, int depth, const x265cu_la_intra_jo
 
 int x265cu_lookahead_cost_batch(x265cu_ctx* c, int depth, const x265cu_la_job* jobs, int n, int stride, int w8, int h8, const uint16_t* mvcost)
 {
+    cudaSetDevice(c->device);
     if (n <= 0) return 0;
     const size_t smem = sizeof(MeShared) * LA_WARPS;
     // cluster size: enough CTAs (of LA_WARPS warps) for the longest anti-diagonal in one round, at most 4
