@@ -1,24 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- 2160p preset-slow CTU-analysis throughput (CTUs/s) of the B200 block-primitive path.
+"""bench.py -- CTU-analysis throughput (CTUs/s) of the B200 block-primitive path on the BASELINE.json configs.
 
-A step = one pass of the hot path over one 3840x2160 8-bit frame per GPU (BASELINE.json configs[2]):
-all PUs (2Nx2N/2NxN/Nx2N at 64..8) x 4 references through motionEstimate (STAR, merange 57, subme 3),
-then per CU fused MC -> residual -> DCT -> quant -> dequant -> IDCT -> recon -> SSE, then the 35-mode
-intra SA8D search (DESIGN.md "Frame analysis workload").  2040 CTUs per frame.
+  --config c3 (default) : 3840x2160  8-bit preset slow    : 4 refs, STAR, merange 57, subme 3, rect, chroma-SATD on (4:2:0)
+  --config c4           : 3840x2160 10-bit preset slower  : 5 refs, subme 4, rect + AMP, chroma-SATD on
+  --config c5           : 7680x4320 10-bit preset veryslow: 5 refs, subme 4, rect + AMP, chroma-SATD on
+  --config c2           : 1920x1080  8-bit preset medium lookahead: Lowres init + intra + estimateFrameCost over a 20-frame
+                          window (bframes 4); metric = lowres CUs/s; N>1 shards the lookahead FRAMES (owner(b) = b % N)
 
-  value : whole-job CTUs/s with inputs resident in HBM (kernels only, CUDA events, L2 flushed between steps)
-  e2e   : same metric through the public call x265_b200.Analyser.analyse() with pinned HOST buffers,
-          H2D of the frame + predictor field and D2H of all results inside the timed region
-  --impl reference : the same workload on the reference's own C code (oracle/_ref: MotionEstimate class +
-          C primitive table compiled from /root/reference) on all host cores, bounded sample per step.
+A step (c3/c4/c5) = one pass of the hot path over one frame per GPU: every PU of every CTU x every reference through
+motionEstimate (STAR + sub-pel, chroma-SATD term as MotionEstimate::bChromaSATD runs it, motion.cpp:204-212), then per CU
+the fused MC -> residual -> DCT -> quant -> dequant -> IDCT -> recon -> SSE chain, then the 35-mode intra SA8D search.
 
-Multi-GPU (torchrun, one process per GPU): the frames of a mini-GOP share one reference set, so each rank
-analyses its own frame (weak scaling) and the only exchange is an NCCL broadcast of the newest
-reconstructed reference plane from its owner rank, once per step.
+  value : whole-job units/s with inputs resident in HBM (kernels only, CUDA events, L2 flushed between steps)
+  e2e   : same metric through the public call (x265_b200.Analyser.analyse / Lookahead) with pinned HOST buffers,
+          H2D of the inputs and D2H of the results inside the timed region
+  checks: order-sensitive checksums of the results; the CPU legs compute the same fields on the same geometry
+          (full frame, or its first k CTU rows) and the GPU arm ASSERTS equality on that scope (exit code 3 otherwise)
+  --impl reference : the same workload on the reference's own C code (oracle/_ref: MotionEstimate class + C primitive
+          table compiled from /root/reference) on all host cores.
 
-  --shard rows : the other partition of SURVEY 8(e) (BASELINE configs[4]): ONE frame per step, its CTU rows dealt
-          to the ranks (x265cu_analyser_run_rows), every owner broadcasting its reconstructed rows afterwards
-          (strong scaling; value = CTUs of the frame / max-over-ranks time).  Not the default line.
+Multi-GPU (torchrun, one process per GPU):
+  --shard frames (default): each rank analyses its own frame (weak scaling); the one exchange is the NCCL broadcast of the
+          newest reconstructed reference plane from its owner, issued on a side stream and overlapped with the step.
+  --shard rows : ONE frame per step, its CTU rows dealt to the ranks (strong scaling, BASELINE configs[4]), every owner
+          broadcasting its reconstructed rows afterwards.
 """
 import argparse
 import ctypes as C
@@ -35,9 +40,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-W, H, DEPTH, NREFS, QP = 3840, 2160, 8, 4, 30
-METHOD, SUBME, MERANGE, RECT = 3, 3, 57, 1          # preset slow: STAR / subme 3 / merange 57 / rect (param.cpp:478-492)
-CTUS_PER_FRAME = ((W + 63) // 64) * ((H + 63) // 64)
+# preset table: common/param.cpp:478-534 (slow / slower / veryslow), search.cpp:2059-2060 (bChromaSATD for 4:2:0)
+CONFIGS = {
+    "c3": dict(W=3840, H=2160, depth=8, refs=4, method=3, subme=3, merange=57, rect=1, amp=0, chroma=True, qp=30,
+               label="3840x2160 8-bit preset slow: full ME + sub-pel interp (chroma-SATD on) + DCT/quant + intra primitives on device (BASELINE configs[2])"),
+    "c4": dict(W=3840, H=2160, depth=10, refs=5, method=3, subme=4, merange=57, rect=1, amp=1, chroma=True, qp=30,
+               label="3840x2160 10-bit Main10 preset slower: 5 refs, subme 4, rect + AMP PUs, chroma-SATD on (BASELINE configs[3] analysis part)"),
+    "c5": dict(W=7680, H=4320, depth=10, refs=5, method=3, subme=4, merange=57, rect=1, amp=1, chroma=True, qp=30,
+               label="7680x4320 10-bit preset veryslow: 5 refs, subme 4, rect + AMP PUs, chroma-SATD on (BASELINE configs[4])"),
+    "c2": dict(W=1920, H=1080, depth=8, frames=20, bframes=4, lookahead=True,
+               label="1920x1080 8-bit preset medium lookahead: Lowres init + lowresIntraEstimate + estimateFrameCost (HEX, subme 1 lowres) on device (BASELINE configs[1])"),
+}
+CFG = None          # the selected config dict (set in main)
+CFG_NAME = "c3"
+
+
+def ctus_per_frame():
+    return ((CFG["W"] + 63) // 64) * ((CFG["H"] + 63) // 64)
 
 
 def env_int(name, default):
@@ -96,8 +115,7 @@ class ClockSampler:
 
 
 def host_cores():
-    """Usable host cores: os.cpu_count() capped by the cgroup CPU quota (the GPU box exposes 128 logical CPUs
-    but grants a quota of 16)."""
+    """Usable host cores: os.cpu_count() capped by the cgroup CPU quota and the affinity mask."""
     n = os.cpu_count() or 1
     try:
         quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
@@ -112,6 +130,16 @@ def host_cores():
     return n
 
 
+def asm_status():
+    """The reference's AVX2/AVX-512 primitives are NASM sources (common/x86/*.asm); they can only be built where an
+    assembler exists.  Reported with every CPU number so that a ratio is never read as 'vs AVX-512'."""
+    for tool in ("nasm", "yasm"):
+        for d in os.environ.get("PATH", "").split(os.pathsep):
+            if d and os.path.exists(os.path.join(d, tool)):
+                return "%s present at %s but oracle/_ref is the C-primitive build (no asm objects were assembled)" % (tool, d)
+    return "unavailable (no nasm/yasm on this box): CPU arm = the reference's C primitives (--no-asm path)"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -123,63 +151,96 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------
-CHROMA = False      # --chroma: 4:2:0 planes resident, chroma-SATD term of subpelCompare on (both arms)
+def workload_config(shard="frames"):
+    """The config dict of BOTH arms (identical by construction)."""
+    c = CFG
+    if c.get("lookahead"):
+        return {"workload": c["label"], "config": CFG_NAME, "frames": c["frames"], "bframes": c["bframes"],
+                "lowres_cus_per_frame": ((c["W"] // 2 + 7) // 8) * ((c["H"] // 2 + 7) // 8),
+                "estimates": "P costs at every anchor distance <= bframes+1 and the B costs between them (x265_b200.lookahead.window_triples)",
+                "unit_definition": "lowres CUs of estimateFrameCost per second (frame costs x CUs per frame); the GPU step ALSO does Lowres init + intra of all frames",
+                "l2": "256 MiB memset between timed steps (untimed)",
+                "shard": "lookahead frames: owner(b) = b % N runs every estimate of frame b; each frame's 4 lowres planes are broadcast once from its owner (N>1 only)"}
+    out = {"workload": c["label"], "config": CFG_NAME, "ctus_per_frame": ctus_per_frame(), "refs": c["refs"], "search": "star", "merange": c["merange"],
+           "subme": c["subme"], "rect": c["rect"], "amp": c["amp"], "chroma_satd": bool(c["chroma"]), "qp": c["qp"], "bit_depth": c["depth"],
+           "l2": "256 MiB memset between timed steps (untimed) + >300 MB per-step working set",
+           "frames": "rank k: frame refs+k against frames refs-1+k..k (frame-parallel: own nearest references per frame)"}
+    if shard == "rows":
+        out["frames_per_step"] = "1 per step, CTU rows sharded over the GPUs (contiguous row blocks)"
+        out["exchange"] = "NCCL broadcast of every owner's reconstructed CTU rows (one luma plane in total) per step (N>1 only)"
+    else:
+        out["frames_per_step"] = "1 per GPU"
+        out["exchange"] = "NCCL broadcast of one reference luma plane per step on a side stream, overlapped with the analysis (N>1 only)"
+    return out
 
 
-def cpu_reference(sample_rows, threads, kind_pref="reference", steps=1, warmup=0):
-    """The same workload on host cores: reference-from-source driver (oracle/_ref) or the oracle port."""
+def checks_of(cost, mvx, mvy, numsig, sse, intra, nj, nc):
+    """Order-sensitive checksums over the first nj PU jobs / nc CUs (both arms compute exactly these)."""
+    cost = np.asarray(cost[:nj]).astype(np.int64)
+    mvx = (np.asarray(mvx[:nj]).astype(np.int64) & 0xffff).astype(np.uint64)
+    mvy = (np.asarray(mvy[:nj]).astype(np.int64) & 0xffff).astype(np.uint64)
+    idx = np.arange(nj, dtype=np.uint64)
+    mv_hash = int(((mvx * (idx % np.uint64(251) + np.uint64(1))) + (mvy * (idx % np.uint64(241) + np.uint64(1)))).sum(dtype=np.uint64) & np.uint64((1 << 62) - 1))
+    intra = np.asarray(intra[:nc])
+    return {"jobs": int(nj), "cus": int(nc), "me_cost_sum": int(cost.sum()), "mv_hash": mv_hash,
+            "numsig_sum": int(np.asarray(numsig[:nc]).astype(np.int64).sum()), "sse_sum": int(np.asarray(sse[:nc]).astype(np.uint64).sum()),
+            "intra_cost_sum": int(intra[:, :35].astype(np.int64).sum()), "intra_mode_hist_hash": int((intra[:, 35].astype(np.int64) * (np.arange(nc) % 97 + 1)).sum())}
+
+
+def cpu_reference(max_rows, threads, kind_pref="reference", steps=1, warmup=0, wl=None):
+    """The same workload on host cores: reference-from-source driver (oracle/_ref) or the oracle port, over the first
+    `max_rows` CTU rows of the FULL-frame geometry (0 = the whole frame)."""
     from common import load_ref, load_oracle
     from frame_helpers import Workload, cpu_analyse, lambda_for
     from me_helpers import mvcost_table
-    O = load_oracle(DEPTH)
-    R = load_ref(DEPTH) if kind_pref == "reference" else None
+    c = CFG
+    O = load_oracle(c["depth"])
+    R = load_ref(c["depth"]) if kind_pref == "reference" else None
     lib, fn, kind = (R, "x265ref_analyse_frame", "reference") if R is not None else (O, "orc_analyse_frame", "port")
-    hs = min(H, 64 * sample_rows)
-    wl = Workload(W, hs, depth=DEPTH, numRefs=NREFS, method=METHOD, subme=SUBME, merange=MERANGE, rect=RECT, qp=QP, chroma=CHROMA)
-    tab = mvcost_table(O, lambda_for(QP, DEPTH))
-    ctus = ((W + 63) // 64) * ((hs + 63) // 64)
+    if wl is None:
+        wl = Workload(c["W"], c["H"], depth=c["depth"], numRefs=c["refs"], method=c["method"], subme=c["subme"], merange=c["merange"],
+                      rect=c["rect"], qp=c["qp"], chroma=c["chroma"], amp=c["amp"])
+    tab = mvcost_table(O, lambda_for(c["qp"], c["depth"]))
+    total_rows = (c["H"] + 63) // 64
+    rows = total_rows if max_rows <= 0 or max_rows >= total_rows else max_rows
+    ctus = ((c["W"] + 63) // 64) * rows
     for _ in range(warmup):
-        cpu_analyse(lib, fn, wl, tab, threads=threads)
+        cpu_analyse(lib, fn, wl, tab, threads=threads, max_ctu_rows=rows)
     t0 = time.perf_counter()
     for _ in range(steps):
-        res = cpu_analyse(lib, fn, wl, tab, threads=threads)
+        res = cpu_analyse(lib, fn, wl, tab, threads=threads, max_ctu_rows=rows)
     dt = time.perf_counter() - t0
-    return {"ctus_per_s": ctus * steps / dt, "seconds": dt, "ctus": ctus, "kind": kind, "threads": threads,
-            "sample": "top %d CTU rows (3840x%d crop) of the 2160p workload, %d refs, all PUs, %d step(s)" % (sample_rows, hs, NREFS, steps),
-            "checksum": int(res["me_out"][:, 0].astype(np.int64).sum())}
+    nj, nc = res["njobs_run"], res["ncu_run"]
+    chk = checks_of(res["me_out"][:, 0], res["me_out"][:, 1], res["me_out"][:, 2], res["cu_numsig"], res["cu_sse"], res["intra_cost"], nj, nc)
+    scope = "whole frame" if rows == total_rows else "CTU rows [0, %d) of %d (full-frame geometry)" % (rows, total_rows)
+    return {"ctus_per_s": ctus * steps / dt, "seconds": dt, "ctus": ctus, "kind": kind, "threads": threads, "rows": rows, "whole": rows == total_rows,
+            "sample": "%s of the %dx%d workload, %d refs, all PUs, %d step(s)" % (scope, c["W"], c["H"], c["refs"], steps),
+            "checks": chk, "scope": scope, "wl": wl}
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
+    if CFG.get("lookahead"):
+        return run_lookahead_reference(args)
     threads = host_cores()
-    rows = 1
-    # size the per-step sample so that the whole run stays within a few minutes
-    probe = cpu_reference(rows, threads, steps=1)
+    total_rows = (CFG["H"] + 63) // 64
+    # size the per-step sample so that the whole run stays within a few minutes; the probe step is the warm-up
+    probe = cpu_reference(1, threads, steps=1)
     per_row = probe["seconds"]
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    rows = int(max(1, min(34, budget / max(per_row, 1e-3))))
-    r = cpu_reference(rows, threads, steps=args.steps, warmup=args.warmup)
+    budget = 170.0 / max(1, args.steps)
+    rows = int(max(1, min(total_rows, budget / max(per_row, 1e-3))))
+    r = cpu_reference(rows, threads, steps=args.steps, warmup=0, wl=probe["wl"])
     line = {"impl": "reference", "metric": "2160p preset-slow CTU-analysis throughput", "value": r["ctus_per_s"], "unit": "CTUs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds"] / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(), "cpu_baseline": {"value": r["ctus_per_s"], "unit": "CTUs/s", "cores": threads, "kind": r["kind"], "sample": r["sample"]},
+            "higher_is_better": True, "scaling": "strong" if args.shard == "rows" else "weak", "vs_baseline": None,
+            "dtype": "u8" if CFG["depth"] == 8 else "u16", "data": "synthetic",
+            "config": workload_config(args.shard),
+            "cpu_baseline": {"value": r["ctus_per_s"], "unit": "CTUs/s", "cores": threads, "kind": r["kind"], "sample": r["sample"], "asm": asm_status(),
+                             "warmup_note": "one 1-row probe step is the warm-up (the CPU arm has no caches worth more)"},
             "e2e": {"value": r["ctus_per_s"], "unit": "CTUs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "checks": r["checks"], "checks_scope": r["scope"], "gpu_launches": 0}
     print(json.dumps(line), flush=True)
-
-
-def workload_config(rows=False):
-    if rows:
-        c = workload_config()
-        c["frames_per_step"] = "1 per step, CTU rows sharded over the GPUs (contiguous row blocks)"
-        c["exchange"] = "NCCL broadcast of every owner's reconstructed CTU rows (one luma plane in total) per step (N>1 only)"
-        return c
-    return {"workload": "3840x2160 8-bit preset slow: full ME + sub-pel interp + DCT/quant + intra primitives on device (BASELINE configs[2])",
-            "ctus_per_frame": CTUS_PER_FRAME, "refs": NREFS, "search": "star", "merange": MERANGE, "subme": SUBME, "rect": RECT, "qp": QP,
-            "pu_jobs_per_frame": None, "frames_per_step": "1 per GPU", "l2": "256 MiB memset between timed steps (untimed) + >300 MB per-step working set",
-            "exchange": "NCCL broadcast of one reference luma plane per step (N>1 only)",
-            "frames": "rank k: frame 4+k against frames 3+k..k (frame-parallel: own nearest references per frame)"}
 
 
 def plane_as_tensor(torch, ptr, nbytes, device):
@@ -190,11 +251,34 @@ def plane_as_tensor(torch, ptr, nbytes, device):
     return torch.as_tensor(w, device=device)
 
 
+def primitives_leg(lib, reps=3):
+    """Per-primitive half of the metric: achieved HBM GB/s of every primitive class at frame scale, 8- and 10-bit
+    (profiles/primitive_bench.py), with the ncu DRAM bytes of the committed capture of the same launches when present."""
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import primitive_bench
+    dram = {}
+    try:
+        for row in json.load(open(os.path.join(ROOT, "profiles", "primitives_r2_ncu.json")))["rows"]:
+            dram[(row["kernel"], row["depth"])] = row.get("dram_bytes")
+    except Exception:
+        pass
+    out = []
+    for depth in (8, 10):
+        for row in primitive_bench.run(lib, depth=depth, reps=reps, frames=6, quiet=True):
+            out.append({"kernel": row["kernel"], "depth": depth, "GBps": round(row["GBps"], 1), "frac": round(row["frac_of_measured_peak"], 4),
+                        "algorithmic_bytes": int(row["algorithmic_MB"] * 1e6), "dram_bytes": dram.get((row["kernel"], depth)), "note": row["note"]})
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import x265_b200
     from x265_b200 import shard
     from frame_helpers import gen_luma, gen_chroma, make_field, MARGIN_X, MARGIN_Y
+    c = CFG
+    W, H, DEPTH, NREFS, CHROMA = c["W"], c["H"], c["depth"], c["refs"], c["chroma"]
+    pdt = np.uint8 if DEPTH == 8 else np.uint16
+    es = 1 if DEPTH == 8 else 2
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -203,58 +287,88 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = x265_b200.load(local_rank)
-    an = x265_b200.Analyser(lib, W, H, depth=DEPTH, numRefs=NREFS, method=METHOD, subme=SUBME, merange=MERANGE, rect=RECT, qp=QP)
-    # synthetic clip (BASELINE.md generator).  Frame shards: rank k analyses frame 4 + k against ITS four nearest previous frames
-    # (3 + k .. k), as frame-parallel encoding does, so every rank has the same temporal distances and the same search problem.
-    # Row shards: one frame (4) and one reference set (3..0) for all ranks.
+    an = x265_b200.Analyser(lib, W, H, depth=DEPTH, numRefs=NREFS, method=c["method"], subme=c["subme"], merange=c["merange"], rect=c["rect"],
+                            qp=c["qp"], amp=c["amp"])
+    # synthetic clip (BASELINE.md generator).  Frame shards: rank k analyses frame NREFS + k against ITS nearest previous frames,
+    # as frame-parallel encoding does, so every rank has the same temporal distances and the same search problem.
+    # Row shards: one frame and one reference set for all ranks.
     rows_mode = args.shard == "rows"
     k_frame = 0 if rows_mode else shard.frame_of(0, rank, world)
     for r in range(NREFS):
-        an.set_ref(r, gen_luma(W, H, NREFS - 1 - r + k_frame))
-    cur = gen_luma(W, H, NREFS + k_frame)
+        an.set_ref(r, gen_luma(W, H, NREFS - 1 - r + k_frame, bits=DEPTH))
+    cur = gen_luma(W, H, NREFS + k_frame, bits=DEPTH)
     my_rows = shard.row_blocks(an.ctu_rows, rank, world, "block") if rows_mode else [(0, an.ctu_rows)]
     field = make_field(W, H, NREFS)
     # pinned host buffers: these are what the user hands to the public call
-    pin = lib.L.x265cu_host_alloc(W * H)
-    h_fenc = np.frombuffer((C.c_uint8 * (W * H)).from_address(pin), np.uint8).reshape(H, W)
+    pin = lib.L.x265cu_host_alloc(W * H * es)
+    h_fenc = np.frombuffer((C.c_uint8 * (W * H * es)).from_address(pin), pdt).reshape(H, W)
     h_fenc[:] = cur
     pinf = lib.L.x265cu_host_alloc(field.nbytes)
     h_field = np.frombuffer((C.c_uint8 * field.nbytes).from_address(pinf), np.int16).reshape(field.shape)
     h_field[:] = field
     h_cb = h_cr = None
     if CHROMA:
-        # the reference runs preset slow (subme 3) on a 4:2:0 source with MotionEstimate::bChromaSATD on (motion.cpp:204-212)
+        # the reference runs subme >= 3 on a 4:2:0 source with MotionEstimate::bChromaSATD on (motion.cpp:204-212)
         an.enable_chroma()
         for r in range(NREFS):
-            an.set_ref_chroma(r, gen_chroma(W, H, NREFS - 1 - r + k_frame, 1), gen_chroma(W, H, NREFS - 1 - r + k_frame, 2))
+            an.set_ref_chroma(r, gen_chroma(W, H, NREFS - 1 - r + k_frame, 1, bits=DEPTH), gen_chroma(W, H, NREFS - 1 - r + k_frame, 2, bits=DEPTH))
         cf = NREFS + k_frame
-        pc = [lib.L.x265cu_host_alloc(W * H // 4) for _ in range(2)]
-        h_cb, h_cr = [np.frombuffer((C.c_uint8 * (W * H // 4)).from_address(p), np.uint8).reshape(H // 2, W // 2) for p in pc]
-        h_cb[:] = gen_chroma(W, H, cf, 1); h_cr[:] = gen_chroma(W, H, cf, 2)
+        cbytes = W * H // 4 * es
+        pc = [lib.L.x265cu_host_alloc(cbytes) for _ in range(2)]
+        h_cb, h_cr = [np.frombuffer((C.c_uint8 * cbytes).from_address(p), pdt).reshape(H // 2, W // 2) for p in pc]
+        h_cb[:] = gen_chroma(W, H, cf, 1, bits=DEPTH); h_cr[:] = gen_chroma(W, H, cf, 2, bits=DEPTH)
         an.load_chroma(h_cb, h_cr)
     flush = lib.alloc(256 << 20)
     ref0 = incoming = None
+    side = None
     if world > 1:
         ptr, stride = an.recon_plane_ptr(1) if rows_mode else an.ref_plane_ptr(0)
-        base = ptr - (MARGIN_Y * stride + MARGIN_X)
-        ref0 = plane_as_tensor(torch, base, stride * (H + 2 * MARGIN_Y), dev)
+        base = ptr - (MARGIN_Y * stride + MARGIN_X) * es
+        nb = stride * (H + 2 * MARGIN_Y) * es
+        ref0 = plane_as_tensor(torch, base, nb, dev)
+        side = torch.cuda.Stream(device=dev)
         if not rows_mode:
             # incoming-reference plane: the owner's newest reference lands here on the other ranks (making it a reference is a
             # pointer swap the bench does not do, so that every step analyses the same frames)
-            inc = lib.alloc(stride * (H + 2 * MARGIN_Y))
-            incoming = plane_as_tensor(torch, inc.ptr, stride * (H + 2 * MARGIN_Y), dev)
+            inc = lib.alloc(nb)
+            incoming = plane_as_tensor(torch, inc.ptr, nb, dev)
+
+    # All step timing is on the device: CUDA events on the library's own stream (wrapped as a torch ExternalStream) bracket
+    # the kernels AND, through event waits, the exchange that runs on the side stream.
+    lib_stream = torch.cuda.ExternalStream(lib.L.x265cu_stream(lib.ctx), device=dev)
+    pending = []
 
     def exchange(step):
+        """Newest reconstructed reference plane from its owner (producer side of m_reconRowFlag, framefilter.cpp:664).  Issued
+        on a SIDE stream with no host synchronisation: it overlaps with this step's kernels (which read the current
+        references, not the incoming plane); the library stream waits for it at the END of the step (where the consumer
+        would swap the plane in)."""
         if world > 1 and not rows_mode:
-            shard.exchange_ref(dist, ref0, step, world, recv=incoming)     # newest reconstructed reference plane from its owner
-            torch.cuda.current_stream().synchronize()
+            e0 = torch.cuda.Event()
+            e0.record(lib_stream)
+            side.wait_event(e0)                            # the broadcast starts when the step starts
+            with torch.cuda.stream(side):
+                shard.exchange_ref(dist, ref0, step, world, recv=incoming)
+                e1 = torch.cuda.Event()
+                e1.record(side)
+            pending.append(e1)
 
     def exchange_rows():
-        # rows mode: every owner publishes the CTU rows it reconstructed (CU-size-32 recon plane)
+        # rows mode: every owner publishes the CTU rows it reconstructed (CU-size-32 recon plane) once its kernels are done
         if world > 1 and rows_mode:
-            lib.sync()
-            shard.exchange_rows(dist, ref0, an.ctu_rows, world, H, an.stride, MARGIN_Y)
-            torch.cuda.current_stream().synchronize()
+            e0 = torch.cuda.Event()
+            e0.record(lib_stream)
+            side.wait_event(e0)
+            with torch.cuda.stream(side):
+                shard.exchange_rows(dist, ref0, an.ctu_rows, world, H, an.stride, MARGIN_Y, es=es)
+                e1 = torch.cuda.Event()
+                e1.record(side)
+            pending.append(e1)
+
+    def exchange_join():
+        """The step ends when its exchange has landed too: the library stream waits for the side stream (device-side)."""
+        while pending:
+            lib_stream.wait_event(pending.pop())
 
     def analyse_e2e():
         if CHROMA:
@@ -276,6 +390,7 @@ def run_ours(args, rank, world, local_rank):
         exchange(s)
         analyse_e2e()
         exchange_rows()
+        exchange_join()
     an.load_inputs(h_fenc, h_field)
     lib.sync()
     sampler = ClockSampler(local_rank)
@@ -288,17 +403,15 @@ def run_ours(args, rank, world, local_rank):
     for s in range(args.steps):
         lib.check(lib.L.x265cu_memset(lib.ctx, flush.ptr, s & 255, flush.nbytes))
         lib.sync()
-        t_ex0 = time.perf_counter()
-        exchange(s)
-        t_ex = (time.perf_counter() - t_ex0) * 1000.0 if world > 1 else 0.0
-        lib.timer_begin()
+        t0e = torch.cuda.Event(enable_timing=True); t1e = torch.cuda.Event(enable_timing=True)
+        t0e.record(lib_stream)
+        exchange(s)                                        # side stream: overlaps with the kernels below
         run_resident()
-        t_k = lib.timer_end()
-        t_ex0 = time.perf_counter()
         exchange_rows()
-        if world > 1 and rows_mode:
-            t_ex += (time.perf_counter() - t_ex0) * 1000.0
-        res_ms.append(t_k + t_ex)
+        exchange_join()
+        t1e.record(lib_stream)
+        t1e.synchronize()
+        res_ms.append(t0e.elapsed_time(t1e))               # device time: kernels + (overlapped) exchange
         stage += np.array(an.stage_ms())
         phases += np.array(lib.me_phase_ms())
     barrier()
@@ -312,6 +425,8 @@ def run_ours(args, rank, world, local_rank):
         exchange(s)
         analyse_e2e()
         exchange_rows()
+        exchange_join()
+    lib.sync()
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) * 1000.0
     barrier()
@@ -322,16 +437,16 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_res, t_e2e = float(t[0]), float(t[1])
 
+    rc = 0
     if rank == 0:
         stage /= args.steps
         phases /= args.steps
-        units = CTUS_PER_FRAME * (1 if rows_mode else world) * args.steps
+        units = ctus_per_frame() * (1 if rows_mode else world) * args.steps
         value = units / (t_res / 1000.0)
         e2e = units / (t_e2e / 1000.0)
         peak, peak_src = peaks()
-        es = 1
         plane = W * H * es
-        # dominant kernel: k_me<P,2,-1>, the integer-search launch of the five motion-estimation launches.
+        # dominant kernel: the integer-search launch of the motion-estimation launches.
         # Algorithmic (compulsory) bytes per launch: source plane + each reference plane
         # read once + per job the 40 B job record and the 24 B phase state read and written.
         my_jobs = sum(an.row_range(r0, r1)[1] for r0, r1 in my_rows)
@@ -339,51 +454,262 @@ def run_ours(args, rank, world, local_rank):
         me_bytes = int(plane * (1 + NREFS) * my_share) + my_jobs * (40 + 24 + 24)
         me_ms = phases[1]
         achieved = me_bytes / (me_ms / 1000.0) / 1e9
-        # DRAM bytes of that kernel from the committed ncu capture of this same command (profiles/launches_r1.md)
         traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "me_r1_traffic.json")))
-            if "3840x2160" in tr.get("config", ""):
-                traffic = float(tr["traffic_bytes_per_launch"])
-        except Exception:
-            pass
-        cfg = workload_config(rows_mode)
-        cfg["pu_jobs_per_frame"] = an.njobs
-        cfg["chroma_satd"] = bool(CHROMA)
+        traffic_src = None
+        for name in ("me_r2_traffic.json", "me_r1_traffic.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if ("%dx%d" % (W, H)) in tr.get("config", "") and tr.get("bit_depth", 8) == DEPTH:
+                    traffic = float(tr["traffic_bytes_per_launch"]); traffic_src = "profiles/" + name
+                    break
+            except Exception:
+                pass
+        cfg = workload_config(args.shard)
         sizes = {"resid_bytes": plane * 2 + an.ncoef * 2 + 4 * plane, "intra_bytes": plane + an.ncu * 36 * 4}
         line = {
             "metric": "2160p preset-slow CTU-analysis throughput", "value": value, "unit": "CTUs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_res / args.steps, "higher_is_better": True,
-            "scaling": "strong" if rows_mode else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+            "scaling": "strong" if rows_mode else "weak", "vs_baseline": None, "dtype": "u8" if DEPTH == 8 else "u16", "data": "synthetic", "config": cfg,
+            "pu_jobs_per_frame": an.njobs,
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "CTUs/s", "ms_per_step": t_e2e / args.steps,
-                    "h2d_bytes_per_step": int(an.h2d_bytes(field)) + (W * H // 2 if CHROMA else 0), "d2h_bytes_per_step": int(sum(an.d2h_bytes_rows(r0, r1) for r0, r1 in my_rows))},
+                    "h2d_bytes_per_step": int(an.h2d_bytes(field)) + (W * H // 2 * es if CHROMA else 0), "d2h_bytes_per_step": int(sum(an.d2h_bytes_rows(r0, r1) for r0, r1 in my_rows))},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_me<P,2,-1> (integer search phase of the batched motionEstimate, one warp per PU x ref)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"kernel": "integer-search launch of the batched motionEstimate (k_me_window: TMA-staged shared-memory search window per CU group; k_me<P,2,-1> for the groups that do not fit)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(me_bytes), "kernel_ms": float(me_ms),
-                         "note": "not HBM bound: ~380 SAD candidates per job against 88 B of compulsory traffic, planes L2-resident; ncu: 94 % of l1tex throughput (unaligned candidate-row gathers), 56-59 % of issue slots busy, DRAM traffic = 1.09 x algorithmic bytes (traffic = bytes per launch from profiles/me_r1_traffic.json); see DESIGN.md section 5, profiles/launches_r1.md, profiles/me_r1_ncu.md"},
+                         "note": "not an HBM-bound kernel: ~380 SAD candidates per job against 88 B of compulsory traffic, planes L2-resident; the binding resource is the SM's shared-memory / ALU pipes (DESIGN.md section 5, profiles/)"},
             "stages_ms": {"me_stage": float(stage[0]), "me_prechecks": float(phases[0]), "me_integer_search": float(phases[1]), "me_subpel": float(phases[2]), "residual": float(stage[1]), "intra": float(stage[2])},
             "stage_rooflines": {
                 "k_cu_residual": {"achieved": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9, "unit": "GB/s", "frac": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9 / peak},
                 "k_intra_search": {"achieved": sizes["intra_bytes"] / (stage[2] / 1000.0) / 1e9, "unit": "GB/s", "frac": sizes["intra_bytes"] / (stage[2] / 1000.0) / 1e9 / peak}},
         }
-        # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ----
+        # ---- results of the last e2e step (host arrays) -> checks ----
+        mvp = an.me_packed[:, 1].view(np.uint32)
+        mvx = (mvp & 0xffff).astype(np.int64); mvy = (mvp >> 16).astype(np.int64)
+        full_scope = (not rows_mode) or world == 1
+        if full_scope:
+            line["checks"] = checks_of(an.me_packed[:, 0], mvx, mvy, an.cu_numsig, an.cu_sse, an.intra_cost, an.njobs, an.ncu)
+            line["checks_scope"] = "whole frame"
+        # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) + parity assertion on its scope ----
         if world == 1 and not args.no_cpu:
             threads = host_cores()
             probe = cpu_reference(1, threads)
-            rows = int(max(1, min(34, 15.0 / max(probe["seconds"], 1e-3))))
-            r = cpu_reference(rows, threads) if rows > 1 else probe
-            line["cpu_baseline"] = {"value": r["ctus_per_s"], "unit": "CTUs/s", "cores": threads, "kind": r["kind"], "sample": r["sample"]}
-        # size-independent sanity of the full-size run: every PU job produced a result inside its search window
-        mv = an.me_packed[:, 1].view(np.uint32)
-        line["checks"] = {"me_cost_sum": int(an.me_packed[:, 0].astype(np.int64).sum()), "numsig_sum": int(an.cu_numsig.astype(np.int64).sum()),
-                          "sse_sum": int(an.cu_sse.astype(np.uint64).sum()), "intra_best_hist_nonzero": int((an.intra_cost[:, 35] > 0).sum()),
-                          "mv_nonzero": int((mv != 0).sum())}
+            total_rows = (H + 63) // 64
+            rows = int(max(1, min(total_rows, args.cpu_seconds / max(probe["seconds"], 1e-3))))
+            r = cpu_reference(rows, threads, wl=probe["wl"]) if rows > 1 else probe
+            line["cpu_baseline"] = {"value": r["ctus_per_s"], "unit": "CTUs/s", "cores": threads, "kind": r["kind"], "sample": r["sample"], "asm": asm_status()}
+            cj, cc = r["checks"]["jobs"], r["checks"]["cus"]
+            mine = checks_of(an.me_packed[:, 0], mvx, mvy, an.cu_numsig, an.cu_sse, an.intra_cost, cj, cc)
+            line["checks_vs_cpu"] = {"scope": r["scope"], "gpu": mine, "cpu": r["checks"], "equal": mine == r["checks"]}
+            line["checks_equal"] = bool(mine == r["checks"])
+            if not line["checks_equal"]:
+                rc = 3
+        if world == 1 and args.primitives:
+            try:
+                line["primitives"] = primitives_leg(lib)
+            except Exception as e:          # the per-primitive table must never cost the headline line
+                line["primitives_error"] = repr(e)
         print(json.dumps(line), flush=True)
+        if rc:
+            print("bench.py: PARITY FAILURE: GPU checks differ from the CPU reference on %s" % line["checks_vs_cpu"]["scope"], file=sys.stderr)
     an.close()
     if world > 1:
         dist.destroy_process_group()
+    return rc
+
+
+# ----------------------------------------------------------------------------------------------
+# c2: the lookahead (BASELINE configs[1]); N>1 shards the frames (BASELINE configs[3]'s lookahead partition)
+def lookahead_frames():
+    from frame_helpers import gen_luma
+    c = CFG
+    return [gen_luma(c["W"], c["H"], i, bits=c["depth"]) for i in range(c["frames"])]
+
+
+def run_lookahead_ours(args, rank, world, local_rank):
+    import torch
+    import x265_b200
+    from x265_b200.lookahead import Lookahead, window_triples, conflict_free_batches, owner
+    c = CFG
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = x265_b200.load(local_rank)
+    frames = lookahead_frames()
+    n = len(frames)
+    la = Lookahead(lib, c["W"], c["H"], c["depth"], n)
+    triples = window_triples(n, c["bframes"])
+    mine = [t for t in triples if owner(t[2], world) == rank]
+    batches = conflict_free_batches(mine)
+    flush = lib.alloc(256 << 20)
+    blocks = [plane_as_tensor(torch, *la.plane_block(i), dev) for i in range(n)] if world > 1 else None
+
+    def publish():
+        # every frame's 4 lowres planes: produced on the owner, ONE broadcast per frame (the only data-path exchange)
+        if world > 1:
+            lib.sync()
+            works = [dist.broadcast(blocks[i], src=owner(i, world), async_op=True) for i in range(n)]
+            for w in works:
+                w.wait()
+            torch.cuda.current_stream().synchronize()
+            for i in range(n):
+                la.planes_received(i)
+
+    def step(e2e):
+        la.forget_results()
+        for f in la.fr:
+            f["has_intra"] = False
+        own = [i for i in range(n) if owner(i, world) == rank]
+        for i in own:
+            la.init_frame(i, frames[i])            # H2D of the full-res luma + Lowres::init
+        publish()
+        la.intra_batch(own)
+        preps = [la.prepare_batch(b) for b in batches]
+        for p in preps:
+            la.launch_batch(p)
+        lib.sync()
+        for p in preps:
+            la.collect_batch(p, full=e2e)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(True)
+    sampler = ClockSampler(local_rank)
+    launches0 = lib.launch_count()
+    barrier()
+    sampler.start()
+    # resident: planes + intra in place; time the estimate launches only (CUDA events)
+    t_res = 0.0
+    for s in range(args.steps):
+        la.forget_results()
+        preps = [la.prepare_batch(b) for b in batches]
+        lib.check(lib.L.x265cu_memset(lib.ctx, flush.ptr, s & 255, flush.nbytes))
+        lib.sync()
+        lib.timer_begin()
+        for p in preps:
+            la.launch_batch(p)
+        t_res += lib.timer_end()
+        for p in preps:
+            la.collect_batch(p, full=False)
+    barrier()
+    launches = lib.launch_count() - launches0
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step(True)
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) * 1000.0
+    barrier()
+    clocks = sampler.stop()
+    costs = {t: la.fr[t[2]]["res"][(t[2] - t[0], t[1] - t[2])]["score"] for t in mine}
+    csum = sum(v * (1 + (t[0] * 31 + t[1] * 17 + t[2]) % 13) for t, v in costs.items())
+    if world > 1:
+        t = torch.tensor([t_res, t_e2e, float(csum)], dtype=torch.float64, device=dev)
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        t_res, t_e2e, csum = float(tm[0]), float(tm[1]), int(ts[2])
+    rc = 0
+    if rank == 0:
+        units = len(triples) * la.ncu * args.steps
+        peak, peak_src = peaks()
+        plane_b = la.plane_bytes
+        algo = sum((5 if t[1] == t[2] else 9) * plane_b + la.ncu * 32 for t in mine)      # fenc + 4 (P) / 8 (B) hpel planes read once + 32 B per CU
+        achieved = algo / (t_res / args.steps / 1000.0) / 1e9
+        line = {"metric": "1080p lookahead estimateFrameCost throughput", "value": units / (t_res / 1000.0), "unit": "lowres CUs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_res / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u8" if c["depth"] == 8 else "u16", "data": "synthetic", "config": workload_config(), "clocks": clocks,
+                "e2e": {"value": units / (t_e2e / 1000.0), "unit": "lowres CUs/s", "ms_per_step": t_e2e / args.steps,
+                        "h2d_bytes_per_step": int(sum(frames[i].nbytes for i in range(n) if owner(i, world) == 0)),
+                        "d2h_bytes_per_step": int(len(mine) * (24 + 2 * la.ncu + 4 * la.h8))},
+                "gpu_launches": int(launches), "frame_costs": len(triples), "launches_per_step": len(batches),
+                "roofline": {"kernel": "k_lookahead_cost (cluster wavefront, one cluster per (p0,p1,b))", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo / max(1, len(batches))),
+                             "note": "latency bound: one dependent chain of ~250 CU searches per triple (anti-diagonal wavefront)"},
+                "checks": {"frame_cost_hash": int(csum), "triples": len(triples)}}
+        if world == 1 and not args.no_cpu:
+            r = lookahead_cpu(frames, triples, budget_s=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": r["cus_per_s"], "unit": "lowres CUs/s", "cores": r["procs"], "kind": r["kind"], "sample": r["sample"], "asm": asm_status()}
+            mine_h = sum(costs[t] * (1 + (t[0] * 31 + t[1] * 17 + t[2]) % 13) for t in r["triples"])
+            line["checks_vs_cpu"] = {"scope": r["sample"], "gpu": int(mine_h), "cpu": int(r["hash"]), "equal": int(mine_h) == int(r["hash"])}
+            line["checks_equal"] = line["checks_vs_cpu"]["equal"]
+            if not line["checks_equal"]:
+                rc = 3
+        print(json.dumps(line), flush=True)
+    la.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return rc
+
+
+def _la_worker(args):
+    """One host process of the CPU lookahead arm: its own reference Lookahead over the window, a subset of the triples."""
+    depth, W, H, nframes, bframes, triples, kind = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import load_ref, load_oracle
+    from frame_helpers import gen_luma
+    frames = [gen_luma(W, H, i, bits=depth) for i in range(nframes)]
+    if kind == "reference":
+        from test_lookahead_oracle_vs_ref import RefLookahead
+        h = RefLookahead(load_ref(depth), frames, bframes)
+    else:
+        from lookahead_helpers import OracleLookahead
+        h = OracleLookahead(load_oracle(depth), frames, depth)
+    t0 = time.perf_counter()
+    out = [(t, h.cost(*t)) for t in triples]
+    return out, time.perf_counter() - t0
+
+
+def lookahead_cpu(frames, triples, budget_s=20.0, steps=1):
+    """estimateFrameCost of (a bounded subset of) the window's triples with the REAL reference classes, one process per host
+    core (the reference's serial per-TLD path in each), triples dealt by frame b."""
+    from concurrent.futures import ProcessPoolExecutor
+    from common import load_ref
+    c = CFG
+    kind = "reference" if load_ref(c["depth"]) is not None else "port"
+    procs = max(1, min(host_cores(), c["frames"] - 1))
+    ncu = ((c["W"] // 2 + 7) // 8) * ((c["H"] // 2 + 7) // 8)
+    # ~0.7 M CUs/s per thread (profiles/lookahead_r1.txt): bound the sample
+    per_triple = ncu / 0.5e6
+    maxn = int(max(procs, min(len(triples), budget_s * procs / per_triple)))
+    sub = triples[:maxn]
+    parts = [[t for t in sub if t[2] % procs == k] for k in range(procs)]
+    parts = [p for p in parts if p]
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=len(parts)) as ex:
+        res = list(ex.map(_la_worker, [(c["depth"], c["W"], c["H"], c["frames"], c["bframes"], p, kind) for p in parts]))
+    wall = time.perf_counter() - t0
+    busy = max(r[1] for r in res)                     # the estimate loops run concurrently: the slowest worker is the step
+    costs = dict(kv for r in res for kv in r[0])
+    h = sum(v * (1 + (t[0] * 31 + t[1] * 17 + t[2]) % 13) for t, v in costs.items())
+    return {"cus_per_s": len(sub) * ncu / busy, "procs": len(parts), "kind": kind, "hash": h, "triples": sub, "seconds": busy, "wall": wall,
+            "sample": "%d of the %d frame-cost estimates of the window, %d processes (frame setup untimed)" % (len(sub), len(triples), len(parts))}
+
+
+def run_lookahead_reference(args):
+    from x265_b200.lookahead import window_triples
+    c = CFG
+    triples = window_triples(c["frames"], c["bframes"])
+    budget = 170.0 / max(1, args.steps)
+    t0 = time.perf_counter()
+    r = None
+    for _ in range(args.steps):
+        r = lookahead_cpu(None, triples, budget_s=budget * 0.5)
+    dt = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": "1080p lookahead estimateFrameCost throughput", "value": r["cus_per_s"], "unit": "lowres CUs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(),
+            "cpu_baseline": {"value": r["cus_per_s"], "unit": "lowres CUs/s", "cores": r["procs"], "kind": r["kind"], "sample": r["sample"], "asm": asm_status()},
+            "e2e": {"value": r["cus_per_s"], "unit": "lowres CUs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "checks": {"frame_cost_hash_of_sample": int(r["hash"]), "triples": len(r["triples"])}, "gpu_launches": 0, "wall_s": dt}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -396,20 +722,27 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json config (c2 lookahead, c3 slow [default], c4 slower Main10, c5 8K veryslow)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (and with it the parity assertion)")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="host time budget of the cpu_baseline sample")
     ap.add_argument("--shard", default="frames", choices=["frames", "rows"],
                     help="N>1 partition: a frame per GPU (default, weak scaling) or the CTU rows of one frame per GPU (strong scaling)")
-    ap.add_argument("--chroma", action="store_true",
-                    help="4:2:0 chroma planes resident and the chroma-SATD term of subpelCompare on (MotionEstimate::bChromaSATD), both arms")
+    ap.add_argument("--no-chroma", action="store_true", help="luma-only motion estimation (round-1 line; the presets run with the chroma-SATD term)")
+    ap.add_argument("--primitives", action="store_true", help="add the per-primitive HBM GB/s table (8- and 10-bit) to the line")
     args = ap.parse_args()
-    global CHROMA
-    CHROMA = args.chroma
+    global CFG, CFG_NAME
+    CFG_NAME = args.config
+    CFG = dict(CONFIGS[args.config])
+    if args.no_chroma and "chroma" in CFG:
+        CFG["chroma"] = False
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
-        return
-    run_ours(args, rank, world, local_rank)
+        return 0
+    if CFG.get("lookahead"):
+        return run_lookahead_ours(args, rank, world, local_rank)
+    return run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main() or 0)
