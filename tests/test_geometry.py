@@ -74,6 +74,44 @@ def test_geometry_matches_oracle(geo, size, rect, amp):
         assert (rows_of_pus == r).all()
 
 
+@pytest.mark.parametrize("size", [(200, 136), (352, 288), (1920, 1080), (3840, 2160)])
+@pytest.mark.parametrize("rect,amp", [(1, 0), (1, 1), (0, 0)])
+def test_window_groups_partition_the_jobs(geo, size, rect, amp):
+    """Job groups of the shared-memory-window integer search (me_window.cuh): every PU job is in exactly one group, a group's
+    jobs share the reference and lie inside one 64x64 / 32x32 CU (class 0) or one 16x16 cell (class 1), are ordered largest
+    first, and the per-CTU-row group ranges cover exactly the jobs of those rows (what a row shard launches)."""
+    W, H = size
+    nref = 2
+    g = build(geo, W, H, nref, rect, amp)
+    st = stride_for(W)
+    seen = np.zeros(g["njobs"], np.int32)
+    pus = g["pus"]
+    px, py = pus[:, 0] % st, pus[:, 0] // st
+    for k in range(2):
+        cnt = np.zeros(2, np.int32); geo.geo_get(10 + 4 * k, cnt.ctypes.data_as(C.c_void_p))
+        ng, nj = int(cnt[0]), int(cnt[1])
+        fc = np.zeros(2 * ng, np.int32); geo.geo_get(11 + 4 * k, fc.ctypes.data_as(C.c_void_p)); fc = fc.reshape(-1, 2)
+        jobs = np.zeros(nj, np.int32); geo.geo_get(12 + 4 * k, jobs.ctypes.data_as(C.c_void_p))
+        rowg = np.zeros(g["rows"] + 1, np.int32); geo.geo_get(13 + 4 * k, rowg.ctypes.data_as(C.c_void_p))
+        assert rowg[0] == 0 and rowg[-1] == ng and (np.diff(rowg) >= 0).all()
+        np.add.at(seen, jobs, 1)
+        assert fc[:, 1].max() <= 48 and fc[:, 1].min() >= 1          # MEW_MAX_GROUP
+        for gi in range(0, ng, max(1, ng // 400)):                    # a sample of groups in detail
+            f, c = fc[gi]
+            ids = jobs[f:f + c]
+            assert len(set(pus[ids, 5])) == 1
+            x0, y0 = px[ids].min(), py[ids].min()
+            x1, y1 = (px[ids] + pus[ids, 3]).max(), (py[ids] + pus[ids, 4]).max()
+            lim = 16 if k == 1 else 64
+            assert x1 - x0 <= lim and y1 - y0 <= lim and x0 // lim == (x1 - 1) // lim and y0 // lim == (y1 - 1) // lim
+            area = pus[ids, 3].astype(np.int64) * pus[ids, 4]
+            assert (np.diff(area) <= 0).all()
+        for r in range(g["rows"]):
+            ids = jobs[fc[rowg[r], 0]:(fc[rowg[r + 1] - 1, 0] + fc[rowg[r + 1] - 1, 1])] if rowg[r + 1] > rowg[r] else jobs[:0]
+            assert ((py[ids] // 64) == r).all()
+    assert (seen == 1).all()
+
+
 def test_geometry_8k_ranges(geo):
     """BASELINE configs[4] (7680x4320, 5 references, rect + AMP): counts by formula and every field inside its integer type."""
     W, H, nref = 7680, 4320, 5

@@ -131,3 +131,29 @@ def test_row_shards_equal_full_frame(cu, depth, mode, world):
     padded = np.pad(rec, ((MARGIN_Y, MARGIN_Y), (MARGIN_X, MARGIN_X)), mode="edge")
     assert np.array_equal(newref[:, :vw], padded)
     an.close()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("depth,amp,noise", [(8, 0, False), (8, 0, True), (10, 1, False), (10, 1, True), (8, 1, True)])
+def test_window_search_equals_global_search(cu, depth, amp, noise, monkeypatch):
+    """The shared-memory-window integer search (me_window.cuh: TMA-staged window per CU group, column-walk raster) against
+    the global-memory kernel (X265CU_ME_WINDOW=0) on the same frame: every motionEstimate result identical.  1024x576
+    leaves most search windows unclipped by the picture edge (the small frames above are clipped almost everywhere)."""
+    import x265_b200
+    qp = 30
+    W, H = 1024, 576
+    nrefs = 3
+    wl = Workload(W, H, depth=depth, numRefs=nrefs, method=3, subme=3, merange=57, rect=1, qp=qp, noise=noise, amp=amp)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("X265CU_ME_WINDOW", mode)
+        an = x265_b200.Analyser(cu, W, H, depth=depth, numRefs=nrefs, method=3, subme=3, merange=57, rect=1, qp=qp, lam=lambda_for(qp, depth), amp=amp)
+        for r, ref in enumerate(wl.refs):
+            an.set_ref(r, ref[MARGIN_Y:MARGIN_Y + H, MARGIN_X:MARGIN_X + W])
+        fenc = np.ascontiguousarray(wl.fenc[MARGIN_Y:MARGIN_Y + H, MARGIN_X:MARGIN_X + W])
+        an.analyse(fenc, wl.field, stages=1)
+        res[mode] = (an.fetch("me_out").reshape(-1, 4).copy(), an.fetch("jobs"))
+        an.close()
+    a, b = res["0"][0], res["1"][0]
+    bad = np.nonzero((a[:, :3] != b[:, :3]).any(axis=1))[0]
+    assert len(bad) == 0, (len(bad), len(a), res["0"][1][bad[:4]].tolist(), a[bad[:4]].tolist(), b[bad[:4]].tolist())

@@ -4,7 +4,9 @@
 #include "common.cuh"
 #include "frame.cuh"
 #include "me.cuh"
+#include "me_window.cuh"
 #include <vector>
+#include <stdlib.h>
 
 struct x265cu_analyser
 {
@@ -32,9 +34,20 @@ struct x265cu_analyser
     int chromaOn, cstride, cRows; size_t cPlaneBytes, cOrgBytes;
     uint8_t* d_fencC[2]; uint8_t* d_refC[16][2];
     void** d_refCbTable; void** d_refCrTable;
+    // shared-memory-window integer search (me_window.cuh): group tables (two classes), tensor maps of the reference
+    // planes [ref][MEW_NCLS], leftover list.  windowOn = 0 (X265CU_ME_WINDOW=0) keeps the global-memory kernel for all jobs.
+    int windowOn; MeGroup* d_groups[2]; int32_t* d_grpJobs[2]; std::vector<int> rowGrp[2];
+    CUtensorMap* d_tmaps; int32_t* d_left;
 };
 
 static const int AN_MARGIN_X = 96, AN_MARGIN_Y = 80;       // picyuv.cpp:87-88 with maxCUSize 64
+
+template <typename T> static T* an_upload(x265cu_ctx* c, const std::vector<T>& v)
+{
+    T* d = (T*)x265cu_malloc(c, v.size() * sizeof(T) + 16);
+    if (d && !v.empty()) cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+}
 
 static void an_build_geometry(x265cu_analyser* a)
 {
@@ -43,13 +56,14 @@ static void an_build_geometry(x265cu_analyser* a)
     a->pus.swap(g.pus); a->cus.swap(g.cus); a->tus.swap(g.tus); a->cu_jobs.swap(g.cu_jobs);
     a->ctuRows = g.ctuRows; a->rowJob.swap(g.rowJob); a->rowCu.swap(g.rowCu); a->rowTu.swap(g.rowTu);
     a->njobs = (int)a->pus.size(); a->ncu = (int)a->cus.size(); a->ntu = (int)a->tus.size(); a->ncoef = g.ncoef;
-}
-
-template <typename T> static T* an_upload(x265cu_ctx* c, const std::vector<T>& v)
-{
-    T* d = (T*)x265cu_malloc(c, v.size() * sizeof(T) + 16);
-    if (d && !v.empty()) cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-    return d;
+    for (int k = 0; k < 2; k++)
+    {
+        std::vector<MeGroup> grp(g.grpFirst[k].size());
+        for (size_t i = 0; i < grp.size(); i++) { grp[i].first = g.grpFirst[k][i]; grp[i].count = g.grpCount[k][i]; }
+        a->d_groups[k] = an_upload(a->ctx, grp);
+        a->d_grpJobs[k] = an_upload(a->ctx, g.grpJobs[k]);
+        a->rowGrp[k].swap(g.rowGrp[k]);
+    }
 }
 
 // Runs the stages over the CTU rows [r0, r1).  Every list is sliced by pointer offset only: PU jobs, ME results and
@@ -76,9 +90,20 @@ static int an_run(x265cu_analyser* a, int stages, int r0, int r1)
             ch.fencCb = a->d_fencC[0] + a->cOrgBytes; ch.fencCr = a->d_fencC[1] + a->cOrgBytes;
             ch.refCb = (const void* const*)a->d_refCbTable; ch.refCr = (const void* const*)a->d_refCrTable; ch.cstride = a->cstride;
         }
+        MeWinLaunch win;
+        if (a->windowOn)
+        {
+            win.tmaps = a->d_tmaps; win.allocX = AN_MARGIN_X; win.allocY = AN_MARGIN_Y;
+            for (int k = 0; k < 2; k++)
+            {
+                win.groups[k] = a->d_groups[k] + a->rowGrp[k][r0]; win.ngroups[k] = a->rowGrp[k][r1] - a->rowGrp[k][r0];
+                win.grp_jobs[k] = a->d_grpJobs[k];
+            }
+            win.job0 = job0; win.left_count = c->d_counter + 9; win.left_list = a->d_left;
+        }
         if (launch_me(c, depth, a->d_fenc + a->orgBytes, a->stride, (const void* const*)a->d_refTable, a->stride, 0,
                       a->d_mvcost + a->mvrange, a->d_jobs + job0, nj, a->d_me_out + (size_t)job0 * 4, c->d_counter,
-                      a->chromaOn ? &ch : NULL)) return -1;
+                      a->chromaOn ? &ch : NULL, a->windowOn ? &win : NULL)) return -1;
         CU_CHECK(cudaEventRecord(a->ev[4], c->stream));      // ME search kernel alone ends here
         k_pack_me<<<(nj + 255) / 256, 256, 0, c->stream>>>(a->d_me_out + (size_t)job0 * 4, nj, a->d_me_packed + job0);
         CU_LAUNCH_CHECK(c);
@@ -157,6 +182,27 @@ x265cu_analyser* x265cu_analyser_create(x265cu_ctx* ctx, const x265cu_analysis_p
     a->d_jobs = (x265cu_me_job*)x265cu_malloc(ctx, sizeof(x265cu_me_job) * a->njobs);
     a->d_me_out = (int32_t*)x265cu_malloc(ctx, sizeof(int32_t) * 4 * a->njobs);
     a->d_me_packed = (int2*)x265cu_malloc(ctx, sizeof(int2) * a->njobs);
+    // shared-memory-window search: tensor maps over the reference plane allocations (STAR only; the other methods and any
+    // group whose window does not fit go through the global-memory kernel)
+    {
+        const char* e = getenv("X265CU_ME_WINDOW");
+        a->windowOn = !(e && e[0] == '0') && p->method == 3;
+        a->d_tmaps = NULL;
+        a->d_left = (int32_t*)x265cu_malloc(ctx, sizeof(int32_t) * (a->njobs + 1));
+        if (a->windowOn)
+        {
+            std::vector<CUtensorMap> tm((size_t)p->numRefs * MEW_NCLS);
+            bool ok = a->d_left != NULL;
+            for (int r = 0; r < p->numRefs && ok; r++)
+                ok = a->d_refs[r] && mew_build_tmaps(a->d_refs[r], a->stride, a->planeRows, (int)es, &tm[(size_t)r * MEW_NCLS]) == 0;
+            if (ok)
+            {
+                a->d_tmaps = (CUtensorMap*)x265cu_malloc(ctx, sizeof(CUtensorMap) * tm.size());
+                ok = a->d_tmaps && cudaMemcpy(a->d_tmaps, tm.data(), sizeof(CUtensorMap) * tm.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+            }
+            if (!ok) { fprintf(stderr, "x265cu: tensor maps unavailable, integer search stays on the global-memory kernel: %s\n", x265cu_last_error()); a->windowOn = 0; }
+        }
+    }
     a->d_coef = (int16_t*)x265cu_malloc(ctx, sizeof(int16_t) * a->ncoef);
     a->d_cu_sse = (unsigned long long*)x265cu_malloc(ctx, sizeof(unsigned long long) * a->ncu);
     a->d_cu_numsig = (uint32_t*)x265cu_malloc(ctx, sizeof(uint32_t) * a->ncu);
@@ -181,7 +227,8 @@ void x265cu_analyser_destroy(x265cu_analyser* a)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void* bufs[] = { a->d_fenc, a->d_refTable, a->d_reconTable, a->d_field, a->d_mvcost, a->d_pus, a->d_cus, a->d_tus, a->d_cu_jobs, a->d_jobs,
-                     a->d_me_out, a->d_me_packed, a->d_coef, a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref, a->d_intra };
+                     a->d_me_out, a->d_me_packed, a->d_coef, a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref, a->d_intra,
+                     a->d_groups[0], a->d_groups[1], a->d_grpJobs[0], a->d_grpJobs[1], a->d_tmaps, a->d_left };
     for (void* b : bufs) cudaFree(b);
     for (int r = 0; r < a->p.numRefs; r++) cudaFree(a->d_refs[r]);
     for (int d = 0; d < 4; d++) cudaFree(a->d_recon[d]);

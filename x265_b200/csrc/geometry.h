@@ -20,6 +20,11 @@ struct FrameGeometry
     // range [r0, r1) is one contiguous slice of each list (what a WPP row shard owns, frameencoder.cpp:850-868)
     int ctuRows; std::vector<int> rowJob, rowCu, rowTu;
     int64_t ncoef;
+    // job groups of the shared-memory-window integer search (me_window.cuh): per (CTU, ref) the 64x64 CU's PUs, each 32x32
+    // CU's PUs, and per 16x16 cell the PUs of the 16x16 CU and of its four 8x8 CUs.  grpJobs holds absolute job indices,
+    // largest PU first inside a group; groups are in CTU raster order (rowGrp = first group of every CTU row + end).
+    // Two classes, launched separately (different shared-memory budgets): [0] = CU 64 / CU 32 groups, [1] = 16x16 cells.
+    std::vector<int32_t> grpFirst[2], grpCount[2], grpJobs[2]; std::vector<int> rowGrp[2];
 };
 
 // partitions of a CU of `size`: returns the count and fills part[k] = {x, y, w, h} relative to the CU origin
@@ -54,6 +59,7 @@ static inline void geometry_build(int W, int H, int stride, int nref, int rect, 
     for (int cty = 0; cty < ctuH; cty++)
     {
         g.rowJob.push_back((int)g.pus.size()); g.rowCu.push_back((int)g.cus.size()); g.rowTu.push_back((int)g.tus.size());
+        for (int k = 0; k < 2; k++) g.rowGrp[k].push_back((int)g.grpFirst[k].size());
         for (int ctx = 0; ctx < ctuW; ctx++)
         {
             int local[85]; int nl = 0;
@@ -81,6 +87,8 @@ static inline void geometry_build(int W, int H, int stride, int nref, int rect, 
             for (int r = 0; r < nref; r++)
             {
                 int li = 0;
+                int jobStart[85], jobCount[85];
+                for (int q = 0; q < 85; q++) { jobStart[q] = 0; jobCount[q] = 0; }
                 for (int size = 64; size >= 8; size >>= 1)
                     for (int cy = 0; cy < 64; cy += size)
                         for (int cx = 0; cx < 64; cx += size, li++)
@@ -88,6 +96,7 @@ static inline void geometry_build(int W, int H, int stride, int nref, int rect, 
                             if (local[li] < 0) continue;          // CU crosses the picture edge: no partition of it is evaluated
                             int part[13][4];
                             const int np = geometry_cu_parts(size, rect, amp, part);
+                            jobStart[li] = (int)g.pus.size(); jobCount[li] = np;
                             for (int k = 0; k < np; k++)
                             {
                                 const int x = ctx * 64 + cx + part[k][0], y = cty * 64 + cy + part[k][1], w = part[k][2], h = part[k][3];
@@ -97,9 +106,39 @@ static inline void geometry_build(int W, int H, int stride, int nref, int rect, 
                                 g.pus.push_back(d);
                             }
                         }
+                // groups of this (CTU, ref): CU 64, CUs 32, then the 16x16 cells (CU 16 + its four CUs 8)
+                for (int gi = 0; gi < 21; gi++)
+                {
+                    int members[5], nm = 0;
+                    members[nm++] = gi;
+                    if (gi >= 5)
+                    {
+                        const int k = gi - 5, cy16 = k >> 2, cx16 = k & 3;
+                        for (int a8 = 0; a8 < 2; a8++)
+                            for (int b8 = 0; b8 < 2; b8++) members[nm++] = 21 + (2 * cy16 + a8) * 8 + (2 * cx16 + b8);
+                    }
+                    const int cl = gi < 5 ? 0 : 1;
+                    std::vector<int32_t>& gj = g.grpJobs[cl];
+                    const int first = (int)gj.size();
+                    for (int m = 0; m < nm; m++)
+                        for (int q = 0; q < jobCount[members[m]]; q++) gj.push_back(jobStart[members[m]] + q);
+                    const int count = (int)gj.size() - first;
+                    if (!count) continue;
+                    // largest PU first (stable insertion sort: groups hold at most 33 jobs)
+                    for (int a = first + 1; a < first + count; a++)
+                    {
+                        const int32_t v = gj[a];
+                        const int av = g.pus[v].pw * g.pus[v].ph;
+                        int b = a - 1;
+                        while (b >= first && g.pus[gj[b]].pw * g.pus[gj[b]].ph < av) { gj[b + 1] = gj[b]; b--; }
+                        gj[b + 1] = v;
+                    }
+                    g.grpFirst[cl].push_back(first); g.grpCount[cl].push_back(count);
+                }
             }
         }
     }
+    for (int k = 0; k < 2; k++) g.rowGrp[k].push_back((int)g.grpFirst[k].size());
     g.rowJob.push_back((int)g.pus.size()); g.rowCu.push_back((int)g.cus.size()); g.rowTu.push_back((int)g.tus.size());
     g.ncoef = coefOff;
 }

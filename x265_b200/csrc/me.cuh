@@ -793,6 +793,11 @@ __device__ __forceinline__ int me_cost_fpel(const MeCtx<P>& c, int x, int y)
 
 struct MeStar { int bx, by, bcost, point, dist; };
 
+// shared-memory search window context (me_window.cuh): its evaluation sites are overloads of the same names
+template <typename P> struct MeWin;
+template <typename P> __device__ __forceinline__ int me_eval_points(const MeWin<P>& c, int n, int px, int py, bool x8);
+template <typename P> __device__ __forceinline__ void me_raster(const MeWin<P>& c, MeStar& s);
+
 // Fold a burst in the reference's order.  The sequential `if (cost < bcost)` chain keeps the EARLIEST
 // candidate among those reaching the minimum, so it equals one arg-min with ties to the lowest index:
 // pack (cost << 5 | index) and take a single warp min (REDUX.MIN).  Costs stay below 2^26.
@@ -818,8 +823,8 @@ __device__ __forceinline__ void me_fold(MeStar& s, int n, int cost, int px, int 
 // StarPatternSearch (motion.cpp:362-604).  Each distance level is one burst; candidate order inside
 // a level is the reference's (its x4 fast path and its bounds-checked path visit the same points in
 // the same order), out-of-range candidates are dropped before evaluation.
-template <typename P>
-__device__ __forceinline__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, int earlyExitIters, int merange)
+template <typename CTX>
+__device__ __forceinline__ void me_star_pattern(const CTX& c, MeStar& s, int earlyExitIters, int merange)
 {
     // Levels: 0 = distance 1 (4 points), 1..3 = distances 2, 4, 8 (8 points), 4.. = distances 16, 32, ... <= merange
     // (16 points).  Every level's points depend only on the start position, so levels can be evaluated ahead of the
@@ -871,7 +876,9 @@ __device__ __forceinline__ void me_star_pattern(const MeCtx<P>& c, MeStar& s, in
         }
         const bool valid = mylvl < lvl1 && k < cnt && !(mylvl >= 4 && d > merange) &&
                            px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
-        if (!valid) { px = ox; py = oy; }                        // idle lanes evaluate the (in-range) centre and are masked out
+        // idle lanes evaluate an in-range position (the centre clamped into the search range: the start point can lie outside
+        // it in x when MV 0 won the pre-checks, motion.cpp:806-813) and are masked out
+        if (!valid) { px = min(max(ox, c.minx), c.maxx); py = min(max(oy, c.miny), c.maxy); }
         const int n = spec ? (lvl0 == 0 ? 28 : 32) : (lvl0 == 0 ? 4 : lvl0 < 4 ? 8 : 16);
         const int cost = me_eval_points(c, n, px, py, false);
         for (int l = lvl0; l < lvl1; l++)
@@ -1153,6 +1160,70 @@ __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, M
     st.bmx = bmx; st.bmy = bmy; st.bcost = bcost; st.bprecost = bprecost; st.bestprex = bestprex; st.bestprey = bestprey;
 }
 
+// raster refinement (motion.cpp:1171-1201): grid of step 5 over the whole window.  Every 4th column of a row (when it
+// closes a full x4 group) adds mvcost(tmv << 3) as in the reference.  Global-memory version: 32 points per burst.
+template <typename P>
+__device__ __forceinline__ void me_raster(const MeCtx<P>& c, MeStar& s)
+{
+    const int RD = 5;
+    const int ncols = (c.maxx - c.minx) / RD + 1, nrows = (c.maxy - c.miny) / RD + 1;
+    const int total = ncols * nrows;
+    for (int base = 0; base < total; base += 32)
+    {
+        const int idx = min(base + c.lane, total - 1);
+        const int rj = idx / ncols, ri = idx - rj * ncols;
+        int px = c.minx + ri * RD, py = c.miny + rj * RD;
+        const int n = min(32, total - base);
+        const bool x8 = (ri & 3) == 3;
+        int cost = me_eval_points(c, n, px, py, x8);
+        const unsigned key = (unsigned)me_argmin(n, cost, c.lane);
+        if ((int)(key >> 5) < s.bcost)
+        {
+            s.bcost = (int)(key >> 5);
+            s.bx = __shfl_sync(0xffffffffu, px, (int)(key & 31)); s.by = __shfl_sync(0xffffffffu, py, (int)(key & 31));
+        }
+    }
+}
+
+// STAR (motion.cpp:1132-1240), written as one loop so that the star pattern, the two-point refinement and the raster scan
+// each have exactly one (inlined) evaluation site.  Generic over the context: MeCtx (global-memory gathers) or MeWin
+// (shared-memory search window, me_window.cuh); me_eval_points / me_raster are the per-context evaluation sites.
+template <typename CTX>
+__device__ __forceinline__ void me_star_search(const CTX& c, MeStar& s, int merange)
+{
+    bool first = true;
+    for (;;)
+    {
+        me_star_pattern(c, s, first ? 3 : 32, merange);
+        const bool d1 = s.dist == 1;
+        bool improved = false;
+        if (d1 && s.point)
+        {
+            // the two neighbours of the winning distance-1 point (motion.cpp:1139-1166 / :1215-1236), in order, strict '<'
+            const int saved = s.bcost;
+            const int o = (s.point - 1) * 2 + (c.lane & 1);
+            int px = s.bx + c_star_off[o][0], py = s.by + c_star_off[o][1], pt = s.point, ds = s.dist;
+            const bool valid = c.lane < 2 && ME_INRANGE(px, py);
+            const int n = me_compact(valid, 2, px, py, pt, ds);
+            if (n > 0)
+            {
+                const int cost = me_eval_points(c, n, px, py, false);
+                me_fold(s, n, cost, px, py, pt, ds);
+            }
+            improved = s.bcost != saved;
+        }
+        if (first)
+        {
+            if (d1 && !improved) break;
+            if (s.dist > 5) me_raster(c, s);
+            first = false;
+        }
+        else if (d1) break;
+        if (s.dist <= 0) break;
+        s.dist = 0; s.point = 0;
+    }
+}
+
 // phase 2 (motion.cpp:816-1438): the integer search proper
 template <typename P>
 __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, MeState& st)
@@ -1233,59 +1304,9 @@ __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, M
         }
     }
     else
-    {   // STAR (motion.cpp:1132-1240), written as one loop so that the star pattern, the two-point refinement and
-        // the raster scan each have exactly one (inlined) evaluation site
+    {
         MeStar s; s.bx = bmx; s.by = bmy; s.bcost = bcost; s.point = 0; s.dist = 0;
-        bool first = true;
-        for (;;)
-        {
-            me_star_pattern(c, s, first ? 3 : 32, merange);
-            const bool d1 = s.dist == 1;
-            bool improved = false;
-            if (d1 && s.point)
-            {
-                // the two neighbours of the winning distance-1 point (motion.cpp:1139-1166 / :1215-1236), in order, strict '<'
-                const int saved = s.bcost;
-                const int o = (s.point - 1) * 2 + (c.lane & 1);
-                int px = s.bx + c_star_off[o][0], py = s.by + c_star_off[o][1], pt = s.point, ds = s.dist;
-                const bool valid = c.lane < 2 && ME_INRANGE(px, py);
-                const int n = me_compact(valid, 2, px, py, pt, ds);
-                const int cost = me_eval_points(c, n, px, py, false);
-                me_fold(s, n, cost, px, py, pt, ds);
-                improved = s.bcost != saved;
-            }
-            if (first)
-            {
-                if (d1 && !improved) break;
-                const int RD = 5;
-                if (s.dist > RD)
-                {
-                    // raster refinement (motion.cpp:1171-1201): grid of step 5 over the whole window, 32 points per burst.
-                    // Every 4th column of a row (when it closes a full x4 group) adds mvcost(tmv << 3) as in the reference.
-                    const int ncols = (c.maxx - c.minx) / RD + 1, nrows = (c.maxy - c.miny) / RD + 1;
-                    const int total = ncols * nrows;
-                    for (int base = 0; base < total; base += 32)
-                    {
-                        const int idx = min(base + c.lane, total - 1);
-                        const int rj = idx / ncols, ri = idx - rj * ncols;
-                        int px = c.minx + ri * RD, py = c.miny + rj * RD;
-                        const int n = min(32, total - base);
-                        const bool x8 = (ri & 3) == 3;
-                        int cost = me_eval_points(c, n, px, py, x8);
-                        const unsigned key = (unsigned)me_argmin(n, cost, c.lane);
-                        if ((int)(key >> 5) < s.bcost)
-                        {
-                            s.bcost = (int)(key >> 5);
-                            s.bx = __shfl_sync(0xffffffffu, px, (int)(key & 31)); s.by = __shfl_sync(0xffffffffu, py, (int)(key & 31));
-                        }
-                    }
-                }
-                first = false;
-            }
-            else if (d1) break;
-            if (s.dist <= 0) break;
-            s.dist = 0; s.point = 0;
-        }
+        me_star_search(c, s, merange);
         bmx = s.bx; bmy = s.by; bcost = s.bcost;
     }
 
@@ -1421,17 +1442,21 @@ __device__ __forceinline__ void me_make_ctx(MeCtx<P>& c, const x265cu_me_job& j,
 template <typename P, int PHASE, int CLS>
 __global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : (CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS)) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
                                                            const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
-                                                           int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter)
+                                                           int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter,
+                                                           const int32_t* __restrict__ list = nullptr, const int* __restrict__ list_n = nullptr)
 {
     extern __shared__ unsigned char me_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     MeShared* sm = (MeShared*)me_smem + warp;
+    // with `list`: the jobs are list[0 .. *list_n) (the leftovers of the shared-memory-window search, me_window.cuh)
+    if (list) n = *list_n;
     for (;;)
     {
         int jid = 0;
         if (lane == 0) jid = atomicAdd(counter, 1);
         jid = __shfl_sync(0xffffffffu, jid, 0);
         if (jid >= n) break;
+        if (list) jid = list[jid];
         const x265cu_me_job j = jobs[jid];
         MeCtx<P> c;
         me_make_ctx<P>(c, j, fenc, fstride, refs, rstride, lowres, mvcost, lane, sm);
@@ -1494,22 +1519,36 @@ static int launch_me_chroma_phase(x265cu_ctx* ctx, const void* fenc, int fstride
 
 template <typename P, int PHASE, int CLS>
 static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
-                           const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter)
+                           const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter,
+                           const int32_t* list = NULL, const int* list_n = NULL)
 {
     const int threads = 256, warps = threads / 32;
     const size_t smem = PHASE == 2 ? 0 : sizeof(MeShared) * warps;      // the integer search never touches the interpolation scratch
     int blocks = ctx->sm_count * (PHASE == 2 ? ME_P2_BLOCKS : (CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS));
     int need = (n + warps - 1) / warps;
     if (blocks > need) blocks = need;
-    k_me<P, PHASE, CLS><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, lowres, mvcost, jobs, n, out, state, counter);
+    k_me<P, PHASE, CLS><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, lowres, mvcost, jobs, n, out, state, counter, list, list_n);
     CU_LAUNCH_CHECK(ctx);
     return 0;
 }
 
+// Shared-memory-window integer search (me_window.cuh): the caller (the frame analyser) owns the group tables and the tensor
+// maps of its reference planes; `left_*` receive the jobs the window kernel hands back to the global-memory kernel.
+struct MeWinLaunch
+{
+    const void* tmaps; int allocX, allocY;                  // device array [ref][MEW_NCLS] of CUtensorMap; picture origin inside the allocation
+    const void* groups[2]; int ngroups[2];                  // MeGroup lists of the launch slice: [0] CU 64 / 32 groups, [1] 16x16 cells
+    const int32_t* grp_jobs[2]; int job0;                   // absolute job indices; job0 = first job of the slice
+    int* left_count; int32_t* left_list;
+};
+template <typename P>
+static int launch_me_window(x265cu_ctx* ctx, const void* fenc, int fstride, const uint16_t* mvcost, const x265cu_me_job* jobs,
+                            MeState* st, const MeWinLaunch& w);
+
 template <typename P>
 static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
                        const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* st, int* counter_dev,
-                       const MeChromaArgs* ch)
+                       const MeChromaArgs* ch, const MeWinLaunch* win)
 {
     int rc = 0;
     if (ch)
@@ -1523,7 +1562,14 @@ static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const voi
         rc |= launch_me_phase<P, 1, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
     }
     CU_CHECK(cudaEventRecord(ctx->me_ev[1], ctx->stream));
-    rc |= launch_me_phase<P, 2, -1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
+    if (win && !lowres)
+    {
+        // STAR groups out of shared-memory windows; whatever does not fit (or is not STAR) through the global-memory kernel
+        rc |= launch_me_window<P>(ctx, fenc, fstride, mvcost, jobs, st, *win);
+        rc |= launch_me_phase<P, 2, -1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2, win->left_list, win->left_count);
+    }
+    else
+        rc |= launch_me_phase<P, 2, -1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 2);
     CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
     if (ch)
     {
@@ -1539,7 +1585,8 @@ static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const voi
 }
 
 static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
-                     const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, int* counter_dev, const MeChromaArgs* chroma = NULL)
+                     const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, int* counter_dev, const MeChromaArgs* chroma = NULL,
+                     const MeWinLaunch* win = NULL)
 {
     if (n <= 0) return 0;
     CU_CHECK(cudaMemsetAsync(counter_dev, 0, 8 * sizeof(int), ctx->stream));
@@ -1554,8 +1601,8 @@ static int launch_me(x265cu_ctx* ctx, int depth, const void* fenc, int fstride, 
     MeState* st = (MeState*)ctx->d_me_state;
     CU_CHECK(cudaEventRecord(ctx->me_ev[0], ctx->stream));
     if (chroma && lowres) chroma = NULL;                    // the lowres planes have no chroma (lowres.h)
-    const int rc = depth == 8 ? launch_me_t<uint8_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev, chroma)
-                              : launch_me_t<uint16_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev, chroma);
+    const int rc = depth == 8 ? launch_me_t<uint8_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev, chroma, win)
+                              : launch_me_t<uint16_t>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev, chroma, win);
     CU_CHECK(cudaEventRecord(ctx->me_ev[3], ctx->stream));
     return rc;
 }
