@@ -65,6 +65,7 @@ void* x265cu_get_primitive(int depth, const char* name, int i, int j, int k);
 int x265cu_primitive_error(void);
 const char* x265cu_primitive_error_string(void);
 void x265cu_primitive_error_clear(void);
+uint64_t x265cu_primitive_calls(void);     /* per-call table invocations of this process so far (diagnostics) */
 
 /* ---------- (2) batched API ---------- */
 

@@ -79,9 +79,11 @@ static void fail(const char* what)
     fprintf(stderr, "x265cu: primitive failed: %s: %s\n", what, x265cu_last_error());
 }
 
+static unsigned long long g_prim_calls = 0;         // per-call table invocations of the process (diagnostics)
 static thread_local x265cu_ctx* t_ctx = NULL;
 static x265cu_ctx* tctx()
 {
+    __atomic_fetch_add(&g_prim_calls, 1ull, __ATOMIC_RELAXED);
     if (!t_ctx)
     {
         // X265CU_DEVICE selects the GPU of the per-call table (default 0)
@@ -513,6 +515,7 @@ static void* lookup(const char* name, int i, int j, int k)
 
 } // namespace thunk
 
+extern "C" uint64_t x265cu_primitive_calls(void) { return __atomic_load_n(&thunk::g_prim_calls, __ATOMIC_RELAXED); }
 extern "C" int x265cu_primitive_error(void) { return __atomic_load_n(&thunk::g_prim_error, __ATOMIC_SEQ_CST); }
 extern "C" const char* x265cu_primitive_error_string(void) { return thunk::g_prim_msg; }
 extern "C" void x265cu_primitive_error_clear(void) { __atomic_store_n(&thunk::g_prim_error, 0, __ATOMIC_SEQ_CST); thunk::g_prim_msg[0] = 0; }

@@ -61,6 +61,10 @@ _PROTOS = {
     "x265cu_launch_count": (C.c_uint64, [P]),
     "x265cu_me_phase_ms": (I, [P, C.POINTER(C.c_float)]),
     "x265cu_get_primitive": (P, [I, C.c_char_p, I, I, I]),
+    "x265cu_primitive_error": (I, []),
+    "x265cu_primitive_error_string": (C.c_char_p, []),
+    "x265cu_primitive_error_clear": (None, []),
+    "x265cu_primitive_calls": (C.c_uint64, []),
     "x265cu_pixelcmp_batch": (I, [P, I, I, P, P, P, I, P]),
     "x265cu_pixelcmp_grid": (I, [P, I, I, P, I64, P, I64, I, I, I, I, P]),
     "x265cu_blockop_batch": (I, [P, I, I, P, P, P, P, I]),
