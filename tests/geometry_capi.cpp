@@ -34,12 +34,12 @@ int geo_get(int what, void* out)
     case 4: memcpy(out, g_geo.rowJob.data(), sizeof(int) * g_geo.rowJob.size()); break;
     case 5: memcpy(out, g_geo.rowCu.data(), sizeof(int) * g_geo.rowCu.size()); break;
     case 6: memcpy(out, g_geo.rowTu.data(), sizeof(int) * g_geo.rowTu.size()); break;
-    /* job groups of the shared-memory-window search, class k = 0 (CU 64 / 32) and 1 (16x16 cells):
+    /* job groups of the shared-memory-window search, class k = 0 (CU 64), 1 (CU 32) and 2 (16x16 cells):
      * 10 + 4k: counts {ngroups, njobs}; 11 + 4k: first|count pairs; 12 + 4k: job indices; 13 + 4k: rowGrp */
-    case 10: case 14: { int k = (what - 10) / 4; ((int32_t*)out)[0] = (int32_t)g_geo.grpFirst[k].size(); ((int32_t*)out)[1] = (int32_t)g_geo.grpJobs[k].size(); break; }
-    case 11: case 15: { int k = (what - 11) / 4; int32_t* o = (int32_t*)out; for (size_t i = 0; i < g_geo.grpFirst[k].size(); i++) { o[2 * i] = g_geo.grpFirst[k][i]; o[2 * i + 1] = g_geo.grpCount[k][i]; } break; }
-    case 12: case 16: { int k = (what - 12) / 4; memcpy(out, g_geo.grpJobs[k].data(), sizeof(int32_t) * g_geo.grpJobs[k].size()); break; }
-    case 13: case 17: { int k = (what - 13) / 4; memcpy(out, g_geo.rowGrp[k].data(), sizeof(int) * g_geo.rowGrp[k].size()); break; }
+    case 10: case 14: case 18: { int k = (what - 10) / 4; ((int32_t*)out)[0] = (int32_t)g_geo.grpFirst[k].size(); ((int32_t*)out)[1] = (int32_t)g_geo.grpJobs[k].size(); break; }
+    case 11: case 15: case 19: { int k = (what - 11) / 4; int32_t* o = (int32_t*)out; for (size_t i = 0; i < g_geo.grpFirst[k].size(); i++) { o[2 * i] = g_geo.grpFirst[k][i]; o[2 * i + 1] = g_geo.grpCount[k][i]; } break; }
+    case 12: case 16: case 20: { int k = (what - 12) / 4; memcpy(out, g_geo.grpJobs[k].data(), sizeof(int32_t) * g_geo.grpJobs[k].size()); break; }
+    case 13: case 17: case 21: { int k = (what - 13) / 4; memcpy(out, g_geo.rowGrp[k].data(), sizeof(int) * g_geo.rowGrp[k].size()); break; }
     default: return -1;
     }
     return 0;

@@ -78,7 +78,7 @@ def test_geometry_matches_oracle(geo, size, rect, amp):
 @pytest.mark.parametrize("rect,amp", [(1, 0), (1, 1), (0, 0)])
 def test_window_groups_partition_the_jobs(geo, size, rect, amp):
     """Job groups of the shared-memory-window integer search (me_window.cuh): every PU job is in exactly one group, a group's
-    jobs share the reference and lie inside one 64x64 / 32x32 CU (class 0) or one 16x16 cell (class 1), are ordered largest
+    jobs share the reference and lie inside one 64x64 CU (class 0), one 32x32 CU (class 1) or one 16x16 cell (class 2), are ordered largest
     first, and the per-CTU-row group ranges cover exactly the jobs of those rows (what a row shard launches)."""
     W, H = size
     nref = 2
@@ -87,7 +87,7 @@ def test_window_groups_partition_the_jobs(geo, size, rect, amp):
     seen = np.zeros(g["njobs"], np.int32)
     pus = g["pus"]
     px, py = pus[:, 0] % st, pus[:, 0] // st
-    for k in range(2):
+    for k in range(3):
         cnt = np.zeros(2, np.int32); geo.geo_get(10 + 4 * k, cnt.ctypes.data_as(C.c_void_p))
         ng, nj = int(cnt[0]), int(cnt[1])
         fc = np.zeros(2 * ng, np.int32); geo.geo_get(11 + 4 * k, fc.ctypes.data_as(C.c_void_p)); fc = fc.reshape(-1, 2)
@@ -102,7 +102,7 @@ def test_window_groups_partition_the_jobs(geo, size, rect, amp):
             assert len(set(pus[ids, 5])) == 1
             x0, y0 = px[ids].min(), py[ids].min()
             x1, y1 = (px[ids] + pus[ids, 3]).max(), (py[ids] + pus[ids, 4]).max()
-            lim = 16 if k == 1 else 64
+            lim = (64, 32, 16)[k]
             assert x1 - x0 <= lim and y1 - y0 <= lim and x0 // lim == (x1 - 1) // lim and y0 // lim == (y1 - 1) // lim
             area = pus[ids, 3].astype(np.int64) * pus[ids, 4]
             assert (np.diff(area) <= 0).all()

@@ -58,3 +58,40 @@ def test_lookahead_gpu(cu, depth, size, noise):
         assert np.array_equal(r["lowresCosts"], orc.fr[b]["lowresCosts"][(d0, d1)]), (p0, p1, b)
         assert np.array_equal(r["rowSatds"], orc.fr[b]["rowSatds"][(d0, d1)])
         assert a == c and r["costEstAq"] == orc.fr[b]["costEst"][(d0, d1)][1], ((p0, p1, b), a, c)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_lookahead_frame_shards_equal_single(cu, world):
+    """Lookahead frames sharded per rank (BASELINE configs[3], x265_b200/lookahead.py): `world` Lookahead instances emulate
+    the ranks on one GPU -- each initialises only the frames it owns, receives the other frames' 4-plane blocks (the
+    broadcast payload), estimates the triples whose b it owns.  All costs equal the single-instance run bit for bit."""
+    from x265_b200.lookahead import Lookahead, owner, window_triples, conflict_free_batches
+    depth, W, H, n = 8, 416, 240, 8
+    frames = [gen_luma(W, H, i, s1=17.0, s2=11.0, bits=depth) for i in range(n)]
+    triples = window_triples(n, 3)
+    single = GpuLookahead(cu, frames, depth)
+    want = {}
+    for b in conflict_free_batches(triples):
+        for t, c in zip(b, single.cost_batch(b)):
+            want[t] = c
+    ranks = [Lookahead(cu, W, H, depth, n) for _ in range(world)]
+    for i in range(n):
+        ranks[owner(i, world)].init_frame(i, frames[i])
+    for i in range(n):                                   # "broadcast" of frame i's plane block from its owner
+        src = ranks[owner(i, world)]
+        payload = src.fr[i]["block"].download(np.uint8)
+        assert np.array_equal(payload, single.fr[i]["block"].download(np.uint8))
+        for r, la in enumerate(ranks):
+            if r != owner(i, world):
+                la.fr[i]["block"].upload(payload); la.planes_received(i)
+    got = {}
+    for r, la in enumerate(ranks):
+        la.intra_batch([i for i in range(n) if owner(i, world) == r])
+        mine = [t for t in triples if owner(t[2], world) == r]
+        for b in conflict_free_batches(mine):
+            for t, c in zip(b, la.cost_batch(b)):
+                got[t] = c
+    assert got == want
+    for la in ranks:
+        la.close()
+    single.close()

@@ -98,3 +98,64 @@ def test_row_blocks_are_a_partition(mode):
             assert all(shard.row_owner(r, nrows, world, mode) in range(world) for r in range(nrows))
             sizes = [sum(r1 - r0 for r0, r1 in shard.row_blocks(nrows, g, world, mode)) for g in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- lookahead frames sharded per rank (BASELINE configs[3]; x265_b200/lookahead.py) ----------------------------------
+def _la_worker(rank, world, port, ret):
+    """Every rank builds the lowres planes of ITS frames only (owner(b) = b % world), publishes them with one broadcast per
+    frame, then estimates the triples whose b it owns (CPU oracle arithmetic here; the GPU path runs the same host logic
+    over NCCL).  The gathered costs must equal a single-process run: sharding changes placement, never arithmetic."""
+    import ctypes as C
+    from common import load_oracle
+    from frame_helpers import gen_luma
+    from lookahead_helpers import OracleLookahead, make_lowres
+    from x265_b200.lookahead import owner, window_triples, conflict_free_batches
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    O = load_oracle(8)
+    W, H, n = 208, 144, 6
+    frames = [gen_luma(W, H, i, s1=17.0, s2=11.0) for i in range(n)]
+    blank = [np.zeros_like(f) for f in frames]
+    # a rank only has the source pixels of its own frames
+    la = OracleLookahead(O, [frames[i] if owner(i, world) == rank else blank[i] for i in range(n)], 8)
+    for i in range(n):
+        for k in range(4):
+            t = torch.from_numpy(la.fr[i]["planes"][k])
+            dist.broadcast(t, src=owner(i, world))             # one frame's planes from its owner
+    triples = window_triples(n, 2)
+    mine = [t for t in triples if owner(t[2], world) == rank]
+    # intra costs of the frames this rank estimates are its own (it owns b); p0 / p1 only contribute planes
+    costs = {t: la.cost(*t) for t in mine}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, costs)
+    ok = 1
+    if rank == 0:
+        full = OracleLookahead(O, frames, 8)
+        want = {t: full.cost(*t) for t in triples}
+        got = {}
+        for g in gathered:
+            got.update(g)
+        ok = int(got == want and len(got) == len(triples))
+        # launches never put two searches of one motion field together
+        for b in conflict_free_batches(triples):
+            keys = [(t[2], 0, t[2] - t[0]) for t in b] + [(t[2], 1, t[1] - t[2]) for t in b if t[1] > t[2]]
+            ok = ok and int(len(keys) == len(set(keys)))
+    t = torch.tensor([ok]); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    ret[rank] = int(t.item())
+    dist.destroy_process_group()
+
+
+def test_lookahead_frame_shards_gloo():
+    world = 2
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_la_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r] == 1 for r in range(world))
+
+
+def test_lookahead_owner_is_a_partition():
+    from x265_b200.lookahead import owner, window_triples
+    for world in (1, 2, 4, 8):
+        tr = window_triples(20, 4)
+        per = [[t for t in tr if owner(t[2], world) == g] for g in range(world)]
+        assert sorted(t for p in per for t in p) == sorted(tr)
+        assert max(len(p) for p in per) - min(len(p) for p in per) <= len(tr) // world // 2 + 16

@@ -36,7 +36,7 @@ struct x265cu_analyser
     void** d_refCbTable; void** d_refCrTable;
     // shared-memory-window integer search (me_window.cuh): group tables (two classes), tensor maps of the reference
     // planes [ref][MEW_NCLS], leftover list.  windowOn = 0 (X265CU_ME_WINDOW=0) keeps the global-memory kernel for all jobs.
-    int windowOn; MeGroup* d_groups[2]; int32_t* d_grpJobs[2]; std::vector<int> rowGrp[2];
+    int windowOn; MeGroup* d_groups[3]; int32_t* d_grpJobs[3]; std::vector<int> rowGrp[3];
     CUtensorMap* d_tmaps; int32_t* d_left;
 };
 
@@ -56,7 +56,7 @@ static void an_build_geometry(x265cu_analyser* a)
     a->pus.swap(g.pus); a->cus.swap(g.cus); a->tus.swap(g.tus); a->cu_jobs.swap(g.cu_jobs);
     a->ctuRows = g.ctuRows; a->rowJob.swap(g.rowJob); a->rowCu.swap(g.rowCu); a->rowTu.swap(g.rowTu);
     a->njobs = (int)a->pus.size(); a->ncu = (int)a->cus.size(); a->ntu = (int)a->tus.size(); a->ncoef = g.ncoef;
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < 3; k++)
     {
         std::vector<MeGroup> grp(g.grpFirst[k].size());
         for (size_t i = 0; i < grp.size(); i++) { grp[i].first = g.grpFirst[k][i]; grp[i].count = g.grpCount[k][i]; }
@@ -94,7 +94,8 @@ static int an_run(x265cu_analyser* a, int stages, int r0, int r1)
         if (a->windowOn)
         {
             win.tmaps = a->d_tmaps; win.allocX = AN_MARGIN_X; win.allocY = AN_MARGIN_Y;
-            for (int k = 0; k < 2; k++)
+            win.amp = a->p.amp;
+            for (int k = 0; k < 3; k++)
             {
                 win.groups[k] = a->d_groups[k] + a->rowGrp[k][r0]; win.ngroups[k] = a->rowGrp[k][r1] - a->rowGrp[k][r0];
                 win.grp_jobs[k] = a->d_grpJobs[k];
@@ -228,7 +229,7 @@ void x265cu_analyser_destroy(x265cu_analyser* a)
     cudaStreamSynchronize(c->stream);
     void* bufs[] = { a->d_fenc, a->d_refTable, a->d_reconTable, a->d_field, a->d_mvcost, a->d_pus, a->d_cus, a->d_tus, a->d_cu_jobs, a->d_jobs,
                      a->d_me_out, a->d_me_packed, a->d_coef, a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref, a->d_intra,
-                     a->d_groups[0], a->d_groups[1], a->d_grpJobs[0], a->d_grpJobs[1], a->d_tmaps, a->d_left };
+                     a->d_groups[0], a->d_groups[1], a->d_groups[2], a->d_grpJobs[0], a->d_grpJobs[1], a->d_grpJobs[2], a->d_tmaps, a->d_left };
     for (void* b : bufs) cudaFree(b);
     for (int r = 0; r < a->p.numRefs; r++) cudaFree(a->d_refs[r]);
     for (int d = 0; d < 4; d++) cudaFree(a->d_recon[d]);

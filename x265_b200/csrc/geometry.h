@@ -23,8 +23,8 @@ struct FrameGeometry
     // job groups of the shared-memory-window integer search (me_window.cuh): per (CTU, ref) the 64x64 CU's PUs, each 32x32
     // CU's PUs, and per 16x16 cell the PUs of the 16x16 CU and of its four 8x8 CUs.  grpJobs holds absolute job indices,
     // largest PU first inside a group; groups are in CTU raster order (rowGrp = first group of every CTU row + end).
-    // Two classes, launched separately (different shared-memory budgets): [0] = CU 64 / CU 32 groups, [1] = 16x16 cells.
-    std::vector<int32_t> grpFirst[2], grpCount[2], grpJobs[2]; std::vector<int> rowGrp[2];
+    // Three classes, launched separately (different shared-memory budgets): [0] = CU 64 groups, [1] = CU 32 groups, [2] = 16x16 cells.
+    std::vector<int32_t> grpFirst[3], grpCount[3], grpJobs[3]; std::vector<int> rowGrp[3];
 };
 
 // partitions of a CU of `size`: returns the count and fills part[k] = {x, y, w, h} relative to the CU origin
@@ -59,7 +59,7 @@ static inline void geometry_build(int W, int H, int stride, int nref, int rect, 
     for (int cty = 0; cty < ctuH; cty++)
     {
         g.rowJob.push_back((int)g.pus.size()); g.rowCu.push_back((int)g.cus.size()); g.rowTu.push_back((int)g.tus.size());
-        for (int k = 0; k < 2; k++) g.rowGrp[k].push_back((int)g.grpFirst[k].size());
+        for (int k = 0; k < 3; k++) g.rowGrp[k].push_back((int)g.grpFirst[k].size());
         for (int ctx = 0; ctx < ctuW; ctx++)
         {
             int local[85]; int nl = 0;
@@ -117,7 +117,7 @@ static inline void geometry_build(int W, int H, int stride, int nref, int rect, 
                         for (int a8 = 0; a8 < 2; a8++)
                             for (int b8 = 0; b8 < 2; b8++) members[nm++] = 21 + (2 * cy16 + a8) * 8 + (2 * cx16 + b8);
                     }
-                    const int cl = gi < 5 ? 0 : 1;
+                    const int cl = gi == 0 ? 0 : (gi < 5 ? 1 : 2);
                     std::vector<int32_t>& gj = g.grpJobs[cl];
                     const int first = (int)gj.size();
                     for (int m = 0; m < nm; m++)
@@ -138,7 +138,7 @@ static inline void geometry_build(int W, int H, int stride, int nref, int rect, 
             }
         }
     }
-    for (int k = 0; k < 2; k++) g.rowGrp[k].push_back((int)g.grpFirst[k].size());
+    for (int k = 0; k < 3; k++) g.rowGrp[k].push_back((int)g.grpFirst[k].size());
     g.rowJob.push_back((int)g.pus.size()); g.rowCu.push_back((int)g.cus.size()); g.rowTu.push_back((int)g.tus.size());
     g.ncoef = coefOff;
 }

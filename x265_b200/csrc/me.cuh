@@ -1537,8 +1537,9 @@ static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const
 struct MeWinLaunch
 {
     const void* tmaps; int allocX, allocY;                  // device array [ref][MEW_NCLS] of CUtensorMap; picture origin inside the allocation
-    const void* groups[2]; int ngroups[2];                  // MeGroup lists of the launch slice: [0] CU 64 / 32 groups, [1] 16x16 cells
-    const int32_t* grp_jobs[2]; int job0;                   // absolute job indices; job0 = first job of the slice
+    const void* groups[3]; int ngroups[3];                  // MeGroup lists of the launch slice: [0] CU 64 groups, [1] CU 32 groups, [2] 16x16 cells
+    const int32_t* grp_jobs[3]; int job0;                   // absolute job indices; job0 = first job of the slice
+    int amp;                                                // AMP partitions present (13 PUs per CU instead of 5): sizes the CTAs
     int* left_count; int32_t* left_list;
 };
 template <typename P>

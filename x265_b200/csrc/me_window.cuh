@@ -1,7 +1,7 @@
 // x265_b200/csrc/me_window.cuh -- integer motion search (phase 2 of the batched motionEstimate, STAR: motion.cpp:362-604,
 // 1132-1240) on a SHARED-MEMORY SEARCH WINDOW.
 //
-// One CTA per job GROUP: the PUs of one CU (32x32 / 64x64 groups) or of one 16x16 cell (the 16x16 CU and its four 8x8 CUs)
+// One CTA per job GROUP: the PUs of one CU (64x64 groups, 32x32 groups) or of one 16x16 cell (the 16x16 CU and its four 8x8 CUs)
 // against ONE reference.  Their search windows [PU + mvmin, PU + mvmax + size) overlap almost completely, so the CTA
 //   1. takes the union rectangle of the group's windows,
 //   2. has ONE thread issue TMA tile loads (cp.async.bulk.tensor.2d, box = CLS x 16 rows, mbarrier complete_tx) of that
@@ -48,10 +48,31 @@ struct MeWin
     int minx, miny, maxx, maxy;            // full-pel bounds
     int w, h, lane;
     bool pow2; int nw, lgnw, lgwpr, lgsegw;
+    const struct MewCell* cell;            // shared 4x4 SAD maps of the 16x16 cell (NULL: this job walks its own raster)
+};
+
+// 16x16 cell groups: all PUs of the cell (16x16 CU + four 8x8 CUs) that share one raster grid (same mvmin / mvmax: the
+// predictor field is 16x16-granular, so inside the picture they all do) get their raster costs from ONE set of SAD maps:
+// the SAD of each of the cell's sixteen 4x4 blocks at every grid point, computed once by whichever warps need it
+// (tasks = (block row, grid row), lanes = grid columns) and summed per PU (a PU's SAD at a vector is the sum of its 4x4
+// blocks' SADs at that vector: exact).  A 16x16 PU then costs 16 loads per grid point instead of 256 pixel differences.
+#define MEW_MAP_ROWS 23                    // grid rows (merange 57: (2 * 57) / 5 + 1)
+#define MEW_MAP_BYTES (16 * MEW_MAP_ROWS * 32 * 2)
+struct MewCell
+{
+    int on;                                // maps usable for this group
+    int minx, miny, maxx, maxy;            // the shared grid (full-pel bounds of the group's first job)
+    int ncols, nrows;
+    int ox, oy;                            // cell origin relative to the window origin (pixels)
+    uint32_t fenc;                         // shared address of the cell's source block (pitch 64 pixels)
+    uint32_t map;                          // shared address of the maps: u16 [block 16][MEW_MAP_ROWS][32]
+    int next, done;                        // task queue of the map computation
 };
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 
 template <typename P>
@@ -261,9 +282,97 @@ __device__ __forceinline__ void mew_raster_na(const MeWin<P>& c, MeStar& s)
     else                mew_raster_t<P, 13, LGSEGW>(c, s);
 }
 
+// One task of the cell maps: the 4 blocks of block row `by` at grid row k, every grid column (lane = column).
+template <typename P>
+__device__ __forceinline__ void mew_cell_map_task(const MeWin<P>& c, const MewCell& cell, int by, int k)
+{
+    constexpr int ES = (int)sizeof(P), WB = ES;                    // words per 4-pixel block row
+    const int col = c.lane;
+    const bool act = col < cell.ncols;
+    const int gx = cell.minx + (act ? col : 0) * 5, gy = cell.miny + k * 5;
+    const uint32_t a0 = c.win + (uint32_t)((cell.oy + gy + 4 * by) * c.pitch + (cell.ox + gx) * ES);
+    const unsigned sh = (a0 & 3u) * 8u;
+    const bool hi8 = (a0 & 4u) != 0;
+    const uint32_t a8 = a0 & ~7u;
+    const uint32_t fa = cell.fenc + (uint32_t)(4 * by * 64 * ES);
+    int acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+#pragma unroll
+        for (int hw = 0; hw < WB; hw++)                            // 16 bytes of the row per step: 4 (8-bit) / 2 (16-bit) blocks
+        {
+            uint32_t rr[4], ff[4];
+            mew_load_ref<4>(a8 + r * c.pitch + hw * 16, hi8, sh, rr);
+            mew_load_fenc<4>(fa + r * 64 * ES + hw * 16, ff);      // same address in every lane: broadcast
+#pragma unroll
+            for (int wd = 0; wd < 4; wd++)
+            {
+                const int bx = (hw * 4 + wd) / WB;                 // block column of this word
+                acc[bx] = sad_word<P>(ff[wd], rr[wd], acc[bx]);
+            }
+        }
+    }
+    if (act)
+    {
+#pragma unroll
+        for (int bx = 0; bx < 4; bx++)
+            sts16(cell.map + (uint32_t)((((by * 4 + bx) * MEW_MAP_ROWS + k) * 32 + col) * 2), (uint32_t)acc[bx]);
+    }
+}
+
+// Raster refinement of one PU out of the cell maps (same result as mew_raster_t: minimum cost, ties to the lowest raster index).
+template <typename P>
+__device__ __forceinline__ void mew_raster_maps(const MeWin<P>& c, MeStar& s)
+{
+    MewCell* cell = const_cast<MewCell*>(c.cell);
+    const int ntasks = 4 * cell->nrows;
+    // every warp that needs the maps helps to build them, then waits until all tasks are done
+    for (;;)
+    {
+        int t = 0;
+        if (c.lane == 0) t = atomicAdd(&cell->next, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntasks) break;
+        mew_cell_map_task<P>(c, *cell, t & 3, t >> 2);
+        __syncwarp();
+        if (c.lane == 0) { __threadfence_block(); atomicAdd(&cell->done, 1); }
+    }
+    if (c.lane == 0) { while (*(volatile int*)&cell->done < ntasks) __nanosleep(40); }
+    __syncwarp();
+    __threadfence_block();
+    const int ncols = cell->ncols, nrows = cell->nrows;
+    const int col = c.lane;
+    const bool act = col < ncols;
+    const int gx = c.minx + (act ? col : 0) * 5;
+    const bool x8 = (col & 3) == 3;
+    const int xc = (int)__ldg(c.mvc + ((x8 ? gx * 8 : gx * 4) - c.mvpx));
+    const int bx0 = (c.ox - cell->ox) >> 2, by0 = (c.oy - cell->oy) >> 2, nbx = c.w >> 2, nby = c.h >> 2;
+    int best = 0x7fffffff, bestIdx = 0x7fffffff;
+    for (int k = 0; k < nrows; k++)
+    {
+        int sad = 0;
+        for (int by = by0; by < by0 + nby; by++)
+            for (int bx = bx0; bx < bx0 + nbx; bx++)
+                sad += (int)lds16(cell->map + (uint32_t)((((by * 4 + bx) * MEW_MAP_ROWS + k) * 32 + col) * 2));
+        const int py = c.miny + k * 5;
+        const int cost = sad + (int)(uint16_t)(xc + (int)__ldg(c.mvc + ((x8 ? py * 8 : py * 4) - c.mvpy)));
+        if (act && cost < best) { best = cost; bestIdx = k * ncols + col; }       // k ascending: strict '<' keeps the earliest
+    }
+    const int m = __reduce_min_sync(0xffffffffu, best);
+    const int mi = __reduce_min_sync(0xffffffffu, best == m ? bestIdx : 0x7fffffff);
+    if (m < s.bcost)
+    {
+        s.bcost = m;
+        const int rj = mi / ncols, ri = mi - rj * ncols;
+        s.bx = c.minx + ri * 5; s.by = c.miny + rj * 5;
+    }
+}
+
 template <typename P>
 __device__ __forceinline__ void me_raster(const MeWin<P>& c, MeStar& s)
 {
+    if (c.cell) { mew_raster_maps<P>(c, s); return; }              // 16x16 cell with a shared grid: costs out of the SAD maps
     // pow2 PUs use the widest aligned segment; AMP widths (12 / 24 / 48) walk 4-byte words
     if (c.pow2 && c.lgsegw == 2)      mew_raster_na<P, 2>(c, s);
     else if (c.pow2 && c.lgsegw == 1) mew_raster_na<P, 1>(c, s);
@@ -316,9 +425,10 @@ struct MewHdr
     int wx0, wy0, pitch, ntiles, cls;      // window origin (picture coordinates, pixels), pitch in bytes
     int fx0, fy0, fw, fh;                  // source-block bounding box (picture coordinates, pixels)
     int ref;
+    MewCell cell;                          // shared SAD maps of a 16x16 cell group (CELL launches)
 };
 
-template <typename P>
+template <typename P, bool CELL>
 __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc, int fstride, MeWinArgs wa,
                                                       const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs,
                                                       const MeGroup* __restrict__ groups, const int32_t* __restrict__ grp_jobs, int job0,
@@ -331,6 +441,7 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
     const MeGroup g = groups[blockIdx.x];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(mew_smem);
     const uint32_t s_fenc = sbase + MEW_HDR, s_win = sbase + MEW_HDR + wa.fencBytes;
+    const uint32_t s_map = sbase + (uint32_t)(wa.smemBytes - MEW_MAP_BYTES);      // CELL launches: the maps sit at the end
 
     // ---- 1. union rectangle of the group's search windows and of its source blocks (warp 0) ----
     if (warp == 0)
@@ -338,9 +449,11 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
         int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -0x7fffffff, y1 = -0x7fffffff;
         int fx0 = 0x7fffffff, fy0 = 0x7fffffff, fx1 = -0x7fffffff, fy1 = -0x7fffffff;
         int bad = 0, ref = 0;
+        int g0minx = 0, g0miny = 0, g0maxx = 0, g0maxy = 0;
         for (int i = lane; i < g.count; i += 32)
         {
             const x265cu_me_job j = jobs[grp_jobs[g.first + i] - job0];
+            if (i == 0) { g0minx = j.mvmin[0]; g0miny = j.mvmin[1]; g0maxx = j.mvmax[0]; g0maxy = j.mvmax[1]; }
             const int py = j.offset / fstride, px = j.offset - py * fstride;
             x0 = min(x0, px + j.mvmin[0]); x1 = max(x1, px + j.mvmax[0] + j.pw);
             y0 = min(y0, py + j.mvmin[1]); y1 = max(y1, py + j.mvmax[1] + j.ph);
@@ -371,12 +484,24 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
             if (ok)
             {
                 const int pitch = mew_cls_bytes(ES, cls);
-                ok = MEW_HDR + wa.fencBytes + pitch * ntiles * MEW_BOX_ROWS <= wa.smemBytes && fwB <= 64 * ES && 64 * ES * fhh <= wa.fencBytes;
+                ok = MEW_HDR + wa.fencBytes + pitch * ntiles * MEW_BOX_ROWS + (CELL ? MEW_MAP_BYTES : 0) <= wa.smemBytes && fwB <= 64 * ES && 64 * ES * fhh <= wa.fencBytes;
                 hdr->pitch = pitch;
             }
             hdr->ok = ok; hdr->next = 0; hdr->cls = cls; hdr->ntiles = ntiles;
             hdr->wx0 = ax0a - wa.allocX; hdr->wy0 = y0;
             hdr->fx0 = fx0a; hdr->fy0 = fy0; hdr->fw = fwB; hdr->fh = fhh; hdr->ref = ref;
+            // shared SAD maps: a complete 16x16 cell and a grid of at most 32 x MEW_MAP_ROWS points (lane 0 holds job 0's range)
+            MewCell& cl = hdr->cell;
+            cl.on = 0;
+            if (CELL && ok && fx1 - fx0 == 16 && fy1 - fy0 == 16 && fx0a == fx0)
+            {
+                const int ncols = (g0maxx - g0minx) / 5 + 1, nrows = (g0maxy - g0miny) / 5 + 1;
+                if (ncols <= 32 && nrows <= MEW_MAP_ROWS)
+                {
+                    cl.on = 1; cl.minx = g0minx; cl.miny = g0miny; cl.maxx = g0maxx; cl.maxy = g0maxy; cl.ncols = ncols; cl.nrows = nrows;
+                    cl.ox = fx0 - hdr->wx0; cl.oy = fy0 - y0; cl.fenc = s_fenc; cl.map = s_map; cl.next = 0; cl.done = 0;
+                }
+            }
         }
     }
     __syncthreads();
@@ -438,6 +563,9 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
         c.lgwpr = 31 - __clz(wpr); c.nw = wpr * c.h; c.lgnw = 31 - __clz(c.nw);
         const unsigned fal = c.fenc | (unsigned)c.fpitch;
         c.lgsegw = min(c.lgwpr, (fal & 15u) == 0 ? 2 : (fal & 7u) == 0 ? 1 : 0);
+        c.cell = NULL;
+        if (CELL && hdr->cell.on && c.minx == hdr->cell.minx && c.maxx == hdr->cell.maxx && c.miny == hdr->cell.miny && c.maxy == hdr->cell.maxy)
+            c.cell = &hdr->cell;
         MeState st = state[jid];
         MeStar s; s.bx = st.bmx; s.by = st.bmy; s.bcost = st.bcost; s.point = 0; s.dist = 0;
         me_star_search(c, s, (int)j.merange);
@@ -486,12 +614,13 @@ static int mew_build_tmaps(void* base, int stride, int rows, int es, CUtensorMap
     return 0;
 }
 
-// shared-memory budgets (bytes) of the two group classes: header + source block + window
+// shared-memory budgets (bytes) of the three group classes: header + source block + window (+ SAD maps)
 static inline int mew_smem_bytes(int es, int cls, int* fencBytes)
 {
-    if (cls == 0) { *fencBytes = 64 * 64 * es; return MEW_HDR + *fencBytes + (es == 1 ? 240 * 208 : 464 * 208); }   // CU 64 / 32 groups
+    if (cls == 0) { *fencBytes = 64 * 64 * es; return MEW_HDR + *fencBytes + (es == 1 ? 240 * 192 : 464 * 192); }    // CU 64 groups
+    if (cls == 1) { *fencBytes = 32 * 64 * es; return MEW_HDR + *fencBytes + (es == 1 ? 208 * 160 : 400 * 160); }    // CU 32 groups
     *fencBytes = 16 * 64 * es;
-    return MEW_HDR + *fencBytes + (es == 1 ? 208 * 160 : 336 * 160);                                                  // 16x16 cells
+    return MEW_HDR + *fencBytes + (es == 1 ? 208 * 160 : 336 * 144) + MEW_MAP_BYTES;                                  // 16x16 cells (+ SAD maps)
 }
 
 template <typename P>
@@ -499,15 +628,26 @@ static int launch_me_window(x265cu_ctx* ctx, const void* fenc, int fstride, cons
                             MeState* st, const MeWinLaunch& w)
 {
     CU_CHECK(cudaMemsetAsync(w.left_count, 0, sizeof(int), ctx->stream));
-    for (int cls = 0; cls < 2; cls++)
+    for (int cls = 0; cls < 3; cls++)
     {
         if (w.ngroups[cls] <= 0) continue;
+        // one warp per PU of a CU group (5, or 13 with AMP); cells hold 25 (33) PUs that 8 warps pull from a queue
+        const int threads = cls == 2 ? 256 : (w.amp ? 256 : 160);
         MeWinArgs a;
         a.tmaps = (const CUtensorMap*)w.tmaps; a.allocX = w.allocX; a.allocY = w.allocY;
         a.smemBytes = mew_smem_bytes((int)sizeof(P), cls, &a.fencBytes);
-        CU_CHECK(cudaFuncSetAttribute(k_me_window<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smemBytes));
-        k_me_window<P><<<w.ngroups[cls], 256, a.smemBytes, ctx->stream>>>((const P*)fenc, fstride, a, mvcost, jobs, (const MeGroup*)w.groups[cls],
-                                                                         w.grp_jobs[cls], w.job0, st, w.left_count, w.left_list);
+        if (cls < 2)
+        {
+            CU_CHECK(cudaFuncSetAttribute(k_me_window<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smemBytes));
+            k_me_window<P, false><<<w.ngroups[cls], threads, a.smemBytes, ctx->stream>>>((const P*)fenc, fstride, a, mvcost, jobs, (const MeGroup*)w.groups[cls],
+                                                                                    w.grp_jobs[cls], w.job0, st, w.left_count, w.left_list);
+        }
+        else
+        {
+            CU_CHECK(cudaFuncSetAttribute(k_me_window<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smemBytes));
+            k_me_window<P, true><<<w.ngroups[cls], threads, a.smemBytes, ctx->stream>>>((const P*)fenc, fstride, a, mvcost, jobs, (const MeGroup*)w.groups[cls],
+                                                                                   w.grp_jobs[cls], w.job0, st, w.left_count, w.left_list);
+        }
         CU_LAUNCH_CHECK(ctx);
     }
     return 0;
