@@ -247,7 +247,8 @@ typedef struct {
     int32_t* mvs[2]; int32_t* mvcosts[2];                    /* [cu][2] qpel MVs and [cu] costs per list, in/out */
     const int32_t* intraCost; const int32_t* invQscale;
     uint16_t* lowresCosts; int32_t* rowSatds; int64_t* out;  /* out[3]: costEst, costEstAq, intraMbs */
-    int32_t bidir, doSearch0, doSearch1, pad;
+    int32_t bidir, doSearch0, doSearch1;
+    int32_t rows;                                            /* 0: whole frame; else a cooperative slice (slicetype.cpp:3075-3112): CU rows [rows & 0xffff, rows >> 16) */
 } x265cu_la_job;
 int x265cu_lookahead_cost_batch(x265cu_ctx*, int depth, const x265cu_la_job* jobs_dev, int n, int stride, int w8, int h8,
                                 const uint16_t* mvcost_dev /* centred table base, lambda of X265_LOOKAHEAD_QP */);

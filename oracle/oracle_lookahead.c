@@ -107,6 +107,9 @@ typedef struct {
     const uint16_t* mvcost_tab;     /* centred, lambda of X265_LOOKAHEAD_QP */
     uint16_t* lowresCosts; int32_t* rowSatds;
     int64_t out[3];                 /* costEst, costEstAq, intraMbs */
+    /* cooperative slices (slicetype.cpp:3075-3112, 3143-3173): numSlices > 1 splits the CU rows into numSlices ranges of
+     * rowsPerSlice rows (the last one takes the remainder); every range starts with lastRow = true at its bottom row */
+    int numSlices, rowsPerSlice;
 } orc_la_job;
 
 void orc_lookahead_frame_cost(orc_la_job* j)
@@ -114,9 +117,14 @@ void orc_lookahead_frame_cost(orc_la_job* j)
     const int w8 = j->w8, h8 = j->h8;
     const intptr_t stride = j->stride;
     int64_t costEst = 0, costEstAq = 0, intraMbs = 0;
-    for (int cuY = h8 - 1; cuY >= 0; cuY--)
+    const int nsl = j->numSlices > 1 ? j->numSlices : 1;
+    for (int sl = 0; sl < nsl; sl++)
     {
-        const int lastRow = (cuY == h8 - 1);
+    const int firstY = nsl > 1 ? j->rowsPerSlice * sl : 0;
+    const int lastY = (nsl == 1 || sl == nsl - 1) ? h8 - 1 : j->rowsPerSlice * (sl + 1) - 1;
+    for (int cuY = lastY; cuY >= firstY; cuY--)
+    {
+        const int lastRow = (cuY == lastY);
         j->rowSatds[cuY] = 0;
         for (int cuX = w8 - 1; cuX >= 0; cuX--)
         {
@@ -203,6 +211,7 @@ void orc_lookahead_frame_cost(orc_la_job* j)
             j->rowSatds[cuY] += bcostAq;
             j->lowresCosts[cuXY] = (uint16_t)((bcost < LOWRES_COST_MASK ? bcost : LOWRES_COST_MASK) | (listused << LOWRES_COST_SHIFT));
         }
+    }
     }
     j->out[0] = costEst; j->out[1] = costEstAq; j->out[2] = intraMbs;
 }

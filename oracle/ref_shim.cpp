@@ -320,6 +320,7 @@ extern "C" int x265ref_analyse_frame(drv_frame* f, int stages)
  * (slicetype.cpp:696-805) and CostEstimateGroup::singleCost -> estimateFrameCost -> estimateCUCost
  * (slicetype.cpp:3021-3388) on caller frames, serial (non-coop) path, no weightp / AQ / HME.
  * ------------------------------------------------------------------------------------------ */
+#include <vector>
 #include "slicetype.h"
 #include "picyuv.h"
 #include "x265.h"
@@ -331,11 +332,37 @@ struct RefLookahead
     int n;
     PicYuv** pics;
     Lowres** frames;
+    std::vector<Frame*> aqFrames;
 };
 
 extern "C" {
 
+static void* la_create(int width, int height, int nframes, const pixel* const* luma, intptr_t stride, int bframes, int lslices,
+                       int aqMode = 0, const pixel* const* cb = NULL, const pixel* const* cr = NULL, intptr_t strideC = 0);
 void* x265ref_la_create(int width, int height, int nframes, const pixel* const* luma, intptr_t stride, int bframes)
+{
+    return la_create(width, height, nframes, luma, stride, bframes, 0);
+}
+/* the same with cooperative lookahead slices (param.cpp:173 medium = 8, :492 slow = 4; slicetype.cpp:1016-1040 clamps): the
+ * Lookahead gets a ThreadPool with no running workers, so estimateFrameCost takes the cooperative path
+ * (slicetype.cpp:3143-3173) and the calling thread processes every slice itself (tryBondPeers finds no sleeping peer) */
+void* x265ref_la_create_slices(int width, int height, int nframes, const pixel* const* luma, intptr_t stride, int bframes, int lslices)
+{
+    return la_create(width, height, nframes, luma, stride, bframes, lslices);
+}
+/* the same with adaptive quantisation on (param.cpp:268 default aqMode = AUTO_VARIANCE, strength 1.0): every frame is a real
+ * Frame (fenc PicYuv with chroma + Lowres); LookaheadTLD::calcAdaptiveQuantFrame (slicetype.cpp:444-694) fills
+ * Lowres::invQscaleFactor / qpAqOffset / wp_sum / wp_ssd before lowresIntraEstimate, as PreLookaheadGroup::processTasks does
+ * (slicetype.cpp:1390-1397).  4:2:0 chroma planes are needed (acEnergyCu adds the chroma energy). */
+void* x265ref_la_create_aq(int width, int height, int nframes, const pixel* const* luma, const pixel* const* cb, const pixel* const* cr,
+                           intptr_t stride, intptr_t strideC, int bframes, int lslices, int aqMode)
+{
+    return la_create(width, height, nframes, luma, stride, bframes, lslices, aqMode, cb, cr, strideC);
+}
+}
+#include "frame.h"
+static void* la_create(int width, int height, int nframes, const pixel* const* luma, intptr_t stride, int bframes, int lslices,
+                       int aqMode, const pixel* const* cb, const pixel* const* cr, intptr_t strideC)
 {
     ensure_init();
     static bool scales = false;
@@ -345,11 +372,32 @@ void* x265ref_la_create(int width, int height, int nframes, const pixel* const* 
     x265_param_default(p);
     p->sourceWidth = width; p->sourceHeight = height; p->internalCsp = X265_CSP_I420;
     p->bframes = bframes; p->bEnableWeightedPred = 0; p->bEnableWeightedBiPred = 0;
-    p->rc.aqMode = 0; p->rc.cuTree = 0; p->rc.hevcAq = 0; p->bAQMotion = 0; p->lookaheadSlices = 0; p->bEnableHME = 0;
+    p->rc.aqMode = aqMode; p->rc.cuTree = 0; p->rc.hevcAq = 0; p->bAQMotion = 0; p->lookaheadSlices = lslices; p->bEnableHME = 0;
     p->rc.qgSize = 32; p->maxCUSize = 64; p->rc.vbvBufferSize = 0; p->bFrameAdaptive = 0;
     h->param = p; h->n = nframes;
     h->pics = new PicYuv*[nframes]; h->frames = new Lowres*[nframes + 2];
-    for (int i = 0; i < nframes; i++)
+    for (int i = 0; i < nframes && aqMode; i++)
+    {
+        /* AQ path: a real Frame per picture */
+        Frame* fr = new Frame();
+        fr->m_param = p;
+        fr->create(p, NULL);
+        PicYuv* pic = fr->m_fencPic;
+        for (int y = 0; y < height; y++)
+            memcpy(pic->m_picOrg[0] + (intptr_t)y * pic->m_stride, luma[i] + (intptr_t)y * stride, (size_t)width * sizeof(pixel));
+        for (int y = 0; y < height / 2; y++)
+        {
+            memcpy(pic->m_picOrg[1] + (intptr_t)y * pic->m_strideC, cb[i] + (intptr_t)y * strideC, (size_t)(width / 2) * sizeof(pixel));
+            memcpy(pic->m_picOrg[2] + (intptr_t)y * pic->m_strideC, cr[i] + (intptr_t)y * strideC, (size_t)(width / 2) * sizeof(pixel));
+        }
+        extendPicBorder(pic->m_picOrg[0], pic->m_stride, width, height, pic->m_lumaMarginX, pic->m_lumaMarginY);
+        extendPicBorder(pic->m_picOrg[1], pic->m_strideC, width / 2, height / 2, pic->m_chromaMarginX, pic->m_chromaMarginY);
+        extendPicBorder(pic->m_picOrg[2], pic->m_strideC, width / 2, height / 2, pic->m_chromaMarginX, pic->m_chromaMarginY);
+        fr->m_lowres.init(pic, i);
+        h->pics[i] = pic; h->frames[i] = &fr->m_lowres;
+        h->aqFrames.push_back(fr);
+    }
+    for (int i = 0; i < nframes && !aqMode; i++)
     {
         PicYuv* pic = new PicYuv();
         pic->create(p, true, NULL);
@@ -362,13 +410,32 @@ void* x265ref_la_create(int width, int height, int nframes, const pixel* const* 
         lr->init(pic, i);
         h->pics[i] = pic; h->frames[i] = lr;
     }
-    h->la = new Lookahead(p, NULL);
-    h->la->m_tld = new LookaheadTLD[1];
-    h->la->m_tld[0].init(h->la->m_8x8Width, h->la->m_8x8Height, h->la->m_cuCount);
+    ThreadPool* pool = NULL;
+    if (lslices > 0)
+    {
+        pool = new ThreadPool();
+        pool->create(1, 1, 0);                 /* never started: no worker ever sleeps, so no peer can be bonded */
+    }
+    h->la = new Lookahead(p, pool);
+    const int ntld = 1 + (pool ? pool->m_numWorkers : 0);
+    h->la->m_tld = new LookaheadTLD[ntld];
+    for (int t = 0; t < ntld; t++)
+        h->la->m_tld[t].init(h->la->m_8x8Width, h->la->m_8x8Height, h->la->m_cuCount);
     for (int i = 0; i < nframes; i++)
+    {
+        if (aqMode) h->la->m_tld[0].calcAdaptiveQuantFrame(h->aqFrames[i], p);
         h->la->m_tld[0].lowresIntraEstimate(*h->frames[i], p->rc.qgSize);
+    }
     return h;
 }
+extern "C" {
+/* out = {numCoopSlices, numRowsPerSlice} as the Lookahead constructor settled them (slicetype.cpp:1016-1040) */
+void x265ref_la_slices(void* hv, int* out)
+{
+    RefLookahead* h = (RefLookahead*)hv;
+    out[0] = h->la->m_numCoopSlices; out[1] = h->la->m_numRowsPerSlice;
+}
+
 
 int64_t x265ref_la_cost(void* hv, int p0, int p1, int b)
 {
@@ -430,6 +497,13 @@ int x265ref_la_get(void* hv, int frame, int what, int d0, int d1, void* out)
         memcpy(out, f->lowresPlane[d0] - (intptr_t)my * f->lumaStride - mx, sizeof(pixel) * f->lumaStride * (f->lines + 2 * my));
         break;
     }
+    case 8:     /* Lowres::invQscaleFactor as int32 per lowres CU (rc.qgSize 32 -> one per 8x8 lowres CU), 0 words when AQ is off */
+        if (!f->invQscaleFactor) return -1;
+        for (int i = 0; i < ncu; i++) ((int32_t*)out)[i] = f->invQscaleFactor[i];
+        break;
+    case 9:     /* {wp_sum[0], wp_ssd[0]} of luma as calcAdaptiveQuantFrame leaves them */
+        ((uint64_t*)out)[0] = f->wp_sum[0]; ((uint64_t*)out)[1] = f->wp_ssd[0];
+        break;
     default: return -1;
     }
     return 0;

@@ -14,7 +14,7 @@ LOOKAHEAD_LAMBDA = {8: 1.0, 10: 16.0}     # x265_lambda_tab[X265_LOOKAHEAD_QP = 
 class OrcLaJob(C.Structure):
     _fields_ = [("fenc", P * 4), ("ref0", P * 4), ("ref1", P * 4), ("stride", IP), ("w8", I), ("h8", I), ("bidir", I),
                 ("doSearch", I * 2), ("mvs", P * 2), ("mvcosts", P * 2), ("intraCost", P), ("invQscale", P), ("mvcost_tab", P),
-                ("lowresCosts", P), ("rowSatds", P), ("out", C.c_int64 * 3)]
+                ("lowresCosts", P), ("rowSatds", P), ("out", C.c_int64 * 3), ("numSlices", I), ("rowsPerSlice", I)]
 
 
 def lowres_geometry(W, H):
@@ -53,19 +53,21 @@ def make_lowres(O, img, depth):
 
 
 class OracleLookahead:
-    def __init__(self, O, frames, depth, bframes=3):
+    def __init__(self, O, frames, depth, bframes=3, slices=None, invq=None):
         self.O, self.depth = O, depth
+        self.slices = slices              # (numCoopSlices, numRowsPerSlice) or None: cooperative lookahead slices
+        self.invq = invq                  # per frame Lowres::invQscaleFactor (int32 per lowres CU) or None: AQ off
         self.lam = LOOKAHEAD_LAMBDA[depth]
         self.tab = np.zeros(2 * MVRANGE + 1, np.uint16)
         O.orc_mvcost_table(C.c_double(self.lam), MVRANGE, ptr(self.tab))
         self.fr = []
-        for img in frames:
+        for fi, img in enumerate(frames):
             planes, ls, lorg, w8, h8 = make_lowres(O, img, depth)
             ncu = w8 * h8
             f = dict(planes=planes, intraCost=np.zeros(ncu, np.int32), intraMode=np.zeros(ncu, np.uint8),
                      lowresCosts={}, rowSatds={}, costEst={}, mvs={}, mvcosts={}, intraMbs={})
             lc = np.zeros(ncu, np.uint16); rs = np.zeros(h8, np.int32); ce = np.zeros(2, np.int64)
-            O.orc_lowres_intra(ptr(planes[0], lorg), IP(ls), w8, h8, int(self.lam), None, ptr(f["intraCost"]), ptr(f["intraMode"]), ptr(lc), ptr(rs), ptr(ce))
+            O.orc_lowres_intra(ptr(planes[0], lorg), IP(ls), w8, h8, int(self.lam), ptr(invq[fi]) if invq is not None else None, ptr(f["intraCost"]), ptr(f["intraMode"]), ptr(lc), ptr(rs), ptr(ce))
             f["lowresCosts"][(0, 0)] = lc; f["rowSatds"][(0, 0)] = rs; f["costEst"][(0, 0)] = (int(ce[0]), int(ce[1]))
             self.fr.append(f)
         self.stride, self.org, self.w8, self.h8 = ls, lorg, w8, h8
@@ -93,7 +95,10 @@ class OracleLookahead:
             del_key = (1, d1)
             if del_key in f["mvs"] and j.doSearch[1] == 0 and not f["mvs"][del_key].any():
                 pass
-        j.intraCost = f["intraCost"].ctypes.data; j.invQscale = None
+        if self.slices and self.slices[0] > 1 and (p1 > b or j.doSearch[0] or j.doSearch[1]):
+            j.numSlices, j.rowsPerSlice = self.slices         # the cooperative path (slicetype.cpp:3143)
+        j.intraCost = f["intraCost"].ctypes.data
+        j.invQscale = self.invq[b].ctypes.data if self.invq is not None else None
         j.mvcost_tab = self.tab.ctypes.data + MVRANGE * 2
         lc = np.zeros(ncu, np.uint16); rs = np.zeros(self.h8, np.int32)
         j.lowresCosts = lc.ctypes.data; j.rowSatds = rs.ctypes.data

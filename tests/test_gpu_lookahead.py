@@ -95,3 +95,72 @@ def test_lookahead_frame_shards_equal_single(cu, world):
     for la in ranks:
         la.close()
     single.close()
+
+
+@pytest.mark.parametrize("depth,lslices", [(8, 8), (10, 4)])
+def test_lookahead_cooperative_slices_gpu(cu, depth, lslices):
+    """estimateFrameCost with cooperative lookahead slices (presets medium / slow: 8 / 4; slicetype.cpp:3075-3112, 3143-3173):
+    on the device every slice of a triple is its own wavefront job; costs, motion fields, per-CU costs and row sums equal the
+    oracle's slice loop, which tests/test_lookahead_oracle_vs_ref.py pins to the real Lookahead."""
+    from x265_b200.lookahead import Lookahead, coop_slices
+    O = load_oracle(depth)
+    W, H = 1280, 720
+    frames = [gen_luma(W, H, i, bits=depth) for i in range(3)]
+    sl = coop_slices(H, lslices)
+    assert sl[0] > 1
+    orc = OracleLookahead(O, frames, depth, slices=sl)
+    la = Lookahead(cu, W, H, depth, len(frames), lookahead_slices=lslices)
+    for i, img in enumerate(frames):
+        la.init_frame(i, img)
+    la.intra_batch(range(len(frames)))
+    for (p0, p1, b) in [(0, 1, 1), (0, 2, 1), (0, 2, 2)]:
+        a, c = la.cost(p0, p1, b), orc.cost(p0, p1, b)
+        d0, d1 = b - p0, p1 - b
+        r = la.fr[b]["res"][(d0, d1)]
+        assert np.array_equal(la.fr[b]["mvs"][(0, d0)].download(np.int32).reshape(-1, 2), orc.fr[b]["mvs"][(0, d0)]), (p0, p1, b)
+        assert np.array_equal(r["lowresCosts"], orc.fr[b]["lowresCosts"][(d0, d1)]), (p0, p1, b)
+        assert np.array_equal(r["rowSatds"], orc.fr[b]["rowSatds"][(d0, d1)])
+        assert a == c and r["costEstAq"] == orc.fr[b]["costEst"][(d0, d1)][1], ((p0, p1, b), a, c)
+    la.close()
+
+
+@pytest.mark.parametrize("depth,lslices", [(8, 8), (10, 0)])
+def test_lookahead_adaptive_quant_gpu(cu, depth, lslices):
+    """The lookahead as preset medium runs it: adaptive quantisation weights from the REAL calcAdaptiveQuantFrame
+    (oracle/_ref, slicetype.cpp:444-694) uploaded as Lowres::invQscaleFactor; intra estimate and frame costs on the device
+    (costEst, costEstAq, AQ-weighted row sums, with and without cooperative slices) equal the oracle, which
+    tests/test_lookahead_oracle_vs_ref.py::test_lookahead_with_adaptive_quant pins to the reference."""
+    from common import load_ref
+    from frame_helpers import gen_chroma
+    from test_lookahead_oracle_vs_ref import RefLookahead
+    from x265_b200.lookahead import Lookahead, coop_slices
+    R = load_ref(depth)
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    O = load_oracle(depth)
+    W, H = 1280, 720
+    frames = [gen_luma(W, H, i, bits=depth) for i in range(3)]
+    chroma = [(gen_chroma(W, H, i, 1, bits=depth), gen_chroma(W, H, i, 2, bits=depth)) for i in range(3)]
+    ref = RefLookahead(R, frames, lslices=lslices, aq=2, chroma=chroma)
+    invq = [ref.get(i, 8) for i in range(3)]
+    assert any((q != 256).any() for q in invq)
+    sl = coop_slices(H, lslices)
+    orc = OracleLookahead(O, frames, depth, slices=sl if sl[0] > 1 else None, invq=invq)
+    la = Lookahead(cu, W, H, depth, len(frames), lookahead_slices=lslices)
+    for i, img in enumerate(frames):
+        la.init_frame(i, img)
+        la.set_invqscale(i, invq[i])
+    la.intra_batch(range(len(frames)))
+    for i in range(3):
+        assert np.array_equal(la.fr[i]["intraCost"].download(np.int32), orc.fr[i]["intraCost"])
+        assert np.array_equal(la.fr[i]["rs0"].download(np.int32), orc.fr[i]["rowSatds"][(0, 0)])
+        assert tuple(int(x) for x in la.fr[i]["out0"].download(np.int64)) == orc.fr[i]["costEst"][(0, 0)]
+    for (p0, p1, b) in [(0, 1, 1), (0, 2, 1), (0, 2, 2)]:
+        a, c = la.cost(p0, p1, b), orc.cost(p0, p1, b)
+        d0, d1 = b - p0, p1 - b
+        r = la.fr[b]["res"][(d0, d1)]
+        assert a == c == ref.cost(p0, p1, b), (p0, p1, b)
+        assert r["costEstAq"] == orc.fr[b]["costEst"][(d0, d1)][1]
+        assert np.array_equal(r["rowSatds"], orc.fr[b]["rowSatds"][(d0, d1)])
+        assert np.array_equal(r["lowresCosts"], orc.fr[b]["lowresCosts"][(d0, d1)])
+    la.close()

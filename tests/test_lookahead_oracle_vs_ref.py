@@ -14,7 +14,7 @@ TRIPLES = [(0, 1, 1), (0, 2, 1), (0, 2, 2), (0, 3, 1), (0, 3, 2), (0, 3, 3), (1,
 
 
 class RefLookahead:
-    def __init__(self, R, frames, bframes=3):
+    def __init__(self, R, frames, bframes=3, lslices=0, aq=0, chroma=None):
         self.R = R
         H, W = frames[0].shape
         self.keep = [np.ascontiguousarray(f) for f in frames]
@@ -22,7 +22,24 @@ class RefLookahead:
         R.x265ref_la_create.restype = P; R.x265ref_la_create.argtypes = [I, I, I, P, IP, I]
         R.x265ref_la_cost.restype = C.c_int64; R.x265ref_la_cost.argtypes = [P, I, I, I]
         R.x265ref_la_get.argtypes = [P, I, I, I, I, P]; R.x265ref_la_geometry.argtypes = [P, P]
-        self.h = R.x265ref_la_create(W, H, len(frames), arr, W, bframes)
+        self.slices = None
+        if aq:
+            # adaptive quantisation on: real Frame objects, calcAdaptiveQuantFrame before lowresIntraEstimate
+            cbs = [np.ascontiguousarray(c[0]) for c in chroma]; crs = [np.ascontiguousarray(c[1]) for c in chroma]
+            self.keep += cbs + crs
+            acb = (P * len(frames))(*[C.c_void_p(f.ctypes.data) for f in cbs]); acr = (P * len(frames))(*[C.c_void_p(f.ctypes.data) for f in crs])
+            R.x265ref_la_create_aq.restype = P; R.x265ref_la_create_aq.argtypes = [I, I, I, P, P, P, IP, IP, I, I, I]
+            self.h = R.x265ref_la_create_aq(W, H, len(frames), arr, acb, acr, W, W // 2, bframes, lslices, aq)
+            if lslices:
+                sl = np.zeros(2, np.int32); R.x265ref_la_slices.argtypes = [P, P]; R.x265ref_la_slices(self.h, ptr(sl))
+                self.slices = (int(sl[0]), int(sl[1])) if sl[0] > 1 else None
+        elif lslices:
+            R.x265ref_la_create_slices.restype = P; R.x265ref_la_create_slices.argtypes = [I, I, I, P, IP, I, I]
+            self.h = R.x265ref_la_create_slices(W, H, len(frames), arr, W, bframes, lslices)
+            sl = np.zeros(2, np.int32); R.x265ref_la_slices.argtypes = [P, P]; R.x265ref_la_slices(self.h, ptr(sl))
+            self.slices = (int(sl[0]), int(sl[1]))
+        else:
+            self.h = R.x265ref_la_create(W, H, len(frames), arr, W, bframes)
         g = np.zeros(7, np.int32); R.x265ref_la_geometry(self.h, ptr(g))
         self.w8, self.h8, self.stride, self.lw, self.lh = [int(x) for x in g[:5]]
         self.ncu = self.w8 * self.h8
@@ -72,6 +89,64 @@ def test_lookahead(depth, size, noise):
         st = ref.get(b, 6, d0, d1, np.int64, 3)
         assert (int(st[0]), int(st[1])) == orc.fr[b]["costEst"][(d0, d1)]
         assert int(st[2]) == orc.fr[b]["intraMbs"].get(d0, 0)
+
+
+@pytest.mark.parametrize("depth,lslices", [(8, 4), (8, 8), (10, 4)])
+def test_lookahead_cooperative_slices(depth, lslices):
+    """estimateFrameCost as presets medium / slow run it (param.cpp:173 lookaheadSlices 8, :492 slow 4): the cooperative-slice
+    path (slicetype.cpp:3075-3112, 3143-3173) of the REAL Lookahead (a pool without running workers: the caller processes
+    every slice) against the oracle's slice loop -- frame costs, per-CU costs, row sums and motion fields."""
+    R = load_ref(depth)
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    O = load_oracle(depth)
+    W, H = 1280, 720                                  # slices need a source height >= 720 (slicetype.cpp:1022-1026)
+    frames = [gen_luma(W, H, i, bits=depth) for i in range(3)]
+    ref = RefLookahead(R, frames, lslices=lslices)
+    assert ref.slices[0] > 1, ref.slices
+    orc = OracleLookahead(O, frames, depth, slices=ref.slices)
+    for (p0, p1, b) in [(0, 1, 1), (0, 2, 1), (0, 2, 2)]:
+        a, c = ref.cost(p0, p1, b), orc.cost(p0, p1, b)
+        d0, d1 = b - p0, p1 - b
+        assert np.array_equal(ref.get(b, 4, 0, d0, np.int32, 2 * ref.ncu).reshape(-1, 2), orc.fr[b]["mvs"][(0, d0)]), (p0, p1, b)
+        assert np.array_equal(ref.get(b, 2, d0, d1, np.uint16), orc.fr[b]["lowresCosts"][(d0, d1)]), (p0, p1, b)
+        assert np.array_equal(ref.get(b, 3, d0, d1, np.int32, ref.h8), orc.fr[b]["rowSatds"][(d0, d1)])
+        assert a == c, ((p0, p1, b), a, c)
+    # and the slices change the result (otherwise the test would not see them): serial path on the same frames
+    ser = OracleLookahead(O, frames, depth)
+    assert any(ser.cost(*t) != orc.cost(*t) or not np.array_equal(ser.fr[t[2]]["mvs"][(0, t[2] - t[0])], orc.fr[t[2]]["mvs"][(0, t[2] - t[0])])
+               for t in [(0, 1, 1), (0, 2, 2)])
+
+
+@pytest.mark.parametrize("depth,lslices", [(8, 0), (8, 8), (10, 4)])
+def test_lookahead_with_adaptive_quant(depth, lslices):
+    """The lookahead as preset medium runs it (aqMode AUTO_VARIANCE, param.cpp:268): Lowres::invQscaleFactor comes from the
+    REAL calcAdaptiveQuantFrame (slicetype.cpp:444-694, real Frame objects with 4:2:0 chroma); with it as input the oracle's
+    intra and frame-cost paths must reproduce costEstAq, the AQ-weighted row sums and the frame costs of the reference."""
+    from frame_helpers import gen_chroma
+    R = load_ref(depth)
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    O = load_oracle(depth)
+    W, H = 1280, 720
+    frames = [gen_luma(W, H, i, bits=depth) for i in range(3)]
+    chroma = [(gen_chroma(W, H, i, 1, bits=depth), gen_chroma(W, H, i, 2, bits=depth)) for i in range(3)]
+    ref = RefLookahead(R, frames, lslices=lslices, aq=2, chroma=chroma)
+    invq = [ref.get(i, 8) for i in range(3)]
+    assert any((q != 256).any() for q in invq), "AQ produced no offsets: the test would not see invQscale"
+    orc = OracleLookahead(O, frames, depth, slices=ref.slices, invq=invq)
+    for f in range(3):
+        assert np.array_equal(ref.get(f, 0), orc.fr[f]["intraCost"])
+        assert np.array_equal(ref.get(f, 3, 0, 0, np.int32, ref.h8), orc.fr[f]["rowSatds"][(0, 0)])
+        st = ref.get(f, 6, 0, 0, np.int64, 3)
+        assert (int(st[0]), int(st[1])) == orc.fr[f]["costEst"][(0, 0)]
+    for (p0, p1, b) in [(0, 1, 1), (0, 2, 1), (0, 2, 2)]:
+        a, c = ref.cost(p0, p1, b), orc.cost(p0, p1, b)
+        d0, d1 = b - p0, p1 - b
+        assert a == c, ((p0, p1, b), a, c)
+        assert np.array_equal(ref.get(b, 3, d0, d1, np.int32, ref.h8), orc.fr[b]["rowSatds"][(d0, d1)])
+        st = ref.get(b, 6, d0, d1, np.int64, 3)
+        assert (int(st[0]), int(st[1])) == orc.fr[b]["costEst"][(d0, d1)], (p0, p1, b)
 
 
 def _wp_stats(img):

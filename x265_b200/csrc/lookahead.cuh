@@ -134,24 +134,27 @@ __global__ void __launch_bounds__(LA_WARPS * 32, 1) k_lookahead_cost(const x265c
     const int lane = threadIdx.x & 31, warp = (int)crank * LA_WARPS + (threadIdx.x >> 5);      // warp index inside the cluster
     const int nwarps = (int)csize * LA_WARPS;
     MeShared* sm = (MeShared*)la_smem + (threadIdx.x >> 5);
+    // Cooperative slices (CostEstimateGroup::processTasks, slicetype.cpp:3075-3112; estimateFrameCost :3143-3173): a job may
+    // cover only the CU rows [y0, y1) of the frame; its bottom row is the slice's `lastRow` (no MV predictors from below),
+    // the rows' costs accumulate into the SAME frame totals (jb.out, zeroed by x265cu_lookahead_cost_batch before the launch).
+    // rows == 0: the whole frame (the serial path, :3178-3196).  Slices of one triple are independent wavefronts.
+    const int y0 = jb.rows ? (jb.rows & 0xffff) : 0, y1 = jb.rows ? ((jb.rows >> 16) & 0xffff) : h8;
+    const int hs = y1 - y0;
     if (crank == 0)
-    {
-        for (int i = threadIdx.x; i < h8; i += blockDim.x) jb.rowSatds[i] = 0;
-        if (threadIdx.x < 3) jb.out[threadIdx.x] = 0;
-    }
-    const int ndiag = (w8 - 1) + 2 * (h8 - 1) + 1;
+        for (int i = y0 + threadIdx.x; i < y1; i += blockDim.x) jb.rowSatds[i] = 0;
+    const int ndiag = (w8 - 1) + 2 * (hs - 1) + 1;
     for (int t = 0; t < ndiag; t++)
     {
         // MVs / costs of the previous diagonals are visible to every CTA of the cluster
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-        // CUs on this diagonal: k = 0.. with cuY = h8-1-k, cuX = w8-1-(t-2k)
-        const int kmin = max(0, (t - (w8 - 1) + 1) >> 1), kmax = min(h8 - 1, t >> 1);
+        // CUs on this diagonal: k = 0.. with cuY = y1-1-k, cuX = w8-1-(t-2k)
+        const int kmin = max(0, (t - (w8 - 1) + 1) >> 1), kmax = min(hs - 1, t >> 1);
         for (int k = kmin + warp; k <= kmax; k += nwarps)
         {
-            const int cuY = h8 - 1 - k, cuX = w8 - 1 - (t - 2 * k);
+            const int cuY = y1 - 1 - k, cuX = w8 - 1 - (t - 2 * k);
             if (cuX < 0 || cuX >= w8) continue;
             const int cuXY = cuX + cuY * w8;
-            const bool lastRow = (cuY == h8 - 1);
+            const bool lastRow = (cuY == y1 - 1);
             const int off = 8 * cuX + 8 * cuY * stride;
             x265cu_me_job mj;
             mj.offset = off; mj.ref = 0; mj.pw = 8; mj.ph = 8;

@@ -1021,37 +1021,54 @@ __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* _
 
 // Cb + Cr chroma SATD of the candidates of a burst: lane k (k < n, bit k of `need` set) receives candidate k's cost.
 // chromaSatd is the luma SATD primitive of the chroma-sized block (primitives.cpp:139-158): 8x4 tiles when the chroma
-// width is a multiple of 8, else 4x4 tiles, each tile halved on its own (pixel.cpp:210-297, 1131-1155).  One candidate
-// at a time, the (plane, tile) pairs over the lanes, one REDUX per candidate.
+// width is a multiple of 8, else 4x4 tiles, each tile halved on its own (pixel.cpp:210-297, 1131-1155).
+// Work items = (needed candidate, plane, tile), candidate-major, spread over the lanes 32 at a time: an 8x8 PU (one 4x4
+// tile per plane) evaluates the 8 directions of a refinement round in ONE pass of 16 lanes instead of 8 passes of 2; the
+// per-candidate sums are one REDUX each.  Lanes of different candidates run the tile function with their own fractional
+// phase (its branches serialise per phase class, not per candidate).
 template <typename P>
 __device__ __forceinline__ int me_chroma_batch(const MeCtx<P>& c, const MeChromaCtx<P>& cc, int n, int qx, int qy, unsigned need)
 {
     const int cw = c.w >> 1, chh = c.h >> 1;
     const int tw = (cw & 7) ? 4 : 8;
     const int tpr = cw / tw, nt = tpr * (chh >> 2);                 // tiles per row / per plane
+    const int ipc = 2 * nt;                                        // items per candidate
+    if (n < 32) need &= (1u << n) - 1u;
+    const int nneed = __popc(need);
+    const int total = nneed * ipc;
     int out = 0;
-    for (int k = 0; k < n; k++)
+    for (int base = 0; base < total; base += 32)
     {
-        if (!((need >> k) & 1u)) continue;                         // warp-uniform
-        const int kqx = __shfl_sync(0xffffffffu, qx, k), kqy = __shfl_sync(0xffffffffu, qy, k);
-        const int xf = kqx & 7, yf = kqy & 7;
-        const ptrdiff_t roff = (kqx >> 3) + (ptrdiff_t)(kqy >> 3) * cc.cstride;
-        int part = 0;
-        for (int t = c.lane; t < 2 * nt; t += 32)
+        const int it = base + c.lane;
+        const bool live = it < total;
+        const int ci = live ? it / ipc : 0;
+        const int rem = it - ci * ipc;
+        const int k = (int)__fns(need, 0, ci + 1);                   // the ci-th needed candidate
+        const int kqx = __shfl_sync(0xffffffffu, qx, k & 31), kqy = __shfl_sync(0xffffffffu, qy, k & 31);
+        int v = 0;
+        if (live)
         {
-            const bool cr = t >= nt;
-            const int tt = cr ? t - nt : t;
+            const bool cr = rem >= nt;
+            const int tt = cr ? rem - nt : rem;
             const int ty = tt / tpr, tx = tt - ty * tpr;
+            const int xf = kqx & 7, yf = kqy & 7;
+            const ptrdiff_t roff = (kqx >> 3) + (ptrdiff_t)(kqy >> 3) * cc.cstride;
             const ptrdiff_t o = (ptrdiff_t)(ty * 4) * cc.cstride + tx * tw;
             const P* f = (cr ? cc.fcr : cc.fcb) + o;
             const P* r = (cr ? cc.rcr : cc.rcb) + o + roff;
-            int v = me_chroma_had4x4<P>(f, r, cc.cstride, xf, yf);
+            v = me_chroma_had4x4<P>(f, r, cc.cstride, xf, yf);
             if (tw == 8) v += me_chroma_had4x4<P>(f + 4, r + 4, cc.cstride, xf, yf);
-            part += v >> 1;
+            v >>= 1;
         }
         __syncwarp();
-        const int tot = __reduce_add_sync(0xffffffffu, part);
-        if (c.lane == k) out = tot;
+        // candidates present in this chunk: ci in [base / ipc, (base + 31) / ipc]
+        const int c0 = base / ipc, c1 = min(nneed - 1, (base + 31) / ipc);
+        for (int q = c0; q <= c1; q++)
+        {
+            const int tot = __reduce_add_sync(0xffffffffu, (live && ci == q) ? v : 0);
+            const int kq = (int)__fns(need, 0, q + 1);
+            if (c.lane == kq) out += tot;
+        }
     }
     return out;
 }

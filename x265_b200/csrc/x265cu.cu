@@ -297,10 +297,21 @@ int x265cu_lowres_intra_batch(x265cu_ctx* c, int depth, const x265cu_la_intra_jo
     return 0;
 }
 
+// frame totals of every triple of the batch: zeroed once before the launch (the slices of a triple accumulate into them)
+__global__ void k_la_zero_out(const x265cu_la_job* jobs, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const x265cu_la_job jb = jobs[i];
+    if (jb.rows == 0 || (jb.rows & 0xffff) == 0) { jb.out[0] = 0; jb.out[1] = 0; jb.out[2] = 0; }
+}
+
 int x265cu_lookahead_cost_batch(x265cu_ctx* c, int depth, const x265cu_la_job* jobs, int n, int stride, int w8, int h8, const uint16_t* mvcost)
 {
     cudaSetDevice(c->device);
     if (n <= 0) return 0;
+    k_la_zero_out<<<(n + 127) / 128, 128, 0, c->stream>>>(jobs, n);
+    CU_LAUNCH_CHECK(c);
     const size_t smem = sizeof(MeShared) * LA_WARPS;
     // cluster size: enough CTAs (of LA_WARPS warps) for the longest anti-diagonal in one round, at most 4
     const int maxdiag = h8 < (w8 + 1) / 2 ? h8 : (w8 + 1) / 2;

@@ -240,7 +240,7 @@ LA_INTRA_JOB = np.dtype([("plane0", "<u8"), ("invQscale", "<u8"), ("intraCost", 
                          ("rowSatds", "<u8"), ("out", "<u8")], align=True)
 LA_JOB = np.dtype([("fenc", "<u8", 4), ("ref0", "<u8", 4), ("ref1", "<u8", 4), ("mvs", "<u8", 2), ("mvcosts", "<u8", 2), ("intraCost", "<u8"),
                    ("invQscale", "<u8"), ("lowresCosts", "<u8"), ("rowSatds", "<u8"), ("out", "<u8"), ("bidir", "<i4"), ("doSearch0", "<i4"),
-                   ("doSearch1", "<i4"), ("pad", "<i4")], align=True)
+                   ("doSearch1", "<i4"), ("rows", "<i4")], align=True)
 assert LA_INTRA_JOB.itemsize == 56 and LA_JOB.itemsize == 184
 
 

@@ -39,6 +39,16 @@ def full_plane(img, depth):
     return buf, stride, MARGIN_Y * stride + MARGIN_X
 
 
+def coop_slices(H, lookahead_slices):
+    """(numCoopSlices, numRowsPerSlice) as the Lookahead constructor settles them (slicetype.cpp:1016-1040): slices need a
+    source height >= 720, at least 10 CU rows each; presets medium / slow ask for 8 / 4 (param.cpp:173, 492)."""
+    h8 = ((H // 2) + 7) >> 3
+    if lookahead_slices <= 1 or H < 720:
+        return 1, h8
+    rows = min(max(h8 // lookahead_slices, 10), h8)
+    return h8 // rows, rows
+
+
 def owner(poc, world):
     """Rank that owns lookahead frame `poc` (its lowres planes, intra costs and every estimate with b == poc)."""
     return poc % world
@@ -61,8 +71,9 @@ class _PlaneView:
 class Lookahead:
     """Device-resident lookahead window of `nframes` frames of one geometry."""
 
-    def __init__(self, lib, W, H, depth, nframes):
+    def __init__(self, lib, W, H, depth, nframes, lookahead_slices=0):
         self.cu, self.depth, self.W, self.H, self.n = lib, depth, W, H, nframes
+        self.nslices, self.rows_per_slice = coop_slices(H, lookahead_slices)
         self.w8, self.h8, self.ls = lowres_geometry(W, H)
         self.ncu = self.w8 * self.h8
         self.es = 1 if depth == 8 else 2
@@ -76,7 +87,7 @@ class Lookahead:
             planes = [_PlaneView(block, k * self.plane_bytes, self.plane_bytes) for k in range(4)]
             self.fr.append(dict(block=block, planes=planes, intraCost=lib.alloc(4 * self.ncu), intraMode=lib.alloc(self.ncu),
                                 lc0=lib.alloc(2 * self.ncu), rs0=lib.alloc(4 * self.h8), out0=lib.alloc(16), mvs={}, mvcosts={}, res={},
-                                has_planes=False, has_intra=False))
+                                has_planes=False, has_intra=False, invq=None))
         self.tab = lib.to_device(lib.mvcost_table(LOOKAHEAD_LAMBDA[depth], MVRANGE))
         self._full = None
         lib.sync()
@@ -93,6 +104,16 @@ class Lookahead:
                                                *[p.ptr + self.lorg for p in f["planes"]], self.ls, self.w8 * 8, self.h8 * 8, MARGIN_X, MARGIN_Y))
         cu.sync()
         f["has_planes"] = True
+
+    def set_invqscale(self, i, invq):
+        """Lowres::invQscaleFactor of frame i (int32 per lowres CU, 256 = 1.0): the adaptive-quantisation weights that
+        calcAdaptiveQuantFrame (slicetype.cpp:444-694, host float math) produced; costEstAq and the row sums use them."""
+        a = np.ascontiguousarray(invq, np.int32)
+        assert a.size == self.ncu
+        f = self.fr[i]
+        if f["invq"] is None:
+            f["invq"] = self.cu.alloc(4 * self.ncu)
+        f["invq"].upload(a)
 
     def plane_block(self, i):
         """(device pointer, bytes) of frame i's 4 planes: what its owner broadcasts."""
@@ -114,7 +135,7 @@ class Lookahead:
             f = self.fr[i]
             assert f["has_planes"], "frame %d has no lowres planes on this rank" % i
             j = jobs[n]
-            j["plane0"] = f["planes"][0].ptr + self.lorg; j["invQscale"] = 0; j["intraCost"] = f["intraCost"].ptr; j["intraMode"] = f["intraMode"].ptr
+            j["plane0"] = f["planes"][0].ptr + self.lorg; j["invQscale"] = f["invq"].ptr if f["invq"] is not None else 0; j["intraCost"] = f["intraCost"].ptr; j["intraMode"] = f["intraMode"].ptr
             j["lowresCosts"] = f["lc0"].ptr; j["rowSatds"] = f["rs0"].ptr; j["out"] = f["out0"].ptr
         d_jobs = cu.to_device(jobs)
         cu.check(cu.L.x265cu_lowres_intra_batch(cu.ctx, self.depth, d_jobs.ptr, len(ids), self.ls, self.w8, self.h8, int(LOOKAHEAD_LAMBDA[self.depth])))
@@ -132,13 +153,13 @@ class Lookahead:
         from .lib import LA_JOB
         cu = self.cu
         todo = [t for t in triples if (t[2] - t[0], t[1] - t[2]) not in self.fr[t[2]]["res"]]
-        jobs = np.zeros(max(len(todo), 1), LA_JOB)
+        recs = []
         bufs = []
-        for n, (p0, p1, b) in enumerate(todo):
+        for (p0, p1, b) in todo:
             f = self.fr[b]
             assert f["has_intra"] and self.fr[p0]["has_planes"] and self.fr[p1]["has_planes"], (p0, p1, b)
             d0, d1 = b - p0, p1 - b
-            j = jobs[n]
+            j = np.zeros(1, LA_JOB)[0]
             for k in range(4):
                 j["fenc"][k] = f["planes"][k].ptr + self.lorg
                 j["ref0"][k] = self.fr[p0]["planes"][k].ptr + self.lorg
@@ -154,15 +175,25 @@ class Lookahead:
                 j["mvs"][lst] = f["mvs"][(lst, dist)].ptr; j["mvcosts"][lst] = f["mvcosts"][(lst, dist)].ptr
             lc, rs, out = cu.alloc(2 * self.ncu), cu.alloc(4 * self.h8), cu.alloc(24)
             bufs.append((lc, rs, out))
-            j["intraCost"] = f["intraCost"].ptr; j["invQscale"] = 0; j["lowresCosts"] = lc.ptr; j["rowSatds"] = rs.ptr; j["out"] = out.ptr
+            j["intraCost"] = f["intraCost"].ptr; j["invQscale"] = f["invq"].ptr if f["invq"] is not None else 0; j["lowresCosts"] = lc.ptr; j["rowSatds"] = rs.ptr; j["out"] = out.ptr
+            # cooperative slices (slicetype.cpp:3143): one job per slice, each an independent wavefront over its CU rows
+            if self.nslices > 1 and (p1 > b or j["doSearch0"] or j["doSearch1"]):
+                for sl in range(self.nslices):
+                    y0 = self.rows_per_slice * sl
+                    y1 = self.h8 if sl == self.nslices - 1 else self.rows_per_slice * (sl + 1)
+                    js = j.copy(); js["rows"] = y0 | (y1 << 16)
+                    recs.append(js)
+            else:
+                recs.append(j)
+        jobs = np.array(recs, LA_JOB) if recs else np.zeros(1, LA_JOB)
         d_j = cu.to_device(jobs) if todo else None
-        return dict(todo=todo, bufs=bufs, d_jobs=d_j)
+        return dict(todo=todo, bufs=bufs, d_jobs=d_j, njobs=len(recs))
 
     def launch_batch(self, prep):
         """ONE kernel launch for all prepared triples (asynchronous on the context's stream)."""
         cu = self.cu
         if prep["todo"]:
-            cu.check(cu.L.x265cu_lookahead_cost_batch(cu.ctx, self.depth, prep["d_jobs"].ptr, len(prep["todo"]), self.ls, self.w8, self.h8,
+            cu.check(cu.L.x265cu_lookahead_cost_batch(cu.ctx, self.depth, prep["d_jobs"].ptr, prep["njobs"], self.ls, self.w8, self.h8,
                                                       self.tab.ptr + 2 * MVRANGE))
 
     def collect_batch(self, prep, full=True):
@@ -201,6 +232,8 @@ class Lookahead:
         for f in self.fr:
             for k in ("block", "intraCost", "intraMode", "lc0", "rs0", "out0"):
                 f[k].free()
+            if f["invq"] is not None:
+                f["invq"].free()
         self.tab.free()
         if self._full is not None:
             self._full.free()
