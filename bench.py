@@ -48,7 +48,7 @@ CONFIGS = {
                label="3840x2160 10-bit Main10 preset slower: 5 refs, subme 4, rect + AMP PUs, chroma-SATD on (BASELINE configs[3] analysis part)"),
     "c5": dict(W=7680, H=4320, depth=10, refs=5, method=3, subme=4, merange=57, rect=1, amp=1, chroma=True, qp=30,
                label="7680x4320 10-bit preset veryslow: 5 refs, subme 4, rect + AMP PUs, chroma-SATD on (BASELINE configs[4])"),
-    "c2": dict(W=1920, H=1080, depth=8, frames=20, bframes=4, lookahead=True,
+    "c2": dict(W=1920, H=1080, depth=8, frames=20, bframes=4, lookahead=True, lslices=0,
                label="1920x1080 8-bit preset medium lookahead: Lowres init + lowresIntraEstimate + estimateFrameCost (HEX, subme 1 lowres) on device (BASELINE configs[1])"),
 }
 CFG = None          # the selected config dict (set in main)
@@ -542,7 +542,15 @@ def run_lookahead_ours(args, rank, world, local_rank):
     lib = x265_b200.load(local_rank)
     frames = lookahead_frames()
     n = len(frames)
-    la = Lookahead(lib, c["W"], c["H"], c["depth"], n)
+    # pinned host copies: what the caller (the encoder's input queue) hands over; H2D is then real asynchronous DMA
+    pinned = []
+    for f in frames:
+        p = lib.L.x265cu_host_alloc(f.nbytes)
+        a = np.frombuffer((C.c_uint8 * f.nbytes).from_address(p), f.dtype).reshape(f.shape)
+        a[:] = f
+        pinned.append(a)
+    frames = pinned
+    la = Lookahead(lib, c["W"], c["H"], c["depth"], n, lookahead_slices=c.get("lslices", 0))
     triples = window_triples(n, c["bframes"])
     mine = [t for t in triples if owner(t[2], world) == rank]
     batches = conflict_free_batches(mine)
@@ -566,7 +574,7 @@ def run_lookahead_ours(args, rank, world, local_rank):
             f["has_intra"] = False
         own = [i for i in range(n) if owner(i, world) == rank]
         for i in own:
-            la.init_frame(i, frames[i])            # H2D of the full-res luma + Lowres::init
+            la.init_frame(i, frames[i], sync=False)   # H2D of the full-res luma + border extension + Lowres::init, stream-ordered
         publish()
         la.intra_batch(own)
         preps = [la.prepare_batch(b) for b in batches]

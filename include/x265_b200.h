@@ -45,6 +45,8 @@ void  x265cu_host_free(void* p);
 int  x265cu_h2d(x265cu_ctx*, void* dev, const void* host, size_t bytes);   /* async on ctx stream */
 int  x265cu_d2h(x265cu_ctx*, void* host, const void* dev, size_t bytes);   /* async on ctx stream */
 int  x265cu_memset(x265cu_ctx*, void* dev, int value, size_t bytes);
+/* strided 2-D copy on the context's stream (asynchronous): kind 0 = host->device, 1 = device->host, 2 = device->device */
+int  x265cu_copy2d(x265cu_ctx*, void* dst, size_t dpitch, const void* src, size_t spitch, size_t widthBytes, size_t rows, int kind);
 /* timing on the ctx stream (cudaEvent): returns ms between begin/end, <0 on error */
 int  x265cu_timer_begin(x265cu_ctx*);
 float x265cu_timer_end(x265cu_ctx*);
@@ -252,6 +254,12 @@ typedef struct {
 } x265cu_la_job;
 int x265cu_lookahead_cost_batch(x265cu_ctx*, int depth, const x265cu_la_job* jobs_dev, int n, int stride, int w8, int h8,
                                 const uint16_t* mvcost_dev /* centred table base, lambda of X265_LOOKAHEAD_QP */);
+
+/* cuTree: estimateCUPropagateCost (common/pixel.cpp:914-940; EncoderPrimitives::propagateCost, primitives.h:212, 356) over
+ * `len` lowres CUs -- a whole frame in one launch instead of one call per CU row (slicetype.cpp:2654-2664).  Device arrays;
+ * fpsFactor as the reference passes it (slicetype.cpp:2652).  Double precision, bit-exact to the C primitive. */
+int x265cu_propagate_cost_batch(x265cu_ctx*, int* dst_dev, const uint16_t* propagateIn_dev, const int32_t* intraCosts_dev,
+                                const uint16_t* interCosts_dev, const int32_t* invQscales_dev, double fpsFactor, int64_t len);
 
 /* Lookahead weighted-prediction analysis: LookaheadTLD::weightsAnalyse + weightCostLuma (slicetype.cpp:807-840, 860-961), the
  * call estimateFrameCost makes before the L0 search when --weightp is on (slicetype.cpp:3137).  Planes are whole padded

@@ -95,6 +95,8 @@ uint32_t orc_nquant(const int16_t* coef, const int32_t* quantCoeff, int16_t* qCo
 void orc_dequant_normal(const int16_t* q, int16_t* coef, int num, int scale, int shift);
 void orc_dequant_scaling(const int16_t* q, const int32_t* dq, int16_t* coef, int num, int per, int shift);
 void orc_denoise_dct(int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, int numCoeff);
+void orc_propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts,
+                        const int32_t* invQscales, const double* fpsFactor, int len);
 
 /* ---- intra (intrapred.cpp:31-234); srcPix = [topLeft, top 2N, left 2N] ---- */
 void orc_intra_filter(const pixel* samples, pixel* filtered, int n);

@@ -321,3 +321,21 @@ int orc_la_weights_analyse(const pixel* fencBuf, const pixel* const* refBuf, pix
     wpOut[0] = minscale; wpOut[1] = mindenom; wpOut[2] = minoff;
     return 1;
 }
+
+/* cuTree: estimateCUPropagateCost (common/pixel.cpp:914-940): plain double arithmetic, `(int)` conversion of the host. */
+void orc_propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts,
+                        const int32_t* invQscales, const double* fpsFactor, int len)
+{
+    const double fps = *fpsFactor / 256;
+    for (int i = 0; i < len; i++)
+    {
+        const int intraCost = intraCosts[i];
+        const int inter = interCosts[i] & LOWRES_COST_MASK;
+        const int interCost = intraCost < inter ? intraCost : inter;
+        const double propagateIntra = (double)intraCost * invQscales[i];
+        const double propagateAmount = (double)propagateIn[i] + propagateIntra * fps;
+        const double propagateNum = (double)(intraCost - interCost);
+        const double propagateDenom = (double)intraCost;
+        dst[i] = (int)(propagateAmount * propagateNum / propagateDenom + 0.5);
+    }
+}

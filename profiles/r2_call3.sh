@@ -1,0 +1,22 @@
+#!/bin/bash
+# Round 2, GPU call 3: LDS.32 row loads, prefix-sum maps, shared first star round, chroma batch over lanes, lookahead slices / AQ / propagateCost.
+mkdir -p gpurun_out
+(time timeout 900 python -m pytest tests -m gpu -q --maxfail=12 -x -k "frame or window or me_batch") > gpurun_out/t_frame.log 2>&1
+tail -n 12 gpurun_out/t_frame.log
+(time timeout 900 python -m pytest tests -m gpu -q --maxfail=12 -k "not frame and not window and not me_batch") > gpurun_out/t_rest.log 2>&1
+tail -n 12 gpurun_out/t_rest.log
+timeout 300 python bench.py --steps 5 --warmup 3 --cpu-seconds 15 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "bench c3 rc=$?"
+timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu --no-chroma > gpurun_out/bench_c3_luma.json 2> gpurun_out/bench_c3_luma.err
+timeout 300 python bench.py --config c2 --steps 3 --warmup 2 --cpu-seconds 10 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench c2 rc=$?"
+for f in c3 c3_luma c2; do python - "$f" <<'P'
+import json, sys
+try:
+    d = json.load(open("gpurun_out/bench_%s.json" % sys.argv[1])); print(sys.argv[1], round(d["value"]), "e2e", round(d["e2e"]["value"]), d.get("stages_ms"), d.get("checks_equal"), d.get("cpu_baseline", {}).get("value"))
+except Exception as e:
+    print(sys.argv[1], "failed", e)
+P
+done
+tail -n 5 gpurun_out/bench_c3.err gpurun_out/bench_c2.err
+M=gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active,sm__icc_request_hit_rate.pct,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed
+timeout 300 ncu --metrics $M --clock-control none -k regex:k_me -c 9 --csv --log-file gpurun_out/me_launches_r2c.csv python profiles/run_small.py 1920 1088 1 1 > gpurun_out/me_launches_r2c.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_me_window -c 3 -o gpurun_out/mew_r2c python profiles/run_small.py 1920 1088 1 1 > gpurun_out/mew_ncu.log 2>&1

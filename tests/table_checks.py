@@ -327,6 +327,18 @@ def check_transforms(get, O, depth, kind):
             get("denoiseDct", None, [P, P, P, I])(ptr(c1), ptr(rs1), ptr(off), num)
             O.orc_denoise_dct(ptr(c2), ptr(rs2), ptr(off), num)
             assert np.array_equal(c1, c2) and np.array_equal(rs1, rs2)
+    # cuTree propagateCost (pixel.cpp:914-940): double arithmetic, incl. the degenerate intraCost == 0 entries (0/0 -> INT_MIN)
+    for it in range(3):
+        n = int(rng.integers(16, 400))
+        pin = rng.integers(0, 65536, n).astype(np.uint16); intra = rng.integers(0 if it else 1, 1 << 15, n).astype(np.int32)
+        inter = rng.integers(0, 65536, n).astype(np.uint16); invq = rng.integers(1, 1024, n).astype(np.int32)
+        if kind == "max":
+            intra[:] = (1 << 15) - 1; pin[:] = 65535
+        fps = np.array([256.0 * (0.01 + 0.33 * it)], np.float64)
+        d1 = np.full(n, -3, np.int32); d2 = np.full(n, -3, np.int32)
+        get("propagateCost", None, [P, P, P, P, P, P, I])(ptr(d1), ptr(pin), ptr(intra), ptr(inter), ptr(invq), ptr(fps), n)
+        O.orc_propagate_cost(ptr(d2), ptr(pin), ptr(intra), ptr(inter), ptr(invq), ptr(fps), n)
+        assert np.array_equal(d1, d2), (it, np.nonzero(d1 != d2)[0][:5])
 
 
 def check_intra(get, O, depth, kind):

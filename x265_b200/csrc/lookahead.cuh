@@ -294,3 +294,29 @@ __global__ void __launch_bounds__(LA_WARPS * 32, 1) k_lookahead_cost(const x265c
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// cuTree: estimateCUPropagateCost (common/pixel.cpp:914-940), the per-CU amount of "influence on future quality" that
+// Lookahead::estimateCUPropagate (slicetype.cpp:2641-2670) scatters over the reference frames.  Double precision, each
+// operation rounded on its own as the host's scalar code does (no FMA contraction: __dmul_rn / __dadd_rn / __ddiv_rn), and
+// the final double -> int conversion with x86 cvttsd2si semantics (NaN / out of range -> INT_MIN) so that degenerate
+// inputs (intraCost 0) match the C primitive bit for bit too.  One thread per CU.
+__device__ __forceinline__ int la_cvttsd2si(double v)
+{
+    return (v >= -2147483648.0 && v < 2147483648.0) ? (int)v : (int)0x80000000;
+}
+__global__ void __launch_bounds__(256) k_propagate_cost(int* __restrict__ dst, const uint16_t* __restrict__ propagateIn, const int32_t* __restrict__ intraCosts,
+                                                        const uint16_t* __restrict__ interCosts, const int32_t* __restrict__ invQscales, double fpsFactor, int64_t len)
+{
+    const double fps = fpsFactor / 256;                             // range [0.01, 1.00]
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+    {
+        const int intraCost = intraCosts[i];
+        const int interCost = min(intraCost, (int)(interCosts[i] & LA_COST_MASK));
+        const double propagateIntra = __dmul_rn((double)intraCost, (double)invQscales[i]);              // Q16 x Q8.8 = Q24.8
+        const double propagateAmount = __dadd_rn((double)propagateIn[i], __dmul_rn(propagateIntra, fps));
+        const double propagateNum = (double)(intraCost - interCost);
+        const double propagateDenom = (double)intraCost;
+        dst[i] = la_cvttsd2si(__dadd_rn(__ddiv_rn(__dmul_rn(propagateAmount, propagateNum), propagateDenom), 0.5));
+    }
+}

@@ -823,8 +823,51 @@ __device__ __forceinline__ void me_fold(MeStar& s, int n, int cost, int px, int 
 // StarPatternSearch (motion.cpp:362-604).  Each distance level is one burst; candidate order inside
 // a level is the reference's (its x4 fast path and its bounds-checked path visit the same points in
 // the same order), out-of-range candidates are dropped before evaluation.
+// Candidate k of star level `mylvl` around (ox, oy) (motion.cpp:362-604; the order inside a level is the reference's):
+// levels 0 = distance 1 (4 points), 1..3 = distances 2, 4, 8 (8 points), 4.. = distances 16, 32, ... (16 points).
+__device__ __forceinline__ void me_star_point(int mylvl, int k, int ox, int oy, int& px, int& py, int& point, int& dist)
+{
+    const int d = mylvl < 4 ? (1 << mylvl) : (16 << (mylvl - 4));
+    if (mylvl == 0)
+    {
+        // dist 1: top(2) left(4) right(5) bottom(7)
+        px = ox + (k == 1 ? -1 : k == 2 ? 1 : 0); py = oy + (k == 0 ? -1 : k == 3 ? 1 : 0);
+        point = k == 0 ? 2 : k == 1 ? 4 : k == 2 ? 5 : 7; dist = 1;
+    }
+    else if (mylvl < 4)
+    {
+        // order: 2(top) 1 3 4(left) 5(right) 6 8 7(bottom); half-distance points need both their checks
+        const int h2 = d >> 1, kk = k & 7;
+        const int dx = kk == 0 ? 0 : kk == 1 ? -1 : kk == 2 ? 1 : kk == 3 ? -2 : kk == 4 ? 2 : kk == 5 ? -1 : kk == 6 ? 1 : 0;
+        const int dy = kk == 0 ? -2 : kk < 3 ? -1 : kk < 5 ? 0 : kk < 7 ? 1 : 2;
+        px = ox + dx * h2; py = oy + dy * h2;
+        point = kk == 0 ? 2 : kk == 1 ? 1 : kk == 2 ? 3 : kk == 3 ? 4 : kk == 4 ? 5 : kk == 5 ? 6 : kk == 6 ? 8 : 7;
+        dist = (kk == 1 || kk == 2 || kk == 5 || kk == 6) ? h2 : d;
+    }
+    else
+    {
+        // order: top, left, right, bottom, then j = 1..3: (xl,yt) (xr,yt) (xl,yb) (xr,yb)
+        const int q = d >> 2, kk = k & 15;
+        if (kk < 4) { px = ox + (kk == 1 ? -d : kk == 2 ? d : 0); py = oy + (kk == 0 ? -d : kk == 3 ? d : 0); }
+        else
+        {
+            const int jj = ((kk - 4) >> 2) + 1, m = (kk - 4) & 3;
+            px = ox + ((m & 1) ? q * jj : -q * jj);
+            py = (m & 2) ? (oy + d - q * jj) : (oy - d + q * jj);
+        }
+        point = 0; dist = d;
+    }
+}
+
+// Hooks of the shared-memory-window search (me_window.cuh): the first star round of a 16x16 cell's PUs that start at the
+// same point reads its candidates' SADs from a table computed once per cell.  Global-memory contexts never have one.
+template <typename P> __device__ __forceinline__ bool me_star_cached(const MeCtx<P>&) { return false; }
+template <typename P> __device__ __forceinline__ int me_star_lookup(const MeCtx<P>&, int, int, int, int) { return 0; }
+template <typename P> __device__ __forceinline__ bool me_star_cached(const MeWin<P>& c);
+template <typename P> __device__ __forceinline__ int me_star_lookup(const MeWin<P>& c, int mylvl, int k, int px, int py);
+
 template <typename CTX>
-__device__ __forceinline__ void me_star_pattern(const CTX& c, MeStar& s, int earlyExitIters, int merange)
+__device__ __forceinline__ void me_star_pattern(const CTX& c, MeStar& s, int earlyExitIters, int merange, bool first = false)
 {
     // Levels: 0 = distance 1 (4 points), 1..3 = distances 2, 4, 8 (8 points), 4.. = distances 16, 32, ... <= merange
     // (16 points).  Every level's points depend only on the start position, so levels can be evaluated ahead of the
@@ -845,42 +888,16 @@ __device__ __forceinline__ void me_star_pattern(const CTX& c, MeStar& s, int ear
         const int d = mylvl < 4 ? (1 << mylvl) : (16 << (mylvl - 4));
         const int cnt = mylvl == 0 ? 4 : mylvl < 4 ? 8 : 16;
         int px, py, point, dist;
-        if (mylvl == 0)
-        {
-            // dist 1: top(2) left(4) right(5) bottom(7)
-            px = ox + (k == 1 ? -1 : k == 2 ? 1 : 0); py = oy + (k == 0 ? -1 : k == 3 ? 1 : 0);
-            point = k == 0 ? 2 : k == 1 ? 4 : k == 2 ? 5 : 7; dist = 1;
-        }
-        else if (mylvl < 4)
-        {
-            // order: 2(top) 1 3 4(left) 5(right) 6 8 7(bottom); half-distance points need both their checks
-            const int h2 = d >> 1, kk = k & 7;
-            const int dx = kk == 0 ? 0 : kk == 1 ? -1 : kk == 2 ? 1 : kk == 3 ? -2 : kk == 4 ? 2 : kk == 5 ? -1 : kk == 6 ? 1 : 0;
-            const int dy = kk == 0 ? -2 : kk < 3 ? -1 : kk < 5 ? 0 : kk < 7 ? 1 : 2;
-            px = ox + dx * h2; py = oy + dy * h2;
-            point = kk == 0 ? 2 : kk == 1 ? 1 : kk == 2 ? 3 : kk == 3 ? 4 : kk == 4 ? 5 : kk == 5 ? 6 : kk == 6 ? 8 : 7;
-            dist = (kk == 1 || kk == 2 || kk == 5 || kk == 6) ? h2 : d;
-        }
-        else
-        {
-            // order: top, left, right, bottom, then j = 1..3: (xl,yt) (xr,yt) (xl,yb) (xr,yb)
-            const int q = d >> 2, kk = k & 15;
-            if (kk < 4) { px = ox + (kk == 1 ? -d : kk == 2 ? d : 0); py = oy + (kk == 0 ? -d : kk == 3 ? d : 0); }
-            else
-            {
-                const int jj = ((kk - 4) >> 2) + 1, m = (kk - 4) & 3;
-                px = ox + ((m & 1) ? q * jj : -q * jj);
-                py = (m & 2) ? (oy + d - q * jj) : (oy - d + q * jj);
-            }
-            point = 0; dist = d;
-        }
+        me_star_point(mylvl, k, ox, oy, px, py, point, dist);
         const bool valid = mylvl < lvl1 && k < cnt && !(mylvl >= 4 && d > merange) &&
                            px >= c.minx && px <= c.maxx && py >= c.miny && py <= c.maxy;
         // idle lanes evaluate an in-range position (the centre clamped into the search range: the start point can lie outside
         // it in x when MV 0 won the pre-checks, motion.cpp:806-813) and are masked out
         if (!valid) { px = min(max(ox, c.minx), c.maxx); py = min(max(oy, c.miny), c.maxy); }
         const int n = spec ? (lvl0 == 0 ? 28 : 32) : (lvl0 == 0 ? 4 : lvl0 < 4 ? 8 : 16);
-        const int cost = me_eval_points(c, n, px, py, false);
+        // the first round of a cell's PUs that share the start point: SADs out of the cell's star table (me_window.cuh)
+        const int cost = (first && me_star_cached(c)) ? (valid ? me_star_lookup(c, mylvl, k, px, py) : 0x7fffffff)
+                                                      : me_eval_points(c, n, px, py, false);
         for (int l = lvl0; l < lvl1; l++)
         {
             if (l >= 4 && (16 << (l - 4)) > merange) return;
@@ -1211,7 +1228,7 @@ __device__ __forceinline__ void me_star_search(const CTX& c, MeStar& s, int mera
     bool first = true;
     for (;;)
     {
-        me_star_pattern(c, s, first ? 3 : 32, merange);
+        me_star_pattern(c, s, first ? 3 : 32, merange, first);
         const bool d1 = s.dist == 1;
         bool improved = false;
         if (d1 && s.point)

@@ -49,6 +49,7 @@ struct MeWin
     int w, h, lane;
     bool pow2; int nw, lgnw, lgwpr, lgsegw;
     const struct MewCell* cell;            // shared 4x4 SAD maps of the 16x16 cell (NULL: this job walks its own raster)
+    bool star;                             // this job starts at the cell's common start point: first star round out of the star table
 };
 
 // 16x16 cell groups: all PUs of the cell (16x16 CU + four 8x8 CUs) that share one raster grid (same mvmin / mvmax: the
@@ -57,7 +58,9 @@ struct MeWin
 // (tasks = (block row, grid row), lanes = grid columns) and summed per PU (a PU's SAD at a vector is the sum of its 4x4
 // blocks' SADs at that vector: exact).  A 16x16 PU then costs 16 loads per grid point instead of 256 pixel differences.
 #define MEW_MAP_ROWS 23                    // grid rows (merange 57: (2 * 57) / 5 + 1)
-#define MEW_MAP_BYTES (16 * MEW_MAP_ROWS * 32 * 2)
+#define MEW_STAR_POINTS 60                 // first star round: levels 0-3 (4 + 3 * 8) and levels 4, 5 (distances 16, 32: 2 * 16)
+#define MEW_STAR_BYTES (MEW_STAR_POINTS * 4 * 8)
+#define MEW_MAP_BYTES (16 * MEW_MAP_ROWS * 32 * 2 + 2048)          // raster maps + star table
 struct MewCell
 {
     int on;                                // maps usable for this group
@@ -65,8 +68,12 @@ struct MewCell
     int ncols, nrows;
     int ox, oy;                            // cell origin relative to the window origin (pixels)
     uint32_t fenc;                         // shared address of the cell's source block (pitch 64 pixels)
-    uint32_t map;                          // shared address of the maps: u16 [block 16][MEW_MAP_ROWS][32]
+    uint32_t map;                          // shared address of the maps: [block row 4][MEW_MAP_ROWS][32] x (4 x u16 prefix sums)
     int next, done;                        // task queue of the map computation
+    // first star round shared by the PUs that start at the same point (the pre-checks leave most of a cell's PUs at the
+    // rounded MVP): per candidate of StarPatternSearch's levels 0-5 the same 4 x (4 x u16 prefix sums) as the raster maps
+    int starOn, sx, sy;                    // table valid; the common start point (full-pel, relative like minx)
+    uint32_t star;                         // shared address: [MEW_STAR_POINTS][block row 4] x 8 bytes
 };
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -81,28 +88,19 @@ __device__ __forceinline__ int mew_mvcost(const MeWin<P>& c, int qx, int qy)
     return (uint16_t)(__ldg(c.mvc + (qx - c.mvpx)) + __ldg(c.mvc + (qy - c.mvpy)));
 }
 
-// SEGW words of a window row starting at byte address `a` (any phase): 8-byte aligned LDS.64 + one select per word +
-// funnel shifts (SEGW >= 2), or two LDS.32 (SEGW == 1).  `a8`, `hi8`, `sh` are the pre-split address / phase.
+// SEGW words of a window row starting at a byte address of any phase: SEGW + 1 aligned LDS.32 + SEGW funnel shifts.
+// (The global-memory core reads 8-byte aligned LDG.64 pairs and selects: fewer load instructions matter on the L1 path.  Out
+// of shared memory the ALU pipe is the limiter, and a warp-wide LDS.32 is one conflict-free wavefront where an LDS.64 is
+// two, so five LDS.32 + four SHF beat three LDS.64 + five SEL + four SHF.)  `a4` = the address rounded down to 4 bytes,
+// `sh` = 8 * (address & 3).
 template <int SEGW>
-__device__ __forceinline__ void mew_load_ref(uint32_t a8, bool hi8, unsigned sh, uint32_t (&r)[SEGW])
+__device__ __forceinline__ void mew_load_ref(uint32_t a4, unsigned sh, uint32_t (&r)[SEGW])
 {
-    if (SEGW == 4)
-    {
-        const uint2 a0 = lds64(a8), a1 = lds64(a8 + 8), a2 = lds64(a8 + 16);
-        const uint32_t w0 = hi8 ? a0.y : a0.x, w1 = hi8 ? a1.x : a0.y, w2 = hi8 ? a1.y : a1.x, w3 = hi8 ? a2.x : a1.y, w4 = hi8 ? a2.y : a2.x;
-        r[0] = __funnelshift_r(w0, w1, sh); r[1 % SEGW] = __funnelshift_r(w1, w2, sh);
-        r[2 % SEGW] = __funnelshift_r(w2, w3, sh); r[3 % SEGW] = __funnelshift_r(w3, w4, sh);
-    }
-    else if (SEGW == 2)
-    {
-        const uint2 a0 = lds64(a8), a1 = lds64(a8 + 8);
-        const uint32_t w0 = hi8 ? a0.y : a0.x, w1 = hi8 ? a1.x : a0.y, w2 = hi8 ? a1.y : a1.x;
-        r[0] = __funnelshift_r(w0, w1, sh); r[1 % SEGW] = __funnelshift_r(w1, w2, sh);
-    }
-    else
-    {
-        r[0] = __funnelshift_r(lds32(a8), lds32(a8 + 4), sh);          // a8 is 4-byte aligned here
-    }
+    uint32_t w[SEGW + 1];
+#pragma unroll
+    for (int k = 0; k <= SEGW; k++) w[k] = lds32(a4 + 4 * k);
+#pragma unroll
+    for (int k = 0; k < SEGW; k++) r[k] = __funnelshift_r(w[k], w[k + 1], sh);
 }
 
 template <int SEGW>
@@ -128,9 +126,8 @@ __device__ __forceinline__ int mew_sad_multi_t(const MeWin<P>& c, int n, int off
     const int ob = __shfl_sync(0xffffffffu, offB, min(lane >> lglpc, n - 1));
     const uint32_t cptr = c.win + (uint32_t)ob;                            // my candidate's block origin; any byte phase
     const unsigned sh = (cptr & 3u) * 8u;
-    const bool hi8 = SEGW >= 2 && (cptr & 4u) != 0;
     const int subcol = sub & ((1 << lgcols) - 1), subrow = sub >> lgcols;
-    uint32_t rrow = (cptr & ~(uint32_t)(SEGW >= 2 ? 7 : 3)) + subrow * c.pitch + subcol * (SEGW * 4);
+    uint32_t rrow = (cptr & ~3u) + subrow * c.pitch + subcol * (SEGW * 4);
     uint32_t frow = c.fenc + subrow * c.fpitch + subcol * (SEGW * 4);
     const int rowStepR = c.pitch << lgrows, rowStepF = c.fpitch << lgrows, colStep = (SEGW * 4) << lgcols;
     const int nrows = c.h >> lgrows, ncols = 1 << (lgspr - lgcols);
@@ -143,7 +140,7 @@ __device__ __forceinline__ int mew_sad_multi_t(const MeWin<P>& c, int n, int off
         {
             uint32_t f[SEGW], r[SEGW];
             mew_load_fenc<SEGW>(fp, f);
-            mew_load_ref<SEGW>(rp, hi8, sh, r);
+            mew_load_ref<SEGW>(rp, sh, r);
 #pragma unroll
             for (int k = 0; k < SEGW; k++) acc = sad_word<P>(f[k], r[k], acc);
         }
@@ -217,8 +214,7 @@ __device__ __forceinline__ void mew_raster_t(const MeWin<P>& c, MeStar& s)
         const int xc = (int)__ldg(c.mvc + ((x8 ? cx * 8 : cx * 4) - c.mvpx));
         const uint32_t a0 = c.win + (uint32_t)((c.oy + c.miny) * c.pitch + (c.ox + cx) * (int)sizeof(P));
         const unsigned sh = (a0 & 3u) * 8u;
-        const bool hi8 = SEGW >= 2 && (a0 & 4u) != 0;
-        uint32_t rowaddr = a0 & ~(uint32_t)(SEGW >= 2 ? 7 : 3);      // the pitch is a multiple of 16: the phase never changes
+        uint32_t rowaddr = a0 & ~3u;                                 // the pitch is a multiple of 16: the phase never changes
         int acc[NA];
 #pragma unroll
         for (int i = 0; i < NA; i++) acc[i] = 0;
@@ -233,7 +229,7 @@ __device__ __forceinline__ void mew_raster_t(const MeWin<P>& c, MeStar& s)
                     for (int sg = 0; sg < nseg; sg++)
                     {
                         uint32_t r[SEGW];
-                        mew_load_ref<SEGW>(rowaddr + sg * SEGB, hi8, sh, r);
+                        mew_load_ref<SEGW>(rowaddr + sg * SEGB, sh, r);
                         const uint32_t fa = c.fenc + t * c.fpitch + sg * SEGB;
 #pragma unroll
                         for (int i = 0; i < NA; i++)
@@ -282,42 +278,46 @@ __device__ __forceinline__ void mew_raster_na(const MeWin<P>& c, MeStar& s)
     else                mew_raster_t<P, 13, LGSEGW>(c, s);
 }
 
-// One task of the cell maps: the 4 blocks of block row `by` at grid row k, every grid column (lane = column).
+// One task of the cell maps: grid row k, every grid column (lane = column), the cell's 4 block rows one after the other.
+// Stored per (block row, k, column): the 4 prefix sums over the block columns, P[bx] = S[0] + .. + S[bx], as 4 x u16 in
+// one 8-byte word (4 blocks of 16 ten-bit pixels: <= 65472), so that a PU's block-row sum is P[last] - P[first - 1].
 template <typename P>
-__device__ __forceinline__ void mew_cell_map_task(const MeWin<P>& c, const MewCell& cell, int by, int k)
+__device__ __forceinline__ void mew_cell_map_task(const MeWin<P>& c, const MewCell& cell, int k)
 {
     constexpr int ES = (int)sizeof(P), WB = ES;                    // words per 4-pixel block row
     const int col = c.lane;
     const bool act = col < cell.ncols;
     const int gx = cell.minx + (act ? col : 0) * 5, gy = cell.miny + k * 5;
-    const uint32_t a0 = c.win + (uint32_t)((cell.oy + gy + 4 * by) * c.pitch + (cell.ox + gx) * ES);
+    const uint32_t a0 = c.win + (uint32_t)((cell.oy + gy) * c.pitch + (cell.ox + gx) * ES);
     const unsigned sh = (a0 & 3u) * 8u;
-    const bool hi8 = (a0 & 4u) != 0;
-    const uint32_t a8 = a0 & ~7u;
-    const uint32_t fa = cell.fenc + (uint32_t)(4 * by * 64 * ES);
-    int acc[4] = { 0, 0, 0, 0 };
-#pragma unroll
-    for (int r = 0; r < 4; r++)
+    uint32_t a4 = a0 & ~3u;
+    uint32_t fa = cell.fenc;
+#pragma unroll 1
+    for (int by = 0; by < 4; by++)
     {
+        int acc[4] = { 0, 0, 0, 0 };
 #pragma unroll
-        for (int hw = 0; hw < WB; hw++)                            // 16 bytes of the row per step: 4 (8-bit) / 2 (16-bit) blocks
+        for (int r = 0; r < 4; r++)
         {
-            uint32_t rr[4], ff[4];
-            mew_load_ref<4>(a8 + r * c.pitch + hw * 16, hi8, sh, rr);
-            mew_load_fenc<4>(fa + r * 64 * ES + hw * 16, ff);      // same address in every lane: broadcast
 #pragma unroll
-            for (int wd = 0; wd < 4; wd++)
+            for (int hw = 0; hw < WB; hw++)                        // 16 bytes of the row per step: 4 (8-bit) / 2 (16-bit) blocks
             {
-                const int bx = (hw * 4 + wd) / WB;                 // block column of this word
-                acc[bx] = sad_word<P>(ff[wd], rr[wd], acc[bx]);
+                uint32_t rr[4], ff[4];
+                mew_load_ref<4>(a4 + r * c.pitch + hw * 16, sh, rr);
+                mew_load_fenc<4>(fa + r * 64 * ES + hw * 16, ff);  // same address in every lane: broadcast
+#pragma unroll
+                for (int wd = 0; wd < 4; wd++)
+                {
+                    const int bx = (hw * 4 + wd) / WB;             // block column of this word
+                    acc[bx] = sad_word<P>(ff[wd], rr[wd], acc[bx]);
+                }
             }
         }
-    }
-    if (act)
-    {
-#pragma unroll
-        for (int bx = 0; bx < 4; bx++)
-            sts16(cell.map + (uint32_t)((((by * 4 + bx) * MEW_MAP_ROWS + k) * 32 + col) * 2), (uint32_t)acc[bx]);
+        const uint32_t p0 = (uint32_t)acc[0], p1 = p0 + (uint32_t)acc[1], p2 = p1 + (uint32_t)acc[2], p3 = p2 + (uint32_t)acc[3];
+        if (act)
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(cell.map + (uint32_t)(((by * MEW_MAP_ROWS + k) * 32 + col) * 8)),
+                         "r"(p0 | (p1 << 16)), "r"(p2 | (p3 << 16)) : "memory");
+        a4 += 4 * c.pitch; fa += 4 * 64 * ES;
     }
 }
 
@@ -326,7 +326,7 @@ template <typename P>
 __device__ __forceinline__ void mew_raster_maps(const MeWin<P>& c, MeStar& s)
 {
     MewCell* cell = const_cast<MewCell*>(c.cell);
-    const int ntasks = 4 * cell->nrows;
+    const int ntasks = cell->nrows;
     // every warp that needs the maps helps to build them, then waits until all tasks are done
     for (;;)
     {
@@ -334,7 +334,7 @@ __device__ __forceinline__ void mew_raster_maps(const MeWin<P>& c, MeStar& s)
         if (c.lane == 0) t = atomicAdd(&cell->next, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= ntasks) break;
-        mew_cell_map_task<P>(c, *cell, t & 3, t >> 2);
+        mew_cell_map_task<P>(c, *cell, t);
         __syncwarp();
         if (c.lane == 0) { __threadfence_block(); atomicAdd(&cell->done, 1); }
     }
@@ -348,15 +348,25 @@ __device__ __forceinline__ void mew_raster_maps(const MeWin<P>& c, MeStar& s)
     const bool x8 = (col & 3) == 3;
     const int xc = (int)__ldg(c.mvc + ((x8 ? gx * 8 : gx * 4) - c.mvpx));
     const int bx0 = (c.ox - cell->ox) >> 2, by0 = (c.oy - cell->oy) >> 2, nbx = c.w >> 2, nby = c.h >> 2;
+    // block-row sum = P[e] - P[s] (s = bx0 - 1; nothing to subtract when the PU starts at the cell's left edge)
+    const int e = bx0 + nbx - 1, sx = bx0 - 1;
+    const bool ehi = e >= 2, shi = sx >= 2;
+    const unsigned esh = (unsigned)(e & 1) * 16u, ssh = (unsigned)(sx & 1) * 16u;
+    const uint32_t base = cell->map + (uint32_t)((by0 * MEW_MAP_ROWS * 32 + col) * 8);
+    const uint16_t* ymvc = c.mvc - c.mvpy;
+    const int ymul = x8 ? 8 : 4;
     int best = 0x7fffffff, bestIdx = 0x7fffffff;
     for (int k = 0; k < nrows; k++)
     {
         int sad = 0;
-        for (int by = by0; by < by0 + nby; by++)
-            for (int bx = bx0; bx < bx0 + nbx; bx++)
-                sad += (int)lds16(cell->map + (uint32_t)((((by * 4 + bx) * MEW_MAP_ROWS + k) * 32 + col) * 2));
-        const int py = c.miny + k * 5;
-        const int cost = sad + (int)(uint16_t)(xc + (int)__ldg(c.mvc + ((x8 ? py * 8 : py * 4) - c.mvpy)));
+        uint32_t a = base + (uint32_t)(k * 32 * 8);
+        for (int by = 0; by < nby; by++, a += MEW_MAP_ROWS * 32 * 8)
+        {
+            const uint2 v = lds64(a);
+            sad += (int)(((ehi ? v.y : v.x) >> esh) & 0xffffu);
+            if (sx >= 0) sad -= (int)(((shi ? v.y : v.x) >> ssh) & 0xffffu);
+        }
+        const int cost = sad + (int)(uint16_t)(xc + (int)__ldg(ymvc + (c.miny + k * 5) * ymul));
         if (act && cost < best) { best = cost; bestIdx = k * ncols + col; }       // k ascending: strict '<' keeps the earliest
     }
     const int m = __reduce_min_sync(0xffffffffu, best);
@@ -377,6 +387,60 @@ __device__ __forceinline__ void me_raster(const MeWin<P>& c, MeStar& s)
     if (c.pow2 && c.lgsegw == 2)      mew_raster_na<P, 2>(c, s);
     else if (c.pow2 && c.lgsegw == 1) mew_raster_na<P, 1>(c, s);
     else                              mew_raster_na<P, 0>(c, s);
+}
+
+// First star round out of the cell's star table (me.cuh: me_star_pattern): candidate k of level `mylvl` around the common start.
+template <typename P> __device__ __forceinline__ bool me_star_cached(const MeWin<P>& c) { return c.star; }
+template <typename P>
+__device__ __forceinline__ int me_star_lookup(const MeWin<P>& c, int mylvl, int k, int px, int py)
+{
+    const MewCell* cell = c.cell;
+    const int idx = mylvl == 0 ? k : mylvl < 4 ? 4 + (mylvl - 1) * 8 + (k & 7) : 28 + (mylvl - 4) * 16 + (k & 15);
+    const int bx0 = (c.ox - cell->ox) >> 2, by0 = (c.oy - cell->oy) >> 2, nbx = c.w >> 2, nby = c.h >> 2;
+    const int e = bx0 + nbx - 1, sx = bx0 - 1;
+    uint32_t a = cell->star + (uint32_t)((idx * 4 + by0) * 8);
+    int sad = 0;
+    for (int by = 0; by < nby; by++, a += 8)
+    {
+        const uint2 v = lds64(a);
+        sad += (int)(((e >= 2 ? v.y : v.x) >> ((e & 1) * 16)) & 0xffffu);
+        if (sx >= 0) sad -= (int)(((sx >= 2 ? v.y : v.x) >> ((sx & 1) * 16)) & 0xffffu);
+    }
+    return sad + mew_mvcost(c, px * 4, py * 4);
+}
+
+// Star table of a cell: thread = (candidate, block row); 4 rows of the cell against the window at the candidate's vector.
+template <typename P>
+__device__ __forceinline__ void mew_cell_star_build(const MewCell& cell, uint32_t win, int pitch, int tid)
+{
+    constexpr int ES = (int)sizeof(P), WB = ES;
+    const int idx = tid >> 2, by = tid & 3;
+    if (idx >= MEW_STAR_POINTS) return;
+    const int mylvl = idx < 4 ? 0 : idx < 28 ? 1 + ((idx - 4) >> 3) : 4 + ((idx - 28) >> 4);
+    const int k = idx < 4 ? idx : idx < 28 ? (idx - 4) & 7 : (idx - 28) & 15;
+    int px, py, point, dist;
+    me_star_point(mylvl, k, cell.sx, cell.sy, px, py, point, dist);
+    if (px < cell.minx || px > cell.maxx || py < cell.miny || py > cell.maxy) return;        // never looked up (out of the search range)
+    const uint32_t a0 = win + (uint32_t)((cell.oy + py + 4 * by) * pitch + (cell.ox + px) * ES);
+    const unsigned sh = (a0 & 3u) * 8u;
+    const uint32_t a4 = a0 & ~3u;
+    const uint32_t fa = cell.fenc + (uint32_t)(4 * by * 64 * ES);
+    int acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+#pragma unroll
+        for (int hw = 0; hw < WB; hw++)
+        {
+            uint32_t rr[4], ff[4];
+            mew_load_ref<4>(a4 + r * pitch + hw * 16, sh, rr);
+            mew_load_fenc<4>(fa + r * 64 * ES + hw * 16, ff);
+#pragma unroll
+            for (int wd = 0; wd < 4; wd++) acc[(hw * 4 + wd) / WB] = sad_word<P>(ff[wd], rr[wd], acc[(hw * 4 + wd) / WB]);
+        }
+    }
+    const uint32_t p0 = (uint32_t)acc[0], p1 = p0 + (uint32_t)acc[1], p2 = p1 + (uint32_t)acc[2], p3 = p2 + (uint32_t)acc[3];
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(cell.star + (uint32_t)((idx * 4 + by) * 8)), "r"(p0 | (p1 << 16)), "r"(p2 | (p3 << 16)) : "memory");
 }
 
 // ---- mbarrier / TMA (PTX) -----------------------------------------------------------------------------------------
@@ -492,7 +556,7 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
             hdr->fx0 = fx0a; hdr->fy0 = fy0; hdr->fw = fwB; hdr->fh = fhh; hdr->ref = ref;
             // shared SAD maps: a complete 16x16 cell and a grid of at most 32 x MEW_MAP_ROWS points (lane 0 holds job 0's range)
             MewCell& cl = hdr->cell;
-            cl.on = 0;
+            cl.on = 0; cl.starOn = 0;
             if (CELL && ok && fx1 - fx0 == 16 && fy1 - fy0 == 16 && fx0a == fx0)
             {
                 const int ncols = (g0maxx - g0minx) / 5 + 1, nrows = (g0maxy - g0miny) / 5 + 1;
@@ -500,6 +564,11 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
                 {
                     cl.on = 1; cl.minx = g0minx; cl.miny = g0miny; cl.maxx = g0maxx; cl.maxy = g0maxy; cl.ncols = ncols; cl.nrows = nrows;
                     cl.ox = fx0 - hdr->wx0; cl.oy = fy0 - y0; cl.fenc = s_fenc; cl.map = s_map; cl.next = 0; cl.done = 0;
+                    // common start of the first star round: where the pre-checks left the group's first job (its state)
+                    const MeState st0 = state[grp_jobs[g.first] - job0];
+                    cl.star = s_map + (uint32_t)(16 * MEW_MAP_ROWS * 32 * 2);
+                    cl.sx = st0.bmx; cl.sy = st0.bmy;
+                    cl.starOn = st0.bmx >= g0minx && st0.bmx <= g0maxx && st0.bmy >= g0miny && st0.bmy <= g0maxy;
                 }
             }
         }
@@ -541,6 +610,11 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
     }
     __syncthreads();
     mew_mbar_wait(bar, 0);
+    if (CELL && hdr->cell.on && hdr->cell.starOn)
+    {   // the first star round of the cell's PUs: one (candidate, block row) per thread, then everybody may look it up
+        mew_cell_star_build<P>(hdr->cell, s_win, pitch, tid);
+        __syncthreads();
+    }
 
     // ---- 3. the group's jobs, largest first, one warp each ----
     for (;;)
@@ -567,6 +641,8 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
         if (CELL && hdr->cell.on && c.minx == hdr->cell.minx && c.maxx == hdr->cell.maxx && c.miny == hdr->cell.miny && c.maxy == hdr->cell.maxy)
             c.cell = &hdr->cell;
         MeState st = state[jid];
+        // merange < 64: the first round's far levels are distances 16 and 32 only (levels 4, 5), what the table holds
+        c.star = c.cell != NULL && hdr->cell.starOn && j.merange < 64 && st.bmx == hdr->cell.sx && st.bmy == hdr->cell.sy;
         MeStar s; s.bx = st.bmx; s.by = st.bmy; s.bcost = st.bcost; s.point = 0; s.dist = 0;
         me_star_search(c, s, (int)j.merange);
         if (lane == 0) { st.bmx = s.bx; st.bmy = s.by; st.bcost = s.bcost; state[jid] = st; }

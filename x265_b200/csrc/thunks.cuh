@@ -239,6 +239,19 @@ static void denoise(int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, 
     memcpy(resSum, s.h<uint32_t>(orr), (size_t)numCoeff * 4);
 }
 
+// cuTree propagateCost (pixel.cpp:914-940)
+static void propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts, const int32_t* invQscales,
+                           const double* fpsFactor, int len)
+{
+    Stage s; s.ctx = tctx();
+    size_t op = s.put(propagateIn, len, len, 1, 2), oi = s.put(intraCosts, len, len, 1, 4), oc = s.put(interCosts, len, len, 1, 2),
+           oq = s.put(invQscales, len, len, 1, 4), od = s.reserve((size_t)len * 4);
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload() || x265cu_propagate_cost_batch(s.ctx, s.d<int>(od), s.d<uint16_t>(op), s.d<int32_t>(oi), s.d<uint16_t>(oc), s.d<int32_t>(oq), *fpsFactor, len) ||
+        s.download(od, (size_t)len * 4)) { fail("propagateCost"); return; }
+    memcpy(dst, s.h<int>(od), (size_t)len * 4);
+}
+
 // copy_cnt / count_nonzero via the compare kernel's machinery would be overkill: tiny dedicated kernel
 __global__ void k_count_nonzero(const int16_t* __restrict__ q, int n, uint32_t* __restrict__ out)
 {
@@ -506,6 +519,7 @@ static void* lookup(const char* name, int i, int j, int k)
     if (!strcmp(name, "dequant_normal")) return (void*)dequant_normal;
     if (!strcmp(name, "dequant_scaling")) return (void*)dequant_scaling;
     if (!strcmp(name, "denoiseDct")) return (void*)denoise;
+    if (!strcmp(name, "propagateCost")) return (void*)propagate_cost;
     if (!strcmp(name, "scale2D_64to32")) return (void*)X::scale2D;
     if (!strcmp(name, "weight_pp")) return (void*)X::weight_pp;
     if (!strcmp(name, "weight_sp")) return (void*)X::weight_sp;

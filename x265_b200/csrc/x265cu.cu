@@ -96,6 +96,13 @@ void* x265cu_host_alloc(size_t bytes) { void* p = NULL; if (cudaMallocHost(&p, b
 void x265cu_host_free(void* p) { cudaFreeHost(p); }
 int x265cu_h2d(x265cu_ctx* c, void* dev, const void* host, size_t bytes) { cudaSetDevice(c->device); CU_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream)); return 0; }
 int x265cu_d2h(x265cu_ctx* c, void* host, const void* dev, size_t bytes) { cudaSetDevice(c->device); CU_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream)); return 0; }
+int x265cu_copy2d(x265cu_ctx* c, void* dst, size_t dpitch, const void* src, size_t spitch, size_t widthBytes, size_t rows, int kind)
+{
+    cudaSetDevice(c->device);
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CU_CHECK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, widthBytes, rows, k, c->stream));
+    return 0;
+}
 int x265cu_memset(x265cu_ctx* c, void* dev, int value, size_t bytes) { cudaSetDevice(c->device); CU_CHECK(cudaMemsetAsync(dev, value, bytes, c->stream)); return 0; }
 int x265cu_timer_begin(x265cu_ctx* c) { cudaSetDevice(c->device); CU_CHECK(cudaEventRecord(c->ev0, c->stream)); return 0; }
 float x265cu_timer_end(x265cu_ctx* c)
@@ -333,6 +340,17 @@ int x265cu_lookahead_cost_batch(x265cu_ctx* c, int depth, const x265cu_la_job* j
         CU_CHECK(cudaFuncSetAttribute(k_lookahead_cost<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU_CHECK(cudaLaunchKernelEx(&cfg, k_lookahead_cost<uint16_t>, jobs, stride, w8, h8, mvcost));
     }
+    CU_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int x265cu_propagate_cost_batch(x265cu_ctx* c, int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts,
+                                const int32_t* invQscales, double fpsFactor, int64_t len)
+{
+    cudaSetDevice(c->device);
+    if (len <= 0) return 0;
+    int64_t blocks = (len + 255) / 256; if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
+    k_propagate_cost<<<(int)blocks, 256, 0, c->stream>>>(dst, propagateIn, intraCosts, interCosts, invQscales, fpsFactor, len);
     CU_LAUNCH_CHECK(c);
     return 0;
 }

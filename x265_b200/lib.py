@@ -56,6 +56,7 @@ _PROTOS = {
     "x265cu_h2d": (I, [P, P, P, C.c_size_t]),
     "x265cu_d2h": (I, [P, P, P, C.c_size_t]),
     "x265cu_memset": (I, [P, P, I, C.c_size_t]),
+    "x265cu_copy2d": (I, [P, P, C.c_size_t, P, C.c_size_t, C.c_size_t, C.c_size_t, I]),
     "x265cu_timer_begin": (I, [P]),
     "x265cu_timer_end": (C.c_float, [P]),
     "x265cu_launch_count": (C.c_uint64, [P]),
@@ -276,6 +277,7 @@ _AN_PROTOS = {
     "x265cu_analyser_set_ref_chroma": (I, [P, I, P, P, I]),
     "x265cu_analyser_load_chroma": (I, [P, P, P, I]),
 }
+_AN_PROTOS["x265cu_propagate_cost_batch"] = (I, [P, P, P, P, P, P, C.c_double, I64])
 _AN_PROTOS["x265cu_lowres_intra_batch"] = (I, [P, I, P, I, I, I, I, I])
 _AN_PROTOS["x265cu_lookahead_cost_batch"] = (I, [P, I, P, I, I, I, I, P])
 _AN_PROTOS["x265cu_lookahead_weights_analyse"] = (I, [P, I, P, P, P, I64, I, I, I, I64, P, P, P])

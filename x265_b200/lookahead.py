@@ -93,16 +93,25 @@ class Lookahead:
         lib.sync()
 
     # ---- Lowres::init: full-res luma (host) -> 4 half-pel planes with extended borders (device) ----
-    def init_frame(self, i, img):
+    def init_frame(self, i, img, sync=True):
+        """Lowres::init of frame i from its full-resolution luma (host array, ideally pinned): strided H2D straight into the
+        PicYuv-like padded device plane, border extension (pixel.cpp:1027-1041) and the lowres kernel on the device."""
         cu = self.cu
-        full, fs, forg = full_plane(np.ascontiguousarray(img), self.depth)
-        if self._full is None or self._full.nbytes < full.nbytes:
-            self._full = cu.alloc(full.nbytes)
-        self._full.upload(full)
+        img = np.ascontiguousarray(img)
+        H, W = img.shape
+        fs = (W + 63) // 64 * 64 + 2 * MARGIN_X
+        rows = (H + 63) // 64 * 64 + 2 * MARGIN_Y
+        forg = (MARGIN_Y * fs + MARGIN_X) * self.es
+        if self._full is None:
+            self._full = cu.alloc(fs * rows * self.es)
+            cu.check(cu.L.x265cu_memset(cu.ctx, self._full.ptr, 0, self._full.nbytes))
+        cu.check(cu.L.x265cu_copy2d(cu.ctx, self._full.ptr + forg, fs * self.es, img.ctypes.data, W * self.es, W * self.es, H, 0))
+        cu.check(cu.L.x265cu_extend_border(cu.ctx, self.depth, self._full.ptr + forg, fs, W, H, MARGIN_X, MARGIN_Y))
         f = self.fr[i]
-        cu.check(cu.L.x265cu_frame_init_lowres(cu.ctx, self.depth, self._full.ptr + forg * self.es, fs,
+        cu.check(cu.L.x265cu_frame_init_lowres(cu.ctx, self.depth, self._full.ptr + forg, fs,
                                                *[p.ptr + self.lorg for p in f["planes"]], self.ls, self.w8 * 8, self.h8 * 8, MARGIN_X, MARGIN_Y))
-        cu.sync()
+        if sync:
+            cu.sync()          # the host image may be released / the staging plane re-used
         f["has_planes"] = True
 
     def set_invqscale(self, i, invq):

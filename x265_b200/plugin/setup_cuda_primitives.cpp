@@ -91,6 +91,7 @@ void setupCudaPrimitives(EncoderPrimitives& p, int /*cpuMask*/)
     SET(p.dequant_normal, dequant_normal_t, "dequant_normal", 0, 0, 0);
     SET(p.dequant_scaling, dequant_scaling_t, "dequant_scaling", 0, 0, 0);
     SET(p.denoiseDct, denoiseDct_t, "denoiseDct", 0, 0, 0);
+    SET(p.propagateCost, cutree_propagate_cost, "propagateCost", 0, 0, 0);
     SET(p.scale2D_64to32, scale2D_t, "scale2D_64to32", 0, 0, 0);
     SET(p.weight_pp, weightp_pp_t, "weight_pp", 0, 0, 0);
     SET(p.weight_sp, weightp_sp_t, "weight_sp", 0, 0, 0);
