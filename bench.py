@@ -282,8 +282,6 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = x265_b200.load(local_rank)
@@ -438,6 +436,7 @@ def run_ours(args, rank, world, local_rank):
         t_res, t_e2e = float(t[0]), float(t[1])
 
     rc = 0
+    line = None
     if rank == 0:
         stage /= args.steps
         phases /= args.steps
@@ -510,13 +509,11 @@ def run_ours(args, rank, world, local_rank):
                 line["primitives"] = primitives_leg(lib)
             except Exception as e:          # the per-primitive table must never cost the headline line
                 line["primitives_error"] = repr(e)
-        print(json.dumps(line), flush=True)
         if rc:
             print("bench.py: PARITY FAILURE: GPU checks differ from the CPU reference on %s" % line["checks_vs_cpu"]["scope"], file=sys.stderr)
     an.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return rc
+    flush.free()
+    return (line if rank == 0 else None), rc
 
 
 # ----------------------------------------------------------------------------------------------
@@ -535,8 +532,6 @@ def run_lookahead_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = x265_b200.load(local_rank)
@@ -652,8 +647,6 @@ def run_lookahead_ours(args, rank, world, local_rank):
                 rc = 3
         print(json.dumps(line), flush=True)
     la.close()
-    if world > 1:
-        dist.destroy_process_group()
     return rc
 
 
@@ -733,8 +726,9 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json config (c2 lookahead, c3 slow [default], c4 slower Main10, c5 8K veryslow)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (and with it the parity assertion)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="host time budget of the cpu_baseline sample")
-    ap.add_argument("--shard", default="frames", choices=["frames", "rows"],
-                    help="N>1 partition: a frame per GPU (default, weak scaling) or the CTU rows of one frame per GPU (strong scaling)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "frames", "rows"],
+                    help="N>1 partition: a frame per GPU (weak scaling) or the CTU rows of one frame per GPU (strong scaling); "
+                         "auto (default) = the frame shard as the line, with the row shard measured in the same run and attached")
     ap.add_argument("--no-chroma", action="store_true", help="luma-only motion estimation (round-1 line; the presets run with the chroma-SATD term)")
     ap.add_argument("--primitives", action="store_true", help="add the per-primitive HBM GB/s table (8- and 10-bit) to the line")
     args = ap.parse_args()
@@ -744,12 +738,36 @@ def main():
     if args.no_chroma and "chroma" in CFG:
         CFG["chroma"] = False
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    args.shard_auto = args.shard == "auto"
+    if args.shard == "auto":
+        args.shard = "frames"
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return 0
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world)
     if CFG.get("lookahead"):
-        return run_lookahead_ours(args, rank, world, local_rank)
-    return run_ours(args, rank, world, local_rank)
+        rc = run_lookahead_ours(args, rank, world, local_rank)
+    else:
+        # N > 1 without an explicit --shard: the headline line is the frame shard (weak scaling: CTUs/s of N frames in flight);
+        # the same run then measures the CTU-ROW shard of ONE frame (strong scaling, BASELINE configs[4]) and attaches it
+        shard_mode = args.shard if args.shard != "auto" else "frames"
+        args.shard = shard_mode
+        line, rc = run_ours(args, rank, world, local_rank)
+        if world > 1 and args.shard_auto:
+            args.shard = "rows"
+            rows_line, rc2 = run_ours(args, rank, world, local_rank)
+            rc = rc or rc2
+            if rank == 0:
+                line["strong_scaling_rows"] = {k: rows_line[k] for k in ("value", "unit", "ms_per_step", "scaling", "e2e", "stages_ms", "gpu_launches")}
+                line["strong_scaling_rows"]["config"] = rows_line["config"]
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return rc
 
 
 if __name__ == "__main__":

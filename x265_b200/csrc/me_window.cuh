@@ -269,6 +269,93 @@ __device__ __forceinline__ void mew_raster_t(const MeWin<P>& c, MeStar& s)
     }
 }
 
+// The same column walk for PUs whose rows are 1, 2 or 4 aligned 16-byte segments (NSEG): the lane's whole reference row is
+// loaded once into registers, then every live candidate of the ring differences its source row against it -- per
+// (candidate, row): one liveness test, then NSEG x (broadcast LDS.128 + 4 VABSDIFF4), no per-segment conditions.
+template <typename P, int NA, int NSEG>
+__device__ __forceinline__ void mew_raster_wide(const MeWin<P>& c, MeStar& s)
+{
+    constexpr int RD = 5, NW = 4 * NSEG;
+    const int ncols = (c.maxx - c.minx) / RD + 1, nrows = (c.maxy - c.miny) / RD + 1;
+    const int lastRow = (nrows - 1) * RD + c.h - 1;
+    const int nblk = nrows + NA - 1;
+    int best = 0x7fffffff, bestIdx = 0x7fffffff;
+    for (int cbase = 0; cbase < ncols; cbase += 32)
+    {
+        const int ri = cbase + c.lane;
+        const bool act = ri < ncols;
+        const int cx = c.minx + (act ? ri : 0) * RD;
+        const bool x8 = (ri & 3) == 3;
+        const int xc = (int)__ldg(c.mvc + ((x8 ? cx * 8 : cx * 4) - c.mvpx));
+        const int ymul = x8 ? 8 : 4;
+        const uint32_t a0 = c.win + (uint32_t)((c.oy + c.miny) * c.pitch + (c.ox + cx) * (int)sizeof(P));
+        const unsigned sh = (a0 & 3u) * 8u;
+        uint32_t rowaddr = a0 & ~3u;
+        int acc[NA];
+#pragma unroll
+        for (int i = 0; i < NA; i++) acc[i] = 0;
+        for (int b = 0; b < nblk; b++)
+        {
+            const int lo = max(0, b - nrows + 1), hi = min(b, NA - 1);     // live ring slots: candidate k = b - i in [0, nrows)
+#pragma unroll 1
+            for (int t = 0; t < RD; t++, rowaddr += c.pitch)
+            {
+                if (b * RD + t > lastRow) continue;                        // warp-uniform
+                uint32_t w[NW + 1], r[NW];
+#pragma unroll
+                for (int q = 0; q <= NW; q++) w[q] = lds32(rowaddr + 4 * q);
+#pragma unroll
+                for (int q = 0; q < NW; q++) r[q] = __funnelshift_r(w[q], w[q + 1], sh);
+                // live candidates of this row: slot i is live iff lo <= i <= hi and its source row 5 i + t exists
+                const int ihi = min(hi, (c.h - 1 - t) / RD);
+                const uint32_t fa = c.fenc + t * c.fpitch;
+#pragma unroll
+                for (int i = 0; i < NA; i++)
+                {
+                    if (i >= lo && i <= ihi)                               // warp-uniform
+                    {
+#pragma unroll
+                        for (int sg = 0; sg < NSEG; sg++)
+                        {
+                            const uint4 f = lds128(fa + (RD * i) * c.fpitch + sg * 16);    // same address in every lane: broadcast
+                            acc[i] = sad_word<P>(f.x, r[4 * sg], acc[i]); acc[i] = sad_word<P>(f.y, r[4 * sg + 1], acc[i]);
+                            acc[i] = sad_word<P>(f.z, r[4 * sg + 2], acc[i]); acc[i] = sad_word<P>(f.w, r[4 * sg + 3], acc[i]);
+                        }
+                    }
+                }
+            }
+            const int k = b - (NA - 1);                                    // the candidate in the last ring slot is complete
+            if (k >= 0)
+            {
+                const int py = c.miny + k * RD;
+                const int cost = acc[NA - 1] + (int)(uint16_t)(xc + (int)__ldg(c.mvc + (py * ymul - c.mvpy)));
+                const int idx = k * ncols + ri;
+                if (act && (cost < best || (cost == best && idx < bestIdx))) { best = cost; bestIdx = idx; }
+            }
+#pragma unroll
+            for (int i = NA - 1; i > 0; i--) acc[i] = acc[i - 1];
+            acc[0] = 0;
+        }
+    }
+    const int m = __reduce_min_sync(0xffffffffu, best);
+    const int mi = __reduce_min_sync(0xffffffffu, best == m ? bestIdx : 0x7fffffff);
+    if (m < s.bcost)
+    {
+        s.bcost = m;
+        const int rj = mi / ncols, ri = mi - rj * ncols;
+        s.bx = c.minx + ri * RD; s.by = c.miny + rj * RD;
+    }
+}
+
+template <typename P, int NSEG>
+__device__ __forceinline__ void mew_raster_wide_na(const MeWin<P>& c, MeStar& s)
+{
+    if (c.h <= 10)      mew_raster_wide<P, 2, NSEG>(c, s);
+    else if (c.h <= 20) mew_raster_wide<P, 4, NSEG>(c, s);
+    else if (c.h <= 35) mew_raster_wide<P, 7, NSEG>(c, s);
+    else                mew_raster_wide<P, 13, NSEG>(c, s);
+}
+
 template <typename P, int LGSEGW>
 __device__ __forceinline__ void mew_raster_na(const MeWin<P>& c, MeStar& s)
 {
@@ -321,6 +408,40 @@ __device__ __forceinline__ void mew_cell_map_task(const MeWin<P>& c, const MewCe
     }
 }
 
+// Scan of one grid column (this lane) over the grid rows: cost(k) = sum of NBY block-row sums + mvcost; returns the minimum
+// and its first row.  NBY (block rows of the PU: 1 / 2 / 4, 3 for the 12-row AMP parts) is a template so that the loads of a
+// grid point are straight-line code.
+template <int NBY>
+__device__ __forceinline__ void mew_maps_scan(uint32_t base, int nrows, uint32_t eoff, unsigned esh, uint32_t soff, unsigned ssh, bool hasS,
+                                              int xc, const uint16_t* __restrict__ yp, int ystep, int& best, int& bestRow)
+{
+    constexpr uint32_t BR = MEW_MAP_ROWS * 32 * 8;                  // bytes between block rows
+    uint32_t a = base;
+    if (hasS)
+    {
+        for (int k = 0; k < nrows; k++, a += 32 * 8, yp += ystep)
+        {
+            int sad = 0;
+#pragma unroll
+            for (int by = 0; by < NBY; by++)
+                sad += (int)((lds32(a + by * BR + eoff) >> esh) & 0xffffu) - (int)((lds32(a + by * BR + soff) >> ssh) & 0xffffu);
+            const int cost = sad + (int)(uint16_t)(xc + (int)__ldg(yp));
+            if (cost < best) { best = cost; bestRow = k; }          // k ascending: strict '<' keeps the earliest
+        }
+    }
+    else
+    {
+        for (int k = 0; k < nrows; k++, a += 32 * 8, yp += ystep)
+        {
+            int sad = 0;
+#pragma unroll
+            for (int by = 0; by < NBY; by++) sad += (int)((lds32(a + by * BR + eoff) >> esh) & 0xffffu);
+            const int cost = sad + (int)(uint16_t)(xc + (int)__ldg(yp));
+            if (cost < best) { best = cost; bestRow = k; }
+        }
+    }
+}
+
 // Raster refinement of one PU out of the cell maps (same result as mew_raster_t: minimum cost, ties to the lowest raster index).
 template <typename P>
 __device__ __forceinline__ void mew_raster_maps(const MeWin<P>& c, MeStar& s)
@@ -348,27 +469,22 @@ __device__ __forceinline__ void mew_raster_maps(const MeWin<P>& c, MeStar& s)
     const bool x8 = (col & 3) == 3;
     const int xc = (int)__ldg(c.mvc + ((x8 ? gx * 8 : gx * 4) - c.mvpx));
     const int bx0 = (c.ox - cell->ox) >> 2, by0 = (c.oy - cell->oy) >> 2, nbx = c.w >> 2, nby = c.h >> 2;
-    // block-row sum = P[e] - P[s] (s = bx0 - 1; nothing to subtract when the PU starts at the cell's left edge)
+    // block-row sum = P[e] - P[bx0 - 1] (nothing to subtract when the PU starts at the cell's left edge); each prefix is the
+    // 16-bit half `sh` of the 32-bit word `off` of the entry
     const int e = bx0 + nbx - 1, sx = bx0 - 1;
-    const bool ehi = e >= 2, shi = sx >= 2;
-    const unsigned esh = (unsigned)(e & 1) * 16u, ssh = (unsigned)(sx & 1) * 16u;
+    const uint32_t eoff = (uint32_t)(e >> 1) * 4u, soff = (uint32_t)(max(sx, 0) >> 1) * 4u;
+    const unsigned esh = (unsigned)(e & 1) * 16u, ssh = (unsigned)(max(sx, 0) & 1) * 16u;
     const uint32_t base = cell->map + (uint32_t)((by0 * MEW_MAP_ROWS * 32 + col) * 8);
-    const uint16_t* ymvc = c.mvc - c.mvpy;
     const int ymul = x8 ? 8 : 4;
-    int best = 0x7fffffff, bestIdx = 0x7fffffff;
-    for (int k = 0; k < nrows; k++)
-    {
-        int sad = 0;
-        uint32_t a = base + (uint32_t)(k * 32 * 8);
-        for (int by = 0; by < nby; by++, a += MEW_MAP_ROWS * 32 * 8)
-        {
-            const uint2 v = lds64(a);
-            sad += (int)(((ehi ? v.y : v.x) >> esh) & 0xffffu);
-            if (sx >= 0) sad -= (int)(((shi ? v.y : v.x) >> ssh) & 0xffffu);
-        }
-        const int cost = sad + (int)(uint16_t)(xc + (int)__ldg(ymvc + (c.miny + k * 5) * ymul));
-        if (act && cost < best) { best = cost; bestIdx = k * ncols + col; }       // k ascending: strict '<' keeps the earliest
-    }
+    const uint16_t* yp = c.mvc - c.mvpy + c.miny * ymul;                 // the vertical mvcost term of grid row k: yp[k * 5 * ymul]
+    const int ystep = 5 * ymul;
+    int best = 0x7fffffff, bestRow = 0;
+    if (nby == 4)      mew_maps_scan<4>(base, nrows, eoff, esh, soff, ssh, sx >= 0, xc, yp, ystep, best, bestRow);
+    else if (nby == 2) mew_maps_scan<2>(base, nrows, eoff, esh, soff, ssh, sx >= 0, xc, yp, ystep, best, bestRow);
+    else if (nby == 1) mew_maps_scan<1>(base, nrows, eoff, esh, soff, ssh, sx >= 0, xc, yp, ystep, best, bestRow);
+    else               mew_maps_scan<3>(base, nrows, eoff, esh, soff, ssh, sx >= 0, xc, yp, ystep, best, bestRow);   // AMP: 12 rows
+    if (!act) best = 0x7fffffff;
+    const int bestIdx = bestRow * ncols + col;
     const int m = __reduce_min_sync(0xffffffffu, best);
     const int mi = __reduce_min_sync(0xffffffffu, best == m ? bestIdx : 0x7fffffff);
     if (m < s.bcost)
@@ -384,7 +500,11 @@ __device__ __forceinline__ void me_raster(const MeWin<P>& c, MeStar& s)
 {
     if (c.cell) { mew_raster_maps<P>(c, s); return; }              // 16x16 cell with a shared grid: costs out of the SAD maps
     // pow2 PUs use the widest aligned segment; AMP widths (12 / 24 / 48) walk 4-byte words
-    if (c.pow2 && c.lgsegw == 2)      mew_raster_na<P, 2>(c, s);
+    const int rowB = c.w * (int)sizeof(P);
+    if (c.pow2 && c.lgsegw == 2 && rowB == 64)      mew_raster_wide_na<P, 4>(c, s);
+    else if (c.pow2 && c.lgsegw == 2 && rowB == 32) mew_raster_wide_na<P, 2>(c, s);
+    else if (c.pow2 && c.lgsegw == 2 && rowB == 16) mew_raster_wide_na<P, 1>(c, s);
+    else if (c.pow2 && c.lgsegw == 2) mew_raster_na<P, 2>(c, s);
     else if (c.pow2 && c.lgsegw == 1) mew_raster_na<P, 1>(c, s);
     else                              mew_raster_na<P, 0>(c, s);
 }
