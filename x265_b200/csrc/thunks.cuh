@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include <type_traits>
 #include <stdlib.h>
+#include "loopfilter.cuh"
 
 namespace thunk {
 
@@ -306,6 +307,157 @@ static void intra_allangs(int N, P* dst, const P* refp, const P* filtp, int bLum
     memcpy(dst, s.h<P>(od), (size_t)33 * N * N * sizeof(P));
 }
 
+// ---------- in-loop filters: deblocking edge filters and SAO (loopfilter.cuh) ----------
+// Each call gathers exactly the samples the C primitive reads into compact blocks, runs one small kernel and scatters back
+// exactly the samples it writes (the reference harnesses memcmp whole buffers).
+template <typename P>
+static void lf_sign(int8_t* dst, const P* src1, const P* src2, const int endX)
+{
+    Stage s; s.ctx = tctx();
+    size_t o1 = s.put(src1, endX, endX, 1, sizeof(P)), o2 = s.put(src2, endX, endX, 1, sizeof(P)), od = s.reserve(endX);
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("sign"); return; }
+    lf::k_sign<P><<<1, 128, 0, s.ctx->stream>>>(s.d<int8_t>(od), s.d<P>(o1), s.d<P>(o2), endX);
+    s.ctx->launches++;
+    if (s.download(od, endX)) { fail("sign"); return; }
+    memcpy(dst, s.h<int8_t>(od), endX);
+}
+template <typename P>
+static void lf_sao_e0(P* rec, int8_t* offsetEo, int width, int8_t* signLeft, intptr_t stride)
+{
+    Stage s; s.ctx = tctx();
+    size_t oi = s.put(rec, stride, width + 1, 2, sizeof(P)), oo = s.put(offsetEo, 5, 5, 1, 1), ol = s.put(signLeft, 2, 2, 1, 1),
+           od = s.reserve((size_t)2 * width * sizeof(P));
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("saoCuOrgE0"); return; }
+    lf::k_sao_e0<P><<<1, 128, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(oo), width, s.d<int8_t>(ol));
+    s.ctx->launches++;
+    if (s.download(od, (size_t)2 * width * sizeof(P))) { fail("saoCuOrgE0"); return; }
+    s.get(rec, stride, width, 2, sizeof(P), od);
+}
+template <typename P>
+static void lf_sao_e1_rows(P* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t stride, int width, int rows)
+{
+    Stage s; s.ctx = tctx();
+    size_t oi = s.put(rec, stride, width, rows + 1, sizeof(P)), oo = s.put(offsetEo, 5, 5, 1, 1), ou = s.put(upBuff1, width, width, 1, 1),
+           od = s.reserve((size_t)rows * width * sizeof(P));
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("saoCuOrgE1"); return; }
+    lf::k_sao_e1<P><<<1, 128, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(ou), s.d<int8_t>(oo), width, rows);
+    s.ctx->launches++;
+    if (s.download(ou, (od + (size_t)rows * width * sizeof(P)) - ou)) { fail("saoCuOrgE1"); return; }
+    memcpy(upBuff1, s.h<int8_t>(ou), width);
+    s.get(rec, stride, width, rows, sizeof(P), od);
+}
+template <typename P> static void lf_sao_e1(P* rec, int8_t* up, int8_t* off, intptr_t stride, int width) { lf_sao_e1_rows<P>(rec, up, off, stride, width, 1); }
+template <typename P> static void lf_sao_e1_2rows(P* rec, int8_t* up, int8_t* off, intptr_t stride, int width) { lf_sao_e1_rows<P>(rec, up, off, stride, width, 2); }
+template <typename P>
+static void lf_sao_e2(P* rec, int8_t* bufft, int8_t* buff1, int8_t* offsetEo, int width, intptr_t stride)
+{
+    Stage s; s.ctx = tctx();
+    size_t oi = s.reserve((size_t)2 * width * sizeof(P));
+    if (s.ok) { memcpy(s.h<P>(oi), rec, (size_t)width * sizeof(P)); memcpy(s.h<P>(oi) + width, rec + stride + 1, (size_t)width * sizeof(P)); }
+    size_t oo = s.put(offsetEo, 5, 5, 1, 1), o1 = s.put(buff1, width, width, 1, 1), ot = s.reserve(width), od = s.reserve((size_t)width * sizeof(P));
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("saoCuOrgE2"); return; }
+    lf::k_sao_e2<P><<<1, 128, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(ot), s.d<int8_t>(o1), s.d<int8_t>(oo), width);
+    s.ctx->launches++;
+    if (s.download(ot, (od + (size_t)width * sizeof(P)) - ot)) { fail("saoCuOrgE2"); return; }
+    memcpy(bufft + 1, s.h<int8_t>(ot), width);
+    memcpy(rec, s.h<P>(od), (size_t)width * sizeof(P));
+}
+template <typename P>
+static void lf_sao_e3(P* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t stride, int startX, int endX)
+{
+    const int n = endX - startX - 1;
+    if (n <= 0) return;
+    Stage s; s.ctx = tctx();
+    size_t oi = s.reserve((size_t)2 * n * sizeof(P));
+    if (s.ok) { memcpy(s.h<P>(oi), rec + startX + 1, (size_t)n * sizeof(P)); memcpy(s.h<P>(oi) + n, rec + startX + 1 + stride, (size_t)n * sizeof(P)); }
+    size_t oo = s.put(offsetEo, 5, 5, 1, 1), ou = s.put(upBuff1 + startX, n + 1, n + 1, 1, 1), ow = s.reserve(n), od = s.reserve((size_t)n * sizeof(P));
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("saoCuOrgE3"); return; }
+    lf::k_sao_e3<P><<<1, 128, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(ou), s.d<int8_t>(ow), s.d<int8_t>(oo), n);
+    s.ctx->launches++;
+    if (s.download(ow, (od + (size_t)n * sizeof(P)) - ow)) { fail("saoCuOrgE3"); return; }
+    memcpy(upBuff1 + startX, s.h<int8_t>(ow), n);                     // upBuff1[x - 1] for x = startX + 1 .. endX - 1
+    memcpy(rec + startX + 1, s.h<P>(od), (size_t)n * sizeof(P));
+}
+template <typename P>
+static void lf_sao_b0(P* rec, const int8_t* offset, int ctuWidth, int ctuHeight, intptr_t stride)
+{
+    Stage s; s.ctx = tctx();
+    const size_t n = (size_t)ctuWidth * ctuHeight;
+    size_t oi = s.put(rec, stride, ctuWidth, ctuHeight, sizeof(P)), oo = s.put(offset, 32, 32, 1, 1), od = s.reserve(n * sizeof(P));
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("saoCuOrgB0"); return; }
+    lf::k_sao_b0<P><<<(int)((n + 255) / 256), 256, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(oo), (int)n);
+    s.ctx->launches++;
+    if (s.download(od, n * sizeof(P))) { fail("saoCuOrgB0"); return; }
+    s.get(rec, stride, ctuWidth, ctuHeight, sizeof(P), od);
+}
+// 4 lines x 8 samples across the edge: sample (i, k) = src[i * srcStep + (k - 4) * offset]
+template <typename P>
+static void lf_deblock(P* src, intptr_t srcStep, intptr_t offset, int a, int b, int c, bool luma)
+{
+    Stage s; s.ctx = tctx();
+    size_t oi = s.reserve(32 * sizeof(P)), od = s.reserve(32 * sizeof(P));
+    if (!s.ok) { fail("stage overflow"); return; }
+    for (int i = 0; i < 4; i++) for (int k = 0; k < 8; k++) s.h<P>(oi)[i * 8 + k] = src[i * srcStep + (k - 4) * offset];
+    if (s.upload()) { fail("pelFilter"); return; }
+    if (luma) lf::k_deblock_luma_strong<P><<<1, 32, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), a, b);
+    else      lf::k_deblock_chroma<P><<<1, 32, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), a, b, c);
+    s.ctx->launches++;
+    if (s.download(od, 32 * sizeof(P))) { fail("pelFilter"); return; }
+    const int k0 = luma ? 1 : 3, k1 = luma ? 6 : 4;                 // the samples the C primitive writes
+    for (int i = 0; i < 4; i++) for (int k = k0; k <= k1; k++) src[i * srcStep + (k - 4) * offset] = s.h<P>(od)[i * 8 + k];
+}
+template <typename P> static void lf_luma_strong(P* src, intptr_t srcStep, intptr_t offset, int32_t tcP, int32_t tcQ) { lf_deblock<P>(src, srcStep, offset, tcP, tcQ, 0, true); }
+template <typename P> static void lf_chroma(P* src, intptr_t srcStep, intptr_t offset, int32_t tc, int32_t maskP, int32_t maskQ) { lf_deblock<P>(src, srcStep, offset, tc, maskP, maskQ, false); }
+
+// SAO statistics.  what: 0 BO, 1 E0, 2 E1, 3 E2, 4 E3.  diff has the fixed pitch MAX_CU_SIZE = 64.
+template <typename P>
+static void lf_sao_stats(int what, const int16_t* diff, const P* rec, intptr_t stride, int8_t* upBuff1, int8_t* upBufft, int endX, int endY,
+                         int32_t* stats, int32_t* count)
+{
+    if (endX <= 0 || endY <= 0) return;
+    Stage s; s.ctx = tctx();
+    const int nb = what == 0 ? 32 : 5;
+    size_t odf = s.put(diff, 64, 64, endY, 2);
+    // rec block: columns [c0, c1), rows [0, r1)
+    const int c0 = (what == 1 || what == 3 || what == 4) ? -1 : 0, c1 = (what == 1 || what == 3 || what == 4) ? endX + 1 : endX;
+    const int r1 = (what == 0 || what == 1) ? endY : endY + 1;
+    size_t orc = s.put(rec + c0, stride, c1 - c0, r1, sizeof(P));
+    size_t ost = s.put(stats, nb, nb, 1, 4), oct = s.put(count, nb, nb, 1, 4);
+    size_t oa = 0, ob = 0; int na = 0, nbuf = 0;
+    if (what == 2) { na = endX; oa = s.put(upBuff1, na, na, 1, 1); }
+    if (what == 3) { na = endX + 2; oa = s.put(upBuff1 - 1, na, na, 1, 1); nbuf = na; ob = s.put(upBufft - 1, nbuf, nbuf, 1, 1); }
+    if (what == 4) { na = endX + 1; oa = s.put(upBuff1 - 1, na, na, 1, 1); }
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("saoCuStats"); return; }
+    const int rp = c1 - c0;
+    cudaStream_t st = s.ctx->stream;
+    switch (what)
+    {
+    case 0: lf::k_sao_stats_bo<P><<<1, 256, 0, st>>>(s.d<int16_t>(odf), s.d<P>(orc), rp, endX, endY, s.d<int32_t>(ost), s.d<int32_t>(oct)); break;
+    case 1: lf::k_sao_stats_e0<P><<<1, 256, 0, st>>>(s.d<int16_t>(odf), s.d<P>(orc), rp, endX, endY, s.d<int32_t>(ost), s.d<int32_t>(oct)); break;
+    case 2: lf::k_sao_stats_e1<P><<<1, 64, 0, st>>>(s.d<int16_t>(odf), s.d<P>(orc), s.d<int8_t>(oa), endX, endY, s.d<int32_t>(ost), s.d<int32_t>(oct)); break;
+    case 3: lf::k_sao_stats_e2<P><<<1, 64, 0, st>>>(s.d<int16_t>(odf), s.d<P>(orc), rp, s.d<int8_t>(oa), s.d<int8_t>(ob), endX, endY, s.d<int32_t>(ost), s.d<int32_t>(oct)); break;
+    default: lf::k_sao_stats_e3<P><<<1, 64, 0, st>>>(s.d<int16_t>(odf), s.d<P>(orc), rp, s.d<int8_t>(oa), endX, endY, s.d<int32_t>(ost), s.d<int32_t>(oct)); break;
+    }
+    s.ctx->launches++;
+    if (s.download(ost, s.used - ost)) { fail("saoCuStats"); return; }
+    memcpy(stats, s.h<int32_t>(ost), nb * 4); memcpy(count, s.h<int32_t>(oct), nb * 4);
+    if (what == 2) memcpy(upBuff1, s.h<int8_t>(oa), na);
+    if (what == 3) { memcpy(upBuff1 - 1, s.h<int8_t>(oa), na); memcpy(upBufft - 1, s.h<int8_t>(ob), nbuf); }
+    if (what == 4) memcpy(upBuff1 - 1, s.h<int8_t>(oa), na);
+}
+template <typename P> static void lf_stats_bo(const int16_t* d, const P* r, intptr_t st, int ex, int ey, int32_t* s, int32_t* c) { lf_sao_stats<P>(0, d, r, st, NULL, NULL, ex, ey, s, c); }
+template <typename P> static void lf_stats_e0(const int16_t* d, const P* r, intptr_t st, int ex, int ey, int32_t* s, int32_t* c) { lf_sao_stats<P>(1, d, r, st, NULL, NULL, ex, ey, s, c); }
+template <typename P> static void lf_stats_e1(const int16_t* d, const P* r, intptr_t st, int8_t* u1, int ex, int ey, int32_t* s, int32_t* c) { lf_sao_stats<P>(2, d, r, st, u1, NULL, ex, ey, s, c); }
+template <typename P> static void lf_stats_e2(const int16_t* d, const P* r, intptr_t st, int8_t* u1, int8_t* ut, int ex, int ey, int32_t* s, int32_t* c) { lf_sao_stats<P>(3, d, r, st, u1, ut, ex, ey, s, c); }
+template <typename P> static void lf_stats_e3(const int16_t* d, const P* r, intptr_t st, int8_t* u1, int ex, int ey, int32_t* s, int32_t* c) { lf_sao_stats<P>(4, d, r, st, u1, NULL, ex, ey, s, c); }
+
 // ---------- lowres ----------
 template <typename P>
 static void frame_init_lowres(const P* src0, P* d0, P* dh, P* dv, P* dc, intptr_t sstride, intptr_t dstride, int width, int height)
@@ -520,6 +672,21 @@ static void* lookup(const char* name, int i, int j, int k)
     if (!strcmp(name, "dequant_scaling")) return (void*)dequant_scaling;
     if (!strcmp(name, "denoiseDct")) return (void*)denoise;
     if (!strcmp(name, "propagateCost")) return (void*)propagate_cost;
+    // in-loop filters (loopfilter.cpp:184-200, sao.cpp:1927-1935); i = the array index of the two-entry fields
+    if (!strcmp(name, "sign")) return (void*)lf_sign<P>;
+    if (!strcmp(name, "saoCuOrgE0")) return (void*)lf_sao_e0<P>;
+    if (!strcmp(name, "saoCuOrgE1")) return (void*)lf_sao_e1<P>;
+    if (!strcmp(name, "saoCuOrgE1_2Rows")) return (void*)lf_sao_e1_2rows<P>;
+    if (!strcmp(name, "saoCuOrgE2")) return (i == 0 || i == 1) ? (void*)lf_sao_e2<P> : NULL;
+    if (!strcmp(name, "saoCuOrgE3")) return (i == 0 || i == 1) ? (void*)lf_sao_e3<P> : NULL;
+    if (!strcmp(name, "saoCuOrgB0")) return (void*)lf_sao_b0<P>;
+    if (!strcmp(name, "pelFilterLumaStrong")) return (i == 0 || i == 1) ? (void*)lf_luma_strong<P> : NULL;
+    if (!strcmp(name, "pelFilterChroma")) return (i == 0 || i == 1) ? (void*)lf_chroma<P> : NULL;
+    if (!strcmp(name, "saoCuStatsBO")) return (void*)lf_stats_bo<P>;
+    if (!strcmp(name, "saoCuStatsE0")) return (void*)lf_stats_e0<P>;
+    if (!strcmp(name, "saoCuStatsE1")) return (void*)lf_stats_e1<P>;
+    if (!strcmp(name, "saoCuStatsE2")) return (void*)lf_stats_e2<P>;
+    if (!strcmp(name, "saoCuStatsE3")) return (void*)lf_stats_e3<P>;
     if (!strcmp(name, "scale2D_64to32")) return (void*)X::scale2D;
     if (!strcmp(name, "weight_pp")) return (void*)X::weight_pp;
     if (!strcmp(name, "weight_sp")) return (void*)X::weight_sp;

@@ -92,6 +92,24 @@ void setupCudaPrimitives(EncoderPrimitives& p, int /*cpuMask*/)
     SET(p.dequant_scaling, dequant_scaling_t, "dequant_scaling", 0, 0, 0);
     SET(p.denoiseDct, denoiseDct_t, "denoiseDct", 0, 0, 0);
     SET(p.propagateCost, cutree_propagate_cost, "propagateCost", 0, 0, 0);
+    /* in-loop filters: deblocking edge filters and SAO (loopfilter.cpp:184-200, sao.cpp:1927-1935) */
+    SET(p.sign, sign_t, "sign", 0, 0, 0);
+    SET(p.saoCuOrgE0, saoCuOrgE0_t, "saoCuOrgE0", 0, 0, 0);
+    SET(p.saoCuOrgE1, saoCuOrgE1_t, "saoCuOrgE1", 0, 0, 0);
+    SET(p.saoCuOrgE1_2Rows, saoCuOrgE1_t, "saoCuOrgE1_2Rows", 0, 0, 0);
+    SET(p.saoCuOrgB0, saoCuOrgB0_t, "saoCuOrgB0", 0, 0, 0);
+    SET(p.saoCuStatsBO, saoCuStatsBO_t, "saoCuStatsBO", 0, 0, 0);
+    SET(p.saoCuStatsE0, saoCuStatsE0_t, "saoCuStatsE0", 0, 0, 0);
+    SET(p.saoCuStatsE1, saoCuStatsE1_t, "saoCuStatsE1", 0, 0, 0);
+    SET(p.saoCuStatsE2, saoCuStatsE2_t, "saoCuStatsE2", 0, 0, 0);
+    SET(p.saoCuStatsE3, saoCuStatsE3_t, "saoCuStatsE3", 0, 0, 0);
+    for (int e = 0; e < 2; e++)
+    {
+        SET(p.saoCuOrgE2[e], saoCuOrgE2_t, "saoCuOrgE2", e, 0, 0);
+        SET(p.saoCuOrgE3[e], saoCuOrgE3_t, "saoCuOrgE3", e, 0, 0);
+        SET(p.pelFilterLumaStrong[e], pelFilterLumaStrong_t, "pelFilterLumaStrong", e, 0, 0);
+        SET(p.pelFilterChroma[e], pelFilterChroma_t, "pelFilterChroma", e, 0, 0);
+    }
     SET(p.scale2D_64to32, scale2D_t, "scale2D_64to32", 0, 0, 0);
     SET(p.weight_pp, weightp_pp_t, "weight_pp", 0, 0, 0);
     SET(p.weight_sp, weightp_sp_t, "weight_sp", 0, 0, 0);
