@@ -959,6 +959,26 @@ __device__ __forceinline__ void me_set_chroma(MeChromaCtx<P>& cc, const MeCtx<P>
     cc.rcb = ((const P* const*)a.refCb)[j.ref] + coff; cc.rcr = ((const P* const*)a.refCr)[j.ref] + coff;
 }
 
+// N consecutive pixels starting at p (any alignment) as ints: aligned 32-bit loads + funnel shifts instead of N scalar
+// loads (the chroma tiles are 4 wide + 3 taps: seven byte loads per row cost seven L1 requests, three words cost three).
+// Reads up to 3 bytes before / 4 bytes after the span inside the same words (the planes have margins).
+template <typename P, int N>
+__device__ __forceinline__ void me_ld_px(const P* __restrict__ p, int (&v)[N])
+{
+    constexpr int NB = N * (int)sizeof(P), NWD = (NB + 3) / 4;                 // payload bytes / words after alignment
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+    const unsigned sh = ((unsigned)a & 3u) * 8u;
+    uint32_t w[NWD + 1], x[NWD];
+#pragma unroll
+    for (int k = 0; k <= NWD; k++) w[k] = __ldg(ap + k);
+#pragma unroll
+    for (int k = 0; k < NWD; k++) x[k] = __funnelshift_r(w[k], w[k + 1], sh);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        v[i] = sizeof(P) == 1 ? (int)((x[i >> 2] >> (8 * (i & 3))) & 255u) : (int)((x[i >> 1] >> (16 * (i & 1))) & 65535u);
+}
+
 // un-normalised 4x4 Hadamard abs-sum of (source chroma block - predicted chroma block).  One lane, registers only;
 // out of line (one copy per kernel: the ME kernels are instruction-cache sensitive).
 template <typename P>
@@ -969,9 +989,7 @@ __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* _
     if (!(xf | yf))
     {
 #pragma unroll
-        for (int y = 0; y < 4; y++)
-#pragma unroll
-            for (int x = 0; x < 4; x++) m[y][x] = (int)r[y * stride + x];
+        for (int y = 0; y < 4; y++) me_ld_px<P, 4>(r + y * stride, m[y]);
     }
     else if (!yf)
     {
@@ -980,8 +998,7 @@ __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* _
         for (int y = 0; y < 4; y++)
         {
             int p[7];
-#pragma unroll
-            for (int k = 0; k < 7; k++) p[k] = (int)r[y * stride + k - 1];
+            me_ld_px<P, 7>(r + y * stride - 1, p);
 #pragma unroll
             for (int x = 0; x < 4; x++) m[y][x] = interp_finish<DEPTH>(c0 * p[x] + c1 * p[x + 1] + c2 * p[x + 2] + c3 * p[x + 3], 0);
         }
@@ -989,15 +1006,13 @@ __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* _
     else if (!xf)
     {
         const int c0 = c_chromaFilter[yf][0], c1 = c_chromaFilter[yf][1], c2 = c_chromaFilter[yf][2], c3 = c_chromaFilter[yf][3];
+        int p[7][4];
+#pragma unroll
+        for (int k = 0; k < 7; k++) me_ld_px<P, 4>(r + (k - 1) * stride, p[k]);
 #pragma unroll
         for (int x = 0; x < 4; x++)
-        {
-            int p[7];
 #pragma unroll
-            for (int k = 0; k < 7; k++) p[k] = (int)r[(k - 1) * stride + x];
-#pragma unroll
-            for (int y = 0; y < 4; y++) m[y][x] = interp_finish<DEPTH>(c0 * p[y] + c1 * p[y + 1] + c2 * p[y + 2] + c3 * p[y + 3], 0);
-        }
+            for (int y = 0; y < 4; y++) m[y][x] = interp_finish<DEPTH>(c0 * p[y][x] + c1 * p[y + 1][x] + c2 * p[y + 2][x] + c3 * p[y + 3][x], 0);
     }
     else
     {
@@ -1008,8 +1023,7 @@ __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* _
         for (int k = 0; k < 7; k++)
         {
             int p[7];
-#pragma unroll
-            for (int i = 0; i < 7; i++) p[i] = (int)r[(k - 1) * stride + i - 1];
+            me_ld_px<P, 7>(r + (k - 1) * stride - 1, p);
 #pragma unroll
             for (int x = 0; x < 4; x++) mid[k][x] = interp_finish<DEPTH>(h0 * p[x] + h1 * p[x + 1] + h2 * p[x + 2] + h3 * p[x + 3], 1);
         }
@@ -1022,8 +1036,10 @@ __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* _
 #pragma unroll
     for (int y = 0; y < 4; y++)
     {
+        int fv[4];
+        me_ld_px<P, 4>(f + y * stride, fv);
 #pragma unroll
-        for (int x = 0; x < 4; x++) m[y][x] = (int)f[y * stride + x] - m[y][x];
+        for (int x = 0; x < 4; x++) m[y][x] = fv[x] - m[y][x];
         had4(m[y][0], m[y][1], m[y][2], m[y][3]);
     }
     int acc = 0;

@@ -307,7 +307,7 @@ __device__ __forceinline__ void mew_raster_wide(const MeWin<P>& c, MeStar& s)
 #pragma unroll
                 for (int q = 0; q < NW; q++) r[q] = __funnelshift_r(w[q], w[q + 1], sh);
                 // live candidates of this row: slot i is live iff lo <= i <= hi and its source row 5 i + t exists
-                const int ihi = min(hi, (c.h - 1 - t) / RD);
+                const int ihi = c.h - 1 - t >= 0 ? min(hi, (c.h - 1 - t) / RD) : -1;
                 const uint32_t fa = c.fenc + t * c.fpitch;
 #pragma unroll
                 for (int i = 0; i < NA; i++)
