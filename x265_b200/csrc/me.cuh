@@ -863,8 +863,11 @@ __device__ __forceinline__ void me_star_point(int mylvl, int k, int ox, int oy, 
 // same point reads its candidates' SADs from a table computed once per cell.  Global-memory contexts never have one.
 template <typename P> __device__ __forceinline__ bool me_star_cached(const MeCtx<P>&) { return false; }
 template <typename P> __device__ __forceinline__ int me_star_lookup(const MeCtx<P>&, int, int, int, int) { return 0; }
-template <typename P> __device__ __forceinline__ bool me_star_cached(const MeWin<P>& c);
-template <typename P> __device__ __forceinline__ int me_star_lookup(const MeWin<P>& c, int mylvl, int k, int px, int py);
+template <typename P> struct MeWinCell;
+template <typename P> __device__ __forceinline__ bool me_star_cached(const MeWin<P>&);
+template <typename P> __device__ __forceinline__ int me_star_lookup(const MeWin<P>&, int, int, int, int);
+template <typename P> __device__ __forceinline__ bool me_star_cached(const MeWinCell<P>& c);
+template <typename P> __device__ __forceinline__ int me_star_lookup(const MeWinCell<P>& c, int mylvl, int k, int px, int py);
 
 template <typename CTX>
 __device__ __forceinline__ void me_star_pattern(const CTX& c, MeStar& s, int earlyExitIters, int merange, bool first = false)
@@ -981,18 +984,20 @@ __device__ __forceinline__ void me_ld_px(const P* __restrict__ p, int (&v)[N])
 
 // un-normalised 4x4 Hadamard abs-sum of (source chroma block - predicted chroma block).  One lane, registers only;
 // out of line (one copy per kernel: the ME kernels are instruction-cache sensitive).
+// ONE code path for all fractional phases: the separable form filter_hps(rowExt) -> filter_vsp of the reference's hv case
+// (ipfilter.cpp:120-162, 241-282) with the identity taps {0, 64, 0, 0} for a zero phase reproduces the direct forms exactly:
+//   yf == 0 is excluded below only for 10-bit horizontal-only phases, where hps drops two bits that hpp keeps;
+//   xf == 0: mid = 64 p - 8192 (8-bit) / 16 p - 8192 (10-bit) is exact, so vsp gives (sum(c p) + 32) >> 6 = filter_vpp;
+//   xf == yf == 0: the pixel itself.
+// Lanes of a pass hold candidates of different phases: a single path means no divergence and a small body (the kernels
+// with this term ran at a 60 % instruction-cache hit rate with the four-way version).
 template <typename P>
 __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* __restrict__ r, int stride, int xf, int yf)
 {
     constexpr int DEPTH = PixTraits<P>::depth;
     int m[4][4];
-    if (!(xf | yf))
-    {
-#pragma unroll
-        for (int y = 0; y < 4; y++) me_ld_px<P, 4>(r + y * stride, m[y]);
-    }
-    else if (!yf)
-    {
+    if (DEPTH != 8 && xf && !yf)
+    {   // 10-bit horizontal only: filter_hpp directly
         const int c0 = c_chromaFilter[xf][0], c1 = c_chromaFilter[xf][1], c2 = c_chromaFilter[xf][2], c3 = c_chromaFilter[xf][3];
 #pragma unroll
         for (int y = 0; y < 4; y++)
@@ -1002,17 +1007,6 @@ __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* _
 #pragma unroll
             for (int x = 0; x < 4; x++) m[y][x] = interp_finish<DEPTH>(c0 * p[x] + c1 * p[x + 1] + c2 * p[x + 2] + c3 * p[x + 3], 0);
         }
-    }
-    else if (!xf)
-    {
-        const int c0 = c_chromaFilter[yf][0], c1 = c_chromaFilter[yf][1], c2 = c_chromaFilter[yf][2], c3 = c_chromaFilter[yf][3];
-        int p[7][4];
-#pragma unroll
-        for (int k = 0; k < 7; k++) me_ld_px<P, 4>(r + (k - 1) * stride, p[k]);
-#pragma unroll
-        for (int x = 0; x < 4; x++)
-#pragma unroll
-            for (int y = 0; y < 4; y++) m[y][x] = interp_finish<DEPTH>(c0 * p[y][x] + c1 * p[y + 1][x] + c2 * p[y + 2][x] + c3 * p[y + 3][x], 0);
     }
     else
     {
@@ -1052,6 +1046,20 @@ __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* _
     return acc;
 }
 
+// position of the (n + 1)-th set bit of `mask` (n < popc(mask)): five halving steps on population counts (__fns is a
+// long software loop: it was 17 % of the instructions of the chroma kernels)
+__device__ __forceinline__ int me_nth_set_bit(unsigned mask, int n)
+{
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1)
+    {
+        const int c = __popc(mask & ((1u << w) - 1u));
+        if (n >= c) { n -= c; mask >>= w; pos += w; }
+    }
+    return pos;
+}
+
 // Cb + Cr chroma SATD of the candidates of a burst: lane k (k < n, bit k of `need` set) receives candidate k's cost.
 // chromaSatd is the luma SATD primitive of the chroma-sized block (primitives.cpp:139-158): 8x4 tiles when the chroma
 // width is a multiple of 8, else 4x4 tiles, each tile halved on its own (pixel.cpp:210-297, 1131-1155).
@@ -1076,7 +1084,7 @@ __device__ __forceinline__ int me_chroma_batch(const MeCtx<P>& c, const MeChroma
         const bool live = it < total;
         const int ci = live ? it / ipc : 0;
         const int rem = it - ci * ipc;
-        const int k = (int)__fns(need, 0, ci + 1);                   // the ci-th needed candidate
+        const int k = need == (nneed >= 32 ? 0xffffffffu : ((1u << nneed) - 1u)) ? ci : me_nth_set_bit(need, ci);   // the ci-th needed candidate
         const int kqx = __shfl_sync(0xffffffffu, qx, k & 31), kqy = __shfl_sync(0xffffffffu, qy, k & 31);
         int v = 0;
         if (live)
@@ -1099,7 +1107,7 @@ __device__ __forceinline__ int me_chroma_batch(const MeCtx<P>& c, const MeChroma
         for (int q = c0; q <= c1; q++)
         {
             const int tot = __reduce_add_sync(0xffffffffu, (live && ci == q) ? v : 0);
-            const int kq = (int)__fns(need, 0, q + 1);
+            const int kq = me_nth_set_bit(need, q);
             if (c.lane == kq) out += tot;
         }
     }

@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "me.cuh"
 #include <cuda.h>
+#include <type_traits>
 
 #define MEW_BOX_ROWS 16                    // rows per TMA tile
 #define MEW_NCLS 5                         // box-width classes
@@ -52,6 +53,11 @@ struct MeWin
     bool star;                             // this job starts at the cell's common start point: first star round out of the star table
 };
 
+// The context of the 16x16-cell kernel: same fields, its own overloads of me_raster / me_star_cached so that each kernel
+// instantiation carries only the code it can execute (the kernels are instruction-cache bound: the CU 32 / CU 64 kernel has
+// no map / star-table code, the cell kernel none of the wide column-walk variants).
+template <typename P> struct MeWinCell : MeWin<P> {};
+
 // 16x16 cell groups: all PUs of the cell (16x16 CU + four 8x8 CUs) that share one raster grid (same mvmin / mvmax: the
 // predictor field is 16x16-granular, so inside the picture they all do) get their raster costs from ONE set of SAD maps:
 // the SAD of each of the cell's sixteen 4x4 blocks at every grid point, computed once by whichever warps need it
@@ -74,6 +80,8 @@ struct MewCell
     // rounded MVP): per candidate of StarPatternSearch's levels 0-5 the same 4 x (4 x u16 prefix sums) as the raster maps
     int starOn, sx, sy;                    // table valid; the common start point (full-pel, relative like minx)
     uint32_t star;                         // shared address: [MEW_STAR_POINTS][block row 4] x 8 bytes
+    uint32_t zero;                         // shared address of a zero word
+    int zeroWord;
 };
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -192,7 +200,6 @@ __device__ __forceinline__ int me_eval_points(const MeWin<P>& c, int n, int px, 
     if (c.lane < n) cost = mysad + (x8 ? mew_mvcost(c, px * 8, py * 8) : mew_mvcost(c, px * 4, py * 4));
     return cost;
 }
-
 // ---- raster refinement out of the window (motion.cpp:1171-1201) ---------------------------------------------------
 // Grid of step 5 over [minx, maxx] x [miny, maxy] in raster order; the reference's sequential `cost < bcost` chain = the
 // minimum with ties to the lowest raster index.  Lane = grid column; NA = accumulators = ceil(h / 5) (template: 2/4/7/13).
@@ -412,33 +419,21 @@ __device__ __forceinline__ void mew_cell_map_task(const MeWin<P>& c, const MewCe
 // and its first row.  NBY (block rows of the PU: 1 / 2 / 4, 3 for the 12-row AMP parts) is a template so that the loads of a
 // grid point are straight-line code.
 template <int NBY>
-__device__ __forceinline__ void mew_maps_scan(uint32_t base, int nrows, uint32_t eoff, unsigned esh, uint32_t soff, unsigned ssh, bool hasS,
+__device__ __forceinline__ void mew_maps_scan(uint32_t base, int nrows, uint32_t eoff, unsigned esh, uint32_t soff, unsigned ssh, bool hasS, uint32_t zaddr,
                                               int xc, const uint16_t* __restrict__ yp, int ystep, int& best, int& bestRow)
 {
     constexpr uint32_t BR = MEW_MAP_ROWS * 32 * 8;                  // bytes between block rows
-    uint32_t a = base;
-    if (hasS)
+    // a PU at the cell's left edge subtracts nothing: its "P[-1]" reads a zero word (one code path for both cases)
+    uint32_t ae = base + eoff, as = hasS ? base + soff : zaddr;
+    const uint32_t sk = hasS ? 32u * 8u : 0u, sb = hasS ? BR : 0u;
+    for (int k = 0; k < nrows; k++, ae += 32 * 8, as += sk, yp += ystep)
     {
-        for (int k = 0; k < nrows; k++, a += 32 * 8, yp += ystep)
-        {
-            int sad = 0;
+        int sad = 0;
 #pragma unroll
-            for (int by = 0; by < NBY; by++)
-                sad += (int)((lds32(a + by * BR + eoff) >> esh) & 0xffffu) - (int)((lds32(a + by * BR + soff) >> ssh) & 0xffffu);
-            const int cost = sad + (int)(uint16_t)(xc + (int)__ldg(yp));
-            if (cost < best) { best = cost; bestRow = k; }          // k ascending: strict '<' keeps the earliest
-        }
-    }
-    else
-    {
-        for (int k = 0; k < nrows; k++, a += 32 * 8, yp += ystep)
-        {
-            int sad = 0;
-#pragma unroll
-            for (int by = 0; by < NBY; by++) sad += (int)((lds32(a + by * BR + eoff) >> esh) & 0xffffu);
-            const int cost = sad + (int)(uint16_t)(xc + (int)__ldg(yp));
-            if (cost < best) { best = cost; bestRow = k; }
-        }
+        for (int by = 0; by < NBY; by++)
+            sad += (int)((lds32(ae + by * BR) >> esh) & 0xffffu) - (int)((lds32(as + by * sb) >> ssh) & 0xffffu);
+        const int cost = sad + (int)(uint16_t)(xc + (int)__ldg(yp));
+        if (cost < best) { best = cost; bestRow = k; }              // k ascending: strict '<' keeps the earliest
     }
 }
 
@@ -473,16 +468,16 @@ __device__ __forceinline__ void mew_raster_maps(const MeWin<P>& c, MeStar& s)
     // 16-bit half `sh` of the 32-bit word `off` of the entry
     const int e = bx0 + nbx - 1, sx = bx0 - 1;
     const uint32_t eoff = (uint32_t)(e >> 1) * 4u, soff = (uint32_t)(max(sx, 0) >> 1) * 4u;
-    const unsigned esh = (unsigned)(e & 1) * 16u, ssh = (unsigned)(max(sx, 0) & 1) * 16u;
+    const unsigned esh = (unsigned)(e & 1) * 16u, ssh = sx >= 0 ? (unsigned)(sx & 1) * 16u : 0u;
     const uint32_t base = cell->map + (uint32_t)((by0 * MEW_MAP_ROWS * 32 + col) * 8);
     const int ymul = x8 ? 8 : 4;
     const uint16_t* yp = c.mvc - c.mvpy + c.miny * ymul;                 // the vertical mvcost term of grid row k: yp[k * 5 * ymul]
     const int ystep = 5 * ymul;
     int best = 0x7fffffff, bestRow = 0;
-    if (nby == 4)      mew_maps_scan<4>(base, nrows, eoff, esh, soff, ssh, sx >= 0, xc, yp, ystep, best, bestRow);
-    else if (nby == 2) mew_maps_scan<2>(base, nrows, eoff, esh, soff, ssh, sx >= 0, xc, yp, ystep, best, bestRow);
-    else if (nby == 1) mew_maps_scan<1>(base, nrows, eoff, esh, soff, ssh, sx >= 0, xc, yp, ystep, best, bestRow);
-    else               mew_maps_scan<3>(base, nrows, eoff, esh, soff, ssh, sx >= 0, xc, yp, ystep, best, bestRow);   // AMP: 12 rows
+    if (nby == 4)      mew_maps_scan<4>(base, nrows, eoff, esh, soff, ssh, sx >= 0, cell->zero, xc, yp, ystep, best, bestRow);
+    else if (nby == 2) mew_maps_scan<2>(base, nrows, eoff, esh, soff, ssh, sx >= 0, cell->zero, xc, yp, ystep, best, bestRow);
+    else if (nby == 1) mew_maps_scan<1>(base, nrows, eoff, esh, soff, ssh, sx >= 0, cell->zero, xc, yp, ystep, best, bestRow);
+    else               mew_maps_scan<3>(base, nrows, eoff, esh, soff, ssh, sx >= 0, cell->zero, xc, yp, ystep, best, bestRow);   // AMP: 12 rows
     if (!act) best = 0x7fffffff;
     const int bestIdx = bestRow * ncols + col;
     const int m = __reduce_min_sync(0xffffffffu, best);
@@ -498,8 +493,7 @@ __device__ __forceinline__ void mew_raster_maps(const MeWin<P>& c, MeStar& s)
 template <typename P>
 __device__ __forceinline__ void me_raster(const MeWin<P>& c, MeStar& s)
 {
-    if (c.cell) { mew_raster_maps<P>(c, s); return; }              // 16x16 cell with a shared grid: costs out of the SAD maps
-    // pow2 PUs use the widest aligned segment; AMP widths (12 / 24 / 48) walk 4-byte words
+    // CU 32 / CU 64 groups.  pow2 PUs use the widest aligned segment; AMP widths (12 / 24 / 48) walk 4-byte words
     const int rowB = c.w * (int)sizeof(P);
     if (c.pow2 && c.lgsegw == 2 && rowB == 64)      mew_raster_wide_na<P, 4>(c, s);
     else if (c.pow2 && c.lgsegw == 2 && rowB == 32) mew_raster_wide_na<P, 2>(c, s);
@@ -508,11 +502,21 @@ __device__ __forceinline__ void me_raster(const MeWin<P>& c, MeStar& s)
     else if (c.pow2 && c.lgsegw == 1) mew_raster_na<P, 1>(c, s);
     else                              mew_raster_na<P, 0>(c, s);
 }
+template <typename P>
+__device__ __forceinline__ void me_raster(const MeWinCell<P>& c, MeStar& s)
+{
+    // 16x16 cells: costs out of the shared SAD maps; a PU whose grid differs from the cell's (picture edges) walks its own
+    // raster with the generic 4-byte-word variant
+    if (c.cell) mew_raster_maps<P>(c, s);
+    else        mew_raster_na<P, 0>(c, s);
+}
 
 // First star round out of the cell's star table (me.cuh: me_star_pattern): candidate k of level `mylvl` around the common start.
-template <typename P> __device__ __forceinline__ bool me_star_cached(const MeWin<P>& c) { return c.star; }
+template <typename P> __device__ __forceinline__ bool me_star_cached(const MeWin<P>&) { return false; }
+template <typename P> __device__ __forceinline__ int me_star_lookup(const MeWin<P>&, int, int, int, int) { return 0; }
+template <typename P> __device__ __forceinline__ bool me_star_cached(const MeWinCell<P>& c) { return c.star; }
 template <typename P>
-__device__ __forceinline__ int me_star_lookup(const MeWin<P>& c, int mylvl, int k, int px, int py)
+__device__ __forceinline__ int me_star_lookup(const MeWinCell<P>& c, int mylvl, int k, int px, int py)
 {
     const MewCell* cell = c.cell;
     const int idx = mylvl == 0 ? k : mylvl < 4 ? 4 + (mylvl - 1) * 8 + (k & 7) : 28 + (mylvl - 4) * 16 + (k & 15);
@@ -676,7 +680,8 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
             hdr->fx0 = fx0a; hdr->fy0 = fy0; hdr->fw = fwB; hdr->fh = fhh; hdr->ref = ref;
             // shared SAD maps: a complete 16x16 cell and a grid of at most 32 x MEW_MAP_ROWS points (lane 0 holds job 0's range)
             MewCell& cl = hdr->cell;
-            cl.on = 0; cl.starOn = 0;
+            cl.on = 0; cl.starOn = 0; cl.zeroWord = 0;
+            cl.zero = sbase + (uint32_t)offsetof(MewHdr, cell) + (uint32_t)offsetof(MewCell, zeroWord);
             if (CELL && ok && fx1 - fx0 == 16 && fy1 - fy0 == 16 && fx0a == fx0)
             {
                 const int ncols = (g0maxx - g0minx) / 5 + 1, nrows = (g0maxy - g0miny) / 5 + 1;
@@ -745,7 +750,7 @@ __global__ void __launch_bounds__(256, 3) k_me_window(const P* __restrict__ fenc
         if (slot >= g.count) break;
         const int jid = grp_jobs[g.first + slot] - job0;
         const x265cu_me_job j = jobs[jid];
-        MeWin<P> c;
+        typename std::conditional<CELL, MeWinCell<P>, MeWin<P> >::type c;
         const int py = j.offset / fstride, px = j.offset - py * fstride;
         c.win = s_win; c.pitch = pitch; c.ox = px - wx0; c.oy = py - wy0;
         c.fpitch = 64 * ES; c.fenc = s_fenc + (py - hdr->fy0) * c.fpitch + (px - hdr->fx0) * ES;
