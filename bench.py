@@ -401,6 +401,11 @@ def run_ours(args, rank, world, local_rank):
     for s in range(args.steps):
         lib.check(lib.L.x265cu_memset(lib.ctx, flush.ptr, s & 255, flush.nbytes))
         lib.sync()
+        if world > 1:
+            # untimed, like the flush: line the ranks up before the step.  The exchange inside the step is a collective, so
+            # without this the step of an early rank would absorb the host-side skew (Python, the memset) of the latest one
+            dist.barrier()
+            torch.cuda.synchronize()
         t0e = torch.cuda.Event(enable_timing=True); t1e = torch.cuda.Event(enable_timing=True)
         t0e.record(lib_stream)
         exchange(s)                                        # side stream: overlaps with the kernels below
@@ -445,24 +450,34 @@ def run_ours(args, rank, world, local_rank):
         e2e = units / (t_e2e / 1000.0)
         peak, peak_src = peaks()
         plane = W * H * es
-        # dominant kernel: the integer-search launch of the motion-estimation launches.
-        # Algorithmic (compulsory) bytes per launch: source plane + each reference plane
-        # read once + per job the 40 B job record and the 24 B phase state read and written.
+        # Dominant kernel = the longest of the three motion-estimation phases (each phase = the launches of one kernel family).
+        # Algorithmic (compulsory) bytes per phase: the source plane + every reference plane read
+        # once (+ the 4:2:0 chroma planes where the phase evaluates the chroma-SATD term) + per job the 40 B record and the
+        # 24 B phase state read and written (the sub-pel phase writes the 16 B result instead of the state).
         my_jobs = sum(an.row_range(r0, r1)[1] for r0, r1 in my_rows)
         my_share = sum(r1 - r0 for r0, r1 in my_rows) / float(an.ctu_rows)
-        me_bytes = int(plane * (1 + NREFS) * my_share) + my_jobs * (40 + 24 + 24)
-        me_ms = phases[1]
+        luma_bytes = int(plane * (1 + NREFS) * my_share)
+        chroma_bytes = int(plane // 2 * (1 + NREFS) * my_share) if CHROMA else 0
+        phase_info = [
+            ("prechecks", "k_me_chroma<P,1,*>" if CHROMA else "k_me<P,1,*>", "pre-check launches of the batched motionEstimate (MVP / zero / candidate costs; small-PU and large-PU kernels)",
+             luma_bytes + chroma_bytes + my_jobs * (40 + 24)),
+            ("integer_search", "k_me_window<P,*> (+ k_me<P,2,-1> for groups that do not fit)", "STAR integer search out of TMA-staged shared-memory search windows, one CTA per CU group / 16x16 cell",
+             luma_bytes + my_jobs * (40 + 24 + 24)),
+            ("subpel", "k_me_chroma<P,3,*>" if CHROMA else "k_me<P,3,*>", "sub-pel refinement launches (interpolation + SATD%s; small-PU and large-PU kernels)" % (" + chroma-SATD term" if CHROMA else ""),
+             luma_bytes + chroma_bytes + my_jobs * (40 + 24 + 16))]
+        dom = int(np.argmax(phases))
+        me_bytes = phase_info[dom][3]
+        me_ms = phases[dom]
         achieved = me_bytes / (me_ms / 1000.0) / 1e9
         traffic = None
         traffic_src = None
-        for name in ("me_r2_traffic.json", "me_r1_traffic.json"):
-            try:
-                tr = json.load(open(os.path.join(ROOT, "profiles", name)))
-                if ("%dx%d" % (W, H)) in tr.get("config", "") and tr.get("bit_depth", 8) == DEPTH:
-                    traffic = float(tr["traffic_bytes_per_launch"]); traffic_src = "profiles/" + name
-                    break
-            except Exception:
-                pass
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "me_r2_traffic.json")))
+            key = "%s_%dx%d_%dbit_%s" % (CFG_NAME, W, H, DEPTH, phase_info[dom][0])
+            if key in tr.get("phases", {}):
+                traffic = float(tr["phases"][key]["dram_bytes_per_step"]); traffic_src = "profiles/me_r2_traffic.json (" + tr.get("how", "ncu") + ")"
+        except Exception:
+            pass
         cfg = workload_config(args.shard)
         sizes = {"resid_bytes": plane * 2 + an.ncoef * 2 + 4 * plane, "intra_bytes": plane + an.ncu * 36 * 4}
         line = {
@@ -474,10 +489,12 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "CTUs/s", "ms_per_step": t_e2e / args.steps,
                     "h2d_bytes_per_step": int(an.h2d_bytes(field)) + (W * H // 2 * es if CHROMA else 0), "d2h_bytes_per_step": int(sum(an.d2h_bytes_rows(r0, r1) for r0, r1 in my_rows))},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "integer-search launch of the batched motionEstimate (k_me_window: TMA-staged shared-memory search window per CU group; k_me<P,2,-1> for the groups that do not fit)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": phase_info[dom][1], "what": phase_info[dom][2], "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(me_bytes), "kernel_ms": float(me_ms),
-                         "note": "not an HBM-bound kernel: ~380 SAD candidates per job against 88 B of compulsory traffic, planes L2-resident; the binding resource is the SM's shared-memory / ALU pipes (DESIGN.md section 5, profiles/)"},
+                         "note": "the dominant launches of the step (longest motion-estimation phase); not an HBM-bound kernel family: hundreds of SAD / SATD candidates per job against < 100 B of compulsory traffic, planes L2-resident; the binding resources are the SM's ALU pipe, shared-memory bandwidth and instruction cache (DESIGN.md section 5, profiles/)"},
+            "phase_rooflines": {pi[0]: {"kernel": pi[1], "ms": float(phases[i]), "algorithmic_bytes": int(pi[3]), "GBps": pi[3] / (phases[i] / 1000.0) / 1e9,
+                                        "frac": pi[3] / (phases[i] / 1000.0) / 1e9 / peak} for i, pi in enumerate(phase_info)},
             "stages_ms": {"me_stage": float(stage[0]), "me_prechecks": float(phases[0]), "me_integer_search": float(phases[1]), "me_subpel": float(phases[2]), "residual": float(stage[1]), "intra": float(stage[2])},
             "stage_rooflines": {
                 "k_cu_residual": {"achieved": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9, "unit": "GB/s", "frac": sizes["resid_bytes"] / (stage[1] / 1000.0) / 1e9 / peak},
@@ -504,7 +521,7 @@ def run_ours(args, rank, world, local_rank):
             line["checks_equal"] = bool(mine == r["checks"])
             if not line["checks_equal"]:
                 rc = 3
-        if world == 1 and args.primitives:
+        if world == 1 and not args.no_primitives:
             try:
                 line["primitives"] = primitives_leg(lib)
             except Exception as e:          # the per-primitive table must never cost the headline line
@@ -730,7 +747,7 @@ def main():
                     help="N>1 partition: a frame per GPU (weak scaling) or the CTU rows of one frame per GPU (strong scaling); "
                          "auto (default) = the frame shard as the line, with the row shard measured in the same run and attached")
     ap.add_argument("--no-chroma", action="store_true", help="luma-only motion estimation (round-1 line; the presets run with the chroma-SATD term)")
-    ap.add_argument("--primitives", action="store_true", help="add the per-primitive HBM GB/s table (8- and 10-bit) to the line")
+    ap.add_argument("--no-primitives", action="store_true", help="skip the per-primitive HBM GB/s table (8- and 10-bit) of the N=1 line")
     args = ap.parse_args()
     global CFG, CFG_NAME
     CFG_NAME = args.config

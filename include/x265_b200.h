@@ -51,7 +51,7 @@ int  x265cu_copy2d(x265cu_ctx*, void* dst, size_t dpitch, const void* src, size_
 int  x265cu_timer_begin(x265cu_ctx*);
 float x265cu_timer_end(x265cu_ctx*);
 /* number of kernels this library has launched since the ctx was created */
-uint64_t x265cu_launch_count(x265cu_ctx*);
+uint64_t x265cu_launch_count(x265cu_ctx*);   /* kernel launches of the whole process so far (all contexts, per-call table included) */
 /* device ms of the three launches of the last motion-estimation batch: pre-checks, integer search, sub-pel */
 int x265cu_me_phase_ms(x265cu_ctx*, float ms[3]);
 

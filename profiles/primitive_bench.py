@@ -22,7 +22,15 @@ W, H = 3840, 2160
 FRAMES = 24          # one launch covers a lookahead-window-sized batch: 24 stacked 2160p frames (~200 MB per plane)
 
 
+SINGLE = False       # --single: every primitive runs exactly once (the ncu dram-bytes pass: profiles/r2_final.sh)
+
+
 def timed(lib, flush, fn, reps):
+    if SINGLE:
+        lib.sync()
+        lib.timer_begin()
+        fn()
+        return lib.timer_end()
     for _ in range(2):
         fn()
     lib.sync()
@@ -69,9 +77,13 @@ def run(lib, depth=8, reps=7, frames=FRAMES, quiet=False, only=None):
     def want(name):
         return only is None or any(o in name for o in only)
 
+    launch_mark = [lib.launch_count()]
+
     def add(name, ms, nbytes, note=""):
         gbs = nbytes / (ms / 1000.0) / 1e9
-        rows.append({"kernel": name, "depth": depth, "ms": ms, "algorithmic_MB": nbytes / 1e6, "GBps": gbs, "frac_of_measured_peak": gbs / peak, "note": note})
+        l0, l1 = launch_mark[0], lib.launch_count()
+        launch_mark[0] = l1
+        rows.append({"kernel": name, "depth": depth, "ms": ms, "launch0": l0, "launch1": l1, "algorithmic_MB": nbytes / 1e6, "GBps": gbs, "frac_of_measured_peak": gbs / peak, "note": note})
         if not quiet:
             print("%-34s %8.3f ms %9.1f MB %8.1f GB/s  %5.1f%% of %.0f  %s" % (name, ms, nbytes / 1e6, gbs, 100 * gbs / peak, peak, note), flush=True)
 
@@ -177,7 +189,10 @@ def main():
     ap.add_argument("--depth", default="8,10")
     ap.add_argument("--only", default=None, help="comma-separated substrings of kernel names")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--single", action="store_true", help="run every primitive exactly once (for the ncu dram-bytes pass)")
     args = ap.parse_args()
+    global SINGLE
+    SINGLE = args.single
     lib = x265_b200.load()
     rows = []
     for d in [int(x) for x in args.depth.split(",")]:

@@ -40,6 +40,7 @@ int geo_get(int what, void* out)
     case 11: case 15: case 19: { int k = (what - 11) / 4; int32_t* o = (int32_t*)out; for (size_t i = 0; i < g_geo.grpFirst[k].size(); i++) { o[2 * i] = g_geo.grpFirst[k][i]; o[2 * i + 1] = g_geo.grpCount[k][i]; } break; }
     case 12: case 16: case 20: { int k = (what - 12) / 4; memcpy(out, g_geo.grpJobs[k].data(), sizeof(int32_t) * g_geo.grpJobs[k].size()); break; }
     case 13: case 17: case 21: { int k = (what - 13) / 4; memcpy(out, g_geo.rowGrp[k].data(), sizeof(int) * g_geo.rowGrp[k].size()); break; }
+    case 22: memcpy(out, g_geo.order.data(), sizeof(int32_t) * g_geo.order.size()); break;   /* shape-sorted job order per CTU row */
     default: return -1;
     }
     return 0;

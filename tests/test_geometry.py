@@ -110,6 +110,14 @@ def test_window_groups_partition_the_jobs(geo, size, rect, amp):
             ids = jobs[fc[rowg[r], 0]:(fc[rowg[r + 1] - 1, 0] + fc[rowg[r + 1] - 1, 1])] if rowg[r + 1] > rowg[r] else jobs[:0]
             assert ((py[ids] // 64) == r).all()
     assert (seen == 1).all()
+    # shape-sorted job order: a permutation of every CTU row's jobs, PU area non-increasing inside a row
+    order = np.zeros(g["njobs"], np.int32); geo.geo_get(22, order.ctypes.data_as(C.c_void_p))
+    for r in range(g["rows"]):
+        j0, j1 = g["rowJob"][r], g["rowJob"][r + 1]
+        seg = order[j0:j1]
+        assert np.array_equal(np.sort(seg), np.arange(j0, j1))
+        area = pus[seg, 3].astype(np.int64) * pus[seg, 4]
+        assert (np.diff(area) <= 0).all()
 
 
 def test_geometry_8k_ranges(geo):

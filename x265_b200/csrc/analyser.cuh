@@ -38,6 +38,7 @@ struct x265cu_analyser
     // planes [ref][MEW_NCLS], leftover list.  windowOn = 0 (X265CU_ME_WINDOW=0) keeps the global-memory kernel for all jobs.
     int windowOn; MeGroup* d_groups[3]; int32_t* d_grpJobs[3]; std::vector<int> rowGrp[3];
     CUtensorMap* d_tmaps; int32_t* d_left;
+    int32_t* d_order;                     // jobs of every CTU row sorted by PU shape (geometry.h)
 };
 
 static const int AN_MARGIN_X = 96, AN_MARGIN_Y = 80;       // picyuv.cpp:87-88 with maxCUSize 64
@@ -56,6 +57,7 @@ static void an_build_geometry(x265cu_analyser* a)
     a->pus.swap(g.pus); a->cus.swap(g.cus); a->tus.swap(g.tus); a->cu_jobs.swap(g.cu_jobs);
     a->ctuRows = g.ctuRows; a->rowJob.swap(g.rowJob); a->rowCu.swap(g.rowCu); a->rowTu.swap(g.rowTu);
     a->njobs = (int)a->pus.size(); a->ncu = (int)a->cus.size(); a->ntu = (int)a->tus.size(); a->ncoef = g.ncoef;
+    a->d_order = an_upload(a->ctx, g.order);
     for (int k = 0; k < 3; k++)
     {
         std::vector<MeGroup> grp(g.grpFirst[k].size());
@@ -101,6 +103,7 @@ static int an_run(x265cu_analyser* a, int stages, int r0, int r1)
                 win.grp_jobs[k] = a->d_grpJobs[k];
             }
             win.job0 = job0; win.left_count = c->d_counter + 9; win.left_list = a->d_left;
+            win.order = a->d_order + job0;
         }
         if (launch_me(c, depth, a->d_fenc + a->orgBytes, a->stride, (const void* const*)a->d_refTable, a->stride, 0,
                       a->d_mvcost + a->mvrange, a->d_jobs + job0, nj, a->d_me_out + (size_t)job0 * 4, c->d_counter,
@@ -229,7 +232,7 @@ void x265cu_analyser_destroy(x265cu_analyser* a)
     cudaStreamSynchronize(c->stream);
     void* bufs[] = { a->d_fenc, a->d_refTable, a->d_reconTable, a->d_field, a->d_mvcost, a->d_pus, a->d_cus, a->d_tus, a->d_cu_jobs, a->d_jobs,
                      a->d_me_out, a->d_me_packed, a->d_coef, a->d_cu_sse, a->d_cu_numsig, a->d_cu_ref, a->d_intra,
-                     a->d_groups[0], a->d_groups[1], a->d_groups[2], a->d_grpJobs[0], a->d_grpJobs[1], a->d_grpJobs[2], a->d_tmaps, a->d_left };
+                     a->d_groups[0], a->d_groups[1], a->d_groups[2], a->d_grpJobs[0], a->d_grpJobs[1], a->d_grpJobs[2], a->d_tmaps, a->d_left, a->d_order };
     for (void* b : bufs) cudaFree(b);
     for (int r = 0; r < a->p.numRefs; r++) cudaFree(a->d_refs[r]);
     for (int d = 0; d < 4; d++) cudaFree(a->d_recon[d]);

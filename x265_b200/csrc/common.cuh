@@ -23,10 +23,14 @@ struct x265cu_ctx
 };
 
 void x265cu_set_error(const char* what, cudaError_t e, const char* file, int line);
+// kernel launches of the whole process (every context, the per-call table's per-thread contexts included): what
+// x265cu_launch_count() reports
+extern unsigned long long g_x265cu_launches;
+static inline void x265cu_count_launch(x265cu_ctx* c) { c->launches++; __atomic_fetch_add(&g_x265cu_launches, 1ull, __ATOMIC_RELAXED); }
 
 #define CU_CHECK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
     x265cu_set_error(#expr, e__, __FILE__, __LINE__); return -1; } } while (0)
-#define CU_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { \
+#define CU_LAUNCH_CHECK(ctx) do { x265cu_count_launch(ctx); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { \
     x265cu_set_error("kernel launch", e__, __FILE__, __LINE__); return -1; } } while (0)
 
 template <typename P> struct PixTraits;

@@ -7,6 +7,7 @@
 #pragma once
 #include <stdint.h>
 #include <vector>
+#include <utility>
 
 struct PuDesc { int32_t offset; int16_t cuX, cuY; int8_t pw, ph; int16_t ref; };   // static per geometry
 struct CuDesc { int16_t x, y, size, pad; int64_t coef_off; };
@@ -25,6 +26,9 @@ struct FrameGeometry
     // largest PU first inside a group; groups are in CTU raster order (rowGrp = first group of every CTU row + end).
     // Three classes, launched separately (different shared-memory budgets): [0] = CU 64 groups, [1] = CU 32 groups, [2] = 16x16 cells.
     std::vector<int32_t> grpFirst[3], grpCount[3], grpJobs[3]; std::vector<int> rowGrp[3];
+    // the jobs of every CTU row sorted by PU shape (largest first; absolute job indices; row r = order[rowJob[r] .. rowJob[r + 1])):
+    // the pre-check and sub-pel launches hand out jobs in this order so that all warps run the same code paths together
+    std::vector<int32_t> order;
 };
 
 // partitions of a CU of `size`: returns the count and fills part[k] = {x, y, w, h} relative to the CU origin
@@ -141,4 +145,29 @@ static inline void geometry_build(int W, int H, int stride, int nref, int rect, 
     for (int k = 0; k < 3; k++) g.rowGrp[k].push_back((int)g.grpFirst[k].size());
     g.rowJob.push_back((int)g.pus.size()); g.rowCu.push_back((int)g.cus.size()); g.rowTu.push_back((int)g.tus.size());
     g.ncoef = coefOff;
+    // shape-sorted job order per CTU row: counting sort on (w, h) keys, stable (area descending, then width descending)
+    g.order.resize(g.pus.size());
+    for (int r = 0; r < ctuH; r++)
+    {
+        const int j0 = g.rowJob[r], j1 = g.rowJob[r + 1];
+        // key = (area, w): collect distinct shapes
+        std::vector<std::pair<int, int> > shapes;
+        for (int j = j0; j < j1; j++)
+        {
+            const std::pair<int, int> sh(g.pus[j].pw * g.pus[j].ph, g.pus[j].pw);
+            bool seen = false;
+            for (size_t q = 0; q < shapes.size(); q++) if (shapes[q] == sh) { seen = true; break; }
+            if (!seen) shapes.push_back(sh);
+        }
+        for (size_t a = 1; a < shapes.size(); a++)          // insertion sort, descending
+        {
+            const std::pair<int, int> v = shapes[a]; size_t b = a;
+            while (b > 0 && shapes[b - 1] < v) { shapes[b] = shapes[b - 1]; b--; }
+            shapes[b] = v;
+        }
+        int pos = j0;
+        for (size_t q = 0; q < shapes.size(); q++)
+            for (int j = j0; j < j1; j++)
+                if (g.pus[j].pw * g.pus[j].ph == shapes[q].first && g.pus[j].pw == shapes[q].second) g.order[pos++] = j;
+    }
 }

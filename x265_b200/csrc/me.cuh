@@ -64,6 +64,24 @@ template <typename P> __device__ __forceinline__ int sad_word(uint32_t a, uint32
 {
     return sizeof(P) == 1 ? (int)(__vsadu4(a, b) + (uint32_t)acc) : (int)(__vsadu2(a, b) + (uint32_t)acc);
 }
+// SAD of N (<= 16) words.  8-bit: N VABSDIFF4 with accumulate.  16-bit: sm_100a has no packed absolute-difference-and-add
+// for halves (__vsadu2 is ~8 instructions); max - min per half IS native (VIMNMX.U16x2) and cannot borrow, so the N packed
+// differences are summed in the two 16-bit lanes (<= 16 * 1023 each for 10-bit pixels, <= 16 * 4095 for 12-bit) and folded
+// once: about 3 instructions per word instead of 8.
+template <typename P, int N>
+__device__ __forceinline__ int sad_words(const uint32_t (&a)[N], const uint32_t (&b)[N], int acc)
+{
+    if (sizeof(P) == 1)
+    {
+#pragma unroll
+        for (int k = 0; k < N; k++) acc = (int)(__vsadu4(a[k], b[k]) + (uint32_t)acc);
+        return acc;
+    }
+    uint32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) t += __vmaxu2(a[k], b[k]) - __vminu2(a[k], b[k]);
+    return acc + (int)(t & 0xffffu) + (int)(t >> 16);
+}
 
 // ---- full-pel SAD of up to 32 candidate positions at once (pow2 PUs) -----------------------------
 // The PU is cut into row segments of SEGW words (16 bytes when the rows are wide and aligned enough).
@@ -111,15 +129,18 @@ __device__ __forceinline__ int me_sad_multi_t(const MeCtx<P>& c, const uint8_t* 
                 const uint4 f = __ldg((const uint4*)fp);
                 const uint2 a0 = __ldg((const uint2*)rp), a1 = __ldg((const uint2*)rp + 1), a2 = __ldg((const uint2*)rp + 2);
                 const uint32_t w0 = hi8 ? a0.y : a0.x, w1 = hi8 ? a1.x : a0.y, w2 = hi8 ? a1.y : a1.x, w3 = hi8 ? a2.x : a1.y, w4 = hi8 ? a2.y : a2.x;
-                acc = sad_word<P>(f.x, __funnelshift_r(w0, w1, sh), acc); acc = sad_word<P>(f.y, __funnelshift_r(w1, w2, sh), acc);
-                acc = sad_word<P>(f.z, __funnelshift_r(w2, w3, sh), acc); acc = sad_word<P>(f.w, __funnelshift_r(w3, w4, sh), acc);
+                const uint32_t fa[4] = { f.x, f.y, f.z, f.w };
+                const uint32_t ra[4] = { __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh) };
+                acc = sad_words<P, 4>(fa, ra, acc);
             }
             else if (SEGW == 2)
             {
                 const uint2 f = __ldg((const uint2*)fp);
                 const uint2 a0 = __ldg((const uint2*)rp), a1 = __ldg((const uint2*)rp + 1);
                 const uint32_t w0 = hi8 ? a0.y : a0.x, w1 = hi8 ? a1.x : a0.y, w2 = hi8 ? a1.y : a1.x;
-                acc = sad_word<P>(f.x, __funnelshift_r(w0, w1, sh), acc); acc = sad_word<P>(f.y, __funnelshift_r(w1, w2, sh), acc);
+                const uint32_t fa[2] = { f.x, f.y };
+                const uint32_t ra[2] = { __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh) };
+                acc = sad_words<P, 2>(fa, ra, acc);
             }
             else
             {
@@ -1501,7 +1522,8 @@ template <typename P, int PHASE, int CLS>
 __global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : (CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS)) k_me(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride, int lowres,
                                                            const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
                                                            int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter,
-                                                           const int32_t* __restrict__ list = nullptr, const int* __restrict__ list_n = nullptr)
+                                                           const int32_t* __restrict__ list = nullptr, const int* __restrict__ list_n = nullptr,
+                                                           const int32_t* __restrict__ order = nullptr, int order0 = 0)
 {
     extern __shared__ unsigned char me_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1515,6 +1537,9 @@ __global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : (CLS == 1 ? M
         jid = __shfl_sync(0xffffffffu, jid, 0);
         if (jid >= n) break;
         if (list) jid = list[jid];
+        // `order`: the launch slice's jobs sorted by PU shape (absolute job indices, slice start order0): the warps of the whole
+        // GPU then run the same PU size -- the same code paths -- at the same time (the kernels are instruction-cache bound)
+        if (order) jid = order[jid] - order0;
         const x265cu_me_job j = jobs[jid];
         MeCtx<P> c;
         me_make_ctx<P>(c, j, fenc, fstride, refs, rstride, lowres, mvcost, lane, sm);
@@ -1537,7 +1562,8 @@ __global__ void __launch_bounds__(256, PHASE == 2 ? ME_P2_BLOCKS : (CLS == 1 ? M
 template <typename P, int PHASE, int CLS>
 __global__ void __launch_bounds__(256, CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS) k_me_chroma(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride,
                                                            MeChromaArgs ch, const uint16_t* __restrict__ mvcost, const x265cu_me_job* __restrict__ jobs, int n,
-                                                           int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter)
+                                                           int32_t* __restrict__ out, MeState* __restrict__ state, int* __restrict__ counter,
+                                                           const int32_t* __restrict__ order = nullptr, int order0 = 0)
 {
     extern __shared__ unsigned char me_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1548,6 +1574,7 @@ __global__ void __launch_bounds__(256, CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS)
         if (lane == 0) jid = atomicAdd(counter, 1);
         jid = __shfl_sync(0xffffffffu, jid, 0);
         if (jid >= n) break;
+        if (order) jid = order[jid] - order0;          // shape-sorted job order (see k_me)
         const x265cu_me_job j = jobs[jid];
         MeCtx<P> c;
         me_make_ctx<P>(c, j, fenc, fstride, refs, rstride, 0, mvcost, lane, sm);
@@ -1563,14 +1590,15 @@ __global__ void __launch_bounds__(256, CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS)
 
 template <typename P, int PHASE, int CLS>
 static int launch_me_chroma_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, const MeChromaArgs& ch,
-                                  const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter)
+                                  const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter,
+                                  const int32_t* order = NULL, int order0 = 0)
 {
     const int threads = 256, warps = threads / 32;
     const size_t smem = sizeof(MeShared) * warps;
     int blocks = ctx->sm_count * (CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS);
     int need = (n + warps - 1) / warps;
     if (blocks > need) blocks = need;
-    k_me_chroma<P, PHASE, CLS><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, ch, mvcost, jobs, n, out, state, counter);
+    k_me_chroma<P, PHASE, CLS><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, ch, mvcost, jobs, n, out, state, counter, order, order0);
     CU_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1578,14 +1606,14 @@ static int launch_me_chroma_phase(x265cu_ctx* ctx, const void* fenc, int fstride
 template <typename P, int PHASE, int CLS>
 static int launch_me_phase(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, int lowres,
                            const uint16_t* mvcost, const x265cu_me_job* jobs, int n, int32_t* out, MeState* state, int* counter,
-                           const int32_t* list = NULL, const int* list_n = NULL)
+                           const int32_t* list = NULL, const int* list_n = NULL, const int32_t* order = NULL, int order0 = 0)
 {
     const int threads = 256, warps = threads / 32;
     const size_t smem = PHASE == 2 ? 0 : sizeof(MeShared) * warps;      // the integer search never touches the interpolation scratch
     int blocks = ctx->sm_count * (PHASE == 2 ? ME_P2_BLOCKS : (CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS));
     int need = (n + warps - 1) / warps;
     if (blocks > need) blocks = need;
-    k_me<P, PHASE, CLS><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, lowres, mvcost, jobs, n, out, state, counter, list, list_n);
+    k_me<P, PHASE, CLS><<<blocks, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, lowres, mvcost, jobs, n, out, state, counter, list, list_n, order, order0);
     CU_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1598,6 +1626,7 @@ struct MeWinLaunch
     const void* groups[3]; int ngroups[3];                  // MeGroup lists of the launch slice: [0] CU 64 groups, [1] CU 32 groups, [2] 16x16 cells
     const int32_t* grp_jobs[3]; int job0;                   // absolute job indices; job0 = first job of the slice
     int amp;                                                // AMP partitions present (13 PUs per CU instead of 5): sizes the CTAs
+    const int32_t* order;                                   // the slice's jobs sorted by PU shape (absolute indices) or NULL
     int* left_count; int32_t* left_list;
 };
 template <typename P>
@@ -1610,15 +1639,17 @@ static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const voi
                        const MeChromaArgs* ch, const MeWinLaunch* win)
 {
     int rc = 0;
+    const int32_t* ord = (win && !lowres) ? win->order : NULL;
+    const int ord0 = win ? win->job0 : 0;
     if (ch)
     {
-        rc |= launch_me_chroma_phase<P, 1, 0>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 0);
-        rc |= launch_me_chroma_phase<P, 1, 1>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 1);
+        rc |= launch_me_chroma_phase<P, 1, 0>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 0, ord, ord0);
+        rc |= launch_me_chroma_phase<P, 1, 1>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 1, ord, ord0);
     }
     else
     {
-        rc |= launch_me_phase<P, 1, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0);
-        rc |= launch_me_phase<P, 1, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1);
+        rc |= launch_me_phase<P, 1, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 0, NULL, NULL, ord, ord0);
+        rc |= launch_me_phase<P, 1, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 1, NULL, NULL, ord, ord0);
     }
     CU_CHECK(cudaEventRecord(ctx->me_ev[1], ctx->stream));
     if (win && !lowres)
@@ -1632,13 +1663,13 @@ static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const voi
     CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
     if (ch)
     {
-        rc |= launch_me_chroma_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 3);
-        rc |= launch_me_chroma_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 4);
+        rc |= launch_me_chroma_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 3, ord, ord0);
+        rc |= launch_me_chroma_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 4, ord, ord0);
     }
     else
     {
-        rc |= launch_me_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 3);
-        rc |= launch_me_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 4);
+        rc |= launch_me_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 3, NULL, NULL, ord, ord0);
+        rc |= launch_me_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, lowres, mvcost, jobs, n, out, st, counter_dev + 4, NULL, NULL, ord, ord0);
     }
     return rc;
 }

@@ -149,8 +149,7 @@ __device__ __forceinline__ int mew_sad_multi_t(const MeWin<P>& c, int n, int off
             uint32_t f[SEGW], r[SEGW];
             mew_load_fenc<SEGW>(fp, f);
             mew_load_ref<SEGW>(rp, sh, r);
-#pragma unroll
-            for (int k = 0; k < SEGW; k++) acc = sad_word<P>(f[k], r[k], acc);
+            acc = sad_words<P, SEGW>(f, r, acc);
         }
     }
     for (int o = 1; o < (1 << lglpc); o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -245,8 +244,7 @@ __device__ __forceinline__ void mew_raster_t(const MeWin<P>& c, MeStar& s)
                             {
                                 uint32_t f[SEGW];
                                 mew_load_fenc<SEGW>(fa + (RD * i) * c.fpitch, f);    // same address in every lane: broadcast
-#pragma unroll
-                                for (int k = 0; k < SEGW; k++) acc[i] = sad_word<P>(f[k], r[k], acc[i]);
+                                acc[i] = sad_words<P, SEGW>(f, r, acc[i]);
                             }
                         }
                     }
@@ -325,8 +323,9 @@ __device__ __forceinline__ void mew_raster_wide(const MeWin<P>& c, MeStar& s)
                         for (int sg = 0; sg < NSEG; sg++)
                         {
                             const uint4 f = lds128(fa + (RD * i) * c.fpitch + sg * 16);    // same address in every lane: broadcast
-                            acc[i] = sad_word<P>(f.x, r[4 * sg], acc[i]); acc[i] = sad_word<P>(f.y, r[4 * sg + 1], acc[i]);
-                            acc[i] = sad_word<P>(f.z, r[4 * sg + 2], acc[i]); acc[i] = sad_word<P>(f.w, r[4 * sg + 3], acc[i]);
+                            const uint32_t fw[4] = { f.x, f.y, f.z, f.w };
+                            const uint32_t rw[4] = { r[4 * sg], r[4 * sg + 1], r[4 * sg + 2], r[4 * sg + 3] };
+                            acc[i] = sad_words<P, 4>(fw, rw, acc[i]);
                         }
                     }
                 }

@@ -234,7 +234,7 @@ static void denoise(int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, 
     if (!s.ok) { fail("stage overflow"); return; }
     if (s.upload()) { fail("denoise"); return; }
     k_denoise<<<(numCoeff + 255) / 256, 256, 0, s.ctx->stream>>>(s.d<int16_t>(oc), s.d<uint32_t>(orr), s.d<uint16_t>(oo), numCoeff);
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(oc, (orr + (size_t)numCoeff * 4) - oc)) { fail("denoise"); return; }
     memcpy(dctCoef, s.h<int16_t>(oc), (size_t)numCoeff * 2);
     memcpy(resSum, s.h<uint32_t>(orr), (size_t)numCoeff * 4);
@@ -267,7 +267,7 @@ static uint32_t count_nonzero_blk(const int16_t* src, intptr_t stride, int N, in
     size_t oq = s.put(src, stride, N, N, 2), on = s.reserve(4);
     if (!s.ok || s.upload()) { fail("count_nonzero"); return 0; }
     k_count_nonzero<<<1, 32, 0, s.ctx->stream>>>(s.d<int16_t>(oq), N * N, s.d<uint32_t>(on));
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(oq, (on + 4) - oq)) { fail("count_nonzero"); return 0; }     // coefficients come back from the device copy
     if (copyTo) memcpy(copyTo, s.h<int16_t>(oq), (size_t)N * N * 2);
     return *s.h<uint32_t>(on);
@@ -318,7 +318,7 @@ static void lf_sign(int8_t* dst, const P* src1, const P* src2, const int endX)
     if (!s.ok) { fail("stage overflow"); return; }
     if (s.upload()) { fail("sign"); return; }
     lf::k_sign<P><<<1, 128, 0, s.ctx->stream>>>(s.d<int8_t>(od), s.d<P>(o1), s.d<P>(o2), endX);
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(od, endX)) { fail("sign"); return; }
     memcpy(dst, s.h<int8_t>(od), endX);
 }
@@ -331,7 +331,7 @@ static void lf_sao_e0(P* rec, int8_t* offsetEo, int width, int8_t* signLeft, int
     if (!s.ok) { fail("stage overflow"); return; }
     if (s.upload()) { fail("saoCuOrgE0"); return; }
     lf::k_sao_e0<P><<<1, 128, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(oo), width, s.d<int8_t>(ol));
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(od, (size_t)2 * width * sizeof(P))) { fail("saoCuOrgE0"); return; }
     s.get(rec, stride, width, 2, sizeof(P), od);
 }
@@ -344,7 +344,7 @@ static void lf_sao_e1_rows(P* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t s
     if (!s.ok) { fail("stage overflow"); return; }
     if (s.upload()) { fail("saoCuOrgE1"); return; }
     lf::k_sao_e1<P><<<1, 128, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(ou), s.d<int8_t>(oo), width, rows);
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(ou, (od + (size_t)rows * width * sizeof(P)) - ou)) { fail("saoCuOrgE1"); return; }
     memcpy(upBuff1, s.h<int8_t>(ou), width);
     s.get(rec, stride, width, rows, sizeof(P), od);
@@ -361,7 +361,7 @@ static void lf_sao_e2(P* rec, int8_t* bufft, int8_t* buff1, int8_t* offsetEo, in
     if (!s.ok) { fail("stage overflow"); return; }
     if (s.upload()) { fail("saoCuOrgE2"); return; }
     lf::k_sao_e2<P><<<1, 128, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(ot), s.d<int8_t>(o1), s.d<int8_t>(oo), width);
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(ot, (od + (size_t)width * sizeof(P)) - ot)) { fail("saoCuOrgE2"); return; }
     memcpy(bufft + 1, s.h<int8_t>(ot), width);
     memcpy(rec, s.h<P>(od), (size_t)width * sizeof(P));
@@ -378,7 +378,7 @@ static void lf_sao_e3(P* rec, int8_t* upBuff1, int8_t* offsetEo, intptr_t stride
     if (!s.ok) { fail("stage overflow"); return; }
     if (s.upload()) { fail("saoCuOrgE3"); return; }
     lf::k_sao_e3<P><<<1, 128, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(ou), s.d<int8_t>(ow), s.d<int8_t>(oo), n);
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(ow, (od + (size_t)n * sizeof(P)) - ow)) { fail("saoCuOrgE3"); return; }
     memcpy(upBuff1 + startX, s.h<int8_t>(ow), n);                     // upBuff1[x - 1] for x = startX + 1 .. endX - 1
     memcpy(rec + startX + 1, s.h<P>(od), (size_t)n * sizeof(P));
@@ -392,7 +392,7 @@ static void lf_sao_b0(P* rec, const int8_t* offset, int ctuWidth, int ctuHeight,
     if (!s.ok) { fail("stage overflow"); return; }
     if (s.upload()) { fail("saoCuOrgB0"); return; }
     lf::k_sao_b0<P><<<(int)((n + 255) / 256), 256, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), s.d<int8_t>(oo), (int)n);
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(od, n * sizeof(P))) { fail("saoCuOrgB0"); return; }
     s.get(rec, stride, ctuWidth, ctuHeight, sizeof(P), od);
 }
@@ -407,7 +407,7 @@ static void lf_deblock(P* src, intptr_t srcStep, intptr_t offset, int a, int b, 
     if (s.upload()) { fail("pelFilter"); return; }
     if (luma) lf::k_deblock_luma_strong<P><<<1, 32, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), a, b);
     else      lf::k_deblock_chroma<P><<<1, 32, 0, s.ctx->stream>>>(s.d<P>(oi), s.d<P>(od), a, b, c);
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(od, 32 * sizeof(P))) { fail("pelFilter"); return; }
     const int k0 = luma ? 1 : 3, k1 = luma ? 6 : 4;                 // the samples the C primitive writes
     for (int i = 0; i < 4; i++) for (int k = k0; k <= k1; k++) src[i * srcStep + (k - 4) * offset] = s.h<P>(od)[i * 8 + k];
@@ -445,7 +445,7 @@ static void lf_sao_stats(int what, const int16_t* diff, const P* rec, intptr_t s
     case 3: lf::k_sao_stats_e2<P><<<1, 64, 0, st>>>(s.d<int16_t>(odf), s.d<P>(orc), rp, s.d<int8_t>(oa), s.d<int8_t>(ob), endX, endY, s.d<int32_t>(ost), s.d<int32_t>(oct)); break;
     default: lf::k_sao_stats_e3<P><<<1, 64, 0, st>>>(s.d<int16_t>(odf), s.d<P>(orc), rp, s.d<int8_t>(oa), endX, endY, s.d<int32_t>(ost), s.d<int32_t>(oct)); break;
     }
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(ost, s.used - ost)) { fail("saoCuStats"); return; }
     memcpy(stats, s.h<int32_t>(ost), nb * 4); memcpy(count, s.h<int32_t>(oct), nb * 4);
     if (what == 2) memcpy(upBuff1, s.h<int8_t>(oa), na);
@@ -527,7 +527,7 @@ static int ads(int w, int h, int* encDC, uint32_t* sums, int delta, uint16_t* co
     size_t om = s.reserve((size_t)width * 2), on = s.reserve(4);
     if (!s.ok || s.upload()) { fail("ads"); return 0; }
     k_ads<<<1, 32, 0, s.ctx->stream>>>(terms, half, s.d<int>(oe), s.d<uint32_t>(os), delta, s.d<uint16_t>(oc), s.d<int16_t>(om), width, thresh, s.d<int>(on));
-    s.ctx->launches++;
+    x265cu_count_launch(s.ctx);
     if (s.download(om, (on + 4) - om)) { fail("ads"); return 0; }
     int n = *s.h<int>(on);
     memcpy(mvs, s.h<int16_t>(om), (size_t)n * 2);
