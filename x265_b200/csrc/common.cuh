@@ -62,4 +62,7 @@ __constant__ int16_t c_chromaFilter[8][4] = {
     { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
 // transform matrices, generated on the host at context creation (transform.cuh: build_dct_tables)
 __constant__ int8_t c_dct[4][32 * 32];   // [log2N-2][k*N + j]
+// the same matrices in GLOBAL memory for lane-indexed reads (a constant-bank access with 32 different addresses is
+// replayed 32 times: the tensor-core transform's fragment set-up spent ~100 us per launch in such reads)
+__device__ int8_t d_dct[4][32 * 32];
 __constant__ int8_t c_dst4[16];

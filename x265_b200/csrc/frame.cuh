@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) k_cu_residual(const P* __restrict__ fenc,
         const int px = cu.x + tu.tx, py = cu.y + tu.ty;
         const P* src = refs[best] + (size_t)py * stride + px + (qx >> 2) + (ptrdiff_t)(qy >> 2) * stride;
         __syncthreads();
-        for (int i = tid; i < NN; i += blockDim.x) s_m[i] = c_dct[lg - 2][i];
+        for (int i = tid; i < NN; i += blockDim.x) s_m[i] = d_dct[lg - 2][i];
         // ---- luma MC into s_pred ----
         if (!(xf | yf))
         {

@@ -1003,6 +1003,44 @@ __device__ __forceinline__ void me_ld_px(const P* __restrict__ p, int (&v)[N])
         v[i] = sizeof(P) == 1 ? (int)((x[i >> 2] >> (8 * (i & 3))) & 255u) : (int)((x[i >> 1] >> (16 * (i & 1))) & 65535u);
 }
 
+// the 4-tap chroma filters as packed signed bytes (DP4A / DP2A operand): all taps are within [-6, 64].  In GLOBAL memory:
+// the lanes of a pass look up different phases, which a constant-bank access would serialise.
+__device__ const uint32_t d_chromaTaps4[8] = {
+    0x00004000u, 0xfe0a3afeu, 0xfe1036fcu, 0xfc1c2efau, 0xfc2424fcu, 0xfa2e1cfcu, 0xfc3610feu, 0xfe3a0afeu };
+
+// un-normalised 4-tap horizontal sums of the 4 outputs whose support is the 7 pixels starting at p (any alignment):
+// aligned words + funnel shifts, then one DP4A (8-bit) / two DP2A (16-bit) per output instead of four IMADs and the
+// per-pixel extraction.  Reads up to 3 bytes before / 5 bytes after the span inside the same words (plane margins).
+template <typename P>
+__device__ __forceinline__ void me_chroma_hsum4(const P* __restrict__ p, uint32_t taps, int (&s)[4])
+{
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+    const unsigned sh = ((unsigned)a & 3u) * 8u;
+    if (sizeof(P) == 1)
+    {
+        const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
+        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+        s[0] = dp4a_us(x0, taps, 0);
+        s[1] = dp4a_us(__funnelshift_r(x0, x1, 8), taps, 0);
+        s[2] = dp4a_us(__funnelshift_r(x0, x1, 16), taps, 0);
+        s[3] = dp4a_us(__funnelshift_r(x0, x1, 24), taps, 0);
+    }
+    else
+    {
+        uint32_t w[5], x[4];
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[k] = __ldg(ap + k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k], w[k + 1], sh);
+        const uint32_t p1 = __funnelshift_r(x[0], x[1], 16), p3 = __funnelshift_r(x[1], x[2], 16), p5 = __funnelshift_r(x[2], x[3], 16);
+        s[0] = dp2a_hi_ss(x[1], taps, dp2a_lo_ss(x[0], taps, 0));
+        s[1] = dp2a_hi_ss(p3, taps, dp2a_lo_ss(p1, taps, 0));
+        s[2] = dp2a_hi_ss(x[2], taps, dp2a_lo_ss(x[1], taps, 0));
+        s[3] = dp2a_hi_ss(p5, taps, dp2a_lo_ss(p3, taps, 0));
+    }
+}
+
 // un-normalised 4x4 Hadamard abs-sum of (source chroma block - predicted chroma block).  One lane, registers only;
 // out of line (one copy per kernel: the ME kernels are instruction-cache sensitive).
 // ONE code path for all fractional phases: the separable form filter_hps(rowExt) -> filter_vsp of the reference's hv case
@@ -1019,28 +1057,29 @@ __device__ __noinline__ int me_chroma_had4x4(const P* __restrict__ f, const P* _
     int m[4][4];
     if (DEPTH != 8 && xf && !yf)
     {   // 10-bit horizontal only: filter_hpp directly
-        const int c0 = c_chromaFilter[xf][0], c1 = c_chromaFilter[xf][1], c2 = c_chromaFilter[xf][2], c3 = c_chromaFilter[xf][3];
+        const uint32_t th = __ldg(&d_chromaTaps4[xf]);
 #pragma unroll
         for (int y = 0; y < 4; y++)
         {
-            int p[7];
-            me_ld_px<P, 7>(r + y * stride - 1, p);
+            int hs[4];
+            me_chroma_hsum4<P>(r + y * stride - 1, th, hs);
 #pragma unroll
-            for (int x = 0; x < 4; x++) m[y][x] = interp_finish<DEPTH>(c0 * p[x] + c1 * p[x + 1] + c2 * p[x + 2] + c3 * p[x + 3], 0);
+            for (int x = 0; x < 4; x++) m[y][x] = interp_finish<DEPTH>(hs[x], 0);
         }
     }
     else
     {
-        const int h0 = c_chromaFilter[xf][0], h1 = c_chromaFilter[xf][1], h2 = c_chromaFilter[xf][2], h3 = c_chromaFilter[xf][3];
-        const int v0 = c_chromaFilter[yf][0], v1 = c_chromaFilter[yf][1], v2 = c_chromaFilter[yf][2], v3 = c_chromaFilter[yf][3];
+        const uint32_t th = __ldg(&d_chromaTaps4[xf]);
+        const uint32_t tv = __ldg(&d_chromaTaps4[yf]);
+        const int v0 = (int)(int8_t)tv, v1 = (int)(int8_t)(tv >> 8), v2 = (int)(int8_t)(tv >> 16), v3 = (int)tv >> 24;
         int mid[7][4];                     // filter_hps with isRowExt: rows -1 .. +5 of the block (ipfilter.cpp:120-162)
 #pragma unroll
         for (int k = 0; k < 7; k++)
         {
-            int p[7];
-            me_ld_px<P, 7>(r + (k - 1) * stride - 1, p);
+            int hs[4];
+            me_chroma_hsum4<P>(r + (k - 1) * stride - 1, th, hs);
 #pragma unroll
-            for (int x = 0; x < 4; x++) mid[k][x] = interp_finish<DEPTH>(h0 * p[x] + h1 * p[x + 1] + h2 * p[x + 2] + h3 * p[x + 3], 1);
+            for (int x = 0; x < 4; x++) mid[k][x] = interp_finish<DEPTH>(hs[x], 1);
         }
 #pragma unroll
         for (int y = 0; y < 4; y++)
@@ -1081,15 +1120,34 @@ __device__ __forceinline__ int me_nth_set_bit(unsigned mask, int n)
     return pos;
 }
 
+// un-normalised 4-tap horizontal sum of the four pixels starting at p (any alignment): aligned words, funnel shifts and
+// one DP4A (8-bit) / two DP2A (16-bit) -- exact in int32
+template <typename P>
+__device__ __forceinline__ int me_chroma_hsum(const P* __restrict__ p, uint32_t taps)
+{
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+    const unsigned sh = ((unsigned)a & 3u) * 8u;
+    if (sizeof(P) == 1)
+    {
+        const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1);
+        return dp4a_us(__funnelshift_r(w0, w1, sh), taps, 0);
+    }
+    else
+    {
+        const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
+        return dp2a_hi_ss(__funnelshift_r(w1, w2, sh), taps, dp2a_lo_ss(__funnelshift_r(w0, w1, sh), taps, 0));
+    }
+}
+
 // Cb + Cr chroma SATD of the candidates of a burst: lane k (k < n, bit k of `need` set) receives candidate k's cost.
 // chromaSatd is the luma SATD primitive of the chroma-sized block (primitives.cpp:139-158): 8x4 tiles when the chroma
 // width is a multiple of 8, else 4x4 tiles, each tile halved on its own (pixel.cpp:210-297, 1131-1155).
-// Work items = (needed candidate, plane, tile), candidate-major, spread over the lanes 32 at a time: an 8x8 PU (one 4x4
-// tile per plane) evaluates the 8 directions of a refinement round in ONE pass of 16 lanes instead of 8 passes of 2; the
-// per-candidate sums are one REDUX each.  Lanes of different candidates run the tile function with their own fractional
-// phase (its branches serialise per phase class, not per candidate).
+//
+// CLS 1 (large / non power-of-two PUs): work items = (needed candidate, plane, tile), one lane per tile, candidate-major,
+// 32 at a time (a 32x32 PU has 16 tiles per candidate: the warp is full); per-candidate sums are one REDUX each.
 template <typename P>
-__device__ __forceinline__ int me_chroma_batch(const MeCtx<P>& c, const MeChromaCtx<P>& cc, int n, int qx, int qy, unsigned need)
+__device__ __forceinline__ int me_chroma_batch_tiles(const MeCtx<P>& c, const MeChromaCtx<P>& cc, int n, int qx, int qy, unsigned need)
 {
     const int cw = c.w >> 1, chh = c.h >> 1;
     const int tw = (cw & 7) ? 4 : 8;
@@ -1135,6 +1193,87 @@ __device__ __forceinline__ int me_chroma_batch(const MeCtx<P>& c, const MeChroma
     return out;
 }
 
+// CLS 0 (8x8, 16x8, 8x16, 16x16 PUs: chroma blocks of 1, 2, 2, 4 4x4 tiles per plane): a refinement round has 4-8
+// candidates of 2-8 tiles, so one lane per tile leaves most of the warp idle while it issues the whole 600-instruction
+// tile function.  Here FOUR lanes share a 4x4 tile, one COLUMN each: a lane's 7 horizontal sums (rows -1 .. +5 of its
+// column, one DP4A each) are exactly what its 4 outputs need -- no redundant filtering --, the vertical Hadamard is in-lane and
+// the horizontal one two shuffle butterflies.  Lane-items per candidate = 8 / 16 / 32 (powers of two: shifts, no
+// divisions; a candidate never straddles a pass), so tile and candidate sums are xor butterflies too.  An 8x8 PU's round
+// of 4 candidates is ONE pass of ~200 instructions with all 32 lanes busy (was: 8 lanes x 600); the body is 1/4 the size.
+// One code path for all fractional phases as in me_chroma_had4x4 (identity taps for a zero phase; 10-bit
+// horizontal-only phases take filter_hpp's rounding by a select).
+template <typename P>
+__device__ __forceinline__ int me_chroma_batch_cols(const MeCtx<P>& c, const MeChromaCtx<P>& cc, int n, int qx, int qy, unsigned need)
+{
+    constexpr int DEPTH = PixTraits<P>::depth;
+    const int lgtpr = c.lgw - 3;                                   // log2(4x4 tiles per chroma row): 0 or 1
+    const int lgnt = lgtpr + (31 - __clz(c.h)) - 3;                // log2(4x4 tiles per plane): 0 .. 2
+    const int lgipc = lgnt + 3;                                    // log2(lane-items per candidate): 2 planes x tiles x 4 columns
+    const int lggs = 2 + lgtpr;                                    // log2(lanes per SATD tile): 4x4 -> 4 lanes, 8x4 -> 8
+    if (n < 32) need &= (1u << n) - 1u;
+    const int nneed = __popc(need);
+    const int total = nneed << lgipc;
+    const bool dense = need == (nneed >= 32 ? 0xffffffffu : ((1u << nneed) - 1u));
+    const int myq = __popc(need & ((1u << c.lane) - 1u));           // rank of this lane's candidate among the needed ones
+    const int col = c.lane & 3;
+    const int s1 = (c.lane & 1) ? -1 : 1, s2 = (c.lane & 2) ? -1 : 1;
+    int out = 0;
+    for (int base = 0; base < total; base += 32)
+    {
+        const int it = min(base + c.lane, total - 1);              // idle lanes (whole candidates) redo the last item: harmless
+        const int ci = it >> lgipc;
+        const int t = (it & ((1 << lgipc) - 1)) >> 2;              // tile of the candidate, both planes
+        const int k = dense ? ci : me_nth_set_bit(need, ci);
+        const int kqx = __shfl_sync(0xffffffffu, qx, k & 31), kqy = __shfl_sync(0xffffffffu, qy, k & 31);
+        const bool cr = (t >> lgnt) != 0;
+        const int tt = t & ((1 << lgnt) - 1);
+        const int ty = tt >> lgtpr, tx = tt & ((1 << lgtpr) - 1);
+        const int xf = kqx & 7, yf = kqy & 7;
+        const ptrdiff_t o = (ptrdiff_t)(ty * 4) * cc.cstride + tx * 4 + col;
+        const P* f = (cr ? cc.fcr : cc.fcb) + o;
+        const P* r = (cr ? cc.rcr : cc.rcb) + o + (kqx >> 3) + (ptrdiff_t)(kqy >> 3) * cc.cstride - 1 - cc.cstride;
+        const uint32_t th = __ldg(&d_chromaTaps4[xf]);
+        const uint32_t tv = __ldg(&d_chromaTaps4[yf]);
+        const int v0 = (int)(int8_t)tv, v1 = (int)(int8_t)(tv >> 8), v2 = (int)(int8_t)(tv >> 16), v3 = (int)tv >> 24;
+        int S[7];
+#pragma unroll
+        for (int q = 0; q < 7; q++) S[q] = me_chroma_hsum<P>(r + q * cc.cstride, th);
+        int d[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+        {
+            const int m = interp_finish<DEPTH>(v0 * interp_finish<DEPTH>(S[y], 1) + v1 * interp_finish<DEPTH>(S[y + 1], 1) +
+                                               v2 * interp_finish<DEPTH>(S[y + 2], 1) + v3 * interp_finish<DEPTH>(S[y + 3], 1), 2);
+            const int mh = DEPTH != 8 ? interp_finish<DEPTH>(S[y + 1], 0) : 0;      // filter_hpp keeps the two bits hps drops
+            d[y] = (int)__ldg(f + y * cc.cstride) - ((DEPTH != 8 && !yf) ? mh : m);
+        }
+        had4(d[0], d[1], d[2], d[3]);
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+        {
+            d[y] = __shfl_xor_sync(0xffffffffu, d[y], 1) + s1 * d[y];
+            d[y] = __shfl_xor_sync(0xffffffffu, d[y], 2) + s2 * d[y];
+        }
+        int v = abs(d[0]) + abs(d[1]) + abs(d[2]) + abs(d[3]);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (lggs == 3) v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v >>= 1;                                                   // every lane of the tile holds its halved SATD
+        for (int s = lggs; s < lgipc; s++) v += __shfl_xor_sync(0xffffffffu, v, 1 << s);   // ... and now the candidate's sum
+        const int src = (myq << lgipc) - base;
+        const int got = __shfl_sync(0xffffffffu, v, src & 31);
+        if (src >= 0 && src < 32 && ((need >> c.lane) & 1u)) out += got;
+    }
+    return out;
+}
+
+template <typename P, int CLS>
+__device__ __forceinline__ int me_chroma_batch(const MeCtx<P>& c, const MeChromaCtx<P>& cc, int n, int qx, int qy, unsigned need)
+{
+    if (CLS == 0) return me_chroma_batch_cols<P>(c, cc, n, qx, qy, need);
+    return me_chroma_batch_tiles<P>(c, cc, n, qx, qy, need);
+}
+
 struct MeState { int bmx, bmy, bcost, bprecost, bestprex, bestprey; };
 
 #define ME_YOK(y) (((y) >= c.miny) & ((y) <= c.maxy))
@@ -1146,7 +1285,6 @@ __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, M
 {
 
     const int qminx = c.minx * 4, qminy = c.miny * 4, qmaxx = c.maxx * 4, qmaxy = c.maxy * 4;
-    const int merange = j.merange;
     // clipped() = min with max first, then max with min (mv.h:100-105)
     const int pmvx = max(min(c.mvpx, qmaxx), qminx), pmvy = max(min(c.mvpy, qmaxy), qminy);
     int bestprex = pmvx, bestprey = pmvy;
@@ -1209,7 +1347,7 @@ __device__ __forceinline__ void me_phase1(MeCtx<P>& c, const x265cu_me_job& j, M
             // the clipped MVP and the candidates go through subpelCompare (chroma term included); the MVP's full-pel
             // rounding and MV 0 are plain COST_MV SADs (motion.cpp:771-814)
             const bool wantC = lane < n && (tag == 0 || tag >= 3);
-            const int ccost = me_chroma_batch<P>(c, *cc, n, qx, qy, __ballot_sync(0xffffffffu, wantC));
+            const int ccost = me_chroma_batch<P, CLS>(c, *cc, n, qx, qy, __ballot_sync(0xffffffffu, wantC));
             if (wantC) cost += ccost;
         }
         const bool mine = lane < n;
@@ -1452,7 +1590,7 @@ __device__ __forceinline__ void me_phase3(MeCtx<P>& c, const x265cu_me_job& j, c
             int cost = me_subpel_batch<P, CLS>(c, n, qx, qy, satd);
             if (CHROMA && cc->on)
             {
-                const int ccost = me_chroma_batch<P>(c, *cc, n, qx, qy, n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+                const int ccost = me_chroma_batch<P, CLS>(c, *cc, n, qx, qy, n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
                 if (c.lane < n) cost += ccost;
             }
             if (c.lane < n) cost += me_mvcost(c, qx, qy);
@@ -1639,7 +1777,11 @@ static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const voi
                        const MeChromaArgs* ch, const MeWinLaunch* win)
 {
     int rc = 0;
-    const int32_t* ord = (win && !lowres) ? win->order : NULL;
+    // shape-sorted job order (geometry.h `order`): measured on B200 at 2160p it takes the chroma launches from 36.7 to 27.6 ms
+    // (sub-pel; instruction-cache bound kernels) but COSTS the luma-only ones ~10 % (they hit the cache anyway and lose the
+    // raster order's L1 / L2 locality).  X265CU_ME_ORDER = 0: never, 1: chroma launches only (default), 2: all.
+    static const int ordMode = [] { const char* e = getenv("X265CU_ME_ORDER"); return e ? atoi(e) : 1; }();
+    const int32_t* ord = (win && !lowres && (ordMode >= 2 || (ordMode == 1 && ch))) ? win->order : NULL;
     const int ord0 = win ? win->job0 : 0;
     if (ch)
     {

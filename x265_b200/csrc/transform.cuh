@@ -44,6 +44,7 @@ static int build_dct_tables(int device)
     std::lock_guard<std::mutex> lock(mtx);
     if (device >= 0 && device < 64 && uploaded[device]) return 0;
     CU_CHECK(cudaMemcpyToSymbol(c_dct, host.tab, sizeof(host.tab)));
+    CU_CHECK(cudaMemcpyToSymbol(d_dct, host.tab, sizeof(host.tab)));
     CU_CHECK(cudaMemcpyToSymbol(c_dst4, dst4, sizeof(dst4)));
     CU_CHECK(cudaDeviceSynchronize());
     if (device >= 0 && device < 64) uploaded[device] = true;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) k_transform(int op, const int16_t* __rest
     __shared__ int8_t s_m[NN];
     const bool fwd = (op == X265CU_DCT || op == X265CU_DST4);
     const bool dstm = (op == X265CU_DST4 || op == X265CU_IDST4);
-    for (int i = threadIdx.x; i < NN; i += blockDim.x) s_m[i] = dstm ? c_dst4[i] : c_dct[LG - 2][i];
+    for (int i = threadIdx.x; i < NN; i += blockDim.x) s_m[i] = dstm ? c_dst4[i] : d_dct[LG - 2][i];
     const int shift1 = fwd ? LG - 1 + (DEPTH - 8) : 7;
     const int shift2 = fwd ? LG + 6 : 12 - (DEPTH - 8);
     const int tl = threadIdx.x / TPT, tt = threadIdx.x % TPT;      // TU slot in the CTA, thread inside the TU

@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
     constexpr int shift2 = FWD ? LG + 6 : 12 - (DEPTH - 8);
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int8_t* M = c_dct[LG - 2];
+    // the matrix through shared memory: the fragment set-up below indexes it per lane (see d_dct in common.cuh)
+    __shared__ __align__(16) int8_t M[N * N];
+    for (int i = threadIdx.x * 4; i < N * N; i += blockDim.x * 4) *(uint32_t*)(M + i) = *(const uint32_t*)(d_dct[LG - 2] + i);
+    __syncthreads();
 
     // constant A fragments: pass 1 uses the natural K order, pass 2 the accumulator-induced permutation.
     // forward: A[row][k] = M[row][k];  inverse: A[row][k] = M[k][row]  (A = M^T)
