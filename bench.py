@@ -264,7 +264,7 @@ def primitives_leg(lib, reps=3):
         pass
     out = []
     for depth in (8, 10):
-        for row in primitive_bench.run(lib, depth=depth, reps=reps, frames=6, quiet=True):
+        for row in primitive_bench.run(lib, depth=depth, reps=reps, frames=24, quiet=True):
             out.append({"kernel": row["kernel"], "depth": depth, "GBps": round(row["GBps"], 1), "frac": round(row["frac_of_measured_peak"], 4),
                         "algorithmic_bytes": int(row["algorithmic_MB"] * 1e6), "dram_bytes": dram.get((row["kernel"], depth)), "note": row["note"]})
     return out

@@ -174,7 +174,7 @@ def run(lib, depth=8, reps=7, frames=FRAMES, quiet=False, only=None):
         lorg = (32 * lstride + 32) * es
         ms = timed(lib, flush, lambda: lib.check(lib.L.x265cu_frame_init_lowres(lib.ctx, depth, dA.ptr + org * es, stride, planes[0].ptr + lorg, planes[1].ptr + lorg,
                                                                                  planes[2].ptr + lorg, planes[3].ptr + lorg, lstride, lw, lh, 32, 32)), reps)
-        add("k_lowres_init + extend (5 launches)", ms, 2 * W * H * es, "")
+        add("k_lowres_init + extend (2 launches)", ms, 2 * W * H * es, "")
     lib.sync()
     for bf in bufs:
         bf.free()

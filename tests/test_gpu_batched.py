@@ -74,6 +74,66 @@ def test_interp_batch_luma(cu, depth, op):
 
 
 @pytest.mark.parametrize("depth", [8, 10])
+def test_pixelcmp_batch_small_groups(cu, depth):
+    """Lists of SMALL blocks: the job-list kernel packs 32 / width jobs per warp pass (width = pow2ceil(work units of the
+    largest job among 32 consecutive ones)); uniform 4x4 / 8x8 / 16x16 lists, mixed small lists, n not a multiple of 32,
+    sa8d lists mixing sub-8 blocks (SATD path) with 8x8 / 16x16 / 24x32 ones, and the one-plane / int16 costs."""
+    from x265_b200.lib import CMP_JOB
+    O = load_oracle(depth)
+    rng = np.random.default_rng(50 + depth)
+    dt = pixel_dtype(depth)
+    a = rng.integers(0, 1 << depth, (200, 320)).astype(dt)
+    b = rng.integers(0, 1 << depth, (200, 288)).astype(dt)
+    sa16 = rng.integers(-600, 600, (200, 320)).astype(np.int16)
+    sb16 = rng.integers(-600, 600, (200, 288)).astype(np.int16)
+    sse_t = C.c_uint32 if depth == 8 else C.c_uint64
+    two = {"sad": (O.orc_sad, C.c_int), "satd": (O.orc_satd, C.c_int), "sa8d": (O.orc_sa8d, C.c_int), "sse_pp": (O.orc_sse_pp, sse_t)}
+    lists = {"sad": [[(8, 8)], [(4, 4)], [(16, 16)], [(8, 4), (4, 8), (8, 8), (4, 16)], [(12, 16), (16, 12), (8, 8)]],
+             "satd": [[(8, 8)], [(4, 4)], [(16, 16)], [(8, 4), (4, 8), (8, 8), (16, 4)], [(12, 16), (16, 8), (8, 16)]],
+             "sa8d": [[(8, 8)], [(16, 16)], [(4, 4), (8, 8), (16, 16), (8, 4)], [(24, 32), (8, 16), (16, 8), (32, 8)], [(4, 8), (8, 4)]],
+             "sse_pp": [[(8, 8)], [(4, 4)], [(16, 16)], [(8, 4), (4, 8), (16, 8)]]}
+    dA, dB = cu.to_device(a), cu.to_device(b)
+    for op, (ofn, res) in two.items():
+        ofn.restype = res
+        for sizes in lists[op]:
+            n = 32 * 3 + 7
+            j = np.zeros(n, CMP_JOB); want = np.zeros(n, np.uint64)
+            for k in range(n):
+                w, h = sizes[int(rng.integers(0, len(sizes)))]
+                ao = int(rng.integers(0, 200 - 32)) * 320 + int(rng.integers(0, 320 - 32))
+                bo = int(rng.integers(0, 200 - 32)) * 288 + int(rng.integers(0, 288 - 32))
+                j[k] = (ao, bo, 320, 288, w, h, 0)
+                want[k] = ofn(ptr(a, ao), IP(320), ptr(b, bo), IP(288), w, h)
+            dJ, dO = cu.to_device(j), cu.alloc(8 * n)
+            cu.pixelcmp_batch(depth, op, dA, dB, dJ, n, dO)
+            np.testing.assert_array_equal(dO.download(np.uint64), want, err_msg="%s %s" % (op, sizes))
+            dJ.free(); dO.free()
+    # one-plane and int16 costs on square blocks (cu[] entries): var, ssd_s, sse_ss, psy
+    O.orc_var.restype = C.c_uint64; O.orc_ssd_s.restype = sse_t; O.orc_sse_ss.restype = sse_t; O.orc_psy_cost_pp.restype = C.c_int
+    dSA, dSB = cu.to_device(sa16), cu.to_device(sb16)
+    for op in ("var", "ssd_s", "sse_ss", "psy"):
+        for sizes in ([8], [16], [4, 8, 16] if op != "var" else [8, 16], [32, 8]):
+            n = 32 * 2 + 5
+            j = np.zeros(n, CMP_JOB); want = np.zeros(n, np.uint64)
+            for k in range(n):
+                s = sizes[int(rng.integers(0, len(sizes)))]
+                ao = int(rng.integers(0, 200 - 32)) * 320 + int(rng.integers(0, 320 - 32))
+                bo = int(rng.integers(0, 200 - 32)) * 288 + int(rng.integers(0, 288 - 32))
+                j[k] = (ao, bo, 320, 288, s, s, 0)
+                if op == "var":      want[k] = O.orc_var(ptr(a, ao), IP(320), s)
+                elif op == "ssd_s":  want[k] = O.orc_ssd_s(ptr(sa16, ao), IP(320), s)
+                elif op == "sse_ss": want[k] = O.orc_sse_ss(ptr(sa16, ao), IP(320), ptr(sb16, bo), IP(288), s, s)
+                else:                want[k] = O.orc_psy_cost_pp(ptr(a, ao), IP(320), ptr(b, bo), IP(288), s)
+            dJ, dO = cu.to_device(j), cu.alloc(8 * n)
+            pa, pb = (dSA, dSB) if op in ("ssd_s", "sse_ss") else (dA, dB)
+            cu.pixelcmp_batch(depth, op, pa, pb, dJ, n, dO)
+            np.testing.assert_array_equal(dO.download(np.uint64), want, err_msg="%s %s" % (op, sizes))
+            dJ.free(); dO.free()
+    for d in (dA, dB, dSA, dSB):
+        d.free()
+
+
+@pytest.mark.parametrize("depth", [8, 10])
 @pytest.mark.parametrize("N", [4, 8, 16, 32])
 @pytest.mark.parametrize("layout", ["contiguous", "strided"])
 def test_transform_batch(cu, depth, N, layout):

@@ -268,34 +268,46 @@ __global__ void __launch_bounds__(256) k_lowres_init_u8x8(const uint8_t* __restr
     *(uint2*)(dc + o) = make_uint2(out[3][0], out[3][1]);
 }
 
-// replicate left/right edges (rows 0..height-1), then copy first/last rows into the top/bottom margins
+// extendPicBorder (pixel.cpp:1027-1041) in ONE launch for up to four planes of the same geometry (round 1: a left/right
+// and a top/bottom launch per plane, nine launches for a lowres init).  The reference replicates the edge pixels of every
+// row, then copies `stride` elements of the (extended) first / last row into the margin rows; every output here is a pure
+// function of the un-extended picture (margin rows read the source row and its two edge pixels directly), so the two
+// passes need no ordering.  Block = one output row of one plane.
+template <typename P> struct ExtPlanes { P* p[4]; };
 template <typename P>
-__global__ void k_extend_lr(P* __restrict__ pic, int stride, int width, int height, int marginX)
+__global__ void __launch_bounds__(128) k_extend_border(ExtPlanes<P> pl, int stride, int width, int height, int mx, int my)
 {
-    int y = blockIdx.x;
-    if (y >= height) return;
-    P* row = pic + (int64_t)y * stride;
-    P l = row[0], r = row[width - 1];
-    for (int x = threadIdx.x; x < marginX; x += blockDim.x) { row[-marginX + x] = l; row[width + x] = r; }
-}
-template <typename P>
-__global__ void k_extend_tb(P* __restrict__ pic, int stride, int width, int height, int marginX, int marginY)
-{
-    int m = blockIdx.x;                  // 0..2*marginY-1
-    const P* srcrow = (m < marginY) ? pic - marginX : pic - marginX + (int64_t)(height - 1) * stride;
-    P* dst = (m < marginY) ? pic - marginX - (int64_t)(m + 1) * stride : pic - marginX + (int64_t)(height + (m - marginY)) * stride;
-    for (int x = threadIdx.x; x < stride; x += blockDim.x) dst[x] = srcrow[x];
+    P* pic = pl.p[blockIdx.y];
+    const int r = (int)blockIdx.x - my;                              // output row: -my .. height + my - 1
+    const int sr = min(max(r, 0), height - 1);
+    const P* srow = pic + (int64_t)sr * stride;
+    P* drow = pic + (int64_t)r * stride;
+    const P l = srow[0], rt = srow[width - 1];
+    if (r == sr)
+    {
+        for (int x = threadIdx.x; x < mx; x += blockDim.x) { drow[-mx + x] = l; drow[width + x] = rt; }
+    }
+    else
+    {   // `stride` elements from column -mx: margins replicated, the row itself, and whatever padding follows (as memcpy does)
+        for (int x = threadIdx.x; x < stride; x += blockDim.x)
+        {
+            const int sx = x - mx;
+            drow[sx] = sx < 0 ? l : sx < width ? srow[sx] : sx < width + mx ? rt : srow[sx];
+        }
+    }
 }
 
 template <typename P>
+static int extend_border_n(x265cu_ctx* ctx, P* const* pics, int nplanes, int stride, int width, int height, int mx, int my)
+{
+    ExtPlanes<P> pl;
+    for (int i = 0; i < 4; i++) pl.p[i] = pics[i < nplanes ? i : 0];
+    k_extend_border<P><<<dim3(height + 2 * my, nplanes), 128, 0, ctx->stream>>>(pl, stride, width, height, mx, my);
+    CU_LAUNCH_CHECK(ctx);
+    return 0;
+}
+template <typename P>
 static int extend_border_t(x265cu_ctx* ctx, P* pic, int stride, int width, int height, int mx, int my)
 {
-    k_extend_lr<P><<<height, 64, 0, ctx->stream>>>(pic, stride, width, height, mx);
-    CU_LAUNCH_CHECK(ctx);
-    if (my > 0)
-    {
-        k_extend_tb<P><<<2 * my, 256, 0, ctx->stream>>>(pic, stride, width, height, mx, my);
-        CU_LAUNCH_CHECK(ctx);
-    }
-    return 0;
+    return extend_border_n<P>(ctx, &pic, 1, stride, width, height, mx, my);
 }

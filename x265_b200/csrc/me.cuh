@@ -1777,11 +1777,15 @@ static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const voi
                        const MeChromaArgs* ch, const MeWinLaunch* win)
 {
     int rc = 0;
-    // shape-sorted job order (geometry.h `order`): measured on B200 at 2160p it takes the chroma launches from 36.7 to 27.6 ms
-    // (sub-pel; instruction-cache bound kernels) but COSTS the luma-only ones ~10 % (they hit the cache anyway and lose the
-    // raster order's L1 / L2 locality).  X265CU_ME_ORDER = 0: never, 1: chroma launches only (default), 2: all.
+    // shape-sorted job order (geometry.h `order`), measured on B200 at 2160p (profiles/me_r2_ncu.md section 5): it helps kernels
+    // that miss the instruction cache (the chroma sub-pel launches: 24.2 -> 23.2 ms; 36.7 -> 27.6 ms before the column-split
+    // chroma term made them small) and costs the others ~10 % (they lose the raster order's L1 / L2 locality: luma-only
+    // pre-checks 9.1 -> 10.4 ms, chroma pre-checks 9.7 -> 10.9 ms).  X265CU_ME_ORDER = 0: never, 1: chroma sub-pel launches
+    // only (default), 2: every pre-check / sub-pel launch.
     static const int ordMode = [] { const char* e = getenv("X265CU_ME_ORDER"); return e ? atoi(e) : 1; }();
-    const int32_t* ord = (win && !lowres && (ordMode >= 2 || (ordMode == 1 && ch))) ? win->order : NULL;
+    const int32_t* ordAll = (win && !lowres) ? win->order : NULL;
+    const int32_t* ord = ordMode >= 2 ? ordAll : NULL;                       // pre-checks, luma-only sub-pel
+    const int32_t* ord3 = (ordMode >= 2 || (ordMode == 1 && ch)) ? ordAll : NULL;   // chroma sub-pel
     const int ord0 = win ? win->job0 : 0;
     if (ch)
     {
@@ -1805,8 +1809,8 @@ static int launch_me_t(x265cu_ctx* ctx, const void* fenc, int fstride, const voi
     CU_CHECK(cudaEventRecord(ctx->me_ev[2], ctx->stream));
     if (ch)
     {
-        rc |= launch_me_chroma_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 3, ord, ord0);
-        rc |= launch_me_chroma_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 4, ord, ord0);
+        rc |= launch_me_chroma_phase<P, 3, 0>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 3, ord3, ord0);
+        rc |= launch_me_chroma_phase<P, 3, 1>(ctx, fenc, fstride, refs, rstride, *ch, mvcost, jobs, n, out, st, counter_dev + 4, ord3, ord0);
     }
     else
     {

@@ -223,57 +223,245 @@ __device__ __forceinline__ int warp_psy(const P* __restrict__ s, int ss, const P
     return warp_sum(acc);
 }
 
-// ---- batched generic kernel: one warp per job ---------------------------------------------
+// ---- batched job-list kernel ---------------------------------------------------------------------------------
+// Round 1 ran one warp per job: an 8x8 SATD kept 2 of 32 lanes busy and an 8x8 SAD paid a 5-step reduction for 64 pixels
+// (2-4 % of the HBM roofline on frame-sized lists of small blocks).  Now a warp takes 32 consecutive jobs (one coalesced
+// 1 KB read of the records), picks the SUB-GROUP width the largest of them needs -- lanes per job = pow2ceil(work units),
+// units = 8x4 tiles for SATD, 8x8 tiles for SA8D / PSY, 16-pixel groups for the element-wise costs -- and runs
+// 32 / width jobs side by side per pass; results go back to the lane that read the job, so the 32 outputs are one
+// coalesced store.  width = 32 is exactly the old behaviour (64x64 blocks).  The arithmetic per job is unchanged.
+__device__ __forceinline__ int grp_sum(int v, int lpj)
+{
+    for (int o = 1; o < lpj; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long grp_sum64(unsigned long long v, int lpj)
+{
+    for (int o = 1; o < lpj; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ uint32_t pc_ld32(uintptr_t a)          // 4 bytes at any alignment (planes have margins)
+{
+    const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t lo = __ldg(ap);
+    return sh ? __funnelshift_r(lo, __ldg(ap + 1), sh) : lo;
+}
+
+// SAD on packed words: 4 (8-bit) / 2 (16-bit) pixels per VABSDIFF4 / max-min pair
+template <typename P>
+__device__ __forceinline__ int grp_sad(const P* __restrict__ a, int sa, const P* __restrict__ b, int sb, int w, int h, int sub, int lpj)
+{
+    constexpr int PPW = 4 / (int)sizeof(P);                       // pixels per word
+    const int wq = w / PPW, nq = wq * h;
+    uint32_t acc = 0;
+    for (int i = sub; i < nq; i += lpj)
+    {
+        const int y = i / wq, x = (i - y * wq) * PPW;
+        const uint32_t wa = pc_ld32((uintptr_t)(a + y * sa + x)), wb = pc_ld32((uintptr_t)(b + y * sb + x));
+        if (sizeof(P) == 1) acc = __vsadu4(wa, wb) + acc;
+        else { const uint32_t t = __vmaxu2(wa, wb) - __vminu2(wa, wb); acc += (t & 0xffffu) + (t >> 16); }
+    }
+    return grp_sum((int)acc, lpj);
+}
+
+template <typename PA, typename PB>
+__device__ __forceinline__ int grp_satd(const PA* __restrict__ a, int sa, const PB* __restrict__ b, int sb, int w, int h, int sub, int lpj)
+{
+    int acc = 0;
+    if ((w & 7) == 0)
+    {
+        const int tw = w >> 3, nt = tw * (h >> 2);
+        for (int t = sub; t < nt; t += lpj)
+        {
+            const int ty = t / tw, tx = t - ty * tw;
+            const PA* pa = a + (ty * 4) * sa + tx * 8; const PB* pb = b + (ty * 4) * sb + tx * 8;
+            acc += (had4x4_abs(pa, sa, pb, sb) + had4x4_abs(pa + 4, sa, pb + 4, sb)) >> 1;
+        }
+    }
+    else
+    {
+        const int tw = w >> 2, nt = tw * (h >> 2);
+        for (int t = sub; t < nt; t += lpj)
+        {
+            const int ty = t / tw, tx = t - ty * tw;
+            acc += had4x4_abs(a + (ty * 4) * sa + tx * 4, sa, b + (ty * 4) * sb + tx * 4, sb) >> 1;
+        }
+    }
+    return grp_sum(acc, lpj);
+}
+
+// `ntmax` = the largest 8x8-tile count among the jobs of this pass (warp-uniform): the 16x16 rounding combines four
+// lanes by shuffles inside the loop, so every lane runs the same number of trips
+template <typename PA, typename PB>
+__device__ __forceinline__ int grp_sa8d(const PA* __restrict__ a, int sa, const PB* __restrict__ b, int sb, int w, int h, int sub, int lpj, int ntmax)
+{
+    const int tw = w >> 3, nt = tw * (h >> 3);
+    const bool r16 = ((w | h) & 15) == 0;
+    int acc = 0;
+    for (int t0 = 0; t0 < ntmax; t0 += lpj)
+    {
+        const int t = t0 + sub;
+        int v = 0;
+        if (t < nt)
+        {
+            int y, x;
+            if (r16)
+            {   // four consecutive t form one 16x16
+                const int t16 = t >> 2, q = t & 3, tw16 = w >> 4;
+                const int y16 = t16 / tw16, x16 = t16 - y16 * tw16;
+                y = y16 * 16 + (q >> 1) * 8; x = x16 * 16 + (q & 1) * 8;
+            }
+            else { const int ty = t / tw; y = ty * 8; x = (t - ty * tw) * 8; }
+            v = had8x8_abs<PA, PB, false>(a + y * sa + x, sa, b + y * sb + x, sb);
+        }
+        const int v4 = v + __shfl_xor_sync(0xffffffffu, v, 1);
+        const int v16 = v4 + __shfl_xor_sync(0xffffffffu, v4, 2);
+        if (t < nt) acc += r16 ? ((sub & 3) == 0 ? (v16 + 2) >> 2 : 0) : (v + 2) >> 2;
+    }
+    return grp_sum(acc, lpj);
+}
+
+template <typename PA, typename PB>
+__device__ __forceinline__ unsigned long long grp_sse(const PA* __restrict__ a, int sa, const PB* __restrict__ b, int sb, int w, int h, int sub, int lpj)
+{
+    unsigned long long acc = 0;
+    const int n = w * h;
+    for (int i = sub; i < n; i += lpj)
+    {
+        const int y = i / w, x = i - y * w;
+        const int d = (int)a[y * sa + x] - (int)b[y * sb + x];
+        acc += (unsigned)(d * d);
+    }
+    return grp_sum64(acc, lpj);
+}
+
+template <typename P>
+__device__ __forceinline__ int grp_psy(const P* __restrict__ s, int ss, const P* __restrict__ r, int rs, int n, int sub, int lpj)
+{
+    int acc = 0;
+    if (n == 4)
+    {
+        if (sub == 0)
+        {
+            int sadS = 0, sadR = 0;
+            for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) { sadS += s[y * ss + x]; sadR += r[y * rs + x]; }
+            const int es = (had4x4_abs_zero(s, ss) >> 1) - (sadS >> 2);
+            const int er = (had4x4_abs_zero(r, rs) >> 1) - (sadR >> 2);
+            acc = abs(es - er);
+        }
+        return grp_sum(acc, lpj);
+    }
+    const int tw = n >> 3, nt = tw * tw;
+    for (int t = sub; t < nt; t += lpj)
+    {
+        const int ty = t / tw, tx = t - ty * tw;
+        const P* ps = s + ty * 8 * ss + tx * 8; const P* pr = r + ty * 8 * rs + tx * 8;
+        int sadS = 0, sadR = 0;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) { sadS += ps[y * ss + x]; sadR += pr[y * rs + x]; }
+        const int es = ((had8x8_abs<P, P, true>(ps, ss, ps, ss) + 2) >> 2) - (sadS >> 2);
+        const int er = ((had8x8_abs<P, P, true>(pr, rs, pr, rs) + 2) >> 2) - (sadR >> 2);
+        acc += abs(es - er);
+    }
+    return grp_sum(acc, lpj);
+}
+
+// work units of a job for the sub-group width (see above)
+__device__ __forceinline__ int pixelcmp_units(int op, int w, int h)
+{
+    switch (op)
+    {
+    case X265CU_SATD: return (w & 7) ? (w >> 2) * (h >> 2) : (w >> 3) * (h >> 2);
+    case X265CU_SA8D: return (w < 8 || h < 8) ? ((w & 7) ? (w >> 2) * (h >> 2) : (w >> 3) * (h >> 2)) : max(4, (w >> 3) * (h >> 3));
+    case X265CU_PSY:  return max(1, (w >> 3) * (w >> 3));
+    default:          return max(1, (w * h) >> 4);
+    }
+}
+
 template <typename P>
 __global__ void __launch_bounds__(256) k_pixelcmp(int op, const P* __restrict__ A, const P* __restrict__ B,
                                                   const x265cu_cmp_job* __restrict__ jobs, int n, uint64_t* __restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < n; j += gridDim.x * wpb)
+    const int nchunks = (n + 31) >> 5;
+    for (int ch = blockIdx.x * wpb + (threadIdx.x >> 5); ch < nchunks; ch += gridDim.x * wpb)
     {
-        const x265cu_cmp_job job = jobs[j];
-        const int w = job.w, h = job.h, sa = job.a_stride, sb = job.b_stride;
-        uint64_t res = 0;
-        switch (op)
+        const int j0 = ch << 5, cnt = min(32, n - j0);
+        x265cu_cmp_job mine;
+        mine.a_off = 0; mine.b_off = 0; mine.a_stride = 0; mine.b_stride = 0; mine.w = 4; mine.h = 4;
+        if (lane < cnt) mine = jobs[j0 + lane];
+        const int units = lane < cnt ? pixelcmp_units(op, mine.w, mine.h) : 1;
+        const int umax = __reduce_max_sync(0xffffffffu, units);
+        int lpj = 1;
+        while (lpj < umax && lpj < 32) lpj <<= 1;
+        const int lglpj = 31 - __clz(lpj), jpp = 32 >> lglpj;                  // jobs per pass
+        const int sub = lane & (lpj - 1);
+        uint64_t myres = 0;
+        for (int pass = 0; pass < lpj && pass * jpp < cnt; pass++)
         {
-        case X265CU_SAD:  res = (uint32_t)warp_sad(A + job.a_off, sa, B + job.b_off, sb, w, h, lane); break;
-        case X265CU_SATD: res = (uint32_t)warp_satd(A + job.a_off, sa, B + job.b_off, sb, w, h, lane); break;
-        case X265CU_SA8D: res = (uint32_t)warp_sa8d(A + job.a_off, sa, B + job.b_off, sb, w, h, lane); break;
-        case X265CU_SSE_PP:
-        {
-            unsigned long long v = warp_sse(A + job.a_off, sa, B + job.b_off, sb, w, h, lane);
-            res = PixTraits<P>::depth == 8 ? (uint64_t)(uint32_t)v : v;     // sse_t width (common.h:144-148)
-            break;
+            const int k = pass * jpp + (lane >> lglpj);                       // the job (lane of this chunk) my sub-group works on
+            const int ks = min(k, cnt - 1);
+            const long long a_off = __shfl_sync(0xffffffffu, (long long)mine.a_off, ks), b_off = __shfl_sync(0xffffffffu, (long long)mine.b_off, ks);
+            const int sa = __shfl_sync(0xffffffffu, (int)mine.a_stride, ks), sb = __shfl_sync(0xffffffffu, (int)mine.b_stride, ks);
+            const int wh = __shfl_sync(0xffffffffu, ((int)mine.w << 16) | (int)(uint16_t)mine.h, ks);
+            const int w = wh >> 16, h = wh & 0xffff;
+            uint64_t res = 0;
+            switch (op)
+            {
+            case X265CU_SAD:  res = (uint32_t)grp_sad<P>(A + a_off, sa, B + b_off, sb, w, h, sub, lpj); break;
+            case X265CU_SATD: res = (uint32_t)grp_satd(A + a_off, sa, B + b_off, sb, w, h, sub, lpj); break;
+            case X265CU_SA8D:
+            {
+                // blocks below 8x8 take the SATD path; a pass mixing both kinds would diverge around the in-loop shuffles
+                const bool small = w < 8 || h < 8;
+                const unsigned anySmall = __ballot_sync(0xffffffffu, small), anyBig = __ballot_sync(0xffffffffu, !small);
+                const int nt = small ? 0 : (w >> 3) * (h >> 3);
+                const int ntmax = __reduce_max_sync(0xffffffffu, nt);
+                int v = 0;
+                if (anyBig)  v = grp_sa8d(A + a_off, sa, B + b_off, sb, small ? 8 : w, small ? 8 : h, sub, lpj, ntmax);
+                if (anySmall) { const int v2 = grp_satd(A + a_off, sa, B + b_off, sb, small ? w : 4, small ? h : 4, sub, lpj); if (small) v = v2; }
+                res = (uint32_t)v;
+                break;
+            }
+            case X265CU_SSE_PP:
+            {
+                const unsigned long long v = grp_sse(A + a_off, sa, B + b_off, sb, w, h, sub, lpj);
+                res = PixTraits<P>::depth == 8 ? (uint64_t)(uint32_t)v : v;     // sse_t width (common.h:144-148)
+                break;
+            }
+            case X265CU_SSE_SS:
+            {
+                const int16_t* a = (const int16_t*)A + a_off; const int16_t* b = (const int16_t*)B + b_off;
+                const unsigned long long v = grp_sse(a, sa, b, sb, w, h, sub, lpj);
+                res = PixTraits<P>::depth == 8 ? (uint64_t)(uint32_t)v : v;
+                break;
+            }
+            case X265CU_SSD_S:
+            {
+                const int16_t* a = (const int16_t*)A + a_off;
+                unsigned long long acc = 0;
+                for (int i = sub; i < w * h; i += lpj) { const int y = i / w, x = i - y * w; const int v = a[y * sa + x]; acc += (unsigned)(v * v); }
+                acc = grp_sum64(acc, lpj);
+                res = PixTraits<P>::depth == 8 ? (uint64_t)(uint32_t)acc : acc;
+                break;
+            }
+            case X265CU_VAR:
+            {
+                const P* a = A + a_off;
+                unsigned s = 0, q = 0;
+                for (int i = sub; i < w * h; i += lpj) { const int y = i / w, x = i - y * w; const unsigned v = a[y * sa + x]; s += v; q += v * v; }
+                s = (unsigned)grp_sum((int)s, lpj); q = (unsigned)grp_sum((int)q, lpj);
+                res = (uint64_t)s + ((uint64_t)q << 32);
+                break;
+            }
+            case X265CU_PSY: res = (uint32_t)grp_psy(A + a_off, sa, B + b_off, sb, w, sub, lpj); break;
+            }
+            // hand the result to the lane that owns job k: lane L's job was worked on in pass L / jpp by sub-group L % jpp
+            const unsigned long long got = __shfl_sync(0xffffffffu, (unsigned long long)res, (lane & (jpp - 1)) << lglpj);
+            if ((lane >> (5 - lglpj)) == pass) myres = got;
         }
-        case X265CU_SSE_SS:
-        {
-            const int16_t* a = (const int16_t*)A + job.a_off; const int16_t* b = (const int16_t*)B + job.b_off;
-            unsigned long long v = warp_sse(a, sa, b, sb, w, h, lane);
-            res = PixTraits<P>::depth == 8 ? (uint64_t)(uint32_t)v : v;
-            break;
-        }
-        case X265CU_SSD_S:
-        {
-            const int16_t* a = (const int16_t*)A + job.a_off;
-            unsigned long long acc = 0;
-            for (int i = lane; i < w * h; i += 32) { int y = i / w, x = i - y * w; int v = a[y * sa + x]; acc += (unsigned)(v * v); }
-            acc = warp_sum64(acc);
-            res = PixTraits<P>::depth == 8 ? (uint64_t)(uint32_t)acc : acc;
-            break;
-        }
-        case X265CU_VAR:
-        {
-            const P* a = A + job.a_off;
-            unsigned s = 0, q = 0;
-            for (int i = lane; i < w * h; i += 32) { int y = i / w, x = i - y * w; unsigned v = a[y * sa + x]; s += v; q += v * v; }
-            s = (unsigned)warp_sum((int)s); q = (unsigned)warp_sum((int)q);
-            res = (uint64_t)s + ((uint64_t)q << 32);
-            break;
-        }
-        case X265CU_PSY: res = (uint32_t)warp_psy(A + job.a_off, sa, B + job.b_off, sb, w, lane); break;
-        }
-        if (lane == 0) out[j] = res;
+        if (lane < cnt) out[j0 + lane] = myres;
     }
 }
 
@@ -282,7 +470,7 @@ static int launch_pixelcmp(x265cu_ctx* ctx, int depth, int op, const void* A, co
 {
     if (n <= 0) return 0;
     const int threads = 256, wpb = threads / 32;
-    int blocks = (n + wpb - 1) / wpb;
+    int blocks = ((n + 31) / 32 + wpb - 1) / wpb;                 // a warp takes 32 jobs at a time
     int maxb = ctx->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (depth == 8)

@@ -50,8 +50,14 @@ __device__ __forceinline__ void split4(int v0, int v1, int v2, int v3, uint32_t&
 
 // N = 16 or 32.  FWD: src strided (stride / tu_pitch in elements), dst contiguous N*N per TU; INV: the reverse.
 template <int DEPTH, int N, bool FWD>
-__global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int stride, int64_t tu_pitch, int n)
+__global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int stride, int64_t tu_pitch, int n, int vecStore)
 {
+    // inverse only: the pass-2 accumulators hold residual COLUMNS along the lanes (2-byte scattered stores, half of every
+    // 32-byte sector wasted: 49-57 % of the HBM roofline); with 16-byte aligned destination rows a warp transposes its TU
+    // through a padded shared tile (pitch chosen so that the 32 scattered halfword writes of one store hit 32 banks) and
+    // writes whole 16-byte row pieces
+    constexpr int OP = N == 32 ? 40 : 24;                         // tile row pitch in int16
+    __shared__ __align__(16) int16_t s_out[FWD ? 1 : 8][FWD ? 8 : N * OP];
     constexpr int LG = N == 32 ? 5 : 4;
     constexpr int MT = N / 16, NT = N / 8, KR = N / 16;          // m tiles, n tiles, B registers per n tile
     constexpr int K32 = N == 32;
@@ -169,6 +175,13 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
                     *(uint32_t*)(d + (g + 16 * mt) * N + 8 * nt + 2 * t)     = ((uint32_t)(uint16_t)v[0]) | ((uint32_t)(uint16_t)v[1] << 16);
                     *(uint32_t*)(d + (g + 8 + 16 * mt) * N + 8 * nt + 2 * t) = ((uint32_t)(uint16_t)v[2]) | ((uint32_t)(uint16_t)v[3] << 16);
                 }
+                else if (vecStore)
+                {
+                    int16_t* sw = s_out[FWD ? 0 : (threadIdx.x >> 5)];
+                    const int j0 = 8 * nt + 2 * t, i0 = g + 16 * mt;
+                    sw[j0 * OP + i0] = (int16_t)v[0];       sw[(j0 + 1) * OP + i0] = (int16_t)v[1];
+                    sw[j0 * OP + i0 + 8] = (int16_t)v[2];   sw[(j0 + 1) * OP + i0 + 8] = (int16_t)v[3];
+                }
                 else
                 {   // D2[i2][j2] = Out[j2][i2]: dst[j2 * stride + i2]
                     const int j0 = 8 * nt + 2 * t, i0 = g + 16 * mt;
@@ -178,6 +191,17 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
                     d[(int64_t)(j0 + 1) * stride + i0 + 8] = (int16_t)v[3];
                 }
             }
+        if (!FWD && vecStore)
+        {
+            const int16_t* sw = s_out[FWD ? 0 : (threadIdx.x >> 5)];
+            __syncwarp();
+            for (int id = lane; id < N * N / 8; id += 32)
+            {
+                const int row = id / (N / 8), c8 = (id % (N / 8)) * 8;
+                *(uint4*)(d + (int64_t)row * stride + c8) = *(const uint4*)(sw + row * OP + c8);
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -194,15 +218,17 @@ static int launch_transform_mma(x265cu_ctx* ctx, int op, int N, const int16_t* s
     }
     int blocks = (n + 7) / 8;
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    // inverse: whole 16-byte row pieces when every destination row starts 16-byte aligned
+    const int vec = !fwd && !(((uintptr_t)dst) & 15) && !(stride & 7) && !(tu_pitch & 7);
     if (N == 32)
     {
-        if (fwd) k_transform_mma<DEPTH, 32, true><<<blocks, 256, 0, ctx->stream>>>(src, dst, stride, tu_pitch, n);
-        else     k_transform_mma<DEPTH, 32, false><<<blocks, 256, 0, ctx->stream>>>(src, dst, stride, tu_pitch, n);
+        if (fwd) k_transform_mma<DEPTH, 32, true><<<blocks, 256, 0, ctx->stream>>>(src, dst, stride, tu_pitch, n, 0);
+        else     k_transform_mma<DEPTH, 32, false><<<blocks, 256, 0, ctx->stream>>>(src, dst, stride, tu_pitch, n, vec);
     }
     else
     {
-        if (fwd) k_transform_mma<DEPTH, 16, true><<<blocks, 256, 0, ctx->stream>>>(src, dst, stride, tu_pitch, n);
-        else     k_transform_mma<DEPTH, 16, false><<<blocks, 256, 0, ctx->stream>>>(src, dst, stride, tu_pitch, n);
+        if (fwd) k_transform_mma<DEPTH, 16, true><<<blocks, 256, 0, ctx->stream>>>(src, dst, stride, tu_pitch, n, 0);
+        else     k_transform_mma<DEPTH, 16, false><<<blocks, 256, 0, ctx->stream>>>(src, dst, stride, tu_pitch, n, vec);
     }
     return 1;
 }

@@ -189,9 +189,9 @@ int x265cu_intra_filter_batch(x265cu_ctx* c, int depth, int size, const void* nb
 {
     cudaSetDevice(c->device);
     if (n <= 0) return 0;
-    int blocks = n < c->sm_count * 8 ? n : c->sm_count * 8;
-    if (depth == 8) k_intra_filter<uint8_t><<<blocks, 160, 0, c->stream>>>(size, (const uint8_t*)nb, (uint8_t*)filt, pitch, n);
-    else            k_intra_filter<uint16_t><<<blocks, 160, 0, c->stream>>>(size, (const uint16_t*)nb, (uint16_t*)filt, pitch, n);
+    int blocks = (n + 7) / 8 < c->sm_count * 8 ? (n + 7) / 8 : c->sm_count * 8;       // a warp per neighbour array
+    if (depth == 8) k_intra_filter<uint8_t><<<blocks, 256, 0, c->stream>>>(size, (const uint8_t*)nb, (uint8_t*)filt, pitch, n);
+    else            k_intra_filter<uint16_t><<<blocks, 256, 0, c->stream>>>(size, (const uint16_t*)nb, (uint16_t*)filt, pitch, n);
     CU_LAUNCH_CHECK(c);
     return 0;
 }
@@ -241,9 +241,9 @@ int x265cu_frame_init_lowres(x265cu_ctx* c, int depth, const void* src, int sstr
     CU_LAUNCH_CHECK(c);
     if (mx > 0 || my > 0)
     {
-        void* planes[4] = { d0, dh, dv, dc };
-        for (int i = 0; i < 4; i++)
-            if (x265cu_extend_border(c, depth, planes[i], dstride, width, height, mx, my)) return -1;
+        void* planes[4] = { d0, dh, dv, dc };                    // all four planes in one launch
+        if (depth == 8) { if (extend_border_n<uint8_t>(c, (uint8_t* const*)planes, 4, dstride, width, height, mx, my)) return -1; }
+        else            { if (extend_border_n<uint16_t>(c, (uint16_t* const*)planes, 4, dstride, width, height, mx, my)) return -1; }
     }
     return 0;
 }
