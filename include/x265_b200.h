@@ -184,6 +184,32 @@ int x265cu_me_batch_chroma(x265cu_ctx*, int depth, const void* fenc_dev, int fen
                            const void* const* refplanes_dev, int refStride, const x265cu_me_chroma* chroma,
                            const uint16_t* mvcost_dev, int mvcost_range, const x265cu_me_job* jobs_dev, int n, int32_t* out_dev);
 
+/* ---------- prediction costs around the motion search ----------
+ * The motion-compensated prediction + cost evaluations Search::predInterSearch makes besides motionEstimate:
+ *   - Search::selectMVP (encoder/search.cpp:1992-2023): SAD of the luma prediction at each AMVP candidate
+ *     (predInterLumaPixel + MotionEstimate::bufSAD)                              -> cost = X265CU_PRED_SAD, one list;
+ *   - Search::mergeEstimation (search.cpp:1901-1960): Predict::motionCompensation of the merge candidate (uni or bi),
+ *     bufSATD + bufChromaSATD                                                     -> X265CU_PRED_SATD | X265CU_PRED_CHROMA;
+ *   - the bi-directional estimate (search.cpp:2474-2607): with bChromaSATD the same motionCompensation(bi) path
+ *     (addAvg of the two 14-bit intermediates, luma + chroma), without it pixelavg_pp of the two pixel predictions
+ *     (luma only)                                                                -> X265CU_PRED_AVG_PP.
+ * Prediction = the unweighted paths of common/predict.cpp:76-420 (4:2:0; eighth-pel chroma vector = the luma vector).
+ * Vectors are quarter-pel and already clipped (CUData::clipMv, cudata.cpp:1915-1928).  The chroma term needs a chroma block
+ * that is a multiple of 4x4 (motion.cpp:204-212) and chroma planes; it is skipped otherwise.  out_dev[n]: the distortion
+ * (the caller adds the bit costs).  `chroma` may be NULL (no X265CU_PRED_CHROMA jobs). */
+enum { X265CU_PRED_SAD = 0, X265CU_PRED_SATD = 1 };
+enum { X265CU_PRED_CHROMA = 1, X265CU_PRED_AVG_PP = 2 };
+typedef struct {
+    int32_t offset;            /* PU origin: element offset into the luma planes (source and references share the geometry) */
+    int16_t pw, ph;
+    int8_t  ref0, ref1;        /* index into refplanes_dev / the chroma tables; -1 = list unused */
+    uint8_t cost;              /* X265CU_PRED_SAD / X265CU_PRED_SATD */
+    uint8_t flags;             /* X265CU_PRED_CHROMA | X265CU_PRED_AVG_PP */
+    int16_t mv0[2], mv1[2];    /* quarter-pel */
+} x265cu_pred_job;
+int x265cu_pred_cost_batch(x265cu_ctx*, int depth, const void* fenc_dev, int fencStride, const void* const* refplanes_dev, int refStride,
+                           const x265cu_me_chroma* chroma, const x265cu_pred_job* jobs_dev, int n, int32_t* out_dev);
+
 /* ---------- frame-level CTU analysis (DESIGN.md "Frame analysis workload") ----------
  * One analyser = one picture geometry.  Reference planes stay resident in HBM (x265cu_analyser_set_ref
  * = what the recon-row broadcast feeds); per frame the host passes the source luma and the 16x16

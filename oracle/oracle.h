@@ -84,6 +84,10 @@ void orc_interp_vsp(const int16_t* s, intptr_t ss, pixel* d, intptr_t ds, int co
 void orc_interp_vss(const int16_t* s, intptr_t ss, int16_t* d, intptr_t ds, int coeffIdx, int ntaps, int w, int h);
 void orc_interp_hvpp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int idxX, int idxY, int ntaps, int w, int h);
 
+/* ---- prediction costs around the motion search (oracle_pred.c: search.cpp:1901-2023, 2474-2607; predict.cpp:76-420) ---- */
+struct orc_pred_job_s;
+int orc_pred_cost(const struct orc_pred_job_s* j);      /* the job struct is defined in oracle_pred.c / tests/pred_helpers.py */
+
 /* ---- transforms / quant (dct.cpp:43-742) ---- */
 const int16_t* orc_dct_matrix(int n);        /* n x n HEVC matrix, regenerated from the 32-pt basis */
 void orc_dct(const int16_t* src, int16_t* dst, intptr_t srcStride, int n);

@@ -361,6 +361,10 @@ void* x265ref_la_create_aq(int width, int height, int nframes, const pixel* cons
 }
 }
 #include "frame.h"
+#include "predict.h"
+#include "cudata.h"
+#include "slice.h"
+#include "framedata.h"
 static void* la_create(int width, int height, int nframes, const pixel* const* luma, intptr_t stride, int bframes, int lslices,
                        int aqMode, const pixel* const* cb, const pixel* const* cr, intptr_t strideC)
 {
@@ -507,6 +511,101 @@ int x265ref_la_get(void* hv, int frame, int what, int d0, int d1, void* out)
     default: return -1;
     }
     return 0;
+}
+
+
+/* Prediction costs around the motion search on the REAL classes (pins oracle/oracle_pred.c):
+ * Predict::motionCompensation (common/predict.cpp:76-240) / predInterLumaPixel for the prediction, then
+ * MotionEstimate::bufSAD / bufSATD / bufChromaSATD (encoder/motion.h:87-95) exactly as Search::selectMVP
+ * (search.cpp:1992-2023), Search::mergeEstimation (:1901-1960) and the bidir block of predInterSearch (:2474-2607) call
+ * them.  All planes are handed over at the PU origin (PicYuv offset tables = a single zero, as in
+ * x265ref_motion_estimate_chroma); the slice is a B slice without weighted prediction; the picture is made large
+ * enough that CUData::clipMv leaves the vectors alone (the batched entry point takes clipped vectors).
+ * ref0 / ref1 == NULL: list unused.  cost: 0 = SAD, 1 = SATD; chroma: + bufChromaSATD; biAvgPP: search.cpp:2499-2510. */
+int x265ref_pred_cost(const pixel* const* fenc, const pixel* const* ref0, const pixel* const* ref1, intptr_t stride, intptr_t cstride,
+                      int pw, int ph, const int* mv0, const int* mv1, int cost, int chroma, int biAvgPP)
+{
+    ensure_init();
+    static bool scales = false;
+    if (!scales) { MotionEstimate::initScales(); scales = true; }
+    Yuv src, predYuv;
+    if (!src.create(64, X265_CSP_I420) || !predYuv.create(64, X265_CSP_I420)) return -1;
+    for (int y = 0; y < ph; y++) memcpy(src.m_buf[0] + y * src.m_size, fenc[0] + y * stride, pw * sizeof(pixel));
+    for (int y = 0; y < ph / 2; y++)
+    {
+        memcpy(src.m_buf[1] + y * src.m_csize, fenc[1] + y * cstride, (pw / 2) * sizeof(pixel));
+        memcpy(src.m_buf[2] + y * src.m_csize, fenc[2] + y * cstride, (pw / 2) * sizeof(pixel));
+    }
+    MotionEstimate me;
+    me.init(X265_CSP_I420);
+    me.setQP(30);
+    me.setSourcePU(src, 0, 0, 0, pw, ph, X265_STAR_SEARCH, chroma ? 3 : 2, !!chroma);
+    const bool bChromaSATD = me.bChromaSATD;
+
+    intptr_t zero = 0;
+    PicYuv pic[2];
+    for (int l = 0; l < 2; l++)
+    {
+        const pixel* const* r = l ? ref1 : ref0;
+        pic[l].m_cuOffsetY = &zero; pic[l].m_cuOffsetC = &zero; pic[l].m_buOffsetY = &zero; pic[l].m_buOffsetC = &zero;
+        pic[l].m_stride = stride; pic[l].m_strideC = cstride;
+        for (int k = 0; k < 3; k++) pic[l].m_picOrg[k] = r ? (pixel*)r[k] : NULL;
+    }
+    x265_param param; memset(&param, 0, sizeof(param)); param.maxCUSize = 64;
+    SPS* sps = (SPS*)calloc(1, sizeof(SPS));
+    PPS* pps = (PPS*)calloc(1, sizeof(PPS));
+    FrameData* fd = (FrameData*)calloc(1, sizeof(FrameData));
+    Slice* slice = (Slice*)calloc(1, sizeof(Slice));
+    CUData* cu = (CUData*)calloc(1, sizeof(CUData));
+    sps->picWidthInLumaSamples = 1 << 15; sps->picHeightInLumaSamples = 1 << 15;
+    pps->bUseWeightPred = false; pps->bUseWeightedBiPred = false;
+    fd->m_param = &param;
+    slice->m_sps = sps; slice->m_pps = pps; slice->m_sliceType = B_SLICE;
+    slice->m_numRefIdx[0] = slice->m_numRefIdx[1] = 1;
+    slice->m_refReconPicList[0][0] = &pic[0]; slice->m_refReconPicList[1][0] = &pic[1];
+    int8_t refIdx[2] = { (int8_t)(ref0 ? 0 : -1), (int8_t)(ref1 ? 0 : -1) };
+    MV mvs[2] = { MV(mv0[0], mv0[1]), MV(mv1[0], mv1[1]) };
+    cu->m_slice = slice; cu->m_encData = fd;
+    cu->m_cuPelX = 1 << 14; cu->m_cuPelY = 1 << 14;
+    cu->m_refIdx[0] = &refIdx[0]; cu->m_refIdx[1] = &refIdx[1];
+    cu->m_mv[0] = &mvs[0]; cu->m_mv[1] = &mvs[1];
+    alignas(PredictionUnit) char pubuf[sizeof(PredictionUnit)];
+    PredictionUnit& pu = *(PredictionUnit*)pubuf;
+    pu.ctuAddr = 0; pu.cuAbsPartIdx = 0; pu.puAbsPartIdx = 0; pu.width = pw; pu.height = ph;
+    Predict pred;
+    pred.allocBuffers(X265_CSP_I420);
+
+    int out;
+    if (ref0 && ref1 && biAvgPP)
+    {   /* search.cpp:2499-2510 */
+        Yuv bidirYuv[2];
+        bidirYuv[0].create(64, X265_CSP_I420); bidirYuv[1].create(64, X265_CSP_I420);
+        pred.predInterLumaPixel(pu, bidirYuv[0], pic[0], mvs[0]);
+        pred.predInterLumaPixel(pu, bidirYuv[1], pic[1], mvs[1]);
+        primitives.pu[me.partEnum].pixelavg_pp[(predYuv.m_size % 64 == 0) && (bidirYuv[0].m_size % 64 == 0) && (bidirYuv[1].m_size % 64 == 0)](
+            predYuv.m_buf[0], predYuv.m_size, bidirYuv[0].getLumaAddr(0), bidirYuv[0].m_size, bidirYuv[1].getLumaAddr(0), bidirYuv[1].m_size, 32);
+        out = me.bufSATD(predYuv.m_buf[0], predYuv.m_size);
+        bidirYuv[0].destroy(); bidirYuv[1].destroy();
+    }
+    else if (!cost)
+    {   /* search.cpp:2017-2018 */
+        pred.predInterLumaPixel(pu, predYuv, ref0 ? pic[0] : pic[1], ref0 ? mvs[0] : mvs[1]);
+        out = me.bufSAD(predYuv.getLumaAddr(0), predYuv.m_size);
+    }
+    else
+    {   /* search.cpp:1944-1948, 2489-2493 */
+        pred.motionCompensation(*cu, pu, predYuv, true, bChromaSATD);
+        out = me.bufSATD(predYuv.getLumaAddr(0), predYuv.m_size);
+        if (bChromaSATD) out += me.bufChromaSATD(predYuv, 0);
+    }
+    for (int l = 0; l < 2; l++)
+    {
+        pic[l].m_cuOffsetY = pic[l].m_cuOffsetC = pic[l].m_buOffsetY = pic[l].m_buOffsetC = NULL;
+        pic[l].m_picOrg[0] = pic[l].m_picOrg[1] = pic[l].m_picOrg[2] = NULL;
+    }
+    src.destroy(); predYuv.destroy();
+    free(sps); free(pps); free(fd); free(slice); free(cu);
+    return out;
 }
 
 } // extern "C"

@@ -40,6 +40,7 @@ def test_job_layouts_match_header():
     from x265_b200 import lib as L
     assert L.CMP_JOB.itemsize == 32 and L.BLK_JOB.itemsize == 56
     assert L.INTERP_JOB.itemsize == 32 and L.ME_JOB.itemsize == 40 and L.INTRA_JOB.itemsize == 8
+    assert L.PRED_JOB.itemsize == 20            # x265cu_pred_job
 
 
 def test_mvcost_table_matches_oracle():

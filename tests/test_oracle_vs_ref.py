@@ -108,3 +108,24 @@ def test_motion_estimate_chroma_satd(depth, method):
                 assert r == o, (w, h, method, subme, smooth, r, o)
                 n += 1
     assert n == len(sizes) * 10
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+@pytest.mark.parametrize("smooth", [True, False])
+def test_pred_cost(depth, smooth):
+    """AMVP candidate SAD (Search::selectMVP), merge candidate SATD + chroma SATD (mergeEstimation, uni and bi through
+    Predict::motionCompensation) and the pixelavg_pp bidir estimate of predInterSearch: the oracle's restatement against the
+    REAL Predict / MotionEstimate classes, every PU size, full / half / quarter-pel vectors in both components."""
+    import pred_helpers as ph
+    R, O = libs(depth)
+    rng = np.random.default_rng(400 + depth + int(smooth))
+    pl = ph.make_planes(depth, rng, smooth)
+    n = 0
+    for (w, h) in ph.LUMA_PUS:
+        for kind in ("amvp", "merge_uni", "merge_bi", "bidir_pp"):
+            for _ in range(3):
+                jb = ph.random_job(pl, rng, w, h, kind)
+                r, o = ph.ref_cost(R, pl, jb), ph.oracle_cost(O, pl, jb)
+                assert r == o, (w, h, kind, jb["mvs"], r, o)
+                n += 1
+    assert n == len(ph.LUMA_PUS) * 12

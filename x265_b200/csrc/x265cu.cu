@@ -8,6 +8,7 @@
 #include "transform.cuh"
 #include "intra.cuh"
 #include "me.cuh"
+#include "predcost.cuh"
 #include "frame.cuh"
 #include "lookahead.cuh"
 #include <math.h>
@@ -282,6 +283,20 @@ int x265cu_me_batch_chroma(x265cu_ctx* c, int depth, const void* fenc, int fencS
     MeChromaArgs a;
     a.fencCb = chroma->fencCb_dev; a.fencCr = chroma->fencCr_dev; a.refCb = chroma->refCb_dev; a.refCr = chroma->refCr_dev; a.cstride = chroma->cstride;
     return launch_me(c, depth, fenc, fencStride, refs, refStride, 0, mvcost, jobs, n, out, c->d_counter, &a);
+}
+
+int x265cu_pred_cost_batch(x265cu_ctx* c, int depth, const void* fenc, int fencStride, const void* const* refs, int refStride,
+                           const x265cu_me_chroma* chroma, const x265cu_pred_job* jobs, int n, int32_t* out)
+{
+    cudaSetDevice(c->device);
+    if (n <= 0) return 0;
+    PredChroma ch = { NULL, NULL, NULL, NULL, 0 };
+    if (chroma && chroma->fencCb_dev && chroma->fencCr_dev && chroma->refCb_dev && chroma->refCr_dev && chroma->cstride > 0)
+    {
+        ch.fcb = chroma->fencCb_dev; ch.fcr = chroma->fencCr_dev; ch.rcb = chroma->refCb_dev; ch.rcr = chroma->refCr_dev; ch.cstride = chroma->cstride;
+    }
+    if (depth == 8) return launch_pred_cost_t<uint8_t>(c, fenc, fencStride, refs, refStride, ch, jobs, n, out);
+    return launch_pred_cost_t<uint16_t>(c, fenc, fencStride, refs, refStride, ch, jobs, n, out);
 }
 
 __global__ void k_la_intra_zero(const x265cu_la_intra_job* jobs, int h8)

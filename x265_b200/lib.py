@@ -31,6 +31,9 @@ BLK_JOB = np.dtype([("d_off", "<i8"), ("a_off", "<i8"), ("b_off", "<i8"), ("d_st
 INTERP_JOB = np.dtype([("s_off", "<i8"), ("d_off", "<i8"), ("s_stride", "<i4"), ("d_stride", "<i4"), ("w", "<i2"), ("h", "<i2"),
                        ("idxX", "i1"), ("idxY", "i1"), ("rowExt", "i1"), ("ntaps", "i1")], align=True)
 INTRA_JOB = np.dtype([("mode", "<i4"), ("bFilter", "<i4")], align=True)
+PRED_JOB = np.dtype([("offset", "<i4"), ("pw", "<i2"), ("ph", "<i2"), ("ref0", "i1"), ("ref1", "i1"), ("cost", "u1"), ("flags", "u1"),
+                     ("mv0", "<i2", 2), ("mv1", "<i2", 2)])
+PRED_SAD, PRED_SATD, PRED_CHROMA, PRED_AVG_PP = 0, 1, 1, 2
 ME_JOB = np.dtype([("offset", "<i4"), ("ref", "<i2"), ("pw", "i1"), ("ph", "i1"), ("mvmin", "<i2", 2), ("mvmax", "<i2", 2),
                    ("qmvp", "<i2", 2), ("mvc", "<i2", 8), ("numCand", "i1"), ("method", "i1"), ("subme", "i1"), ("merange", "i1")], align=True)
 assert CMP_JOB.itemsize == 32 and BLK_JOB.itemsize == 56 and INTERP_JOB.itemsize == 32 and ME_JOB.itemsize == 40
@@ -82,6 +85,7 @@ _PROTOS = {
     "x265cu_mvcost_table": (None, [C.c_double, I, P]),
     "x265cu_me_batch": (I, [P, I, P, I, P, I, I, P, I, P, I, P]),
     "x265cu_me_batch_chroma": (I, [P, I, P, I, P, I, P, P, I, P, I, P]),
+    "x265cu_pred_cost_batch": (I, [P, I, P, I, P, I, P, P, I, P]),
 }
 
 
@@ -210,6 +214,13 @@ class Lib:
         ch = MeChroma(fenc_cb.ptr, fenc_cr.ptr, ref_cb_table.ptr, ref_cr_table.ptr, cstride)
         self.check(self.L.x265cu_me_batch_chroma(self.ctx, depth, fenc.ptr, fstride, refs_ptr_table.ptr, rstride, C.byref(ch),
                                                  mvcost_dev.ptr + 2 * mvcost_range, mvcost_range, jobs_dev.ptr, n, out_dev.ptr))
+
+    def pred_cost_batch(self, depth, fenc, fstride, refs_ptr_table, rstride, chroma, jobs_dev, n, out_dev):
+        """x265cu_pred_cost_batch: AMVP candidate SADs, merge candidate / bidir SATDs (search.cpp:1901-2023, 2474-2607).
+        chroma: None or (fenc_cb, fenc_cr, ref_cb_table, ref_cr_table, cstride) device buffers."""
+        ch = MeChroma(chroma[0].ptr, chroma[1].ptr, chroma[2].ptr, chroma[3].ptr, chroma[4]) if chroma else None
+        self.check(self.L.x265cu_pred_cost_batch(self.ctx, depth, fenc.ptr, fstride, refs_ptr_table.ptr, rstride,
+                                                 C.byref(ch) if ch else None, jobs_dev.ptr, n, out_dev.ptr))
 
     def lookahead_weights_analyse(self, depth, fenc_buf, ref_bufs, wbuf, planesize, stride, width, lines, padoffset, intra_cost, stats):
         """x265cu_lookahead_weights_analyse: returns (isWeighted, scale, log2denom, offset); wbuf then holds the 4 weighted planes."""
