@@ -270,6 +270,108 @@ def primitives_leg(lib, reps=3):
     return out
 
 
+def pred_jobs_of(jobs, me_out, nrefs, chroma):
+    """Four prediction costs per motion-search job (PU, reference r), as predInterSearch asks around motionEstimate:
+    the two AMVP candidates' SADs (Search::selectMVP: the job's MVP and its first MV candidate), one merge candidate's SATD
+    (uni, the second MV candidate) and one bi-prediction (the search result on r with the MVP on the next reference).  Vectors
+    are clipped to the job's search window (quarter-pel), as CUData::clipMv / setSearchRange keep them inside the padded
+    picture.  With the chroma-SATD term on (presets >= subme 3) the SATD jobs carry it and the bi job is the addAvg path;
+    without it the bi job is the pixelavg_pp estimate (search.cpp:2499-2510)."""
+    from x265_b200.lib import PRED_JOB, PRED_CHROMA, PRED_AVG_PP
+    n = len(jobs)
+    lo = jobs["mvmin"].astype(np.int32) * 4; hi = jobs["mvmax"].astype(np.int32) * 4
+    clip = lambda v: np.clip(v.astype(np.int32), lo, hi).astype(np.int16)
+    pj = np.zeros((n, 4), PRED_JOB)
+    for k in range(4):
+        pj[:, k]["offset"] = jobs["offset"]; pj[:, k]["pw"] = jobs["pw"]; pj[:, k]["ph"] = jobs["ph"]
+        pj[:, k]["ref0"] = jobs["ref"]; pj[:, k]["ref1"] = -1
+    pj[:, 0]["mv0"] = clip(jobs["qmvp"]); pj[:, 1]["mv0"] = clip(jobs["mvc"][:, 0:2]); pj[:, 2]["mv0"] = clip(jobs["mvc"][:, 2:4])
+    pj[:, 2]["cost"] = 1; pj[:, 3]["cost"] = 1
+    pj[:, 2]["flags"] = PRED_CHROMA if chroma else 0
+    pj[:, 3]["flags"] = PRED_CHROMA if chroma else PRED_AVG_PP
+    pj[:, 3]["mv0"] = me_out[:n, 1:3].astype(np.int16)
+    pj[:, 3]["ref1"] = (jobs["ref"] + 1) % nrefs
+    pj[:, 3]["mv1"] = clip(jobs["qmvp"])
+    return pj.reshape(-1)
+
+
+def pred_checks(cost):
+    cost = np.asarray(cost).astype(np.int64)
+    idx = np.arange(cost.size, dtype=np.int64)
+    return {"jobs": int(cost.size), "cost_sum": int(cost.sum()), "cost_hash": int((cost * (idx % 239 + 1)).sum() & ((1 << 62) - 1))}
+
+
+def pred_cpu(wl, pj, threads, budget_s):
+    """Reference arm of the prediction-cost leg: the real Predict / MotionEstimate classes (oracle/_ref: x265ref_pred_cost_batch)
+    over the first jobs of the list, sized to `budget_s` seconds of host time."""
+    from common import load_ref
+    c = CFG
+    R = load_ref(c["depth"])
+    if R is None:
+        return None
+    es = 1 if c["depth"] == 8 else 2
+    nref = len(wl.refs)
+    PA = C.c_void_p * nref
+    refs = PA(*[r.ctypes.data + wl.org * es for r in wl.refs])
+    rcb = PA(*[wl.refC[r][0].ctypes.data + wl.corg * es for r in range(nref)])
+    rcr = PA(*[wl.refC[r][1].ctypes.data + wl.corg * es for r in range(nref)])
+    R.x265ref_pred_cost_batch.restype = C.c_int
+    R.x265ref_pred_cost_batch.argtypes = [C.c_void_p] * 6 + [C.c_ssize_t, C.c_ssize_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+
+    def run(m):
+        out = np.zeros(m, np.int32)
+        t0 = time.perf_counter()
+        R.x265ref_pred_cost_batch(wl.fenc.ctypes.data + wl.org * es, wl.fencC[0].ctypes.data + wl.corg * es, wl.fencC[1].ctypes.data + wl.corg * es,
+                                  refs, rcb, rcr, wl.stride, wl.cstride, pj.ctypes.data, m, out.ctypes.data, threads)
+        return out, time.perf_counter() - t0
+    m0 = min(len(pj), 40000)
+    out, dt = run(m0)
+    m = int(min(len(pj), max(m0, m0 * budget_s / max(dt, 1e-4))))
+    if m > m0:
+        out, dt = run(m)
+    return {"jobs": m, "seconds": dt, "jobs_per_s": m / dt, "cost": out, "threads": threads}
+
+
+def pred_cost_leg(lib, an, wl, cpu_seconds, reps=3):
+    """The prediction costs around the motion search (x265cu_pred_cost_batch) for the analysed frame: job list derived from
+    the frame's motion-search jobs and results (pred_jobs_of), planes as the analyser holds them, device time by CUDA events;
+    the CPU arm runs the reference's own classes on the first jobs of the same list and the costs are compared exactly."""
+    c = CFG
+    es = 1 if c["depth"] == 8 else 2
+    jobs = an.fetch("jobs"); me = an.fetch("me_out").reshape(-1, 4)
+    pj = pred_jobs_of(jobs, me, c["refs"], True)
+    d_f = lib.to_device(wl.fenc); d_r = [lib.to_device(r) for r in wl.refs]
+    d_fc = [lib.to_device(x) for x in wl.fencC]; d_rc = [[lib.to_device(x) for x in rc] for rc in wl.refC]
+    tab = lib.to_device(np.array([d.ptr + wl.org * es for d in d_r], np.uint64))
+    tcb = lib.to_device(np.array([rc[0].ptr + wl.corg * es for rc in d_rc], np.uint64))
+    tcr = lib.to_device(np.array([rc[1].ptr + wl.corg * es for rc in d_rc], np.uint64))
+    d_j = lib.to_device(pj); d_o = lib.alloc(4 * len(pj))
+
+    class _At:                      # a device pointer at the plane's pixel (0, 0)
+        def __init__(self, buf, off): self.ptr = buf.ptr + off
+    chroma = (_At(d_fc[0], wl.corg * es), _At(d_fc[1], wl.corg * es), tcb, tcr, wl.cstride)
+    call = lambda: lib.pred_cost_batch(c["depth"], _At(d_f, wl.org * es), wl.stride, tab, wl.stride, chroma, d_j, len(pj), d_o)
+    call(); lib.sync()
+    ts = []
+    for _ in range(reps):
+        lib.timer_begin(); call(); ts.append(lib.timer_end())
+    ms = float(np.median(ts))
+    got = d_o.download(np.int32)
+    out = {"what": "AMVP candidate SADs (Search::selectMVP), merge-candidate and bi-prediction SATD + chroma SATD (mergeEstimation, predInterSearch bidir) on Predict::motionCompensation: 4 costs per motion-search job",
+           "jobs": int(len(pj)), "ms": ms, "jobs_per_s": len(pj) / (ms / 1000.0), "checks": pred_checks(got), "launches_per_call": 2}
+    if cpu_seconds > 0:
+        r = pred_cpu(wl, pj, host_cores(), cpu_seconds)
+        if r is not None:
+            m = r["jobs"]
+            out["cpu"] = {"jobs_per_s": r["jobs_per_s"], "cores": r["threads"], "kind": "reference", "sample": "first %d jobs of the list" % m,
+                          "checks": pred_checks(r["cost"])}
+            out["gpu_checks_on_sample"] = pred_checks(got[:m])
+            out["checks_equal"] = bool(np.array_equal(got[:m], r["cost"]))
+    for d in [d_f, tab, tcb, tcr, d_j, d_o] + d_r + d_fc + [x for rc in d_rc for x in rc]:
+        d.free()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import x265_b200
@@ -521,6 +623,18 @@ def run_ours(args, rank, world, local_rank):
             line["checks_equal"] = bool(mine == r["checks"])
             if not line["checks_equal"]:
                 rc = 3
+        if world == 1 and CHROMA and not args.no_pred:
+            try:
+                from frame_helpers import Workload
+                wl = r["wl"] if (not args.no_cpu) else Workload(W, H, depth=DEPTH, numRefs=NREFS, method=c["method"], subme=c["subme"], merange=c["merange"],
+                                                               rect=c["rect"], qp=c["qp"], chroma=True, amp=c["amp"])
+                an.analyse(h_fenc, h_field)                   # whole-frame results resident for the job list
+                line["pred_cost"] = pred_cost_leg(lib, an, wl, 0.0 if args.no_cpu else min(8.0, args.cpu_seconds))
+                if line["pred_cost"].get("checks_equal") is False:
+                    rc = rc or 4
+                    print("bench.py: PARITY FAILURE: prediction costs differ from the reference on the CPU sample", file=sys.stderr)
+            except Exception as e:
+                line["pred_cost_error"] = repr(e)
         if world == 1 and not args.no_primitives:
             try:
                 line["primitives"] = primitives_leg(lib)
@@ -747,6 +861,7 @@ def main():
                     help="N>1 partition: a frame per GPU (weak scaling) or the CTU rows of one frame per GPU (strong scaling); "
                          "auto (default) = the frame shard as the line, with the row shard measured in the same run and attached")
     ap.add_argument("--no-chroma", action="store_true", help="luma-only motion estimation (round-1 line; the presets run with the chroma-SATD term)")
+    ap.add_argument("--no-pred", action="store_true", help="skip the prediction-cost leg (AMVP / merge / bidir costs) of the N=1 line")
     ap.add_argument("--no-primitives", action="store_true", help="skip the per-primitive HBM GB/s table (8- and 10-bit) of the N=1 line")
     args = ap.parse_args()
     global CFG, CFG_NAME

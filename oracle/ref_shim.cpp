@@ -361,6 +361,7 @@ void* x265ref_la_create_aq(int width, int height, int nframes, const pixel* cons
 }
 }
 #include "frame.h"
+#include <thread>
 #include "predict.h"
 #include "cudata.h"
 #include "slice.h"
@@ -522,90 +523,140 @@ int x265ref_la_get(void* hv, int frame, int what, int d0, int d1, void* out)
  * x265ref_motion_estimate_chroma); the slice is a B slice without weighted prediction; the picture is made large
  * enough that CUData::clipMv leaves the vectors alone (the batched entry point takes clipped vectors).
  * ref0 / ref1 == NULL: list unused.  cost: 0 = SAD, 1 = SATD; chroma: + bufChromaSATD; biAvgPP: search.cpp:2499-2510. */
+struct RefPredCtx
+{
+    Yuv src, predYuv, bidirYuv[2];
+    MotionEstimate me;
+    Predict pred;
+    PicYuv pic[2];
+    x265_param param;
+    SPS* sps; PPS* pps; FrameData* fd; Slice* slice; CUData* cu;
+    intptr_t zero;
+    bool ok;
+    RefPredCtx()
+    {
+        ok = src.create(64, X265_CSP_I420) && predYuv.create(64, X265_CSP_I420) && bidirYuv[0].create(64, X265_CSP_I420) && bidirYuv[1].create(64, X265_CSP_I420);
+        me.init(X265_CSP_I420);
+        me.setQP(30);
+        pred.allocBuffers(X265_CSP_I420);
+        zero = 0;
+        memset(&param, 0, sizeof(param)); param.maxCUSize = 64;
+        sps = (SPS*)calloc(1, sizeof(SPS)); pps = (PPS*)calloc(1, sizeof(PPS)); fd = (FrameData*)calloc(1, sizeof(FrameData));
+        slice = (Slice*)calloc(1, sizeof(Slice)); cu = (CUData*)calloc(1, sizeof(CUData));
+        sps->picWidthInLumaSamples = 1 << 15; sps->picHeightInLumaSamples = 1 << 15;
+        pps->bUseWeightPred = false; pps->bUseWeightedBiPred = false;
+        fd->m_param = &param;
+        slice->m_sps = sps; slice->m_pps = pps; slice->m_sliceType = B_SLICE;
+        slice->m_numRefIdx[0] = slice->m_numRefIdx[1] = 1;
+        slice->m_refReconPicList[0][0] = &pic[0]; slice->m_refReconPicList[1][0] = &pic[1];
+        cu->m_slice = slice; cu->m_encData = fd;
+        cu->m_cuPelX = 1 << 14; cu->m_cuPelY = 1 << 14;
+        for (int l = 0; l < 2; l++)
+        {
+            pic[l].m_cuOffsetY = &zero; pic[l].m_cuOffsetC = &zero; pic[l].m_buOffsetY = &zero; pic[l].m_buOffsetC = &zero;
+        }
+    }
+    ~RefPredCtx()
+    {
+        for (int l = 0; l < 2; l++)
+        {
+            pic[l].m_cuOffsetY = pic[l].m_cuOffsetC = pic[l].m_buOffsetY = pic[l].m_buOffsetC = NULL;
+            pic[l].m_picOrg[0] = pic[l].m_picOrg[1] = pic[l].m_picOrg[2] = NULL;
+        }
+        src.destroy(); predYuv.destroy(); bidirYuv[0].destroy(); bidirYuv[1].destroy();
+        free(sps); free(pps); free(fd); free(slice); free(cu);
+    }
+    int run(const pixel* const* fenc, const pixel* const* ref0, const pixel* const* ref1, intptr_t stride, intptr_t cstride,
+            int pw, int ph, const int* mv0, const int* mv1, int cost, int chroma, int biAvgPP)
+    {
+        for (int y = 0; y < ph; y++) memcpy(src.m_buf[0] + y * src.m_size, fenc[0] + y * stride, pw * sizeof(pixel));
+        for (int y = 0; y < ph / 2; y++)
+        {
+            memcpy(src.m_buf[1] + y * src.m_csize, fenc[1] + y * cstride, (pw / 2) * sizeof(pixel));
+            memcpy(src.m_buf[2] + y * src.m_csize, fenc[2] + y * cstride, (pw / 2) * sizeof(pixel));
+        }
+        me.setSourcePU(src, 0, 0, 0, pw, ph, X265_STAR_SEARCH, chroma ? 3 : 2, !!chroma);
+        const bool bChromaSATD = me.bChromaSATD;
+        for (int l = 0; l < 2; l++)
+        {
+            const pixel* const* r = l ? ref1 : ref0;
+            pic[l].m_stride = stride; pic[l].m_strideC = cstride;
+            for (int k = 0; k < 3; k++) pic[l].m_picOrg[k] = r ? (pixel*)r[k] : NULL;
+        }
+        int8_t refIdx[2] = { (int8_t)(ref0 ? 0 : -1), (int8_t)(ref1 ? 0 : -1) };
+        MV mvs[2] = { MV(mv0[0], mv0[1]), MV(mv1[0], mv1[1]) };
+        cu->m_refIdx[0] = &refIdx[0]; cu->m_refIdx[1] = &refIdx[1];
+        cu->m_mv[0] = &mvs[0]; cu->m_mv[1] = &mvs[1];
+        alignas(PredictionUnit) char pubuf[sizeof(PredictionUnit)];
+        PredictionUnit& pu = *(PredictionUnit*)pubuf;
+        pu.ctuAddr = 0; pu.cuAbsPartIdx = 0; pu.puAbsPartIdx = 0; pu.width = pw; pu.height = ph;
+        int out;
+        if (ref0 && ref1 && biAvgPP)
+        {   /* search.cpp:2499-2510 */
+            pred.predInterLumaPixel(pu, bidirYuv[0], pic[0], mvs[0]);
+            pred.predInterLumaPixel(pu, bidirYuv[1], pic[1], mvs[1]);
+            primitives.pu[me.partEnum].pixelavg_pp[(predYuv.m_size % 64 == 0) && (bidirYuv[0].m_size % 64 == 0) && (bidirYuv[1].m_size % 64 == 0)](
+                predYuv.m_buf[0], predYuv.m_size, bidirYuv[0].getLumaAddr(0), bidirYuv[0].m_size, bidirYuv[1].getLumaAddr(0), bidirYuv[1].m_size, 32);
+            out = me.bufSATD(predYuv.m_buf[0], predYuv.m_size);
+        }
+        else if (!cost)
+        {   /* search.cpp:2017-2018 */
+            pred.predInterLumaPixel(pu, predYuv, ref0 ? pic[0] : pic[1], ref0 ? mvs[0] : mvs[1]);
+            out = me.bufSAD(predYuv.getLumaAddr(0), predYuv.m_size);
+        }
+        else
+        {   /* search.cpp:1944-1948, 2489-2493 */
+            pred.motionCompensation(*cu, pu, predYuv, true, bChromaSATD);
+            out = me.bufSATD(predYuv.getLumaAddr(0), predYuv.m_size);
+            if (bChromaSATD) out += me.bufChromaSATD(predYuv, 0);
+        }
+        cu->m_refIdx[0] = cu->m_refIdx[1] = NULL; cu->m_mv[0] = cu->m_mv[1] = NULL;
+        return out;
+    }
+};
+
 int x265ref_pred_cost(const pixel* const* fenc, const pixel* const* ref0, const pixel* const* ref1, intptr_t stride, intptr_t cstride,
                       int pw, int ph, const int* mv0, const int* mv1, int cost, int chroma, int biAvgPP)
 {
     ensure_init();
     static bool scales = false;
     if (!scales) { MotionEstimate::initScales(); scales = true; }
-    Yuv src, predYuv;
-    if (!src.create(64, X265_CSP_I420) || !predYuv.create(64, X265_CSP_I420)) return -1;
-    for (int y = 0; y < ph; y++) memcpy(src.m_buf[0] + y * src.m_size, fenc[0] + y * stride, pw * sizeof(pixel));
-    for (int y = 0; y < ph / 2; y++)
-    {
-        memcpy(src.m_buf[1] + y * src.m_csize, fenc[1] + y * cstride, (pw / 2) * sizeof(pixel));
-        memcpy(src.m_buf[2] + y * src.m_csize, fenc[2] + y * cstride, (pw / 2) * sizeof(pixel));
-    }
-    MotionEstimate me;
-    me.init(X265_CSP_I420);
-    me.setQP(30);
-    me.setSourcePU(src, 0, 0, 0, pw, ph, X265_STAR_SEARCH, chroma ? 3 : 2, !!chroma);
-    const bool bChromaSATD = me.bChromaSATD;
+    RefPredCtx c;
+    if (!c.ok) return -1;
+    return c.run(fenc, ref0, ref1, stride, cstride, pw, ph, mv0, mv1, cost, chroma, biAvgPP);
+}
 
-    intptr_t zero = 0;
-    PicYuv pic[2];
-    for (int l = 0; l < 2; l++)
-    {
-        const pixel* const* r = l ? ref1 : ref0;
-        pic[l].m_cuOffsetY = &zero; pic[l].m_cuOffsetC = &zero; pic[l].m_buOffsetY = &zero; pic[l].m_buOffsetC = &zero;
-        pic[l].m_stride = stride; pic[l].m_strideC = cstride;
-        for (int k = 0; k < 3; k++) pic[l].m_picOrg[k] = r ? (pixel*)r[k] : NULL;
-    }
-    x265_param param; memset(&param, 0, sizeof(param)); param.maxCUSize = 64;
-    SPS* sps = (SPS*)calloc(1, sizeof(SPS));
-    PPS* pps = (PPS*)calloc(1, sizeof(PPS));
-    FrameData* fd = (FrameData*)calloc(1, sizeof(FrameData));
-    Slice* slice = (Slice*)calloc(1, sizeof(Slice));
-    CUData* cu = (CUData*)calloc(1, sizeof(CUData));
-    sps->picWidthInLumaSamples = 1 << 15; sps->picHeightInLumaSamples = 1 << 15;
-    pps->bUseWeightPred = false; pps->bUseWeightedBiPred = false;
-    fd->m_param = &param;
-    slice->m_sps = sps; slice->m_pps = pps; slice->m_sliceType = B_SLICE;
-    slice->m_numRefIdx[0] = slice->m_numRefIdx[1] = 1;
-    slice->m_refReconPicList[0][0] = &pic[0]; slice->m_refReconPicList[1][0] = &pic[1];
-    int8_t refIdx[2] = { (int8_t)(ref0 ? 0 : -1), (int8_t)(ref1 ? 0 : -1) };
-    MV mvs[2] = { MV(mv0[0], mv0[1]), MV(mv1[0], mv1[1]) };
-    cu->m_slice = slice; cu->m_encData = fd;
-    cu->m_cuPelX = 1 << 14; cu->m_cuPelY = 1 << 14;
-    cu->m_refIdx[0] = &refIdx[0]; cu->m_refIdx[1] = &refIdx[1];
-    cu->m_mv[0] = &mvs[0]; cu->m_mv[1] = &mvs[1];
-    alignas(PredictionUnit) char pubuf[sizeof(PredictionUnit)];
-    PredictionUnit& pu = *(PredictionUnit*)pubuf;
-    pu.ctuAddr = 0; pu.cuAbsPartIdx = 0; pu.puAbsPartIdx = 0; pu.width = pw; pu.height = ph;
-    Predict pred;
-    pred.allocBuffers(X265_CSP_I420);
-
-    int out;
-    if (ref0 && ref1 && biAvgPP)
-    {   /* search.cpp:2499-2510 */
-        Yuv bidirYuv[2];
-        bidirYuv[0].create(64, X265_CSP_I420); bidirYuv[1].create(64, X265_CSP_I420);
-        pred.predInterLumaPixel(pu, bidirYuv[0], pic[0], mvs[0]);
-        pred.predInterLumaPixel(pu, bidirYuv[1], pic[1], mvs[1]);
-        primitives.pu[me.partEnum].pixelavg_pp[(predYuv.m_size % 64 == 0) && (bidirYuv[0].m_size % 64 == 0) && (bidirYuv[1].m_size % 64 == 0)](
-            predYuv.m_buf[0], predYuv.m_size, bidirYuv[0].getLumaAddr(0), bidirYuv[0].m_size, bidirYuv[1].getLumaAddr(0), bidirYuv[1].m_size, 32);
-        out = me.bufSATD(predYuv.m_buf[0], predYuv.m_size);
-        bidirYuv[0].destroy(); bidirYuv[1].destroy();
-    }
-    else if (!cost)
-    {   /* search.cpp:2017-2018 */
-        pred.predInterLumaPixel(pu, predYuv, ref0 ? pic[0] : pic[1], ref0 ? mvs[0] : mvs[1]);
-        out = me.bufSAD(predYuv.getLumaAddr(0), predYuv.m_size);
-    }
-    else
-    {   /* search.cpp:1944-1948, 2489-2493 */
-        pred.motionCompensation(*cu, pu, predYuv, true, bChromaSATD);
-        out = me.bufSATD(predYuv.getLumaAddr(0), predYuv.m_size);
-        if (bChromaSATD) out += me.bufChromaSATD(predYuv, 0);
-    }
-    for (int l = 0; l < 2; l++)
-    {
-        pic[l].m_cuOffsetY = pic[l].m_cuOffsetC = pic[l].m_buOffsetY = pic[l].m_buOffsetC = NULL;
-        pic[l].m_picOrg[0] = pic[l].m_picOrg[1] = pic[l].m_picOrg[2] = NULL;
-    }
-    src.destroy(); predYuv.destroy();
-    free(sps); free(pps); free(fd); free(slice); free(cu);
-    return out;
+/* The same over a job list in the batched entry point's layout (include/x265_b200.h: x265cu_pred_job), `nthreads` host
+ * threads, one context (Predict, MotionEstimate, Yuv buffers) per thread: bench.py's CPU arm of the `pred_cost` leg.
+ * Planes are given at the picture origin (pixel (0,0)); refs / refCb / refCr are tables indexed by job.ref0 / ref1. */
+struct ref_pred_job { int32_t offset; int16_t pw, ph; int8_t ref0, ref1; uint8_t cost, flags; int16_t mv0[2], mv1[2]; };
+int x265ref_pred_cost_batch(const pixel* fenc, const pixel* fencCb, const pixel* fencCr, const pixel* const* refs, const pixel* const* refCb,
+                            const pixel* const* refCr, intptr_t stride, intptr_t cstride, const void* jobsv, int n, int32_t* out, int nthreads)
+{
+    ensure_init();
+    static bool scales = false;
+    if (!scales) { MotionEstimate::initScales(); scales = true; }
+    const ref_pred_job* jobs = (const ref_pred_job*)jobsv;
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([=]() {
+            RefPredCtx c;
+            for (int i = t; i < n; i += nthreads)
+            {
+                const ref_pred_job& j = jobs[i];
+                const intptr_t py = j.offset / stride, px = j.offset % stride;
+                const intptr_t coff = (py >> 1) * cstride + (px >> 1);
+                const pixel* f[3] = { fenc + j.offset, fencCb + coff, fencCr + coff };
+                const pixel* r0[3]; const pixel* r1[3];
+                if (j.ref0 >= 0) { r0[0] = refs[j.ref0] + j.offset; r0[1] = refCb[j.ref0] + coff; r0[2] = refCr[j.ref0] + coff; }
+                if (j.ref1 >= 0) { r1[0] = refs[j.ref1] + j.offset; r1[1] = refCb[j.ref1] + coff; r1[2] = refCr[j.ref1] + coff; }
+                const int mv0[2] = { j.mv0[0], j.mv0[1] }, mv1[2] = { j.mv1[0], j.mv1[1] };
+                out[i] = c.run(f, j.ref0 >= 0 ? r0 : NULL, j.ref1 >= 0 ? r1 : NULL, stride, cstride, j.pw, j.ph, mv0, mv1, j.cost, j.flags & 1, (j.flags >> 1) & 1);
+            }
+        });
+    for (auto& x : th) x.join();
+    return 0;
 }
 
 } // extern "C"

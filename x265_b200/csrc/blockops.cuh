@@ -268,6 +268,43 @@ __global__ void __launch_bounds__(256) k_lowres_init_u8x8(const uint8_t* __restr
     *(uint2*)(dc + o) = make_uint2(out[3][0], out[3][1]);
 }
 
+// 16-bit fast path (10 / 12-bit pixels): a thread produces 4 adjacent lowres pixels of all 4 planes on packed halfword pairs:
+// (a + b + 1) >> 1 of two pixels per 32-bit add (no carry between the halves: sums stay below 2^13), PRMT for the
+// even / odd column split, three 16-byte row loads (+ the ninth pixel), four 8-byte stores.
+__device__ __forceinline__ uint32_t avg2_u16(uint32_t a, uint32_t b) { return ((a + b + 0x00010001u) >> 1) & 0x7fff7fffu; }
+__global__ void __launch_bounds__(256) k_lowres_init_u16x4(const uint16_t* __restrict__ src, int sstride, uint16_t* __restrict__ d0, uint16_t* __restrict__ dh,
+                                                           uint16_t* __restrict__ dv, uint16_t* __restrict__ dc, int dstride, int width4, int height)
+{
+    const int xu = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xu >= width4 || y >= height) return;
+    const uint16_t* r0 = src + (int64_t)(2 * y) * sstride + 8 * xu;
+    const uint16_t* r1 = r0 + sstride;
+    const uint16_t* r2 = r1 + sstride;
+    const uint4 a = __ldg((const uint4*)r0), b = __ldg((const uint4*)r1), c = __ldg((const uint4*)r2);
+    const uint32_t a8 = __ldg(r0 + 8), b8 = __ldg(r1 + 8), c8 = __ldg(r2 + 8);
+    const uint32_t A[4] = { a.x, a.y, a.z, a.w }, B[4] = { b.x, b.y, b.z, b.w }, C4[4] = { c.x, c.y, c.z, c.w };
+    uint32_t out[4][2];
+#pragma unroll
+    for (int half = 0; half < 2; half++)
+    {
+        uint32_t V[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) V[i] = half ? avg2_u16(B[i], C4[i]) : avg2_u16(A[i], B[i]);
+        const uint32_t t = half ? (b8 + c8 + 1) >> 1 : (a8 + b8 + 1) >> 1;
+        const uint32_t E0 = __byte_perm(V[0], V[1], 0x5410), O0 = __byte_perm(V[0], V[1], 0x7632);       // (v0, v2), (v1, v3)
+        const uint32_t E1 = __byte_perm(V[2], V[3], 0x5410), O1 = __byte_perm(V[2], V[3], 0x7632);       // (v4, v6), (v5, v7)
+        const uint32_t ES0 = __byte_perm(E0, E1, 0x5432), ES1 = __byte_perm(E1, t, 0x5432);              // (v2, v4), (v6, v8)
+        out[2 * half][0] = avg2_u16(E0, O0);      out[2 * half][1] = avg2_u16(E1, O1);
+        out[2 * half + 1][0] = avg2_u16(O0, ES0); out[2 * half + 1][1] = avg2_u16(O1, ES1);
+    }
+    const int64_t o = (int64_t)y * dstride + 4 * xu;
+    *(uint2*)(d0 + o) = make_uint2(out[0][0], out[0][1]);
+    *(uint2*)(dh + o) = make_uint2(out[1][0], out[1][1]);
+    *(uint2*)(dv + o) = make_uint2(out[2][0], out[2][1]);
+    *(uint2*)(dc + o) = make_uint2(out[3][0], out[3][1]);
+}
+
 // extendPicBorder (pixel.cpp:1027-1041) in ONE launch for up to four planes of the same geometry (round 1: a left/right
 // and a top/bottom launch per plane, nine launches for a lowres init).  The reference replicates the edge pixels of every
 // row, then copies `stride` elements of the (extended) first / last row into the margin rows; every output here is a pure
@@ -275,21 +312,24 @@ __global__ void __launch_bounds__(256) k_lowres_init_u8x8(const uint8_t* __restr
 // passes need no ordering.  Block = one output row of one plane.
 template <typename P> struct ExtPlanes { P* p[4]; };
 template <typename P>
-__global__ void __launch_bounds__(128) k_extend_border(ExtPlanes<P> pl, int stride, int width, int height, int mx, int my)
+__global__ void __launch_bounds__(256) k_extend_border(ExtPlanes<P> pl, int stride, int width, int height, int mx, int my)
 {
+    // a WARP per output row (8 rows per CTA): a CTA per row meant 100 K tiny CTAs for a stacked batch of lowres planes
     P* pic = pl.p[blockIdx.y];
-    const int r = (int)blockIdx.x - my;                              // output row: -my .. height + my - 1
+    const int lane = threadIdx.x & 31;
+    const int r = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) - my;      // output row: -my .. height + my - 1
+    if (r >= height + my) return;
     const int sr = min(max(r, 0), height - 1);
     const P* srow = pic + (int64_t)sr * stride;
     P* drow = pic + (int64_t)r * stride;
     const P l = srow[0], rt = srow[width - 1];
     if (r == sr)
     {
-        for (int x = threadIdx.x; x < mx; x += blockDim.x) { drow[-mx + x] = l; drow[width + x] = rt; }
+        for (int x = lane; x < mx; x += 32) { drow[-mx + x] = l; drow[width + x] = rt; }
     }
     else
     {   // `stride` elements from column -mx: margins replicated, the row itself, and whatever padding follows (as memcpy does)
-        for (int x = threadIdx.x; x < stride; x += blockDim.x)
+        for (int x = lane; x < stride; x += 32)
         {
             const int sx = x - mx;
             drow[sx] = sx < 0 ? l : sx < width ? srow[sx] : sx < width + mx ? rt : srow[sx];
@@ -302,7 +342,7 @@ static int extend_border_n(x265cu_ctx* ctx, P* const* pics, int nplanes, int str
 {
     ExtPlanes<P> pl;
     for (int i = 0; i < 4; i++) pl.p[i] = pics[i < nplanes ? i : 0];
-    k_extend_border<P><<<dim3(height + 2 * my, nplanes), 128, 0, ctx->stream>>>(pl, stride, width, height, mx, my);
+    k_extend_border<P><<<dim3((height + 2 * my + 7) / 8, nplanes), 256, 0, ctx->stream>>>(pl, stride, width, height, mx, my);
     CU_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -254,10 +254,12 @@ __device__ __forceinline__ int grp_sad(const P* __restrict__ a, int sa, const P*
 {
     constexpr int PPW = 4 / (int)sizeof(P);                       // pixels per word
     const int wq = w / PPW, nq = wq * h;
+    const bool p2 = (wq & (wq - 1)) == 0;                         // no integer division per word for the power-of-two widths
+    const int lgq = 31 - __clz(wq);
     uint32_t acc = 0;
     for (int i = sub; i < nq; i += lpj)
     {
-        const int y = i / wq, x = (i - y * wq) * PPW;
+        const int y = p2 ? i >> lgq : i / wq, x = (i - y * wq) * PPW;
         const uint32_t wa = pc_ld32((uintptr_t)(a + y * sa + x)), wb = pc_ld32((uintptr_t)(b + y * sb + x));
         if (sizeof(P) == 1) acc = __vsadu4(wa, wb) + acc;
         else { const uint32_t t = __vmaxu2(wa, wb) - __vminu2(wa, wb); acc += (t & 0xffffu) + (t >> 16); }
@@ -327,9 +329,11 @@ __device__ __forceinline__ unsigned long long grp_sse(const PA* __restrict__ a, 
 {
     unsigned long long acc = 0;
     const int n = w * h;
+    const bool p2 = (w & (w - 1)) == 0;
+    const int lgw = 31 - __clz(w);
     for (int i = sub; i < n; i += lpj)
     {
-        const int y = i / w, x = i - y * w;
+        const int y = p2 ? i >> lgw : i / w, x = i - y * w;
         const int d = (int)a[y * sa + x] - (int)b[y * sb + x];
         acc += (unsigned)(d * d);
     }
@@ -380,14 +384,15 @@ __device__ __forceinline__ int pixelcmp_units(int op, int w, int h)
 
 template <typename P>
 __global__ void __launch_bounds__(256) k_pixelcmp(int op, const P* __restrict__ A, const P* __restrict__ B,
-                                                  const x265cu_cmp_job* __restrict__ jobs, int n, uint64_t* __restrict__ out)
+                                                  const x265cu_cmp_job* __restrict__ jobs, int n, uint64_t* __restrict__ out, int lgChunk)
 {
+    // a warp takes 2^lgChunk consecutive jobs (32 for long lists; fewer when the list is too short to give every SM its warps)
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    const int nchunks = (n + 31) >> 5;
+    const int nchunks = (n + (1 << lgChunk) - 1) >> lgChunk;
     for (int ch = blockIdx.x * wpb + (threadIdx.x >> 5); ch < nchunks; ch += gridDim.x * wpb)
     {
-        const int j0 = ch << 5, cnt = min(32, n - j0);
+        const int j0 = ch << lgChunk, cnt = min(1 << lgChunk, n - j0);
         x265cu_cmp_job mine;
         mine.a_off = 0; mine.b_off = 0; mine.a_stride = 0; mine.b_stride = 0; mine.w = 4; mine.h = 4;
         if (lane < cnt) mine = jobs[j0 + lane];
@@ -470,13 +475,17 @@ static int launch_pixelcmp(x265cu_ctx* ctx, int depth, int op, const void* A, co
 {
     if (n <= 0) return 0;
     const int threads = 256, wpb = threads / 32;
-    int blocks = ((n + 31) / 32 + wpb - 1) / wpb;                 // a warp takes 32 jobs at a time
+    // jobs per warp chunk: 32 when that still leaves every SM ~32 warps of work, else the largest power of two that does
+    int lgChunk = 5;
+    while (lgChunk > 0 && (n >> lgChunk) < ctx->sm_count * 32) lgChunk--;
+    const int nchunks = (n + (1 << lgChunk) - 1) >> lgChunk;
+    int blocks = (nchunks + wpb - 1) / wpb;
     int maxb = ctx->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (depth == 8)
-        k_pixelcmp<uint8_t><<<blocks, threads, 0, ctx->stream>>>(op, (const uint8_t*)A, (const uint8_t*)B, jobs, n, out);
+        k_pixelcmp<uint8_t><<<blocks, threads, 0, ctx->stream>>>(op, (const uint8_t*)A, (const uint8_t*)B, jobs, n, out, lgChunk);
     else
-        k_pixelcmp<uint16_t><<<blocks, threads, 0, ctx->stream>>>(op, (const uint16_t*)A, (const uint16_t*)B, jobs, n, out);
+        k_pixelcmp<uint16_t><<<blocks, threads, 0, ctx->stream>>>(op, (const uint16_t*)A, (const uint16_t*)B, jobs, n, out, lgChunk);
     CU_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -235,6 +235,11 @@ int x265cu_frame_init_lowres(x265cu_ctx* c, int depth, const void* src, int sstr
         dim3 g8((width / 8 + 63) / 64, (height + 3) / 4);
         k_lowres_init_u8x8<<<g8, block, 0, c->stream>>>((const uint8_t*)src, sstride, (uint8_t*)d0, (uint8_t*)dh, (uint8_t*)dv, (uint8_t*)dc, dstride, width / 8, height);
     }
+    else if (depth != 8 && (width & 3) == 0 && (((uintptr_t)src | (uintptr_t)(sstride * 2)) & 15) == 0 && (((uintptr_t)d0 | (uintptr_t)dh | (uintptr_t)dv | (uintptr_t)dc | (uintptr_t)(dstride * 2)) & 7) == 0)
+    {
+        dim3 g4((width / 4 + 63) / 64, (height + 3) / 4);
+        k_lowres_init_u16x4<<<g4, block, 0, c->stream>>>((const uint16_t*)src, sstride, (uint16_t*)d0, (uint16_t*)dh, (uint16_t*)dv, (uint16_t*)dc, dstride, width / 4, height);
+    }
     else if (depth == 8)
         k_lowres_init<uint8_t><<<grid, block, 0, c->stream>>>((const uint8_t*)src, sstride, (uint8_t*)d0, (uint8_t*)dh, (uint8_t*)dv, (uint8_t*)dc, dstride, width, height);
     else
