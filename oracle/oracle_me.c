@@ -365,6 +365,16 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
         bmv.x += k_square1[dir].x; bmv.y += k_square1[dir].y;
         break;
     }
+    case 5: /* X265_FULL_SEARCH motion.cpp:1397-1440: every full-pel position of [mvmin, mvmax], raster order, strict '<' */
+    {
+        for (int ty = c->mvmin.y; ty <= c->mvmax.y; ty++)
+            for (int tx = c->mvmin.x; tx <= c->mvmax.x; tx++)
+            {
+                int cost = cost_fpel(c, tx, ty);
+                if (cost < bcost) { bcost = cost; bmv.x = tx; bmv.y = ty; }
+            }
+        break;
+    }
     case 3: /* X265_STAR_SEARCH motion.cpp:1132-1240 */
     {
         star_t s; s.bmv = bmv; s.bcost = bcost; s.point = 0; s.dist = 0;

@@ -69,7 +69,7 @@ def oracle_run(O, depth, fenc, refs, stride, jobs, lowres, tab):
 
 
 @pytest.mark.parametrize("depth", [8, 10])
-@pytest.mark.parametrize("method", [0, 1, 3])
+@pytest.mark.parametrize("method", [0, 1, 3, 5])
 @pytest.mark.parametrize("lowres", [0, 1])
 @pytest.mark.parametrize("smooth", [True, False])
 def test_me_batch(cu, depth, method, lowres, smooth):
@@ -77,7 +77,7 @@ def test_me_batch(cu, depth, method, lowres, smooth):
     rng = np.random.default_rng(100 + method * 7 + lowres * 3 + depth + smooth)
     W, H, margin = 256, 192, 96
     mx = (1 << depth) - 1
-    merange = 57 if (method == 3 and not lowres) else 16
+    merange = 57 if (method == 3 and not lowres) else (9 if method == 5 else 16)      # 5 = X265_FULL_SEARCH: exhaustive
     if lowres:
         yy, xx = np.mgrid[0:H * 2, 0:W * 2]
         def img(shift):

@@ -77,6 +77,21 @@ def test_motion_estimate(depth, method):
 
 
 @pytest.mark.parametrize("depth", DEPTHS)
+def test_motion_estimate_full_search(depth):
+    """X265_FULL_SEARCH (motion.cpp:1397-1440): exhaustive scan of [mvmin, mvmax]; small search ranges keep it quick."""
+    R, O = libs(depth)
+    rng = np.random.default_rng(77)
+    n = 0
+    for (w, h) in [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (32, 16), (24, 32), (16, 4), (4, 8), (12, 16), (64, 48)]:
+        for subme in (0, 2, 3):
+            for smooth in (True, False):
+                r, o = _me_job(O, R, depth, rng, w, h, 5, subme, 0, smooth, int(rng.integers(3, 12)))
+                assert r == o, (w, h, subme, smooth, r, o)
+                n += 1
+    assert n == 72
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
 def test_motion_estimate_lowres(depth):
     R, O = libs(depth)
     rng = np.random.default_rng(17)

@@ -1520,6 +1520,21 @@ __device__ __forceinline__ void me_phase2(MeCtx<P>& c, const x265cu_me_job& j, M
             bmx += c_square1[dir][0]; bmy += c_square1[dir][1];
         }
     }
+    else if (j.method == 5)
+    {   // X265_FULL_SEARCH (motion.cpp:1397-1440): every full-pel position of [mvmin, mvmax] in raster order with a strict '<':
+        // bursts of 32 consecutive x positions; a burst's winner is its minimum with ties to the lowest x, which is the
+        // position the sequential compare would keep, and it replaces the best so far only when strictly cheaper
+        for (int ty = c.miny; ty <= c.maxy; ty++)
+            for (int tx0 = c.minx; tx0 <= c.maxx; tx0 += 32)
+            {
+                const int n = min(32, c.maxx - tx0 + 1);
+                const int px = tx0 + min(c.lane, n - 1);
+                const int cost = me_eval_points(c, n, px, ty, false);
+                const unsigned key = c.lane < n ? (((unsigned)cost << 5) | (unsigned)c.lane) : 0xffffffffu;
+                const unsigned m = __reduce_min_sync(0xffffffffu, key);
+                if ((int)(m >> 5) < bcost) { bcost = (int)(m >> 5); bmx = tx0 + (int)(m & 31); bmy = ty; }
+            }
+    }
     else
     {
         MeStar s; s.bx = bmx; s.by = bmy; s.bcost = bcost; s.point = 0; s.dist = 0;

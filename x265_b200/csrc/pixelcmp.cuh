@@ -257,6 +257,7 @@ __device__ __forceinline__ int grp_sad(const P* __restrict__ a, int sa, const P*
     const bool p2 = (wq & (wq - 1)) == 0;                         // no integer division per word for the power-of-two widths
     const int lgq = 31 - __clz(wq);
     uint32_t acc = 0;
+#pragma unroll 4
     for (int i = sub; i < nq; i += lpj)
     {
         const int y = p2 ? i >> lgq : i / wq, x = (i - y * wq) * PPW;
@@ -331,6 +332,7 @@ __device__ __forceinline__ unsigned long long grp_sse(const PA* __restrict__ a, 
     const int n = w * h;
     const bool p2 = (w & (w - 1)) == 0;
     const int lgw = 31 - __clz(w);
+#pragma unroll 4
     for (int i = sub; i < n; i += lpj)
     {
         const int y = p2 ? i >> lgw : i / w, x = i - y * w;
@@ -382,7 +384,10 @@ __device__ __forceinline__ int pixelcmp_units(int op, int w, int h)
     }
 }
 
-template <typename P>
+// HAD = false: the element-wise costs (SAD, SSE, SSD_S, VAR); HAD = true: the Hadamard costs (SATD, SA8D, PSY).  Two
+// instantiations because the 8x8 Hadamard needs 128 registers (16 resident warps per SM), which starved the latency-bound
+// element-wise loops: on their own they need ~40 registers and run with 64 warps per SM.
+template <typename P, bool HAD>
 __global__ void __launch_bounds__(256) k_pixelcmp(int op, const P* __restrict__ A, const P* __restrict__ B,
                                                   const x265cu_cmp_job* __restrict__ jobs, int n, uint64_t* __restrict__ out, int lgChunk)
 {
@@ -412,11 +417,12 @@ __global__ void __launch_bounds__(256) k_pixelcmp(int op, const P* __restrict__ 
             const int wh = __shfl_sync(0xffffffffu, ((int)mine.w << 16) | (int)(uint16_t)mine.h, ks);
             const int w = wh >> 16, h = wh & 0xffff;
             uint64_t res = 0;
-            switch (op)
+            switch (HAD ? op : (op == X265CU_SATD || op == X265CU_SA8D || op == X265CU_PSY ? -1 : op))
             {
             case X265CU_SAD:  res = (uint32_t)grp_sad<P>(A + a_off, sa, B + b_off, sb, w, h, sub, lpj); break;
-            case X265CU_SATD: res = (uint32_t)grp_satd(A + a_off, sa, B + b_off, sb, w, h, sub, lpj); break;
+            case X265CU_SATD: if (HAD) res = (uint32_t)grp_satd(A + a_off, sa, B + b_off, sb, w, h, sub, lpj); break;
             case X265CU_SA8D:
+            if (HAD)
             {
                 // blocks below 8x8 take the SATD path; a pass mixing both kinds would diverge around the in-loop shuffles
                 const bool small = w < 8 || h < 8;
@@ -427,8 +433,8 @@ __global__ void __launch_bounds__(256) k_pixelcmp(int op, const P* __restrict__ 
                 if (anyBig)  v = grp_sa8d(A + a_off, sa, B + b_off, sb, small ? 8 : w, small ? 8 : h, sub, lpj, ntmax);
                 if (anySmall) { const int v2 = grp_satd(A + a_off, sa, B + b_off, sb, small ? w : 4, small ? h : 4, sub, lpj); if (small) v = v2; }
                 res = (uint32_t)v;
-                break;
             }
+            break;
             case X265CU_SSE_PP:
             {
                 const unsigned long long v = grp_sse(A + a_off, sa, B + b_off, sb, w, h, sub, lpj);
@@ -460,7 +466,7 @@ __global__ void __launch_bounds__(256) k_pixelcmp(int op, const P* __restrict__ 
                 res = (uint64_t)s + ((uint64_t)q << 32);
                 break;
             }
-            case X265CU_PSY: res = (uint32_t)grp_psy(A + a_off, sa, B + b_off, sb, w, sub, lpj); break;
+            case X265CU_PSY: if (HAD) res = (uint32_t)grp_psy(A + a_off, sa, B + b_off, sb, w, sub, lpj); break;
             }
             // hand the result to the lane that owns job k: lane L's job was worked on in pass L / jpp by sub-group L % jpp
             const unsigned long long got = __shfl_sync(0xffffffffu, (unsigned long long)res, (lane & (jpp - 1)) << lglpj);
@@ -482,10 +488,17 @@ static int launch_pixelcmp(x265cu_ctx* ctx, int depth, int op, const void* A, co
     int blocks = (nchunks + wpb - 1) / wpb;
     int maxb = ctx->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
+    const bool had = op == X265CU_SATD || op == X265CU_SA8D || op == X265CU_PSY;
     if (depth == 8)
-        k_pixelcmp<uint8_t><<<blocks, threads, 0, ctx->stream>>>(op, (const uint8_t*)A, (const uint8_t*)B, jobs, n, out, lgChunk);
+    {
+        if (had) k_pixelcmp<uint8_t, true><<<blocks, threads, 0, ctx->stream>>>(op, (const uint8_t*)A, (const uint8_t*)B, jobs, n, out, lgChunk);
+        else     k_pixelcmp<uint8_t, false><<<blocks, threads, 0, ctx->stream>>>(op, (const uint8_t*)A, (const uint8_t*)B, jobs, n, out, lgChunk);
+    }
     else
-        k_pixelcmp<uint16_t><<<blocks, threads, 0, ctx->stream>>>(op, (const uint16_t*)A, (const uint16_t*)B, jobs, n, out, lgChunk);
+    {
+        if (had) k_pixelcmp<uint16_t, true><<<blocks, threads, 0, ctx->stream>>>(op, (const uint16_t*)A, (const uint16_t*)B, jobs, n, out, lgChunk);
+        else     k_pixelcmp<uint16_t, false><<<blocks, threads, 0, ctx->stream>>>(op, (const uint16_t*)A, (const uint16_t*)B, jobs, n, out, lgChunk);
+    }
     CU_LAUNCH_CHECK(ctx);
     return 0;
 }

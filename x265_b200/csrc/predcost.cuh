@@ -17,6 +17,11 @@
 
 template <int TPJ> __device__ __forceinline__ void pc_sync() { if (TPJ == 32) __syncwarp(); else __syncthreads(); }
 
+// i -> (row, column) of a block `w` wide: a shift for the power-of-two widths (every symmetric PU), a division for 12 / 24 / 48
+struct PcDiv { int w, lg; };
+__device__ __forceinline__ PcDiv pc_div(int width) { PcDiv d; d.w = width; d.lg = (width & (width - 1)) ? -1 : 31 - __clz(width); return d; }
+__device__ __forceinline__ void pc_split(const PcDiv& d, int i, int& y, int& x) { y = d.lg >= 0 ? i >> d.lg : i / d.w; x = i - y * d.w; }
+
 // One plane's prediction of a w x h block into dst (int16, pitch DP): pixel domain (SHORT = false: copy / hpp / vpp / hvpp)
 // or the 14-bit intermediate (SHORT = true: p2s / hps / vps / hps + vss).  NT = 8 (luma, quarter-pel) or 4 (chroma, eighth).
 template <typename P, int TPJ, int MAXS, int NT, bool SHORT>
@@ -30,9 +35,10 @@ __device__ __forceinline__ void pc_predict(const P* __restrict__ ref, int stride
     const P* src = ref + (mvx >> FB) + (ptrdiff_t)(mvy >> FB) * stride;
     if (!(xf | yf))
     {
+        const PcDiv dw = pc_div(w);
         for (int i = t; i < w * h; i += TPJ)
         {
-            const int y = i / w, x = i - y * w;
+            int y, x; pc_split(dw, i, y, x);
             const int p = src[(ptrdiff_t)y * stride + x];
             dst[y * DP + x] = (int16_t)(SHORT ? (p << (14 - DEPTH)) - 8192 : p);
         }
@@ -40,6 +46,7 @@ __device__ __forceinline__ void pc_predict(const P* __restrict__ ref, int stride
     }
     const int hl = xf ? HL : 0, vt = yf ? HL : 0;
     const int ww = w + (xf ? NT - 1 : 0), wh = h + (yf ? NT - 1 : 0);
+    const PcDiv dw = pc_div(w);
     for (int i = t; i < ww * wh; i += TPJ)
     {
         const int r = i / ww, c = i - r * ww;
@@ -54,7 +61,7 @@ __device__ __forceinline__ void pc_predict(const P* __restrict__ ref, int stride
         const int16_t* cf = !yf ? cx : cy;
         for (int i = t; i < w * h; i += TPJ)
         {
-            const int y = i / w, x = i - y * w;
+            int y, x; pc_split(dw, i, y, x);
             int sum = 0;
 #pragma unroll
             for (int k = 0; k < NT; k++) sum += (int)s_win[y * WP + x + k * step] * cf[k];
@@ -65,7 +72,7 @@ __device__ __forceinline__ void pc_predict(const P* __restrict__ ref, int stride
     {
         for (int i = t; i < w * wh; i += TPJ)
         {
-            const int r = i / w, x = i - r * w;
+            int r, x; pc_split(dw, i, r, x);
             int sum = 0;
 #pragma unroll
             for (int k = 0; k < NT; k++) sum += (int)s_win[r * WP + x + k] * cx[k];
@@ -74,7 +81,7 @@ __device__ __forceinline__ void pc_predict(const P* __restrict__ ref, int stride
         pc_sync<TPJ>();
         for (int i = t; i < w * h; i += TPJ)
         {
-            const int y = i / w, x = i - y * w;
+            int y, x; pc_split(dw, i, y, x);
             int sum = 0;
 #pragma unroll
             for (int k = 0; k < NT; k++) sum += (int)s_mid[(y + k) * DP + x] * cy[k];
@@ -103,9 +110,10 @@ __device__ __forceinline__ void pc_plane(const P* r0, const P* r1, int stride, c
         pc_sync<TPJ>();
         pc_predict<P, TPJ, MAXS, NT, false>(r1, stride, jb.mv1[0], jb.mv1[1], w, h, s_p1, s_win, s_mid, t);
         pc_sync<TPJ>();
+        const PcDiv dw = pc_div(w);
         for (int i = t; i < w * h; i += TPJ)
         {
-            const int y = i / w, x = i - y * w;
+            int y, x; pc_split(dw, i, y, x);
             s_p0[y * DP + x] = (int16_t)(((int)s_p0[y * DP + x] + (int)s_p1[y * DP + x] + 1) >> 1);       // pixelavg_pp (pixel.cpp:545-557)
         }
     }
@@ -116,9 +124,10 @@ __device__ __forceinline__ void pc_plane(const P* r0, const P* r1, int stride, c
         pc_predict<P, TPJ, MAXS, NT, true>(r1, stride, jb.mv1[0], jb.mv1[1], w, h, s_p1, s_win, s_mid, t);
         pc_sync<TPJ>();
         constexpr int shift = 15 - DEPTH, offset = (1 << (shift - 1)) + 2 * 8192;                       // addAvg (pixel.cpp:842-862)
+        const PcDiv dw = pc_div(w);
         for (int i = t; i < w * h; i += TPJ)
         {
-            const int y = i / w, x = i - y * w;
+            int y, x; pc_split(dw, i, y, x);
             s_p0[y * DP + x] = (int16_t)clip3i(0, maxv, ((int)s_p0[y * DP + x] + (int)s_p1[y * DP + x] + offset) >> shift);
         }
     }
@@ -134,7 +143,8 @@ __device__ __forceinline__ int pc_cost(const P* __restrict__ f, int fs, const in
     int acc = 0;
     if (!satd)
     {
-        for (int i = t; i < w * h; i += TPJ) { const int y = i / w, x = i - y * w; acc += abs((int)f[(ptrdiff_t)y * fs + x] - (int)pr[y * DP + x]); }
+        const PcDiv dw = pc_div(w);
+        for (int i = t; i < w * h; i += TPJ) { int y, x; pc_split(dw, i, y, x); acc += abs((int)f[(ptrdiff_t)y * fs + x] - (int)pr[y * DP + x]); }
     }
     else if (!(w & 7))
     {
@@ -162,7 +172,7 @@ struct PredChroma { const void* fcb; const void* fcr; const void* const* rcb; co
 
 // TPJ = 32: a warp per job (PUs up to MAXS = 16); TPJ = 128: a CTA per job (MAXS = 64)
 template <typename P, int TPJ, int MAXS>
-__global__ void __launch_bounds__(128) k_pred_cost(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride,
+__global__ void __launch_bounds__(128, TPJ == 32 ? 8 : 4) k_pred_cost(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride,
                                                    PredChroma ch, const x265cu_pred_job* __restrict__ jobs, int n, int32_t* __restrict__ out)
 {
     constexpr int JPB = 128 / TPJ;

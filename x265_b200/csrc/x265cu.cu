@@ -204,6 +204,24 @@ int x265cu_intra_allangs_batch(x265cu_ctx* c, int depth, int size, const void* r
     if ((((uintptr_t)dst) & 7) == 0 && size >= 4 && size <= 32)
     {   // vector-store kernel: one CTA per block, all 33 modes
         int blocks = n < c->sm_count * 16 ? n : c->sm_count * 16;
+        if (!((uintptr_t)dst & 15))
+        {   // packed-pixel kernel (16-byte row pieces): words per item = min(row bytes, 16) / 4
+            const int rowBytes = size * (depth == 8 ? 1 : 2), uw = (rowBytes < 16 ? rowBytes : 16) / 4;
+            blocks = n < c->sm_count * 8 ? n : c->sm_count * 8;
+            if (depth == 8)
+            {
+                if (uw == 4)      k_intra_allangs_packed<uint8_t, 4><<<blocks, 256, 0, c->stream>>>(size, (const uint8_t*)ref, (const uint8_t*)filt, nb_pitch, (uint8_t*)dst, bLuma, n);
+                else if (uw == 2) k_intra_allangs_packed<uint8_t, 2><<<blocks, 256, 0, c->stream>>>(size, (const uint8_t*)ref, (const uint8_t*)filt, nb_pitch, (uint8_t*)dst, bLuma, n);
+                else              k_intra_allangs_packed<uint8_t, 1><<<blocks, 256, 0, c->stream>>>(size, (const uint8_t*)ref, (const uint8_t*)filt, nb_pitch, (uint8_t*)dst, bLuma, n);
+            }
+            else
+            {
+                if (uw == 4)      k_intra_allangs_packed<uint16_t, 4><<<blocks, 256, 0, c->stream>>>(size, (const uint16_t*)ref, (const uint16_t*)filt, nb_pitch, (uint16_t*)dst, bLuma, n);
+                else              k_intra_allangs_packed<uint16_t, 2><<<blocks, 256, 0, c->stream>>>(size, (const uint16_t*)ref, (const uint16_t*)filt, nb_pitch, (uint16_t*)dst, bLuma, n);
+            }
+            CU_LAUNCH_CHECK(c);
+            return 0;
+        }
         if (depth == 8) k_intra_allangs_cta<uint8_t><<<blocks, 256, 0, c->stream>>>(size, (const uint8_t*)ref, (const uint8_t*)filt, nb_pitch, (uint8_t*)dst, bLuma, n);
         else            k_intra_allangs_cta<uint16_t><<<blocks, 256, 0, c->stream>>>(size, (const uint16_t*)ref, (const uint16_t*)filt, nb_pitch, (uint16_t*)dst, bLuma, n);
         CU_LAUNCH_CHECK(c);
