@@ -18,7 +18,7 @@ done
 tail -n 3 gpurun_out/bench_c3.err gpurun_out/bench_c4.err gpurun_out/bench_c2.err
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 timeout 300 ncu --metrics $M --clock-control none -k regex:k_me -c 9 --csv --log-file gpurun_out/me_traffic_2160.csv python profiles/run_small.py 3840 2160 1 1 1 > gpurun_out/me_traffic_2160.log 2>&1
-timeout 500 ncu --metrics $M --clock-control none -k "regex:^(void )?(lf::)?k_" --csv --log-file gpurun_out/prims_ncu.csv python profiles/primitive_bench.py --single --frames 6 --depth 8,10 --json gpurun_out/prims_single.json > gpurun_out/prims_ncu.log 2>&1
+timeout 500 ncu --metrics $M --clock-control none -k "regex:^(void )?(lf::)?k_" --csv --log-file gpurun_out/prims_ncu.csv python profiles/primitive_bench.py --single --frames 24 --depth 8,10 --json gpurun_out/prims_single.json > gpurun_out/prims_ncu.log 2>&1
 tail -n 3 gpurun_out/prims_ncu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -n 2 gpurun_out/smoke.log
 du -sh gpurun_out

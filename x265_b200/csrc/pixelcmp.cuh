@@ -325,6 +325,39 @@ __device__ __forceinline__ int grp_sa8d(const PA* __restrict__ a, int sa, const 
     return grp_sum(acc, lpj);
 }
 
+// sse_pp on packed words.  8-bit: |a - b| of four pixels (VABSDIFF4), squared and summed by ONE DP4A(d, d) into a 32-bit partial
+// (a lane adds at most 4 * 255^2 per word and sees at most 1024 words of a 64x64 block: no overflow).  16-bit pixels: the two
+// halves' differences (max - min, no borrow) squared and added in 64 bits.
+template <typename P>
+__device__ __forceinline__ unsigned long long grp_sse_pp(const P* __restrict__ a, int sa, const P* __restrict__ b, int sb, int w, int h, int sub, int lpj)
+{
+    constexpr int PPW = 4 / (int)sizeof(P);
+    const int wq = w / PPW, nq = wq * h;
+    const bool p2 = (wq & (wq - 1)) == 0;
+    const int lgq = 31 - __clz(wq);
+    unsigned long long acc = 0;
+    uint32_t part = 0;
+#pragma unroll 4
+    for (int i = sub; i < nq; i += lpj)
+    {
+        const int y = p2 ? i >> lgq : i / wq, x = (i - y * wq) * PPW;
+        const uint32_t wa = pc_ld32((uintptr_t)(a + y * sa + x)), wb = pc_ld32((uintptr_t)(b + y * sb + x));
+        if (sizeof(P) == 1)
+        {
+            const uint32_t d = __vabsdiffu4(wa, wb);
+            part = __dp4a(d, d, part);
+        }
+        else
+        {
+            const uint32_t t = __vmaxu2(wa, wb) - __vminu2(wa, wb);
+            const uint32_t d0 = t & 0xffffu, d1 = t >> 16;
+            acc += (unsigned long long)(d0 * d0) + (unsigned long long)(d1 * d1);
+        }
+    }
+    acc += part;
+    return grp_sum64(acc, lpj);
+}
+
 template <typename PA, typename PB>
 __device__ __forceinline__ unsigned long long grp_sse(const PA* __restrict__ a, int sa, const PB* __restrict__ b, int sb, int w, int h, int sub, int lpj)
 {
@@ -437,7 +470,7 @@ __global__ void __launch_bounds__(256) k_pixelcmp(int op, const P* __restrict__ 
             break;
             case X265CU_SSE_PP:
             {
-                const unsigned long long v = grp_sse(A + a_off, sa, B + b_off, sb, w, h, sub, lpj);
+                const unsigned long long v = grp_sse_pp<P>(A + a_off, sa, B + b_off, sb, w, h, sub, lpj);
                 res = PixTraits<P>::depth == 8 ? (uint64_t)(uint32_t)v : v;     // sse_t width (common.h:144-148)
                 break;
             }

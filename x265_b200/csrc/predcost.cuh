@@ -8,8 +8,9 @@
 // the costs are MotionEstimate::bufSAD / bufSATD / bufChromaSATD (encoder/motion.h:87-95).  4:2:0, vectors clipped by the
 // caller (CUData::clipMv).  One job = one (PU, candidate); nothing is written but the cost.
 //
-// Two launches over the same list: PUs up to 16x16 take one WARP each (four per CTA, private shared tiles, warp barriers
-// only), larger PUs one 128-thread CTA each.  The prediction lives in shared memory from the source window to the cost.
+// Four launches over the same list: one-list jobs on the motion search's sub-pel code (k_pred_uni, small / large PUs), two-list
+// jobs staged through shared memory (k_pred_cost): PUs up to 16x16 take one WARP each (four per CTA, private tiles, warp
+// barriers only), larger PUs one 128-thread CTA each; the prediction lives in shared memory from the source window to the cost.
 #pragma once
 #include "common.cuh"
 #include "interp.cuh"
@@ -173,7 +174,7 @@ struct PredChroma { const void* fcb; const void* fcr; const void* const* rcb; co
 // TPJ = 32: a warp per job (PUs up to MAXS = 16); TPJ = 128: a CTA per job (MAXS = 64)
 template <typename P, int TPJ, int MAXS>
 __global__ void __launch_bounds__(128, TPJ == 32 ? 8 : 4) k_pred_cost(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride,
-                                                   PredChroma ch, const x265cu_pred_job* __restrict__ jobs, int n, int32_t* __restrict__ out)
+                                                   PredChroma ch, const x265cu_pred_job* __restrict__ jobs, int n, int32_t* __restrict__ out, int uniElsewhere)
 {
     constexpr int JPB = 128 / TPJ;
     constexpr int WIN = (MAXS + 7) * (MAXS + 8), MID = (MAXS + 7) * MAXS, PRD = MAXS * MAXS;
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(128, TPJ == 32 ? 8 : 4) k_pred_cost(const P* _
         const int w = jb.pw, h = jb.ph;
         const bool small = w <= 16 && h <= 16;
         if (small != (MAXS == 16)) continue;                     // the sibling launch owns this job
+        if (uniElsewhere && (jb.ref0 < 0 || jb.ref1 < 0)) continue;   // one-list jobs: k_pred_uni (the motion search's sub-pel code)
         const P* r0 = jb.ref0 >= 0 ? refs[jb.ref0] + jb.offset : nullptr;
         const P* r1 = jb.ref1 >= 0 ? refs[jb.ref1] + jb.offset : nullptr;
         pc_plane<P, TPJ, MAXS, 8>(r0, r1, rstride, jb, w, h, s_p0, s_p1, s_win, s_mid, t);
@@ -218,16 +220,78 @@ __global__ void __launch_bounds__(128, TPJ == 32 ? 8 : 4) k_pred_cost(const P* _
     }
 }
 
+// One-list jobs (AMVP candidates, uni-directional merge candidates) are exactly what MotionEstimate::subpelCompare computes for
+// one candidate (motion.cpp:1571-1664: the same copy / hpp / vpp / hvpp prediction, SAD or SATD, + the chroma-SATD term), so
+// they run on the motion search's own sub-pel code (me.cuh: me_subpel_batch, me_chroma_batch -- lane-per-row-segment DP4A
+// interpolation straight from the planes) instead of the staged generic path above: a warp per job, small-PU and large-PU
+// instantiations as in the search.  Same arithmetic, ~5x fewer instructions per job.
+template <typename P, int CLS>
+__global__ void __launch_bounds__(256, CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS) k_pred_uni(const P* __restrict__ fenc, int fstride, const P* const* __restrict__ refs, int rstride,
+                                                                                        MeChromaArgs ch, int haveChroma, const x265cu_pred_job* __restrict__ jobs, int n,
+                                                                                        int32_t* __restrict__ out, int* __restrict__ counter)
+{
+    extern __shared__ unsigned char me_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    MeShared* sm = (MeShared*)me_smem + warp;
+    for (;;)
+    {
+        int jid = 0;
+        if (lane == 0) jid = atomicAdd(counter, 1);
+        jid = __shfl_sync(0xffffffffu, jid, 0);
+        if (jid >= n) break;
+        const x265cu_pred_job pj = jobs[jid];
+        if (pj.ref0 >= 0 && pj.ref1 >= 0) continue;                // two lists: k_pred_cost
+        const bool l0 = pj.ref0 >= 0;
+        x265cu_me_job j;
+        j.offset = pj.offset; j.ref = (int16_t)(l0 ? pj.ref0 : pj.ref1); j.pw = (int8_t)pj.pw; j.ph = (int8_t)pj.ph;
+        j.mvmin[0] = j.mvmin[1] = j.mvmax[0] = j.mvmax[1] = 0; j.qmvp[0] = j.qmvp[1] = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) j.mvc[k] = 0;
+        j.numCand = 0; j.method = 3; j.merange = 0;
+        j.subme = (int8_t)((pj.flags & X265CU_PRED_CHROMA) ? 3 : 2);
+        MeCtx<P> c;
+        me_make_ctx<P>(c, j, fenc, fstride, refs, rstride, 0, nullptr, lane, sm);
+        if (me_subpel_class(c) != CLS) continue;                   // the sibling launch owns this job
+        const int qx = l0 ? pj.mv0[0] : pj.mv1[0], qy = l0 ? pj.mv0[1] : pj.mv1[1];
+        const bool satd = pj.cost == X265CU_PRED_SATD;
+        int cost = me_subpel_batch<P, CLS>(c, 1, qx, qy, satd);
+        if (satd && haveChroma && (pj.flags & X265CU_PRED_CHROMA))
+        {
+            MeChromaCtx<P> cc;
+            me_set_chroma<P>(cc, c, j, ch, fstride);
+            if (cc.on) cost += me_chroma_batch<P, CLS>(c, cc, 1, qx, qy, 1u);
+        }
+        if (lane == 0) out[jid] = cost;
+        __syncwarp();
+    }
+}
+
 template <typename P>
 static int launch_pred_cost_t(x265cu_ctx* ctx, const void* fenc, int fstride, const void* const* refs, int rstride, const PredChroma& ch,
                               const x265cu_pred_job* jobs, int n, int32_t* out)
 {
+    // one-list jobs
+    {
+        CU_CHECK(cudaMemsetAsync(ctx->d_counter + 12, 0, 2 * sizeof(int), ctx->stream));
+        MeChromaArgs a; a.fencCb = ch.fcb; a.fencCr = ch.fcr; a.refCb = ch.rcb; a.refCr = ch.rcr; a.cstride = ch.cstride;
+        const int threads = 256, warps = threads / 32;
+        const size_t smem = sizeof(MeShared) * warps;
+        const int need = (n + warps - 1) / warps;
+        int b0 = ctx->sm_count * ME_MIN_BLOCKS, b1 = ctx->sm_count * ME_BIG_BLOCKS;
+        if (b0 > need) b0 = need;
+        if (b1 > need) b1 = need;
+        k_pred_uni<P, 0><<<b0, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, a, ch.fcb != NULL, jobs, n, out, ctx->d_counter + 12);
+        CU_LAUNCH_CHECK(ctx);
+        k_pred_uni<P, 1><<<b1, threads, smem, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, a, ch.fcb != NULL, jobs, n, out, ctx->d_counter + 13);
+        CU_LAUNCH_CHECK(ctx);
+    }
+    // two-list jobs
     const int maxb = ctx->sm_count * 16;
     int b1 = (n + 3) / 4; if (b1 > maxb) b1 = maxb;
     int b2 = n < maxb ? n : maxb;
-    k_pred_cost<P, 32, 16><<<b1, 128, 0, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, ch, jobs, n, out);
+    k_pred_cost<P, 32, 16><<<b1, 128, 0, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, ch, jobs, n, out, 1);
     CU_LAUNCH_CHECK(ctx);
-    k_pred_cost<P, 128, 64><<<b2, 128, 0, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, ch, jobs, n, out);
+    k_pred_cost<P, 128, 64><<<b2, 128, 0, ctx->stream>>>((const P*)fenc, fstride, (const P* const*)refs, rstride, ch, jobs, n, out, 1);
     CU_LAUNCH_CHECK(ctx);
     return 0;
 }
