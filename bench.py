@@ -215,7 +215,7 @@ def cpu_reference(max_rows, threads, kind_pref="reference", steps=1, warmup=0, w
     scope = "whole frame" if rows == total_rows else "CTU rows [0, %d) of %d (full-frame geometry)" % (rows, total_rows)
     return {"ctus_per_s": ctus * steps / dt, "seconds": dt, "ctus": ctus, "kind": kind, "threads": threads, "rows": rows, "whole": rows == total_rows,
             "sample": "%s of the %dx%d workload, %d refs, all PUs, %d step(s)" % (scope, c["W"], c["H"], c["refs"], steps),
-            "checks": chk, "scope": scope, "wl": wl}
+            "checks": chk, "scope": scope, "wl": wl, "jobs": res["jobs"][:nj], "me_out": res["me_out"][:nj]}
 
 
 def run_reference_arm(args, rank, world):
@@ -240,6 +240,17 @@ def run_reference_arm(args, rank, world):
                              "warmup_note": "one 1-row probe step is the warm-up (the CPU arm has no caches worth more)"},
             "e2e": {"value": r["ctus_per_s"], "unit": "CTUs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "checks": r["checks"], "checks_scope": r["scope"], "gpu_launches": 0}
+    if CFG["chroma"] and not args.no_pred:
+        # the prediction costs around the motion search (Search::selectMVP / mergeEstimation / bidir) of the rows just analysed, on
+        # the reference's own Predict / MotionEstimate classes: the same job list the GPU arm's `pred_cost` leg evaluates
+        try:
+            pj = pred_jobs_of(r["jobs"], r["me_out"], CFG["refs"], True)
+            pr = pred_cpu(r["wl"], pj, threads, 8.0)
+            if pr is not None:
+                line["pred_cost"] = {"jobs_per_s": pr["jobs_per_s"], "cores": pr["threads"], "kind": "reference", "sample": "first %d of %d jobs (4 per motion-search job of %s)" % (pr["jobs"], len(pj), r["scope"]),
+                                     "checks": pred_checks(pr["cost"])}
+        except Exception as e:
+            line["pred_cost_error"] = repr(e)
     print(json.dumps(line), flush=True)
 
 

@@ -193,27 +193,14 @@ __global__ void __launch_bounds__(128) k_transform_reg(const int16_t* __restrict
     constexpr int shift1 = FWD ? LG - 1 + (DEPTH - 8) : 7;
     constexpr int shift2 = FWD ? LG + 6 : 12 - (DEPTH - 8);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    // 8x8: a thread's TU is 128 bytes, so per-thread 16-byte accesses touch 32 different lines per warp instruction
-    // (56 % of the HBM roofline, L1 wavefront bound).  The CTA moves its 128 TUs (16 KB) between global and shared memory
-    // with consecutive 16-byte pieces per lane instead; rows of 9 pieces keep the per-thread shared accesses conflict-free.
-    constexpr bool STAGE = N == 8;
-    __shared__ __align__(16) uint4 s_tu[STAGE ? 128 * 9 : 1];
-    const int t0 = blockIdx.x * blockDim.x, cnt = min((int)blockDim.x, n - t0);
-    if (STAGE)
-    {
-        const uint4* gs = (const uint4*)(src + (size_t)t0 * NN);
-        for (int i = threadIdx.x; i < cnt * 8; i += blockDim.x) s_tu[(i >> 3) * 9 + (i & 7)] = __ldg(gs + i);
-        __syncthreads();
-    }
-    else if (t >= n) return;
+    if (t >= n) return;
     int a[N][N];
-    if (!STAGE || t < n)
     {
-        const uint4* sp = STAGE ? (const uint4*)(s_tu + threadIdx.x * 9) : (const uint4*)(src + (size_t)t * NN);
+        const uint4* sp = (const uint4*)(src + (size_t)t * NN);
 #pragma unroll
         for (int i = 0; i < NN / 8; i++)
         {
-            const uint4 v = STAGE ? sp[i] : __ldg(sp + i);
+            const uint4 v = __ldg(sp + i);
             const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -269,27 +256,18 @@ __global__ void __launch_bounds__(128) k_transform_reg(const int16_t* __restrict
             for (int i = 0; i < N; i++) o[c][i] = clip16((y[i] + (1 << (shift2 - 1))) >> shift2);
         }
     }
-    uint4* dp = STAGE ? (uint4*)(s_tu + threadIdx.x * 9) : (uint4*)(dst + (size_t)t * NN);
-    if (!STAGE || t < n)
-    {
+    uint4* dp = (uint4*)(dst + (size_t)t * NN);
 #pragma unroll
-        for (int i = 0; i < NN / 8; i++)
+    for (int i = 0; i < NN / 8; i++)
+    {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
         {
-            uint32_t w[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                const int e = i * 8 + k * 2;
-                w[k] = ((uint32_t)o[e / N][e % N] & 0xffffu) | ((uint32_t)o[(e + 1) / N][(e + 1) % N] << 16);
-            }
-            dp[i] = make_uint4(w[0], w[1], w[2], w[3]);
+            const int e = i * 8 + k * 2;
+            w[k] = ((uint32_t)o[e / N][e % N] & 0xffffu) | ((uint32_t)o[(e + 1) / N][(e + 1) % N] << 16);
         }
-    }
-    if (STAGE)
-    {
-        __syncthreads();
-        uint4* gd = (uint4*)(dst + (size_t)t0 * NN);
-        for (int i = threadIdx.x; i < cnt * 8; i += blockDim.x) gd[i] = s_tu[(i >> 3) * 9 + (i & 7)];
+        dp[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
