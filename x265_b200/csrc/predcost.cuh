@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(128, TPJ == 32 ? 8 : 4) k_pred_cost(const P* _
         const bool small = w <= 16 && h <= 16;
         if (small != (MAXS == 16)) continue;                     // the sibling launch owns this job
         if (uniElsewhere && (jb.ref0 < 0 || jb.ref1 < 0)) continue;   // one-list jobs: k_pred_uni (the motion search's sub-pel code)
+        if (uniElsewhere && small && !((w & (w - 1)) | (h & (h - 1)))) continue;   // ... and so are the two-list jobs of small pow2 PUs
         const P* r0 = jb.ref0 >= 0 ? refs[jb.ref0] + jb.offset : nullptr;
         const P* r1 = jb.ref1 >= 0 ? refs[jb.ref1] + jb.offset : nullptr;
         pc_plane<P, TPJ, MAXS, 8>(r0, r1, rstride, jb, w, h, s_p0, s_p1, s_win, s_mid, t);
@@ -220,6 +221,191 @@ __global__ void __launch_bounds__(128, TPJ == 32 ? 8 : 4) k_pred_cost(const P* _
     }
 }
 
+// ---- two-list jobs of small PUs (pow2, up to 16x16: 94 % of a frame's PUs) on the search's lane-per-row-segment code ------------
+// The lane's row segment (NPX pixels of one row) of a prediction of the PU at the quarter-pel vector (qx, qy) on plane `ref`:
+// SHORT = the 14-bit intermediate of predInterLumaShort (p2s / hps / vps / hps + vss), else the pixel prediction of
+// predInterLumaPixel.  Same helpers and lane mapping as me_subpel_small_t (lane = row + h * segment; lanes >= h * segments idle);
+// the hv case stages its h + 7 horizontally filtered rows in the warp's scratch.  All 32 lanes call.
+template <typename P, int NPX, bool SHORT>
+__device__ __forceinline__ void pb_seg(const MeCtx<P>& c, const P* __restrict__ ref, int qx, int qy, int (&pr)[NPX])
+{
+    constexpr int DEPTH = PixTraits<P>::depth;
+    const int lane = c.lane;
+    const int lgsegs = NPX == 8 ? c.lgw - 3 : 0, lgh = 31 - __clz(c.h);
+    const int lpc = 1 << (lgh + lgsegs);
+    const int tasksPer = (c.h + 7) << lgsegs;
+    int16_t* mid = c.sm->mid;
+    const int xf = qx & 3, yf = qy & 3;
+    __syncwarp();
+    if (xf && yf)
+        for (int t = lane; t < tasksPer; t += 32)
+        {
+            const int mrow = t >> lgsegs, seg = t & ((1 << lgsegs) - 1);
+            const P* s = ref + (qx >> 2) + (ptrdiff_t)((qy >> 2) - 3 + mrow) * c.rstride + seg * 8;
+            int sum[NPX];
+            me_hrow<P, NPX>(s, xf, sum);
+            uint32_t pk[NPX / 2];
+#pragma unroll
+            for (int i = 0; i < NPX / 2; i++)
+                pk[i] = ((uint32_t)interp_finish<DEPTH>(sum[2 * i], 1) & 0xffffu) | ((uint32_t)interp_finish<DEPTH>(sum[2 * i + 1], 1) << 16);
+            int16_t* d = mid + mrow * c.w + seg * 8;
+            if (NPX == 8) *(uint4*)d = make_uint4(pk[0], pk[1], pk[NPX / 2 - 2], pk[NPX / 2 - 1]);
+            else          *(uint2*)d = make_uint2(pk[0], pk[NPX / 2 - 1]);
+        }
+    __syncwarp();
+    const int sub = lane & (lpc - 1), row = sub & (c.h - 1), seg = sub >> lgh;
+    if (lane < lpc)
+    {
+        const P* r = ref + (qx >> 2) + (ptrdiff_t)((qy >> 2) + row) * c.rstride + seg * 8;
+        if (!(xf | yf))
+        {
+#pragma unroll
+            for (int x = 0; x < NPX; x++) { const int p = (int)__ldg(r + x); pr[x] = SHORT ? (p << (14 - DEPTH)) - 8192 : p; }
+        }
+        else if (!yf)
+        {
+            me_hrow<P, NPX>(r, xf, pr);
+#pragma unroll
+            for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], SHORT ? 1 : 0);
+        }
+        else if (!xf)
+        {
+            me_vcol<P, NPX>(r - 3 * (ptrdiff_t)c.rstride, c.rstride, yf, pr);
+#pragma unroll
+            for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], SHORT ? 1 : 0);
+        }
+        else
+        {
+            me_vmid<NPX>(mid + row * c.w + seg * 8, c.w, yf, pr);
+#pragma unroll
+            for (int x = 0; x < NPX; x++) pr[x] = interp_finish<DEPTH>(pr[x], SHORT ? 3 : 2);
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int x = 0; x < NPX; x++) pr[x] = 0;
+    }
+}
+
+// luma cost of a bi-prediction: addAvg of the two 14-bit predictions (Yuv::addAvg) or, with avgpp, pixelavg_pp of the two
+// pixel predictions; SAD or SATD against the source rows as in me_subpel_small_t's stage 3.  Result in lane 0.
+template <typename P, int NPX>
+__device__ __forceinline__ int pb_bi_luma(const MeCtx<P>& c, const P* __restrict__ ref0, const P* __restrict__ ref1, int qx0, int qy0, int qx1, int qy1,
+                                          bool avgpp, bool satd)
+{
+    constexpr int DEPTH = PixTraits<P>::depth, maxv = PixTraits<P>::maxv;
+    const int lane = c.lane;
+    const int lgsegs = NPX == 8 ? c.lgw - 3 : 0, lgh = 31 - __clz(c.h);
+    const int lpc = 1 << (lgh + lgsegs);
+    int a[NPX], b[NPX], d[NPX];
+    if (avgpp) { pb_seg<P, NPX, false>(c, ref0, qx0, qy0, a); pb_seg<P, NPX, false>(c, ref1, qx1, qy1, b); }
+    else       { pb_seg<P, NPX, true>(c, ref0, qx0, qy0, a);  pb_seg<P, NPX, true>(c, ref1, qx1, qy1, b); }
+    const int sub = lane & (lpc - 1), row = sub & (c.h - 1), seg = sub >> lgh;
+    if (lane < lpc)
+    {
+        constexpr int shift = 15 - DEPTH, offset = (1 << (shift - 1)) + 2 * 8192;
+        int fv[NPX];
+        me_load_fenc<P, NPX>(c, c.fenc + (ptrdiff_t)row * c.fstride + seg * 8, fv);
+#pragma unroll
+        for (int x = 0; x < NPX; x++)
+        {
+            const int pr = avgpp ? (a[x] + b[x] + 1) >> 1 : clip3i(0, maxv, (a[x] + b[x] + offset) >> shift);
+            d[x] = fv[x] - pr;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int x = 0; x < NPX; x++) d[x] = 0;
+    }
+    int part = 0;
+    if (!satd)
+    {
+#pragma unroll
+        for (int x = 0; x < NPX; x++) part += abs(d[x]);
+        for (int o = 1; o < lpc; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    }
+    else
+    {
+#pragma unroll
+        for (int x = 0; x < NPX; x += 4) had4(d[x], d[x + 1], d[x + 2], d[x + 3]);
+#pragma unroll
+        for (int st = 1; st <= 2; st <<= 1)
+        {
+            const bool up = (lane & st) != 0;
+#pragma unroll
+            for (int x = 0; x < NPX; x++)
+            {
+                const int o = __shfl_xor_sync(0xffffffffu, d[x], st);
+                d[x] = up ? o - d[x] : o + d[x];
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < NPX; x++) part += abs(d[x]);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part = (lane & 3) ? 0 : (part >> 1);                        // one 8x4 (4x4) tile per 4 lanes, halved per tile
+        for (int o = 4; o < lpc; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    }
+    return __shfl_sync(0xffffffffu, part, 0);
+}
+
+// Cb + Cr SATD of a bi-prediction's chroma (predInterChromaShort x 2 + addAvg), small PUs: me_chroma_batch_cols' lane mapping
+// (four lanes per 4x4 tile, one column each) for ONE candidate with two lists.  The single separable path (hps with rowExt, then
+// vss) reproduces p2s / hps / vps exactly for zero phases through the identity taps {0, 64, 0, 0}: mid = 64 p - 8192 (8-bit) or
+// 16 p - 8192 (10-bit) is exact and sum(c) = 64, so (sum(c mid)) >> 6 equals the direct forms.
+template <typename P>
+__device__ __forceinline__ int pb_bi_chroma(const MeCtx<P>& c, const MeChromaCtx<P>& c0, const MeChromaCtx<P>& c1, int qx0, int qy0, int qx1, int qy1)
+{
+    constexpr int DEPTH = PixTraits<P>::depth, maxv = PixTraits<P>::maxv;
+    const int lgtpr = c.lgw - 3;
+    const int lgnt = lgtpr + (31 - __clz(c.h)) - 3;
+    const int lgipc = lgnt + 3, total = 1 << lgipc;                // lane-items of the candidate: 8 / 16 / 32
+    const int lggs = 2 + lgtpr;
+    const int it = min(c.lane, total - 1);
+    const int col = it & 3, t = it >> 2;
+    const bool cr = (t >> lgnt) != 0;
+    const int tt = t & ((1 << lgnt) - 1);
+    const int ty = tt >> lgtpr, tx = tt & ((1 << lgtpr) - 1);
+    const ptrdiff_t o = (ptrdiff_t)(ty * 4) * c0.cstride + tx * 4 + col;
+    const P* f = (cr ? c0.fcr : c0.fcb) + o;
+    int sh[2][4];
+#pragma unroll
+    for (int l = 0; l < 2; l++)
+    {
+        const MeChromaCtx<P>& cc = l ? c1 : c0;
+        const int qx = l ? qx1 : qx0, qy = l ? qy1 : qy0;
+        const P* r = (cr ? cc.rcr : cc.rcb) + o + (qx >> 3) + (ptrdiff_t)(qy >> 3) * cc.cstride - 1 - cc.cstride;
+        const uint32_t th = __ldg(&d_chromaTaps4[qx & 7]), tv = __ldg(&d_chromaTaps4[qy & 7]);
+        const int v0 = (int)(int8_t)tv, v1 = (int)(int8_t)(tv >> 8), v2 = (int)(int8_t)(tv >> 16), v3 = (int)tv >> 24;
+        int mid[7];
+#pragma unroll
+        for (int q = 0; q < 7; q++) mid[q] = interp_finish<DEPTH>(me_chroma_hsum<P>(r + q * cc.cstride, th), 1);
+#pragma unroll
+        for (int y = 0; y < 4; y++) sh[l][y] = interp_finish<DEPTH>(v0 * mid[y] + v1 * mid[y + 1] + v2 * mid[y + 2] + v3 * mid[y + 3], 3);
+    }
+    constexpr int shift = 15 - DEPTH, offset = (1 << (shift - 1)) + 2 * 8192;
+    int d[4];
+#pragma unroll
+    for (int y = 0; y < 4; y++) d[y] = (int)__ldg(f + y * c0.cstride) - clip3i(0, maxv, (sh[0][y] + sh[1][y] + offset) >> shift);
+    had4(d[0], d[1], d[2], d[3]);
+    const int s1 = (c.lane & 1) ? -1 : 1, s2 = (c.lane & 2) ? -1 : 1;
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+    {
+        d[y] = __shfl_xor_sync(0xffffffffu, d[y], 1) + s1 * d[y];
+        d[y] = __shfl_xor_sync(0xffffffffu, d[y], 2) + s2 * d[y];
+    }
+    int v = abs(d[0]) + abs(d[1]) + abs(d[2]) + abs(d[3]);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (lggs == 3) v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v >>= 1;
+    for (int s = lggs; s < lgipc; s++) v += __shfl_xor_sync(0xffffffffu, v, 1 << s);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
 // One-list jobs (AMVP candidates, uni-directional merge candidates) are exactly what MotionEstimate::subpelCompare computes for
 // one candidate (motion.cpp:1571-1664: the same copy / hpp / vpp / hvpp prediction, SAD or SATD, + the chroma-SATD term), so
 // they run on the motion search's own sub-pel code (me.cuh: me_subpel_batch, me_chroma_batch -- lane-per-row-segment DP4A
@@ -240,7 +426,8 @@ __global__ void __launch_bounds__(256, CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS)
         jid = __shfl_sync(0xffffffffu, jid, 0);
         if (jid >= n) break;
         const x265cu_pred_job pj = jobs[jid];
-        if (pj.ref0 >= 0 && pj.ref1 >= 0) continue;                // two lists: k_pred_cost
+        const bool bi = pj.ref0 >= 0 && pj.ref1 >= 0;
+        if (bi && CLS != 0) continue;                              // two lists, large PUs: k_pred_cost
         const bool l0 = pj.ref0 >= 0;
         x265cu_me_job j;
         j.offset = pj.offset; j.ref = (int16_t)(l0 ? pj.ref0 : pj.ref1); j.pw = (int8_t)pj.pw; j.ph = (int8_t)pj.ph;
@@ -251,9 +438,27 @@ __global__ void __launch_bounds__(256, CLS == 1 ? ME_BIG_BLOCKS : ME_MIN_BLOCKS)
         j.subme = (int8_t)((pj.flags & X265CU_PRED_CHROMA) ? 3 : 2);
         MeCtx<P> c;
         me_make_ctx<P>(c, j, fenc, fstride, refs, rstride, 0, nullptr, lane, sm);
-        if (me_subpel_class(c) != CLS) continue;                   // the sibling launch owns this job
-        const int qx = l0 ? pj.mv0[0] : pj.mv1[0], qy = l0 ? pj.mv0[1] : pj.mv1[1];
+        if (me_subpel_class(c) != CLS) continue;                   // the sibling launch owns this job (two lists: k_pred_cost)
         const bool satd = pj.cost == X265CU_PRED_SATD;
+        if (bi)
+        {   // CLS 0 only: both lists on the lane-per-row-segment code
+            const P* ref1 = refs[pj.ref1] + pj.offset;
+            const bool avgpp = (pj.flags & X265CU_PRED_AVG_PP) != 0;
+            int cost = c.w >= 8 ? pb_bi_luma<P, 8>(c, c.ref[0], ref1, pj.mv0[0], pj.mv0[1], pj.mv1[0], pj.mv1[1], avgpp, satd)
+                                : pb_bi_luma<P, 4>(c, c.ref[0], ref1, pj.mv0[0], pj.mv0[1], pj.mv1[0], pj.mv1[1], avgpp, satd);
+            if (satd && !avgpp && haveChroma && (pj.flags & X265CU_PRED_CHROMA))
+            {
+                MeChromaCtx<P> c0, c1;
+                me_set_chroma<P>(c0, c, j, ch, fstride);
+                j.ref = (int16_t)pj.ref1;
+                me_set_chroma<P>(c1, c, j, ch, fstride);
+                if (c0.on) cost += pb_bi_chroma<P>(c, c0, c1, pj.mv0[0], pj.mv0[1], pj.mv1[0], pj.mv1[1]);
+            }
+            if (lane == 0) out[jid] = cost;
+            __syncwarp();
+            continue;
+        }
+        const int qx = l0 ? pj.mv0[0] : pj.mv1[0], qy = l0 ? pj.mv0[1] : pj.mv1[1];
         int cost = me_subpel_batch<P, CLS>(c, 1, qx, qy, satd);
         if (satd && haveChroma && (pj.flags & X265CU_PRED_CHROMA))
         {
