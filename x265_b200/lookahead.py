@@ -90,7 +90,15 @@ class Lookahead:
                                 has_planes=False, has_intra=False, invq=None))
         self.tab = lib.to_device(lib.mvcost_table(LOOKAHEAD_LAMBDA[depth], MVRANGE))
         self._full = None
-        lib.sync()
+        self._pool = {}                  # size -> free device buffers: the per-step result / motion-field buffers are recycled
+        lib.sync()                       # (a window's step made ~2000 cudaMalloc / cudaFree calls before: most of its host time)
+
+    def _take(self, nbytes):
+        free = self._pool.get(nbytes)
+        return free.pop() if free else self.cu.alloc(nbytes)
+
+    def _give(self, buf):
+        self._pool.setdefault(buf.nbytes, []).append(buf)
 
     # ---- Lowres::init: full-res luma (host) -> 4 half-pel planes with extended borders (device) ----
     def init_frame(self, i, img, sync=True):
@@ -164,7 +172,12 @@ class Lookahead:
         todo = [t for t in triples if (t[2] - t[0], t[1] - t[2]) not in self.fr[t[2]]["res"]]
         recs = []
         bufs = []
-        for (p0, p1, b) in todo:
+        # the batch's results land in three blocks (per-CU costs, row sums, frame totals): one D2H each in collect_batch()
+        nt = len(todo)
+        lcB = self._take(2 * self.ncu * nt) if nt else None
+        rsB = self._take(4 * self.h8 * nt) if nt else None
+        outB = self._take(32 * nt) if nt else None
+        for ti, (p0, p1, b) in enumerate(todo):
             f = self.fr[b]
             assert f["has_intra"] and self.fr[p0]["has_planes"] and self.fr[p1]["has_planes"], (p0, p1, b)
             d0, d1 = b - p0, p1 - b
@@ -177,12 +190,12 @@ class Lookahead:
             for lst, dist in ((0, d0), (1, d1)):
                 new = (lst, dist) not in f["mvs"]
                 if new:
-                    f["mvs"][(lst, dist)] = cu.alloc(8 * self.ncu); f["mvcosts"][(lst, dist)] = cu.alloc(4 * self.ncu)
+                    f["mvs"][(lst, dist)] = self._take(8 * self.ncu); f["mvcosts"][(lst, dist)] = self._take(4 * self.ncu)
                     cu.check(cu.L.x265cu_memset(cu.ctx, f["mvs"][(lst, dist)].ptr, 0, 8 * self.ncu))
                     cu.check(cu.L.x265cu_memset(cu.ctx, f["mvcosts"][(lst, dist)].ptr, 0, 4 * self.ncu))
                 j["doSearch%d" % lst] = int(new and (lst == 0 or p1 > b))
                 j["mvs"][lst] = f["mvs"][(lst, dist)].ptr; j["mvcosts"][lst] = f["mvcosts"][(lst, dist)].ptr
-            lc, rs, out = cu.alloc(2 * self.ncu), cu.alloc(4 * self.h8), cu.alloc(24)
+            lc = _PlaneView(lcB, ti * 2 * self.ncu, 2 * self.ncu); rs = _PlaneView(rsB, ti * 4 * self.h8, 4 * self.h8); out = _PlaneView(outB, ti * 32, 24)
             bufs.append((lc, rs, out))
             j["intraCost"] = f["intraCost"].ptr; j["invQscale"] = f["invq"].ptr if f["invq"] is not None else 0; j["lowresCosts"] = lc.ptr; j["rowSatds"] = rs.ptr; j["out"] = out.ptr
             # cooperative slices (slicetype.cpp:3143): one job per slice, each an independent wavefront over its CU rows
@@ -195,8 +208,11 @@ class Lookahead:
             else:
                 recs.append(j)
         jobs = np.array(recs, LA_JOB) if recs else np.zeros(1, LA_JOB)
-        d_j = cu.to_device(jobs) if todo else None
-        return dict(todo=todo, bufs=bufs, d_jobs=d_j, njobs=len(recs))
+        d_j = None
+        if todo:
+            d_j = self._take((jobs.nbytes + 65535) // 65536 * 65536)
+            d_j.upload(jobs)
+        return dict(todo=todo, bufs=bufs, d_jobs=d_j, njobs=len(recs), blocks=(lcB, rsB, outB))
 
     def launch_batch(self, prep):
         """ONE kernel launch for all prepared triples (asynchronous on the context's stream)."""
@@ -207,18 +223,24 @@ class Lookahead:
 
     def collect_batch(self, prep, full=True):
         """D2H of the launched triples' results: frame cost always; per-CU lowresCosts / rowSatds when `full`."""
-        for (p0, p1, b), (lc, rs, out) in zip(prep["todo"], prep["bufs"]):
-            o = out.download(np.int64)
+        lcB, rsB, outB = prep["blocks"]
+        nt = len(prep["todo"])
+        if nt:
+            outs = outB.download(np.int64, 4 * nt).reshape(nt, 4)
+            lcs = lcB.download(np.uint16, self.ncu * nt).reshape(nt, self.ncu) if full else None
+            rss = rsB.download(np.int32, self.h8 * nt).reshape(nt, self.h8) if full else None
+        for ti, (p0, p1, b) in enumerate(prep["todo"]):
+            o = outs[ti]
             score = int(o[0])
             if b != p1:
                 score = score * 100 // 130          # slicetype.cpp:3205-3206, bFrameBias = 0
             r = dict(score=score, costEstAq=int(o[1]), intraMbs=int(o[2]))
             if full:
-                r["lowresCosts"] = lc.download(np.uint16); r["rowSatds"] = rs.download(np.int32)
+                r["lowresCosts"] = lcs[ti].copy(); r["rowSatds"] = rss[ti].copy()
             self.fr[b]["res"][(b - p0, p1 - b)] = r
-            lc.free(); rs.free(); out.free()
-        if prep["d_jobs"] is not None:
-            prep["d_jobs"].free()
+        for blk in (lcB, rsB, outB, prep["d_jobs"]):
+            if blk is not None:
+                self._give(blk)
 
     def cost_batch(self, triples, full=True):
         """Frame costs of `triples` (one launch for those not estimated yet)."""
@@ -232,7 +254,7 @@ class Lookahead:
         for f in self.fr:
             for d in (f["mvs"], f["mvcosts"]):
                 for v in d.values():
-                    v.free()
+                    self._give(v)
                 d.clear()
             f["res"].clear()
 
@@ -246,6 +268,10 @@ class Lookahead:
         self.tab.free()
         if self._full is not None:
             self._full.free()
+        for free in self._pool.values():
+            for b in free:
+                b.free()
+        self._pool.clear()
 
 
 def window_triples(nframes, bframes):
