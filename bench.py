@@ -369,7 +369,7 @@ def pred_cost_leg(lib, an, wl, cpu_seconds, reps=3):
     ms = float(np.median(ts))
     got = d_o.download(np.int32)
     out = {"what": "AMVP candidate SADs (Search::selectMVP), merge-candidate and bi-prediction SATD + chroma SATD (mergeEstimation, predInterSearch bidir) on Predict::motionCompensation: 4 costs per motion-search job",
-           "jobs": int(len(pj)), "ms": ms, "jobs_per_s": len(pj) / (ms / 1000.0), "checks": pred_checks(got), "launches_per_call": 2}
+           "jobs": int(len(pj)), "ms": ms, "jobs_per_s": len(pj) / (ms / 1000.0), "checks": pred_checks(got), "launches_per_call": 4}
     if cpu_seconds > 0:
         r = pred_cpu(wl, pj, host_cores(), cpu_seconds)
         if r is not None:

@@ -74,6 +74,10 @@ void orc_frame_init_lowres(const pixel* src0, pixel* dst0, pixel* dsth, pixel* d
                            intptr_t src_stride, intptr_t dst_stride, int width, int height);
 void orc_extend_pic_border(pixel* pic, intptr_t stride, int width, int height, int marginX, int marginY);
 
+/* ---- SEA integral planes (framefilter.cpp:39-143) ---- */
+void orc_integral_inith(uint32_t* sum, const pixel* pix, intptr_t stride, int n);
+void orc_integral_initv(uint32_t* sum, intptr_t stride, int n);
+
 /* ---- interpolation (ipfilter.cpp:40-369); ntaps = 8 (luma) or 4 (chroma) ---- */
 void orc_p2s(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds, int w, int h);
 void orc_interp_hpp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int coeffIdx, int ntaps, int w, int h);

@@ -383,3 +383,21 @@ void orc_extend_pic_border(pixel* pic, intptr_t stride, int width, int height, i
         memcpy(bot + y * stride, bot, (size_t)stride * sizeof(pixel));
     }
 }
+
+/* ---- SEA integral planes (encoder/framefilter.cpp:39-143): integral_init{4,8,12,16,24,32}{h,v}, width n as a run-time argument.
+ * inith: running n-wide row sums added to the row above (sum[x - stride]); initv: sum[x] = sum[x + n * stride] - sum[x]. ---- */
+void orc_integral_inith(uint32_t* sum, const pixel* pix, intptr_t stride, int n)
+{
+    int32_t v = 0;
+    for (int k = 0; k < n; k++) v += pix[k];
+    for (int16_t x = 0; x < stride - n; x++)
+    {
+        sum[x] = v + sum[x - stride];
+        v += pix[x + n] - pix[x];
+    }
+}
+
+void orc_integral_initv(uint32_t* sum, intptr_t stride, int n)
+{
+    for (int x = 0; x < stride; x++) sum[x] = sum[x + n * stride] - sum[x];
+}

@@ -7,7 +7,8 @@ timeout 400 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c3.json 2> g
 timeout 400 python bench.py --config c4 --steps 3 --warmup 2 --cpu-seconds 15 --no-primitives > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "bench c4 rc=$?"
 timeout 300 python bench.py --config c2 --steps 3 --warmup 2 --cpu-seconds 10 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench c2 rc=$?"
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-chroma --no-primitives > gpurun_out/bench_c3_luma.json 2> gpurun_out/bench_c3_luma.err
-for f in c3 c3_luma c4 c2; do python - "$f" <<'P'
+timeout 400 python bench.py --config c5 --steps 2 --warmup 1 --no-cpu --no-primitives --no-pred > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "bench c5 rc=$?"
+for f in c3 c3_luma c4 c2 c5; do python - "$f" <<'P'
 import json, sys
 try:
     d = json.load(open("gpurun_out/bench_%s.json" % sys.argv[1])); print(sys.argv[1], round(d["value"]), "e2e", round(d["e2e"]["value"]), d.get("stages_ms"), d.get("checks_equal"), d.get("cpu_baseline", {}).get("value"), len(d.get("primitives", [])), d.get("primitives_error"))

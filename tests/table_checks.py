@@ -341,6 +341,25 @@ def check_transforms(get, O, depth, kind):
         assert np.array_equal(d1, d2), (it, np.nonzero(d1 != d2)[0][:5])
 
 
+def check_integral(get, O, depth):
+    """SEA integral-plane primitives (framefilter.cpp:39-143): integral_inith[k] / integral_initv[k], k = IntegralSize
+    (4, 8, 12, 16, 24, 32); uint32 wrap-around sums, rows as FrameFilter::computeMEIntegral hands them over."""
+    rng = np.random.default_rng(33 + depth)
+    dt = pixel_dtype(depth)
+    for k, n in enumerate((4, 8, 12, 16, 24, 32)):
+        for stride in (56, 64, 200):
+            pix = rng.integers(0, 1 << depth, stride + 64).astype(dt)
+            base = rng.integers(0, 1 << 32, stride * (n + 3), dtype=np.uint64).astype(np.uint32)
+            a, b = base.copy(), base.copy()
+            get("integral_inith", None, [P, P, IP], k)(ptr(a, stride), ptr(pix), IP(stride))
+            O.orc_integral_inith(ptr(b, stride), ptr(pix), IP(stride), n)
+            assert np.array_equal(a, b), ("inith", n, stride)
+            a, b = base.copy(), base.copy()
+            get("integral_initv", None, [P, IP], k)(ptr(a, stride), IP(stride))
+            O.orc_integral_initv(ptr(b, stride), IP(stride), n)
+            assert np.array_equal(a, b), ("initv", n, stride)
+
+
 def check_intra(get, O, depth, kind):
     rng = np.random.default_rng(6)
     dt = pixel_dtype(depth)

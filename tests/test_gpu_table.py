@@ -43,3 +43,8 @@ def test_native_library_loaded(cu):
     assert cu.path.endswith("x265_b200/libx265cu.so")
     with open("/proc/self/maps") as f:
         assert "libx265cu.so" in f.read()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_integral(cu, depth):
+    table_checks.check_integral(cuda_getter(cu, depth), load_oracle(depth), depth)

@@ -53,6 +53,13 @@ def test_ads(depth):
     table_checks.check_ads(ref_getter(R), O, depth)
 
 
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_integral(depth):
+    # SEA integral planes: not in the four TestBench harness classes used above; checked directly (framefilter.cpp:39-143)
+    R, O = libs(depth)
+    table_checks.check_integral(ref_getter(R), O, depth)
+
+
 def _me_job(O, R, depth, rng, w, h, method, subme, lowres, smooth, merange, qp=30):
     """Run the same motionEstimate job through the real MotionEstimate and the oracle."""
     from me_helpers import run_both

@@ -253,6 +253,52 @@ static void propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t*
     memcpy(dst, s.h<int>(od), (size_t)len * 4);
 }
 
+// ---------- SEA integral planes (framefilter.cpp:39-143: integral_init{4,8,12,16,24,32}{h,v}) ----------
+// inith: sum[x] = (pix[x] + ... + pix[x + N - 1]) + sum[x - stride] for x < stride - N (uint32 wrap-around arithmetic);
+// initv: sum[x] = sum[x + N * stride] - sum[x] for x < stride.  One row per call, as FrameFilter::computeMEIntegral drives them.
+template <typename P>
+__global__ void k_integral_h(uint32_t* __restrict__ out, const uint32_t* __restrict__ prev, const P* __restrict__ pix, int N, int n)
+{
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x)
+    {
+        uint32_t v = 0;
+        for (int k = 0; k < N; k++) v += pix[x + k];
+        out[x] = v + prev[x];
+    }
+}
+__global__ void k_integral_v(uint32_t* __restrict__ out, const uint32_t* __restrict__ top, const uint32_t* __restrict__ bottom, int n)
+{
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) out[x] = bottom[x] - top[x];
+}
+template <typename P, int N>
+static void integral_inith(uint32_t* sum, P* pix, intptr_t stride)
+{
+    const int n = (int)stride - N;
+    if (n <= 0) return;
+    Stage s; s.ctx = tctx();
+    size_t op = s.put(pix, stride, stride, 1, sizeof(P)), oq = s.put(sum - stride, n, n, 1, 4), od = s.reserve((size_t)n * 4);
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("integral_inith"); return; }
+    k_integral_h<P><<<(n + 255) / 256, 256, 0, s.ctx->stream>>>(s.d<uint32_t>(od), s.d<uint32_t>(oq), s.d<P>(op), N, n);
+    x265cu_count_launch(s.ctx);
+    if (s.download(od, (size_t)n * 4)) { fail("integral_inith"); return; }
+    memcpy(sum, s.h<uint32_t>(od), (size_t)n * 4);
+}
+template <int N>
+static void integral_initv(uint32_t* sum, intptr_t stride)
+{
+    const int n = (int)stride;
+    if (n <= 0) return;
+    Stage s; s.ctx = tctx();
+    size_t ot = s.put(sum, n, n, 1, 4), ob = s.put(sum + (intptr_t)N * stride, n, n, 1, 4), od = s.reserve((size_t)n * 4);
+    if (!s.ok) { fail("stage overflow"); return; }
+    if (s.upload()) { fail("integral_initv"); return; }
+    k_integral_v<<<(n + 255) / 256, 256, 0, s.ctx->stream>>>(s.d<uint32_t>(od), s.d<uint32_t>(ot), s.d<uint32_t>(ob), n);
+    x265cu_count_launch(s.ctx);
+    if (s.download(od, (size_t)n * 4)) { fail("integral_initv"); return; }
+    memcpy(sum, s.h<uint32_t>(od), (size_t)n * 4);
+}
+
 // copy_cnt / count_nonzero via the compare kernel's machinery would be overkill: tiny dedicated kernel
 __global__ void k_count_nonzero(const int16_t* __restrict__ q, int n, uint32_t* __restrict__ out)
 {
@@ -672,6 +718,19 @@ static void* lookup(const char* name, int i, int j, int k)
     if (!strcmp(name, "dequant_scaling")) return (void*)dequant_scaling;
     if (!strcmp(name, "denoiseDct")) return (void*)denoise;
     if (!strcmp(name, "propagateCost")) return (void*)propagate_cost;
+    // SEA integral planes; i = IntegralSize (primitives.h:122-131: 4, 8, 12, 16, 24, 32)
+    if (!strcmp(name, "integral_inith"))
+    {
+        static void* const t[6] = { (void*)integral_inith<P, 4>, (void*)integral_inith<P, 8>, (void*)integral_inith<P, 12>, (void*)integral_inith<P, 16>,
+                                    (void*)integral_inith<P, 24>, (void*)integral_inith<P, 32> };
+        return i >= 0 && i < 6 ? t[i] : NULL;
+    }
+    if (!strcmp(name, "integral_initv"))
+    {
+        static void* const t[6] = { (void*)integral_initv<4>, (void*)integral_initv<8>, (void*)integral_initv<12>, (void*)integral_initv<16>,
+                                    (void*)integral_initv<24>, (void*)integral_initv<32> };
+        return i >= 0 && i < 6 ? t[i] : NULL;
+    }
     // in-loop filters (loopfilter.cpp:184-200, sao.cpp:1927-1935); i = the array index of the two-entry fields
     if (!strcmp(name, "sign")) return (void*)lf_sign<P>;
     if (!strcmp(name, "saoCuOrgE0")) return (void*)lf_sao_e0<P>;

@@ -38,6 +38,29 @@ __device__ __forceinline__ void imma(int (&d)[4], const uint32_t* a, const uint3
                          : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(b[0]));
     }
 }
+// the data as the A operand (u8 low bytes or s8 high bytes) against the s8 constant matrix as B
+template <int K32>
+__device__ __forceinline__ void imma_da(int (&d)[4], const uint32_t* a, const uint32_t* b, bool a_unsigned)
+{
+    if (K32)
+    {
+        if (a_unsigned)
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+        else
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    else
+    {
+        if (a_unsigned)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                         : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(b[0]));
+        else
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                         : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(b[0]));
+    }
+}
 
 // four int16 values -> (4 high bytes, 4 low bytes)
 __device__ __forceinline__ void split4(int v0, int v1, int v2, int v3, uint32_t& hi, uint32_t& lo)
@@ -50,14 +73,8 @@ __device__ __forceinline__ void split4(int v0, int v1, int v2, int v3, uint32_t&
 
 // N = 16 or 32.  FWD: src strided (stride / tu_pitch in elements), dst contiguous N*N per TU; INV: the reverse.
 template <int DEPTH, int N, bool FWD>
-__global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int stride, int64_t tu_pitch, int n, int vecStore)
+__global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int stride, int64_t tu_pitch, int n, int swapStore)
 {
-    // inverse only: the pass-2 accumulators hold residual COLUMNS along the lanes (2-byte scattered stores, half of every
-    // 32-byte sector wasted: 49-57 % of the HBM roofline); with 16-byte aligned destination rows a warp transposes its TU
-    // through a padded shared tile (pitch chosen so that the 32 scattered halfword writes of one store hit 32 banks) and
-    // writes whole 16-byte row pieces
-    constexpr int OP = N == 32 ? 40 : 24;                         // tile row pitch in int16
-    __shared__ __align__(16) int16_t s_out[FWD ? 1 : 8][FWD ? 8 : N * OP];
     constexpr int LG = N == 32 ? 5 : 4;
     constexpr int MT = N / 16, NT = N / 8, KR = N / 16;          // m tiles, n tiles, B registers per n tile
     constexpr int K32 = N == 32;
@@ -94,6 +111,30 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
                 }
                 a1[mt][2 * r + h] = w1; a2[mt][2 * r + h] = w2;      // register order: (r0,h0) (r0,h1) (r1,h0) (r1,h1)
             }
+
+    // inverse with 4-byte aligned destination rows (swapStore): pass 2 runs with the operand roles SWAPPED -- the pass-1 results are
+    // the A operand (rows = residual rows) and the matrix the B operand (B[k][i] = M[k][i], K slots in the accumulator-induced
+    // order), so the accumulators come out row-major (two adjacent residual columns per register pair) and leave as 4-byte stores
+    // like the forward transform's coefficients; the un-swapped form leaves residual COLUMNS along the lanes (2-byte scattered
+    // stores, half of every sector wasted)
+    uint32_t b2c[NT][KR];
+    if (!FWD)
+    {
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int r = 0; r < KR; r++)
+            {
+                uint32_t w = 0;
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                {
+                    const int k2 = 8 * (2 * r + (e >> 1)) + 2 * t + (e & 1);
+                    w |= (uint32_t)(uint8_t)(int8_t)M[k2 * N + 8 * nt + g] << (8 * e);
+                }
+                b2c[nt][r] = w;
+            }
+    }
 
     for (int tu = warp; tu < n; tu += nwarps)
     {
@@ -154,6 +195,32 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
                            ch[2 * mt + half][r], cl[2 * mt + half][r]);
         // ---- pass 2 + store ----
         int16_t* d = dst + (int64_t)tu * (FWD ? (int64_t)N * N : tu_pitch);
+        if (!FWD && swapStore)
+        {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+            {
+                uint32_t aH[2 * KR], aL[2 * KR];
+#pragma unroll
+                for (int r = 0; r < KR; r++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) { aH[2 * r + h] = ch[2 * mt + h][r]; aL[2 * r + h] = cl[2 * mt + h][r]; }
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++)
+                {
+                    int ah[4] = { 0, 0, 0, 0 }, al[4] = { 0, 0, 0, 0 };
+                    imma_da<K32>(ah, aH, b2c[nt], false);
+                    imma_da<K32>(al, aL, b2c[nt], true);
+                    int v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) v[q] = clip16((((ah[q] << 8) + al[q]) + (1 << (shift2 - 1))) >> shift2);
+                    // accumulator element q: residual row = g + 8*(q>>1) + 16 mt, column = 8 nt + 2 t + (q&1)
+                    *(uint32_t*)(d + (int64_t)(g + 16 * mt) * stride + 8 * nt + 2 * t)     = ((uint32_t)(uint16_t)v[0]) | ((uint32_t)(uint16_t)v[1] << 16);
+                    *(uint32_t*)(d + (int64_t)(g + 8 + 16 * mt) * stride + 8 * nt + 2 * t) = ((uint32_t)(uint16_t)v[2]) | ((uint32_t)(uint16_t)v[3] << 16);
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -175,13 +242,6 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
                     *(uint32_t*)(d + (g + 16 * mt) * N + 8 * nt + 2 * t)     = ((uint32_t)(uint16_t)v[0]) | ((uint32_t)(uint16_t)v[1] << 16);
                     *(uint32_t*)(d + (g + 8 + 16 * mt) * N + 8 * nt + 2 * t) = ((uint32_t)(uint16_t)v[2]) | ((uint32_t)(uint16_t)v[3] << 16);
                 }
-                else if (vecStore)
-                {
-                    int16_t* sw = s_out[FWD ? 0 : (threadIdx.x >> 5)];
-                    const int j0 = 8 * nt + 2 * t, i0 = g + 16 * mt;
-                    sw[j0 * OP + i0] = (int16_t)v[0];       sw[(j0 + 1) * OP + i0] = (int16_t)v[1];
-                    sw[j0 * OP + i0 + 8] = (int16_t)v[2];   sw[(j0 + 1) * OP + i0 + 8] = (int16_t)v[3];
-                }
                 else
                 {   // D2[i2][j2] = Out[j2][i2]: dst[j2 * stride + i2]
                     const int j0 = 8 * nt + 2 * t, i0 = g + 16 * mt;
@@ -191,17 +251,6 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
                     d[(int64_t)(j0 + 1) * stride + i0 + 8] = (int16_t)v[3];
                 }
             }
-        if (!FWD && vecStore)
-        {
-            const int16_t* sw = s_out[FWD ? 0 : (threadIdx.x >> 5)];
-            __syncwarp();
-            for (int id = lane; id < N * N / 8; id += 32)
-            {
-                const int row = id / (N / 8), c8 = (id % (N / 8)) * 8;
-                *(uint4*)(d + (int64_t)row * stride + c8) = *(const uint4*)(sw + row * OP + c8);
-            }
-            __syncwarp();
-        }
     }
 }
 
@@ -218,8 +267,9 @@ static int launch_transform_mma(x265cu_ctx* ctx, int op, int N, const int16_t* s
     }
     int blocks = (n + 7) / 8;
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-    // inverse: whole 16-byte row pieces when every destination row starts 16-byte aligned
-    const int vec = !fwd && !(((uintptr_t)dst) & 15) && !(stride & 7) && !(tu_pitch & 7);
+    // inverse: role-swapped pass 2 with 4-byte stores when every destination row is 4-byte aligned (X265CU_IDCT_SWAP=0 disables)
+    static const int swapOn = [] { const char* e = getenv("X265CU_IDCT_SWAP"); return e ? atoi(e) : 1; }();
+    const int vec = swapOn && !fwd && !(((uintptr_t)dst) & 3) && !(stride & 1) && !(tu_pitch & 1);
     if (N == 32)
     {
         if (fwd) k_transform_mma<DEPTH, 32, true><<<blocks, 256, 0, ctx->stream>>>(src, dst, stride, tu_pitch, n, 0);

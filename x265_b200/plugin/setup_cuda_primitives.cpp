@@ -92,6 +92,11 @@ void setupCudaPrimitives(EncoderPrimitives& p, int /*cpuMask*/)
     SET(p.dequant_scaling, dequant_scaling_t, "dequant_scaling", 0, 0, 0);
     SET(p.denoiseDct, denoiseDct_t, "denoiseDct", 0, 0, 0);
     SET(p.propagateCost, cutree_propagate_cost, "propagateCost", 0, 0, 0);
+    for (int i = 0; i < NUM_INTEGRAL_SIZE; i++)
+    {   // SEA integral planes (framefilter.cpp:39-143, driven row by row from FrameFilter::computeMEIntegral)
+        SET(p.integral_inith[i], integralh_t, "integral_inith", i, 0, 0);
+        SET(p.integral_initv[i], integralv_t, "integral_initv", i, 0, 0);
+    }
     /* in-loop filters: deblocking edge filters and SAO (loopfilter.cpp:184-200, sao.cpp:1927-1935) */
     SET(p.sign, sign_t, "sign", 0, 0, 0);
     SET(p.saoCuOrgE0, saoCuOrgE0_t, "saoCuOrgE0", 0, 0, 0);
