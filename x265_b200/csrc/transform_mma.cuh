@@ -75,6 +75,9 @@ __device__ __forceinline__ void split4(int v0, int v1, int v2, int v3, uint32_t&
 template <int DEPTH, int N, bool FWD>
 __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int stride, int64_t tu_pitch, int n, int swapStore)
 {
+    constexpr int IP = N + 2;                                        // inverse: input tile pitch (halfwords)
+    __shared__ __align__(16) int16_t s_in[FWD ? 1 : 8][FWD ? 8 : N * IP];
+    const bool in16 = (((uintptr_t)src) & 15) == 0;                 // contiguous TUs of N * N int16: 16-byte pieces when the base allows
     constexpr int LG = N == 32 ? 5 : 4;
     constexpr int MT = N / 16, NT = N / 8, KR = N / 16;          // m tiles, n tiles, B registers per n tile
     constexpr int K32 = N == 32;
@@ -155,14 +158,33 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
         }
         else
         {
+            // The fragments need four coefficients of one COLUMN per lane (2-byte loads N elements apart from global memory:
+            // half of every sector wasted).  The warp copies its TU with 16-byte row pieces into a padded shared tile (pitch N + 2
+            // halfwords: the four rows a quad of lanes reads are 4 banks apart) and picks the columns out of that.
             const int16_t* s = src + (int64_t)tu * N * N;
+            int16_t* tile = s_in[threadIdx.x >> 5];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < N * N / 256; q++)
+            {
+                const int e0 = (q * 32 + lane) * 8, row = e0 >> LG, col = e0 & (N - 1);
+                const uint4 w = in16 ? *(const uint4*)(s + e0) : make_uint4(0, 0, 0, 0);
+                uint32_t* tp = (uint32_t*)(tile + row * IP + col);
+                if (in16) { tp[0] = w.x; tp[1] = w.y; tp[2] = w.z; tp[3] = w.w; }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) tile[row * IP + col + k] = s[e0 + k];
+                }
+            }
+            __syncwarp();
 #pragma unroll
             for (int nt = 0; nt < NT; nt++)
 #pragma unroll
                 for (int r = 0; r < KR; r++)
                 {   // B[k][j] = In[k][j]: k = 16 r + 4 t + e (coefficient row), j = g + 8 nt
-                    const int16_t* p = s + (16 * r + 4 * t) * N + g + 8 * nt;
-                    split4(p[0], p[N], p[2 * N], p[3 * N], bh[nt][r], bl[nt][r]);
+                    const int16_t* p = tile + (16 * r + 4 * t) * IP + g + 8 * nt;
+                    split4(p[0], p[IP], p[2 * IP], p[3 * IP], bh[nt][r], bl[nt][r]);
                 }
         }
         // ---- pass 1 ----
