@@ -139,6 +139,14 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
             }
     }
 
+    constexpr bool PRE = !FWD && N == 16;                           // (32x32: the 16 prefetch registers would cost a resident CTA)
+    uint4 pre[PRE ? N * N / 256 : 1];
+    if (PRE && in16 && warp < n)
+    {
+        const int16_t* sn = src + (int64_t)warp * N * N;
+#pragma unroll
+        for (int q = 0; q < N * N / 256; q++) pre[PRE ? q : 0] = __ldg((const uint4*)(sn + (q * 32 + lane) * 8));
+    }
     for (int tu = warp; tu < n; tu += nwarps)
     {
         // ---- pass-1 B fragments from memory ----
@@ -168,9 +176,12 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
             for (int q = 0; q < N * N / 256; q++)
             {
                 const int e0 = (q * 32 + lane) * 8, row = e0 >> LG, col = e0 & (N - 1);
-                const uint4 w = in16 ? *(const uint4*)(s + e0) : make_uint4(0, 0, 0, 0);
                 uint32_t* tp = (uint32_t*)(tile + row * IP + col);
-                if (in16) { tp[0] = w.x; tp[1] = w.y; tp[2] = w.z; tp[3] = w.w; }
+                if (in16)
+                {
+                    const uint4 w = PRE ? pre[PRE ? q : 0] : __ldg((const uint4*)(s + e0));
+                    tp[0] = w.x; tp[1] = w.y; tp[2] = w.z; tp[3] = w.w;
+                }
                 else
                 {
 #pragma unroll
@@ -178,6 +189,15 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
                 }
             }
             __syncwarp();
+            // the NEXT TU's coefficients are requested now and land while this TU is transformed (one warp per TU is a long
+            // dependent chain: load -> tile -> fragments -> 2 x MMA passes -> stores; without the prefetch the inverse sat at
+            // ~57 % of the HBM roofline whatever its access patterns were)
+            if (PRE && in16 && tu + nwarps < n)
+            {
+                const int16_t* sn = src + (int64_t)(tu + nwarps) * N * N;
+#pragma unroll
+                for (int q = 0; q < N * N / 256; q++) pre[PRE ? q : 0] = __ldg((const uint4*)(sn + (q * 32 + lane) * 8));
+            }
 #pragma unroll
             for (int nt = 0; nt < NT; nt++)
 #pragma unroll
