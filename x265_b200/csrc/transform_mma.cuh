@@ -172,6 +172,12 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
             const int16_t* s = src + (int64_t)tu * N * N;
             int16_t* tile = s_in[threadIdx.x >> 5];
             __syncwarp();
+            uint4 wv[N * N / 256];                                   // all pieces requested before the first shared store
+            if (in16)
+            {
+#pragma unroll
+                for (int q = 0; q < N * N / 256; q++) wv[q] = PRE ? pre[PRE ? q : 0] : __ldg((const uint4*)(s + (q * 32 + lane) * 8));
+            }
 #pragma unroll
             for (int q = 0; q < N * N / 256; q++)
             {
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(256) k_transform_mma(const int16_t* __restrict
                 uint32_t* tp = (uint32_t*)(tile + row * IP + col);
                 if (in16)
                 {
-                    const uint4 w = PRE ? pre[PRE ? q : 0] : __ldg((const uint4*)(s + e0));
+                    const uint4 w = wv[q];
                     tp[0] = w.x; tp[1] = w.y; tp[2] = w.z; tp[3] = w.w;
                 }
                 else
