@@ -137,8 +137,16 @@ typedef struct {
     const pixel* fencC[2];  /* source Cb, Cr (origin pixel) */
     const pixel* refC[2];   /* reference Cb, Cr (origin pixel) */
     intptr_t cstride;
+    /* X265_SEA (method 4; motion.cpp:1242-1395): the 12 integral planes of the reference picture (FrameFilter::computeMEIntegral,
+     * framefilter.cpp:725-822; orc_build_integral) at pixel (0, 0); the search adds `offset` as Search::predInterSearch does
+     * (search.cpp:2264).  NULL for the other methods. */
+    const uint32_t* const* integral;
 } orc_me_job;
 int orc_motion_estimate(const orc_me_job* job, int* outQMv);
+/* planes[k] = pixel (0, 0) of integral plane k in a buffer of the picture plane's geometry (same stride, >= padY + 1 rows above,
+ * >= padX columns left); picHeightCtu = picture height in 64-pixel CTU rows.  k: 0 32x32, 1 32x24, 2 32x8, 3 24x32, 4 16x16,
+ * 5 16x12, 6 16x4, 7 12x16, 8 8x32, 9 8x8, 10 4x16, 11 4x4 (width x height of the box sums). */
+void orc_build_integral(const pixel* picOrg, intptr_t stride, int picHeightCtu, uint32_t* const* planes);
 
 #ifdef __cplusplus
 }

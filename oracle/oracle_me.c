@@ -7,6 +7,7 @@
  *   lowresQPelCost            common/lowres.h:94-120
  * Pinned against the real MotionEstimate through oracle/_ref (x265ref_motion_estimate).
  */
+#include <stdlib.h>
 #include "oracle.h"
 #include <math.h>
 #include <string.h>
@@ -29,6 +30,8 @@ void orc_mvcost_table(double lambda, int range, uint16_t* out)
 long long g_orc_cnt[4];   /* fpel SAD evaluations, sub-pel compares, raster points, jobs */
 
 typedef struct { int x, y; } mv_t;
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
 typedef int (*cmp_fn)(const pixel*, intptr_t, const pixel*, intptr_t, int, int);
 
 typedef struct {
@@ -365,6 +368,83 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
         bmv.x += k_square1[dir].x; bmv.y += k_square1[dir].y;
         break;
     }
+    case 4: /* X265_SEA motion.cpp:1242-1395: successive elimination on the integral planes, literally (incl. its quirks: the row
+             * cost p_cost_mvy[tmv.y] << 2 indexes the quarter-pel table with a full-pel value; the scanned width is rounded up to 4) */
+    {
+        const int w = j->pw, h = j->ph;
+        const int minX = imax(bmv.x - merange, c->mvmin.x), minY = imax(bmv.y - merange, c->mvmin.y);      /* omv = bmv */
+        const int maxX = imin(bmv.x + merange, c->mvmax.x), maxY = imin(bmv.y + merange, c->mvmax.y);
+        const int meRangeWidth = (maxX - minX + 3) & ~3;
+        int16_t* scratch = (int16_t*)calloc((size_t)(merange * 2 + 4 > meRangeWidth + 4 ? merange * 2 + 4 : meRangeWidth + 4), sizeof(int16_t));
+        int deltaX = (w <= 8) ? w : (w >> 1), deltaY = (h <= 8) ? h : (h >> 1);
+        const int smallRect = (w == 4 && h == 4) || (w == 16 && h == 12) || (w == 12 && h == 16) || (w == 16 && h == 4) || (w == 4 && h == 16);
+        const int verticalRect = (w == 32 && h == 64) || (w == 16 && h == 32) || (w == 8 && h == 16) || (w == 4 && h == 8);
+        const int horizontalRect = (w == 64 && h == 32) || (w == 32 && h == 16) || (w == 16 && h == 8) || (w == 8 && h == 4);
+        const int asymV = (w == 12 && h == 16) || (w == 4 && h == 16) || (w == 24 && h == 32) || (w == 8 && h == 32) || (w == 48 && h == 64) || (w == 16 && h == 64);
+        const int asymH = (w == 16 && h == 12) || (w == 16 && h == 4) || (w == 32 && h == 24) || (w == 32 && h == 8) || (w == 64 && h == 48) || (w == 64 && h == 16);
+        int tw, th;                                        /* the sub-block whose four sums are the source's "DC"s */
+        if (verticalRect) { tw = w; th = h >> 1; }
+        else if (horizontalRect) { tw = w >> 1; th = h; }
+        else if (asymV || asymH) { tw = smallRect ? w : w >> 1; th = smallRect ? h : h >> 1; }
+        else { tw = (w <= 8) ? w : w >> 1; th = (w <= 8) ? h : h >> 1; }
+        int encDC[4];
+        {   /* sad_x4 against a zero block = the four sub-block sums of the source (motion.cpp:1304-1311) */
+            const pixel* f[4] = { c->fenc, c->fenc + deltaX, c->fenc + deltaY * 64, c->fenc + deltaX + deltaY * 64 };
+            for (int k = 0; k < 4; k++)
+            {
+                int sum = 0;
+                for (int y = 0; y < th; y++) for (int x = 0; x < tw; x++) sum += f[k][y * 64 + x];
+                encDC[k] = sum;
+            }
+        }
+        int plane;
+        switch (deltaX)
+        {
+        case 32: plane = (deltaY % 24 == 0) ? 1 : (deltaY == 8 ? 2 : 0); break;
+        case 24: plane = 3; break;
+        case 16: plane = (deltaY % 12 == 0) ? 5 : (deltaY == 4 ? 6 : 4); break;
+        case 12: plane = 7; break;
+        case 8:  plane = (deltaY == 32) ? 8 : 9; break;
+        case 4:  plane = (deltaY == 16) ? 10 : 11; break;
+        default: plane = 11; break;
+        }
+        const uint32_t* sumsBase = j->integral[plane] + j->offset;
+        if ((w == 64 && h == 64) || (w == 32 && h == 32) || (w == 16 && h == 16) || verticalRect || asymV)
+            deltaY *= (int)c->stride;
+        if (verticalRect) encDC[1] = encDC[2];
+        if (horizontalRect) deltaY = deltaX;
+        /* m_cost_mvx / m_cost_mvy are already centred on the MVP (bitcost.h:42: m_cost - mvp); the SEA branch subtracts qmvp AGAIN
+         * (motion.cpp:1250-1251), so its p_cost tables are centred on 2 * mvp -- restated as written.  The ADS column costs come from
+         * m_fpelMvCosts[-qmvp.x & 3] + (-qmvp.x >> 2) (motion.cpp:1264; bitcost.cpp:68-75: [j][i] = cost[4 i + j]), centred on mvp. */
+        const uint16_t* p_cost_mvx = j->mvcost - 2 * c->mvp.x;
+        const uint16_t* p_cost_mvy = j->mvcost - 2 * c->mvp.y;
+        uint16_t* costX = (uint16_t*)malloc((size_t)(meRangeWidth + 4) * sizeof(uint16_t));
+        for (int i = 0; i < meRangeWidth + 4; i++) costX[i] = j->mvcost[((minX + i) << 2) - c->mvp.x];
+        for (int ty = minY; ty <= maxY; ty++)
+        {
+            const int ycost = p_cost_mvy[ty] << 2;
+            if (bcost <= ycost) continue;
+            bcost -= ycost;
+            const int xn = orc_ads(encDC, sumsBase + minX + (intptr_t)ty * c->stride, deltaY, costX, scratch, meRangeWidth, bcost, w, h);
+            int i;
+            for (i = 0; i < xn - 2; i += 3)
+                for (int k = 0; k < 3; k++)
+                {   /* COST_MV_X3_ABS: SAD + the x cost only, against the row-relative best */
+                    const int tx = minX + scratch[i + k];
+                    const int cost = fpel_sad(c, tx, ty) + p_cost_mvx[tx << 2];
+                    if (cost < bcost) { bcost = cost; bmv.x = tx; bmv.y = ty; }
+                }
+            bcost += ycost;
+            for (; i < xn; i++)
+            {
+                const int tx = minX + scratch[i];
+                const int cost = cost_fpel(c, tx, ty);
+                if (cost < bcost) { bcost = cost; bmv.x = tx; bmv.y = ty; }
+            }
+        }
+        free(costX); free(scratch);
+        break;
+    }
     case 5: /* X265_FULL_SEARCH motion.cpp:1397-1440: every full-pel position of [mvmin, mvmax], raster order, strict '<' */
     {
         for (int ty = c->mvmin.y; ty <= c->mvmax.y; ty++)
@@ -515,4 +595,25 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
     outQMv[0] = bx; outQMv[1] = by;
     return bcost;
 #undef CLIPQ
+}
+
+/* FrameFilter::computeMEIntegral (encoder/framefilter.cpp:725-822) for a whole picture: per plane (W x H), row y + 1 = the running
+ * W-wide row sums of picture row y added to row y (integral_inith), and once H rows exist the row H above is turned into box sums
+ * (integral_initv).  Rows run from -padY to picHeight + padY - 2, columns from -padX over `stride` elements, padX = 96, padY = 80. */
+void orc_build_integral(const pixel* picOrg, intptr_t stride, int picHeightCtu, uint32_t* const* planes)
+{
+    static const int W[12] = { 32, 32, 32, 24, 16, 16, 16, 12, 8, 8, 4, 4 };
+    static const int H[12] = { 32, 24, 8, 32, 16, 12, 4, 16, 32, 8, 16, 4 };
+    const int padX = 96, padY = 80, maxHeight = picHeightCtu * 64;
+    for (int k = 0; k < 12; k++) memset(planes[k] - padY * stride - padX, 0, (size_t)stride * sizeof(uint32_t));
+    for (int y = -padY; y < maxHeight + padY - 1; y++)
+    {
+        const pixel* pix = picOrg + (intptr_t)y * stride - padX;
+        for (int k = 0; k < 12; k++)
+        {
+            uint32_t* sum = planes[k] + (intptr_t)(y + 1) * stride - padX;
+            orc_integral_inith(sum, pix, stride, W[k]);
+            if (y >= H[k] - padY) orc_integral_initv(sum - (intptr_t)H[k] * stride, stride, H[k]);
+        }
+    }
 }

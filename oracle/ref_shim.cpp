@@ -157,6 +157,54 @@ int x265ref_motion_estimate(pixel* fencPlane, intptr_t fencStride, intptr_t offs
     return cost;
 }
 
+/* The 12 SEA integral planes of a picture exactly as FrameFilter::computeMEIntegral produces them (encoder/framefilter.cpp:725-822),
+ * driven row by row through the REAL integral_inith / integral_initv primitives; planes[k] = pixel (0, 0) of plane k in a buffer of
+ * the picture plane's geometry (pins oracle/oracle_me.c: orc_build_integral). */
+void x265ref_build_integral(const pixel* picOrg, intptr_t stride, int picHeightCtu, uint32_t* const* planes)
+{
+    ensure_init();
+    static const int W[12] = { INTEGRAL_32, INTEGRAL_32, INTEGRAL_32, INTEGRAL_24, INTEGRAL_16, INTEGRAL_16, INTEGRAL_16, INTEGRAL_12, INTEGRAL_8, INTEGRAL_8, INTEGRAL_4, INTEGRAL_4 };
+    static const int Hk[12] = { INTEGRAL_32, INTEGRAL_24, INTEGRAL_8, INTEGRAL_32, INTEGRAL_16, INTEGRAL_12, INTEGRAL_4, INTEGRAL_16, INTEGRAL_32, INTEGRAL_8, INTEGRAL_16, INTEGRAL_4 };
+    static const int Hn[12] = { 32, 24, 8, 32, 16, 12, 4, 16, 32, 8, 16, 4 };
+    const int padX = 64 + 32, padY = 64 + 16, maxHeight = picHeightCtu * 64;
+    for (int k = 0; k < INTEGRAL_PLANE_NUM; k++) memset(planes[k] - padY * stride - padX, 0, stride * sizeof(uint32_t));
+    for (int y = -padY; y < maxHeight + padY - 1; y++)
+    {
+        pixel* pix = (pixel*)picOrg + y * stride - padX;
+        for (int k = 0; k < INTEGRAL_PLANE_NUM; k++)
+        {
+            uint32_t* sum = planes[k] + (y + 1) * stride - padX;
+            primitives.integral_inith[W[k]](sum, pix, stride);
+            if (y >= Hn[k] - padY) primitives.integral_initv[Hk[k]](sum - Hn[k] * stride, stride);
+        }
+    }
+}
+
+/* motionEstimate with X265_SEA: MotionEstimate::integral[] set as Search::predInterSearch sets it (search.cpp:2264): plane + PU offset */
+int x265ref_motion_estimate_sea(pixel* fencPlane, intptr_t fencStride, intptr_t offset, pixel* refPlane, intptr_t refStride,
+                                uint32_t* const* integral, int pw, int ph, int subme, int qp,
+                                const int* mvmin, const int* mvmax, const int* qmvp, int numCand, const int* mvc, int merange, int* outQMv)
+{
+    ensure_init();
+    static bool scales = false;
+    if (!scales) { MotionEstimate::initScales(); scales = true; }
+    MotionEstimate me;
+    me.init(X265_CSP_I400);
+    me.setQP(qp);
+    me.setSourcePU(fencPlane, fencStride, offset, pw, ph, X265_SEA, X265_SEA, X265_SEA, subme);
+    for (int k = 0; k < INTEGRAL_PLANE_NUM; k++) me.integral[k] = integral[k] + offset;
+    ReferencePlanes ref;
+    ref.lumaStride = refStride;
+    ref.isLowres = false;
+    ref.fpelPlane[0] = refPlane;
+    MV mn(mvmin[0], mvmin[1]), mx(mvmax[0], mvmax[1]), mvp(qmvp[0], qmvp[1]), out;
+    MV cands[32];
+    for (int i = 0; i < numCand && i < 32; i++) cands[i] = MV(mvc[2 * i], mvc[2 * i + 1]);
+    int cost = me.motionEstimate(&ref, mn, mx, mvp, numCand, cands, merange, out, 1, NULL);
+    outQMv[0] = out.x; outQMv[1] = out.y;
+    return cost;
+}
+
 /* The same call with the chroma-SATD term of subpelCompare active (motion.cpp:204-212, 1601-1661): driven
  * through the Yuv variant of setSourcePU (motion.cpp:194-222) with bChroma = true, 4:2:0.  The PU is handed
  * over as a Yuv whose top-left block is the PU (puPartIdx 0) and the reference as planes already offset to the

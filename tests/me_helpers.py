@@ -12,7 +12,7 @@ class OrcMeJob(C.Structure):
                 ("lowres", I), ("pw", I), ("ph", I), ("method", I), ("subme", I),
                 ("mvmin", I * 2), ("mvmax", I * 2), ("qmvp", I * 2), ("numCand", I), ("mvc", P),
                 ("merange", I), ("mvcost", P),
-                ("chroma", I), ("fencC", P * 2), ("refC", P * 2), ("cstride", IP)]
+                ("chroma", I), ("fencC", P * 2), ("refC", P * 2), ("cstride", IP), ("integral", P)]
 
 
 _tables = {}
@@ -160,3 +160,54 @@ def run_both_chroma(O, R, depth, rng, w, h, method, subme, smooth, merange, qp=3
     O.orc_motion_estimate.argtypes = [C.POINTER(OrcMeJob), P]
     co = O.orc_motion_estimate(C.byref(job), ptr(out_o))
     return (cr, int(out_r[0]), int(out_r[1])), (co, int(out_o[0]), int(out_o[1]))
+
+
+def run_both_sea(O, R, depth, rng, w, h, subme, smooth, merange, qp=30):
+    """X265_SEA (motion.cpp:1242-1395) through the real MotionEstimate with the 12 integral planes FrameFilter::computeMEIntegral
+    would hand it (x265ref_build_integral: the real integral_init primitives) and through the oracle (orc_build_integral +
+    method 4); also checks the two sets of planes against each other over the region the search can touch."""
+    mx = (1 << depth) - 1
+    W, H, margin = 256, 192, 96
+    lam = R.x265ref_lambda(qp)
+    tab = mvcost_table(O, lam)
+    fenc, stride, org = make_plane(rng, depth, W, H, margin, smooth=smooth)
+    refb, _, _ = make_plane(rng, depth, W, H, margin, smooth=smooth)
+    if smooth:
+        sh = np.roll(np.roll(fenc, int(rng.integers(-9, 10)), axis=0), int(rng.integers(-9, 10)), axis=1)
+        refb = np.clip(sh.astype(np.int64) + rng.integers(-3, 4, sh.shape), 0, mx).astype(fenc.dtype)
+    ipl_r = [np.zeros(refb.shape, np.uint32) for _ in range(12)]
+    ipl_o = [np.zeros(refb.shape, np.uint32) for _ in range(12)]
+    PA = P * 12
+    arr_r = PA(*[p.ctypes.data + org * 4 for p in ipl_r]); arr_o = PA(*[p.ctypes.data + org * 4 for p in ipl_o])
+    R.x265ref_build_integral.argtypes = [P, IP, I, C.POINTER(P)]; R.x265ref_build_integral.restype = None
+    O.orc_build_integral.argtypes = [P, IP, I, C.POINTER(P)]; O.orc_build_integral.restype = None
+    R.x265ref_build_integral(ptr(refb, org), stride, H // 64, arr_r)
+    O.orc_build_integral(ptr(refb, org), stride, H // 64, arr_o)
+    rows = slice(margin - 79, margin + H + 78)
+    for a, b in zip(ipl_r, ipl_o):
+        assert np.array_equal(a[rows], b[rows])
+    bx = int(rng.integers(0, (W - w) // 4 + 1)) * 4; by = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+    offset = org + by * stride + bx
+    qmvp = (int(rng.integers(-40, 41)), int(rng.integers(-40, 41)))
+    lim = margin - 40
+    mvmin = (max(-bx - lim, (qmvp[0] >> 2) - merange), max(-by - lim, (qmvp[1] >> 2) - merange))
+    mvmax = (min(W - w - bx + lim, (qmvp[0] >> 2) + merange), min(H - h - by + lim, (qmvp[1] >> 2) + merange))
+    ncand = int(rng.integers(0, 4))
+    mvc = rng.integers(-60, 61, (max(ncand, 1), 2)).astype(np.int32)
+    out_r = np.zeros(2, np.int32); out_o = np.zeros(2, np.int32)
+    mn = np.array(mvmin, np.int32); mxv = np.array(mvmax, np.int32); mp = np.array(qmvp, np.int32)
+    R.x265ref_motion_estimate_sea.argtypes = [P, IP, IP, P, IP, C.POINTER(P), I, I, I, I, P, P, P, I, P, I, P]
+    cr = R.x265ref_motion_estimate_sea(ptr(fenc), stride, offset, ptr(refb), stride, arr_r, w, h, subme, qp,
+                                       ptr(mn), ptr(mxv), ptr(mp), ncand, ptr(mvc), merange, ptr(out_r))
+    job = OrcMeJob()
+    job.fenc = fenc.ctypes.data; job.fencStride = stride; job.offset = offset
+    for i in range(4):
+        job.ref[i] = refb.ctypes.data
+    job.refStride = stride; job.lowres = 0; job.pw = w; job.ph = h; job.method = 4; job.subme = subme
+    job.mvmin[0], job.mvmin[1] = mvmin; job.mvmax[0], job.mvmax[1] = mvmax; job.qmvp[0], job.qmvp[1] = qmvp
+    job.numCand = ncand; job.mvc = mvc.ctypes.data; job.merange = merange
+    job.mvcost = tab.ctypes.data + MVRANGE * 2
+    job.integral = C.cast(arr_o, C.c_void_p)
+    O.orc_motion_estimate.argtypes = [C.POINTER(OrcMeJob), P]; O.orc_motion_estimate.restype = I
+    co = O.orc_motion_estimate(C.byref(job), ptr(out_o))
+    return (int(cr), int(out_r[0]), int(out_r[1])), (int(co), int(out_o[0]), int(out_o[1]))

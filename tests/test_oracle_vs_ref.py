@@ -99,6 +99,26 @@ def test_motion_estimate_full_search(depth):
 
 
 @pytest.mark.parametrize("depth", DEPTHS)
+def test_motion_estimate_sea(depth):
+    """X265_SEA (motion.cpp:1242-1395) restated literally -- partition-dependent integral plane / ADS variant / delta, the row cost
+    p_cost_mvy[tmv.y] << 2, the width rounded up to 4 -- against the real MotionEstimate fed with integral planes built by the real
+    integral_init primitives in FrameFilter::computeMEIntegral's order.  Every PU size."""
+    from me_helpers import run_both_sea
+    R, O = libs(depth)
+    rng = np.random.default_rng(404)
+    sizes = [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (32, 16), (16, 32), (64, 32), (32, 64),
+             (16, 12), (12, 16), (16, 4), (4, 16), (32, 24), (24, 32), (32, 8), (8, 32), (64, 48), (48, 64), (64, 16), (16, 64), (8, 4), (4, 8)]
+    n = 0
+    for (w, h) in sizes:
+        for subme in (0, 2):
+            for smooth in (True, False):
+                r, o = run_both_sea(O, R, depth, rng, w, h, subme, smooth, int(rng.integers(4, 17)))
+                assert r == o, (w, h, subme, smooth, r, o)
+                n += 1
+    assert n == len(sizes) * 4
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
 def test_motion_estimate_lowres(depth):
     R, O = libs(depth)
     rng = np.random.default_rng(17)
