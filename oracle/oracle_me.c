@@ -234,6 +234,10 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
     me_ctx ctx; me_ctx* c = &ctx;
     c->j = j;
     g_orc_cnt[3]++;
+    /* SEA sums source sub-blocks at offsets that can lie OUTSIDE a narrow PU (e.g. fenc + 8 for an 8x32 PU, motion.cpp:1304-1311):
+     * the reference reads whatever its 64-stride PU cache holds there.  The pinned model is a cache that was zero before the PU
+     * was copied in (the shim zeroes MotionEstimate::fencPUYuv before setSourcePU); only method 4 ever looks there. */
+    if (j->method == 4) memset(c->fenc, 0, sizeof(c->fenc));
     orc_copy_pp(c->fenc, 64, j->fenc + j->offset, j->fencStride, j->pw, j->ph);
     c->fref = j->ref[0] + j->offset;
     c->stride = j->refStride;

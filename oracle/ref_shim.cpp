@@ -191,6 +191,9 @@ int x265ref_motion_estimate_sea(pixel* fencPlane, intptr_t fencStride, intptr_t 
     MotionEstimate me;
     me.init(X265_CSP_I400);
     me.setQP(qp);
+    /* SEA reads source sub-blocks beyond a narrow PU's width (motion.cpp:1304-1311 with deltaX = w for w <= 8): make the PU cache
+     * deterministic (zero) outside the PU instead of leaving malloc's content there */
+    memset(me.fencPUYuv.m_buf[0], 0, sizeof(pixel) * me.fencPUYuv.m_size * me.fencPUYuv.m_size);
     me.setSourcePU(fencPlane, fencStride, offset, pw, ph, X265_SEA, X265_SEA, X265_SEA, subme);
     for (int k = 0; k < INTEGRAL_PLANE_NUM; k++) me.integral[k] = integral[k] + offset;
     ReferencePlanes ref;
