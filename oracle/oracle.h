@@ -122,7 +122,7 @@ typedef struct {
     intptr_t refStride;
     int lowres;             /* 1: lowres.h:67-120 qpel-by-averaging path */
     int pw, ph;             /* PU size */
-    int method;             /* 0 DIA, 1 HEX, 3 STAR (x265.h X265_*_SEARCH) */
+    int method;             /* 0 DIA, 1 HEX, 2 UMH, 3 STAR, 4 SEA (needs `integral`), 5 FULL (x265.h X265_*_SEARCH) */
     int subme;              /* 0..7 (motion.cpp:48-58) */
     int mvmin[2], mvmax[2]; /* full-pel */
     int qmvp[2];            /* qpel predictor */

@@ -229,6 +229,43 @@ static const struct { int hpel_iters, hpel_dirs, qpel_iters, qpel_dirs, hpel_sat
 
 static inline int yok(const me_ctx* c, int y) { return (y >= c->mvmin.y) & (y <= c->mvmax.y); }
 
+/* ---- X265_UMH_SEARCH helpers (motion.cpp:226-360 macros as functions over a small state) ---- */
+typedef struct { const me_ctx* c; mv_t bmv, omv; int bcost; } umh_t;
+static void umh_cost_mv(umh_t* u, int x, int y)                       /* COST_MV */
+{
+    int cost = cost_fpel(u->c, x, y);
+    if (cost < u->bcost) { u->bcost = cost; u->bmv.x = x; u->bmv.y = y; }
+}
+static void umh_x4(umh_t* u, int x0, int y0, int x1, int y1, int x2, int y2, int x3, int y3)   /* COST_MV_X4: around omv, y range only */
+{
+    const int o[8] = { x0, y0, x1, y1, x2, y2, x3, y3 };
+    int costs[4];
+    for (int k = 0; k < 4; k++) costs[k] = cost_fpel(u->c, u->omv.x + o[2 * k], u->omv.y + o[2 * k + 1]);
+    for (int k = 0; k < 4; k++)
+        if (yok(u->c, u->omv.y + o[2 * k + 1]) && costs[k] < u->bcost)
+        { u->bcost = costs[k]; u->bmv.x = u->omv.x + o[2 * k]; u->bmv.y = u->omv.y + o[2 * k + 1]; }
+}
+static void umh_cross(umh_t* u, int start, int x_max, int y_max)     /* CROSS (motion.cpp:336-360) */
+{
+    const me_ctx* c = u->c;
+    int16_t i = (int16_t)start;
+    if (x_max <= imin(c->mvmax.x - u->omv.x, u->omv.x - c->mvmin.x))
+        for (; i < x_max - 2; i += 4) umh_x4(u, i, 0, -i, 0, i + 2, 0, -i - 2, 0);
+    for (; i < x_max; i += 2)
+    {
+        if (u->omv.x + i <= c->mvmax.x) umh_cost_mv(u, u->omv.x + i, u->omv.y);
+        if (u->omv.x - i >= c->mvmin.x) umh_cost_mv(u, u->omv.x - i, u->omv.y);
+    }
+    i = (int16_t)start;
+    if (y_max <= imin(c->mvmax.y - u->omv.y, u->omv.y - c->mvmin.y))
+        for (; i < y_max - 2; i += 4) umh_x4(u, 0, i, 0, -i, 0, i + 2, 0, -i - 2);
+    for (; i < y_max; i += 2)
+    {
+        if (u->omv.y + i <= c->mvmax.y) umh_cost_mv(u, u->omv.x, u->omv.y + i);
+        if (u->omv.y - i >= c->mvmin.y) umh_cost_mv(u, u->omv.x, u->omv.y - i);
+    }
+}
+
 int orc_motion_estimate(const orc_me_job* j, int* outQMv)
 {
     me_ctx ctx; me_ctx* c = &ctx;
@@ -290,8 +327,8 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
             if (cost < bprecost) { bprecost = cost; bestprex = mx; bestprey = my; }
         }
     }
-    /* pmv.roundToFPel() / omv are only used by UMH/SEA (not restated) */
 
+    int hexRange = merange;                 /* UMH hands its adapted range to the hexagon search it falls into */
     switch (j->method)
     {
     case 0: /* X265_DIA_SEARCH motion.cpp:822-846 */
@@ -315,6 +352,90 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
         bcost >>= 4;
         break;
     }
+    case 2: /* X265_UMH_SEARCH motion.cpp:946-1130: predictor refinement, early termination, cross, 5x5, hexagon grid, then me_hex2 */
+    {
+        static const mv_t hex4[16] = { {0,-4}, {0,4}, {-2,-3}, {2,-3}, {-4,-2}, {4,-2}, {-4,-1}, {4,-1}, {-4,0}, {4,0}, {-4,1}, {4,1}, {-4,2}, {4,2}, {-2,3}, {2,3} };
+        const int scale = (j->ph * j->ph) >> 4;                         /* sizeScale[partEnum] = (H * H) >> 4 (motion.cpp:123-152) */
+#define SAD_THRESH(v) (u.bcost < (((v) >> 4) * scale))
+        const mv_t pmv = { (pmvx + 2) >> 2, (pmvy + 2) >> 2 };          /* pmv.roundToFPel() (motion.cpp:816) */
+        umh_t u; u.c = c; u.bmv = bmv; u.bcost = bcost;
+        int um = merange, cross_start = 1, done = 0;
+        u.omv = u.bmv;
+        const int ucost1 = u.bcost;
+        u.omv = pmv; umh_x4(&u, 0, -1, 0, 1, -1, 0, 1, 0);              /* DIA1_ITER(pmv) */
+        if (pmv.x | pmv.y) { u.omv.x = 0; u.omv.y = 0; umh_x4(&u, 0, -1, 0, 1, -1, 0, 1, 0); }
+        const int ucost2 = u.bcost;
+        if ((u.bmv.x | u.bmv.y) && !(u.bmv.x == pmv.x && u.bmv.y == pmv.y)) { u.omv = u.bmv; umh_x4(&u, 0, -1, 0, 1, -1, 0, 1, 0); }
+        if (u.bcost == ucost2) cross_start = 3;
+        u.omv = u.bmv;
+        if (u.bcost == ucost2 && SAD_THRESH(2000))
+        {
+            umh_x4(&u, 0, -2, -1, -1, 1, -1, -2, 0);
+            umh_x4(&u, 2, 0, -1, 1, 1, 1, 0, 2);
+            if (u.bcost == ucost1 && SAD_THRESH(500)) done = 1;
+            else if (u.bcost == ucost2)
+            {
+                const int range = (int16_t)(um >> 1) | 1;
+                umh_cross(&u, 3, range, range);
+                umh_x4(&u, -1, -2, 1, -2, -2, -1, 2, -1);
+                umh_x4(&u, -2, 1, 2, 1, -1, 2, 1, 2);
+                if (u.bcost == ucost2) done = 1;
+                cross_start = range + 2;
+            }
+        }
+        if (done) { bmv = u.bmv; bcost = u.bcost; break; }
+        if (j->numCand)
+        {   /* adaptive search range (motion.cpp:986-1037) */
+            static const uint8_t range_mul[4][4] = { { 3, 3, 4, 4 }, { 3, 4, 4, 4 }, { 4, 4, 4, 5 }, { 4, 4, 5, 6 } };
+            const int is64 = j->pw == 64 && j->ph == 64;
+            int mvd, denom = 1;
+            if (j->numCand == 1)
+                mvd = is64 ? 25 : abs(j->qmvp[0] - j->mvc[0]) + abs(j->qmvp[1] - j->mvc[1]);
+            else
+            {
+                denom = j->numCand - 1;
+                mvd = 0;
+                if (!is64) { mvd = abs(j->qmvp[0] - j->mvc[0]) + abs(j->qmvp[1] - j->mvc[1]); denom++; }
+                for (int i = 0; i < j->numCand - 1; i++)                /* predictorDifference (motion.cpp:87-98) */
+                    mvd += abs(j->mvc[2 * i] - j->mvc[2 * i + 2]) + abs(j->mvc[2 * i + 1] - j->mvc[2 * i + 3]);
+            }
+            const int sad_ctx = SAD_THRESH(1000) ? 0 : SAD_THRESH(2000) ? 1 : SAD_THRESH(4000) ? 2 : 3;
+            const int mvd_ctx = mvd < 10 * denom ? 0 : mvd < 20 * denom ? 1 : mvd < 40 * denom ? 2 : 3;
+            um = (um * range_mul[mvd_ctx][sad_ctx]) >> 2;
+        }
+        umh_cross(&u, cross_start, um, um >> 1);
+        umh_x4(&u, -2, -2, -2, 2, 2, -2, 2, 2);
+        /* hexagon grid (motion.cpp:1045-1124) */
+        u.omv = u.bmv;
+        uint16_t i = 1;
+        do
+        {
+            const int lim = imin(imin(c->mvmax.x - u.omv.x, u.omv.x - c->mvmin.x), imin(c->mvmax.y - u.omv.y, u.omv.y - c->mvmin.y));
+            if (4 * i > lim)
+            {
+                for (int k = 0; k < 16; k++)
+                {
+                    const int x = u.omv.x + hex4[k].x * i, y = u.omv.y + hex4[k].y * i;
+                    if (in_range(c, x, y)) umh_cost_mv(&u, x, y);
+                }
+            }
+            else
+            {
+                int dir = -1;
+                for (int k = 0; k < 16; k++)
+                {
+                    const int cost = cost_fpel(c, u.omv.x + hex4[k].x * i, u.omv.y + hex4[k].y * i);
+                    if (yok(c, u.omv.y + hex4[k].y) && cost < u.bcost) { u.bcost = cost; dir = k; }   /* MIN_MV: the y test uses the UNSCALED offset */
+                }
+                if (dir >= 0) { u.bmv.x = u.omv.x + i * hex4[dir].x; u.bmv.y = u.omv.y + i * hex4[dir].y; }
+            }
+        }
+        while (++i <= um >> 2);
+#undef SAD_THRESH
+        bmv = u.bmv; bcost = u.bcost; hexRange = um;
+        if (!in_range(c, bmv.x, bmv.y)) break;
+    }
+    /* fall through: goto me_hex2 (motion.cpp:1125-1127) */
     case 1: /* X265_HEX_SEARCH motion.cpp:848-945 */
     {
         int c0 = cost_fpel(c, bmv.x - 2, bmv.y), c1 = cost_fpel(c, bmv.x - 1, bmv.y + 2), c2 = cost_fpel(c, bmv.x + 1, bmv.y + 2);
@@ -338,7 +459,7 @@ int orc_motion_estimate(const orc_me_job* j, int* outQMv)
             if (yok(c, bmv.y + k_hex2[dir + 1].y))
             {
                 bmv.x += k_hex2[dir + 1].x; bmv.y += k_hex2[dir + 1].y;
-                for (int i = (merange >> 1) - 1; i > 0 && in_range(c, bmv.x, bmv.y); i--)
+                for (int i = (hexRange >> 1) - 1; i > 0 && in_range(c, bmv.x, bmv.y); i--)
                 {
                     c0 = cost_fpel(c, bmv.x + k_hex2[dir + 0].x, bmv.y + k_hex2[dir + 0].y);
                     c1 = cost_fpel(c, bmv.x + k_hex2[dir + 1].x, bmv.y + k_hex2[dir + 1].y);

@@ -67,7 +67,7 @@ def _me_job(O, R, depth, rng, w, h, method, subme, lowres, smooth, merange, qp=3
 
 
 @pytest.mark.parametrize("depth", DEPTHS)
-@pytest.mark.parametrize("method", [0, 1, 3])
+@pytest.mark.parametrize("method", [0, 1, 2, 3])
 def test_motion_estimate(depth, method):
     R, O = libs(depth)
     rng = np.random.default_rng(7 + method)
@@ -81,6 +81,23 @@ def test_motion_estimate(depth, method):
                 assert r == o, (w, h, method, subme, smooth, r, o)
                 n += 1
     assert n > 100
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_motion_estimate_umh_wide(depth):
+    """X265_UMH_SEARCH (motion.cpp:946-1130) with the presets' search range: the adaptive range, the cross and the hexagon grid run
+    many more iterations than with the range of 16 test_motion_estimate uses."""
+    R, O = libs(depth)
+    rng = np.random.default_rng(909)
+    n = 0
+    for (w, h) in [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (32, 16), (16, 32), (64, 32), (32, 64), (24, 32), (16, 4), (4, 8), (12, 16), (64, 48), (8, 32)]:
+        for subme in (0, 3):
+            for smooth in (True, False):
+                for rep in range(2):
+                    r, o = _me_job(O, R, depth, rng, w, h, 2, subme, 0, smooth, 57)
+                    assert r == o, (w, h, subme, smooth, r, o)
+                    n += 1
+    assert n == 128
 
 
 @pytest.mark.parametrize("depth", DEPTHS)
